@@ -1,0 +1,199 @@
+// C ABI (include/fv3lm_b200.h): handle, metrics upload, module runner.
+#include "../../include/fv3lm_b200.h"
+#include "engine.h"
+#include "mosaic.h"
+#include "modules.h"
+#include <memory>
+
+using namespace fv3lm;
+
+struct fv3lm_handle {
+  fv3lm_config cfg;
+  Device dv;
+  Mosaic mo;
+  std::vector<double> ak, bk;
+  std::map<std::string, double*> metric_dev;
+  std::string err;
+};
+
+static thread_local std::string g_err;
+
+#define FV3LM_TRY try {
+#define FV3LM_CATCH(h)                                            \
+  }                                                               \
+  catch (const std::exception& e) {                               \
+    g_err = e.what();                                             \
+    if (h) (h)->err = e.what();                                   \
+    return 1;                                                     \
+  }                                                               \
+  return 0;
+
+// host [rows][NX] contiguous <-> device [rows][pitch]
+static void up2d(const Geom& g, double* d, const double* h, size_t rows) {
+#ifndef FV3LM_HOST_EMU
+  if (cudaMemcpy2DAsync(d, g.pitch * sizeof(double), h, g.NX * sizeof(double), g.NX * sizeof(double), rows,
+                        cudaMemcpyHostToDevice, dev::stream()) != cudaSuccess)
+    throw std::runtime_error("fv3lm: cudaMemcpy2D h2d failed");
+#else
+  for (size_t r = 0; r < rows; r++) memcpy(d + r * g.pitch, h + r * g.NX, g.NX * sizeof(double));
+#endif
+}
+static void down2d(const Geom& g, double* h, const double* d, size_t rows) {
+#ifndef FV3LM_HOST_EMU
+  if (cudaMemcpy2DAsync(h, g.NX * sizeof(double), d, g.pitch * sizeof(double), g.NX * sizeof(double), rows,
+                        cudaMemcpyDeviceToHost, dev::stream()) != cudaSuccess)
+    throw std::runtime_error("fv3lm: cudaMemcpy2D d2h failed");
+#else
+  for (size_t r = 0; r < rows; r++) memcpy(h + r * g.NX, d + r * g.pitch, g.NX * sizeof(double));
+#endif
+}
+
+extern "C" {
+
+int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv3lm_handle** out) {
+  fv3lm_handle* h = nullptr;
+  FV3LM_TRY
+  if (!cfg || !out) throw std::runtime_error("fv3lm_create: null argument");
+  if (cfg->ntiles != 6 || cfg->npx != cfg->npy || cfg->ng != 3) throw std::runtime_error("fv3lm_create: need 6 square tiles and ng = 3");
+  if (cfg->npz > 127) throw std::runtime_error("fv3lm_create: npz > 127 unsupported");
+#ifndef FV3LM_HOST_EMU
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw std::runtime_error("fv3lm_create: no CUDA device -- this library has no CPU fallback");
+#endif
+  h = new fv3lm_handle();
+  h->cfg = *cfg;
+  Geom& g = h->dv.g;
+  g.N = cfg->npx - 1; g.npx = cfg->npx; g.npy = cfg->npy; g.ng = cfg->ng;
+  g.is = 1; g.ie = g.N; g.js = 1; g.je = g.N;
+  g.NX = g.N + 2 * g.ng + 1; g.NY = g.NX;
+  g.pitch = (g.NX + 3) / 4 * 4;
+  g.ntile = 6; g.K = cfg->npz; g.slab = g.pitch * g.NY;
+  if (ak && bk) { h->ak.assign(ak, ak + cfg->npz + 1); h->bk.assign(bk, bk + cfg->npz + 1); }
+  memset(&h->dv.m, 0, sizeof(Metrics));
+  h->mo.build(g);
+  *out = h;
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_destroy(fv3lm_handle* h) {
+  if (!h) return 0;
+  FV3LM_TRY
+  dev::sync();
+  for (auto& kv : h->metric_dev) dev::free_(kv.second);
+  h->mo.destroy();
+  delete h;
+  h = nullptr;
+  FV3LM_CATCH(h)
+}
+
+const char* fv3lm_last_error(const fv3lm_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int fv3lm_set_metric(fv3lm_handle* h, const char* name, const double* host, int is_1d) {
+  FV3LM_TRY
+  const Geom& g = h->dv.g;
+  std::string nm(name);
+  double*& d = h->metric_dev[nm];
+  if (!d) { d = (double*)dev::alloc((size_t)g.ntile * g.slab * sizeof(double)); dev::zero(d, (size_t)g.ntile * g.slab * sizeof(double)); }
+  if (is_1d) {
+    for (int t = 0; t < g.ntile; t++) dev::h2d(d + (size_t)t * g.slab, host + (size_t)t * g.NX, g.NX * sizeof(double));
+  } else {
+    up2d(g, d, host, (size_t)g.ntile * g.NY);
+  }
+  dev::sync();
+  bool found = false;
+#define X(n) if (nm == #n) { h->dv.m.n = d; found = true; }
+  FV3LM_METRIC_LIST(X)
+#undef X
+  if (!found) throw std::runtime_error("fv3lm_set_metric: unknown metric " + nm);
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_set_metric_scalar(fv3lm_handle* h, const char* name, double value) {
+  FV3LM_TRY
+  std::string nm(name);
+  if (nm == "da_min") h->dv.m.da_min = value;
+  else if (nm == "da_min_c") h->dv.m.da_min_c = value;
+  else throw std::runtime_error("fv3lm_set_metric_scalar: unknown " + nm);
+  FV3LM_CATCH(h)
+}
+
+const char* fv3lm_module_list(void) { return module_list(); }
+
+int fv3lm_module_run(fv3lm_handle* h, const char* module, int mode, int nfields, const char* const* names,
+                     double* const* traj, double* const* pert, int nparams, const char* const* pnames,
+                     const double* pvals) {
+  FV3LM_TRY
+  const Geom& g = h->dv.g;
+  ModuleParams prm;
+  for (int n = 0; n < nparams; n++) prm.v[pnames[n]] = pvals[n];
+  prm.cfg = &h->cfg;
+  Program P; P.dv = &h->dv; P.name = module;
+  ModuleIO io;
+  build_module(module, P, h->mo, io, prm);
+  std::map<std::string, int> idx;
+  for (int n = 0; n < nfields; n++) idx[names[n]] = n;
+  // bind externals
+  std::vector<int> ext;
+  for (auto& kv : io.inputs) ext.push_back(kv.second);
+  for (auto& kv : io.outputs) if (!io.is_input(kv.second)) ext.push_back(kv.second);
+  auto host_of = [&](int id, bool want_pert) -> double* {
+    auto it = idx.find(P.vals[id].name);
+    if (it == idx.end()) return nullptr;
+    return want_pert ? pert[it->second] : traj[it->second];
+  };
+  for (auto& kv : io.inputs) {
+    int id = kv.second; Value& v = P.vals[id];
+    double* ht = host_of(id, false);
+    if (!ht) throw std::runtime_error(std::string("module ") + module + ": missing input field " + v.name);
+    v.traj = h->dv.pool.get(P.val_doubles(id));
+    up2d(g, v.traj, ht, (size_t)g.ntile * v.nk * g.NY);
+    v.active = (mode != MODE_NL) && host_of(id, true) != nullptr;
+  }
+  P.analyse();
+  for (int id : ext) {
+    Value& v = P.vals[id];
+    if (!v.traj) { v.traj = h->dv.pool.get(P.val_doubles(id)); dev::zero(v.traj, P.val_doubles(id) * sizeof(double)); }
+    if (v.active) {
+      v.pert = h->dv.pool.get(P.val_doubles(id));
+      dev::zero(v.pert, P.val_doubles(id) * sizeof(double));
+    }
+  }
+  if (mode == MODE_TL) {
+    for (auto& kv : io.inputs) { Value& v = P.vals[kv.second]; if (v.active) up2d(g, v.pert, host_of(kv.second, true), (size_t)g.ntile * v.nk * g.NY); }
+  } else if (mode == MODE_AD) {
+    for (auto& kv : io.outputs) {
+      Value& v = P.vals[kv.second];
+      double* hp = host_of(kv.second, true);
+      if (v.active && hp) up2d(g, v.pert, hp, (size_t)g.ntile * v.nk * g.NY);
+    }
+  }
+  P.run((Mode)mode);
+  // download
+  for (auto& kv : io.outputs) {
+    Value& v = P.vals[kv.second];
+    double* ht = host_of(kv.second, false);
+    if (ht) down2d(g, ht, v.traj, (size_t)g.ntile * v.nk * g.NY);
+    if (mode == MODE_TL) { double* hp = host_of(kv.second, true); if (hp && v.active) down2d(g, hp, v.pert, (size_t)g.ntile * v.nk * g.NY); }
+  }
+  if (mode == MODE_AD) {
+    for (auto& kv : io.inputs) {
+      Value& v = P.vals[kv.second];
+      double* hp = host_of(kv.second, true);
+      if (hp && v.active) down2d(g, hp, v.pert, (size_t)g.ntile * v.nk * g.NY);
+    }
+  }
+  dev::sync();
+  for (int id : ext) { Value& v = P.vals[id]; h->dv.pool.put(v.traj); h->dv.pool.put(v.pert); v.traj = v.pert = nullptr; }
+  FV3LM_CATCH(h)
+}
+
+long long fv3lm_launch_count(void) { return dev::launches; }
+double fv3lm_pool_peak_bytes(const fv3lm_handle* h) { return h ? (double)h->dv.pool.bytes_peak : 0.0; }
+int fv3lm_sync(fv3lm_handle* h) {
+  FV3LM_TRY
+  dev::sync();
+  FV3LM_CATCH(h)
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+// Device layer, buffer pool and the program executor (NL / TL / AD sweeps).
+#include "engine.h"
+#include <algorithm>
+
+namespace fv3lm {
+namespace dev {
+long long launches = 0;
+
+#ifndef FV3LM_HOST_EMU
+static cudaStream_t g_stream = nullptr;
+cudaStream_t stream() {
+  if (!g_stream) {
+    if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess)
+      throw std::runtime_error("fv3lm: cannot create a CUDA stream (no usable GPU; there is no CPU fallback)");
+  }
+  return g_stream;
+}
+static void ck(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string("fv3lm CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+void* alloc(size_t bytes) { void* p = nullptr; ck(cudaMalloc(&p, bytes), "cudaMalloc"); return p; }
+void free_(void* p) { if (p) cudaFree(p); }
+void h2d(void* d, const void* h, size_t b) { ck(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, stream()), "h2d"); }
+void d2h(void* h, const void* d, size_t b) { ck(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, stream()), "d2h"); ck(cudaStreamSynchronize(stream()), "d2h sync"); }
+void d2d(void* d, const void* s, size_t b) { ck(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, stream()), "d2d"); }
+void zero(void* d, size_t b) { ck(cudaMemsetAsync(d, 0, b, stream()), "memset"); }
+void sync() { ck(cudaStreamSynchronize(stream()), "sync"); }
+void check(const char* what) { ck(cudaGetLastError(), what); }
+#else
+void* alloc(size_t bytes) { void* p = malloc(bytes); if (!p) throw std::runtime_error("malloc"); return p; }
+void free_(void* p) { free(p); }
+void h2d(void* d, const void* h, size_t b) { memcpy(d, h, b); }
+void d2h(void* h, const void* d, size_t b) { memcpy(h, d, b); }
+void d2d(void* d, const void* s, size_t b) { memcpy(d, s, b); }
+void zero(void* d, size_t b) { memset(d, 0, b); }
+void sync() {}
+void check(const char*) {}
+#endif
+}  // namespace dev
+
+// ---------------------------------------------------------------------------------
+double* Pool::get(size_t n) {
+  size_t bytes = n * sizeof(double);
+  auto& fl = free_[bytes];
+  void* p;
+  if (!fl.empty()) { p = fl.back(); fl.pop_back(); }
+  else { p = dev::alloc(bytes); bytes_total += bytes; }
+  live_[p] = bytes;
+  bytes_live += bytes;
+  bytes_peak = std::max(bytes_peak, bytes_live);
+  return (double*)p;
+}
+void Pool::put(double* p) {
+  if (!p) return;
+  auto it = live_.find(p);
+  if (it == live_.end()) return;
+  free_[it->second].push_back(p);
+  bytes_live -= it->second;
+  live_.erase(it);
+}
+void Pool::trim() {
+  for (auto& kv : free_) { for (void* p : kv.second) { dev::free_(p); bytes_total -= kv.first; } kv.second.clear(); }
+}
+Pool::~Pool() {
+  trim();
+  for (auto& kv : live_) dev::free_(kv.first);
+}
+
+// ---------------------------------------------------------------------------------
+size_t Program::val_doubles(int id) const {
+  const Geom& g = dv->g;
+  return (size_t)g.ntile * vals[id].nk * g.slab;
+}
+
+void Program::analyse() {
+  // activity: propagate from active externals through the op list
+  for (auto& v : vals) if (!v.external) v.active = false;
+  for (auto& op : ops) {
+    bool any = false;
+    for (int i : op.in) any = any || vals[i].active;
+    if (!op.inplace) for (int o : op.out) vals[o].active = any;
+  }
+  for (auto& v : vals) { v.first_def = -1; v.last_use = -1; }
+  for (int n = 0; n < (int)ops.size(); n++) {
+    for (int i : ops[n].in) vals[i].last_use = n;
+    for (int o : ops[n].out) { if (vals[o].first_def < 0) vals[o].first_def = n; vals[o].last_use = std::max(vals[o].last_use, n); }
+  }
+}
+
+void Program::ensure_traj(int id) {
+  Value& v = vals[id];
+  if (!v.traj) {
+    if (v.external) throw std::runtime_error("external value without storage: " + v.name);
+    v.traj = dv->pool.get(val_doubles(id));
+    // intermediates are only defined on the range their producer writes; zero the
+    // rest so that nothing downstream can pick up NaNs from recycled memory
+    dev::zero(v.traj, val_doubles(id) * sizeof(double));
+  }
+}
+void Program::ensure_pert(int id, bool zero_it) {
+  Value& v = vals[id];
+  if (!v.active) return;
+  if (!v.pert) {
+    if (v.external) throw std::runtime_error("external active value without pert storage: " + v.name);
+    v.pert = dv->pool.get(val_doubles(id));
+    zero_it = true;
+  } else {
+    zero_it = false;
+  }
+  if (zero_it) dev::zero(v.pert, val_doubles(id) * sizeof(double));
+}
+void Program::release(int id) {
+  Value& v = vals[id];
+  if (v.external) return;
+  if (v.traj) { dv->pool.put(v.traj); v.traj = nullptr; }
+  if (v.pert) { dv->pool.put(v.pert); v.pert = nullptr; }
+}
+
+void Program::run(Mode mode) {
+  analyse();
+  const int nop = (int)ops.size();
+  if (mode == MODE_NL || mode == MODE_TL) {
+    for (int n = 0; n < nop; n++) {
+      Op& op = ops[n];
+      for (int o : op.out) { ensure_traj(o); if (mode == MODE_TL) ensure_pert(o, true); }
+      op.run(*this, op, mode);
+      // free values whose last use was this op
+      for (int i : op.in) if (vals[i].last_use == n) release(i);
+      for (int o : op.out) if (vals[o].last_use == n) release(o);
+    }
+  } else {
+    // forward sweep, keep everything ("device checkpoint arena")
+    for (int n = 0; n < nop; n++) {
+      Op& op = ops[n];
+      for (int o : op.out) ensure_traj(o);
+      op.run(*this, op, MODE_ADFWD);
+    }
+    // reverse sweep
+    for (int n = nop - 1; n >= 0; n--) {
+      Op& op = ops[n];
+      bool any_out = false;
+      for (int o : op.out) if (vals[o].active && vals[o].pert) any_out = true;
+      if (any_out || op.inplace) {
+        for (int o : op.out) ensure_pert(o, true);
+        for (int i : op.in) ensure_pert(i, true);
+        op.run(*this, op, MODE_AD);
+      }
+      if (!op.inplace)
+        for (int o : op.out) if (vals[o].first_def == n) release(o);
+    }
+    // inputs that nobody produced (non-external temporaries) are released
+    for (int id = 0; id < (int)vals.size(); id++)
+      if (!vals[id].external && vals[id].first_def < 0) release(id);
+  }
+  dev::check(name.c_str());
+}
+
+}  // namespace fv3lm

@@ -1,0 +1,324 @@
+// fv3lm engine: device-resident fields, stencil "stages", and static programs of
+// stages that can be executed in three modes:
+//   NL  nonlinear trajectory only
+//   TL  trajectory + tangent (dual numbers, value and perturbation in one sweep, the
+//       same structure as the reference's Tapenade tangent mode)
+//   AD  forward NL sweep that keeps every intermediate in HBM (the "device checkpoint
+//       arena" replacing utils/tapenade/adStack.c), then the reverse sweep in
+//       GATHER form: each thread owns one input cell and sums the contributions of
+//       every output cell that read it; no atomics, fixed summation order.
+//
+// A Stage is a struct with
+//     static constexpr int NI, NO;            number of input / output fields
+//     struct P {...};                          POD parameters
+//     static constexpr Tap taps[NT];           union of (input, di, dj, dk) it may read
+//     template<class X> static void eval(X&, const P&);
+// eval is written once against a context X (X::T = double or Dual).
+#pragma once
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "platform.h"
+#include "dual.h"
+
+namespace fv3lm {
+
+// ---------------------------------------------------------------------------------
+// geometry of the device arrays
+// ---------------------------------------------------------------------------------
+struct Geom {
+  int N, npx, npy, ng;  // cells per tile edge; npx = npy = N + 1; halo width (3)
+  int is, ie, js, je;   // compute domain of this sub-domain in tile-global indices
+  int NX, NY, pitch;    // logical extents N + 2 ng + 1 and the row pitch (doubles)
+  int ntile;            // cube tiles resident on this device
+  int K;                // npz
+  int slab;             // pitch * NY
+};
+
+// 2-D metric arrays, each [ntile][NY][pitch]; sin_sg/cos_sg 1..4 (+5 for sin) split out.
+// Definitions: SURVEY appendix D  (model/fv_grid_utils_nlm.F90, tools/fv_grid_tools_nlm.F90)
+#define FV3LM_METRIC_LIST(X)                                                              \
+  X(area) X(rarea) X(area_c) X(rarea_c) X(dx) X(dy) X(rdx) X(rdy) X(dxa) X(dya) X(rdxa)   \
+  X(rdya) X(dxc) X(dyc) X(rdxc) X(rdyc) X(cosa) X(sina) X(rsina) X(cosa_u) X(sina_u)      \
+  X(rsin_u) X(cosa_v) X(sina_v) X(rsin_v) X(cosa_s) X(rsin2) X(sin_sg1) X(sin_sg2)        \
+  X(sin_sg3) X(sin_sg4) X(cos_sg1) X(cos_sg2) X(cos_sg3) X(cos_sg4) X(divg_u) X(divg_v)   \
+  X(del6_u) X(del6_v) X(f0) X(fC) X(agrid_lon) X(agrid_lat) X(grid_lon) X(grid_lat)       \
+  X(edge_w) X(edge_e) X(edge_s) X(edge_n) X(edge_vect_w) X(edge_vect_e) X(edge_vect_s)    \
+  X(edge_vect_n)
+// (the edge_* arrays are 1-D, stored in row 0 of a slab so they share the layout)
+
+struct Metrics {
+#define X(n) const double* n;
+  FV3LM_METRIC_LIST(X)
+#undef X
+  double da_min, da_min_c;
+};
+
+struct Tap { int f, di, dj, dk; };
+
+template <int N> struct FArr {
+  double* p[N > 0 ? N : 1];
+  int nk[N > 0 ? N : 1];
+};
+
+// ---------------------------------------------------------------------------------
+// contexts
+// ---------------------------------------------------------------------------------
+struct CtxBase {
+  Geom g; Metrics m;
+  int ii, jj, kk, tile;   // array column/row, level, tile
+  int i, j;               // Fortran tile-global indices
+  DEV void setpos(int ii_, int jj_, int kk_, int tile_) {
+    ii = ii_; jj = jj_; kk = kk_; tile = tile_; i = ii_ - (g.ng - 1); j = jj_ - (g.ng - 1);
+  }
+  // metric at relative offset
+  DEV double M(const double* a, int di = 0, int dj = 0) const {
+    return a[(size_t)tile * g.slab + (size_t)(jj + dj) * g.pitch + (ii + di)];
+  }
+  // metric at absolute Fortran index
+  DEV double Mabs(const double* a, int ai, int aj) const {
+    return a[(size_t)tile * g.slab + (size_t)(aj + g.ng - 1) * g.pitch + (ai + g.ng - 1)];
+  }
+  // 1-D edge array, Fortran index
+  DEV double M1(const double* a, int ai) const { return a[(size_t)tile * g.slab + (ai + g.ng - 1)]; }
+  DEV bool in_rect(int i0, int i1, int j0, int j1) const { return i >= i0 && i <= i1 && j >= j0 && j <= j1; }
+  DEV size_t off(int nkf, int di, int dj, int dk) const {
+    int k = kk + dk;
+    if (k > nkf - 1) k = nkf - 1;
+    if (k < 0) k = 0;
+    return ((size_t)tile * nkf + k) * g.slab + (size_t)(jj + dj) * g.pitch + (ii + di);
+  }
+};
+
+template <class S> struct CtxNL : CtxBase {
+  using T = double;
+  static constexpr int mode = 0;
+  FArr<S::NI> in_; FArr<S::NO> out_;
+  DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const { return in_.p[f][off(in_.nk[f], di, dj, dk)]; }
+  DEV void out(int o, T v) const { out_.p[o][off(out_.nk[o], 0, 0, 0)] = v; }
+};
+
+template <class S> struct CtxTL : CtxBase {
+  using T = Dual;
+  static constexpr int mode = 1;
+  FArr<S::NI> in_, ind_; FArr<S::NO> out_, outd_;
+  DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const {
+    size_t o = off(in_.nk[f], di, dj, dk);
+    return Dual(in_.p[f][o], ind_.p[f] ? ind_.p[f][o] : 0.0);
+  }
+  DEV void out(int o, T v) const {
+    size_t q = off(out_.nk[o], 0, 0, 0);
+    out_.p[o][q] = v.v;
+    if (outd_.p[o]) outd_.p[o][q] = v.d;
+  }
+};
+
+template <class S> struct CtxAD : CtxBase {
+  using T = Dual;
+  static constexpr int mode = 2;
+  FArr<S::NI> in_; FArr<S::NO> outad_;
+  int sf, sdi, sdj, sdk;  // the seeded tap
+  double acc;
+  DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const {
+    return Dual(in_.p[f][off(in_.nk[f], di, dj, dk)], (f == sf && di == sdi && dj == sdj && dk == sdk) ? 1.0 : 0.0);
+  }
+  DEV void out(int o, T v) {
+    if (outad_.p[o]) acc += v.d * outad_.p[o][off(outad_.nk[o], 0, 0, 0)];
+  }
+};
+
+// ---------------------------------------------------------------------------------
+// kernel functors (called for every (ii, jj, z = tile * nk + k) of the padded arrays)
+// ---------------------------------------------------------------------------------
+template <class S> struct KernNL {
+  typename S::P p; Geom g; Metrics m; FArr<S::NI> in; FArr<S::NO> out; int nk;
+  DEV void operator()(int ii, int jj, int z) const {
+    CtxNL<S> x; x.g = g; x.m = m; x.in_ = in; x.out_ = out;
+    x.setpos(ii, jj, z % nk, z / nk);
+    S::eval(x, p);
+  }
+};
+template <class S> struct KernTL {
+  typename S::P p; Geom g; Metrics m; FArr<S::NI> in, ind; FArr<S::NO> out, outd; int nk;
+  DEV void operator()(int ii, int jj, int z) const {
+    CtxTL<S> x; x.g = g; x.m = m; x.in_ = in; x.ind_ = ind; x.out_ = out; x.outd_ = outd;
+    x.setpos(ii, jj, z % nk, z / nk);
+    S::eval(x, p);
+  }
+};
+
+template <class S, int n> struct AdTaps {
+  template <class K> DEV static void run(const K& kn, int ii, int jj, int kk, int tile, double* acc) {
+    if constexpr (n < S::NT) {
+      constexpr Tap t = S::taps[n];
+      int oi = ii - t.di, oj = jj - t.dj, ok = kk - t.dk;
+      if (oi >= 0 && oi < kn.g.NX && oj >= 0 && oj < kn.g.NY && ok >= 0 && ok < kn.nk_fwd) {
+        CtxAD<S> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in; x.outad_ = kn.outad;
+        x.sf = t.f; x.sdi = t.di; x.sdj = t.dj; x.sdk = t.dk; x.acc = 0.0;
+        x.setpos(oi, oj, ok, tile);
+        S::eval(x, kn.p);
+        acc[t.f] += x.acc;
+      }
+      AdTaps<S, n + 1>::run(kn, ii, jj, kk, tile, acc);
+    }
+  }
+};
+
+template <class S> struct KernAD {
+  typename S::P p; Geom g; Metrics m; FArr<S::NI> in, inad; FArr<S::NO> outad; int nk, nk_fwd;
+  DEV void operator()(int ii, int jj, int z) const {
+    double acc[S::NI];
+#pragma unroll
+    for (int f = 0; f < S::NI; f++) acc[f] = 0.0;
+    int kk = z % nk, tile = z / nk;
+    AdTaps<S, 0>::run(*this, ii, jj, kk, tile, acc);
+#pragma unroll
+    for (int f = 0; f < S::NI; f++) {
+      if (inad.p[f] && kk < inad.nk[f]) {
+        size_t o = ((size_t)tile * inad.nk[f] + kk) * g.slab + (size_t)jj * g.pitch + ii;
+        inad.p[f][o] += acc[f];
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------
+// device layer
+// ---------------------------------------------------------------------------------
+namespace dev {
+void* alloc(size_t bytes);
+void free_(void* p);
+void h2d(void* d, const void* h, size_t bytes);
+void d2h(void* h, const void* d, size_t bytes);
+void d2d(void* d, const void* s, size_t bytes);
+void zero(void* d, size_t bytes);
+void sync();
+void check(const char* what);
+extern long long launches;   // number of kernels launched (bench.py gpu_launches)
+#ifndef FV3LM_HOST_EMU
+cudaStream_t stream();
+#endif
+}  // namespace dev
+
+#ifndef FV3LM_HOST_EMU
+template <class F> GLOBAL void kern3d(F f, int nx, int ny) {
+  int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  int jj = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ii < nx && jj < ny) f(ii, jj, (int)blockIdx.z);
+}
+template <class F> void launch3d(const F& f, int nx, int ny, int nz) {
+  if (nz <= 0) return;
+  dim3 b(32, 8, 1), gr((nx + 31) / 32, (ny + 7) / 8, nz);
+  kern3d<F><<<gr, b, 0, dev::stream()>>>(f, nx, ny);
+  dev::launches++;
+}
+#else
+template <class F> void launch3d(const F& f, int nx, int ny, int nz) {
+  for (int z = 0; z < nz; z++)
+    for (int jj = 0; jj < ny; jj++)
+      for (int ii = 0; ii < nx; ii++) f(ii, jj, z);
+  dev::launches++;
+}
+#endif
+
+// ---------------------------------------------------------------------------------
+// programs
+// ---------------------------------------------------------------------------------
+enum Mode { MODE_NL = 0, MODE_TL = 1, MODE_AD = 2, MODE_ADFWD = 3 };
+
+struct Pool {
+  std::map<size_t, std::vector<void*>> free_;
+  std::map<void*, size_t> live_;
+  size_t bytes_total = 0, bytes_peak = 0, bytes_live = 0;
+  double* get(size_t n_doubles);
+  void put(double* p);
+  void trim();
+  ~Pool();
+};
+
+struct Value {
+  std::string name;
+  int nk = 1;
+  bool active = false;     // carries a perturbation / adjoint
+  bool external = false;   // owned by the caller of the program (never pooled)
+  double* traj = nullptr;
+  double* pert = nullptr;  // TL tangent, or AD adjoint
+  int first_def = -1, last_use = -1;
+};
+
+struct Device;  // per-handle state (geometry, metrics, pool)
+
+struct Op {
+  std::string name;
+  std::vector<int> in, out;
+  bool inplace = false;    // patch op: out == in, mutates cells that were dead
+  int nk_launch = 1;
+  std::function<void(struct Program&, Op&, int /*Mode or 3 = AD reverse*/)> run;
+};
+
+struct Program {
+  Device* dv = nullptr;
+  std::vector<Value> vals;
+  std::vector<Op> ops;
+  std::string name;
+
+  int val(const std::string& nm, int nk, bool external = false) {
+    Value v; v.name = nm; v.nk = nk; v.external = external;
+    vals.push_back(v);
+    return (int)vals.size() - 1;
+  }
+  size_t val_doubles(int id) const;
+  void analyse();                    // activity + liveness
+  void run(Mode mode);               // NL, TL, or AD (forward store-all + reverse)
+  void ensure_traj(int id);
+  void ensure_pert(int id, bool zero_it);
+  void release(int id);
+  template <class S>
+  void add(const char* nm, const typename S::P& prm, std::vector<int> ins, std::vector<int> outs, int nk_launch);
+};
+
+struct Device {
+  Geom g;
+  Metrics m;
+  std::vector<double*> metric_bufs;
+  Pool pool;
+  std::string err;
+};
+
+template <class S>
+void Program::add(const char* nm, const typename S::P& prm, std::vector<int> ins, std::vector<int> outs, int nk_launch) {
+  if ((int)ins.size() != S::NI || (int)outs.size() != S::NO) throw std::runtime_error(std::string("arity mismatch in ") + nm);
+  Op op; op.name = nm; op.in = ins; op.out = outs; op.nk_launch = nk_launch;
+  typename S::P p = prm;
+  op.run = [p](Program& P, Op& o, int mode) {
+    const Geom& g = P.dv->g;
+    if (mode == MODE_NL || mode == MODE_TL || mode == MODE_ADFWD) {
+      FArr<S::NI> in, ind; FArr<S::NO> out, outd;
+      for (int f = 0; f < S::NI; f++) { Value& v = P.vals[o.in[f]]; in.p[f] = v.traj; in.nk[f] = v.nk; ind.p[f] = v.active ? v.pert : nullptr; ind.nk[f] = v.nk; }
+      for (int f = 0; f < S::NO; f++) { Value& v = P.vals[o.out[f]]; out.p[f] = v.traj; out.nk[f] = v.nk; outd.p[f] = v.active ? v.pert : nullptr; outd.nk[f] = v.nk; }
+      if (mode != MODE_TL) {
+        KernNL<S> k{p, g, P.dv->m, in, out, o.nk_launch};
+        launch3d(k, g.NX, g.NY, g.ntile * o.nk_launch);
+      } else {
+        KernTL<S> k{p, g, P.dv->m, in, ind, out, outd, o.nk_launch};
+        launch3d(k, g.NX, g.NY, g.ntile * o.nk_launch);
+      }
+    } else {  // AD reverse
+      FArr<S::NI> in, inad; FArr<S::NO> outad;
+      int nk = o.nk_launch; bool any = false;
+      for (int f = 0; f < S::NI; f++) { Value& v = P.vals[o.in[f]]; in.p[f] = v.traj; in.nk[f] = v.nk; inad.p[f] = v.active ? v.pert : nullptr; inad.nk[f] = v.nk; if (v.active) { any = true; if (v.nk > nk) nk = v.nk; } }
+      for (int f = 0; f < S::NO; f++) { Value& v = P.vals[o.out[f]]; outad.p[f] = v.active ? v.pert : nullptr; outad.nk[f] = v.nk; }
+      if (!any) return;
+      KernAD<S> k{p, g, P.dv->m, in, inad, outad, nk, o.nk_launch};
+      launch3d(k, g.NX, g.NY, g.ntile * nk);
+    }
+  };
+  ops.push_back(op);
+}
+
+}  // namespace fv3lm

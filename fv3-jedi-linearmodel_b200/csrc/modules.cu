@@ -1,0 +1,83 @@
+#include "modules.h"
+#include "stages_tp.h"
+
+namespace fv3lm {
+
+static LevOrd lev_ord(int K, int ord, int n_sponge, int ord_sponge) {
+  LevOrd o;
+  for (int k = 0; k < 128; k++) o.v[k] = (signed char)((k < n_sponge) ? ord_sponge : ord);
+  (void)K;
+  return o;
+}
+
+// ---------------------------------------------------------------------------------
+// fv_tp_2d   (model_tlmadm/tp_core_tlm.F90:2123-2324)
+// ---------------------------------------------------------------------------------
+TpOut build_fv_tp_2d(Program& P, Mosaic& mo, int q, int crx, int cry, int xfx, int yfx, int ra_x, int ra_y,
+                     int mfx, int mfy, const LevOrd& hord, int nk, const std::string& tag) {
+  const Geom& g = P.dv->g;
+  const int is = g.is, ie = g.ie, js = g.js, je = g.je, ng = g.ng;
+  const int isd = is - ng, ied = ie + ng, jsd = js - ng, jed = je + ng;
+  auto nm = [&](const char* s) { return tag + "." + s; };
+  int fy2 = P.val(nm("fy2"), nk), q_i = P.val(nm("q_i"), nk), fxo = P.val(nm("fx_ou"), nk);
+  int fx2 = P.val(nm("fx2"), nk), q_j = P.val(nm("q_j"), nk), fyo = P.val(nm("fy_ou"), nk);
+  int fx = P.val(nm("fx"), nk), fy = P.val(nm("fy"), nk);
+  add_patch(P, "copy_corners_y", &mo.cc2, {q});
+  P.add<S_ppm<1>>("yppm_in", {isd, ied, js, je + 1, hord}, {q, cry}, {fy2}, nk);
+  P.add<S_inner<1>>("q_i", {isd, ied, js, je}, {q, fy2, yfx, ra_y}, {q_i}, nk);
+  P.add<S_ppm<0>>("xppm_ou", {is, ie + 1, js, je, hord}, {q_i, crx}, {fxo}, nk);
+  add_patch(P, "copy_corners_x", &mo.cc1, {q});
+  P.add<S_ppm<0>>("xppm_in", {is, ie + 1, jsd, jed, hord}, {q, crx}, {fx2}, nk);
+  P.add<S_inner<0>>("q_j", {is, ie, jsd, jed}, {q, fx2, xfx, ra_x}, {q_j}, nk);
+  P.add<S_ppm<1>>("yppm_ou", {is, ie, js, je + 1, hord}, {q_j, cry}, {fyo}, nk);
+  P.add<S_favg>("fx_avg", {is, ie + 1, js, je}, {fxo, fx2, mfx >= 0 ? mfx : xfx}, {fx}, nk);
+  P.add<S_favg>("fy_avg", {is, ie, js, je + 1}, {fyo, fy2, mfy >= 0 ? mfy : yfx}, {fy}, nk);
+  return {fx, fy};
+}
+
+static void mod_fv_tp_2d(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
+  const int K = P.dv->g.K;
+  int q = io.in(P, "q", K), crx = io.in(P, "crx", K), cry = io.in(P, "cry", K), xfx = io.in(P, "xfx", K),
+      yfx = io.in(P, "yfx", K), ra_x = io.in(P, "ra_x", K), ra_y = io.in(P, "ra_y", K);
+  int mfx = -1, mfy = -1;
+  if (prm.geti("use_mf", 0)) { mfx = io.in(P, "mfx", K); mfy = io.in(P, "mfy", K); }
+  LevOrd ho = lev_ord(K, prm.geti("hord", 2), prm.geti("n_sponge", 0), 1);
+  TpOut o = build_fv_tp_2d(P, mo, q, crx, cry, xfx, yfx, ra_x, ra_y, mfx, mfy, ho, K, "tp");
+  io.out(P, "fx", o.fx); io.out(P, "fy", o.fy);
+  io.out(P, "q", q);   // corner ghost cells are rewritten in place
+}
+
+// halo exchanges and corner fills on their own (mosaic.cu)
+static void mod_halo(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
+  const int K = P.dv->g.K;
+  int q = io.in(P, "q", K), qc = io.in(P, "qc", K), u = io.in(P, "u", K), v = io.in(P, "v", K), uc = io.in(P, "uc", K), vc = io.in(P, "vc", K);
+  add_patch(P, "halo_center", &mo.h_center, {q});
+  add_patch(P, "halo_corner", &mo.h_corner, {qc});
+  add_patch(P, "halo_dgrid", &mo.h_dgrid, {u, v});
+  add_patch(P, "halo_cgrid", &mo.h_cgrid, {uc, vc});
+  if (prm.geti("corners", 1)) {
+    add_patch(P, "fill_corners_bgrid_x", &mo.fcb_x, {qc});
+    add_patch(P, "fill_corners_dgrid", &mo.fc_dgrid_vec, {vc, uc});
+    add_patch(P, "fill_4corners_x", &mo.f4c1, {q});
+  }
+  io.out(P, "q", q); io.out(P, "qc", qc); io.out(P, "u", u); io.out(P, "v", v); io.out(P, "uc", uc); io.out(P, "vc", vc);
+}
+
+struct ModEntry { const char* name; void (*fn)(Program&, Mosaic&, ModuleIO&, const ModuleParams&); const char* doc; };
+static const ModEntry g_mods[] = {
+    {"fv_tp_2d", mod_fv_tp_2d, "in: q crx cry xfx yfx ra_x ra_y [mfx mfy]; out: fx fy q; params: hord n_sponge use_mf"},
+    {"halo", mod_halo, "in/out: q qc u v uc vc; params: corners"},
+};
+
+void build_module(const std::string& name, Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
+  for (const ModEntry& e : g_mods)
+    if (name == e.name) { e.fn(P, mo, io, prm); return; }
+  throw std::runtime_error("unknown module " + name);
+}
+const char* module_list() {
+  static std::string s;
+  if (s.empty()) for (const ModEntry& e : g_mods) s += std::string(e.name) + ": " + e.doc + "\n";
+  return s.c_str();
+}
+
+}  // namespace fv3lm

@@ -1,0 +1,50 @@
+// Cubed-sphere mosaic: halo-exchange and corner ghost-cell fills as precomputed index
+// maps ("patch" operators).  Replaces FMS mpp_update_domains / mpp_get_boundary and
+// their adjoints (tools/fv_mp_nlm_mod.F90:285-591 contact table, :966-1471 corner
+// fills; model_tlmadm/fv_mp_adm.F90:488-725 adjoint halo = accumulate then zero).
+//
+// forward :  F[dcomp][dst] = sign * F[scomp][src]            (dst cells were dead)
+// adjoint :  ad[scomp][src] += sum_dst sign * ad[dcomp][dst]  (CSR gather, fixed order)
+//            ad[dcomp][dst]  = 0
+#pragma once
+#include <vector>
+#include "engine.h"
+
+namespace fv3lm {
+
+struct PatchEntry { int dtile, dpos, dcomp, stile, spos, scomp; double sign; };
+
+struct PatchMap {
+  std::string name;
+  int n = 0;           // forward entries
+  int nsrc = 0;        // distinct sources (adjoint rows)
+  bool restore = false;  // corner-type patch: save & restore overwritten trajectory cells
+  // device arrays
+  int *d_dtile = nullptr, *d_dpos = nullptr, *d_dcomp = nullptr, *d_stile = nullptr, *d_spos = nullptr, *d_scomp = nullptr;
+  double* d_sign = nullptr;
+  int *a_stile = nullptr, *a_spos = nullptr, *a_scomp = nullptr, *a_row = nullptr;  // CSR rows -> forward entry ids
+  int* a_ent = nullptr;
+  std::vector<PatchEntry> host;
+  void upload();
+  void destroy();
+};
+
+// staggering codes (x = i - 1 + ox, y = j - 1 + oy)
+enum Stag { ST_CENTER = 0, ST_CORNER = 1, ST_YSTAG = 2 /* D-grid u, C-grid vc */, ST_XSTAG = 3 /* D-grid v, C-grid uc */ };
+
+struct Mosaic {
+  Geom g;
+  // halo exchanges
+  PatchMap h_center, h_corner, h_dgrid, h_cgrid;
+  // corner fills
+  PatchMap cc1, cc2;        // copy_corners(dir)        model/tp_core_nlm.F90:214
+  PatchMap f4c1, f4c2;      // fill_4corners(dir)       model/sw_core_nlm.F90:3102
+  PatchMap fcb_x, fcb_y;    // fill_corners BGRID X/Y   tools/fv_mp_nlm_mod.F90:1046
+  PatchMap fc_dgrid_vec;    // fill_corners(vc,uc,VECTOR,DGRID) :1271
+  void build(const Geom& g);
+  void destroy();
+};
+
+void add_patch(Program& P, const char* nm, PatchMap* map, std::vector<int> fields);
+
+}  // namespace fv3lm

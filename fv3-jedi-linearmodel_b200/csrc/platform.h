@@ -1,0 +1,16 @@
+// Build-mode switch.  The product library (libfv3lm_b200.so) is compiled by nvcc for
+// sm_100a and runs every kernel on the GPU.  A second, TEST-ONLY build of the same
+// stage functors (FV3LM_HOST_EMU, plain g++) lets the CPU test-suite check stage
+// arithmetic without a GPU; it is a different .so that the product never loads.
+#pragma once
+#include <stddef.h>
+#ifdef FV3LM_HOST_EMU
+#define HD inline
+#define DEV inline
+#define GLOBAL
+#else
+#include <cuda_runtime.h>
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+#define GLOBAL __global__
+#endif

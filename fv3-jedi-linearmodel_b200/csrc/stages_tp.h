@@ -1,0 +1,113 @@
+// tp_core: 1-D PPM fluxes and the Lin-Rood 2-D flux-form transport operator fv_tp_2d.
+// Reference: model_tlmadm/tp_core_tlm.F90  FV_TP_2D_TLM :2123, XPPM_TLM :2328, YPPM_TLM :2496,
+// COPY_CORNERS_TLM :2843 (primal model/tp_core_nlm.F90:78-289, 291-420).  Only the linear
+// orders the TL/AD implement are provided: iord = 1 (upwind) and 2 (unlimited PPM)
+// (tp_core_tlm.F90:2431-2466).
+#pragma once
+#include "engine.h"
+#include "mosaic.h"
+
+namespace fv3lm {
+
+struct LevOrd { signed char v[128]; };   // per-level scheme order (sponge layers differ)
+
+namespace tp {
+constexpr double p1 = 7.0 / 12.0, p2 = -1.0 / 12.0;
+constexpr double c1 = -2.0 / 14.0, c2 = 11.0 / 14.0, c3 = 5.0 / 14.0;
+
+// q at offset d along direction DIR (0 = x, 1 = y) of input f
+template <int DIR, class X> DEV typename X::T Q(const X& x, int f, int d) {
+  return DIR == 0 ? x.in(f, d, 0) : x.in(f, 0, d);
+}
+template <int DIR, class X> DEV double DA(const X& x, int d) {   // dxa / dya
+  return DIR == 0 ? x.M(x.m.dxa, d, 0) : x.M(x.m.dya, 0, d);
+}
+
+// PPM edge value al at index (pos + d), pos = current i (DIR 0) or j (DIR 1).
+// tp_core_tlm.F90:2396-2430 (x) and the symmetric y code.
+template <int DIR, class X> DEV typename X::T edge_al(const X& x, int f, int d) {
+  using T = typename X::T;
+  const int ia = (DIR == 0 ? x.i : x.j) + d;
+  const int np = DIR == 0 ? x.g.npx : x.g.npy;
+  if (ia == 0 || ia == np - 1) return c1 * Q<DIR>(x, f, d - 2) + c2 * Q<DIR>(x, f, d - 1) + c3 * Q<DIR>(x, f, d);
+  if (ia == 2 || ia == np + 1) return c3 * Q<DIR>(x, f, d - 1) + c2 * Q<DIR>(x, f, d) + c1 * Q<DIR>(x, f, d + 1);
+  if (ia == 1 || ia == np) {
+    double a0 = DA<DIR>(x, d - 1), am = DA<DIR>(x, d - 2), a1 = DA<DIR>(x, d), a2 = DA<DIR>(x, d + 1);
+    T l = ((2.0 * a0 + am) * Q<DIR>(x, f, d - 1) - a0 * Q<DIR>(x, f, d - 2)) / (am + a0);
+    T r = ((2.0 * a1 + a2) * Q<DIR>(x, f, d) - a1 * Q<DIR>(x, f, d + 1)) / (a1 + a2);
+    return 0.5 * (l + r);
+  }
+  return p1 * (Q<DIR>(x, f, d - 1) + Q<DIR>(x, f, d)) + p2 * (Q<DIR>(x, f, d - 2) + Q<DIR>(x, f, d + 1));
+}
+
+// 1-D flux at the current face from q (input fq) and Courant number c
+template <int DIR, class X> DEV typename X::T ppm_flux(const X& x, int fq, typename X::T c, int ord) {
+  using T = typename X::T;
+  if (ord == 1) return val(c) > 0.0 ? Q<DIR>(x, fq, -1) : Q<DIR>(x, fq, 0);
+  T al0 = edge_al<DIR>(x, fq, 0);
+  if (val(c) > 0.0) {
+    T qt = Q<DIR>(x, fq, -1);
+    T alm = edge_al<DIR>(x, fq, -1);
+    return qt + (1.0 - c) * (al0 - qt - c * (alm + al0 - (qt + qt)));
+  } else {
+    T qt = Q<DIR>(x, fq, 0);
+    T alp = edge_al<DIR>(x, fq, 1);
+    return qt + (1.0 + c) * (al0 - qt + c * (al0 + alp - (qt + qt)));
+  }
+}
+}  // namespace tp
+
+// flux(i,j) = xppm / yppm (q, c) on a rectangle.  in: 0 = q, 1 = c ; out: 0 = flux
+template <int DIR> struct S_ppm {
+  static constexpr int NI = 2, NO = 1;
+  struct P { int i0, i1, j0, j1; LevOrd ord; };
+  static constexpr int NT = 7;
+  static constexpr Tap taps[NT] = {
+      {0, DIR == 0 ? -3 : 0, DIR == 0 ? 0 : -3, 0}, {0, DIR == 0 ? -2 : 0, DIR == 0 ? 0 : -2, 0},
+      {0, DIR == 0 ? -1 : 0, DIR == 0 ? 0 : -1, 0}, {0, 0, 0, 0},
+      {0, DIR == 0 ? 1 : 0, DIR == 0 ? 0 : 1, 0},   {0, DIR == 0 ? 2 : 0, DIR == 0 ? 0 : 2, 0},
+      {1, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
+    x.out(0, tp::ppm_flux<DIR>(x, 0, x.in(1), p.ord.v[x.kk]));
+  }
+};
+
+// inner update  q_i = (q*area + fyy(j) - fyy(j+1)) / ra_y ,  fyy = yfx * fy2   (DIR = 1)
+//               q_j = (q*area + fx1(i) - fx1(i+1)) / ra_x ,  fx1 = xfx * fx2   (DIR = 0)
+// in: 0 = q, 1 = inner flux (fy2/fx2), 2 = yfx/xfx, 3 = ra ; out: 0 = q_i/q_j
+template <int DIR> struct S_inner {
+  static constexpr int NI = 4, NO = 1;
+  struct P { int i0, i1, j0, j1; };
+  static constexpr int NT = 6;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {1, DIR == 0, DIR == 1, 0},
+                                   {2, 0, 0, 0}, {2, DIR == 0, DIR == 1, 0}, {3, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
+    using T = typename X::T;
+    constexpr int di = DIR == 0, dj = DIR == 1;
+    T f0 = x.in(2) * x.in(1), f1 = x.in(2, di, dj) * x.in(1, di, dj);
+    x.out(0, (x.in(0) * x.M(x.m.area) + f0 - f1) / x.in(3));
+  }
+};
+
+// flux averaging  f = 0.5*(f_outer + f_inner) * m   (tp_core_tlm.F90:2268-2313)
+// in: 0 = outer flux, 1 = inner flux, 2 = multiplier (xfx/yfx or mfx/mfy) ; out: 0
+struct S_favg {
+  static constexpr int NI = 3, NO = 1;
+  struct P { int i0, i1, j0, j1; };
+  static constexpr int NT = 3;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
+    x.out(0, 0.5 * (x.in(0) + x.in(1)) * x.in(2));
+  }
+};
+
+// Builder: appends fv_tp_2d to a program.  q is patched in place (copy_corners).
+// mfx/mfy < 0 selects the "delp / vorticity" form (multiplier = xfx/yfx).
+struct TpOut { int fx, fy; };
+TpOut build_fv_tp_2d(Program& P, Mosaic& mo, int q, int crx, int cry, int xfx, int yfx, int ra_x, int ra_y,
+                     int mfx, int mfy, const LevOrd& hord, int nk, const std::string& tag);
+
+}  // namespace fv3lm

@@ -1,0 +1,148 @@
+"""ctypes binding of the C ABI in include/fv3lm_b200.h (used by tests/ and bench.py; a
+Fortran host binds the same symbols through ISO_C_BINDING).
+
+There is no CPU fallback: `load()` opens libfv3lm_b200.so (nvcc, sm_100a) and every
+compute entry point fails loudly without a GPU.  `load(emu=True)` opens the TEST-ONLY
+host emulation build of the same stage functors (tests marked "not gpu" use it to check
+stage arithmetic against the oracle); nothing in the product path ever asks for it.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+MODE_NL, MODE_TL, MODE_AD = 0, 1, 2
+
+
+class Config(C.Structure):
+    _fields_ = [("npx", C.c_int), ("npy", C.c_int), ("npz", C.c_int), ("ng", C.c_int), ("ntiles", C.c_int),
+                ("hydrostatic", C.c_int), ("n_split", C.c_int), ("k_split", C.c_int), ("nq", C.c_int),
+                ("hord_mt", C.c_int), ("hord_vt", C.c_int), ("hord_tm", C.c_int), ("hord_dp", C.c_int),
+                ("hord_tr", C.c_int), ("n_sponge", C.c_int), ("nord", C.c_int),
+                ("dt", C.c_double), ("ptop", C.c_double),
+                ("dddmp", C.c_double), ("d2_bg", C.c_double), ("d4_bg", C.c_double), ("vtdm4", C.c_double),
+                ("d2_bg_k1", C.c_double), ("d2_bg_k2", C.c_double), ("d_ext", C.c_double), ("beta", C.c_double),
+                ("zvir", C.c_double), ("kappa", C.c_double), ("cp", C.c_double), ("rdgas", C.c_double),
+                ("grav", C.c_double), ("do_vort_damp", C.c_int), ("reserved", C.c_int * 16)]
+
+
+EXPORTS = ["fv3lm_create", "fv3lm_destroy", "fv3lm_last_error", "fv3lm_set_metric", "fv3lm_set_metric_scalar",
+           "fv3lm_module_run", "fv3lm_module_list", "fv3lm_launch_count", "fv3lm_pool_peak_bytes", "fv3lm_sync"]
+
+METRICS_2D = ["area", "rarea", "area_c", "rarea_c", "dx", "dy", "rdx", "rdy", "dxa", "dya", "rdxa", "rdya", "dxc",
+              "dyc", "rdxc", "rdyc", "cosa", "sina", "rsina", "cosa_u", "sina_u", "rsin_u", "cosa_v", "sina_v",
+              "rsin_v", "cosa_s", "rsin2", "divg_u", "divg_v", "del6_u", "del6_v", "f0", "fC"]
+METRICS_1D = ["edge_w", "edge_e", "edge_s", "edge_n", "edge_vect_w", "edge_vect_e", "edge_vect_s", "edge_vect_n"]
+
+
+def lib_path(emu=False):
+    return os.path.join(_HERE, "libfv3lm_hostemu.so" if emu else "libfv3lm_b200.so")
+
+
+def load(emu=False):
+    path = lib_path(emu)
+    if not os.path.exists(path):
+        raise RuntimeError("%s is missing: run __graft_entry__.build() (there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    lib.fv3lm_last_error.restype = C.c_char_p
+    lib.fv3lm_module_list.restype = C.c_char_p
+    lib.fv3lm_launch_count.restype = C.c_longlong
+    lib.fv3lm_pool_peak_bytes.restype = C.c_double
+    return lib
+
+
+def default_config(N, npz, **kw):
+    """defaults follow SURVEY 8(d): linear schemes, split_* = false"""
+    rdgas = 8314.47 / 28.965
+    cfg = Config()
+    cfg.npx = cfg.npy = N + 1
+    cfg.npz = npz; cfg.ng = 3; cfg.ntiles = 6
+    cfg.hydrostatic = 1; cfg.n_split = 1; cfg.k_split = 1; cfg.nq = 4
+    cfg.hord_mt = cfg.hord_vt = cfg.hord_tm = cfg.hord_dp = cfg.hord_tr = 2
+    cfg.n_sponge = 0; cfg.nord = 1
+    cfg.dt = 900.0; cfg.ptop = 1.0
+    cfg.dddmp = 0.2; cfg.d2_bg = 0.015; cfg.d4_bg = 0.15; cfg.vtdm4 = 0.0005
+    cfg.d2_bg_k1 = 4.0; cfg.d2_bg_k2 = 2.0; cfg.d_ext = 0.02; cfg.beta = 0.0
+    cfg.rdgas = rdgas; cfg.cp = 3.5 * rdgas; cfg.kappa = rdgas / (3.5 * rdgas)
+    cfg.zvir = (8314.47 / 18.015) / rdgas - 1.0; cfg.grav = 9.80665
+    cfg.do_vort_damp = 1
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+class FV3LM:
+    """One handle = one GPU's share of the cubed sphere (whole sphere for a single GPU)."""
+
+    def __init__(self, cfg, ak=None, bk=None, emu=False):
+        self.lib = load(emu)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        akp = bkp = None
+        if ak is not None:
+            self._ak = np.ascontiguousarray(ak, dtype=np.float64); self._bk = np.ascontiguousarray(bk, dtype=np.float64)
+            akp = self._ak.ctypes.data_as(C.POINTER(C.c_double)); bkp = self._bk.ctypes.data_as(C.POINTER(C.c_double))
+        rc = self.lib.fv3lm_create(C.byref(cfg), akp, bkp, C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError("fv3lm_create failed: %s" % self.lib.fv3lm_last_error(None).decode())
+        self.N = cfg.npx - 1
+        self.NX = self.N + 2 * cfg.ng + 1
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed: %s" % (what, self.lib.fv3lm_last_error(self.h).decode()))
+
+    def set_metrics(self, M):
+        """M: dict from oracle.grid.build_metrics (or the host model's gridstruct)"""
+        dp = C.POINTER(C.c_double)
+        def up(name, arr, is1d):
+            a = np.ascontiguousarray(arr, dtype=np.float64)
+            self._check(self.lib.fv3lm_set_metric(self.h, name.encode(), a.ctypes.data_as(dp), int(is1d)), "set_metric " + name)
+        for n in METRICS_2D:
+            up(n, M[n], False)
+        for k in (1, 2, 3, 4):
+            up("sin_sg%d" % k, M["sin_sg"][..., k], False)
+            up("cos_sg%d" % k, M["cos_sg"][..., k], False)
+        up("agrid_lon", M["agrid"][..., 0], False); up("agrid_lat", M["agrid"][..., 1], False)
+        up("grid_lon", M["grid"][..., 0], False); up("grid_lat", M["grid"][..., 1], False)
+        for n in METRICS_1D:
+            up(n, M[n], True)
+        for n in ("da_min", "da_min_c"):
+            self._check(self.lib.fv3lm_set_metric_scalar(self.h, n.encode(), C.c_double(M[n])), "set_metric_scalar")
+
+    def module_run(self, module, mode, traj, pert=None, params=None):
+        """traj / pert: dict name -> float64 ndarray [6, nk, NY, NX] (modified in place)."""
+        pert = pert or {}
+        params = params or {}
+        names = list(traj.keys())
+        for n in pert:
+            if n not in traj:
+                raise KeyError("pert field %s has no traj array" % n)
+        dp = C.POINTER(C.c_double)
+        n = len(names)
+        for k in names:
+            a = traj[k]
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], k
+        c_names = (C.c_char_p * n)(*[s.encode() for s in names])
+        c_traj = (dp * n)(*[traj[k].ctypes.data_as(dp) for k in names])
+        c_pert = (dp * n)(*[(pert[k].ctypes.data_as(dp) if k in pert else C.cast(None, dp)) for k in names])
+        pn = list(params.keys())
+        c_pn = (C.c_char_p * max(1, len(pn)))(*[s.encode() for s in pn]) if pn else (C.c_char_p * 1)()
+        c_pv = (C.c_double * max(1, len(pn)))(*[float(params[k]) for k in pn]) if pn else (C.c_double * 1)()
+        rc = self.lib.fv3lm_module_run(self.h, module.encode(), int(mode), n, c_names, c_traj, c_pert, len(pn), c_pn, c_pv)
+        self._check(rc, "module_run(%s)" % module)
+
+    def launch_count(self):
+        return int(self.lib.fv3lm_launch_count())
+
+    def close(self):
+        if self.h:
+            self.lib.fv3lm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

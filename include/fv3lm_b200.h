@@ -1,0 +1,76 @@
+/* fv3lm_b200 -- C ABI of the B200-native FV3 tangent-linear / adjoint dynamics.
+ *
+ * This is the boundary a Fortran ISO_C_BINDING shim (see INTEGRATION.md and
+ * fv3-jedi-linearmodel_b200/fortran/) binds in place of the reference's
+ *   src/dynamics/fv3jedi_lm_dynamics_mod.F90   create :69, step_nl :268, step_tl :347,
+ *                                              step_ad :460, delete :237
+ * All functions return 0 on success, non-zero on error (message via fv3lm_last_error);
+ * the reference aborts instead (src/fv3jedi_lm_mod.F90:91-94), the shim turns a non-zero
+ * status into the same abort.  No C++ or torch types cross this boundary; the caller
+ * owns every host array, the library owns all device memory.
+ *
+ * Host array layout for "halo'd" fields (module-level entry points): C order
+ * [6 tiles][nk][NY][NX], NX = NY = N + 2*ng + 1, Fortran tile index (i,j) at
+ * [j + ng - 1][i + ng - 1]  (one array shape serves A-, C-, D-grid and corner fields,
+ * exactly like the reference's isd:ied+1 / jsd:jed+1 allocations,
+ * model/fv_arrays_nlm.F90:999-1139).
+ */
+#ifndef FV3LM_B200_H
+#define FV3LM_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fv3lm_handle fv3lm_handle;
+
+/* flat POD mirror of the run-time switches the path needs:
+ * fv_flags_type (model/fv_arrays_nlm.F90:236-506), fv_flags_pert_type
+ * (model_tlmadm/fv_arrays_tlmadm.F90:37-92) and fv3jedi_lm_conf (utils/fv3jedi_lm_utils_mod.F90:14-32) */
+typedef struct fv3lm_config {
+  int npx, npy, npz;      /* corner counts per tile edge (N+1) and number of layers            */
+  int ng;                 /* halo width, 3 (tools/fv_mp_nlm_mod.F90:63)                        */
+  int ntiles;             /* 6                                                                 */
+  int hydrostatic;        /* 1 = hydrostatic                                                   */
+  int n_split, k_split;   /* acoustic / remap sub-cycling                                      */
+  int nq;                 /* number of tracers (4: qv ql qi o3)                                */
+  int hord_mt, hord_vt, hord_tm, hord_dp, hord_tr;   /* must be 1 or 2 (linear schemes)       */
+  int n_sponge;           /* layers using first-order (hord_*_ks = 1) transport                */
+  int nord;               /* divergence damping order                                          */
+  double dt;              /* model time step [s]                                               */
+  double ptop;
+  double dddmp, d2_bg, d4_bg, vtdm4, d2_bg_k1, d2_bg_k2, d_ext, beta;
+  double zvir, kappa, cp, rdgas, grav;   /* physical constants (both constant sets, SURVEY G) */
+  int do_vort_damp;
+  int reserved[16];
+} fv3lm_config;
+
+int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv3lm_handle** out);
+int fv3lm_destroy(fv3lm_handle* h);
+const char* fv3lm_last_error(const fv3lm_handle* h);
+
+/* grid metrics (gridstruct members, model/fv_arrays_nlm.F90:115-234). 2-D arrays are
+ * [6][NY][NX]; the 1-D edge_* factors are [6][NX]; sin_sg/cos_sg are passed per index
+ * as "sin_sg1".."sin_sg4", "cos_sg1".."cos_sg4". */
+int fv3lm_set_metric(fv3lm_handle* h, const char* name, const double* host, int is_1d);
+int fv3lm_set_metric_scalar(fv3lm_handle* h, const char* name, double value);   /* da_min, da_min_c */
+
+/* Kernel-family entry points used by the parity tests: run one family ("module") of the
+ * hot path in mode 0 = NL, 1 = TL, 2 = AD on host arrays.
+ *   traj[f] : in/out trajectory array of field names[f]
+ *   pert[f] : TL: perturbation in (inputs) / out (outputs);
+ *             AD: adjoint in (outputs) / out (inputs).  NULL = field not active.
+ * Modules and their field names are listed by fv3lm_module_list(). */
+int fv3lm_module_run(fv3lm_handle* h, const char* module, int mode, int nfields, const char* const* names,
+                     double* const* traj, double* const* pert, int nparams, const char* const* pnames,
+                     const double* pvals);
+const char* fv3lm_module_list(void);
+
+/* counters for bench.py */
+long long fv3lm_launch_count(void);
+double fv3lm_pool_peak_bytes(const fv3lm_handle* h);
+int fv3lm_sync(fv3lm_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
