@@ -63,9 +63,12 @@ static void mod_halo(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& p
   io.out(P, "q", q); io.out(P, "qc", qc); io.out(P, "u", u); io.out(P, "v", v); io.out(P, "uc", uc); io.out(P, "vc", vc);
 }
 
+void mod_c_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
+
 struct ModEntry { const char* name; void (*fn)(Program&, Mosaic&, ModuleIO&, const ModuleParams&); const char* doc; };
 static const ModEntry g_mods[] = {
     {"fv_tp_2d", mod_fv_tp_2d, "in: q crx cry xfx yfx ra_x ra_y [mfx mfy]; out: fx fy q; params: hord n_sponge use_mf"},
+    {"c_sw", mod_c_sw, "in: delp pt u v w; out: delpc ptc wc uc vc ua va ut vt divg_d; params: dt2 hydrostatic nord"},
     {"halo", mod_halo, "in/out: q qc u v uc vc; params: corners"},
 };
 

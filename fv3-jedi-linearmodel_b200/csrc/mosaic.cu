@@ -171,10 +171,29 @@ void Mosaic::build(const Geom& g_) {
     }
     build_local(fc_dgrid_vec, g, a); fc_dgrid_vec.name = "fill_corners_dgrid_vec";
   }
-  for (PatchMap* p : {&h_center, &h_corner, &h_dgrid, &h_cgrid, &cc1, &cc2, &f4c1, &f4c2, &fcb_x, &fcb_y, &fc_dgrid_vec}) p->upload();
+  // d2a2c_vect: corner values of the A-grid winds are taken from the other component of the
+  // neighbouring face (dst comp 0 <- src comp 1), model/sw_core_nlm.F90:2884-2925, :2986-3030
+  {
+    const int je = g.je, ie = g.ie;
+    std::vector<CF> ut, ua, vt, va;
+    for (int i = -2; i <= 0; i++) { ut.push_back({i, 0, 0, 0, 1 - i, 1, -1.0}); ut.push_back({i, npy, 0, 0, je + i, 1, 1.0}); }
+    for (int i = 0; i <= 2; i++) { ut.push_back({npx + i, 0, 0, npx, i + 1, 1, 1.0}); ut.push_back({npx + i, npy, 0, npx, je - i, 1, -1.0}); }
+    ua = {{-1, 0, 0, 0, 2, 1, -1.0}, {0, 0, 0, 0, 1, 1, -1.0}, {npx, 0, 0, npx, 1, 1, 1.0}, {npx + 1, 0, 0, npx, 2, 1, 1.0},
+          {npx, npy, 0, npx, npy - 1, 1, -1.0}, {npx + 1, npy, 0, npx, npy - 2, 1, -1.0}, {-1, npy, 0, 0, npy - 2, 1, 1.0}, {0, npy, 0, 0, npy - 1, 1, 1.0}};
+    for (int j = -2; j <= 0; j++) { vt.push_back({0, j, 0, 1 - j, 0, 1, -1.0}); vt.push_back({npx, j, 0, ie + j, 0, 1, 1.0}); }
+    for (int j = 0; j <= 2; j++) { vt.push_back({0, npy + j, 0, j + 1, npy, 1, 1.0}); vt.push_back({npx, npy + j, 0, ie - j, npy, 1, -1.0}); }
+    va = {{0, -1, 0, 2, 0, 1, -1.0}, {0, 0, 0, 1, 0, 1, -1.0}, {npx, 0, 0, npx - 1, 0, 1, 1.0}, {npx, -1, 0, npx - 2, 0, 1, 1.0},
+          {npx, npy, 0, npx - 1, npy, 1, -1.0}, {npx, npy + 1, 0, npx - 2, npy, 1, -1.0}, {0, npy, 0, 1, npy, 1, 1.0}, {0, npy + 1, 0, 2, npy, 1, 1.0}};
+    build_local(c_utmp, g, ut); build_local(c_ua, g, ua); build_local(c_vtmp, g, vt); build_local(c_va, g, va);
+    c_utmp.name = "d2a2c_utmp_corners"; c_ua.name = "d2a2c_ua_corners"; c_vtmp.name = "d2a2c_vtmp_corners"; c_va.name = "d2a2c_va_corners";
+  }
+  for (PatchMap* p : all()) p->upload();
+}
+std::vector<PatchMap*> Mosaic::all() {
+  return {&h_center, &h_corner, &h_dgrid, &h_cgrid, &cc1, &cc2, &f4c1, &f4c2, &fcb_x, &fcb_y, &fc_dgrid_vec, &c_utmp, &c_ua, &c_vtmp, &c_va};
 }
 void Mosaic::destroy() {
-  for (PatchMap* p : {&h_center, &h_corner, &h_dgrid, &h_cgrid, &cc1, &cc2, &f4c1, &f4c2, &fcb_x, &fcb_y, &fc_dgrid_vec}) p->destroy();
+  for (PatchMap* p : all()) p->destroy();
 }
 
 // ---------------------------------------------------------------------------------

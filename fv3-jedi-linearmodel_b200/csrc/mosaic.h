@@ -41,6 +41,9 @@ struct Mosaic {
   PatchMap f4c1, f4c2;      // fill_4corners(dir)       model/sw_core_nlm.F90:3102
   PatchMap fcb_x, fcb_y;    // fill_corners BGRID X/Y   tools/fv_mp_nlm_mod.F90:1046
   PatchMap fc_dgrid_vec;    // fill_corners(vc,uc,VECTOR,DGRID) :1271
+  // d2a2c_vect corner exchanges between the x and y components (model/sw_core_nlm.F90:2884-2925, :2986-3030)
+  PatchMap c_utmp, c_ua, c_vtmp, c_va;   // fields {dst, src}
+  std::vector<PatchMap*> all();
   void build(const Geom& g);
   void destroy();
 };

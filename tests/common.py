@@ -47,3 +47,72 @@ def relerr(a, b):
 
 def region(a, i0, i1, j0, j1):
     return a[..., R(j0, j1), R(i0, i1)]
+
+
+def check_module(h, module, N, K, inputs, active, outs, oracle_fn, params, rng, tol=1e-12, dot_tol=1e-13,
+                 pert_scale=1e-2, tol_tl=None, tol_ad=None):
+    """Generic parity check of one kernel family through the C ABI against the oracle.
+    inputs : dict name -> ndarray (all inputs of the module, in module order)
+    active : names of the inputs that carry perturbations / adjoints
+    outs   : dict name -> (i0, i1, j0, j1) valid Fortran index range of each output
+    oracle_fn(*active tensors) -> tuple of output tensors (same order as outs)
+    Checks NL, TL (jvp), AD (vjp) and the dot-product identity."""
+    import fv3lm
+    tol_tl = tol_tl or tol
+    tol_ad = tol_ad or tol
+    names = list(inputs.keys())
+    onames = list(outs.keys())
+    tin = [torch.from_numpy(inputs[n].copy()) for n in active]
+    zero = lambda: np.zeros_like(inputs[names[0]])
+    def newtraj():
+        t = {n: inputs[n].copy() for n in names}
+        for o in onames:
+            if o not in t:
+                t[o] = zero()
+        return t
+    res = {}
+    # NL
+    traj = newtraj()
+    h.module_run(module, fv3lm.MODE_NL, traj, params=params)
+    ref = oracle_fn(*tin)
+    for o, r in zip(onames, ref):
+        e = relerr(region(traj[o], *outs[o]), region(r.detach().numpy(), *outs[o]))
+        res["nl." + o] = e
+        assert e < tol, ("NL", o, e)
+    # TL
+    dp = {n: rnd(rng, N, K)[:, :inputs[n].shape[1]] * (np.abs(inputs[n]).mean() * pert_scale + 1e-30) for n in active}
+    traj = newtraj()
+    pert = {n: dp[n].copy() for n in active}
+    for o in onames:
+        if o not in pert:
+            pert[o] = zero()
+    h.module_run(module, fv3lm.MODE_TL, traj, pert, params=params)
+    _, dref = torch.func.jvp(oracle_fn, tuple(tin), tuple(torch.from_numpy(dp[n]) for n in active))
+    tl = {}
+    for o, r in zip(onames, dref):
+        e = relerr(region(pert[o], *outs[o]), region(r.numpy(), *outs[o]))
+        res["tl." + o] = e
+        assert e < tol_tl, ("TL", o, e)
+        tl[o] = pert[o].copy()
+    # AD
+    yb = {}
+    for o in onames:
+        y = zero()
+        region(y, *outs[o])[...] = region(rnd(rng, N, K), *outs[o])
+        yb[o] = y
+    traj = newtraj()
+    pert = {n: np.zeros_like(inputs[n]) for n in active}
+    for o in onames:
+        pert[o] = yb[o].copy() if o not in active else pert[o]
+    h.module_run(module, fv3lm.MODE_AD, traj, pert, params=params)
+    _, vjp = torch.func.vjp(oracle_fn, *tin)
+    aref = vjp(tuple(torch.from_numpy(yb[o]) for o in onames))
+    for n, a in zip(active, aref):
+        e = relerr(pert[n], a.numpy())
+        res["ad." + n] = e
+        assert e < tol_ad, ("AD", n, e)
+    lhs = sum((region(tl[o], *outs[o]) * region(yb[o], *outs[o])).sum() for o in onames)
+    rhs = sum((dp[n] * pert[n]).sum() for n in active)
+    res["dot"] = abs(lhs - rhs) / max(abs(lhs), abs(rhs), 1e-300)
+    assert res["dot"] <= dot_tol, ("dot", lhs, rhs)
+    return res
