@@ -1,0 +1,171 @@
+// d_sw program builder (model/sw_core_nlm.F90:492-1545) and the shared del-n flux builder.
+#include "stages_dsw.h"
+#include "modules.h"
+
+namespace fv3lm {
+
+static int maxord(const LevOrd& o, int nk) { int m = -1; for (int k = 0; k < nk; k++) m = std::max(m, (int)o.v[k]); return m; }
+
+// del-n damping fluxes of q (deln_flux / del6_vt_flux).  nord(k) < 0 switches a level off.
+// returns {fx2, fy2}
+static std::pair<int, int> build_deln(Program& P, Mosaic& mo, int q, const LevOrd& nord, const LevD& damp, int nk, const std::string& tag) {
+  auto nm = [&](const std::string& s) { return tag + "." + s; };
+  const int nmax = maxord(nord, nk);
+  int d2 = P.val(nm("d2_0"), nk);
+  P.add<S_del_d2>("del_d2", {nord, damp}, {q}, {d2}, nk);
+  if (nmax > 0) add_patch(P, "del_cc1", &mo.cc1, {d2});
+  int fx2 = P.val(nm("fx2_0"), nk), fy2 = P.val(nm("fy2_0"), nk);
+  P.add<S_del_flux<0>>("del_fx", {nord, 0}, {d2, d2}, {fx2}, nk);
+  if (nmax > 0) add_patch(P, "del_cc2", &mo.cc2, {d2});
+  P.add<S_del_flux<1>>("del_fy", {nord, 0}, {d2, d2}, {fy2}, nk);
+  for (int it = 1; it <= nmax; it++) {
+    int d2n = P.val(nm("d2_" + std::to_string(it)), nk);
+    P.add<S_del_div>("del_div", {nord, it}, {fx2, fy2}, {d2n}, nk);
+    add_patch(P, "del_cc1", &mo.cc1, {d2n});
+    int fxn = P.val(nm("fx2_" + std::to_string(it)), nk), fyn = P.val(nm("fy2_" + std::to_string(it)), nk);
+    P.add<S_del_flux<0>>("del_fx", {nord, it}, {d2n, fx2}, {fxn}, nk);
+    add_patch(P, "del_cc2", &mo.cc2, {d2n});
+    P.add<S_del_flux<1>>("del_fy", {nord, it}, {d2n, fy2}, {fyn}, nk);
+    fx2 = fxn; fy2 = fyn;
+  }
+  return {fx2, fy2};
+}
+
+// fv_tp_2d followed by the optional deln_flux (tp_core_nlm.F90:168-208)
+static TpOut build_tp_damped(Program& P, Mosaic& mo, int q, int crx, int cry, int xfx, int yfx, int ra_x, int ra_y, int mfx, int mfy,
+                             int mass, const LevOrd& hord, const LevOrd& nord, const LevD& damp_c, int nk, const std::string& tag) {
+  TpOut o = build_fv_tp_2d(P, mo, q, crx, cry, xfx, yfx, ra_x, ra_y, mfx, mfy, hord, nk, tag);
+  const double da_min = P.dv->m.da_min;
+  LevOrd n2; LevD dmp; bool any = false;
+  for (int k = 0; k < 128; k++) n2.v[k] = -1;
+  for (int k = 0; k < 96; k++) dmp.v[k] = 0.0;
+  for (int k = 0; k < nk; k++)
+    if (damp_c.v[k] > 1.e-4) { n2.v[k] = nord.v[k]; dmp.v[k] = pow(damp_c.v[k] * da_min, (double)(nord.v[k] + 1)); any = true; }
+  if (!any) return o;
+  const bool use_mass = mass >= 0;
+  LevD one; for (int k = 0; k < 96; k++) one.v[k] = 1.0;
+  auto f2 = build_deln(P, mo, q, n2, use_mass ? one : dmp, nk, tag + ".deln");
+  const Geom& g = P.dv->g; (void)g;
+  int fx = P.val(tag + ".fxd", nk), fy = P.val(tag + ".fyd", nk);
+  int m = use_mass ? mass : q;
+  P.add<S_del_add<0>>("deln_add_x", {n2, dmp, use_mass ? 1 : 0}, {o.fx, f2.first, m}, {fx}, nk);
+  P.add<S_del_add<1>>("deln_add_y", {n2, dmp, use_mass ? 1 : 0}, {o.fy, f2.second, m}, {fy}, nk);
+  return {fx, fy};
+}
+
+DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w, int uc, int vc, int ua, int va, int divg_d,
+                  const DswParams& prm, int nk, const std::string& tag) {
+  auto nm = [&](const char* s) { return tag + "." + s; };
+  const double da_min_c = P.dv->m.da_min_c;
+  DswOut o;
+  // contravariant winds, Courant numbers, flux areas
+  int ut0 = P.val(nm("ut0"), nk), vt0 = P.val(nm("vt0"), nk), ut = P.val(nm("ut"), nk), vt = P.val(nm("vt"), nk);
+  P.add<S_dwind1>("dwind1", {prm.dt}, {uc, vc}, {ut0, vt0}, nk);
+  P.add<S_dwind2>("dwind2", {0}, {ut0, vt0, uc, vc}, {ut, vt}, nk);
+  o.crx = P.val(nm("crx"), nk); o.xfx = P.val(nm("xfx"), nk); o.cry = P.val(nm("cry"), nk); o.yfx = P.val(nm("yfx"), nk);
+  P.add<S_dcourant>("dcourant", {prm.dt}, {ut, vt}, {o.crx, o.xfx, o.cry, o.yfx}, nk);
+  int ra_x = P.val(nm("ra_x"), nk), ra_y = P.val(nm("ra_y"), nk);
+  P.add<S_ra>("ra", {0}, {o.xfx, o.yfx}, {ra_x, ra_y}, nk);
+  // mass
+  TpOut fdp = build_tp_damped(P, mo, delp, o.crx, o.cry, o.xfx, o.yfx, ra_x, ra_y, -1, -1, -1, prm.hord_dp, prm.nord_v, prm.damp_v, nk, tag + ".tp_dp");
+  o.fx = fdp.fx; o.fy = fdp.fy;
+  // w
+  const int nh = prm.hydrostatic ? 0 : 1;
+  int gxw = P.val(nm("gxw"), nk), gyw = gxw, fx2w = gxw, fy2w = gxw;
+  LevD dw_on; for (int k = 0; k < 96; k++) dw_on.v[k] = 0.0;
+  if (nh) {
+    LevOrd nw; LevD d4;
+    for (int k = 0; k < 128; k++) nw.v[k] = -1;
+    for (int k = 0; k < 96; k++) d4.v[k] = 0.0;
+    bool any = false;
+    for (int k = 0; k < nk; k++)
+      if (prm.damp_w.v[k] > 1.e-5) { nw.v[k] = prm.nord_w.v[k]; d4.v[k] = pow(prm.damp_w.v[k] * da_min_c, (double)(prm.nord_w.v[k] + 1)); dw_on.v[k] = 1.0; any = true; }
+    if (any) { auto f = build_deln(P, mo, w, nw, d4, nk, tag + ".del6w"); fx2w = f.first; fy2w = f.second; }
+    TpOut fw = build_fv_tp_2d(P, mo, w, o.crx, o.cry, o.xfx, o.yfx, ra_x, ra_y, o.fx, o.fy, prm.hord_vt, nk, tag + ".tp_w");
+    gxw = fw.fx; gyw = fw.fy;
+  }
+  // pt
+  TpOut fpt = build_tp_damped(P, mo, pt, o.crx, o.cry, o.xfx, o.yfx, ra_x, ra_y, o.fx, o.fy, delp, prm.hord_tm, prm.nord_t, prm.damp_t, nk, tag + ".tp_pt");
+  o.delp = P.val(nm("delp"), nk); o.pt = P.val(nm("pt"), nk); o.w = P.val(nm("w"), nk);
+  P.add<S_dupd>("dupd", {nh, dw_on}, {delp, pt, w, o.fx, o.fy, fpt.fx, fpt.fy, gxw, gyw, fx2w, fy2w}, {o.delp, o.pt, o.w}, nk);
+  // kinetic energy
+  int vb = P.val(nm("vb"), nk), ub = P.val(nm("ub"), nk), ubf = P.val(nm("ubf"), nk), vbf = P.val(nm("vbf"), nk), ke = P.val(nm("ke"), nk);
+  P.add<S_dvbub>("dvbub", {prm.dt}, {ut, vt, uc, vc}, {vb, ub}, nk);
+  P.add<S_tpuv<1>>("ytp_v", {prm.hord_mt}, {vb, v}, {ubf}, nk);
+  P.add<S_tpuv<0>>("xtp_u", {prm.hord_mt}, {ub, u}, {vbf}, nk);
+  P.add<S_dke>("dke", {prm.dt}, {vb, ubf, ub, vbf, ut, vt, u, v}, {ke}, nk);
+  // relative vorticity
+  int wk = P.val(nm("wk"), nk);
+  P.add<S_relvort>("relvort", {0}, {u, v}, {wk}, nk);
+  // divergence damping
+  int delpc0 = P.val(nm("delpc0"), nk), vq = P.val(nm("vq0"), nk), dd = divg_d;
+  bool any0 = false; int nmax = 0;
+  for (int k = 0; k < nk; k++) { if (prm.nord.v[k] == 0) any0 = true; nmax = std::max(nmax, (int)prm.nord.v[k]); }
+  if (any0) P.add<S_ddiv0>("ddiv0", {prm.nord}, {u, v, ua, va, uc, vc}, {delpc0}, nk);
+  if (nmax > 0) {
+    for (int it = 1; it <= nmax; it++) {
+      const bool fill_c = (nmax - it) != 0;
+      int vcw = P.val(nm("dd_vc"), nk), ucw = P.val(nm("dd_uc"), nk), ddn = P.val(nm("dd"), nk);
+      if (fill_c) add_patch(P, "fill_corners_bx", &mo.fcb_x, {dd});
+      P.add<S_dd_grad<0>>("dd_vc", {prm.nord, it}, {dd}, {vcw}, nk);
+      if (fill_c) add_patch(P, "fill_corners_by", &mo.fcb_y, {dd});
+      P.add<S_dd_grad<1>>("dd_uc", {prm.nord, it}, {dd}, {ucw}, nk);
+      if (fill_c) add_patch(P, "fill_corners_dvec", &mo.fc_dgrid_vec, {vcw, ucw});
+      P.add<S_dd_div>("dd_div", {prm.nord, it}, {ucw, vcw, dd}, {ddn}, nk);
+      dd = ddn;
+    }
+    if (prm.dddmp >= 1.e-5) vq = build_a2b_ord4(P, mo, wk, nk, tag + ".a2b");
+  }
+  int vd = P.val(nm("vd"), nk);
+  P.add<S_ddamp>("ddamp", {prm.nord, prm.d2_bg, prm.dddmp, prm.d4_bg, prm.dt}, {delpc0, divg_d, vq, dd}, {vd}, nk);
+  // vorticity transport
+  int avort = P.val(nm("avort"), nk);
+  P.add<S_absvort>("absvort", {0}, {wk}, {avort}, nk);
+  TpOut fv = build_fv_tp_2d(P, mo, avort, o.crx, o.cry, o.xfx, o.yfx, ra_x, ra_y, -1, -1, prm.hord_vt, nk, tag + ".tp_vort");
+  // vorticity damping
+  int ut3 = wk, vt3 = wk;
+  LevD vd_on; for (int k = 0; k < 96; k++) vd_on.v[k] = 0.0;
+  {
+    LevOrd nv; LevD d4; bool any = false;
+    for (int k = 0; k < 128; k++) nv.v[k] = -1;
+    for (int k = 0; k < 96; k++) d4.v[k] = 0.0;
+    for (int k = 0; k < nk; k++)
+      if (prm.damp_v.v[k] > 1.e-5) { nv.v[k] = prm.nord_v.v[k]; d4.v[k] = pow(prm.damp_v.v[k] * da_min_c, (double)(prm.nord_v.v[k] + 1)); vd_on.v[k] = 1.0; any = true; }
+    if (any) { auto f = build_deln(P, mo, wk, nv, d4, nk, tag + ".del6v"); ut3 = f.first; vt3 = f.second; }
+  }
+  o.u = P.val(nm("u"), nk); o.v = P.val(nm("v"), nk);
+  P.add<S_duv>("duv", {vd_on}, {u, v, ke, vd, fv.fx, fv.fy, ut3, vt3}, {o.u, o.v}, nk);
+  return o;
+}
+
+void fill_dsw_params(DswParams& d, const ModuleParams& prm, int K) {
+  auto LO = [&](const char* base, int dflt) {
+    LevOrd o; int v = prm.geti(base, dflt);
+    for (int k = 0; k < 128; k++) o.v[k] = (signed char)v;
+    for (int k = 0; k < K; k++) { std::string key = std::string(base) + "@" + std::to_string(k); if (prm.v.count(key)) o.v[k] = (signed char)prm.geti(key, v); }
+    return o;
+  };
+  auto LD = [&](const char* base, double dflt) {
+    LevD o; double v = prm.get(base, dflt);
+    for (int k = 0; k < 96; k++) o.v[k] = v;
+    for (int k = 0; k < K; k++) { std::string key = std::string(base) + "@" + std::to_string(k); if (prm.v.count(key)) o.v[k] = prm.get(key, v); }
+    return o;
+  };
+  d.hord_mt = LO("hord_mt", 2); d.hord_vt = LO("hord_vt", 2); d.hord_tm = LO("hord_tm", 2); d.hord_dp = LO("hord_dp", 2);
+  d.nord = LO("nord", 1); d.nord_v = LO("nord_v", 1); d.nord_w = LO("nord_w", 1); d.nord_t = LO("nord_t", 1);
+  d.d2_bg = LD("d2_bg", 0.015); d.damp_v = LD("damp_v", 0.0005); d.damp_w = LD("damp_w", 0.0005); d.damp_t = LD("damp_t", 0.0005);
+  d.dddmp = prm.get("dddmp", 0.2); d.d4_bg = prm.get("d4_bg", 0.15); d.dt = prm.get("dt", 450.0);
+  d.hydrostatic = prm.geti("hydrostatic", 1) != 0;
+}
+
+void mod_d_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
+  const int K = P.dv->g.K;
+  int delp = io.in(P, "delp", K), pt = io.in(P, "pt", K), u = io.in(P, "u", K), v = io.in(P, "v", K), w = io.in(P, "w", K);
+  int uc = io.in(P, "uc", K), vc = io.in(P, "vc", K), ua = io.in(P, "ua", K), va = io.in(P, "va", K), divg_d = io.in(P, "divg_d", K);
+  DswParams d; fill_dsw_params(d, prm, K);
+  DswOut o = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, ua, va, divg_d, d, K, "dsw");
+  io.out(P, "delp_n", o.delp); io.out(P, "pt_n", o.pt); io.out(P, "u_n", o.u); io.out(P, "v_n", o.v); io.out(P, "w_n", o.w);
+  io.out(P, "fx", o.fx); io.out(P, "fy", o.fy); io.out(P, "crx", o.crx); io.out(P, "cry", o.cry); io.out(P, "xfx", o.xfx); io.out(P, "yfx", o.yfx);
+}
+
+}  // namespace fv3lm

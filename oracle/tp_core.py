@@ -141,3 +141,91 @@ def fv_tp_2d(q, crx, cry, hord, xfx, yfx, g, ra_x, ra_y, mfx=None, mfy=None):
     r = (..., R(js, je + 1), R(is_, ie))
     fyo[r] = 0.5 * (fy[r] + fy2[r]) * my[r]
     return fxo, fyo, q
+
+
+def deln_flux(nord, damp, q, fx, fy, g, mass=None):
+    """model/tp_core_nlm.F90:1015-1163 (del-n damping flux added to fx, fy).  nord: python
+    int (0..2); damp: float.  q is the transported field AFTER fv_tp_2d (corner state
+    irrelevant: copy_corners is re-applied on d2)."""
+    is_, ie, js, je = g.is_, g.ie, g.js, g.je
+    npx, npy = g.npx, g.npy
+    def S(a, i0, i1, j0, j1): return a[..., R(j0, j1), R(i0, i1)]
+    def put(a, i0, i1, j0, j1, v):
+        a = a.clone(); a[..., R(j0, j1), R(i0, i1)] = v; return a
+    i1_, i2_, j1_, j2_ = is_ - 1 - nord, ie + 1 + nord, js - 1 - nord, je + 1 + nord
+    d2 = torch.zeros_like(q)
+    d2 = put(d2, i1_, i2_, j1_, j2_, (S(q, i1_, i2_, j1_, j2_) if mass is not None else damp * S(q, i1_, i2_, j1_, j2_)))
+    fx2 = torch.zeros_like(q); fy2 = torch.zeros_like(q)
+    if nord > 0:
+        d2 = copy_corners(d2, npx, npy, 1)
+    i0, i1, j0, j1 = is_ - nord, ie + nord + 1, js - nord, je + nord
+    fx2 = put(fx2, i0, i1, j0, j1, S(g.del6_v, i0, i1, j0, j1) * (S(d2, i0 - 1, i1 - 1, j0, j1) - S(d2, i0, i1, j0, j1)))
+    if nord > 0:
+        d2 = copy_corners(d2, npx, npy, 2)
+    i0, i1, j0, j1 = is_ - nord, ie + nord, js - nord, je + nord + 1
+    fy2 = put(fy2, i0, i1, j0, j1, S(g.del6_u, i0, i1, j0, j1) * (S(d2, i0, i1, j0 - 1, j1 - 1) - S(d2, i0, i1, j0, j1)))
+    for n in range(1, nord + 1):
+        nt = nord - n
+        i0, i1, j0, j1 = is_ - nt - 1, ie + nt + 1, js - nt - 1, je + nt + 1
+        d2 = put(torch.zeros_like(q), i0, i1, j0, j1,
+                 (S(fx2, i0, i1, j0, j1) - S(fx2, i0 + 1, i1 + 1, j0, j1) + S(fy2, i0, i1, j0, j1) - S(fy2, i0, i1, j0 + 1, j1 + 1)) *
+                 S(g.rarea, i0, i1, j0, j1))
+        d2 = copy_corners(d2, npx, npy, 1)
+        i0, i1, j0, j1 = is_ - nt, ie + nt + 1, js - nt, je + nt
+        fx2 = put(torch.zeros_like(q), i0, i1, j0, j1, S(g.del6_v, i0, i1, j0, j1) * (S(d2, i0, i1, j0, j1) - S(d2, i0 - 1, i1 - 1, j0, j1)))
+        d2 = copy_corners(d2, npx, npy, 2)
+        i0, i1, j0, j1 = is_ - nt, ie + nt, js - nt, je + nt + 1
+        fy2 = put(torch.zeros_like(q), i0, i1, j0, j1, S(g.del6_u, i0, i1, j0, j1) * (S(d2, i0, i1, j0, j1) - S(d2, i0, i1, j0 - 1, j1 - 1)))
+    if mass is not None:
+        damp2 = 0.5 * damp
+        i0, i1, j0, j1 = is_, ie + 1, js, je
+        fx = put(fx, i0, i1, j0, j1, S(fx, i0, i1, j0, j1) + damp2 * (S(mass, i0 - 1, i1 - 1, j0, j1) + S(mass, i0, i1, j0, j1)) * S(fx2, i0, i1, j0, j1))
+        i0, i1, j0, j1 = is_, ie, js, je + 1
+        fy = put(fy, i0, i1, j0, j1, S(fy, i0, i1, j0, j1) + damp2 * (S(mass, i0, i1, j0 - 1, j1 - 1) + S(mass, i0, i1, j0, j1)) * S(fy2, i0, i1, j0, j1))
+    else:
+        i0, i1, j0, j1 = is_, ie + 1, js, je
+        fx = put(fx, i0, i1, j0, j1, S(fx, i0, i1, j0, j1) + S(fx2, i0, i1, j0, j1))
+        i0, i1, j0, j1 = is_, ie, js, je + 1
+        fy = put(fy, i0, i1, j0, j1, S(fy, i0, i1, j0, j1) + S(fy2, i0, i1, j0, j1))
+    return fx, fy
+
+
+def lev_select(vals_by_level, variants):
+    """variants: dict key -> tensor [6,K,..]; vals_by_level: list (len K) of keys.  Returns the
+    tensor that takes, for each level k, variants[vals_by_level[k]]."""
+    keys = sorted(set(vals_by_level))
+    if len(keys) == 1:
+        return variants[keys[0]]
+    out = None
+    for key in keys:
+        m = torch.tensor([v == key for v in vals_by_level], dtype=torch.bool).view(1, -1, 1, 1)
+        out = variants[key] if out is None else torch.where(m, variants[key], out)
+    return out
+
+
+def fv_tp_2d_damp(q, crx, cry, hord, xfx, yfx, g, ra_x, ra_y, mfx=None, mfy=None, mass=None, nord=None, damp_c=None):
+    """fv_tp_2d including the optional deln_flux (tp_core_nlm.F90:168-208).  nord / damp_c:
+    per-level python lists (len K) or None."""
+    fx, fy, q = fv_tp_2d(q, crx, cry, hord, xfx, yfx, g, ra_x, ra_y, mfx, mfy)
+    if nord is None:
+        return fx, fy, q
+    K = q.shape[1]
+    use_mass = (mfx is not None) and (mass is not None)
+    if mfx is not None and mass is None:
+        return fx, fy, q
+    fxv, fyv, keys = {}, {}, []
+    for k in range(K):
+        if damp_c[k] > 1.e-4:
+            keys.append((nord[k], damp_c[k]))
+        else:
+            keys.append(None)
+    for key in set(keys):
+        if key is None:
+            fxv[key], fyv[key] = fx, fy
+        else:
+            damp = (key[1] * g.da_min) ** (key[0] + 1)
+            fxv[key], fyv[key] = deln_flux(key[0], damp, q, fx, fy, g, mass if use_mass else None)
+    skeys = [str(k) for k in keys]
+    fx = lev_select(skeys, {str(k): v for k, v in fxv.items()})
+    fy = lev_select(skeys, {str(k): v for k, v in fyv.items()})
+    return fx, fy, q

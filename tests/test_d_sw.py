@@ -1,0 +1,105 @@
+"""d_sw (D-grid step) and a2b_ord4: C-ABI library vs the torch oracle."""
+import numpy as np
+import pytest
+import torch
+from oracle import d_sw as odsw
+from oracle.a2b_edge import a2b_ord4
+from common import metrics, ograd, handle, rnd, check_module
+
+
+def dsw_inputs(N, K, seed):
+    rng = np.random.default_rng(seed)
+    f = {}
+    f["delp"] = 1000.0 + 50.0 * rnd(rng, N, K)
+    f["pt"] = 300.0 + 5.0 * rnd(rng, N, K)
+    f["u"] = 10.0 * rnd(rng, N, K)
+    f["v"] = 10.0 * rnd(rng, N, K)
+    f["w"] = 0.5 * rnd(rng, N, K)
+    f["uc"] = 10.0 * rnd(rng, N, K)
+    f["vc"] = 10.0 * rnd(rng, N, K)
+    f["ua"] = 10.0 * rnd(rng, N, K)
+    f["va"] = 10.0 * rnd(rng, N, K)
+    f["divg_d"] = 1e-5 * rnd(rng, N, K)
+    return f, rng
+
+
+def level_params(K, sponge):
+    """per-level switches like dyn_core_nlm.F90:579-625 with a 1-layer sponge at k=0"""
+    p = dict(hord_mt=[2] * K, hord_vt=[2] * K, hord_tm=[2] * K, hord_dp=[2] * K, nord=[1] * K, nord_v=[1] * K,
+             nord_w=[1] * K, nord_t=[1] * K, d2_bg=[0.015] * K, damp_v=[0.0005] * K, damp_w=[0.0005] * K, damp_t=[0.0005] * K)
+    if sponge:
+        for n in ("hord_mt", "hord_vt", "hord_tm", "hord_dp"):
+            p[n][0] = 1
+        p["nord"][0] = 0; p["d2_bg"][0] = 4.0
+        p["nord_w"][0] = 0; p["damp_w"][0] = 4.0
+        p["nord_v"][0] = 0; p["damp_v"][0] = 2.0
+        p["nord_t"][0] = 0; p["damp_t"][0] = 0.0005
+    return p
+
+
+def flat_params(p, K):
+    out = {}
+    for name, v in p.items():
+        if isinstance(v, list):
+            out[name] = v[-1]
+            for k in range(K):
+                if v[k] != v[-1]:
+                    out["%s@%d" % (name, k)] = v[k]
+        else:
+            out[name] = v
+    return out
+
+
+def _run_dsw(emu, hydrostatic, sponge):
+    N, K = 12, 2
+    f, rng = dsw_inputs(N, K, 11)
+    g = ograd(N)
+    dt = 450.0
+    prm = level_params(K, sponge)
+    prm.update(dddmp=0.2, d4_bg=0.15, hydrostatic=hydrostatic)
+    names = list(f.keys())
+    act = [n for n in names if not (hydrostatic and n == "w")]
+    onames = ["delp_n", "pt_n", "u_n", "v_n", "fx", "fy", "crx", "cry", "xfx", "yfx"] + ([] if hydrostatic else ["w_n"])
+    key = dict(delp_n="delp", pt_n="pt", u_n="u", v_n="v", w_n="w")
+    def fn(*a):
+        d = {n: torch.from_numpy(f[n]) for n in names}
+        d.update(dict(zip(act, a)))
+        o = odsw.d_sw(d["delp"], d["pt"], d["u"], d["v"], d["w"], d["uc"], d["vc"], d["ua"], d["va"], d["divg_d"], g, dt, prm)
+        return tuple(o[key.get(k, k)] for k in onames)
+    npx = N + 1
+    C = (1, N, 1, N)
+    outs = dict(delp_n=C, pt_n=C, w_n=C, u_n=(1, N, 1, npx), v_n=(1, npx, 1, N), fx=(1, npx, 1, N), fy=(1, N, 1, npx),
+                crx=(1, npx, -2, N + 3), xfx=(1, npx, -2, N + 3), cry=(-2, N + 3, 1, npx), yfx=(-2, N + 3, 1, npx))
+    outs = {k: outs[k] for k in onames}
+    h = handle(N, K, emu)
+    p = flat_params(prm, K); p["dt"] = dt; p["hydrostatic"] = int(hydrostatic)
+    return check_module(h, "d_sw", N, K, f, act, outs, fn, p, rng, tol=2e-12, dot_tol=1e-12)
+
+
+def _run_a2b(emu):
+    N, K = 12, 2
+    rng = np.random.default_rng(3)
+    f = {"qin": rnd(rng, N, K)}
+    g = ograd(N)
+    h = handle(N, K, emu)
+    return check_module(h, "a2b_ord4", N, K, f, ["qin"], {"qout": (1, N + 1, 1, N + 1)}, lambda q: (a2b_ord4(q, g),), {}, rng)
+
+
+def test_a2b_ord4_emu():
+    _run_a2b(True)
+
+
+@pytest.mark.parametrize("hydrostatic,sponge", [(True, False), (False, True)])
+def test_d_sw_emu(hydrostatic, sponge):
+    _run_dsw(True, hydrostatic, sponge)
+
+
+@pytest.mark.gpu
+def test_a2b_ord4_gpu():
+    _run_a2b(False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hydrostatic,sponge", [(True, False), (False, True), (False, False)])
+def test_d_sw_gpu(hydrostatic, sponge):
+    _run_dsw(False, hydrostatic, sponge)
