@@ -1,0 +1,116 @@
+// dyn_core: the acoustic sub-cycle (model/dyn_core_nlm.F90:78-1040; TL dyn_core_tlm.F90:93,
+// AD dyn_core_adm.F90:115/1686) assembled from the c_sw / d_sw / geopk / pressure-gradient
+// stages with the halo exchanges of mosaic.cu in the reference's positions.
+#include "dyn.h"
+#include "modules.h"
+
+namespace fv3lm {
+
+// per-level switches of the k-loop in front of d_sw (dyn_core_nlm.F90:579-625) plus the
+// TL module's first-order sponge transport (dyn_core_tlm.F90:740-926)
+void level_params(const DynConfig& c, int K, DswParams& d) {
+  for (int k = 0; k < 128; k++) { d.hord_mt.v[k] = d.hord_vt.v[k] = d.hord_tm.v[k] = d.hord_dp.v[k] = 2; d.nord.v[k] = d.nord_v.v[k] = d.nord_w.v[k] = d.nord_t.v[k] = 0; }
+  for (int k = 0; k < 96; k++) d.d2_bg.v[k] = d.damp_v.v[k] = d.damp_w.v[k] = d.damp_t.v[k] = 0.0;
+  for (int k = 1; k <= K; k++) {
+    int nord_k = c.nord, nord_v = std::min(2, c.nord);
+    double d2 = std::min(0.20, c.d2_bg);
+    double damp_vt = c.do_vort_damp ? c.vtdm4 : 0.0;
+    int nord_w = nord_v, nord_t = nord_v; double damp_w = damp_vt, damp_t = damp_vt;
+    if (K == 1 || c.n_sponge < 0) {
+      d2 = c.d2_bg;
+    } else {
+      if (k == 1) {
+        nord_k = 0; d2 = std::max(0.01, std::max(c.d2_bg, c.d2_bg_k1)); nord_w = 0; damp_w = d2;
+        if (c.do_vort_damp) { nord_v = 0; damp_vt = 0.5 * d2; }
+      } else if (k == std::max(2, c.n_sponge - 1) && c.d2_bg_k2 > 0.01) {
+        nord_k = 0; d2 = std::max(c.d2_bg, c.d2_bg_k2); nord_w = 0; damp_w = d2;
+        if (c.do_vort_damp) { nord_v = 0; damp_vt = 0.5 * d2; }
+      } else if (k == std::max(3, c.n_sponge) && c.d2_bg_k2 > 0.05) {
+        nord_k = 0; d2 = std::max(c.d2_bg, 0.2 * c.d2_bg_k2); nord_w = 0; damp_w = d2;
+      }
+    }
+    const bool sp = k <= c.n_sponge_ord;
+    d.hord_mt.v[k - 1] = sp ? 1 : c.hord_mt; d.hord_vt.v[k - 1] = sp ? 1 : c.hord_vt;
+    d.hord_tm.v[k - 1] = sp ? 1 : c.hord_tm; d.hord_dp.v[k - 1] = sp ? 1 : c.hord_dp;
+    d.nord.v[k - 1] = nord_k; d.nord_v.v[k - 1] = nord_v; d.nord_w.v[k - 1] = nord_w; d.nord_t.v[k - 1] = nord_t;
+    d.d2_bg.v[k - 1] = d2; d.damp_v.v[k - 1] = damp_vt; d.damp_w.v[k - 1] = damp_w; d.damp_t.v[k - 1] = damp_t;
+  }
+  d.dddmp = c.dddmp; d.d4_bg = c.d4_bg; d.hydrostatic = c.hydrostatic;
+}
+
+DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s) {
+  const Geom& g = P.dv->g;
+  const int K = g.K, is = g.is, ie = g.ie, js = g.js, je = g.je, ng = g.ng;
+  const int isd = is - ng, ied = ie + ng, jsd = js - ng, jed = je + ng;
+  const double dt = c.bdt / c.n_split, dt2 = 0.5 * dt;
+  if (!c.hydrostatic) throw std::runtime_error("build_dyn_core: non-hydrostatic path is built by build_dyn_core_nh");
+  DswParams dp; level_params(c, K, dp); dp.dt = dt;
+  DynOut o;
+  int u = s.u, v = s.v, pt = s.pt, delp = s.delp, w = s.w;
+  int mfx = -1, mfy = -1, cx = -1, cy = -1;
+  for (int it = 1; it <= c.n_split; it++) {
+    const std::string tg = "it" + std::to_string(it);
+    CswOut cs = build_c_sw(P, mo, delp, pt, u, v, w, dt2, true, c.nord, K, tg + ".csw");
+    if (c.nord > 0) add_patch(P, "halo_divgd", &mo.h_corner, {cs.divg_d});
+    int pkc = P.val(tg + ".pkc", K + 1), gz = P.val(tg + ".gzc", K + 1), pe0 = P.val(tg + ".pe_c", K + 1), pl0 = P.val(tg + ".peln_c", K + 1), pz0 = P.val(tg + ".pkz_c", K);
+    add_col<S_geopk>(P, "geopk_c", {c.ptop, c.akap, c.cp_air, 1, 1, K}, {cs.delpc, cs.ptc, s.phis}, {pkc, gz, pe0, pl0, pz0});
+    int uc = P.val(tg + ".uc", K), vc = P.val(tg + ".vc", K);
+    P.add<S_pgrad_c>("p_grad_c", {dt2, 1}, {cs.uc, cs.vc, pkc, gz, cs.delpc}, {uc, vc}, K);
+    add_patch(P, "halo_ucvc", &mo.h_cgrid, {uc, vc});
+    DswOut ds = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, cs.ua, cs.va, cs.divg_d, dp, K, tg + ".dsw");
+    // flux capacitors (d_sw :913-931)
+    if (mfx < 0) { mfx = ds.fx; mfy = ds.fy; cx = ds.crx; cy = ds.cry; }
+    else {
+      int a = P.val(tg + ".mfx", K), b = P.val(tg + ".mfy", K), cc = P.val(tg + ".cx", K), d = P.val(tg + ".cy", K);
+      P.add<S_add2>("acc_mfx", {is, ie + 1, js, je}, {mfx, ds.fx}, {a}, K);
+      P.add<S_add2>("acc_mfy", {is, ie, js, je + 1}, {mfy, ds.fy}, {b}, K);
+      P.add<S_add2>("acc_cx", {is, ie + 1, jsd, jed}, {cx, ds.crx}, {cc}, K);
+      P.add<S_add2>("acc_cy", {isd, ied, js, je + 1}, {cy, ds.cry}, {d}, K);
+      mfx = a; mfy = b; cx = cc; cy = d;
+    }
+    delp = ds.delp; pt = ds.pt;
+    add_patch(P, "halo_delp", &mo.h_center, {delp});
+    add_patch(P, "halo_pt", &mo.h_center, {pt});
+    int pkd = P.val(tg + ".pk", K + 1), gzd = P.val(tg + ".gz", K + 1);
+    o.pe = P.val(tg + ".pe", K + 1); o.peln = P.val(tg + ".peln", K + 1); o.pkz = P.val(tg + ".pkz", K);
+    add_col<S_geopk>(P, "geopk_d", {c.ptop, c.akap, c.cp_air, 2, 0, K}, {delp, pt, s.phis}, {pkd, gzd, o.pe, o.peln, o.pkz});
+    o.pk = pkd;
+    int pkb = build_a2b_ord4(P, mo, pkd, K + 1, tg + ".a2b_pk"), gzb = build_a2b_ord4(P, mo, gzd, K + 1, tg + ".a2b_gz");
+    u = P.val(tg + ".u", K); v = P.val(tg + ".v", K);
+    P.add<S_gradp>("one_grad_p", {dt, pow(c.ptop, c.akap), 0}, {ds.u, ds.v, pkb, gzb, pkb, pkb}, {u, v}, K);
+    if (it == c.n_split) add_patch(P, "get_boundary_uv", &mo.gb_dgrid, {u, v});
+    else add_patch(P, "halo_uv", &mo.h_dgrid, {u, v});
+  }
+  o.u = u; o.v = v; o.pt = pt; o.delp = delp; o.w = w; o.mfx = mfx; o.mfy = mfy; o.cx = cx; o.cy = cy;
+  return o;
+}
+
+void dyn_config_from(DynConfig& c, const ModuleParams& prm) {
+  const fv3lm_config* f = prm.cfg;
+  c.hydrostatic = prm.geti("hydrostatic", f->hydrostatic) != 0;
+  c.n_split = prm.geti("n_split", f->n_split);
+  c.bdt = prm.get("bdt", f->dt);
+  c.nord = prm.geti("nord", f->nord);
+  c.hord_mt = prm.geti("hord_mt", f->hord_mt); c.hord_vt = prm.geti("hord_vt", f->hord_vt);
+  c.hord_tm = prm.geti("hord_tm", f->hord_tm); c.hord_dp = prm.geti("hord_dp", f->hord_dp);
+  c.n_sponge = prm.geti("n_sponge", f->n_sponge); c.n_sponge_ord = prm.geti("n_sponge_ord", 0);
+  c.d2_bg = prm.get("d2_bg", f->d2_bg); c.d2_bg_k1 = prm.get("d2_bg_k1", f->d2_bg_k1); c.d2_bg_k2 = prm.get("d2_bg_k2", f->d2_bg_k2);
+  c.d4_bg = prm.get("d4_bg", f->d4_bg); c.dddmp = prm.get("dddmp", f->dddmp); c.vtdm4 = prm.get("vtdm4", f->vtdm4);
+  c.do_vort_damp = prm.geti("do_vort_damp", f->do_vort_damp) != 0;
+  c.ptop = prm.get("ptop", f->ptop); c.akap = prm.get("akap", f->kappa); c.cp_air = prm.get("cp_air", f->cp);
+  c.rdgas = prm.get("rdgas", f->rdgas); c.grav = prm.get("grav", f->grav);
+}
+
+void mod_dyn_core(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
+  const int K = P.dv->g.K;
+  DynConfig c; dyn_config_from(c, prm);
+  DynState s;
+  s.u = io.in(P, "u", K); s.v = io.in(P, "v", K); s.pt = io.in(P, "pt", K); s.delp = io.in(P, "delp", K);
+  s.w = io.in(P, "w", K); s.phis = io.in(P, "phis", 1);
+  DynOut o = build_dyn_core(P, mo, c, s);
+  io.out(P, "u_n", o.u); io.out(P, "v_n", o.v); io.out(P, "pt_n", o.pt); io.out(P, "delp_n", o.delp);
+  io.out(P, "mfx", o.mfx); io.out(P, "mfy", o.mfy); io.out(P, "cx", o.cx); io.out(P, "cy", o.cy);
+  io.out(P, "pkz", o.pkz); io.out(P, "pe", o.pe); io.out(P, "peln", o.peln); io.out(P, "pk", o.pk);
+}
+
+}  // namespace fv3lm

@@ -1,0 +1,32 @@
+// dyn_core / fv_dynamics program builders
+#pragma once
+#include "engine.h"
+#include "mosaic.h"
+#include "stages_tp.h"
+#include "stages_csw.h"
+#include "stages_dsw.h"
+#include "stages_dyn.h"
+
+namespace fv3lm {
+
+struct DynConfig {
+  bool hydrostatic = true;
+  int n_split = 1, k_split = 1, nq = 0;
+  double bdt = 900.0;      // time step of one dyn_core call (dt / k_split)
+  int nord = 1, hord_mt = 2, hord_vt = 2, hord_tm = 2, hord_dp = 2, hord_tr = 2;
+  int n_sponge = 0, n_sponge_ord = 0;
+  double d2_bg = 0.015, d2_bg_k1 = 4.0, d2_bg_k2 = 2.0, d4_bg = 0.15, dddmp = 0.2, vtdm4 = 0.0005;
+  bool do_vort_damp = true;
+  double ptop = 1.0, akap = 2.0 / 7.0, cp_air = 1004.6, rdgas = 287.05, grav = 9.80665, zvir = 0.6078;
+  double a_imp = 1.0, p_fac = 0.05;
+};
+
+struct DynState { int u, v, w, delz, pt, delp, phis; };
+struct DynOut { int u, v, w, delz, pt, delp, mfx, mfy, cx, cy, pkz, pe, peln, pk; };
+
+void level_params(const DynConfig& c, int K, DswParams& d);
+DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s);
+struct ModuleParams;
+void dyn_config_from(DynConfig& c, const ModuleParams& prm);
+
+}  // namespace fv3lm

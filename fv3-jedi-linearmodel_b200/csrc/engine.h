@@ -282,6 +282,67 @@ struct Program {
   void add(const char* nm, const typename S::P& prm, std::vector<int> ins, std::vector<int> outs, int nk_launch);
 };
 
+// ---------------------------------------------------------------------------------
+// column stages: one thread owns a whole (i, j) column and marches in k (vertical
+// solvers, prefix sums).  NL/TL share one templated eval; the adjoint is hand-written
+// (eval_ad) as a thread-local reverse sweep -- columns never interact, so no reduction.
+//   struct S { NI, NO; struct P; template<class X> eval(X&, P&); template<class X> eval_ad(X&, P&); }
+// ---------------------------------------------------------------------------------
+template <class S> struct ColNL : CtxBase {
+  using T = double;
+  FArr<S::NI> in_; FArr<S::NO> out_;
+  DEV size_t o2(int nkf, int k, int di, int dj) const { return ((size_t)tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + (size_t)(jj + dj) * g.pitch + (ii + di); }
+  DEV T in(int f, int k, int di = 0, int dj = 0) const { return in_.p[f][o2(in_.nk[f], k, di, dj)]; }
+  DEV void out(int o, int k, T v) const { out_.p[o][o2(out_.nk[o], k, 0, 0)] = v; }
+  DEV T rd(int o, int k) const { return out_.p[o][o2(out_.nk[o], k, 0, 0)]; }   // read back own output
+};
+template <class S> struct ColTL : CtxBase {
+  using T = Dual;
+  FArr<S::NI> in_, ind_; FArr<S::NO> out_, outd_;
+  DEV size_t o2(int nkf, int k, int di, int dj) const { return ((size_t)tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + (size_t)(jj + dj) * g.pitch + (ii + di); }
+  DEV T in(int f, int k, int di = 0, int dj = 0) const {
+    size_t o = o2(in_.nk[f], k, di, dj);
+    return Dual(in_.p[f][o], ind_.p[f] ? ind_.p[f][o] : 0.0);
+  }
+  DEV void out(int o, int k, T v) const {
+    size_t q = o2(out_.nk[o], k, 0, 0);
+    out_.p[o][q] = v.v;
+    if (outd_.p[o]) outd_.p[o][q] = v.d;
+  }
+  DEV T rd(int o, int k) const { size_t q = o2(out_.nk[o], k, 0, 0); return Dual(out_.p[o][q], outd_.p[o] ? outd_.p[o][q] : 0.0); }
+};
+template <class S> struct ColAD : CtxBase {
+  FArr<S::NI> in_, inad_; FArr<S::NO> out_, outad_;
+  DEV size_t o2(int nkf, int k) const { return ((size_t)tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + (size_t)jj * g.pitch + ii; }
+  DEV double in(int f, int k) const { return in_.p[f][o2(in_.nk[f], k)]; }
+  DEV double outv(int o, int k) const { return out_.p[o][o2(out_.nk[o], k)]; }          // stored forward value
+  DEV double oad(int o, int k) const { return outad_.p[o] ? outad_.p[o][o2(outad_.nk[o], k)] : 0.0; }
+  DEV void oad_add(int o, int k, double v) const { if (outad_.p[o]) outad_.p[o][o2(outad_.nk[o], k)] += v; }  // workspace use
+  DEV void add(int f, int k, double v) const { if (inad_.p[f]) inad_.p[f][o2(inad_.nk[f], k)] += v; }
+  DEV bool active(int f) const { return inad_.p[f] != nullptr; }
+};
+template <class S> struct KernColNL {
+  typename S::P p; Geom g; Metrics m; FArr<S::NI> in; FArr<S::NO> out;
+  DEV void operator()(int ii, int jj, int z) const {
+    ColNL<S> x; x.g = g; x.m = m; x.in_ = in; x.out_ = out; x.setpos(ii, jj, 0, z);
+    S::eval(x, p);
+  }
+};
+template <class S> struct KernColTL {
+  typename S::P p; Geom g; Metrics m; FArr<S::NI> in, ind; FArr<S::NO> out, outd;
+  DEV void operator()(int ii, int jj, int z) const {
+    ColTL<S> x; x.g = g; x.m = m; x.in_ = in; x.ind_ = ind; x.out_ = out; x.outd_ = outd; x.setpos(ii, jj, 0, z);
+    S::eval(x, p);
+  }
+};
+template <class S> struct KernColAD {
+  typename S::P p; Geom g; Metrics m; FArr<S::NI> in, inad; FArr<S::NO> out, outad;
+  DEV void operator()(int ii, int jj, int z) const {
+    ColAD<S> x; x.g = g; x.m = m; x.in_ = in; x.inad_ = inad; x.out_ = out; x.outad_ = outad; x.setpos(ii, jj, 0, z);
+    S::eval_ad(x, p);
+  }
+};
+
 struct Device {
   Geom g;
   Metrics m;
@@ -320,5 +381,23 @@ void Program::add(const char* nm, const typename S::P& prm, std::vector<int> ins
   };
   ops.push_back(op);
 }
+
+template <class S>
+void add_col(Program& P, const char* nm, const typename S::P& prm, std::vector<int> ins, std::vector<int> outs) {
+  if ((int)ins.size() != S::NI || (int)outs.size() != S::NO) throw std::runtime_error(std::string("arity mismatch in ") + nm);
+  Op op; op.name = nm; op.in = ins; op.out = outs; op.nk_launch = 1;
+  typename S::P p = prm;
+  op.run = [p](Program& P, Op& o, int mode) {
+    const Geom& g = P.dv->g;
+    FArr<S::NI> in, ind; FArr<S::NO> out, outd;
+    for (int f = 0; f < S::NI; f++) { Value& v = P.vals[o.in[f]]; in.p[f] = v.traj; in.nk[f] = v.nk; ind.p[f] = v.active ? v.pert : nullptr; ind.nk[f] = v.nk; }
+    for (int f = 0; f < S::NO; f++) { Value& v = P.vals[o.out[f]]; out.p[f] = v.traj; out.nk[f] = v.nk; outd.p[f] = v.active ? v.pert : nullptr; outd.nk[f] = v.nk; }
+    if (mode == MODE_TL) launch3d(KernColTL<S>{p, g, P.dv->m, in, ind, out, outd}, g.NX, g.NY, g.ntile);
+    else if (mode == MODE_AD) launch3d(KernColAD<S>{p, g, P.dv->m, in, ind, out, outd}, g.NX, g.NY, g.ntile);
+    else launch3d(KernColNL<S>{p, g, P.dv->m, in, out}, g.NX, g.NY, g.ntile);
+  };
+  P.ops.push_back(op);
+}
+
 
 }  // namespace fv3lm

@@ -64,6 +64,7 @@ static void mod_halo(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& p
 }
 
 void mod_c_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
+void mod_dyn_core(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_d_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_a2b_ord4(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 
@@ -73,6 +74,7 @@ static const ModEntry g_mods[] = {
     {"c_sw", mod_c_sw, "in: delp pt u v w; out: delpc ptc wc uc vc ua va ut vt divg_d; params: dt2 hydrostatic nord"},
     {"d_sw", mod_d_sw, "in: delp pt u v w uc vc ua va divg_d; out: delp_n pt_n u_n v_n w_n fx fy crx cry xfx yfx; params: dt hydrostatic hord_* nord* d2_bg damp_* dddmp d4_bg (per level: name@k)"},
     {"a2b_ord4", mod_a2b_ord4, "in: qin; out: qout"},
+    {"dyn_core", mod_dyn_core, "in: u v pt delp w phis; out: u_n v_n pt_n delp_n mfx mfy cx cy pkz pe peln pk; params: n_split bdt + config overrides"},
     {"halo", mod_halo, "in/out: q qc u v uc vc; params: corners"},
 };
 

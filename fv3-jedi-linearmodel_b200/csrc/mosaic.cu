@@ -125,6 +125,32 @@ void Mosaic::build(const Geom& g_) {
   { int s[1] = {ST_CORNER}; build_halo(h_corner, g, 1, s, false); h_corner.name = "halo_corner"; }
   { int s[2] = {ST_YSTAG, ST_XSTAG}; build_halo(h_dgrid, g, 2, s, true); h_dgrid.name = "halo_dgrid"; }
   { int s[2] = {ST_XSTAG, ST_YSTAG}; build_halo(h_cgrid, g, 2, s, true); h_cgrid.name = "halo_cgrid"; }
+  // mpp_get_boundary for the D grid (dyn_core_nlm.F90:943-955, fv3jedi_lm_dynamics_mod.F90:386-399): the
+  // shared north row of u and east column of v are taken from the tile that owns them
+  // as its south / west edge.  fields {u, v}
+  {
+    const int N = g.N, o = g.ng - 1;
+    int stags[2] = {ST_YSTAG, ST_XSTAG};
+    for (int t = 0; t < 6; t++)
+      for (int e = 0; e < 2; e++)
+        for (int n = 1; n <= N; n++) {
+          int i = (e == 0) ? n : N + 1, j = (e == 0) ? N + 1 : n;   // e = 0: u(i, N+1) ; e = 1: v(N+1, j)
+          double ox, oy; stag_off(stags[e], ox, oy);
+          double x = i - 1 + ox, y = j - 1 + oy;
+          int tb, rot; double xb, yb;
+          to_neighbour(t, e == 0 ? x : x + 0.25, e == 0 ? y + 0.25 : y, N, tb, xb, yb, rot);
+          if (e == 0) { if (rot == 0) yb -= 0.25; else xb -= 0.25; } else { if (rot == 0) xb -= 0.25; else yb -= 0.25; }
+          int sc = e; double sg = 1.0;
+          if (rot != 0) { sc = 1 - e; sg = (rot == +1) ? (e == 0 ? -1.0 : 1.0) : (e == 0 ? 1.0 : -1.0); }
+          double sox, soy; stag_off(stags[sc], sox, soy);
+          int si = (int)std::lround(xb - sox + 1), sj = (int)std::lround(yb - soy + 1);
+          PatchEntry pe;
+          pe.dtile = t; pe.dpos = (j + o) * g.pitch + (i + o); pe.dcomp = e;
+          pe.stile = tb; pe.spos = (sj + o) * g.pitch + (si + o); pe.scomp = sc; pe.sign = sg;
+          gb_dgrid.host.push_back(pe);
+        }
+    gb_dgrid.name = "get_boundary_dgrid";
+  }
   // copy_corners, model/tp_core_nlm.F90:214-289
   for (int dir = 1; dir <= 2; dir++) {
     std::vector<CF> cf;
@@ -190,7 +216,7 @@ void Mosaic::build(const Geom& g_) {
   for (PatchMap* p : all()) p->upload();
 }
 std::vector<PatchMap*> Mosaic::all() {
-  return {&h_center, &h_corner, &h_dgrid, &h_cgrid, &cc1, &cc2, &f4c1, &f4c2, &fcb_x, &fcb_y, &fc_dgrid_vec, &c_utmp, &c_ua, &c_vtmp, &c_va};
+  return {&h_center, &h_corner, &h_dgrid, &h_cgrid, &gb_dgrid, &cc1, &cc2, &f4c1, &f4c2, &fcb_x, &fcb_y, &fc_dgrid_vec, &c_utmp, &c_ua, &c_vtmp, &c_va};
 }
 void Mosaic::destroy() {
   for (PatchMap* p : all()) p->destroy();

@@ -36,6 +36,7 @@ struct Mosaic {
   Geom g;
   // halo exchanges
   PatchMap h_center, h_corner, h_dgrid, h_cgrid;
+  PatchMap gb_dgrid;        // mpp_get_boundary(u, v, DGRID_NE): north row of u, east column of v from the owner tile
   // corner fills
   PatchMap cc1, cc2;        // copy_corners(dir)        model/tp_core_nlm.F90:214
   PatchMap f4c1, f4c2;      // fill_4corners(dir)       model/sw_core_nlm.F90:3102

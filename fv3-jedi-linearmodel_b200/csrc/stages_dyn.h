@@ -1,0 +1,156 @@
+// dyn_core helpers: geopk (model/dyn_core_nlm.F90:1954-2087), p_grad_c (:1369-1429),
+// one_grad_p (:1645-1779), nh_p_grad (:1431-1529) and small accumulation stages.
+// TL: model_tlmadm/dyn_core_tlm.F90 GEOPK_TLM :4578, P_GRAD_C_TLM :3194, ONE_GRAD_P_TLM :3867,
+// NH_P_GRAD_TLM :3340; AD: dyn_core_adm.F90.
+#pragma once
+#include "engine.h"
+#include "mosaic.h"
+
+namespace fv3lm {
+
+// geopk: column prefix sum of delp -> pe, peln, pk = exp(akap*log(pe)); suffix sum of
+// cp*pt*dpk -> gz; pkz.   in: delp pt hs ; out: pk gz pe peln pkz
+struct S_geopk {
+  static constexpr int NI = 3, NO = 5;
+  struct P { double ptop, akap, cp_air; int halo; int cg; int K; };   // halo = 1 (C grid) or 2 (D grid)
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is - p.halo, g.ie + p.halo, g.js - p.halo, g.je + p.halo)) return;
+    const int K = p.K;
+    const double ptk = pow(p.ptop, p.akap), peln1 = log(p.ptop);
+    const bool in_dom = x.in_rect(g.is, g.ie, g.js, g.je);
+    T p1 = T(p.ptop);
+    x.out(0, 0, T(ptk)); x.out(2, 0, T(p.ptop)); x.out(3, 0, T(peln1));
+    T pk_prev = T(ptk), ln_prev = T(peln1);
+    for (int k = 1; k <= K; k++) {
+      p1 = p1 + x.in(0, k - 1);
+      T lp = m_log(p1);
+      T pk = m_exp(p.akap * lp);
+      x.out(0, k, pk); x.out(2, k, p1); x.out(3, k, lp);
+      if (in_dom && !p.cg) x.out(4, k - 1, (pk - pk_prev) / (p.akap * (lp - ln_prev)));
+      pk_prev = pk; ln_prev = lp;
+    }
+    T gz = x.in(2, 0);
+    x.out(1, K, gz);
+    for (int k = K - 1; k >= 0; k--) {
+      gz = gz + p.cp_air * x.in(1, k) * (x.rd(0, k + 1) - x.rd(0, k));
+      x.out(1, k, gz);
+    }
+  }
+  template <class X> DEV static void eval_ad(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is - p.halo, g.ie + p.halo, g.js - p.halo, g.je + p.halo)) return;
+    const int K = p.K;
+    const bool in_dom = x.in_rect(g.is, g.ie, g.js, g.je);
+    // pkz -> pk, peln adjoints (the output adjoint arrays serve as workspace; they are dead afterwards)
+    if (in_dom && !p.cg) {
+      for (int k = 0; k < K; k++) {
+        double a = x.oad(4, k);
+        double dln = x.outv(3, k + 1) - x.outv(3, k), pkz = x.outv(4, k);
+        double dpk_ad = a / (p.akap * dln), dln_ad = -a * pkz / dln;
+        x.oad_add(0, k + 1, dpk_ad); x.oad_add(0, k, -dpk_ad);
+        x.oad_add(3, k + 1, dln_ad); x.oad_add(3, k, -dln_ad);
+      }
+    }
+    // gz suffix sum:  gz(k) = gz(k+1) + cp*pt(k)*(pk(k+1)-pk(k))
+    double g_ad = 0.0;
+    for (int k = 0; k < K; k++) {
+      g_ad += x.oad(1, k);
+      double dpk = x.outv(0, k + 1) - x.outv(0, k);
+      x.add(1, k, g_ad * p.cp_air * dpk);
+      double c = g_ad * p.cp_air * x.in(1, k);
+      x.oad_add(0, k + 1, c); x.oad_add(0, k, -c);
+    }
+    // pressure prefix sum:  p(k) = p(k-1) + delp(k-1); lp = log p; pk = exp(akap lp)
+    double p_ad = 0.0;
+    for (int k = K; k >= 1; k--) {
+      double lp_ad = x.oad(0, k) * p.akap * x.outv(0, k) + x.oad(3, k);
+      p_ad += lp_ad / x.outv(2, k) + x.oad(2, k);
+      x.add(0, k - 1, p_ad);
+    }
+  }
+};
+
+// p_grad_c (hydrostatic: wk = pkc(k+1)-pkc(k); non-hydrostatic: wk = delpc)
+// in: uc vc pkc gz delpc ; out: uc_new vc_new
+struct S_pgrad_c {
+  static constexpr int NI = 5, NO = 2;
+  struct P { double dt2; int hydrostatic; };
+  static constexpr int NT = 17;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0},
+                                   {2, 0, 0, 0}, {2, -1, 0, 0}, {2, 0, -1, 0}, {2, 0, 0, 1}, {2, -1, 0, 1}, {2, 0, -1, 1},
+                                   {3, 0, 0, 0}, {3, -1, 0, 0}, {3, 0, -1, 0}, {3, 0, 0, 1}, {3, -1, 0, 1}, {3, 0, -1, 1},
+                                   {4, 0, 0, 0}, {4, -1, 0, 0}, {4, 0, -1, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    auto wk = [&](int di, int dj) -> T { return p.hydrostatic ? x.in(2, di, dj, 1) - x.in(2, di, dj, 0) : x.in(4, di, dj); };
+    if (x.in_rect(g.is, g.ie + 1, g.js, g.je)) {
+      x.out(0, x.in(0) + p.dt2 * x.M(x.m.rdxc) / (wk(-1, 0) + wk(0, 0)) *
+                             ((x.in(3, -1, 0, 1) - x.in(3, 0, 0, 0)) * (x.in(2, 0, 0, 1) - x.in(2, -1, 0, 0)) +
+                              (x.in(3, -1, 0, 0) - x.in(3, 0, 0, 1)) * (x.in(2, -1, 0, 1) - x.in(2, 0, 0, 0))));
+    }
+    if (x.in_rect(g.is, g.ie, g.js, g.je + 1)) {
+      x.out(1, x.in(1) + p.dt2 * x.M(x.m.rdyc) / (wk(0, -1) + wk(0, 0)) *
+                             ((x.in(3, 0, -1, 1) - x.in(3, 0, 0, 0)) * (x.in(2, 0, 0, 1) - x.in(2, 0, -1, 0)) +
+                              (x.in(3, 0, -1, 0) - x.in(3, 0, 0, 1)) * (x.in(2, 0, -1, 1) - x.in(2, 0, 0, 0))));
+    }
+  }
+};
+
+// one_grad_p / nh_p_grad wind update from B-grid (corner) pk, gz [, pp, delp_b]
+// in: u v pkb gzb ppb dpb ; out: u_new v_new.    pk(k=0) = top value (ptk) and pp(k=0) = 0 are
+// imposed on read, like the reference does on the arrays (:1689-1693, :1465-1470).
+struct S_gradp {
+  static constexpr int NI = 6, NO = 2;
+  struct P { double dt, top; int nonhydro; };
+  static constexpr int NT = 23;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0},
+                                   {2, 0, 0, 0}, {2, 1, 0, 0}, {2, 0, 1, 0}, {2, 0, 0, 1}, {2, 1, 0, 1}, {2, 0, 1, 1},
+                                   {3, 0, 0, 0}, {3, 1, 0, 0}, {3, 0, 1, 0}, {3, 0, 0, 1}, {3, 1, 0, 1}, {3, 0, 1, 1},
+                                   {4, 0, 0, 0}, {4, 1, 0, 0}, {4, 0, 1, 0}, {4, 0, 0, 1}, {4, 1, 0, 1}, {4, 0, 1, 1},
+                                   {5, 0, 0, 0}, {5, 1, 0, 0}, {5, 0, 1, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    auto PK = [&](int di, int dj, int dk) -> T { return (x.kk + dk == 0) ? T(p.top) : x.in(2, di, dj, dk); };
+    auto PP = [&](int di, int dj, int dk) -> T { return (x.kk + dk == 0) ? T(0.0) : x.in(4, di, dj, dk); };
+    auto GZ = [&](int di, int dj, int dk) -> T { return x.in(3, di, dj, dk); };
+    auto wk = [&](int di, int dj) -> T { return PK(di, dj, 1) - PK(di, dj, 0); };
+    if (x.in_rect(g.is, g.ie, g.js, g.je + 1)) {
+      T du = p.dt / (wk(0, 0) + wk(1, 0)) * ((GZ(0, 0, 1) - GZ(1, 0, 0)) * (PK(1, 0, 1) - PK(0, 0, 0)) + (GZ(0, 0, 0) - GZ(1, 0, 1)) * (PK(0, 0, 1) - PK(1, 0, 0)));
+      if (p.nonhydro) {
+        T dn = p.dt / (x.in(5, 0, 0) + x.in(5, 1, 0)) * ((GZ(0, 0, 1) - GZ(1, 0, 0)) * (PP(1, 0, 1) - PP(0, 0, 0)) + (GZ(0, 0, 0) - GZ(1, 0, 1)) * (PP(0, 0, 1) - PP(1, 0, 0)));
+        x.out(0, (x.in(0) + du + dn) * x.M(x.m.rdx));
+      } else {
+        x.out(0, x.M(x.m.rdx) * (0.0 + x.in(0) + du));
+      }
+    }
+    if (x.in_rect(g.is, g.ie + 1, g.js, g.je)) {
+      T dv = p.dt / (wk(0, 0) + wk(0, 1)) * ((GZ(0, 0, 1) - GZ(0, 1, 0)) * (PK(0, 1, 1) - PK(0, 0, 0)) + (GZ(0, 0, 0) - GZ(0, 1, 1)) * (PK(0, 0, 1) - PK(0, 1, 0)));
+      if (p.nonhydro) {
+        T dn = p.dt / (x.in(5, 0, 0) + x.in(5, 0, 1)) * ((GZ(0, 0, 1) - GZ(0, 1, 0)) * (PP(0, 1, 1) - PP(0, 0, 0)) + (GZ(0, 0, 0) - GZ(0, 1, 1)) * (PP(0, 0, 1) - PP(0, 1, 0)));
+        x.out(1, (x.in(1) + dv + dn) * x.M(x.m.rdy));
+      } else {
+        x.out(1, x.M(x.m.rdy) * (0.0 + x.in(1) + dv));
+      }
+    }
+  }
+};
+
+// out = a + b on a rectangle (flux / Courant-number accumulators, dyn_core/d_sw :913-931)
+struct S_add2 {
+  static constexpr int NI = 2, NO = 1;
+  struct P { int i0, i1, j0, j1; };
+  static constexpr int NT = 2;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
+    x.out(0, x.in(0) + x.in(1));
+  }
+};
+
+struct DynParams;  // dyn.cu
+
+}  // namespace fv3lm

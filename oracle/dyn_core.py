@@ -1,0 +1,211 @@
+"""ORACLE (test infrastructure only).  dyn_core: the acoustic sub-cycle, restated in torch
+float64 from model/dyn_core_nlm.F90  dyn_core :78-1040, p_grad_c :1369, nh_p_grad :1431,
+one_grad_p :1645, geopk :1954 (TL model_tlmadm/dyn_core_tlm.F90:93, AD dyn_core_adm.F90:115/1686).
+
+Configuration restated: grid_type 0, non-nested, beta = 0, d_ext = 0 (divg2 = 0), d_con = 0,
+inline_q = F, no USE_COND.  Halo exchanges (mpp_update_domains, un-vendored FMS) are the
+index maps of oracle/cubed_sphere.py.
+
+parity unpinned (no reference vectors).
+"""
+import numpy as np
+import torch
+from .cubed_sphere import R, NG, Halo, neighbour, to_neighbour, STAG
+from .sw_core import c_sw, S, put, Z, O
+from .d_sw import d_sw
+from .a2b_edge import a2b_ord4
+
+
+class GetBoundary:
+    """mpp_get_boundary(u, v, gridtype=DGRID_NE) for whole tiles (dyn_core_nlm.F90:943-955):
+    north row of u and east column of v come from the tile owning them as south/west edge."""
+
+    def __init__(self, N):
+        rec = []
+        o = NG - 1
+        st = ("ystag", "xstag")
+        for t in range(6):
+            for e in (0, 1):
+                for n in range(1, N + 1):
+                    i, j = (n, N + 1) if e == 0 else (N + 1, n)
+                    ox, oy = STAG[st[e]]
+                    x, y = i - 1 + ox, j - 1 + oy
+                    side = "N" if e == 0 else "E"
+                    tb, kind = neighbour(t, side)
+                    xb, yb, rot = to_neighbour(kind, x, y, N)
+                    sc, sg = e, 1.0
+                    if rot != 0:
+                        sc = 1 - e
+                        sg = (-1.0 if e == 0 else 1.0) if rot == 1 else (1.0 if e == 0 else -1.0)
+                    sox, soy = STAG[st[sc]]
+                    si, sj = int(round(xb - sox + 1)), int(round(yb - soy + 1))
+                    rec.append((t, j + o, i + o, e, tb, sj + o, si + o, sc, sg))
+        self.rec = rec
+
+    def __call__(self, u, v):
+        un, vn = u.clone(), v.clone()
+        src = (u, v)
+        for e, dst in ((0, un), (1, vn)):
+            for sc in (0, 1):
+                r = [x for x in self.rec if x[3] == e and x[7] == sc]
+                if not r:
+                    continue
+                dt = torch.tensor([x[0] for x in r]); dj = torch.tensor([x[1] for x in r]); di = torch.tensor([x[2] for x in r])
+                st = torch.tensor([x[4] for x in r]); sj = torch.tensor([x[5] for x in r]); si = torch.tensor([x[6] for x in r])
+                sg = torch.tensor([x[8] for x in r], dtype=u.dtype)
+                dst[dt, :, dj, di] = sg[:, None] * src[sc][st, :, sj, si]
+        return un, vn
+
+
+_cache = {}
+
+
+def halo_of(N):
+    if N not in _cache:
+        _cache[N] = (Halo(N), GetBoundary(N))
+    return _cache[N]
+
+
+def geopk(delp, pt, hs, g, ptop, akap, cp_air, halo, cg):
+    """dyn_core_nlm.F90:1954-2087.  returns pk, gz, pe, peln [6,K+1,..] and pkz [6,K,..]"""
+    K = delp.shape[1]
+    z1 = torch.zeros_like(delp[:, :1])
+    pe = torch.cumsum(torch.cat([z1 + ptop, delp], dim=1), dim=1)      # same summation order as the column loop
+    peln = torch.log(pe)
+    pk = torch.exp(akap * peln)
+    pk = torch.cat([z1 + ptop ** akap, pk[:, 1:]], dim=1)
+    peln = torch.cat([z1 + np.log(ptop), peln[:, 1:]], dim=1)
+    dpk = pk[:, 1:] - pk[:, :-1]
+    incr = cp_air * pt * dpk
+    seq = torch.cat([hs.expand_as(z1) + 0.0 * z1, torch.flip(incr, dims=[1])], dim=1)   # hs, incr(K), incr(K-1), ...
+    gz = torch.flip(torch.cumsum(seq, dim=1), dims=[1])
+    pkz = dpk / (akap * (peln[:, 1:] - peln[:, :-1]))
+    return pk, gz, pe, peln, pkz
+
+
+def p_grad_c(dt2, delpc, pkc, gz, uc, vc, g, hydrostatic):
+    """dyn_core_nlm.F90:1369-1429"""
+    N = g.N
+    is_, ie, js, je = 1, N, 1, N
+    lo = lambda a: a[:, :-1]
+    hi = lambda a: a[:, 1:]
+    wk = (hi(pkc) - lo(pkc)) if hydrostatic else delpc
+    i0, i1, j0, j1 = is_, ie + 1, js, je
+    ucn = S(uc, i0, i1, j0, j1) + dt2 * S(g.rdxc, i0, i1, j0, j1) / (S(wk, i0 - 1, i1 - 1, j0, j1) + S(wk, i0, i1, j0, j1)) * (
+        (S(hi(gz), i0 - 1, i1 - 1, j0, j1) - S(lo(gz), i0, i1, j0, j1)) * (S(hi(pkc), i0, i1, j0, j1) - S(lo(pkc), i0 - 1, i1 - 1, j0, j1)) +
+        (S(lo(gz), i0 - 1, i1 - 1, j0, j1) - S(hi(gz), i0, i1, j0, j1)) * (S(hi(pkc), i0 - 1, i1 - 1, j0, j1) - S(lo(pkc), i0, i1, j0, j1)))
+    i0, i1, j0, j1 = is_, ie, js, je + 1
+    vcn = S(vc, i0, i1, j0, j1) + dt2 * S(g.rdyc, i0, i1, j0, j1) / (S(wk, i0, i1, j0 - 1, j1 - 1) + S(wk, i0, i1, j0, j1)) * (
+        (S(hi(gz), i0, i1, j0 - 1, j1 - 1) - S(lo(gz), i0, i1, j0, j1)) * (S(hi(pkc), i0, i1, j0, j1) - S(lo(pkc), i0, i1, j0 - 1, j1 - 1)) +
+        (S(lo(gz), i0, i1, j0 - 1, j1 - 1) - S(hi(gz), i0, i1, j0, j1)) * (S(hi(pkc), i0, i1, j0 - 1, j1 - 1) - S(lo(pkc), i0, i1, j0, j1)))
+    return put(uc, is_, ie + 1, js, je, ucn), put(vc, is_, ie, js, je + 1, vcn)
+
+
+def grad_p(u, v, pk, gz, g, dt, top_value, pp=None, delp=None):
+    """one_grad_p (:1645, hydrostatic, d_ext = 0) when pp is None, nh_p_grad (:1431) otherwise"""
+    N = g.N
+    is_, ie, js, je = 1, N, 1, N
+    pkb = a2b_ord4(pk, g)
+    pkb = torch.cat([torch.zeros_like(pkb[:, :1]) + top_value, pkb[:, 1:]], dim=1)
+    gzb = a2b_ord4(gz, g)
+    lo = lambda a: a[:, :-1]
+    hi = lambda a: a[:, 1:]
+    wk = hi(pkb) - lo(pkb)
+
+    def lin(q, i0, i1, j0, j1, di, dj):
+        # ((gz(k+1) - gz'(k)) * (q'(k+1) - q(k)) + (gz(k) - gz'(k+1)) * (q(k+1) - q'(k)))  with ' = neighbour (di,dj)
+        return ((S(hi(gzb), i0, i1, j0, j1) - S(lo(gzb), i0 + di, i1 + di, j0 + dj, j1 + dj)) * (S(hi(q), i0 + di, i1 + di, j0 + dj, j1 + dj) - S(lo(q), i0, i1, j0, j1)) +
+                (S(lo(gzb), i0, i1, j0, j1) - S(hi(gzb), i0 + di, i1 + di, j0 + dj, j1 + dj)) * (S(hi(q), i0, i1, j0, j1) - S(lo(q), i0 + di, i1 + di, j0 + dj, j1 + dj)))
+    i0, i1, j0, j1 = is_, ie, js, je + 1
+    du = dt / (S(wk, i0, i1, j0, j1) + S(wk, i0 + 1, i1 + 1, j0, j1)) * lin(pkb, i0, i1, j0, j1, 1, 0)
+    if pp is None:
+        un = S(g.rdx, i0, i1, j0, j1) * (0.0 + S(u, i0, i1, j0, j1) + du)
+    else:
+        ppb = a2b_ord4(pp, g)
+        ppb = torch.cat([torch.zeros_like(ppb[:, :1]), ppb[:, 1:]], dim=1)
+        wk1 = a2b_ord4(delp, g)
+        dn = dt / (S(wk1, i0, i1, j0, j1) + S(wk1, i0 + 1, i1 + 1, j0, j1)) * lin(ppb, i0, i1, j0, j1, 1, 0)
+        un = (S(u, i0, i1, j0, j1) + du + dn) * S(g.rdx, i0, i1, j0, j1)
+    i0, i1, j0, j1 = is_, ie + 1, js, je
+    dv = dt / (S(wk, i0, i1, j0, j1) + S(wk, i0, i1, j0 + 1, j1 + 1)) * lin(pkb, i0, i1, j0, j1, 0, 1)
+    if pp is None:
+        vn = S(g.rdy, i0, i1, j0, j1) * (0.0 + S(v, i0, i1, j0, j1) + dv)
+    else:
+        dn = dt / (S(wk1, i0, i1, j0, j1) + S(wk1, i0, i1, j0 + 1, j1 + 1)) * lin(ppb, i0, i1, j0, j1, 0, 1)
+        vn = (S(v, i0, i1, j0, j1) + dv + dn) * S(g.rdy, i0, i1, j0, j1)
+    return put(u, is_, ie, js, je + 1, un), put(v, is_, ie + 1, js, je, vn)
+
+
+def level_params(cfg, K):
+    """per-level switches of the k-loop before d_sw (dyn_core_nlm.F90:579-625).  cfg: dict with
+    hord_mt hord_vt hord_tm hord_dp nord d2_bg d2_bg_k1 d2_bg_k2 n_sponge vtdm4 do_vort_damp dddmp d4_bg
+    (the TL module additionally uses first-order transport in the sponge, hord_*_ks = 1,
+    model_tlmadm/dyn_core_tlm.F90:740-926: n_sponge_ord layers)"""
+    p = {k: [] for k in ("hord_mt", "hord_vt", "hord_tm", "hord_dp", "nord", "nord_v", "nord_w", "nord_t", "d2_bg", "damp_v", "damp_w", "damp_t")}
+    ns = cfg.get("n_sponge", 0)
+    for k in range(1, K + 1):
+        nord_k = cfg["nord"]
+        nord_v = min(2, cfg["nord"])
+        d2 = min(0.20, cfg["d2_bg"])
+        damp_vt = cfg["vtdm4"] if cfg["do_vort_damp"] else 0.0
+        nord_w = nord_v; nord_t = nord_v; damp_w = damp_vt; damp_t = damp_vt
+        if K == 1 or ns < 0:
+            d2 = cfg["d2_bg"]
+        else:
+            if k == 1:
+                nord_k = 0; d2 = max(0.01, cfg["d2_bg"], cfg["d2_bg_k1"]); nord_w = 0; damp_w = d2
+                if cfg["do_vort_damp"]:
+                    nord_v = 0; damp_vt = 0.5 * d2
+            elif k == max(2, ns - 1) and cfg["d2_bg_k2"] > 0.01:
+                nord_k = 0; d2 = max(cfg["d2_bg"], cfg["d2_bg_k2"]); nord_w = 0; damp_w = d2
+                if cfg["do_vort_damp"]:
+                    nord_v = 0; damp_vt = 0.5 * d2
+            elif k == max(3, ns) and cfg["d2_bg_k2"] > 0.05:
+                nord_k = 0; d2 = max(cfg["d2_bg"], 0.2 * cfg["d2_bg_k2"]); nord_w = 0; damp_w = d2
+        ho = 1 if k <= cfg.get("n_sponge_ord", 0) else None
+        for n in ("hord_mt", "hord_vt", "hord_tm", "hord_dp"):
+            p[n].append(ho if ho else cfg[n])
+        p["nord"].append(nord_k); p["nord_v"].append(nord_v); p["nord_w"].append(nord_w); p["nord_t"].append(nord_t)
+        p["d2_bg"].append(d2); p["damp_v"].append(damp_vt); p["damp_w"].append(damp_w); p["damp_t"].append(damp_t)
+    p["dddmp"] = cfg["dddmp"]; p["d4_bg"] = cfg["d4_bg"]
+    return p
+
+
+def dyn_core_hydro(st, g, cfg):
+    """hydrostatic acoustic loop.  st: dict u v pt delp phis (pt = virtual potential temperature
+    cp*..., as fv_dynamics passes it); u, v, delp, pt must already have valid halos.
+    Returns dict u v pt delp mfx mfy cx cy pkz pe peln pk."""
+    N = g.N
+    is_, ie, js, je = 1, N, 1, N
+    isd, ied, jsd, jed = g.isd, g.ied, g.jsd, g.jed
+    halo, getb = halo_of(N)
+    K = st["delp"].shape[1]
+    n_split = cfg["n_split"]
+    dt = cfg["bdt"] / n_split
+    dt2 = 0.5 * dt
+    prm = level_params(cfg, K)
+    prm["hydrostatic"] = True
+    u, v, pt, delp = st["u"], st["v"], st["pt"], st["delp"]
+    w = Z(u)
+    hs = st["phis"]
+    mfx = Z(u); mfy = Z(u); cx = Z(u); cy = Z(u)
+    ptop, akap, cp_air = cfg["ptop"], cfg["akap"], cfg["cp_air"]
+    for it in range(1, n_split + 1):
+        c = c_sw(delp, pt, u, v, w, g, dt2, True, cfg["nord"])
+        divgd = halo.corner(c["divg_d"]) if cfg["nord"] > 0 else c["divg_d"]
+        pkc, gz, _, _, _ = geopk(c["delpc"], c["ptc"], hs, g, ptop, akap, cp_air, 1, True)
+        uc, vc = p_grad_c(dt2, c["delpc"], pkc, gz, c["uc"], c["vc"], g, True)
+        uc, vc = halo.cgrid(uc, vc)
+        d = d_sw(delp, pt, u, v, w, uc, vc, c["ua"], c["va"], divgd, g, dt, prm)
+        mfx = put(mfx, is_, ie + 1, js, je, S(mfx, is_, ie + 1, js, je) + S(d["fx"], is_, ie + 1, js, je))
+        mfy = put(mfy, is_, ie, js, je + 1, S(mfy, is_, ie, js, je + 1) + S(d["fy"], is_, ie, js, je + 1))
+        cx = put(cx, is_, ie + 1, jsd, jed, S(cx, is_, ie + 1, jsd, jed) + S(d["crx"], is_, ie + 1, jsd, jed))
+        cy = put(cy, isd, ied, js, je + 1, S(cy, isd, ied, js, je + 1) + S(d["cry"], isd, ied, js, je + 1))
+        delp = halo.scalar(d["delp"]); pt = halo.scalar(d["pt"])
+        pkc, gz, pe, peln, pkz = geopk(delp, pt, hs, g, ptop, akap, cp_air, 2, False)
+        u, v = grad_p(d["u"], d["v"], pkc, gz, g, dt, ptop ** akap)
+        if it == n_split:
+            u, v = getb(u, v)
+        else:
+            u, v = halo.dgrid(u, v)
+    return dict(u=u, v=v, pt=pt, delp=delp, mfx=mfx, mfy=mfy, cx=cx, cy=cy, pkz=pkz, pe=pe, peln=peln, pk=pkc)

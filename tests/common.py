@@ -50,7 +50,7 @@ def region(a, i0, i1, j0, j1):
 
 
 def check_module(h, module, N, K, inputs, active, outs, oracle_fn, params, rng, tol=1e-12, dot_tol=1e-13,
-                 pert_scale=1e-2, tol_tl=None, tol_ad=None):
+                 pert_scale=1e-2, tol_tl=None, tol_ad=None, out_nk=None, modes=("nl", "tl", "ad")):
     """Generic parity check of one kernel family through the C ABI against the oracle.
     inputs : dict name -> ndarray (all inputs of the module, in module order)
     active : names of the inputs that carry perturbations / adjoints
@@ -63,12 +63,14 @@ def check_module(h, module, N, K, inputs, active, outs, oracle_fn, params, rng, 
     names = list(inputs.keys())
     onames = list(outs.keys())
     tin = [torch.from_numpy(inputs[n].copy()) for n in active]
-    zero = lambda: np.zeros_like(inputs[names[0]])
+    out_nk = out_nk or {}
+    NX = N + 7
+    zero = lambda o=None: np.zeros((6, out_nk.get(o, K), NX, NX))
     def newtraj():
         t = {n: inputs[n].copy() for n in names}
         for o in onames:
             if o not in t:
-                t[o] = zero()
+                t[o] = zero(o)
         return t
     res = {}
     # NL
@@ -85,7 +87,7 @@ def check_module(h, module, N, K, inputs, active, outs, oracle_fn, params, rng, 
     pert = {n: dp[n].copy() for n in active}
     for o in onames:
         if o not in pert:
-            pert[o] = zero()
+            pert[o] = zero(o)
     h.module_run(module, fv3lm.MODE_TL, traj, pert, params=params)
     _, dref = torch.func.jvp(oracle_fn, tuple(tin), tuple(torch.from_numpy(dp[n]) for n in active))
     tl = {}
@@ -97,8 +99,8 @@ def check_module(h, module, N, K, inputs, active, outs, oracle_fn, params, rng, 
     # AD
     yb = {}
     for o in onames:
-        y = zero()
-        region(y, *outs[o])[...] = region(rnd(rng, N, K), *outs[o])
+        y = zero(o)
+        region(y, *outs[o])[...] = region(rnd(rng, N, y.shape[1]), *outs[o])
         yb[o] = y
     traj = newtraj()
     pert = {n: np.zeros_like(inputs[n]) for n in active}

@@ -1,0 +1,75 @@
+"""dyn_core (acoustic sub-cycle incl. halo exchanges): C-ABI library vs the torch oracle."""
+import numpy as np
+import pytest
+import torch
+from oracle import dyn_core as odyn
+from oracle.dyn_core import halo_of
+from common import metrics, ograd, handle, rnd, check_module
+
+RD = 8314.47 / 28.965
+CFG = dict(nord=1, d2_bg=0.015, d2_bg_k1=4.0, d2_bg_k2=2.0, n_sponge=0, vtdm4=0.0005, do_vort_damp=True, dddmp=0.2, d4_bg=0.15,
+           hord_mt=2, hord_vt=2, hord_tm=2, hord_dp=2, n_sponge_ord=0, ptop=100.0, akap=2.0 / 7.0, cp_air=3.5 * RD)
+
+
+def smooth(rng, N, K, nsm=2):
+    """white noise smoothed a little so that transported fields stay physical"""
+    a = rnd(rng, N, K)
+    for _ in range(nsm):
+        a[..., 1:-1, 1:-1] = 0.2 * (a[..., 1:-1, 1:-1] + a[..., :-2, 1:-1] + a[..., 2:, 1:-1] + a[..., 1:-1, :-2] + a[..., 1:-1, 2:])
+    return a
+
+
+def hydro_state(N, K, seed):
+    """a resting, nearly isothermal atmosphere + noise; halos filled consistently"""
+    rng = np.random.default_rng(seed)
+    halo, getb = halo_of(N)
+    ps = 1.0e5 + 300.0 * smooth(rng, N, 1)
+    ptop = CFG["ptop"]
+    bk = np.linspace(0.0, 1.0, K + 1); ak = ptop * (1.0 - bk)
+    pe = ak[None, :, None, None] + bk[None, :, None, None] * ps
+    delp = pe[:, 1:] - pe[:, :-1]
+    pm = 0.5 * (pe[:, 1:] + pe[:, :-1])
+    T = 280.0 + 3.0 * smooth(rng, N, K)
+    pt = T / (pm / 1.0e5) ** CFG["akap"]               # potential temperature: cp*pt*dpk is the geopotential increment
+    u = 8.0 * smooth(rng, N, K); v = 8.0 * smooth(rng, N, K)
+    phis = 200.0 * 9.80665 * smooth(rng, N, 1)
+    f = dict(u=u, v=v, pt=pt, delp=delp, w=np.zeros_like(u), phis=phis)
+    t = {k: torch.from_numpy(a) for k, a in f.items()}
+    t["delp"] = halo.scalar(t["delp"]); t["pt"] = halo.scalar(t["pt"]); t["phis"] = halo.scalar(t["phis"])
+    t["u"], t["v"] = getb(t["u"], t["v"])
+    t["u"], t["v"] = halo.dgrid(t["u"], t["v"])
+    return {k: a.numpy().copy() for k, a in t.items()}, rng
+
+
+def _run(emu, n_split, K=3, modes=("nl", "tl", "ad")):
+    N = 12
+    f, rng = hydro_state(N, K, 5)
+    g = ograd(N)
+    cfg = dict(CFG); cfg["n_split"] = n_split; cfg["bdt"] = 900.0
+    act = ["u", "v", "pt", "delp"]
+    onames = ["u_n", "v_n", "pt_n", "delp_n", "mfx", "mfy", "cx", "cy", "pkz"]
+    key = dict(u_n="u", v_n="v", pt_n="pt", delp_n="delp")
+    def fn(*a):
+        st = {n: torch.from_numpy(f[n]) for n in f}
+        st.update(dict(zip(act, a)))
+        o = odyn.dyn_core_hydro(st, g, cfg)
+        return tuple(o[key.get(k, k)] for k in onames)
+    npx = N + 1
+    C = (1, N, 1, N)
+    outs = dict(u_n=(1, N, 1, npx), v_n=(1, npx, 1, N), pt_n=C, delp_n=C, mfx=(1, npx, 1, N), mfy=(1, N, 1, npx),
+                cx=(1, npx, -2, N + 3), cy=(-2, N + 3, 1, npx), pkz=C)
+    h = handle(N, K, emu)
+    p = dict(cfg); p["do_vort_damp"] = 1; p["hydrostatic"] = 1
+    return check_module(h, "dyn_core", N, K, f, act, outs, fn, p, rng, tol=5e-11, dot_tol=1e-11, pert_scale=1e-3)
+
+
+@pytest.mark.parametrize("n_split", [1, 2])
+def test_dyn_core_hydro_emu(n_split):
+    r = _run(True, n_split)
+    print(r)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_split", [1, 3])
+def test_dyn_core_hydro_gpu(n_split):
+    _run(False, n_split)
