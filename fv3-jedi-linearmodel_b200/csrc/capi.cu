@@ -127,7 +127,7 @@ int fv3lm_module_run(fv3lm_handle* h, const char* module, int mode, int nfields,
   const Geom& g = h->dv.g;
   ModuleParams prm;
   for (int n = 0; n < nparams; n++) prm.v[pnames[n]] = pvals[n];
-  prm.cfg = &h->cfg;
+  prm.cfg = &h->cfg; prm.ak = &h->ak; prm.bk = &h->bk;
   Program P; P.dv = &h->dv; P.name = module;
   ModuleIO io;
   build_module(module, P, h->mo, io, prm);

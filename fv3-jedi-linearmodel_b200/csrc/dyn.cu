@@ -38,7 +38,7 @@ void level_params(const DynConfig& c, int K, DswParams& d) {
   d.dddmp = c.dddmp; d.d4_bg = c.d4_bg; d.hydrostatic = c.hydrostatic;
 }
 
-DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s) {
+DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, const std::string& tag) {
   const Geom& g = P.dv->g;
   const int K = g.K, is = g.is, ie = g.ie, js = g.js, je = g.je, ng = g.ng;
   const int isd = is - ng, ied = ie + ng, jsd = js - ng, jed = je + ng;
@@ -49,7 +49,7 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s) {
   int u = s.u, v = s.v, pt = s.pt, delp = s.delp, w = s.w;
   int mfx = -1, mfy = -1, cx = -1, cy = -1;
   for (int it = 1; it <= c.n_split; it++) {
-    const std::string tg = "it" + std::to_string(it);
+    const std::string tg = tag + ".it" + std::to_string(it);
     CswOut cs = build_c_sw(P, mo, delp, pt, u, v, w, dt2, true, c.nord, K, tg + ".csw");
     if (c.nord > 0) add_patch(P, "halo_divgd", &mo.h_corner, {cs.divg_d});
     int pkc = P.val(tg + ".pkc", K + 1), gz = P.val(tg + ".gzc", K + 1), pe0 = P.val(tg + ".pe_c", K + 1), pl0 = P.val(tg + ".peln_c", K + 1), pz0 = P.val(tg + ".pkz_c", K);
@@ -99,6 +99,8 @@ void dyn_config_from(DynConfig& c, const ModuleParams& prm) {
   c.do_vort_damp = prm.geti("do_vort_damp", f->do_vort_damp) != 0;
   c.ptop = prm.get("ptop", f->ptop); c.akap = prm.get("akap", f->kappa); c.cp_air = prm.get("cp_air", f->cp);
   c.rdgas = prm.get("rdgas", f->rdgas); c.grav = prm.get("grav", f->grav);
+  c.zvir = prm.get("zvir", f->zvir); c.k_split = prm.geti("k_split", f->k_split); c.nq = prm.geti("nq", f->nq);
+  c.hord_tr = prm.geti("hord_tr", f->hord_tr);
 }
 
 void mod_dyn_core(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {

@@ -25,7 +25,7 @@ struct DynState { int u, v, w, delz, pt, delp, phis; };
 struct DynOut { int u, v, w, delz, pt, delp, mfx, mfy, cx, cy, pkz, pe, peln, pk; };
 
 void level_params(const DynConfig& c, int K, DswParams& d);
-DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s);
+DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, const std::string& tag = "dyn");
 struct ModuleParams;
 void dyn_config_from(DynConfig& c, const ModuleParams& prm);
 

@@ -60,6 +60,7 @@ struct Metrics {
 };
 
 struct Tap { int f, di, dj, dk; };
+constexpr int KLAST = 9999;   // dk value meaning "the last level of that field" (absolute)
 
 template <int N> struct FArr {
   double* p[N > 0 ? N : 1];
@@ -88,7 +89,7 @@ struct CtxBase {
   DEV double M1(const double* a, int ai) const { return a[(size_t)tile * g.slab + (ai + g.ng - 1)]; }
   DEV bool in_rect(int i0, int i1, int j0, int j1) const { return i >= i0 && i <= i1 && j >= j0 && j <= j1; }
   DEV size_t off(int nkf, int di, int dj, int dk) const {
-    int k = kk + dk;
+    int k = (dk == KLAST) ? nkf - 1 : kk + dk;
     if (k > nkf - 1) k = nkf - 1;
     if (k < 0) k = 0;
     return ((size_t)tile * nkf + k) * g.slab + (size_t)(jj + dj) * g.pitch + (ii + di);
@@ -156,13 +157,29 @@ template <class S, int n> struct AdTaps {
   template <class K> DEV static void run(const K& kn, int ii, int jj, int kk, int tile, double* acc) {
     if constexpr (n < S::NT) {
       constexpr Tap t = S::taps[n];
-      int oi = ii - t.di, oj = jj - t.dj, ok = kk - t.dk;
-      if (oi >= 0 && oi < kn.g.NX && oj >= 0 && oj < kn.g.NY && ok >= 0 && ok < kn.nk_fwd) {
-        CtxAD<S> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in; x.outad_ = kn.outad;
-        x.sf = t.f; x.sdi = t.di; x.sdj = t.dj; x.sdk = t.dk; x.acc = 0.0;
-        x.setpos(oi, oj, ok, tile);
-        S::eval(x, kn.p);
-        acc[t.f] += x.acc;
+      int oi = ii - t.di, oj = jj - t.dj;
+      if (oi >= 0 && oi < kn.g.NX && oj >= 0 && oj < kn.g.NY) {
+        if (t.dk == KLAST) {
+          // every output level reads the last level of this input: its owner sums over them
+          if (kk == kn.in.nk[t.f] - 1) {
+            for (int ok = 0; ok < kn.nk_fwd; ok++) {
+              CtxAD<S> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in; x.outad_ = kn.outad;
+              x.sf = t.f; x.sdi = t.di; x.sdj = t.dj; x.sdk = t.dk; x.acc = 0.0;
+              x.setpos(oi, oj, ok, tile);
+              S::eval(x, kn.p);
+              acc[t.f] += x.acc;
+            }
+          }
+        } else {
+          int ok = kk - t.dk;
+          if (ok >= 0 && ok < kn.nk_fwd) {
+            CtxAD<S> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in; x.outad_ = kn.outad;
+            x.sf = t.f; x.sdi = t.di; x.sdj = t.dj; x.sdk = t.dk; x.acc = 0.0;
+            x.setpos(oi, oj, ok, tile);
+            S::eval(x, kn.p);
+            acc[t.f] += x.acc;
+          }
+        }
       }
       AdTaps<S, n + 1>::run(kn, ii, jj, kk, tile, acc);
     }

@@ -1,0 +1,271 @@
+// fv_dynamics: the model-step driver (model/fv_dynamics_nlm.F90:70-760; TL fv_dynamics_tlm.F90:87,
+// AD fv_dynamics_adm.F90:110/874) = theta_v conversion, k_split x (dyn_core, tracer_2d,
+// Lagrangian_to_Eulerian), and the fv3jedi_lm dynamics-component wrapper
+// (src/dynamics/fv3jedi_lm_dynamics_mod.F90:268-689).
+#include "fvdyn.h"
+#include "modules.h"
+
+namespace fv3lm {
+
+// ---------------------------------------------------------------------------------
+// tracer_2d (model/fv_tracer2d_nlm.F90:275-516, q_split = 1)
+// ---------------------------------------------------------------------------------
+// xfx / yfx from the accumulated Courant numbers (:329-349).  in: cx cy ; out: xfx yfx
+struct S_trc_fx {
+  static constexpr int NI = 2, NO = 2;
+  struct P { int dummy; };
+  static constexpr int NT = 2;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P&) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    const int isd = g.is - g.ng, ied = g.ie + g.ng, jsd = g.js - g.ng, jed = g.je + g.ng;
+    if (x.in_rect(g.is, g.ie + 1, jsd, jed)) {
+      T c = x.in(0);
+      x.out(0, val(c) > 0.0 ? c * x.M(x.m.dxa, -1, 0) * x.M(x.m.dy) * x.M(x.m.sin_sg3, -1, 0) : c * x.M(x.m.dxa) * x.M(x.m.dy) * x.M(x.m.sin_sg1));
+    }
+    if (x.in_rect(isd, ied, g.js, g.je + 1)) {
+      T c = x.in(1);
+      x.out(1, val(c) > 0.0 ? c * x.M(x.m.dya, 0, -1) * x.M(x.m.dx) * x.M(x.m.sin_sg4, 0, -1) : c * x.M(x.m.dya) * x.M(x.m.dx) * x.M(x.m.sin_sg2));
+    }
+  }
+};
+// dp2 = dp1 + div(mfx, mfy) * rarea (:441-445).  in: dp1 mfx mfy ; out: dp2
+struct S_trc_dp2 {
+  static constexpr int NI = 3, NO = 1;
+  struct P { int dummy; };
+  static constexpr int NT = 5;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {1, 1, 0, 0}, {2, 0, 0, 0}, {2, 0, 1, 0}};
+  template <class X> DEV static void eval(X& x, const P&) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    x.out(0, x.in(0) + ((x.in(1) - x.in(1, 1, 0)) + (x.in(2) - x.in(2, 0, 1))) * x.M(x.m.rarea));
+  }
+};
+// q = (q*dp1 + div(fx, fy)*rarea) / dp2 (:470-476).  in: q dp1 fx fy dp2 ; out: q_new (halo copied)
+struct S_trc_upd {
+  static constexpr int NI = 5, NO = 1;
+  struct P { int dummy; };
+  static constexpr int NT = 7;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}, {2, 1, 0, 0}, {3, 0, 0, 0}, {3, 0, 1, 0}, {4, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P&) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    x.out(0, (x.in(0) * x.in(1) + ((x.in(2) - x.in(2, 1, 0)) + (x.in(3) - x.in(3, 0, 1))) * x.M(x.m.rarea)) / x.in(4));
+  }
+};
+
+std::vector<int> build_tracer_2d(Program& P, Mosaic& mo, std::vector<int> q, int dp1, int mfx, int mfy, int cx, int cy, int hord_tr, const std::string& tag) {
+  const int K = P.dv->g.K;
+  auto nm = [&](const std::string& s) { return tag + "." + s; };
+  int xfx = P.val(nm("xfx"), K), yfx = P.val(nm("yfx"), K), ra_x = P.val(nm("ra_x"), K), ra_y = P.val(nm("ra_y"), K), dp2 = P.val(nm("dp2"), K);
+  P.add<S_trc_fx>("trc_fx", {0}, {cx, cy}, {xfx, yfx}, K);
+  P.add<S_ra>("trc_ra", {0}, {xfx, yfx}, {ra_x, ra_y}, K);
+  P.add<S_trc_dp2>("trc_dp2", {0}, {dp1, mfx, mfy}, {dp2}, K);
+  LevOrd ho; for (int k = 0; k < 128; k++) ho.v[k] = (signed char)hord_tr;
+  std::vector<int> out;
+  for (size_t n = 0; n < q.size(); n++) {
+    TpOut f = build_fv_tp_2d(P, mo, q[n], cx, cy, xfx, yfx, ra_x, ra_y, mfx, mfy, ho, K, nm("tp_q" + std::to_string(n)));
+    int qn = P.val(nm("q" + std::to_string(n)), K);
+    P.add<S_trc_upd>("trc_upd", {0}, {q[n], dp1, f.fx, f.fy, dp2}, {qn}, K);
+    out.push_back(qn);
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------
+// Lagrangian_to_Eulerian (model/fv_mapz_nlm.F90:60-958), remap_option = 0, |kord| = 17
+// ---------------------------------------------------------------------------------
+// new Eulerian interface pressures (:313-317, :339-350).  in: pe peln pk ; out: pe2 pn2 pk2   (K+1 levels)
+struct S_rm_pe2 {
+  static constexpr int NI = 3, NO = 3;
+  struct P { LevD ak, bk; double ptop, akap; int K; };
+  static constexpr int NT = 3;
+  static constexpr Tap taps[NT] = {{0, 0, 0, KLAST}, {1, 0, 0, 0}, {2, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    const int k = x.kk;
+    if (k == 0 || k == p.K) {
+      x.out(0, k == 0 ? T(p.ptop) : x.in(0, 0, 0, KLAST));
+      x.out(1, x.in(1)); x.out(2, x.in(2));
+    } else {
+      T pe2 = p.ak.v[k] + p.bk.v[k] * x.in(0, 0, 0, KLAST);
+      T pn = m_log(pe2);
+      x.out(0, pe2); x.out(1, pn); x.out(2, m_exp(p.akap * pn));
+    }
+  }
+};
+// theta_v -> T_v, new delp, new pkz (:242-246, :318-328, :468-472)   in: pt pk peln pe2 pk2 pn2 ; out: tv dp2 pkz
+struct S_rm_tv {
+  static constexpr int NI = 6, NO = 3;
+  struct P { double akap; };
+  static constexpr int NT = 11;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {1, 0, 0, 1}, {2, 0, 0, 0}, {2, 0, 0, 1},
+                                   {3, 0, 0, 0}, {3, 0, 0, 1}, {4, 0, 0, 0}, {4, 0, 0, 1}, {5, 0, 0, 0}, {5, 0, 0, 1}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    x.out(0, x.in(0) * (x.in(1, 0, 0, 1) - x.in(1)) / (p.akap * (x.in(2, 0, 0, 1) - x.in(2))));
+    x.out(1, x.in(3, 0, 0, 1) - x.in(3));
+    x.out(2, (x.in(4, 0, 0, 1) - x.in(4)) / (p.akap * (x.in(5, 0, 0, 1) - x.in(5))));
+  }
+};
+// interface pressures at the D-grid wind points (:544-596).  DIR 0: u rows (j-1, j) ; DIR 1: v columns (i-1, i)
+// in: pe ; out: pe0 pe3   (K+1 levels)
+template <int DIR> struct S_rm_pew {
+  static constexpr int NI = 1, NO = 2;
+  struct P { LevD ak, bk; };
+  static constexpr int NT = 4;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {0, DIR == 1 ? -1 : 0, DIR == 0 ? -1 : 0, 0}, {0, 0, 0, KLAST}, {0, DIR == 1 ? -1 : 0, DIR == 0 ? -1 : 0, KLAST}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    if (DIR == 0) { if (!x.in_rect(g.is, g.ie, g.js, g.je + 1)) return; }
+    else { if (!x.in_rect(g.is, g.ie + 1, g.js, g.je)) return; }
+    constexpr int di = DIR == 1 ? -1 : 0, dj = DIR == 0 ? -1 : 0;
+    const int k = x.kk;
+    x.out(0, k == 0 ? x.in(0) : 0.5 * (x.in(0, di, dj, 0) + x.in(0)));
+    if (DIR == 1 && k == 0) x.out(1, T(p.ak.v[0]));
+    else x.out(1, p.ak.v[k] + (0.5 * p.bk.v[k]) * (x.in(0, di, dj, KLAST) + x.in(0, 0, 0, KLAST)));
+  }
+};
+// back to the model's thermodynamic variable (:883-887 last step, :923-931 otherwise).  in: tn q1 pkz ; out: pt
+struct S_rm_pt {
+  static constexpr int NI = 3, NO = 1;
+  struct P { double zvir; int last_step; };
+  static constexpr int NT = 3;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    if (p.last_step) x.out(0, x.in(0) / (1.0 + p.zvir * x.in(1)));
+    else x.out(0, x.in(0) / x.in(2));
+  }
+};
+// out = in on a rectangle (insert a remapped field into a full-size array value)
+struct S_copy {
+  static constexpr int NI = 1, NO = 1;
+  struct P { int i0, i1, j0, j1; };
+  static constexpr int NT = 1;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
+    x.out(0, x.in(0));
+  }
+};
+
+static LevD lev_of(const std::vector<double>& a) {
+  LevD o; for (int k = 0; k < 96; k++) o.v[k] = k < (int)a.size() ? a[k] : 0.0; return o;
+}
+
+RemapOut build_remap(Program& P, Mosaic& mo, const DynConfig& c, const std::vector<double>& ak, const std::vector<double>& bk,
+                     int pe, int pk, int peln, int pt, std::vector<int> q, int u, int v, bool last_step, const std::string& tag) {
+  (void)mo;
+  const Geom& g = P.dv->g;
+  const int K = g.K, is = g.is, ie = g.ie, js = g.js, je = g.je;
+  auto nm = [&](const std::string& s) { return tag + "." + s; };
+  LevD AK = lev_of(ak), BK = lev_of(bk);
+  RemapOut o;
+  int pe2 = P.val(nm("pe2"), K + 1), pn2 = P.val(nm("pn2"), K + 1), pk2 = P.val(nm("pk2"), K + 1);
+  P.add<S_rm_pe2>("rm_pe2", {AK, BK, c.ptop, c.akap, K}, {pe, peln, pk}, {pe2, pn2, pk2}, K + 1);
+  int tv = P.val(nm("tv"), K), dp2 = P.val(nm("dp2"), K), pkz = P.val(nm("pkz"), K);
+  P.add<S_rm_tv>("rm_tv", {c.akap}, {pt, pk, peln, pe2, pk2, pn2}, {tv, dp2, pkz}, K);
+  int dummy2d = P.val(nm("qs0"), 1);
+  int tn = P.val(nm("tn"), K);
+  add_col<S_remap>(P, "map_scalar_T", {K, 1, 0, is, ie, js, je}, {tv, peln, pn2, dummy2d, dp2}, {tn});
+  for (size_t n = 0; n < q.size(); n++) {
+    int qn = P.val(nm("q" + std::to_string(n)), K);
+    add_col<S_remap>(P, "map1_q2", {K, 0, 1, is, ie, js, je}, {q[n], pe, pe2, dummy2d, dp2}, {qn});
+    o.q.push_back(qn);
+  }
+  int pe0u = P.val(nm("pe0u"), K + 1), pe3u = P.val(nm("pe3u"), K + 1), pe0v = P.val(nm("pe0v"), K + 1), pe3v = P.val(nm("pe3v"), K + 1);
+  P.add<S_rm_pew<0>>("rm_pe_u", {AK, BK}, {pe}, {pe0u, pe3u}, K + 1);
+  P.add<S_rm_pew<1>>("rm_pe_v", {AK, BK}, {pe}, {pe0v, pe3v}, K + 1);
+  o.u = P.val(nm("u"), K); o.v = P.val(nm("v"), K);
+  add_col<S_remap>(P, "map1_ppm_u", {K, -1, 0, is, ie, js, je + 1}, {u, pe0u, pe3u, dummy2d, dp2}, {o.u});
+  add_col<S_remap>(P, "map1_ppm_v", {K, -1, 0, is, ie + 1, js, je}, {v, pe0v, pe3v, dummy2d, dp2}, {o.v});
+  o.pt = P.val(nm("pt"), K);
+  P.add<S_rm_pt>("rm_pt", {c.zvir, last_step ? 1 : 0}, {tn, o.q.empty() ? tn : o.q[0], pkz}, {o.pt}, K);
+  o.delp = dp2; o.pkz = pkz; o.pe = pe2; o.pk = pk2; o.peln = pn2;
+  return o;
+}
+
+// ---------------------------------------------------------------------------------
+// fv_dynamics
+// ---------------------------------------------------------------------------------
+// pt = T (1 + zvir q) / pkz  (:396-403).   in: t q1 pkz ; out: theta_v
+struct S_thv {
+  static constexpr int NI = 3, NO = 1;
+  struct P { double zvir; };
+  static constexpr int NT = 3;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    x.out(0, x.in(0) * (1.0 + p.zvir * x.in(1)) / x.in(2));
+  }
+};
+
+FvOut build_fv_dynamics(Program& P, Mosaic& mo, const DynConfig& c, const std::vector<double>& ak, const std::vector<double>& bk, FvState s) {
+  const Geom& g = P.dv->g;
+  const int K = g.K;
+  if (!c.hydrostatic) throw std::runtime_error("build_fv_dynamics: non-hydrostatic model step not built yet");
+  FvOut o;
+  // hydrostatic: pkz from compute_fv3_pressures (fv_pressure.F90:22-69) = geopk restricted to the compute domain
+  int pk0 = P.val("fv.pk0", K + 1), gz0 = P.val("fv.gz0", K + 1), pe0 = P.val("fv.pe0", K + 1), pl0 = P.val("fv.peln0", K + 1), pkz0 = P.val("fv.pkz0", K);
+  add_col<S_geopk>(P, "compute_fv3_pressures", {c.ptop, c.akap, c.cp_air, 0, 0, K}, {s.delp, s.pt, s.phis}, {pk0, gz0, pe0, pl0, pkz0});
+  int pt = P.val("fv.thv", K);
+  P.add<S_thv>("thv", {c.zvir}, {s.pt, s.q.empty() ? s.pt : s.q[0], pkz0}, {pt}, K);
+  int u = s.u, v = s.v, delp = s.delp, w = s.w;
+  std::vector<int> q = s.q;
+  DynConfig cd = c; cd.bdt = c.bdt / c.k_split;
+  for (int n_map = 1; n_map <= c.k_split; n_map++) {
+    const std::string tg = "m" + std::to_string(n_map);
+    add_patch(P, "halo_delp0", &mo.h_center, {delp});
+    add_patch(P, "halo_pt0", &mo.h_center, {pt});
+    add_patch(P, "halo_uv0", &mo.h_dgrid, {u, v});
+    const int dp1 = delp;
+    DynState ds; ds.u = u; ds.v = v; ds.w = w; ds.delz = -1; ds.pt = pt; ds.delp = delp; ds.phis = s.phis;
+    DynOut d = build_dyn_core(P, mo, cd, ds, tg);
+    for (int& x : q) add_patch(P, "halo_q", &mo.h_center, {x});
+    q = build_tracer_2d(P, mo, q, dp1, d.mfx, d.mfy, d.cx, d.cy, c.hord_tr, tg + ".trc");
+    RemapOut r = build_remap(P, mo, c, ak, bk, d.pe, d.pk, d.peln, d.pt, q, d.u, d.v, n_map == c.k_split, tg + ".rm");
+    u = r.u; v = r.v; pt = r.pt; delp = r.delp; q = r.q;
+  }
+  o.u = u; o.v = v; o.pt = pt; o.delp = delp; o.q = q; o.w = w;
+  return o;
+}
+
+// ---------------------------------------------------------------------------------
+// module wrappers
+// ---------------------------------------------------------------------------------
+void mod_remap(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
+  const int K = P.dv->g.K;
+  DynConfig c; dyn_config_from(c, prm);
+  int pe = io.in(P, "pe", K + 1), pk = io.in(P, "pk", K + 1), peln = io.in(P, "peln", K + 1), pt = io.in(P, "pt", K);
+  int q0 = io.in(P, "q0", K), u = io.in(P, "u", K), v = io.in(P, "v", K);
+  RemapOut r = build_remap(P, mo, c, *prm.ak, *prm.bk, pe, pk, peln, pt, {q0}, u, v, prm.geti("last_step", 1) != 0, "rm");
+  io.out(P, "pt_n", r.pt); io.out(P, "q0_n", r.q[0]); io.out(P, "u_n", r.u); io.out(P, "v_n", r.v); io.out(P, "delp_n", r.delp);
+  io.out(P, "pkz_n", r.pkz); io.out(P, "pe_n", r.pe);
+}
+
+void mod_step(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
+  // one fv3jedi_lm dynamics step on halo'd arrays whose compute domain holds the API state
+  const int K = P.dv->g.K;
+  DynConfig c; dyn_config_from(c, prm);
+  FvState s;
+  s.u = io.in(P, "u", K); s.v = io.in(P, "v", K); s.pt = io.in(P, "t", K); s.delp = io.in(P, "delp", K);
+  const char* qn[4] = {"qv", "ql", "qi", "o3"};
+  for (int n = 0; n < c.nq; n++) s.q.push_back(io.in(P, qn[n], K));
+  s.w = io.in(P, "w", K); s.delz = -1; s.phis = io.in(P, "phis", 1);
+  // traj_to_fv3 / pert_to_fv3: shared edge rows of the D-grid winds, halo of phis (fv3jedi_lm_dynamics_mod.F90:782-800)
+  add_patch(P, "get_boundary_in", &mo.gb_dgrid, {s.u, s.v});
+  add_patch(P, "halo_phis", &mo.h_center, {s.phis});
+  FvOut o = build_fv_dynamics(P, mo, c, *prm.ak, *prm.bk, s);
+  io.out(P, "u_n", o.u); io.out(P, "v_n", o.v); io.out(P, "t_n", o.pt); io.out(P, "delp_n", o.delp);
+  for (int n = 0; n < c.nq; n++) io.out(P, std::string(qn[n]) + "_n", o.q[n]);
+}
+
+}  // namespace fv3lm

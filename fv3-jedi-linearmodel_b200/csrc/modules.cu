@@ -65,6 +65,8 @@ static void mod_halo(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& p
 
 void mod_c_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_dyn_core(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
+void mod_remap(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
+void mod_step(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_d_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_a2b_ord4(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 
@@ -75,6 +77,8 @@ static const ModEntry g_mods[] = {
     {"d_sw", mod_d_sw, "in: delp pt u v w uc vc ua va divg_d; out: delp_n pt_n u_n v_n w_n fx fy crx cry xfx yfx; params: dt hydrostatic hord_* nord* d2_bg damp_* dddmp d4_bg (per level: name@k)"},
     {"a2b_ord4", mod_a2b_ord4, "in: qin; out: qout"},
     {"dyn_core", mod_dyn_core, "in: u v pt delp w phis; out: u_n v_n pt_n delp_n mfx mfy cx cy pkz pe peln pk; params: n_split bdt + config overrides"},
+    {"remap", mod_remap, "in: pe pk peln pt q0 u v; out: pt_n q0_n u_n v_n delp_n pkz_n pe_n; params: last_step"},
+    {"step", mod_step, "in: u v t delp qv ql qi o3 w phis; out: u_n v_n t_n delp_n qv_n ql_n qi_n o3_n (one fv3jedi_lm dynamics step)"},
     {"halo", mod_halo, "in/out: q qc u v uc vc; params: corners"},
 };
 

@@ -13,6 +13,8 @@ namespace fv3lm {
 struct ModuleParams {
   std::map<std::string, double> v;
   const fv3lm_config* cfg = nullptr;
+  const std::vector<double>* ak = nullptr;
+  const std::vector<double>* bk = nullptr;
   double get(const std::string& k, double dflt) const { auto it = v.find(k); return it == v.end() ? dflt : it->second; }
   int geti(const std::string& k, int dflt) const { return (int)get(k, (double)dflt); }
 };

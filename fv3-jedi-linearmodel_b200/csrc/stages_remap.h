@@ -1,0 +1,269 @@
+// Vertical remap (model/fv_mapz_nlm.F90): cs_profile / scalar_profile for |kord| > 16
+// (:2113-2200, :1730-1813) + the overlap integration of map_scalar / map1_ppm / map1_q2
+// (:1237-1330, :1332-1424, :1541-1634); tracer_2d helper stages (fv_tracer2d_nlm.F90:275-516).
+// TL: model_tlmadm/fv_mapz_tlm.F90 MAP_SCALAR_TLM :7765, MAP1_PPM_TLM :7909, MAP1_Q2_TLM :8222,
+// CS_PROFILE_TLM :8513; AD fv_mapz_adm.F90.  The adjoint is a hand-written column reverse sweep.
+#pragma once
+#include "engine.h"
+#include "mosaic.h"
+
+namespace fv3lm {
+
+constexpr int KMAX = 96;
+
+namespace rmp {
+constexpr double r3 = 1.0 / 3.0, r23 = 2.0 / 3.0;
+
+// interface values q[0..K] (q[k] = top edge of layer k, 0-based) of the cubic-spline profile
+template <class T> DEV void cs_profile(const T* a, const T* dp, T* q, T* gam, int K, int iv, T qs) {
+  if (iv == -2) {
+    // gam is shifted by one in the reference (gam(k+1)); store gam[k] = reference gam(k+1), k 0-based
+    gam[1] = T(0.5);
+    q[0] = 1.5 * a[0];
+    for (int k = 1; k < K - 1; k++) {
+      T grat = dp[k - 1] / dp[k];
+      T bet = 2.0 + grat + grat - gam[k];
+      q[k] = (3.0 * (a[k - 1] + a[k]) - q[k - 1]) / bet;
+      gam[k + 1] = grat / bet;
+    }
+    T grat = dp[K - 2] / dp[K - 1];
+    q[K - 1] = (3.0 * (a[K - 2] + a[K - 1]) - grat * qs - q[K - 2]) / (2.0 + grat + grat - gam[K - 1]);
+    q[K] = qs;
+    for (int k = K - 2; k >= 0; k--) q[k] = q[k] - gam[k + 1] * q[k + 1];
+  } else {
+    T grat = dp[1] / dp[0];
+    T bet = grat * (grat + 0.5);
+    q[0] = ((grat + grat) * (grat + 1.0) * a[0] + a[1]) / bet;
+    gam[0] = (1.0 + grat * (grat + 1.5)) / bet;
+    T d4 = T(0.0);
+    for (int k = 1; k < K; k++) {
+      d4 = dp[k - 1] / dp[k];
+      bet = 2.0 + d4 + d4 - gam[k - 1];
+      q[k] = (3.0 * (a[k - 1] + d4 * a[k]) - q[k - 1]) / bet;
+      gam[k] = d4 / bet;
+    }
+    T a_bot = 1.0 + d4 * (d4 + 1.5);
+    q[K] = (2.0 * d4 * (d4 + 1.0) * a[K - 1] + a[K - 2] - a_bot * q[K - 1]) / (d4 * (d4 + 0.5) - a_bot * gam[K - 1]);
+    for (int k = K - 1; k >= 0; k--) q[k] = q[k] - gam[k] * q[k + 1];
+  }
+}
+
+// layer (0-based) of source grid pe1 containing p, reference tie rule: first l with pe1[l] <= p <= pe1[l+1]
+DEV int find_layer(const double* pe1v, double p, int l0, int K) {
+  int l = l0;
+  while (l < K - 1 && !(p >= pe1v[l] && p <= pe1v[l + 1])) l++;
+  return l;
+}
+}  // namespace rmp
+
+// Remap one field.   in: a pe1 pe2 qs dp2 ; out: q2
+//   iv = -2 : bottom boundary value qs (2-D field) is used (w);  use_dp2: divide by dp2 (map1_q2)
+struct S_remap {
+  static constexpr int NI = 5, NO = 1;
+  struct P { int K, iv, use_dp2; int i0, i1, j0, j1; };
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
+    const int K = p.K;
+    T a[KMAX], pe1[KMAX + 1], pe2[KMAX + 1], dp[KMAX], q[KMAX + 1], gam[KMAX + 1];
+    double pe1v[KMAX + 1];
+    for (int k = 0; k <= K; k++) { pe1[k] = x.in(1, k); pe2[k] = x.in(2, k); pe1v[k] = val(pe1[k]); }
+    for (int k = 0; k < K; k++) { a[k] = x.in(0, k); dp[k] = pe1[k + 1] - pe1[k]; }
+    T qs = (p.iv == -2) ? x.in(3, 0) : T(0.0);
+    rmp::cs_profile(a, dp, q, gam, K, p.iv, qs);
+    int k0 = 0;
+    for (int k = 0; k < K; k++) {
+      int l = rmp::find_layer(pe1v, val(pe2[k]), k0, K);
+      T a2 = q[l], a3 = q[l + 1], a4 = 3.0 * (2.0 * a[l] - (a2 + a3));
+      T pl = (pe2[k] - pe1[l]) / dp[l];
+      T res;
+      if (val(pe2[k + 1]) <= pe1v[l + 1]) {
+        T pr = (pe2[k + 1] - pe1[l]) / dp[l];
+        res = a2 + 0.5 * (a4 + a3 - a2) * (pr + pl) - a4 * rmp::r3 * (pr * (pr + pl) + pl * pl);
+        k0 = l;
+      } else {
+        T qsum = (pe1[l + 1] - pe2[k]) * (a2 + 0.5 * (a4 + a3 - a2) * (1.0 + pl) - a4 * (rmp::r3 * (1.0 + pl * (1.0 + pl))));
+        for (int m = l + 1; m < K; m++) {
+          if (val(pe2[k + 1]) > pe1v[m + 1]) {
+            qsum = qsum + dp[m] * a[m];
+          } else {
+            T dpl = pe2[k + 1] - pe1[m];
+            T esl = dpl / dp[m];
+            T b2 = q[m], b3 = q[m + 1], b4 = 3.0 * (2.0 * a[m] - (b2 + b3));
+            qsum = qsum + dpl * (b2 + 0.5 * esl * (b3 - b2 + b4 * (1.0 - rmp::r23 * esl)));
+            k0 = m;
+            break;
+          }
+        }
+        T den = p.use_dp2 ? x.in(4, k) : pe2[k + 1] - pe2[k];
+        res = qsum / den;
+      }
+      x.out(0, k, res);
+    }
+  }
+
+  // ---- hand-written adjoint: recompute the forward column in double, then reverse
+  template <class X> DEV static void eval_ad(X& x, const P& p) {
+    if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
+    const int K = p.K;
+    double a[KMAX], pe1[KMAX + 1], pe2[KMAX + 1], dp[KMAX], q[KMAX + 1], gam[KMAX + 1];
+    double qt[KMAX + 1], bet[KMAX], d4[KMAX];
+    double a_ad[KMAX], q_ad[KMAX + 1], pe1_ad[KMAX + 1], pe2_ad[KMAX + 1], dp_ad[KMAX], gam_ad[KMAX + 1], dp2_ad[KMAX];
+    for (int k = 0; k <= K; k++) { pe1[k] = x.in(1, k); pe2[k] = x.in(2, k); q_ad[k] = 0.0; pe1_ad[k] = 0.0; pe2_ad[k] = 0.0; gam_ad[k] = 0.0; }
+    for (int k = 0; k < K; k++) { a[k] = x.in(0, k); dp[k] = pe1[k + 1] - pe1[k]; a_ad[k] = 0.0; dp_ad[k] = 0.0; dp2_ad[k] = 0.0; }
+    const double qs = (p.iv == -2) ? x.in(3, 0) : 0.0;
+    double qs_ad = 0.0;
+    // forward profile keeping the elimination intermediates
+    if (p.iv == -2) {
+      gam[1] = 0.5; qt[0] = 1.5 * a[0];
+      for (int k = 1; k < K - 1; k++) {
+        d4[k] = dp[k - 1] / dp[k];
+        bet[k] = 2.0 + d4[k] + d4[k] - gam[k];
+        qt[k] = (3.0 * (a[k - 1] + a[k]) - qt[k - 1]) / bet[k];
+        gam[k + 1] = d4[k] / bet[k];
+      }
+      d4[K - 1] = dp[K - 2] / dp[K - 1];
+      bet[K - 1] = 2.0 + d4[K - 1] + d4[K - 1] - gam[K - 1];
+      qt[K - 1] = (3.0 * (a[K - 2] + a[K - 1]) - d4[K - 1] * qs - qt[K - 2]) / bet[K - 1];
+      q[K] = qs; q[K - 1] = qt[K - 1];
+      for (int k = K - 2; k >= 0; k--) q[k] = qt[k] - gam[k + 1] * q[k + 1];
+    } else {
+      double grat = dp[1] / dp[0];
+      bet[0] = grat * (grat + 0.5);
+      qt[0] = ((grat + grat) * (grat + 1.0) * a[0] + a[1]) / bet[0];
+      gam[0] = (1.0 + grat * (grat + 1.5)) / bet[0];
+      d4[0] = grat;
+      for (int k = 1; k < K; k++) {
+        d4[k] = dp[k - 1] / dp[k];
+        bet[k] = 2.0 + d4[k] + d4[k] - gam[k - 1];
+        qt[k] = (3.0 * (a[k - 1] + d4[k] * a[k]) - qt[k - 1]) / bet[k];
+        gam[k] = d4[k] / bet[k];
+      }
+      double d = d4[K - 1], a_bot = 1.0 + d * (d + 1.5);
+      q[K] = (2.0 * d * (d + 1.0) * a[K - 1] + a[K - 2] - a_bot * qt[K - 1]) / (d * (d + 0.5) - a_bot * gam[K - 1]);
+      for (int k = K - 1; k >= 0; k--) q[k] = qt[k] - gam[k] * q[k + 1];
+    }
+    // ---- reverse of the integration (target layers are independent)
+    auto a4ad = [&](int l, double v) { a_ad[l] += 6.0 * v; q_ad[l] -= 3.0 * v; q_ad[l + 1] -= 3.0 * v; };
+    int k0 = 0;
+    for (int k = 0; k < K; k++) {
+      const double r_ad = x.oad(0, k);
+      int l = rmp::find_layer(pe1, pe2[k], k0, K);
+      double a2 = q[l], a3 = q[l + 1], a4 = 3.0 * (2.0 * a[l] - (a2 + a3));
+      double pl = (pe2[k] - pe1[l]) / dp[l];
+      double pl_ad = 0.0;
+      if (pe2[k + 1] <= pe1[l + 1]) {
+        double pr = (pe2[k + 1] - pe1[l]) / dp[l], s = pr + pl;
+        double c = 0.5 * (a4 + a3 - a2);
+        q_ad[l] += r_ad * (1.0 - 0.5 * s); q_ad[l + 1] += r_ad * 0.5 * s;
+        a4ad(l, r_ad * (0.5 * s - rmp::r3 * (pr * s + pl * pl)));
+        double pr_ad = r_ad * (c - a4 * rmp::r3 * (2.0 * pr + pl));
+        pl_ad = r_ad * (c - a4 * rmp::r3 * (pr + 2.0 * pl));
+        pe2_ad[k + 1] += pr_ad / dp[l]; pe1_ad[l] -= pr_ad / dp[l]; dp_ad[l] -= pr_ad * pr / dp[l];
+        k0 = l;
+      } else {
+        // recompute qsum pieces
+        double F = a2 + 0.5 * (a4 + a3 - a2) * (1.0 + pl) - a4 * (rmp::r3 * (1.0 + pl * (1.0 + pl)));
+        double qsum = (pe1[l + 1] - pe2[k]) * F;
+        int mlast = -1;
+        for (int m = l + 1; m < K; m++) {
+          if (pe2[k + 1] > pe1[m + 1]) qsum += dp[m] * a[m];
+          else {
+            double dpl = pe2[k + 1] - pe1[m], esl = dpl / dp[m];
+            double b2 = q[m], b3 = q[m + 1], b4 = 3.0 * (2.0 * a[m] - (b2 + b3));
+            qsum += dpl * (b2 + 0.5 * esl * (b3 - b2 + b4 * (1.0 - rmp::r23 * esl)));
+            mlast = m;
+            break;
+          }
+        }
+        double den = p.use_dp2 ? x.in(4, k) : pe2[k + 1] - pe2[k];
+        double qs_ad_ = r_ad / den;                 // adjoint of qsum
+        double den_ad = -r_ad * (qsum / den) / den;
+        if (p.use_dp2) dp2_ad[k] += den_ad; else { pe2_ad[k + 1] += den_ad; pe2_ad[k] -= den_ad; }
+        // first piece
+        double w = pe1[l + 1] - pe2[k];
+        pe1_ad[l + 1] += qs_ad_ * F; pe2_ad[k] -= qs_ad_ * F;
+        double F_ad = qs_ad_ * w;
+        q_ad[l] += F_ad * (1.0 - 0.5 * (1.0 + pl)); q_ad[l + 1] += F_ad * 0.5 * (1.0 + pl);
+        a4ad(l, F_ad * (0.5 * (1.0 + pl) - rmp::r3 * (1.0 + pl + pl * pl)));
+        pl_ad = F_ad * (0.5 * (a4 + a3 - a2) - a4 * rmp::r3 * (1.0 + 2.0 * pl));
+        // full layers and the last partial layer
+        const int mend = (mlast >= 0) ? mlast : K;
+        for (int m = l + 1; m < mend; m++) { dp_ad[m] += qs_ad_ * a[m]; a_ad[m] += qs_ad_ * dp[m]; }
+        if (mlast >= 0) {
+          int m = mlast;
+          double dpl = pe2[k + 1] - pe1[m], esl = dpl / dp[m];
+          double b2 = q[m], b3 = q[m + 1], b4 = 3.0 * (2.0 * a[m] - (b2 + b3));
+          double G = b2 + 0.5 * esl * (b3 - b2 + b4 * (1.0 - rmp::r23 * esl));
+          double dpl_ad = qs_ad_ * G, G_ad = qs_ad_ * dpl;
+          q_ad[m] += G_ad * (1.0 - 0.5 * esl); q_ad[m + 1] += G_ad * 0.5 * esl;
+          a4ad(m, G_ad * 0.5 * esl * (1.0 - rmp::r23 * esl));
+          double esl_ad = G_ad * 0.5 * (b3 - b2 + b4 * (1.0 - 2.0 * rmp::r23 * esl));
+          dpl_ad += esl_ad / dp[m]; dp_ad[m] -= esl_ad * esl / dp[m];
+          pe2_ad[k + 1] += dpl_ad; pe1_ad[m] -= dpl_ad;
+          k0 = m;
+        }
+      }
+      // pl = (pe2[k] - pe1[l]) / dp[l]
+      pe2_ad[k] += pl_ad / dp[l]; pe1_ad[l] -= pl_ad / dp[l]; dp_ad[l] -= pl_ad * pl / dp[l];
+    }
+    // ---- reverse of the profile
+    double qt_ad[KMAX + 1];
+    for (int k = 0; k <= K; k++) qt_ad[k] = 0.0;
+    if (p.iv == -2) {
+      for (int k = 0; k <= K - 2; k++) {            // q[k] = qt[k] - gam[k+1] q[k+1]
+        qt_ad[k] += q_ad[k]; gam_ad[k + 1] -= q_ad[k] * q[k + 1]; q_ad[k + 1] -= gam[k + 1] * q_ad[k];
+      }
+      qt_ad[K - 1] += q_ad[K - 1]; qs_ad += q_ad[K];
+      {  // qt[K-1] = (3(a[K-2]+a[K-1]) - d4 qs - qt[K-2]) / bet
+        int k = K - 1;
+        double n_ad = qt_ad[k] / bet[k], bet_ad = -qt_ad[k] * qt[k] / bet[k];
+        a_ad[k - 1] += 3.0 * n_ad; a_ad[k] += 3.0 * n_ad; qs_ad -= n_ad * d4[k]; qt_ad[k - 1] -= n_ad;
+        double d4_ad = -n_ad * qs + 2.0 * bet_ad;
+        gam_ad[k] -= bet_ad;
+        dp_ad[k - 1] += d4_ad / dp[k]; dp_ad[k] -= d4_ad * d4[k] / dp[k];
+      }
+      for (int k = K - 2; k >= 1; k--) {
+        double d4_ad = gam_ad[k + 1] / bet[k], bet_ad = -gam_ad[k + 1] * gam[k + 1] / bet[k];
+        double n_ad = qt_ad[k] / bet[k]; bet_ad -= qt_ad[k] * qt[k] / bet[k];
+        a_ad[k - 1] += 3.0 * n_ad; a_ad[k] += 3.0 * n_ad; qt_ad[k - 1] -= n_ad;
+        d4_ad += 2.0 * bet_ad; gam_ad[k] -= bet_ad;
+        dp_ad[k - 1] += d4_ad / dp[k]; dp_ad[k] -= d4_ad * d4[k] / dp[k];
+      }
+      a_ad[0] += 1.5 * qt_ad[0];
+      x.add(3, 0, qs_ad);
+    } else {
+      for (int k = 0; k < K; k++) {                 // q[k] = qt[k] - gam[k] q[k+1]
+        qt_ad[k] += q_ad[k]; gam_ad[k] -= q_ad[k] * q[k + 1]; q_ad[k + 1] -= gam[k] * q_ad[k];
+      }
+      double d = d4[K - 1], a_bot = 1.0 + d * (d + 1.5), den = d * (d + 0.5) - a_bot * gam[K - 1];
+      double num_ad = q_ad[K] / den, den_ad = -q_ad[K] * q[K] / den;
+      double d_ad = num_ad * 2.0 * (2.0 * d + 1.0) * a[K - 1] + den_ad * (2.0 * d + 0.5);
+      a_ad[K - 1] += num_ad * 2.0 * d * (d + 1.0); a_ad[K - 2] += num_ad;
+      double abot_ad = -num_ad * qt[K - 1] - den_ad * gam[K - 1];
+      qt_ad[K - 1] -= num_ad * a_bot; gam_ad[K - 1] -= den_ad * a_bot;
+      d_ad += abot_ad * (2.0 * d + 1.5);
+      double d4_carry = d_ad;                       // adjoint of d4[K-1] from the bottom closure
+      for (int k = K - 1; k >= 1; k--) {
+        double d4_ad = (k == K - 1 ? d4_carry : 0.0) + gam_ad[k] / bet[k];
+        double bet_ad = -gam_ad[k] * gam[k] / bet[k];
+        double n_ad = qt_ad[k] / bet[k]; bet_ad -= qt_ad[k] * qt[k] / bet[k];
+        a_ad[k - 1] += 3.0 * n_ad; d4_ad += 3.0 * n_ad * a[k]; a_ad[k] += 3.0 * n_ad * d4[k]; qt_ad[k - 1] -= n_ad;
+        d4_ad += 2.0 * bet_ad; gam_ad[k - 1] -= bet_ad;
+        dp_ad[k - 1] += d4_ad / dp[k]; dp_ad[k] -= d4_ad * d4[k] / dp[k];
+      }
+      double grat = d4[0];
+      double g_ad = gam_ad[0];
+      double grat_ad = g_ad * (2.0 * grat + 1.5) / bet[0], b_ad = -g_ad * gam[0] / bet[0];
+      double n_ad = qt_ad[0] / bet[0]; b_ad -= qt_ad[0] * qt[0] / bet[0];
+      grat_ad += n_ad * (4.0 * grat + 2.0) * a[0]; a_ad[0] += n_ad * 2.0 * grat * (grat + 1.0); a_ad[1] += n_ad;
+      grat_ad += b_ad * (2.0 * grat + 0.5);
+      dp_ad[1] += grat_ad / dp[0]; dp_ad[0] -= grat_ad * grat / dp[0];
+    }
+    for (int k = 0; k < K; k++) { pe1_ad[k + 1] += dp_ad[k]; pe1_ad[k] -= dp_ad[k]; }
+    for (int k = 0; k < K; k++) { x.add(0, k, a_ad[k]); if (p.use_dp2) x.add(4, k, dp2_ad[k]); }
+    for (int k = 0; k <= K; k++) { x.add(1, k, pe1_ad[k]); x.add(2, k, pe2_ad[k]); }
+  }
+};
+
+}  // namespace fv3lm

@@ -24,11 +24,11 @@ def ograd(N):
 _handles = {}
 
 
-def handle(N, K, emu, **kw):
-    key = (N, K, emu, tuple(sorted(kw.items())))
+def handle(N, K, emu, ak=None, bk=None, **kw):
+    key = (N, K, emu, tuple(sorted(kw.items())), None if ak is None else tuple(ak))
     if key not in _handles:
         cfg = fv3lm.default_config(N, K, **kw)
-        h = fv3lm.FV3LM(cfg, emu=emu)
+        h = fv3lm.FV3LM(cfg, ak, bk, emu=emu)
         h.set_metrics(metrics(N))
         _handles[key] = h
     return _handles[key]
@@ -82,7 +82,7 @@ def check_module(h, module, N, K, inputs, active, outs, oracle_fn, params, rng, 
         res["nl." + o] = e
         assert e < tol, ("NL", o, e)
     # TL
-    dp = {n: rnd(rng, N, K)[:, :inputs[n].shape[1]] * (np.abs(inputs[n]).mean() * pert_scale + 1e-30) for n in active}
+    dp = {n: rnd(rng, N, inputs[n].shape[1]) * (np.abs(inputs[n]).mean() * pert_scale + 1e-30) for n in active}
     traj = newtraj()
     pert = {n: dp[n].copy() for n in active}
     for o in onames:
