@@ -1,32 +1,9 @@
 // C ABI (include/fv3lm_b200.h): handle, metrics upload, module runner.
-#include "../../include/fv3lm_b200.h"
-#include "engine.h"
-#include "mosaic.h"
-#include "modules.h"
-#include <memory>
+#include "capi_internal.h"
 
 using namespace fv3lm;
 
-struct fv3lm_handle {
-  fv3lm_config cfg;
-  Device dv;
-  Mosaic mo;
-  std::vector<double> ak, bk;
-  std::map<std::string, double*> metric_dev;
-  std::string err;
-};
-
-static thread_local std::string g_err;
-
-#define FV3LM_TRY try {
-#define FV3LM_CATCH(h)                                            \
-  }                                                               \
-  catch (const std::exception& e) {                               \
-    g_err = e.what();                                             \
-    if (h) (h)->err = e.what();                                   \
-    return 1;                                                     \
-  }                                                               \
-  return 0;
+thread_local std::string fv3lm_g_err;
 
 // host [rows][NX] contiguous <-> device [rows][pitch]
 static void up2d(const Geom& g, double* d, const double* h, size_t rows) {
@@ -81,13 +58,22 @@ int fv3lm_destroy(fv3lm_handle* h) {
   FV3LM_TRY
   dev::sync();
   for (auto& kv : h->metric_dev) dev::free_(kv.second);
+  if (h->step) {
+    StepRunner* r = h->step;
+    for (auto& kv : r->io.inputs) { dev::free_(r->P.vals[kv.second].traj); dev::free_(r->P.vals[kv.second].pert); }
+    for (auto& kv : r->io.outputs) if (!r->io.is_input(kv.second)) { dev::free_(r->P.vals[kv.second].traj); dev::free_(r->P.vals[kv.second].pert); }
+    for (int f = 0; f < NFIELD; f++) dev::free_(r->pert[f]);
+    dev::free_(r->phis);
+    for (auto& s : r->slots) for (double* p : s) dev::free_(p);
+    delete r;
+  }
   h->mo.destroy();
   delete h;
   h = nullptr;
   FV3LM_CATCH(h)
 }
 
-const char* fv3lm_last_error(const fv3lm_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+const char* fv3lm_last_error(const fv3lm_handle* h) { return h ? h->err.c_str() : fv3lm_g_err.c_str(); }
 
 int fv3lm_set_metric(fv3lm_handle* h, const char* name, const double* host, int is_1d) {
   FV3LM_TRY

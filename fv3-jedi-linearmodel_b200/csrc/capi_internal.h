@@ -1,0 +1,42 @@
+// shared between capi.cu and step_api.cu
+#pragma once
+#include "../../include/fv3lm_b200.h"
+#include "engine.h"
+#include "mosaic.h"
+#include "modules.h"
+#include <map>
+#include <memory>
+
+constexpr int NFIELD = 10;
+
+struct StepRunner {
+  fv3lm::Program P;
+  fv3lm::ModuleIO io;
+  int nf = 8;                                     // prognostic fields: 8 hydrostatic, 10 with w, delz
+  std::map<std::string, int> in_id, out_id;
+  double* pert[NFIELD];                           // device-resident perturbation / adjoint state (compact)
+  double* phis = nullptr;
+  std::vector<std::vector<double*>> slots;        // device-resident trajectory window (compact)
+};
+
+struct fv3lm_handle {
+  fv3lm_config cfg;
+  fv3lm::Device dv;
+  fv3lm::Mosaic mo;
+  std::vector<double> ak, bk;
+  std::map<std::string, double*> metric_dev;
+  std::string err;
+  StepRunner* step = nullptr;
+};
+
+extern thread_local std::string fv3lm_g_err;
+
+#define FV3LM_TRY try {
+#define FV3LM_CATCH(h)                                            \
+  }                                                               \
+  catch (const std::exception& e) {                               \
+    fv3lm_g_err = e.what();                                       \
+    if (h) (h)->err = e.what();                                   \
+    return 1;                                                     \
+  }                                                               \
+  return 0;

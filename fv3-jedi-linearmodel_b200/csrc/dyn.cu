@@ -50,6 +50,7 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, co
   int mfx = -1, mfy = -1, cx = -1, cy = -1;
   for (int it = 1; it <= c.n_split; it++) {
     const std::string tg = tag + ".it" + std::to_string(it);
+    P.mark_segment();
     CswOut cs = build_c_sw(P, mo, delp, pt, u, v, w, dt2, true, c.nord, K, tg + ".csw");
     if (c.nord > 0) add_patch(P, "halo_divgd", &mo.h_corner, {cs.divg_d});
     int pkc = P.val(tg + ".pkc", K + 1), gz = P.val(tg + ".gzc", K + 1), pe0 = P.val(tg + ".pe_c", K + 1), pl0 = P.val(tg + ".peln_c", K + 1), pz0 = P.val(tg + ".pkz_c", K);

@@ -128,6 +128,54 @@ void Program::run(Mode mode) {
       for (int i : op.in) if (vals[i].last_use == n) release(i);
       for (int o : op.out) if (vals[o].last_use == n) release(o);
     }
+  } else if (!seg_start.empty()) {
+    // ---- segmented adjoint: checkpoint at segment boundaries, recompute one segment at a time
+    // (replaces the reference's global tape, utils/tapenade/adStack.c: only the values that
+    // cross a segment boundary stay in HBM, the rest is recomputed in the reverse sweep)
+    std::vector<int> seg_of(nop, 0);
+    {
+      int s = 0; size_t nb = 0;
+      for (int n = 0; n < nop; n++) { while (nb < seg_start.size() && seg_start[nb] <= n) { if (seg_start[nb] > 0) s++; nb++; } seg_of[n] = s; }
+    }
+    const int nseg = seg_of[nop - 1] + 1;
+    auto def_seg = [&](int id) { return vals[id].first_def < 0 ? -1 : seg_of[vals[id].first_def]; };
+    auto last_seg = [&](int id) { return vals[id].last_use < 0 ? -1 : seg_of[vals[id].last_use]; };
+    // pass 1: plain forward; segment-local values are freed at their last use, boundary-crossing ones stay
+    for (int n = 0; n < nop; n++) {
+      Op& op = ops[n];
+      for (int o : op.out) ensure_traj(o);
+      // the last segment is reversed first: keep it whole and let its patch ops save what they overwrite
+      op.run(*this, op, seg_of[n] == nseg - 1 ? MODE_ADFWD : MODE_NL);
+      if (seg_of[n] == nseg - 1) continue;
+      for (int i : op.in) if (vals[i].last_use == n && def_seg(i) == seg_of[n]) release(i);
+      for (int o : op.out) if (vals[o].last_use == n && def_seg(o) == seg_of[n]) release(o);
+    }
+    for (int s = nseg - 1; s >= 0; s--) {
+      int n0 = 0, n1 = nop - 1;
+      while (seg_of[n0] != s) n0++;
+      while (seg_of[n1] != s) n1--;
+      // recompute the segment keeping every value (patch ops save what they overwrite)
+      for (int n = n0; n <= n1 && s != nseg - 1; n++) {
+        Op& op = ops[n];
+        for (int o : op.out) ensure_traj(o);
+        op.run(*this, op, MODE_ADFWD);
+      }
+      for (int n = n1; n >= n0; n--) {
+        Op& op = ops[n];
+        bool any_out = false;
+        for (int o : op.out) if (vals[o].active && vals[o].pert) any_out = true;
+        if (any_out || op.inplace) {
+          for (int o : op.out) ensure_pert(o, true);
+          for (int i : op.in) ensure_pert(i, true);
+          op.run(*this, op, MODE_AD);
+        }
+        if (!op.inplace)
+          for (int o : op.out) if (vals[o].first_def == n) release(o);
+      }
+      (void)last_seg;
+    }
+    for (int id = 0; id < (int)vals.size(); id++)
+      if (!vals[id].external && vals[id].first_def < 0) release(id);
   } else {
     // forward sweep, keep everything ("device checkpoint arena")
     for (int n = 0; n < nop; n++) {

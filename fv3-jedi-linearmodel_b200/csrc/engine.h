@@ -283,6 +283,8 @@ struct Program {
   std::vector<Value> vals;
   std::vector<Op> ops;
   std::string name;
+  std::vector<int> seg_start;        // op indices where a recompute segment of the adjoint begins
+  void mark_segment() { seg_start.push_back((int)ops.size()); }
 
   int val(const std::string& nm, int nk, bool external = false) {
     Value v; v.name = nm; v.nk = nk; v.external = external;

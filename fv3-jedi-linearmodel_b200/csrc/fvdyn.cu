@@ -229,8 +229,10 @@ FvOut build_fv_dynamics(Program& P, Mosaic& mo, const DynConfig& c, const std::v
     const int dp1 = delp;
     DynState ds; ds.u = u; ds.v = v; ds.w = w; ds.delz = -1; ds.pt = pt; ds.delp = delp; ds.phis = s.phis;
     DynOut d = build_dyn_core(P, mo, cd, ds, tg);
+    P.mark_segment();
     for (int& x : q) add_patch(P, "halo_q", &mo.h_center, {x});
     q = build_tracer_2d(P, mo, q, dp1, d.mfx, d.mfy, d.cx, d.cy, c.hord_tr, tg + ".trc");
+    P.mark_segment();
     RemapOut r = build_remap(P, mo, c, ak, bk, d.pe, d.pk, d.peln, d.pt, q, d.u, d.v, n_map == c.k_split, tg + ".rm");
     u = r.u; v = r.v; pt = r.pt; delp = r.delp; q = r.q;
   }

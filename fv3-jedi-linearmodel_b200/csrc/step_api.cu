@@ -1,0 +1,251 @@
+// Step-level C ABI: the drop-in for fv3jedi_lm_dynamics_mod's step_nl / step_tl / step_ad
+// (src/dynamics/fv3jedi_lm_dynamics_mod.F90:268/:347/:460) with a device-resident trajectory
+// window and device-resident perturbation state.
+#include "../../include/fv3lm_b200.h"
+#include "capi_internal.h"
+#include "fvdyn.h"
+#include "modules.h"
+
+using namespace fv3lm;
+
+namespace {
+
+const char* kFieldNames[NFIELD] = {"u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz"};
+
+// compact [tile][k][N][N]  <->  halo'd [tile][k][NY][pitch]
+struct KExpand {
+  Geom g; const double* c; double* h; int nk;
+  DEV void operator()(int ii, int jj, int z) const {
+    int i = ii - (g.ng - 1), j = jj - (g.ng - 1);
+    double v = 0.0;
+    if (i >= 1 && i <= g.N && j >= 1 && j <= g.N) v = c[((size_t)z * g.N + (j - 1)) * g.N + (i - 1)];
+    h[(size_t)z * g.slab + (size_t)jj * g.pitch + ii] = v;
+  }
+};
+struct KCompact {
+  Geom g; double* c; const double* h; int nk;
+  DEV void operator()(int ii, int jj, int z) const {
+    int i = ii - (g.ng - 1), j = jj - (g.ng - 1);
+    if (i >= 1 && i <= g.N && j >= 1 && j <= g.N) c[((size_t)z * g.N + (j - 1)) * g.N + (i - 1)] = h[(size_t)z * g.slab + (size_t)jj * g.pitch + ii];
+  }
+};
+
+size_t compact_doubles(const Geom& g, int nk) { return (size_t)g.ntile * nk * g.N * g.N; }
+
+void ensure_runner(fv3lm_handle* h) {
+  if (h->step) return;
+  auto* r = new StepRunner();
+  const Geom& g = h->dv.g;
+  r->P.dv = &h->dv; r->P.name = "step";
+  ModuleParams prm; prm.cfg = &h->cfg; prm.ak = &h->ak; prm.bk = &h->bk;
+  prm.v["bdt"] = h->cfg.dt;
+  if (h->ak.empty()) throw std::runtime_error("fv3lm: ak/bk were not given to fv3lm_create");
+  build_module("step", r->P, h->mo, r->io, prm);
+  r->nf = h->cfg.hydrostatic ? 8 : 10;
+  for (auto& kv : r->io.inputs) {
+    Value& v = r->P.vals[kv.second];
+    v.traj = (double*)dev::alloc(r->P.val_doubles(kv.second) * sizeof(double));
+    dev::zero(v.traj, r->P.val_doubles(kv.second) * sizeof(double));
+    v.pert = (double*)dev::alloc(r->P.val_doubles(kv.second) * sizeof(double));
+    dev::zero(v.pert, r->P.val_doubles(kv.second) * sizeof(double));
+    r->in_id[kv.first] = kv.second;
+  }
+  for (auto& kv : r->io.outputs) {
+    Value& v = r->P.vals[kv.second];
+    if (!v.traj) { v.traj = (double*)dev::alloc(r->P.val_doubles(kv.second) * sizeof(double)); dev::zero(v.traj, r->P.val_doubles(kv.second) * sizeof(double)); }
+    if (!v.pert) { v.pert = (double*)dev::alloc(r->P.val_doubles(kv.second) * sizeof(double)); dev::zero(v.pert, r->P.val_doubles(kv.second) * sizeof(double)); }
+    r->out_id[kv.first] = kv.second;
+  }
+  for (int f = 0; f < NFIELD; f++) { r->pert[f] = nullptr; }
+  for (int f = 0; f < r->nf; f++) r->pert[f] = (double*)dev::alloc(compact_doubles(g, g.K) * sizeof(double));
+  r->phis = (double*)dev::alloc(compact_doubles(g, 1) * sizeof(double));
+  dev::zero(r->phis, compact_doubles(g, 1) * sizeof(double));
+  h->step = r;
+}
+
+double** field_ptr(fv3lm_fields* f, int n) {
+  switch (n) {
+    case 0: return &f->u; case 1: return &f->v; case 2: return &f->t; case 3: return &f->delp; case 4: return &f->qv;
+    case 5: return &f->ql; case 6: return &f->qi; case 7: return &f->o3; case 8: return &f->w; default: return &f->delz;
+  }
+}
+
+double* slot_field(fv3lm_handle* h, int slot, int f) {
+  StepRunner* r = h->step;
+  const Geom& g = h->dv.g;
+  if (slot < 0) throw std::runtime_error("fv3lm: negative trajectory slot");
+  if ((int)r->slots.size() <= slot) r->slots.resize(slot + 1);
+  auto& s = r->slots[slot];
+  if (s.empty()) { s.assign(NFIELD, nullptr); for (int n = 0; n < r->nf; n++) s[n] = (double*)dev::alloc(compact_doubles(g, g.K) * sizeof(double)); }
+  return s[f];
+}
+
+void expand(fv3lm_handle* h, const double* c, double* hal, int nk) { const Geom& g = h->dv.g; launch3d(KExpand{g, c, hal, nk}, g.NX, g.NY, g.ntile * nk); }
+void compact(fv3lm_handle* h, double* c, const double* hal, int nk) { const Geom& g = h->dv.g; launch3d(KCompact{g, c, hal, nk}, g.NX, g.NY, g.ntile * nk); }
+
+// load the trajectory of `slot` (and phis) into the program's input arrays
+void load_traj(fv3lm_handle* h, int slot) {
+  StepRunner* r = h->step; const Geom& g = h->dv.g;
+  for (int f = 0; f < NFIELD; f++) {
+    auto it = r->in_id.find(kFieldNames[f]);
+    if (it == r->in_id.end()) continue;
+    Value& v = r->P.vals[it->second];
+    if (f < r->nf) expand(h, slot_field(h, slot, f), v.traj, g.K);
+    else dev::zero(v.traj, r->P.val_doubles(it->second) * sizeof(double));
+  }
+  expand(h, r->phis, r->P.vals[r->in_id["phis"]].traj, 1);
+}
+
+void run_step(fv3lm_handle* h, int slot, int mode) {
+  StepRunner* r = h->step; const Geom& g = h->dv.g;
+  load_traj(h, slot);
+  for (auto& kv : r->in_id) r->P.vals[kv.second].active = false;
+  if (mode == MODE_TL) {
+    for (int f = 0; f < r->nf; f++) { Value& v = r->P.vals[r->in_id[kFieldNames[f]]]; v.active = true; expand(h, r->pert[f], v.pert, g.K); }
+    r->P.run(MODE_TL);
+    for (int f = 0; f < r->nf; f++) compact(h, r->pert[f], r->P.vals[r->out_id[std::string(kFieldNames[f]) + "_n"]].pert, g.K);
+  } else if (mode == MODE_AD) {
+    for (int f = 0; f < r->nf; f++) {
+      Value& vi = r->P.vals[r->in_id[kFieldNames[f]]]; vi.active = true;
+      dev::zero(vi.pert, r->P.val_doubles(r->in_id[kFieldNames[f]]) * sizeof(double));
+      expand(h, r->pert[f], r->P.vals[r->out_id[std::string(kFieldNames[f]) + "_n"]].pert, g.K);
+    }
+    r->P.run(MODE_AD);
+    for (int f = 0; f < r->nf; f++) compact(h, r->pert[f], r->P.vals[r->in_id[kFieldNames[f]]].pert, g.K);
+  } else {
+    r->P.run(MODE_NL);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int fv3lm_set_phis(fv3lm_handle* h, const double* phis) {
+  FV3LM_TRY
+  ensure_runner(h);
+  dev::h2d(h->step->phis, phis, compact_doubles(h->dv.g, 1) * sizeof(double));
+  dev::sync();
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_traj_set(fv3lm_handle* h, int slot, const fv3lm_fields* traj) {
+  FV3LM_TRY
+  ensure_runner(h);
+  for (int f = 0; f < h->step->nf; f++) {
+    double* src = *field_ptr(const_cast<fv3lm_fields*>(traj), f);
+    if (!src) throw std::runtime_error(std::string("fv3lm_traj_set: missing field ") + kFieldNames[f]);
+    dev::h2d(slot_field(h, slot, f), src, compact_doubles(h->dv.g, h->dv.g.K) * sizeof(double));
+  }
+  dev::sync();
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_traj_get(fv3lm_handle* h, int slot, fv3lm_fields* traj) {
+  FV3LM_TRY
+  ensure_runner(h);
+  for (int f = 0; f < h->step->nf; f++) { double* dst = *field_ptr(traj, f); if (dst) dev::d2h(dst, slot_field(h, slot, f), compact_doubles(h->dv.g, h->dv.g.K) * sizeof(double)); }
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_step_nl(fv3lm_handle* h, int slot_in, int slot_out) {
+  FV3LM_TRY
+  ensure_runner(h);
+  run_step(h, slot_in, MODE_NL);
+  StepRunner* r = h->step;
+  for (int f = 0; f < r->nf; f++) compact(h, slot_field(h, slot_out, f), r->P.vals[r->out_id[std::string(kFieldNames[f]) + "_n"]].traj, h->dv.g.K);
+  dev::sync();
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_pert_upload(fv3lm_handle* h, const fv3lm_fields* pert) {
+  FV3LM_TRY
+  ensure_runner(h);
+  for (int f = 0; f < h->step->nf; f++) {
+    double* src = *field_ptr(const_cast<fv3lm_fields*>(pert), f);
+    if (!src) throw std::runtime_error(std::string("fv3lm_pert_upload: missing field ") + kFieldNames[f]);
+    dev::h2d(h->step->pert[f], src, compact_doubles(h->dv.g, h->dv.g.K) * sizeof(double));
+  }
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_pert_download(fv3lm_handle* h, fv3lm_fields* pert) {
+  FV3LM_TRY
+  ensure_runner(h);
+  for (int f = 0; f < h->step->nf; f++) { double* dst = *field_ptr(pert, f); if (dst) dev::d2h(dst, h->step->pert[f], compact_doubles(h->dv.g, h->dv.g.K) * sizeof(double)); }
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_step_tl_dev(fv3lm_handle* h, int slot) {
+  FV3LM_TRY
+  ensure_runner(h);
+  run_step(h, slot, MODE_TL);
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_step_ad_dev(fv3lm_handle* h, int slot) {
+  FV3LM_TRY
+  ensure_runner(h);
+  run_step(h, slot, MODE_AD);
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_step_tl(fv3lm_handle* h, int slot, fv3lm_fields* pert) {
+  int rc = fv3lm_pert_upload(h, pert);
+  if (!rc) rc = fv3lm_step_tl_dev(h, slot);
+  if (!rc) rc = fv3lm_pert_download(h, pert);
+  return rc;
+}
+
+int fv3lm_step_ad(fv3lm_handle* h, int slot, fv3lm_fields* pert) {
+  int rc = fv3lm_pert_upload(h, pert);
+  if (!rc) rc = fv3lm_step_ad_dev(h, slot);
+  if (!rc) rc = fv3lm_pert_download(h, pert);
+  return rc;
+}
+
+// Timed loop on the library's own stream (CUDA events): `iters` repetitions of one TL step followed
+// by one AD step on resident data.  ms[0] = TL ms/step, ms[1] = AD ms/step.  Used by bench.py.
+int fv3lm_time_steps(fv3lm_handle* h, int slot, int warmup, int iters, double* ms) {
+  FV3LM_TRY
+  ensure_runner(h);
+#ifndef FV3LM_HOST_EMU
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  for (int n = 0; n < warmup; n++) { run_step(h, slot, MODE_TL); run_step(h, slot, MODE_AD); }
+  dev::sync();
+  double tl = 0.0, ad = 0.0;
+  for (int n = 0; n < iters; n++) {
+    cudaEventRecord(e0, dev::stream());
+    run_step(h, slot, MODE_TL);
+    cudaEventRecord(e1, dev::stream());
+    run_step(h, slot, MODE_AD);
+    cudaEventRecord(e2, dev::stream());
+    cudaEventSynchronize(e2);
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2);
+    tl += a; ad += b;
+  }
+  ms[0] = tl / iters; ms[1] = ad / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+#else
+  (void)slot; (void)warmup; (void)iters; ms[0] = ms[1] = 0.0;
+  throw std::runtime_error("fv3lm_time_steps: host emulation build has no timer");
+#endif
+  FV3LM_CATCH(h)
+}
+
+// structural statistics of a module's program: ops, values, bytes if every value is kept (AD)
+int fv3lm_program_stats(fv3lm_handle* h, const char* module, double* out) {
+  FV3LM_TRY
+  ModuleParams prm; prm.cfg = &h->cfg; prm.ak = &h->ak; prm.bk = &h->bk; prm.v["bdt"] = h->cfg.dt;
+  Program P; P.dv = &h->dv; ModuleIO io;
+  build_module(module, P, h->mo, io, prm);
+  double bytes = 0;
+  for (size_t i = 0; i < P.vals.size(); i++) bytes += (double)P.val_doubles((int)i) * 8.0;
+  int npatch = 0; for (auto& o : P.ops) npatch += o.inplace ? 1 : 0;
+  out[0] = (double)P.ops.size(); out[1] = (double)P.vals.size(); out[2] = bytes; out[3] = npatch;
+  FV3LM_CATCH(h)
+}
+
+}  // extern "C"

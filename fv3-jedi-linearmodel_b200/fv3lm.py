@@ -27,7 +27,13 @@ class Config(C.Structure):
                 ("grav", C.c_double), ("do_vort_damp", C.c_int), ("reserved", C.c_int * 16)]
 
 
-EXPORTS = ["fv3lm_create", "fv3lm_destroy", "fv3lm_last_error", "fv3lm_set_metric", "fv3lm_set_metric_scalar",
+class Fields(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_double)) for n in ("u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz")]
+
+
+EXPORTS = ["fv3lm_set_phis", "fv3lm_traj_set", "fv3lm_traj_get", "fv3lm_step_nl", "fv3lm_step_tl", "fv3lm_step_ad",
+           "fv3lm_pert_upload", "fv3lm_pert_download", "fv3lm_step_tl_dev", "fv3lm_step_ad_dev", "fv3lm_time_steps",
+           "fv3lm_program_stats", "fv3lm_create", "fv3lm_destroy", "fv3lm_last_error", "fv3lm_set_metric", "fv3lm_set_metric_scalar",
            "fv3lm_module_run", "fv3lm_module_list", "fv3lm_launch_count", "fv3lm_pool_peak_bytes", "fv3lm_sync"]
 
 METRICS_2D = ["area", "rarea", "area_c", "rarea_c", "dx", "dy", "rdx", "rdy", "dxa", "dya", "rdxa", "rdya", "dxc",
@@ -132,6 +138,73 @@ class FV3LM:
         c_pv = (C.c_double * max(1, len(pn)))(*[float(params[k]) for k in pn]) if pn else (C.c_double * 1)()
         rc = self.lib.fv3lm_module_run(self.h, module.encode(), int(mode), n, c_names, c_traj, c_pert, len(pn), c_pn, c_pv)
         self._check(rc, "module_run(%s)" % module)
+
+    # ---- step-level API (mirror of fv3jedi_lm_dynamics_mod step_nl / step_tl / step_ad) ----
+    FIELDS = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz"]
+
+    def _fields(self, d):
+        """d: dict name -> float64 ndarray [6, K, N, N] (compute domain).  Returns (struct, keepalive)"""
+        dp = C.POINTER(C.c_double)
+        st = Fields()
+        keep = []
+        for n in self.FIELDS:
+            if n in d:
+                a = d[n]
+                assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], n
+                setattr(st, n, a.ctypes.data_as(dp)); keep.append(a)
+            else:
+                setattr(st, n, C.cast(None, dp))
+        return st, keep
+
+    def set_phis(self, phis):
+        a = np.ascontiguousarray(phis, dtype=np.float64)
+        self._check(self.lib.fv3lm_set_phis(self.h, a.ctypes.data_as(C.POINTER(C.c_double))), "set_phis")
+
+    def traj_set(self, slot, traj):
+        st, _k = self._fields(traj)
+        self._check(self.lib.fv3lm_traj_set(self.h, int(slot), C.byref(st)), "traj_set")
+
+    def traj_get(self, slot, traj):
+        st, _k = self._fields(traj)
+        self._check(self.lib.fv3lm_traj_get(self.h, int(slot), C.byref(st)), "traj_get")
+
+    def step_nl(self, slot_in, slot_out):
+        self._check(self.lib.fv3lm_step_nl(self.h, int(slot_in), int(slot_out)), "step_nl")
+
+    def step_tl(self, slot, pert):
+        st, _k = self._fields(pert)
+        self._check(self.lib.fv3lm_step_tl(self.h, int(slot), C.byref(st)), "step_tl")
+
+    def step_ad(self, slot, pert):
+        st, _k = self._fields(pert)
+        self._check(self.lib.fv3lm_step_ad(self.h, int(slot), C.byref(st)), "step_ad")
+
+    def pert_upload(self, pert):
+        st, _k = self._fields(pert)
+        self._check(self.lib.fv3lm_pert_upload(self.h, C.byref(st)), "pert_upload")
+
+    def pert_download(self, pert):
+        st, _k = self._fields(pert)
+        self._check(self.lib.fv3lm_pert_download(self.h, C.byref(st)), "pert_download")
+
+    def step_tl_dev(self, slot):
+        self._check(self.lib.fv3lm_step_tl_dev(self.h, int(slot)), "step_tl_dev")
+
+    def step_ad_dev(self, slot):
+        self._check(self.lib.fv3lm_step_ad_dev(self.h, int(slot)), "step_ad_dev")
+
+    def time_steps(self, slot, warmup, iters):
+        ms = (C.c_double * 2)()
+        self._check(self.lib.fv3lm_time_steps(self.h, int(slot), int(warmup), int(iters), ms), "time_steps")
+        return float(ms[0]), float(ms[1])
+
+    def program_stats(self, module):
+        out = (C.c_double * 4)()
+        self._check(self.lib.fv3lm_program_stats(self.h, module.encode(), out), "program_stats")
+        return dict(ops=int(out[0]), values=int(out[1]), bytes_all_values=float(out[2]), patch_ops=int(out[3]))
+
+    def sync(self):
+        self._check(self.lib.fv3lm_sync(self.h), "sync")
 
     def launch_count(self):
         return int(self.lib.fv3lm_launch_count())

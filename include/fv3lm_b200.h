@@ -65,6 +65,28 @@ int fv3lm_module_run(fv3lm_handle* h, const char* module, int mode, int nfields,
                      const double* pvals);
 const char* fv3lm_module_list(void);
 
+/* ---- step-level API: the drop-in for fv3jedi_lm_dynamics_mod step_nl/step_tl/step_ad ----------
+ * (src/dynamics/fv3jedi_lm_dynamics_mod.F90:268, :347, :460).  Field arrays are the compute
+ * domain only, (isc:iec, jsc:jec, npz) per tile in Fortran order = C order [tile][k][j][i],
+ * exactly the members of fv3jedi_lm_traj / fv3jedi_lm_pert (utils/fv3jedi_lm_utils_mod.F90:35-54).
+ * w, delz are read only when the handle is non-hydrostatic.  The trajectory is kept in a
+ * device-resident window indexed by `slot` (one slot per time level of the assimilation window). */
+typedef struct fv3lm_fields { double *u, *v, *t, *delp, *qv, *ql, *qi, *o3, *w, *delz; } fv3lm_fields;
+int fv3lm_set_phis(fv3lm_handle* h, const double* phis);                       /* [tile][j][i] */
+int fv3lm_traj_set(fv3lm_handle* h, int slot, const fv3lm_fields* traj);       /* host -> window slot */
+int fv3lm_traj_get(fv3lm_handle* h, int slot, fv3lm_fields* traj);
+int fv3lm_step_nl(fv3lm_handle* h, int slot_in, int slot_out);                 /* slot_out = N(slot_in), on device */
+int fv3lm_step_tl(fv3lm_handle* h, int slot, fv3lm_fields* pert);              /* pert in/out on the host */
+int fv3lm_step_ad(fv3lm_handle* h, int slot, fv3lm_fields* pert);              /* adjoint variables in/out */
+/* device-resident increments: a whole window without PCIe round trips */
+int fv3lm_pert_upload(fv3lm_handle* h, const fv3lm_fields* pert);
+int fv3lm_pert_download(fv3lm_handle* h, fv3lm_fields* pert);
+int fv3lm_step_tl_dev(fv3lm_handle* h, int slot);
+int fv3lm_step_ad_dev(fv3lm_handle* h, int slot);
+/* bench helpers: CUDA-event timing of TL+AD steps on resident data; program statistics */
+int fv3lm_time_steps(fv3lm_handle* h, int slot, int warmup, int iters, double* ms_tl_ad);
+int fv3lm_program_stats(fv3lm_handle* h, const char* module, double* out4);
+
 /* counters for bench.py */
 long long fv3lm_launch_count(void);
 double fv3lm_pool_peak_bytes(const fv3lm_handle* h);

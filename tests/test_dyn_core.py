@@ -7,11 +7,11 @@ from oracle.dyn_core import halo_of
 from common import metrics, ograd, handle, rnd, check_module
 
 RD = 8314.47 / 28.965
-CFG = dict(nord=1, d2_bg=0.015, d2_bg_k1=4.0, d2_bg_k2=2.0, n_sponge=0, vtdm4=0.0005, do_vort_damp=True, dddmp=0.2, d4_bg=0.15,
+CFG = dict(nord=1, d2_bg=0.015, d2_bg_k1=0.2, d2_bg_k2=0.1, n_sponge=0, vtdm4=0.0005, do_vort_damp=True, dddmp=0.2, d4_bg=0.15,
            hord_mt=2, hord_vt=2, hord_tm=2, hord_dp=2, n_sponge_ord=0, ptop=100.0, akap=2.0 / 7.0, cp_air=3.5 * RD)
 
 
-def smooth(rng, N, K, nsm=2):
+def smooth(rng, N, K, nsm=4):
     """white noise smoothed a little so that transported fields stay physical"""
     a = rnd(rng, N, K)
     for _ in range(nsm):
@@ -23,16 +23,16 @@ def hydro_state(N, K, seed):
     """a resting, nearly isothermal atmosphere + noise; halos filled consistently"""
     rng = np.random.default_rng(seed)
     halo, getb = halo_of(N)
-    ps = 1.0e5 + 300.0 * smooth(rng, N, 1)
+    ps = 1.0e5 + 100.0 * smooth(rng, N, 1)
     ptop = CFG["ptop"]
     bk = np.linspace(0.0, 1.0, K + 1); ak = ptop * (1.0 - bk)
     pe = ak[None, :, None, None] + bk[None, :, None, None] * ps
     delp = pe[:, 1:] - pe[:, :-1]
     pm = 0.5 * (pe[:, 1:] + pe[:, :-1])
-    T = 280.0 + 3.0 * smooth(rng, N, K)
+    T = 280.0 + 1.0 * smooth(rng, N, K)
     pt = T / (pm / 1.0e5) ** CFG["akap"]               # potential temperature: cp*pt*dpk is the geopotential increment
-    u = 8.0 * smooth(rng, N, K); v = 8.0 * smooth(rng, N, K)
-    phis = 200.0 * 9.80665 * smooth(rng, N, 1)
+    u = 5.0 * smooth(rng, N, K); v = 5.0 * smooth(rng, N, K)
+    phis = 50.0 * 9.80665 * smooth(rng, N, 1)
     f = dict(u=u, v=v, pt=pt, delp=delp, w=np.zeros_like(u), phis=phis)
     t = {k: torch.from_numpy(a) for k, a in f.items()}
     t["delp"] = halo.scalar(t["delp"]); t["pt"] = halo.scalar(t["pt"]); t["phis"] = halo.scalar(t["phis"])

@@ -1,0 +1,90 @@
+"""Step-level C ABI (fv3lm_step_nl / step_tl / step_ad with the device-resident trajectory
+window): consistency with the module-level path, the dot-product (adjoint) test and a
+Taylor test of the TL against finite differences of step_nl."""
+import numpy as np
+import pytest
+import torch
+import fv3lm
+from oracle import fv_dynamics as ofv
+from oracle.cubed_sphere import R
+from common import metrics, ograd, handle, rnd
+from test_dyn_core import CFG
+from test_fv_dynamics import eta, api_state, ZVIR
+
+ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"]
+
+
+def make(emu, N=12, K=4, n_split=2, k_split=1):
+    ptop = CFG["ptop"]
+    ak, bk = eta(K, ptop)
+    f, rng = api_state(N, K, 41, ak, bk)
+    kw = dict(n_split=n_split, k_split=k_split, dt=900.0, ptop=ptop, d2_bg_k1=CFG["d2_bg_k1"], d2_bg_k2=CFG["d2_bg_k2"],
+              kappa=CFG["akap"], cp=CFG["cp_air"], zvir=ZVIR)
+    h = handle(N, K, emu, ak, bk, **kw)
+    C = (slice(None), slice(None), R(1, N), R(1, N))
+    comp = {k: np.ascontiguousarray(f[k][C]) for k in ACT}
+    h.set_phis(np.ascontiguousarray(f["phis"][:, 0][:, R(1, N), R(1, N)]))
+    h.traj_set(0, comp)
+    cfg = dict(CFG); cfg.update(zvir=ZVIR, hydrostatic=True, k_split=k_split, n_split=n_split, dt=900.0, hord_tr=2)
+    return h, f, comp, rng, cfg, ak, bk
+
+
+def _run(emu):
+    N, K = 12, 4
+    h, f, comp, rng, cfg, ak, bk = make(emu, N, K)
+    g = ograd(N)
+    # ---- step_nl against the oracle
+    h.step_nl(0, 1)
+    out = {k: np.zeros_like(comp[k]) for k in ACT}
+    h.traj_get(1, out)
+    full = {k: torch.from_numpy(f[k]) for k in ACT}
+    o = ofv.step_nl(full, g, ak, bk, cfg, torch.from_numpy(f["phis"]))
+    C = (slice(None), slice(None), R(1, N), R(1, N))
+    for k in ACT:
+        ref = o[k][C].numpy()
+        assert np.abs(out[k] - ref).max() <= 2e-10 * np.abs(ref).max(), k
+    # ---- dot-product test  <M dx, y> = <dx, M^T y>
+    dx = {k: rng.standard_normal(comp[k].shape) * (np.abs(comp[k]).mean() * 1e-3) for k in ACT}
+    y = {k: rng.standard_normal(comp[k].shape) / (np.abs(comp[k]).mean() + 1e-30) for k in ACT}
+    mdx = {k: dx[k].copy() for k in ACT}
+    h.step_tl(0, mdx)
+    mty = {k: y[k].copy() for k in ACT}
+    h.step_ad(0, mty)
+    lhs = sum((mdx[k] * y[k]).sum() for k in ACT)
+    rhs = sum((dx[k] * mty[k]).sum() for k in ACT)
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs)), (lhs, rhs)
+    # ---- Taylor test:  || N(x + e dx) - N(x) - e M dx || / || e M dx ||  = O(e)
+    base = {k: np.zeros_like(comp[k]) for k in ACT}
+    h.traj_get(1, base)
+    ratios = []
+    for eps in (1.0, 1e-1, 1e-2, 1e-3):
+        xp = {k: comp[k] + eps * dx[k] for k in ACT}
+        h.traj_set(2, xp)
+        h.step_nl(2, 3)
+        outp = {k: np.zeros_like(comp[k]) for k in ACT}
+        h.traj_get(3, outp)
+        num = 0.0; den = 0.0
+        for k in ACT:
+            sc = 1.0 / (np.abs(base[k]).max() + 1e-300)
+            num += (((outp[k] - base[k]) - eps * mdx[k]) * sc) ** 2 .sum() if False else ((((outp[k] - base[k]) - eps * mdx[k]) * sc) ** 2).sum()
+            den += ((eps * mdx[k] * sc) ** 2).sum()
+        ratios.append(np.sqrt(num / den))
+    # residual must shrink linearly with eps (second-order remainder)
+    assert ratios[1] < 0.2 * ratios[0] and ratios[2] < 0.2 * ratios[1] and ratios[3] < 0.2 * ratios[2], ratios
+    return dict(dot=abs(lhs - rhs) / max(abs(lhs), abs(rhs)), taylor=ratios)
+
+
+def test_step_api_emu():
+    print(_run(True))
+
+
+def test_program_stats_emu():
+    h, *_ = make(True)
+    s = h.program_stats("step")
+    print(s)
+    assert s["ops"] > 100 and s["values"] > 100
+
+
+@pytest.mark.gpu
+def test_step_api_gpu():
+    print(_run(False))
