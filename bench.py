@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py -- TL+AD model steps per second of the FV3 linearized dynamics step.
+
+A "step" = one step_tl followed by one step_ad of length dt (k_split x n_split acoustic
+sub-steps + tracer transport + vertical remap) on synthetic C180 L72 input.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--res 180] [--npz 72]
+
+Rank 0 prints ONE JSON line.  `value` is measured with the inputs resident in HBM (CUDA
+events on the library's stream); `e2e` goes through the host-pointer C ABI (step_tl/step_ad)
+with the H2D/D2H copies of trajectory and increments inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "fv3-jedi-linearmodel_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FIELDS_H = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"]
+ZVIR = (8314.47 / 18.015) / (8314.47 / 28.965) - 1.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class Clocks(threading.Thread):
+    """samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)"""
+
+    def __init__(self):
+        super().__init__(daemon=True)
+        self.stop = False
+        self.rows = []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", "0", "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().splitlines()[0]
+                self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
+
+
+def model_config(N, K, hydrostatic, dt):
+    from synth import state as S
+    return dict(n_split=S.n_split_auto(N, dt, hydrostatic), k_split=1, dt=dt, ptop=1.0, d2_bg_k1=0.20, d2_bg_k2=0.10,
+                hydrostatic=int(hydrostatic), zvir=ZVIR)
+
+
+def alg_passes(n_split, hydrostatic):
+    """SURVEY 8(d) algorithmic array passes per model step (TL, AD)"""
+    if hydrostatic:
+        return n_split * 126 + 104, n_split * 159 + 131
+    return n_split * 170 + 104, n_split * 216 + 131
+
+
+def pinned(shape):
+    import torch
+    return torch.empty(shape, dtype=torch.float64, pin_memory=torch.cuda.is_available()).numpy()
+
+
+def run_gpu(args):
+    import torch
+    import fv3lm
+    from synth import grid as G, state as S
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    N, K = args.res, args.npz
+    hydro = not args.nonhydro
+    dt = 450.0 * 180.0 / N
+    mc = model_config(N, K, hydro, dt)
+    ak, bk = S.eta_levels(K)
+    M = G.build_metrics(N)
+    cfg = fv3lm.default_config(N, K, **mc)
+    h = fv3lm.FV3LM(cfg, ak, bk)
+    h.set_metrics(M)
+    st = S.make_state(M, K, ak, bk, hydrostatic=hydro)
+    fields = [f for f in h.FIELDS if f in st]
+    h.set_phis(st["phis"])
+    traj = {k: st[k] for k in fields}
+    h.traj_set(0, traj)
+    pert = S.make_pert(st, 20261018)
+    h.pert_upload({k: pert[k] for k in fields})
+    # ---- device-resident timing (CUDA events inside the library, on its stream)
+    ck = Clocks(); ck.start()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(); torch.cuda.synchronize()
+    l0 = h.launch_count()
+    ms_tl, ms_ad = h.time_steps(0, args.warmup, args.steps)
+    launches = (h.launch_count() - l0) // (args.warmup + args.steps) * args.steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_tl, ms_ad], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_tl, ms_ad = float(t[0]), float(t[1])
+    ck.stop = True; ck.join()
+    ms_step = ms_tl + ms_ad
+    # ---- end to end through the host-pointer ABI: trajectory + increments cross PCIe every step
+    hp = {k: pinned(st[k].shape) for k in fields}
+    ht = {k: pinned(st[k].shape) for k in fields}
+    for k in fields:
+        hp[k][...] = pert[k]; ht[k][...] = st[k]
+    ne = max(1, min(args.steps, 3))
+    h.traj_set(0, ht); h.step_tl(0, hp); h.step_ad(0, hp)     # warm
+    t0 = time.perf_counter()
+    for _ in range(ne):
+        h.traj_set(0, ht)
+        h.step_tl(0, hp)
+        h.traj_set(0, ht)
+        h.step_ad(0, hp)
+    h.sync()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / ne
+    fb = sum(st[k].nbytes for k in fields)
+    # ---- per-kernel profile (separate, serialised pass) -> dominant kernel roofline
+    rows = []
+    buf = __import__("ctypes").create_string_buffer(1 << 20)
+    h._check(h.lib.fv3lm_profile_steps(h.h, 0, 1, buf, len(buf)), "profile")
+    for line in buf.value.decode().splitlines():
+        nm, n, ms, b = line.split()
+        rows.append((nm, int(n), float(ms), float(b)))
+    rows.sort(key=lambda r: -r[2])
+    tot = sum(r[2] for r in rows)
+    peak, pk_src = peaks()
+    top = rows[0]
+    ach = top[3] / top[1] / (top[2] / top[1] * 1e-3) / 1e9 if top[2] > 0 else 0.0
+    field_bytes = 6.0 * N * N * K * 8.0
+    p_tl, p_ad = alg_passes(mc["n_split"], hydro)
+    step_alg_gb = (p_tl + p_ad) * field_bytes / 1e9
+    out = {
+        "metric": "TL+AD model steps/sec", "value": world * 1000.0 / ms_step, "unit": "TL+AD step pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "replicas" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C%d L%d %s dynamics-only TL+AD step, dt=%gs, n_split=%d, k_split=1, nq=4, linear schemes (hord=2, kord=17), whole sphere on one GPU"
+                               % (N, K, "hydrostatic" if hydro else "non-hydrostatic", dt, mc["n_split"]),
+                   "l2": "working set (%.1f GB of fields per sweep) far exceeds the 126 MB L2" % (60 * field_bytes / 1e9),
+                   "multi_gpu": "N>1 runs independent replicas (tile sharding not built yet)" if world > 1 else "single GPU"},
+        "tl_ms": ms_tl, "ad_ms": ms_ad, "tl_steps_per_s": 1000.0 / ms_tl, "ad_steps_per_s": 1000.0 / ms_ad,
+        "gpu_launches": int(launches),
+        "clocks": ck.summary(),
+        "e2e": {"value": 1000.0 / e2e_ms, "unit": "TL+AD step pairs/s", "h2d_bytes_per_step": int(4 * fb), "d2h_bytes_per_step": int(2 * fb),
+                "note": "trajectory (8 fields) re-sent before each of step_tl and step_ad like the reference API; increments up and down"},
+        "roofline": {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": pk_src, "share_of_step": top[2] / tot if tot > 0 else None,
+                     "note": "algorithmic bytes = 8 B x cells x distinct arrays read+written by that launch (halo excluded)"},
+        "step_roofline": {"alg_gb_per_step_pair": step_alg_gb, "achieved": step_alg_gb / (ms_step * 1e-3), "peak": peak, "unit": "GB/s",
+                          "frac": step_alg_gb / (ms_step * 1e-3) / peak, "note": "SURVEY 8(d) array-pass contract: TL %d + AD %d passes x %.1f MB" % (p_tl, p_ad, field_bytes / 1e6)},
+        "top_kernels": [{"name": r[0], "launches": r[1], "ms": round(r[2], 3), "alg_gbs": (r[3] / (r[2] * 1e-3) / 1e9 if r[2] > 0 else 0)} for r in rows[:12]],
+        "pool_peak_gb": float(h.lib.fv3lm_pool_peak_bytes(h.h)) / 1e9,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(args, bounded=True)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, bounded=True, steps=1, warmup=0):
+    """the oracle port (torch fp64 restatement, all host threads) on a bounded sample"""
+    import torch
+    from oracle import fv_dynamics as ofv
+    from oracle.tp_core import Grid
+    from synth import grid as G, state as S
+    from synth.cubed_sphere import R
+    torch.set_default_dtype(torch.float64)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Ns, K = args.cpu_res, args.npz
+    hydro = not args.nonhydro
+    dt = 450.0 * 180.0 / Ns
+    mc = model_config(Ns, K, hydro, dt)
+    ak, bk = S.eta_levels(K)
+    M = G.build_metrics(Ns)
+    g = Grid(M)
+    st = S.make_state(M, K, ak, bk, hydrostatic=hydro)
+    NX = Ns + 7
+    def full(a):
+        z = np.zeros(a.shape[:-2] + (NX, NX)); z[..., R(1, Ns), R(1, Ns)] = a; return torch.from_numpy(z)
+    act = [f for f in ["u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz"] if f in st]
+    x = tuple(full(st[k]) for k in act)
+    phis = full(st["phis"][:, None])
+    rd = 8314.47 / 28.965
+    cfg = dict(nord=1, d2_bg=0.015, d2_bg_k1=0.2, d2_bg_k2=0.1, n_sponge=0, vtdm4=0.0005, do_vort_damp=True, dddmp=0.2, d4_bg=0.15,
+               hord_mt=2, hord_vt=2, hord_tm=2, hord_dp=2, hord_tr=2, n_sponge_ord=0, ptop=1.0, akap=2.0 / 7.0, cp_air=3.5 * rd,
+               zvir=ZVIR, hydrostatic=hydro, k_split=1, n_split=mc["n_split"], dt=dt, rdgas=rd, grav=9.80665)
+    def fn(*a):
+        o = ofv.step_nl(dict(zip(act, a)), g, ak, bk, cfg, phis)
+        return tuple(o[k] for k in act)
+    pert = S.make_pert(st, 1)
+    dx = tuple(full(pert[k]) for k in act)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, tl = torch.func.jvp(fn, x, dx)
+        _, vjp = torch.func.vjp(fn, *x)
+        ad = vjp(dx)
+        times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times[warmup:]))
+    # scale the sample to the C180 workload: cells x acoustic sub-steps
+    N = args.res
+    mcN = model_config(N, K, hydro, 450.0 * 180.0 / N)
+    scale = (N / float(Ns)) ** 2 * (mcN["n_split"] / float(mc["n_split"]))
+    return {"value": 1.0 / (sec * scale), "unit": "TL+AD step pairs/s", "cores": cores, "kind": "port",
+            "sample": "oracle (torch fp64, %d threads) TL=jvp + AD=vjp of one C%d L%d step (n_split=%d) took %.2f s; scaled x%.1f (cells x sub-steps) to C%d"
+                      % (cores, Ns, K, mc["n_split"], sec, scale, N),
+            "sample_seconds": sec}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = cpu_baseline(args, bounded=True, steps=max(1, min(args.steps, 2)), warmup=min(args.warmup, 1))
+    N, K = args.res, args.npz
+    out = {"impl": "reference", "metric": "TL+AD model steps/sec", "value": b["value"], "unit": b["unit"], "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / b["value"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "C%d L%d %s dynamics-only TL+AD step (CPU: bounded sample, see cpu_baseline.sample)" % (N, K, "hydrostatic" if not args.nonhydro else "non-hydrostatic")},
+           "cpu_baseline": b, "e2e": {"value": b["value"], "unit": b["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "the reference Fortran cannot be built here (no Fortran compiler, FMS, MPI): this arm times the oracle port"}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--res", type=int, default=180)
+    ap.add_argument("--npz", type=int, default=72)
+    ap.add_argument("--cpu-res", type=int, default=12)
+    ap.add_argument("--nonhydro", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

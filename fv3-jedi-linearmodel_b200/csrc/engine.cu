@@ -5,6 +5,8 @@
 namespace fv3lm {
 namespace dev {
 long long launches = 0;
+bool profiling = false;
+std::map<std::string, ProfRow> prof;
 
 #ifndef FV3LM_HOST_EMU
 static cudaStream_t g_stream = nullptr;
@@ -116,6 +118,33 @@ void Program::release(int id) {
   if (v.pert) { dv->pool.put(v.pert); v.pert = nullptr; }
 }
 
+void Program::run_op(Op& op, int mode) {
+  if (!dev::profiling) { op.run(*this, op, mode); return; }
+#ifndef FV3LM_HOST_EMU
+  static cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+  cudaEventRecord(e0, dev::stream());
+  op.run(*this, op, mode);
+  cudaEventRecord(e1, dev::stream());
+  cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+#else
+  op.run(*this, op, mode);
+  float ms = 0;
+#endif
+  // algorithmic bytes: distinct arrays read + written, halo excluded (SURVEY 8(d) counting rule)
+  const Geom& g = dv->g;
+  auto cells = [&](int id) { return (double)g.ntile * vals[id].nk * g.N * g.N * 8.0; };
+  std::vector<int> ins = op.in; std::sort(ins.begin(), ins.end()); ins.erase(std::unique(ins.begin(), ins.end()), ins.end());
+  double b = 0.0;
+  if (op.inplace) { b = 0.0; }
+  else if (mode == MODE_AD) { for (int i : ins) b += cells(i) * (vals[i].active ? 3.0 : 1.0); for (int o : op.out) if (vals[o].active) b += cells(o); }
+  else { const double f = (mode == MODE_TL) ? 2.0 : 1.0; for (int i : ins) b += cells(i) * (vals[i].active ? f : 1.0); for (int o : op.out) b += cells(o) * (vals[o].active ? f : 1.0); }
+  const char* tag = mode == MODE_TL ? "tl:" : mode == MODE_AD ? "ad:" : "nl:";
+  dev::ProfRow& r = dev::prof[std::string(tag) + op.name];
+  r.n++; r.ms += ms; r.alg_bytes += b;
+}
+
 void Program::run(Mode mode) {
   analyse();
   const int nop = (int)ops.size();
@@ -123,7 +152,7 @@ void Program::run(Mode mode) {
     for (int n = 0; n < nop; n++) {
       Op& op = ops[n];
       for (int o : op.out) { ensure_traj(o); if (mode == MODE_TL) ensure_pert(o, true); }
-      op.run(*this, op, mode);
+      run_op(op, mode);
       // free values whose last use was this op
       for (int i : op.in) if (vals[i].last_use == n) release(i);
       for (int o : op.out) if (vals[o].last_use == n) release(o);
@@ -145,7 +174,7 @@ void Program::run(Mode mode) {
       Op& op = ops[n];
       for (int o : op.out) ensure_traj(o);
       // the last segment is reversed first: keep it whole and let its patch ops save what they overwrite
-      op.run(*this, op, seg_of[n] == nseg - 1 ? MODE_ADFWD : MODE_NL);
+      run_op(op, seg_of[n] == nseg - 1 ? MODE_ADFWD : MODE_NL);
       if (seg_of[n] == nseg - 1) continue;
       for (int i : op.in) if (vals[i].last_use == n && def_seg(i) == seg_of[n]) release(i);
       for (int o : op.out) if (vals[o].last_use == n && def_seg(o) == seg_of[n]) release(o);
@@ -158,7 +187,7 @@ void Program::run(Mode mode) {
       for (int n = n0; n <= n1 && s != nseg - 1; n++) {
         Op& op = ops[n];
         for (int o : op.out) ensure_traj(o);
-        op.run(*this, op, MODE_ADFWD);
+        run_op(op, MODE_ADFWD);
       }
       for (int n = n1; n >= n0; n--) {
         Op& op = ops[n];
@@ -167,7 +196,7 @@ void Program::run(Mode mode) {
         if (any_out || op.inplace) {
           for (int o : op.out) ensure_pert(o, true);
           for (int i : op.in) ensure_pert(i, true);
-          op.run(*this, op, MODE_AD);
+          run_op(op, MODE_AD);
         }
         if (!op.inplace)
           for (int o : op.out) if (vals[o].first_def == n) release(o);

@@ -217,6 +217,11 @@ void zero(void* d, size_t bytes);
 void sync();
 void check(const char* what);
 extern long long launches;   // number of kernels launched (bench.py gpu_launches)
+// optional per-op profile (CUDA events around every op; serialises, so only used in a
+// dedicated profiling pass, never inside a timed region)
+struct ProfRow { long long n = 0; double ms = 0.0, alg_bytes = 0.0; };
+extern bool profiling;
+extern std::map<std::string, ProfRow> prof;
 #ifndef FV3LM_HOST_EMU
 cudaStream_t stream();
 #endif
@@ -294,6 +299,7 @@ struct Program {
   size_t val_doubles(int id) const;
   void analyse();                    // activity + liveness
   void run(Mode mode);               // NL, TL, or AD (forward store-all + reverse)
+  void run_op(Op& op, int mode);     // one op, optionally profiled
   void ensure_traj(int id);
   void ensure_pert(int id, bool zero_it);
   void release(int id);

@@ -235,6 +235,27 @@ int fv3lm_time_steps(fv3lm_handle* h, int slot, int warmup, int iters, double* m
   FV3LM_CATCH(h)
 }
 
+// Profiling pass: per-op CUDA-event times of `iters` TL+AD steps (serialised; not a bench number).
+// Writes lines "name launches total_ms alg_bytes" into buf.
+int fv3lm_profile_steps(fv3lm_handle* h, int slot, int iters, char* buf, int buflen) {
+  FV3LM_TRY
+  ensure_runner(h);
+  dev::prof.clear();
+  dev::profiling = true;
+  for (int n = 0; n < iters; n++) { run_step(h, slot, MODE_TL); run_step(h, slot, MODE_AD); }
+  dev::sync();
+  dev::profiling = false;
+  std::string out;
+  for (auto& kv : dev::prof) {
+    char line[512];
+    snprintf(line, sizeof(line), "%s %lld %.6f %.0f\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.alg_bytes);
+    out += line;
+  }
+  if ((int)out.size() + 1 > buflen) out.resize(buflen > 0 ? buflen - 1 : 0);
+  if (buflen > 0) { memcpy(buf, out.c_str(), out.size()); buf[out.size()] = 0; }
+  FV3LM_CATCH(h)
+}
+
 // structural statistics of a module's program: ops, values, bytes if every value is kept (AD)
 int fv3lm_program_stats(fv3lm_handle* h, const char* module, double* out) {
   FV3LM_TRY

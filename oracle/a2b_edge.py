@@ -22,9 +22,12 @@ def _corner_coef(g):
     if hasattr(g, "_a2b_corner"):
         return g._a2b_corner
     npx, npy = g.npx, g.npy
-    grid = g.grid[:, 0].numpy(); agrid = g.agrid[:, 0].numpy()
+    grid = g.grid[:, 0]; agrid = g.agrid[:, 0]
     def GP(i, j): return grid[:, j + O, i + O, :]
     def AP(i, j): return agrid[:, j + O, i + O, :]
+    def gcd(q1, q2):   # great_circle_dist (model/fv_grid_utils_nlm.F90:1967), torch version
+        return 2.0 * torch.asin(torch.sqrt(torch.sin((q1[..., 1] - q2[..., 1]) / 2.0) ** 2 +
+                                           torch.cos(q1[..., 1]) * torch.cos(q2[..., 1]) * torch.sin((q1[..., 0] - q2[..., 0]) / 2.0) ** 2))
     spec = {
         (1, 1): [((1, 1), (2, 2)), ((0, 1), (-1, 2)), ((1, 0), (2, -1))],
         (npx, 1): [((npx - 1, 1), (npx - 2, 2)), ((npx - 1, 0), (npx - 2, -1)), ((npx, 1), (npx + 1, 2))],
@@ -36,8 +39,8 @@ def _corner_coef(g):
         p0 = GP(*c)
         ent = []
         for (a, b) in lst:
-            x1 = G.gc_dist(AP(*a), p0); x2 = G.gc_dist(AP(*b), p0)
-            ent.append((a, b, torch.as_tensor(x1 / (x2 - x1)).view(6, 1)))
+            x1 = gcd(AP(*a), p0); x2 = gcd(AP(*b), p0)
+            ent.append((a, b, (x1 / (x2 - x1)).reshape(6, 1)))
         out[c] = ent
     g._a2b_corner = out
     return out
