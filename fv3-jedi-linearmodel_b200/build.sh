@@ -4,7 +4,7 @@
 #   libfv3lm_hostemu.so  TEST-ONLY host emulation of the same stage functors (g++)
 set -e
 cd "$(dirname "$0")/csrc"
-SRCS="engine.cu mosaic.cu modules.cu csw.cu dsw.cu a2b.cu dyn.cu fvdyn.cu capi.cu step_api.cu"
+SRCS="engine.cu mosaic.cu modules.cu csw.cu dsw.cu a2b.cu dyn.cu fvdyn.cu nh.cu capi.cu step_api.cu"
 OUT=..
 if [ "$1" != "emu" ]; then
   nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -shared \

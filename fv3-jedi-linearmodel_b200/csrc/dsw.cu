@@ -169,3 +169,9 @@ void mod_d_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
 }
 
 }  // namespace fv3lm
+
+namespace fv3lm {
+std::pair<int, int> build_deln_public(Program& P, Mosaic& mo, int q, const LevOrd& nord, const LevD& damp, int nk, const std::string& tag) {
+  return build_deln(P, mo, q, nord, damp, nk, tag);
+}
+}  // namespace fv3lm

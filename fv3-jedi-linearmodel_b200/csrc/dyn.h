@@ -22,7 +22,7 @@ struct DynConfig {
 };
 
 struct DynState { int u, v, w, delz, pt, delp, phis; };
-struct DynOut { int u, v, w, delz, pt, delp, mfx, mfy, cx, cy, pkz, pe, peln, pk; };
+struct DynOut { int u, v, w, delz, pt, delp, mfx, mfy, cx, cy, pkz, pe, peln, pk, ws; };
 
 void level_params(const DynConfig& c, int K, DswParams& d);
 DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, const std::string& tag = "dyn");
