@@ -3,6 +3,7 @@
 // Lagrangian_to_Eulerian), and the fv3jedi_lm dynamics-component wrapper
 // (src/dynamics/fv3jedi_lm_dynamics_mod.F90:268-689).
 #include "fvdyn.h"
+#include "nh.h"
 #include "modules.h"
 
 namespace fv3lm {
@@ -156,13 +157,65 @@ struct S_copy {
   }
 };
 
+
+// non-hydrostatic thermodynamics of the remap (model/fv_mapz_nlm.F90:247-279):
+//   T_v = theta_v * exp(k1k log(rrg delp/delz theta_v)),  delz -> -delz/delp,  dp2 = new delp
+// in: pt delp delz pe2 ; out: tv dp2 dzr
+struct S_rm_tv_nh {
+  static constexpr int NI = 4, NO = 3;
+  struct P { double k1k, rrg; };
+  static constexpr int NT = 5;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}, {3, 0, 0, 0}, {3, 0, 0, 1}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    T pt = x.in(0), dp = x.in(1), dz = x.in(2);
+    x.out(0, pt * m_exp(p.k1k * m_log(p.rrg * dp / dz * pt)));
+    x.out(1, x.in(3, 0, 0, 1) - x.in(3));
+    x.out(2, -dz / dp);
+  }
+};
+// after the remap (:455-466, :497-505): delz = -dzr*dp2 ; pkz = exp(akap log(rrg dp2/delz T_v))
+// in: dzr_n dp2 tn ; out: delz pkz
+struct S_rm_post_nh {
+  static constexpr int NI = 3, NO = 2;
+  struct P { double akap, rrg; };
+  static constexpr int NT = 3;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    T dp2 = x.in(1);
+    T dz = -x.in(0) * dp2;
+    x.out(0, dz);
+    x.out(1, m_exp(p.akap * m_log(p.rrg * dp2 / dz * x.in(2))));
+  }
+};
+// non-hydrostatic pkz at the start of the step (model/fv_dynamics_nlm.F90:345-356):
+//   pkz = exp(kappa log(rdg delp T (1 + zvir q) / delz)).   in: delp t q1 delz ; out: pkz
+struct S_pkz_nh {
+  static constexpr int NI = 4, NO = 1;
+  struct P { double akap, rdg, zvir; };
+  static constexpr int NT = 4;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}, {3, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    x.out(0, m_exp(p.akap * m_log(p.rdg * x.in(0) * x.in(1) * (1.0 + p.zvir * x.in(2)) / x.in(3))));
+  }
+};
+
 static LevD lev_of(const std::vector<double>& a) {
   LevD o; for (int k = 0; k < 96; k++) o.v[k] = k < (int)a.size() ? a[k] : 0.0; return o;
 }
 
 RemapOut build_remap(Program& P, Mosaic& mo, const DynConfig& c, const std::vector<double>& ak, const std::vector<double>& bk,
-                     int pe, int pk, int peln, int pt, std::vector<int> q, int u, int v, bool last_step, const std::string& tag) {
+                     int pe, int pk, int peln, int pt, std::vector<int> q, int u, int v, bool last_step, const std::string& tag,
+                     int delp, int w, int delz, int ws) {
   (void)mo;
+  const bool nh = !c.hydrostatic;
   const Geom& g = P.dv->g;
   const int K = g.K, is = g.is, ie = g.ie, js = g.js, je = g.je;
   auto nm = [&](const std::string& s) { return tag + "." + s; };
@@ -171,10 +224,22 @@ RemapOut build_remap(Program& P, Mosaic& mo, const DynConfig& c, const std::vect
   int pe2 = P.val(nm("pe2"), K + 1), pn2 = P.val(nm("pn2"), K + 1), pk2 = P.val(nm("pk2"), K + 1);
   P.add<S_rm_pe2>("rm_pe2", {AK, BK, c.ptop, c.akap, K}, {pe, peln, pk}, {pe2, pn2, pk2}, K + 1);
   int tv = P.val(nm("tv"), K), dp2 = P.val(nm("dp2"), K), pkz = P.val(nm("pkz"), K);
-  P.add<S_rm_tv>("rm_tv", {c.akap}, {pt, pk, peln, pe2, pk2, pn2}, {tv, dp2, pkz}, K);
+  int dzr = -1;
+  const double rrg = -c.rdgas / c.grav;
+  if (nh) { dzr = P.val(nm("dzr"), K); P.add<S_rm_tv_nh>("rm_tv_nh", {c.akap / (1.0 - c.akap), rrg}, {pt, delp, delz, pe2}, {tv, dp2, dzr}, K); }
+  else P.add<S_rm_tv>("rm_tv", {c.akap}, {pt, pk, peln, pe2, pk2, pn2}, {tv, dp2, pkz}, K);
   int dummy2d = P.val(nm("qs0"), 1);
   int tn = P.val(nm("tn"), K);
   add_col<S_remap>(P, "map_scalar_T", {K, 1, 0, is, ie, js, je}, {tv, peln, pn2, dummy2d, dp2}, {tn});
+  o.w = -1; o.delz = -1;
+  if (nh) {
+    o.w = P.val(nm("w"), K);
+    add_col<S_remap>(P, "map1_ppm_w", {K, -2, 0, is, ie, js, je}, {w, pe, pe2, ws, dp2}, {o.w});
+    int dzn = P.val(nm("dzr_n"), K);
+    add_col<S_remap>(P, "map1_ppm_delz", {K, 1, 0, is, ie, js, je}, {dzr, pe, pe2, dummy2d, dp2}, {dzn});
+    o.delz = P.val(nm("delz"), K);
+    P.add<S_rm_post_nh>("rm_post_nh", {c.akap, rrg}, {dzn, dp2, tn}, {o.delz, pkz}, K);
+  }
   for (size_t n = 0; n < q.size(); n++) {
     int qn = P.val(nm("q" + std::to_string(n)), K);
     add_col<S_remap>(P, "map1_q2", {K, 0, 1, is, ie, js, je}, {q[n], pe, pe2, dummy2d, dp2}, {qn});
@@ -211,14 +276,17 @@ struct S_thv {
 FvOut build_fv_dynamics(Program& P, Mosaic& mo, const DynConfig& c, const std::vector<double>& ak, const std::vector<double>& bk, FvState s) {
   const Geom& g = P.dv->g;
   const int K = g.K;
-  if (!c.hydrostatic) throw std::runtime_error("build_fv_dynamics: non-hydrostatic model step not built yet");
   FvOut o;
   // hydrostatic: pkz from compute_fv3_pressures (fv_pressure.F90:22-69) = geopk restricted to the compute domain
   int pk0 = P.val("fv.pk0", K + 1), gz0 = P.val("fv.gz0", K + 1), pe0 = P.val("fv.pe0", K + 1), pl0 = P.val("fv.peln0", K + 1), pkz0 = P.val("fv.pkz0", K);
   add_col<S_geopk>(P, "compute_fv3_pressures", {c.ptop, c.akap, c.cp_air, 0, 0, K}, {s.delp, s.pt, s.phis}, {pk0, gz0, pe0, pl0, pkz0});
+  if (!c.hydrostatic) {
+    pkz0 = P.val("fv.pkz_nh", K);
+    P.add<S_pkz_nh>("pkz_nh", {c.akap, -c.rdgas / c.grav, c.zvir}, {s.delp, s.pt, s.q.empty() ? s.pt : s.q[0], s.delz}, {pkz0}, K);
+  }
   int pt = P.val("fv.thv", K);
   P.add<S_thv>("thv", {c.zvir}, {s.pt, s.q.empty() ? s.pt : s.q[0], pkz0}, {pt}, K);
-  int u = s.u, v = s.v, delp = s.delp, w = s.w;
+  int u = s.u, v = s.v, delp = s.delp, w = s.w, delz = s.delz;
   std::vector<int> q = s.q;
   DynConfig cd = c; cd.bdt = c.bdt / c.k_split;
   for (int n_map = 1; n_map <= c.k_split; n_map++) {
@@ -227,16 +295,18 @@ FvOut build_fv_dynamics(Program& P, Mosaic& mo, const DynConfig& c, const std::v
     add_patch(P, "halo_pt0", &mo.h_center, {pt});
     add_patch(P, "halo_uv0", &mo.h_dgrid, {u, v});
     const int dp1 = delp;
-    DynState ds; ds.u = u; ds.v = v; ds.w = w; ds.delz = -1; ds.pt = pt; ds.delp = delp; ds.phis = s.phis;
-    DynOut d = build_dyn_core(P, mo, cd, ds, tg);
+    DynState ds; ds.u = u; ds.v = v; ds.w = w; ds.delz = delz; ds.pt = pt; ds.delp = delp; ds.phis = s.phis;
+    DynOut d = c.hydrostatic ? build_dyn_core(P, mo, cd, ds, tg) : build_dyn_core_nh(P, mo, cd, ak, bk, ds, tg);
     P.mark_segment();
     for (int& x : q) add_patch(P, "halo_q", &mo.h_center, {x});
     q = build_tracer_2d(P, mo, q, dp1, d.mfx, d.mfy, d.cx, d.cy, c.hord_tr, tg + ".trc");
     P.mark_segment();
-    RemapOut r = build_remap(P, mo, c, ak, bk, d.pe, d.pk, d.peln, d.pt, q, d.u, d.v, n_map == c.k_split, tg + ".rm");
+    RemapOut r = build_remap(P, mo, c, ak, bk, d.pe, d.pk, d.peln, d.pt, q, d.u, d.v, n_map == c.k_split, tg + ".rm",
+                             d.delp, c.hydrostatic ? -1 : d.w, c.hydrostatic ? -1 : d.delz, c.hydrostatic ? -1 : d.ws);
     u = r.u; v = r.v; pt = r.pt; delp = r.delp; q = r.q;
+    if (!c.hydrostatic) { w = r.w; delz = r.delz; }
   }
-  o.u = u; o.v = v; o.pt = pt; o.delp = delp; o.q = q; o.w = w;
+  o.u = u; o.v = v; o.pt = pt; o.delp = delp; o.q = q; o.w = w; o.delz = delz;
   return o;
 }
 
@@ -245,10 +315,10 @@ FvOut build_fv_dynamics(Program& P, Mosaic& mo, const DynConfig& c, const std::v
 // ---------------------------------------------------------------------------------
 void mod_remap(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
   const int K = P.dv->g.K;
-  DynConfig c; dyn_config_from(c, prm);
+  DynConfig c; dyn_config_from(c, prm); c.hydrostatic = true;
   int pe = io.in(P, "pe", K + 1), pk = io.in(P, "pk", K + 1), peln = io.in(P, "peln", K + 1), pt = io.in(P, "pt", K);
   int q0 = io.in(P, "q0", K), u = io.in(P, "u", K), v = io.in(P, "v", K);
-  RemapOut r = build_remap(P, mo, c, *prm.ak, *prm.bk, pe, pk, peln, pt, {q0}, u, v, prm.geti("last_step", 1) != 0, "rm");
+  RemapOut r = build_remap(P, mo, c, *prm.ak, *prm.bk, pe, pk, peln, pt, {q0}, u, v, prm.geti("last_step", 1) != 0, "rm", -1, -1, -1, -1);
   io.out(P, "pt_n", r.pt); io.out(P, "q0_n", r.q[0]); io.out(P, "u_n", r.u); io.out(P, "v_n", r.v); io.out(P, "delp_n", r.delp);
   io.out(P, "pkz_n", r.pkz); io.out(P, "pe_n", r.pe);
 }
@@ -261,13 +331,14 @@ void mod_step(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
   s.u = io.in(P, "u", K); s.v = io.in(P, "v", K); s.pt = io.in(P, "t", K); s.delp = io.in(P, "delp", K);
   const char* qn[4] = {"qv", "ql", "qi", "o3"};
   for (int n = 0; n < c.nq; n++) s.q.push_back(io.in(P, qn[n], K));
-  s.w = io.in(P, "w", K); s.delz = -1; s.phis = io.in(P, "phis", 1);
+  s.w = io.in(P, "w", K); s.delz = c.hydrostatic ? -1 : io.in(P, "delz", K); s.phis = io.in(P, "phis", 1);
   // traj_to_fv3 / pert_to_fv3: shared edge rows of the D-grid winds, halo of phis (fv3jedi_lm_dynamics_mod.F90:782-800)
   add_patch(P, "get_boundary_in", &mo.gb_dgrid, {s.u, s.v});
   add_patch(P, "halo_phis", &mo.h_center, {s.phis});
   FvOut o = build_fv_dynamics(P, mo, c, *prm.ak, *prm.bk, s);
   io.out(P, "u_n", o.u); io.out(P, "v_n", o.v); io.out(P, "t_n", o.pt); io.out(P, "delp_n", o.delp);
   for (int n = 0; n < c.nq; n++) io.out(P, std::string(qn[n]) + "_n", o.q[n]);
+  if (!c.hydrostatic) { io.out(P, "w_n", o.w); io.out(P, "delz_n", o.delz); }
 }
 
 }  // namespace fv3lm

@@ -48,7 +48,10 @@ def _run_remap(emu, last_step):
     return check_module(h, "remap", N, K, f, act, outs, fn, p, rng, tol=1e-11, dot_tol=1e-12, pert_scale=1e-3)
 
 
-def api_state(N, K, seed, ak, bk):
+RD = 8314.47 / 28.965
+
+
+def api_state(N, K, seed, ak, bk, nonhydro=False):
     rng = np.random.default_rng(seed)
     ps = 1.0e5 + 300.0 * smooth(rng, N, 1)
     pe = ak[None, :, None, None] + bk[None, :, None, None] * ps
@@ -56,17 +59,23 @@ def api_state(N, K, seed, ak, bk):
              qv=0.005 * (1.0 + 0.3 * smooth(rng, N, K)), ql=1e-5 * (1.0 + 0.3 * smooth(rng, N, K)),
              qi=1e-5 * (1.0 + 0.3 * smooth(rng, N, K)), o3=1e-6 * (1.0 + 0.3 * smooth(rng, N, K)),
              w=np.zeros((6, K, N + 7, N + 7)), phis=200.0 * 9.80665 * smooth(rng, N, 1))
+    if nonhydro:
+        # hydrostatically balanced layer thickness + small vertical velocity (fv3jedi_lm traj%delz, traj%w)
+        tv = f["t"] * (1.0 + ZVIR * f["qv"])
+        f["delz"] = -(RD * tv / 9.80665) * (np.log(pe[:, 1:]) - np.log(pe[:, :-1]))
+        f["w"] = 0.05 * smooth(rng, N, K)
     return f, rng
 
 
-def _run_step(emu, k_split, n_split, K=4):
+def _run_step(emu, k_split, n_split, K=4, nonhydro=False):
     N = 12
     ptop = CFG["ptop"]
     ak, bk = eta(K, ptop)
-    f, rng = api_state(N, K, 31, ak, bk)
+    f, rng = api_state(N, K, 31, ak, bk, nonhydro)
     g = ograd(N)
-    cfg = dict(CFG); cfg.update(zvir=ZVIR, hydrostatic=True, k_split=k_split, n_split=n_split, dt=900.0, hord_tr=2)
-    act = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"]
+    cfg = dict(CFG); cfg.update(zvir=ZVIR, hydrostatic=not nonhydro, k_split=k_split, n_split=n_split, dt=900.0, hord_tr=2,
+                                rdgas=RD, grav=9.80665, p_fac=0.05)
+    act = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"] + (["w", "delz"] if nonhydro else [])
     onames = [a + "_n" for a in act]
     phis = torch.from_numpy(f["phis"])
     def fn(*a):
@@ -75,11 +84,14 @@ def _run_step(emu, k_split, n_split, K=4):
     C = (1, N, 1, N)
     outs = {o: C for o in onames}
     h = handle(N, K, emu, ak, bk)
-    p = dict(cfg); p.update(do_vort_damp=1, hydrostatic=1, nq=4, bdt=cfg["dt"])
+    p = dict(cfg); p.update(do_vort_damp=1, hydrostatic=0 if nonhydro else 1, nq=4, bdt=cfg["dt"])
     # the API state lives on the compute domain: zero everything else so both sides see the same input
     from oracle.cubed_sphere import R
     for k in act:
         z = np.zeros_like(f[k]); z[..., R(1, N), R(1, N)] = f[k][..., R(1, N), R(1, N)]; f[k] = z
+    if nonhydro:
+        inputs = {k: f[k] for k in ["u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz", "phis"]}
+        return check_module(h, "step", N, K, inputs, act, outs, fn, p, rng, tol=2e-9, dot_tol=1e-10, pert_scale=1e-3)
     return check_module(h, "step", N, K, f, act, outs, fn, p, rng, tol=2e-10, dot_tol=1e-11, pert_scale=1e-3)
 
 
@@ -92,6 +104,10 @@ def test_step_hydro_emu():
     print(_run_step(True, 1, 2))
 
 
+def test_step_nonhydro_emu():
+    print(_run_step(True, 1, 2, nonhydro=True))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("last_step", [True, False])
 def test_remap_gpu(last_step):
@@ -102,3 +118,8 @@ def test_remap_gpu(last_step):
 @pytest.mark.parametrize("k_split,n_split", [(1, 2), (2, 1)])
 def test_step_hydro_gpu(k_split, n_split):
     _run_step(False, k_split, n_split)
+
+
+@pytest.mark.gpu
+def test_step_nonhydro_gpu():
+    _run_step(False, 1, 2, nonhydro=True)
