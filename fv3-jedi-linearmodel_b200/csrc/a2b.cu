@@ -40,8 +40,9 @@ template <int DIR> struct S_a2b_q1 {
     using T = typename X::T;
     const Geom& g = x.g;
     const int np = DIR == 0 ? g.npx : g.npy;
-    if (DIR == 0) { if (!x.in_rect(1, g.npx, 1, g.npy - 1)) return; }
-    else { if (!x.in_rect(1, g.npx - 1, 1, g.npy)) return; }
+    // a2b_edge_nlm.F90:108-110 / :152-154: rows js-2..je+2 (columns is-2..ie+2) clipped to the tile
+    if (DIR == 0) { if (!x.in_rect(g.is, g.ie + 1, g.js - 2, g.je + 2) || !x.in_tile(1, g.npx, 1, g.npy - 1)) return; }
+    else { if (!x.in_rect(g.is - 2, g.ie + 2, g.js, g.je + 1) || !x.in_tile(1, g.npx - 1, 1, g.npy)) return; }
     const int pos = DIR == 0 ? x.i : x.j;
     T r;
     if (pos == 1) r = edge(x, 0, true);
@@ -76,7 +77,7 @@ struct S_a2b_edge {
     using T = typename X::T;
     const Geom& g = x.g;
     const int i = x.i, j = x.j, npx = g.npx, npy = g.npy;
-    if (!x.in_rect(1, npx, 1, npy)) return;
+    if (!x.in_rect(g.is, g.ie + 1, g.js, g.je + 1)) return;
     const bool ei = (i == 1 || i == npx), ej = (j == 1 || j == npy);
     if (!ei && !ej) return;
     T r;
@@ -117,7 +118,7 @@ struct S_a2b_q2 {
     using T = typename X::T;
     const Geom& g = x.g;
     const int i = x.i, j = x.j, npx = g.npx, npy = g.npy;
-    if (!x.in_rect(1, npx, 1, npy)) return;
+    if (!x.in_rect(g.is, g.ie + 1, g.js, g.je + 1)) return;
     if (i == 1 || i == npx || j == 1 || j == npy) { x.out(0, x.in(2)); return; }
     T qxx, qyy;
     if (j == 2) qxx = a2b::c1 * (x.in(0, 0, -1) + x.in(0)) + a2b::c2 * (x.in(2, 0, -1) + xx(x, 1));

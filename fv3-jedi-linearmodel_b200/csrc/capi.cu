@@ -42,13 +42,23 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
   h->cfg = *cfg;
   Geom& g = h->dv.g;
   g.N = cfg->npx - 1; g.npx = cfg->npx; g.npy = cfg->npy; g.ng = cfg->ng;
-  g.is = 1; g.ie = g.N; g.js = 1; g.je = g.N;
-  g.NX = g.N + 2 * g.ng + 1; g.NY = g.NX;
+  Decomp& dc = h->dc;
+  dc.init(g.N, cfg->rank, cfg->nranks < 1 ? 1 : cfg->nranks, cfg->layout_x, cfg->layout_y);
+  if (dc.per_rank > MAXSUB) throw std::runtime_error("fv3lm_create: too many sub-domains per rank");
+  g.is = 1; g.ie = dc.nxl; g.js = 1; g.je = dc.nyl;
+  g.NX = dc.nxl + 2 * g.ng + 1; g.NY = dc.nyl + 2 * g.ng + 1;
   g.pitch = (g.NX + 3) / 4 * 4;
-  g.ntile = 6; g.K = cfg->npz; g.slab = g.pitch * g.NY;
+  g.ntile = dc.per_rank; g.K = cfg->npz; g.slab = g.pitch * g.NY;
+  if (g.slab < g.N + 2 * g.ng + 1) throw std::runtime_error("fv3lm_create: sub-domain slab smaller than a tile edge");
+  for (int l = 0; l < MAXSUB; l++) { g.i0[l] = 0; g.j0[l] = 0; g.tile_of[l] = 0; }
+  for (int l = 0; l < dc.per_rank; l++) {
+    const int d = dc.global_id(dc.rank, l);
+    g.i0[l] = (short)dc.i0_of(d); g.j0[l] = (short)dc.j0_of(d); g.tile_of[l] = (short)dc.tile_of(d);
+  }
+  h->comm.rank = dc.rank; h->comm.nranks = dc.nranks;
   if (ak && bk) { h->ak.assign(ak, ak + cfg->npz + 1); h->bk.assign(bk, bk + cfg->npz + 1); }
   memset(&h->dv.m, 0, sizeof(Metrics));
-  h->mo.build(g);
+  h->mo.build(g, dc, &h->comm);
   *out = h;
   FV3LM_CATCH(h)
 }
@@ -68,6 +78,7 @@ int fv3lm_destroy(fv3lm_handle* h) {
     delete r;
   }
   h->mo.destroy();
+  h->comm.destroy();
   delete h;
   h = nullptr;
   FV3LM_CATCH(h)
@@ -82,7 +93,8 @@ int fv3lm_set_metric(fv3lm_handle* h, const char* name, const double* host, int 
   double*& d = h->metric_dev[nm];
   if (!d) { d = (double*)dev::alloc((size_t)g.ntile * g.slab * sizeof(double)); dev::zero(d, (size_t)g.ntile * g.slab * sizeof(double)); }
   if (is_1d) {
-    for (int t = 0; t < g.ntile; t++) dev::h2d(d + (size_t)t * g.slab, host + (size_t)t * g.NX, g.NX * sizeof(double));
+    const int nxg = g.N + 2 * g.ng + 1;   // 1-D edge factors are whole-tile arrays (gridstruct%edge_w(npy) ...)
+    for (int t = 0; t < g.ntile; t++) dev::h2d(d + (size_t)t * g.slab, host + (size_t)t * nxg, nxg * sizeof(double));
   } else {
     up2d(g, d, host, (size_t)g.ntile * g.NY);
   }
@@ -172,6 +184,41 @@ int fv3lm_module_run(fv3lm_handle* h, const char* module, int mode, int nfields,
   dev::sync();
   for (int id : ext) { Value& v = P.vals[id]; h->dv.pool.put(v.traj); h->dv.pool.put(v.pert); v.traj = v.pert = nullptr; }
   FV3LM_CATCH(h)
+}
+
+// ---- domain decomposition / communicator ----------------------------------------------------
+int fv3lm_decomp_info(const fv3lm_handle* h, int* out /* nsub, nxl, nyl, layout_x, layout_y, nsub_total */, int* tile, int* i0, int* j0) {
+  if (!h) return 1;
+  const Decomp& dc = h->dc;
+  if (out) { out[0] = dc.per_rank; out[1] = dc.nxl; out[2] = dc.nyl; out[3] = dc.lx; out[4] = dc.ly; out[5] = dc.nsub_total; }
+  for (int l = 0; l < dc.per_rank; l++) {
+    const int d = dc.global_id(dc.rank, l);
+    if (tile) tile[l] = dc.tile_of(d);
+    if (i0) i0[l] = dc.i0_of(d);
+    if (j0) j0[l] = dc.j0_of(d);
+  }
+  return 0;
+}
+int fv3lm_nccl_unique_id(char* out128) {
+  fv3lm_handle* h = nullptr;
+  FV3LM_TRY
+  Comm::nccl_unique_id(out128);
+  FV3LM_CATCH(h)
+}
+int fv3lm_comm_init_nccl(fv3lm_handle* h, const char* id128) {
+  FV3LM_TRY
+  h->comm.init_nccl(id128);
+  FV3LM_CATCH(h)
+}
+int fv3lm_comm_set_callback(fv3lm_handle* h, fv3lm_exchange_fn fn, void* user) {
+  FV3LM_TRY
+  h->comm.cb = (ExchangeCallback)fn; h->comm.cb_user = user;
+  FV3LM_CATCH(h)
+}
+int fv3lm_comm_stats(const fv3lm_handle* h, double* out2) {
+  if (!h) return 1;
+  out2[0] = (double)h->comm.n_exchanges; out2[1] = h->comm.bytes_sent;
+  return 0;
 }
 
 long long fv3lm_launch_count(void) { return dev::launches; }

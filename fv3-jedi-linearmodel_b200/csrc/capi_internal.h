@@ -23,6 +23,8 @@ struct fv3lm_handle {
   fv3lm_config cfg;
   fv3lm::Device dv;
   fv3lm::Mosaic mo;
+  fv3lm::Decomp dc;
+  fv3lm::Comm comm;
   std::vector<double> ak, bk;
   std::map<std::string, double*> metric_dev;
   std::string err;

@@ -134,7 +134,7 @@ void Program::run_op(Op& op, int mode) {
 #endif
   // algorithmic bytes: distinct arrays read + written, halo excluded (SURVEY 8(d) counting rule)
   const Geom& g = dv->g;
-  auto cells = [&](int id) { return (double)g.ntile * vals[id].nk * g.N * g.N * 8.0; };
+  auto cells = [&](int id) { return (double)g.ntile * vals[id].nk * g.ie * g.je * 8.0; };
   std::vector<int> ins = op.in; std::sort(ins.begin(), ins.end()); ins.erase(std::unique(ins.begin(), ins.end()), ins.end());
   double b = 0.0;
   if (op.inplace) { b = 0.0; }

@@ -31,13 +31,21 @@ namespace fv3lm {
 // ---------------------------------------------------------------------------------
 // geometry of the device arrays
 // ---------------------------------------------------------------------------------
+// A device holds `ntile` SUB-DOMAINS (whole cube tiles for layout 1x1, else the layout(lx,ly)
+// pieces of tools/fv_mp_nlm_mod.F90:411-441), all of the same size nxl x nyl.  Stage code
+// sees two index frames: the LOCAL frame (compute domain is..ie = 1..nxl, js..je = 1..nyl;
+// loop ranges / in_rect) and the TILE-GLOBAL Fortran index x.i, x.j = local + i0/j0
+// (cube-edge special cases keyed on i == 1, i == npx, ... exactly like the reference).
+constexpr int MAXSUB = 24;
 struct Geom {
   int N, npx, npy, ng;  // cells per tile edge; npx = npy = N + 1; halo width (3)
-  int is, ie, js, je;   // compute domain of this sub-domain in tile-global indices
-  int NX, NY, pitch;    // logical extents N + 2 ng + 1 and the row pitch (doubles)
-  int ntile;            // cube tiles resident on this device
+  int is, ie, js, je;   // compute domain in the local frame: 1..nxl, 1..nyl
+  int NX, NY, pitch;    // local array extents nxl + 2 ng + 1, nyl + 2 ng + 1 and the row pitch (doubles)
+  int ntile;            // sub-domains resident on this device
   int K;                // npz
   int slab;             // pitch * NY
+  short i0[MAXSUB], j0[MAXSUB];   // tile-global index = local index + i0 / j0
+  short tile_of[MAXSUB];          // cube tile (0..5) of each resident sub-domain
 };
 
 // 2-D metric arrays, each [ntile][NY][pitch]; sin_sg/cos_sg 1..4 (+5 for sin) split out.
@@ -72,10 +80,12 @@ template <int N> struct FArr {
 // ---------------------------------------------------------------------------------
 struct CtxBase {
   Geom g; Metrics m;
-  int ii, jj, kk, tile;   // array column/row, level, tile
+  int ii, jj, kk, tile;   // array column/row, level, resident sub-domain
   int i, j;               // Fortran tile-global indices
+  int il, jl;             // local-frame indices (compute domain 1..nxl, 1..nyl)
   DEV void setpos(int ii_, int jj_, int kk_, int tile_) {
-    ii = ii_; jj = jj_; kk = kk_; tile = tile_; i = ii_ - (g.ng - 1); j = jj_ - (g.ng - 1);
+    ii = ii_; jj = jj_; kk = kk_; tile = tile_; il = ii_ - (g.ng - 1); jl = jj_ - (g.ng - 1);
+    i = il + g.i0[tile_]; j = jl + g.j0[tile_];
   }
   // metric at relative offset
   DEV double M(const double* a, int di = 0, int dj = 0) const {
@@ -83,11 +93,14 @@ struct CtxBase {
   }
   // metric at absolute Fortran index
   DEV double Mabs(const double* a, int ai, int aj) const {
-    return a[(size_t)tile * g.slab + (size_t)(aj + g.ng - 1) * g.pitch + (ai + g.ng - 1)];
+    return a[(size_t)tile * g.slab + (size_t)(aj - g.j0[tile] + g.ng - 1) * g.pitch + (ai - g.i0[tile] + g.ng - 1)];
   }
-  // 1-D edge array, Fortran index
+  // 1-D edge array (stored whole-tile in the head of the slab), tile-global Fortran index
   DEV double M1(const double* a, int ai) const { return a[(size_t)tile * g.slab + (ai + g.ng - 1)]; }
-  DEV bool in_rect(int i0, int i1, int j0, int j1) const { return i >= i0 && i <= i1 && j >= j0 && j <= j1; }
+  // loop ranges are given in the local frame
+  DEV bool in_rect(int i0, int i1, int j0, int j1) const { return il >= i0 && il <= i1 && jl >= j0 && jl <= j1; }
+  // tile-global rectangle (whole-tile operators such as a2b_ord4)
+  DEV bool in_tile(int i0, int i1, int j0, int j1) const { return i >= i0 && i <= i1 && j >= j0 && j <= j1; }
   DEV size_t off(int nkf, int di, int dj, int dk) const {
     int k = (dk == KLAST) ? nkf - 1 : kk + dk;
     if (k > nkf - 1) k = nkf - 1;

@@ -9,10 +9,24 @@
 #pragma once
 #include <vector>
 #include "engine.h"
+#include "decomp.h"
+#include "comm.h"
 
 namespace fv3lm {
 
+// dtile / stile: resident sub-domain index (after Mosaic::build filtered the global list)
 struct PatchEntry { int dtile, dpos, dcomp, stile, spos, scomp; double sign; };
+
+// entries of a patch whose source lives on another rank: what this rank sends (its source cells)
+// and receives (its destination cells), both in the global entry order so that the two sides agree
+struct PeerList {
+  int peer = -1;
+  int n_send = 0, n_recv = 0, n_srow = 0;
+  std::vector<PatchEntry> send, recv;
+  int *s_tile = nullptr, *s_pos = nullptr, *s_comp = nullptr;                      // send list (source cells)
+  int *r_tile = nullptr, *r_pos = nullptr, *r_comp = nullptr; double* r_sign = nullptr;   // recv list (destination cells)
+  int *a_tile = nullptr, *a_pos = nullptr, *a_comp = nullptr, *a_row = nullptr, *a_ent = nullptr;   // CSR: distinct source cells -> send entries
+};
 
 struct PatchMap {
   std::string name;
@@ -25,6 +39,8 @@ struct PatchMap {
   int *a_stile = nullptr, *a_spos = nullptr, *a_scomp = nullptr, *a_row = nullptr;  // CSR rows -> forward entry ids
   int* a_ent = nullptr;
   std::vector<PatchEntry> host;
+  std::vector<PeerList> peers;   // remote part (empty on a single rank)
+  Comm* comm = nullptr;
   void upload();
   void destroy();
 };
@@ -34,6 +50,8 @@ enum Stag { ST_CENTER = 0, ST_CORNER = 1, ST_YSTAG = 2 /* D-grid u, C-grid vc */
 
 struct Mosaic {
   Geom g;
+  Decomp dc;
+  Comm* comm = nullptr;
   // halo exchanges
   PatchMap h_center, h_corner, h_dgrid, h_cgrid;
   PatchMap gb_dgrid;        // mpp_get_boundary(u, v, DGRID_NE): north row of u, east column of v from the owner tile
@@ -45,7 +63,7 @@ struct Mosaic {
   // d2a2c_vect corner exchanges between the x and y components (model/sw_core_nlm.F90:2884-2925, :2986-3030)
   PatchMap c_utmp, c_ua, c_vtmp, c_va;   // fields {dst, src}
   std::vector<PatchMap*> all();
-  void build(const Geom& g);
+  void build(const Geom& g, const Decomp& dc, Comm* comm);
   void destroy();
 };
 

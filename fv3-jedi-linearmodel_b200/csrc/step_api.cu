@@ -18,7 +18,7 @@ struct KExpand {
   DEV void operator()(int ii, int jj, int z) const {
     int i = ii - (g.ng - 1), j = jj - (g.ng - 1);
     double v = 0.0;
-    if (i >= 1 && i <= g.N && j >= 1 && j <= g.N) v = c[((size_t)z * g.N + (j - 1)) * g.N + (i - 1)];
+    if (i >= 1 && i <= g.ie && j >= 1 && j <= g.je) v = c[((size_t)z * g.je + (j - 1)) * g.ie + (i - 1)];
     h[(size_t)z * g.slab + (size_t)jj * g.pitch + ii] = v;
   }
 };
@@ -26,11 +26,11 @@ struct KCompact {
   Geom g; double* c; const double* h; int nk;
   DEV void operator()(int ii, int jj, int z) const {
     int i = ii - (g.ng - 1), j = jj - (g.ng - 1);
-    if (i >= 1 && i <= g.N && j >= 1 && j <= g.N) c[((size_t)z * g.N + (j - 1)) * g.N + (i - 1)] = h[(size_t)z * g.slab + (size_t)jj * g.pitch + ii];
+    if (i >= 1 && i <= g.ie && j >= 1 && j <= g.je) c[((size_t)z * g.je + (j - 1)) * g.ie + (i - 1)] = h[(size_t)z * g.slab + (size_t)jj * g.pitch + ii];
   }
 };
 
-size_t compact_doubles(const Geom& g, int nk) { return (size_t)g.ntile * nk * g.N * g.N; }
+size_t compact_doubles(const Geom& g, int nk) { return (size_t)g.ntile * nk * g.ie * g.je; }
 
 void ensure_runner(fv3lm_handle* h) {
   if (h->step) return;

@@ -24,14 +24,16 @@ class Config(C.Structure):
                 ("dddmp", C.c_double), ("d2_bg", C.c_double), ("d4_bg", C.c_double), ("vtdm4", C.c_double),
                 ("d2_bg_k1", C.c_double), ("d2_bg_k2", C.c_double), ("d_ext", C.c_double), ("beta", C.c_double),
                 ("zvir", C.c_double), ("kappa", C.c_double), ("cp", C.c_double), ("rdgas", C.c_double),
-                ("grav", C.c_double), ("do_vort_damp", C.c_int), ("reserved", C.c_int * 16)]
+                ("grav", C.c_double), ("do_vort_damp", C.c_int),
+                ("rank", C.c_int), ("nranks", C.c_int), ("layout_x", C.c_int), ("layout_y", C.c_int), ("reserved", C.c_int * 12)]
 
 
 class Fields(C.Structure):
     _fields_ = [(n, C.POINTER(C.c_double)) for n in ("u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz")]
 
 
-EXPORTS = ["fv3lm_set_phis", "fv3lm_traj_set", "fv3lm_traj_get", "fv3lm_step_nl", "fv3lm_step_tl", "fv3lm_step_ad",
+EXPORTS = ["fv3lm_decomp_info", "fv3lm_nccl_unique_id", "fv3lm_comm_init_nccl", "fv3lm_comm_set_callback", "fv3lm_comm_stats",
+           "fv3lm_profile_steps", "fv3lm_set_phis", "fv3lm_traj_set", "fv3lm_traj_get", "fv3lm_step_nl", "fv3lm_step_tl", "fv3lm_step_ad",
            "fv3lm_pert_upload", "fv3lm_pert_download", "fv3lm_step_tl_dev", "fv3lm_step_ad_dev", "fv3lm_time_steps",
            "fv3lm_program_stats", "fv3lm_create", "fv3lm_destroy", "fv3lm_last_error", "fv3lm_set_metric", "fv3lm_set_metric_scalar",
            "fv3lm_module_run", "fv3lm_module_list", "fv3lm_launch_count", "fv3lm_pool_peak_bytes", "fv3lm_sync"]
@@ -94,6 +96,86 @@ class FV3LM:
             raise RuntimeError("fv3lm_create failed: %s" % self.lib.fv3lm_last_error(None).decode())
         self.N = cfg.npx - 1
         self.NX = self.N + 2 * cfg.ng + 1
+        info = (C.c_int * 6)(); t = (C.c_int * 64)(); i0 = (C.c_int * 64)(); j0 = (C.c_int * 64)()
+        self.lib.fv3lm_decomp_info(self.h, info, t, i0, j0)
+        self.nsub, self.nxl, self.nyl, self.lx, self.ly, self.nsub_total = [int(x) for x in info]
+        self.sub_tile = [int(t[l]) for l in range(self.nsub)]
+        self.sub_i0 = [int(i0[l]) for l in range(self.nsub)]
+        self.sub_j0 = [int(j0[l]) for l in range(self.nsub)]
+        self.NXl = self.nxl + 2 * cfg.ng + 1
+        self.NYl = self.nyl + 2 * cfg.ng + 1
+        self.whole = (self.nsub == 6 and self.nxl == self.N and self.nyl == self.N)
+        self._cb = None
+
+    # ---- global (whole cube, [6, ..., N+7, N+7]) <-> this rank's sub-domain arrays ----------------
+    def scatter(self, a):
+        """halo'd global array [6, nk, NYg, NXg] -> [nsub, nk, NYl, NXl] (every cell the sub-domain array holds)"""
+        if self.whole:
+            return np.ascontiguousarray(a)
+        return np.ascontiguousarray(np.stack([a[t, ..., j0:j0 + self.NYl, i0:i0 + self.NXl]
+                                              for t, i0, j0 in zip(self.sub_tile, self.sub_i0, self.sub_j0)]))
+
+    def scatter_owned(self, a):
+        """like scatter, but only the cells a sub-domain owns (1..nxl, 1..nyl); zero elsewhere"""
+        o = self.cfg.ng - 1
+        out = np.zeros((self.nsub,) + a.shape[1:-2] + (self.NYl, self.NXl))
+        for l, (t, i0, j0) in enumerate(zip(self.sub_tile, self.sub_i0, self.sub_j0)):
+            out[l, ..., o + 1:o + 1 + self.nyl, o + 1:o + 1 + self.nxl] = a[t, ..., j0 + o + 1:j0 + o + 1 + self.nyl, i0 + o + 1:i0 + o + 1 + self.nxl]
+        return out
+
+    def gather(self, loc, out, closed=True):
+        """write the (closed: + shared edge row/column) compute region of each sub-domain into the global array"""
+        o = self.cfg.ng - 1; e = 1 if closed else 0
+        for l, (t, i0, j0) in enumerate(zip(self.sub_tile, self.sub_i0, self.sub_j0)):
+            out[t, ..., j0 + o + 1:j0 + o + 1 + self.nyl + e, i0 + o + 1:i0 + o + 1 + self.nxl + e] = \
+                loc[l, ..., o + 1:o + 1 + self.nyl + e, o + 1:o + 1 + self.nxl + e]
+        return out
+
+    def gather_add(self, loc, out):
+        """sum every copy of every cell (adjoint of scatter)"""
+        for l, (t, i0, j0) in enumerate(zip(self.sub_tile, self.sub_i0, self.sub_j0)):
+            out[t, ..., j0:j0 + self.NYl, i0:i0 + self.NXl] += loc[l]
+        return out
+
+    def scatter_c(self, a):
+        """compute-domain global array [6, nk, N, N] -> [nsub, nk, nyl, nxl]"""
+        if self.whole:
+            return np.ascontiguousarray(a)
+        return np.ascontiguousarray(np.stack([a[t, ..., j0:j0 + self.nyl, i0:i0 + self.nxl]
+                                              for t, i0, j0 in zip(self.sub_tile, self.sub_i0, self.sub_j0)]))
+
+    def gather_c(self, loc, out):
+        for l, (t, i0, j0) in enumerate(zip(self.sub_tile, self.sub_i0, self.sub_j0)):
+            out[t, ..., j0:j0 + self.nyl, i0:i0 + self.nxl] = loc[l]
+        return out
+
+    # ---- inter-rank transport ---------------------------------------------------------------------
+    def comm_init_nccl(self, id128):
+        self._check(self.lib.fv3lm_comm_init_nccl(self.h, C.c_char_p(bytes(id128))), "comm_init_nccl")
+
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(128)
+        if self.lib.fv3lm_nccl_unique_id(buf) != 0:
+            raise RuntimeError("fv3lm_nccl_unique_id failed: %s" % self.lib.fv3lm_last_error(None).decode())
+        return buf.raw
+
+    def comm_set_callback(self, fn):
+        """TEST-ONLY (host emulation): fn(peers, sendbufs, recvbufs) with numpy views"""
+        CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_size_t),
+                         C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_size_t))
+
+        def tramp(user, n, peers, sb, sc, rb, rc):
+            ps = [int(peers[k]) for k in range(n)]
+            sends = [np.ctypeslib.as_array(sb[k], shape=(int(sc[k]),)) if sc[k] else np.zeros(0) for k in range(n)]
+            recvs = [np.ctypeslib.as_array(rb[k], shape=(int(rc[k]),)) if rc[k] else np.zeros(0) for k in range(n)]
+            fn(ps, sends, recvs)
+        self._cb = CB(tramp)
+        self._check(self.lib.fv3lm_comm_set_callback(self.h, self._cb, None), "comm_set_callback")
+
+    def comm_stats(self):
+        out = (C.c_double * 2)()
+        self.lib.fv3lm_comm_stats(self.h, out)
+        return int(out[0]), float(out[1])
 
     def _check(self, rc, what):
         if rc != 0:
@@ -103,7 +185,10 @@ class FV3LM:
         """M: dict from oracle.grid.build_metrics (or the host model's gridstruct)"""
         dp = C.POINTER(C.c_double)
         def up(name, arr, is1d):
-            a = np.ascontiguousarray(arr, dtype=np.float64)
+            if is1d:
+                a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64)[self.sub_tile])
+            else:
+                a = np.ascontiguousarray(self.scatter(np.asarray(arr, dtype=np.float64)), dtype=np.float64)
             self._check(self.lib.fv3lm_set_metric(self.h, name.encode(), a.ctypes.data_as(dp), int(is1d)), "set_metric " + name)
         for n in METRICS_2D:
             up(n, M[n], False)

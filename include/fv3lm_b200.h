@@ -17,6 +17,7 @@
  */
 #ifndef FV3LM_B200_H
 #define FV3LM_B200_H
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -41,7 +42,11 @@ typedef struct fv3lm_config {
   double dddmp, d2_bg, d4_bg, vtdm4, d2_bg_k1, d2_bg_k2, d_ext, beta;
   double zvir, kappa, cp, rdgas, grav;   /* physical constants (both constant sets, SURVEY G) */
   int do_vort_damp;
-  int reserved[16];
+  /* domain decomposition (tools/fv_mp_nlm_mod.F90:411-441): this process is `rank` of `nranks`
+   * (one process per GPU); each tile is split layout_x x layout_y (0 = choose automatically) and
+   * the 6*layout_x*layout_y sub-domains are dealt out in consecutive blocks.  nranks = 0 means 1. */
+  int rank, nranks, layout_x, layout_y;
+  int reserved[12];
 } fv3lm_config;
 
 int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv3lm_handle** out);
@@ -87,6 +92,23 @@ int fv3lm_step_ad_dev(fv3lm_handle* h, int slot);
 int fv3lm_time_steps(fv3lm_handle* h, int slot, int warmup, int iters, double* ms_tl_ad);
 int fv3lm_program_stats(fv3lm_handle* h, const char* module, double* out4);
 int fv3lm_profile_steps(fv3lm_handle* h, int slot, int iters, char* buf, int buflen);   /* per-op event times, text */
+
+/* ---- domain decomposition and inter-rank halo exchange (one process per GPU) -------------------
+ * Replaces FMS mpp_define_mosaic / mpp_update_domains(_ad) / mpp_get_boundary(_ad)
+ * (tools/fv_mp_nlm_mod.F90:285-591, model_tlmadm/fv_mp_tlm.F90:420-852, fv_mp_adm.F90:488-725).
+ * With cfg.nranks > 1 every array of the API holds only this rank's sub-domains:
+ *   halo'd fields  [nsub][nk][nyl + 7][nxl + 7],  step-level fields [nsub][nk][nyl][nxl],
+ * sub-domain l of this rank = tile[l], tile-global origin (i0[l], j0[l]) from fv3lm_decomp_info.
+ * Rank 0 obtains a 128-byte NCCL id with fv3lm_nccl_unique_id, the host broadcasts it (MPI / FMS in
+ * the Fortran host), every rank passes it to fv3lm_comm_init_nccl. */
+int fv3lm_decomp_info(const fv3lm_handle* h, int* out6, int* tile, int* i0, int* j0);
+int fv3lm_nccl_unique_id(char* out128);
+int fv3lm_comm_init_nccl(fv3lm_handle* h, const char* id128);
+int fv3lm_comm_stats(const fv3lm_handle* h, double* out2);   /* exchanges issued, bytes sent */
+/* TEST-ONLY transport of the host-emulation build (tests/ drive it with torch.distributed gloo) */
+typedef void (*fv3lm_exchange_fn)(void* user, int npeers, const int* peers, double* const* sendbuf, const size_t* sendcount,
+                                  double* const* recvbuf, const size_t* recvcount);
+int fv3lm_comm_set_callback(fv3lm_handle* h, fv3lm_exchange_fn fn, void* user);
 
 /* counters for bench.py */
 long long fv3lm_launch_count(void);

@@ -22,6 +22,7 @@ def ograd(N):
 
 
 _handles = {}
+LAYOUT = None      # tests/test_decomp.py sets (lx, ly): check_module then compares whole tiles against that layout
 
 
 def handle(N, K, emu, ak=None, bk=None, **kw):
@@ -30,6 +31,7 @@ def handle(N, K, emu, ak=None, bk=None, **kw):
         cfg = fv3lm.default_config(N, K, **kw)
         h = fv3lm.FV3LM(cfg, ak, bk, emu=emu)
         h.set_metrics(metrics(N))
+        h._args = (N, K, emu, ak, bk, dict(kw))
         _handles[key] = h
     return _handles[key]
 
@@ -49,8 +51,64 @@ def region(a, i0, i1, j0, j1):
     return a[..., R(j0, j1), R(i0, i1)]
 
 
+def check_layout(h, h2, module, N, inputs, active, outs, params, rng, out_nk, K, pert_scale, tol=1e-11):
+    """Self-consistency of the domain decomposition: the same module on handle h (whole tiles) and on
+    h2 (tiles split into layout sub-domains, possibly several per rank) must agree for NL, TL and AD.
+    Adjoint seeds live on owned cells (1..N, 1..N) so that every seed has exactly one owner."""
+    import fv3lm
+    names = list(inputs.keys()); onames = list(outs.keys())
+    NX = N + 7
+    zero = lambda o=None: np.zeros((6, out_nk.get(o, K), NX, NX))
+    clip = lambda r: (max(r[0], 1), min(r[1], N + 1), max(r[2], 1), min(r[3], N + 1))
+    own = lambda r: (max(r[0], 1), min(r[1], N), max(r[2], 1), min(r[3], N))
+    dp = {n: rnd(rng, N, inputs[n].shape[1]) * (np.abs(inputs[n]).mean() * pert_scale + 1e-30) for n in active}
+    yb = {}
+    for o in onames:
+        y = zero(o); region(y, *own(outs[o]))[...] = region(rnd(rng, N, y.shape[1]), *own(outs[o])); yb[o] = y
+    res = {}
+    def run(hh, mode):
+        glob = hh.whole
+        sc = (lambda a: a.copy()) if glob else hh.scatter
+        traj = {n: sc(inputs[n]) for n in names}
+        for o in onames:
+            if o not in traj:
+                traj[o] = sc(zero(o))
+        pert = None
+        if mode == fv3lm.MODE_TL:
+            pert = {n: sc(dp[n]) for n in active}
+            for o in onames:
+                if o not in pert:
+                    pert[o] = sc(zero(o))
+        elif mode == fv3lm.MODE_AD:
+            pert = {n: sc(np.zeros_like(inputs[n])) for n in active}
+            for o in onames:
+                if o not in active:
+                    pert[o] = yb[o].copy() if glob else hh.scatter_owned(yb[o])
+        hh.module_run(module, mode, traj, pert, params=params)
+        if mode == fv3lm.MODE_AD:
+            return {n: (pert[n] if glob else hh.gather_add(pert[n], np.zeros_like(inputs[n]))) for n in active}
+        src = traj if mode == fv3lm.MODE_NL else pert
+        return {o: (src[o] if glob else hh.gather(src[o], zero(o))) for o in onames}
+    for mode, tag in ((fv3lm.MODE_NL, "nl"), (fv3lm.MODE_TL, "tl"), (fv3lm.MODE_AD, "ad")):
+        a = run(h, mode); b = run(h2, mode)
+        for k in a:
+            if mode == fv3lm.MODE_AD:
+                e = relerr(b[k], a[k])
+            else:
+                e = relerr(region(b[k], *clip(outs[k])), region(a[k], *clip(outs[k])))
+            res["layout.%s.%s" % (tag, k)] = e
+            assert e < tol, ("layout", tag, k, e)
+    return res
+
+
 def check_module(h, module, N, K, inputs, active, outs, oracle_fn, params, rng, tol=1e-12, dot_tol=1e-13,
-                 pert_scale=1e-2, tol_tl=None, tol_ad=None, out_nk=None, modes=("nl", "tl", "ad")):
+                 pert_scale=1e-2, tol_tl=None, tol_ad=None, out_nk=None, modes=("nl", "tl", "ad"), h2=None):
+    if h2 is None and LAYOUT is not None:
+        N_, K_, emu_, ak_, bk_, kw_ = h._args
+        kw_ = dict(kw_); kw_.update(layout_x=LAYOUT[0], layout_y=LAYOUT[1])
+        h2 = handle(N_, K_, emu_, ak_, bk_, **kw_)
+    if h2 is not None:
+        return check_layout(h, h2, module, N, inputs, active, outs, params, rng, out_nk or {}, K, pert_scale)
     """Generic parity check of one kernel family through the C ABI against the oracle.
     inputs : dict name -> ndarray (all inputs of the module, in module order)
     active : names of the inputs that carry perturbations / adjoints

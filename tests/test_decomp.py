@@ -1,0 +1,44 @@
+"""Domain decomposition: every kernel family run on whole tiles and on tiles split into
+layout(lx, ly) sub-domains (24 sub-domains batched on one rank) must agree for NL, TL and AD.  The
+inter-rank transport itself is covered by tests/test_multirank.py (world_size 2, gloo)."""
+import pytest
+import common
+import test_tp_core, test_c_sw, test_d_sw, test_dyn_core, test_fv_dynamics, test_nh
+
+CASES = {
+    "fv_tp_2d": lambda emu: test_tp_core._run(emu, 2),
+    "c_sw": lambda emu: test_c_sw._run(emu, False),
+    "d_sw": lambda emu: test_d_sw._run_dsw(emu, False, False),
+    "a2b_ord4": lambda emu: test_d_sw._run_a2b(emu),
+    "dyn_core": lambda emu: test_dyn_core._run(emu, 2),
+    "remap": lambda emu: test_fv_dynamics._run_remap(emu, True),
+    "update_dz_c": lambda emu: test_nh._run_dzc(emu),
+    "update_dz_d": lambda emu: test_nh._run_dzd(emu),
+    "dyn_core_nh": lambda emu: test_nh._run_dyn_nh(emu, 2),
+    "step_hydro": lambda emu: test_fv_dynamics._run_step(emu, 1, 2),
+    "step_nonhydro": lambda emu: test_fv_dynamics._run_step(emu, 1, 2, nonhydro=True),
+}
+
+
+def _layout(case, emu, layout):
+    common.LAYOUT = layout
+    try:
+        return CASES[case](emu)
+    finally:
+        common.LAYOUT = None
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_layout_2x2_emu(case):
+    print(_layout(case, True, (2, 2)))
+
+
+@pytest.mark.parametrize("case", ["d_sw", "step_nonhydro"])
+def test_layout_1x2_emu(case):
+    print(_layout(case, True, (1, 2)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["dyn_core", "step_nonhydro"])
+def test_layout_2x2_gpu(case):
+    _layout(case, False, (2, 2))

