@@ -7,10 +7,6 @@ namespace fv3lm {
 namespace a2b {
 constexpr double a1 = 0.5625, a2 = -0.0625, b1 = 7.0 / 12.0, b2 = -1.0 / 12.0, c1 = 2.0 / 3.0, c2 = -1.0 / 6.0, r3 = 1.0 / 3.0;
 
-DEV double gc_dist(double lon1, double lat1, double lon2, double lat2) {
-  double s1 = sin(0.5 * (lat1 - lat2)), s2 = sin(0.5 * (lon1 - lon2));
-  return 2.0 * asin(sqrt(s1 * s1 + cos(lat1) * cos(lat2) * s2 * s2));
-}
 }  // namespace a2b
 
 // qx (DIR 0) / qy (DIR 1): 1-D PPM-form interpolation to cell faces (:108-149 / :152-194)
@@ -65,13 +61,13 @@ struct S_a2b_edge {
   struct P { int dummy; };
   static constexpr int NT = 8;
   static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {0, 1, 1, 0}, {0, -1, 0, 0}, {0, -2, 1, 0}, {0, 0, -1, 0}, {0, 1, -2, 0}, {0, -1, -1, 0}, {0, -2, -2, 0}};
-  template <class X> DEV static typename X::T corner(const X& x, int a1i, int a1j, int a2i, int a2j) {
-    // extrap_corner(p0 = this corner, p1 = agrid(a1), p2 = agrid(a2), q1, q2)
-    double l0 = x.M(x.m.grid_lon), t0 = x.M(x.m.grid_lat);
-    double x1 = a2b::gc_dist(x.Mabs(x.m.agrid_lon, a1i, a1j), x.Mabs(x.m.agrid_lat, a1i, a1j), l0, t0);
-    double x2 = a2b::gc_dist(x.Mabs(x.m.agrid_lon, a2i, a2j), x.Mabs(x.m.agrid_lat, a2i, a2j), l0, t0);
+  // extrap_corner(p0 = this corner, p1 = agrid(a1), p2 = agrid(a2), q1, q2) = q1 + x1/(x2-x1) (q1-q2) with the
+  // great-circle distances x1, x2 (a2b_edge_nlm.F90:800-810).  The weight is pure geometry: it is precomputed once
+  // per tile corner (fv3lm_set_metric -> a2b_cw[corner * 3 + n]) instead of 6 haversines per corner thread.
+  template <class X> DEV static typename X::T corner(const X& x, int cn, int a1i, int a1j, int a2i, int a2j) {
+    const double w = x.m.a2b_cw[(size_t)x.tile * x.g.slab + cn];
     auto q1 = x.in(0, a1i - x.i, a1j - x.j), q2 = x.in(0, a2i - x.i, a2j - x.j);
-    return q1 + x1 / (x2 - x1) * (q1 - q2);
+    return q1 + w * (q1 - q2);
   }
   template <class X> DEV static void eval(X& x, const P&) {
     using T = typename X::T;
@@ -82,10 +78,10 @@ struct S_a2b_edge {
     if (!ei && !ej) return;
     T r;
     if (ei && ej) {
-      if (i == 1 && j == 1) r = (corner(x, 1, 1, 2, 2) + corner(x, 0, 1, -1, 2) + corner(x, 1, 0, 2, -1)) * a2b::r3;
-      else if (i == npx && j == 1) r = (corner(x, npx - 1, 1, npx - 2, 2) + corner(x, npx - 1, 0, npx - 2, -1) + corner(x, npx, 1, npx + 1, 2)) * a2b::r3;
-      else if (i == npx && j == npy) r = (corner(x, npx - 1, npy - 1, npx - 2, npy - 2) + corner(x, npx, npy - 1, npx + 1, npy - 2) + corner(x, npx - 1, npy, npx - 2, npy + 1)) * a2b::r3;
-      else r = (corner(x, 1, npy - 1, 2, npy - 2) + corner(x, 0, npy - 1, -1, npy - 2) + corner(x, 1, npy, 2, npy + 1)) * a2b::r3;
+      if (i == 1 && j == 1) r = (corner(x, 0, 1, 1, 2, 2) + corner(x, 1, 0, 1, -1, 2) + corner(x, 2, 1, 0, 2, -1)) * a2b::r3;
+      else if (i == npx && j == 1) r = (corner(x, 3, npx - 1, 1, npx - 2, 2) + corner(x, 4, npx - 1, 0, npx - 2, -1) + corner(x, 5, npx, 1, npx + 1, 2)) * a2b::r3;
+      else if (i == npx && j == npy) r = (corner(x, 6, npx - 1, npy - 1, npx - 2, npy - 2) + corner(x, 7, npx, npy - 1, npx + 1, npy - 2) + corner(x, 8, npx - 1, npy, npx - 2, npy + 1)) * a2b::r3;
+      else r = (corner(x, 9, 1, npy - 1, 2, npy - 2) + corner(x, 10, 0, npy - 1, -1, npy - 2) + corner(x, 11, 1, npy, 2, npy + 1)) * a2b::r3;
     } else if (ei) {
       // q2(j) = (qin(i-1,j)*dxa(i,j) + qin(i,j)*dxa(i-1,j)) / (dxa(i-1,j)+dxa(i,j))
       auto q2 = [&](int dj) { return (x.in(0, -1, dj) * x.M(x.m.dxa, 0, dj) + x.in(0, 0, dj) * x.M(x.m.dxa, -1, dj)) / (x.M(x.m.dxa, -1, dj) + x.M(x.m.dxa, 0, dj)); };
@@ -140,6 +136,38 @@ int build_a2b_ord4(Program& P, Mosaic& mo, int qin, int nk, const std::string& t
   P.add<S_a2b_edge>("a2b_edge", {0}, {qin}, {qe}, nk);
   P.add<S_a2b_q2>("a2b_q2", {0}, {qx, qy, qe}, {qout}, nk);
   return qout;
+}
+
+// host: the 12 extrap_corner weights of every resident sub-domain that holds a tile corner
+// (lon/lat arrays are the local [ntile][NY][NX] host copies of grid and agrid)
+void a2b_corner_weights(const Geom& g, const double* glon, const double* glat, const double* alon, const double* alat, double* out /* [ntile][12] */) {
+  const int o = g.ng - 1, npx = g.npx, npy = g.npy;
+  auto gc = [](double lon1, double lat1, double lon2, double lat2) {
+    double s1 = sin(0.5 * (lat1 - lat2)), s2 = sin(0.5 * (lon1 - lon2));
+    return 2.0 * asin(sqrt(s1 * s1 + cos(lat1) * cos(lat2) * s2 * s2));
+  };
+  // {corner point, a1, a2} in tile-global indices, same order as S_a2b_edge::eval
+  const int T[12][6] = {{1, 1, 1, 1, 2, 2}, {1, 1, 0, 1, -1, 2}, {1, 1, 1, 0, 2, -1},
+                        {npx, 1, npx - 1, 1, npx - 2, 2}, {npx, 1, npx - 1, 0, npx - 2, -1}, {npx, 1, npx, 1, npx + 1, 2},
+                        {npx, npy, npx - 1, npy - 1, npx - 2, npy - 2}, {npx, npy, npx, npy - 1, npx + 1, npy - 2}, {npx, npy, npx - 1, npy, npx - 2, npy + 1},
+                        {1, npy, 1, npy - 1, 2, npy - 2}, {1, npy, 0, npy - 1, -1, npy - 2}, {1, npy, 1, npy, 2, npy + 1}};
+  for (int t = 0; t < g.ntile; t++)
+    for (int n = 0; n < 12; n++) {
+      out[t * 12 + n] = 0.0;
+      auto at = [&](const double* a, int i, int j, bool& ok) {
+        int ii = i - g.i0[t] + o, jj = j - g.j0[t] + o;
+        if (ii < 0 || ii >= g.NX || jj < 0 || jj >= g.NY) { ok = false; return 0.0; }
+        return a[((size_t)t * g.NY + jj) * g.NX + ii];
+      };
+      bool ok = true;
+      // the corner point must be one this sub-domain computes (is..ie+1, js..je+1)
+      int il = T[n][0] - g.i0[t], jl = T[n][1] - g.j0[t];
+      if (il < 1 || il > g.ie + 1 || jl < 1 || jl > g.je + 1) continue;
+      double l0 = at(glon, T[n][0], T[n][1], ok), t0 = at(glat, T[n][0], T[n][1], ok);
+      double x1 = gc(at(alon, T[n][2], T[n][3], ok), at(alat, T[n][2], T[n][3], ok), l0, t0);
+      double x2 = gc(at(alon, T[n][4], T[n][5], ok), at(alat, T[n][4], T[n][5], ok), l0, t0);
+      if (ok) out[t * 12 + n] = x1 / (x2 - x1);
+    }
 }
 
 void mod_a2b_ord4(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams&) {

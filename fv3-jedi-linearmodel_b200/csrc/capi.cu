@@ -2,6 +2,7 @@
 #include "capi_internal.h"
 
 using namespace fv3lm;
+namespace fv3lm { void a2b_corner_weights(const Geom& g, const double* glon, const double* glat, const double* alon, const double* alat, double* out); }
 
 thread_local std::string fv3lm_g_err;
 
@@ -104,6 +105,21 @@ int fv3lm_set_metric(fv3lm_handle* h, const char* name, const double* host, int 
   FV3LM_METRIC_LIST(X)
 #undef X
   if (!found) throw std::runtime_error("fv3lm_set_metric: unknown metric " + nm);
+  if (nm == "grid_lon" || nm == "grid_lat" || nm == "agrid_lon" || nm == "agrid_lat") {
+    h->geo_host[nm].assign(host, host + (size_t)g.ntile * g.NY * g.NX);
+    if (h->geo_host.size() == 4) {
+      // a2b_ord4 corner extrapolation weights (a2b_edge_nlm.F90:73-106): geometry only, computed once
+      std::vector<double> w((size_t)g.ntile * 12), slabs((size_t)g.ntile * g.slab, 0.0);
+      a2b_corner_weights(g, h->geo_host["grid_lon"].data(), h->geo_host["grid_lat"].data(), h->geo_host["agrid_lon"].data(),
+                         h->geo_host["agrid_lat"].data(), w.data());
+      for (int t = 0; t < g.ntile; t++) for (int n = 0; n < 12; n++) slabs[(size_t)t * g.slab + n] = w[t * 12 + n];
+      double*& dw = h->metric_dev["a2b_cw"];
+      if (!dw) dw = (double*)dev::alloc(slabs.size() * sizeof(double));
+      dev::h2d(dw, slabs.data(), slabs.size() * sizeof(double));
+      dev::sync();
+      h->dv.m.a2b_cw = dw;
+    }
+  }
   FV3LM_CATCH(h)
 }
 

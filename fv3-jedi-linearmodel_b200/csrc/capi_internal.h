@@ -27,6 +27,7 @@ struct fv3lm_handle {
   fv3lm::Comm comm;
   std::vector<double> ak, bk;
   std::map<std::string, double*> metric_dev;
+  std::map<std::string, std::vector<double>> geo_host;   // grid / agrid lon-lat kept to derive a2b_cw
   std::string err;
   StepRunner* step = nullptr;
 };

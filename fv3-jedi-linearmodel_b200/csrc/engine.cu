@@ -41,12 +41,23 @@ void check(const char*) {}
 }  // namespace dev
 
 // ---------------------------------------------------------------------------------
-double* Pool::get(size_t n) {
+double* Pool::get(size_t n, bool* fresh) {
   size_t bytes = n * sizeof(double);
   auto& fl = free_[bytes];
   void* p;
-  if (!fl.empty()) { p = fl.back(); fl.pop_back(); }
-  else { p = dev::alloc(bytes); bytes_total += bytes; }
+  if (fresh) *fresh = false;
+  if (!fl.empty()) {
+    p = fl.back(); fl.pop_back();
+#ifdef FV3LM_HOST_EMU
+    // TEST-ONLY build: recycled buffers are poisoned so that any stage consuming a cell its producer
+    // never wrote shows up as NaN in the parity tests (the product build hands them out as they are)
+    if (fresh) { double* q = (double*)p; for (size_t k = 0; k < n; k++) q[k] = NAN; }
+#endif
+  } else {
+    p = dev::alloc(bytes); bytes_total += bytes;
+    // fresh device memory may hold NaN bit patterns: zero it once; recycled buffers keep stale (finite) data
+    if (fresh) { dev::zero(p, bytes); *fresh = true; }
+  }
   live_[p] = bytes;
   bytes_live += bytes;
   bytes_peak = std::max(bytes_peak, bytes_live);
@@ -93,23 +104,24 @@ void Program::ensure_traj(int id) {
   Value& v = vals[id];
   if (!v.traj) {
     if (v.external) throw std::runtime_error("external value without storage: " + v.name);
-    v.traj = dv->pool.get(val_doubles(id));
-    // intermediates are only defined on the range their producer writes; zero the
-    // rest so that nothing downstream can pick up NaNs from recycled memory
-    dev::zero(v.traj, val_doubles(id) * sizeof(double));
+    // intermediates are only defined on the range their producer writes and consumers only read
+    // that range, so recycled buffers are NOT cleared (a full-array memset per op otherwise)
+    bool fresh;
+    v.traj = dv->pool.get(val_doubles(id), &fresh);
   }
 }
+// zero_it: adjoint accumulators must start from zero; tangents (TL) are fully defined by their producer
 void Program::ensure_pert(int id, bool zero_it) {
   Value& v = vals[id];
   if (!v.active) return;
-  if (!v.pert) {
-    if (v.external) throw std::runtime_error("external active value without pert storage: " + v.name);
-    v.pert = dv->pool.get(val_doubles(id));
-    zero_it = true;
-  } else {
-    zero_it = false;
-  }
+  if (v.pert) return;
+  if (v.external) throw std::runtime_error("external active value without pert storage: " + v.name);
+  bool fresh;
+  v.pert = dv->pool.get(val_doubles(id), &fresh);
+  if (zero_it && !fresh) dev::zero(v.pert, val_doubles(id) * sizeof(double));
+#ifdef FV3LM_HOST_EMU
   if (zero_it) dev::zero(v.pert, val_doubles(id) * sizeof(double));
+#endif
 }
 void Program::release(int id) {
   Value& v = vals[id];
@@ -119,6 +131,26 @@ void Program::release(int id) {
 }
 
 void Program::run_op(Op& op, int mode) {
+#ifdef FV3LM_HOST_EMU
+  static const bool nancheck = getenv("FV3LM_NANCHECK") != nullptr;
+  if (nancheck && mode == MODE_AD) {
+    op.run(*this, op, mode);
+    for (int i : op.in) {
+      Value& v = vals[i];
+      if (!v.pert) continue;
+      size_t n = val_doubles(i), bad = 0, first = 0;
+      for (size_t q = 0; q < n; q++) if (v.pert[q] != v.pert[q]) { if (!bad) first = q; bad++; }
+      if (bad) {
+        const Geom& g = dv->g;
+        size_t pos = first % g.slab;
+        fprintf(stderr, "NANCHECK ad op %s: adjoint of input %s has %zu NaN, first at tile/k %zu jj=%zu ii=%zu\n", op.name.c_str(), v.name.c_str(), bad,
+                first / g.slab, pos / g.pitch, pos % g.pitch);
+        static int cnt = 0; if (++cnt > 6) exit(3);
+      }
+    }
+    return;
+  }
+#endif
   if (!dev::profiling) { op.run(*this, op, mode); return; }
 #ifndef FV3LM_HOST_EMU
   static cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -151,7 +183,7 @@ void Program::run(Mode mode) {
   if (mode == MODE_NL || mode == MODE_TL) {
     for (int n = 0; n < nop; n++) {
       Op& op = ops[n];
-      for (int o : op.out) { ensure_traj(o); if (mode == MODE_TL) ensure_pert(o, true); }
+      for (int o : op.out) { ensure_traj(o); if (mode == MODE_TL) ensure_pert(o, false); }
       run_op(op, mode);
       // free values whose last use was this op
       for (int i : op.in) if (vals[i].last_use == n) release(i);

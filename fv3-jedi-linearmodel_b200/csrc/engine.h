@@ -57,8 +57,9 @@ struct Geom {
   X(sin_sg3) X(sin_sg4) X(cos_sg1) X(cos_sg2) X(cos_sg3) X(cos_sg4) X(divg_u) X(divg_v)   \
   X(del6_u) X(del6_v) X(f0) X(fC) X(agrid_lon) X(agrid_lat) X(grid_lon) X(grid_lat)       \
   X(edge_w) X(edge_e) X(edge_s) X(edge_n) X(edge_vect_w) X(edge_vect_e) X(edge_vect_s)    \
-  X(edge_vect_n)
-// (the edge_* arrays are 1-D, stored in row 0 of a slab so they share the layout)
+  X(edge_vect_n) X(a2b_cw)
+// (the edge_* arrays are 1-D, stored in row 0 of a slab so they share the layout; a2b_cw holds the 4 x 3
+// extrap_corner weights of a2b_ord4, derived by the library from grid / agrid once they are all uploaded)
 
 struct Metrics {
 #define X(n) const double* n;
@@ -83,9 +84,11 @@ struct CtxBase {
   int ii, jj, kk, tile;   // array column/row, level, resident sub-domain
   int i, j;               // Fortran tile-global indices
   int il, jl;             // local-frame indices (compute domain 1..nxl, 1..nyl)
-  DEV void setpos(int ii_, int jj_, int kk_, int tile_) {
+  // i0 / j0: origin of the sub-domain, read by the caller from the kernel parameter (constant bank);
+  // indexing the per-thread copy of Geom dynamically would force it into local memory
+  DEV void setpos(int ii_, int jj_, int kk_, int tile_, int i0_, int j0_) {
     ii = ii_; jj = jj_; kk = kk_; tile = tile_; il = ii_ - (g.ng - 1); jl = jj_ - (g.ng - 1);
-    i = il + g.i0[tile_]; j = jl + g.j0[tile_];
+    i = il + i0_; j = jl + j0_;
   }
   // metric at relative offset
   DEV double M(const double* a, int di = 0, int dj = 0) const {
@@ -93,7 +96,7 @@ struct CtxBase {
   }
   // metric at absolute Fortran index
   DEV double Mabs(const double* a, int ai, int aj) const {
-    return a[(size_t)tile * g.slab + (size_t)(aj - g.j0[tile] + g.ng - 1) * g.pitch + (ai - g.i0[tile] + g.ng - 1)];
+    return a[(size_t)tile * g.slab + (size_t)(aj - (j - jl) + g.ng - 1) * g.pitch + (ai - (i - il) + g.ng - 1)];
   }
   // 1-D edge array (stored whole-tile in the head of the slab), tile-global Fortran index
   DEV double M1(const double* a, int ai) const { return a[(size_t)tile * g.slab + (ai + g.ng - 1)]; }
@@ -142,7 +145,12 @@ template <class S> struct CtxAD : CtxBase {
     return Dual(in_.p[f][off(in_.nk[f], di, dj, dk)], (f == sf && di == sdi && dj == sdj && dk == sdk) ? 1.0 : 0.0);
   }
   DEV void out(int o, T v) {
-    if (outad_.p[o]) acc += v.d * outad_.p[o][off(outad_.nk[o], 0, 0, 0)];
+    if (outad_.p[o]) {
+      // an output cell nobody consumed has a zero adjoint; its value may be computed from cells that were
+      // never written (generous loop ranges), so it must not enter the sum as 0 * garbage
+      const double a = outad_.p[o][off(outad_.nk[o], 0, 0, 0)];
+      if (a != 0.0) acc += v.d * a;
+    }
   }
 };
 
@@ -153,7 +161,7 @@ template <class S> struct KernNL {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in; FArr<S::NO> out; int nk;
   DEV void operator()(int ii, int jj, int z) const {
     CtxNL<S> x; x.g = g; x.m = m; x.in_ = in; x.out_ = out;
-    x.setpos(ii, jj, z % nk, z / nk);
+    x.setpos(ii, jj, z % nk, z / nk, g.i0[z / nk], g.j0[z / nk]);
     S::eval(x, p);
   }
 };
@@ -161,7 +169,7 @@ template <class S> struct KernTL {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in, ind; FArr<S::NO> out, outd; int nk;
   DEV void operator()(int ii, int jj, int z) const {
     CtxTL<S> x; x.g = g; x.m = m; x.in_ = in; x.ind_ = ind; x.out_ = out; x.outd_ = outd;
-    x.setpos(ii, jj, z % nk, z / nk);
+    x.setpos(ii, jj, z % nk, z / nk, g.i0[z / nk], g.j0[z / nk]);
     S::eval(x, p);
   }
 };
@@ -178,7 +186,7 @@ template <class S, int n> struct AdTaps {
             for (int ok = 0; ok < kn.nk_fwd; ok++) {
               CtxAD<S> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in; x.outad_ = kn.outad;
               x.sf = t.f; x.sdi = t.di; x.sdj = t.dj; x.sdk = t.dk; x.acc = 0.0;
-              x.setpos(oi, oj, ok, tile);
+              x.setpos(oi, oj, ok, tile, kn.g.i0[tile], kn.g.j0[tile]);
               S::eval(x, kn.p);
               acc[t.f] += x.acc;
             }
@@ -188,7 +196,7 @@ template <class S, int n> struct AdTaps {
           if (ok >= 0 && ok < kn.nk_fwd) {
             CtxAD<S> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in; x.outad_ = kn.outad;
             x.sf = t.f; x.sdi = t.di; x.sdj = t.dj; x.sdk = t.dk; x.acc = 0.0;
-            x.setpos(oi, oj, ok, tile);
+            x.setpos(oi, oj, ok, tile, kn.g.i0[tile], kn.g.j0[tile]);
             S::eval(x, kn.p);
             acc[t.f] += x.acc;
           }
@@ -270,7 +278,7 @@ struct Pool {
   std::map<size_t, std::vector<void*>> free_;
   std::map<void*, size_t> live_;
   size_t bytes_total = 0, bytes_peak = 0, bytes_live = 0;
-  double* get(size_t n_doubles);
+  double* get(size_t n_doubles, bool* fresh = nullptr);   // fresh != null: zero new memory, report whether it was new
   void put(double* p);
   void trim();
   ~Pool();
@@ -362,21 +370,28 @@ template <class S> struct ColAD : CtxBase {
 template <class S> struct KernColNL {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in; FArr<S::NO> out;
   DEV void operator()(int ii, int jj, int z) const {
-    ColNL<S> x; x.g = g; x.m = m; x.in_ = in; x.out_ = out; x.setpos(ii, jj, 0, z);
+    ColNL<S> x; x.g = g; x.m = m; x.in_ = in; x.out_ = out; x.setpos(ii, jj, 0, z, g.i0[z], g.j0[z]);
     S::eval(x, p);
   }
 };
 template <class S> struct KernColTL {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in, ind; FArr<S::NO> out, outd;
   DEV void operator()(int ii, int jj, int z) const {
-    ColTL<S> x; x.g = g; x.m = m; x.in_ = in; x.ind_ = ind; x.out_ = out; x.outd_ = outd; x.setpos(ii, jj, 0, z);
+    ColTL<S> x; x.g = g; x.m = m; x.in_ = in; x.ind_ = ind; x.out_ = out; x.outd_ = outd; x.setpos(ii, jj, 0, z, g.i0[z], g.j0[z]);
     S::eval(x, p);
   }
 };
 template <class S> struct KernColAD {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in, inad; FArr<S::NO> out, outad;
   DEV void operator()(int ii, int jj, int z) const {
-    ColAD<S> x; x.g = g; x.m = m; x.in_ = in; x.inad_ = inad; x.out_ = out; x.outad_ = outad; x.setpos(ii, jj, 0, z);
+    ColAD<S> x; x.g = g; x.m = m; x.in_ = in; x.inad_ = inad; x.out_ = out; x.outad_ = outad; x.setpos(ii, jj, 0, z, g.i0[z], g.j0[z]);
+    // a column whose outputs nobody consumed (all adjoints zero) contributes nothing; skipping it also keeps
+    // 0 * (values derived from never-written cells) out of the sums
+    bool any = false;
+#pragma unroll
+    for (int o = 0; o < S::NO; o++)
+      if (outad.p[o]) for (int k = 0; k < outad.nk[o] && !any; k++) any = x.oad(o, k) != 0.0;
+    if (!any) return;
     S::eval_ad(x, p);
   }
 };

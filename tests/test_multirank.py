@@ -126,3 +126,15 @@ def _check(world, nonhydro):
 @pytest.mark.parametrize("world,nonhydro", [(2, False), (2, True), (4, True)])
 def test_multirank_step_gloo(world, nonhydro):
     _check(world, nonhydro)
+
+
+@pytest.mark.gpu
+def test_multirank_step_nccl_gpu():
+    """product build, NCCL transport: needs >= 2 GPUs (skipped on a single-GPU box)"""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py"), "--nonhydro"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
