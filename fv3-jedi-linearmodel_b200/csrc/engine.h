@@ -23,6 +23,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <type_traits>
 #include "platform.h"
 #include "dual.h"
 
@@ -174,31 +175,89 @@ template <class S> struct KernTL {
   }
 };
 
+// ---- taps grouped by stencil offset --------------------------------------------------------------
+// The reverse sweep needs d(out)/d(tap) for every tap.  Taps of DIFFERENT input fields at the SAME offset
+// (di, dj, dk) are read by the same output cell, so one evaluation of the stage there with a multi-seed
+// dual number (DualN<M>, M = fields at that offset) yields all M derivatives at once: the number of stage
+// evaluations per thread drops from NT (taps) to the number of distinct offsets.
+template <class S> struct TapInfo {
+  static constexpr bool same(int a, int b) {
+    return S::taps[a].di == S::taps[b].di && S::taps[a].dj == S::taps[b].dj && S::taps[a].dk == S::taps[b].dk;
+  }
+  static constexpr bool leader(int n) { for (int m = 0; m < n; m++) if (same(m, n)) return false; return true; }
+  static constexpr int count(int n) { int c = 0; for (int m = 0; m < S::NT; m++) if (same(m, n)) c++; return c; }
+  // input field of the m-th tap that shares the offset of tap n
+  static constexpr int field(int n, int m) {
+    int c = 0;
+    for (int q = 0; q < S::NT; q++) if (same(q, n)) { if (c == m) return S::taps[q].f; c++; }
+    return -1;
+  }
+};
+
+template <class S, int n> struct CtxADN : CtxBase {
+  static constexpr int NM = TapInfo<S>::count(n);
+  using T = DualN<NM>;
+  static constexpr int mode = 2;
+  FArr<S::NI> in_; FArr<S::NO> outad_;
+  double acc[NM];
+  template <int m> DEV static void seed(T& r, int f) {
+    if constexpr (m < NM) {
+      constexpr int fm = TapInfo<S>::field(n, m);
+      r.d[m] = (f == fm) ? 1.0 : 0.0;
+      seed<m + 1>(r, f);
+    }
+  }
+  DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const {
+    constexpr Tap t = S::taps[n];
+    T r(in_.p[f][off(in_.nk[f], di, dj, dk)]);
+    if (di == t.di && dj == t.dj && dk == t.dk) seed<0>(r, f);
+    return r;
+  }
+  DEV void out(int o, const T& v) {
+    if (outad_.p[o]) {
+      // an output cell nobody consumed has a zero adjoint; its value may be computed from cells that were
+      // never written (generous loop ranges), so it must not enter the sum as 0 * garbage
+      const double a = outad_.p[o][off(outad_.nk[o], 0, 0, 0)];
+      if (a != 0.0) {
+#pragma unroll
+        for (int m = 0; m < NM; m++) acc[m] += v.d[m] * a;
+      }
+    }
+  }
+};
+
+template <class S, int n, int m> struct AdScatter {
+  DEV static void run(const double* src, double* acc) {
+    if constexpr (m < TapInfo<S>::count(n)) {
+      constexpr int fm = TapInfo<S>::field(n, m);
+      acc[fm] += src[m];
+      AdScatter<S, n, m + 1>::run(src, acc);
+    }
+  }
+};
+
 template <class S, int n> struct AdTaps {
+  template <class K> DEV static void eval_at(const K& kn, int oi, int oj, int ok, int tile, double* acc) {
+    CtxADN<S, n> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in; x.outad_ = kn.outad;
+#pragma unroll
+    for (int m = 0; m < CtxADN<S, n>::NM; m++) x.acc[m] = 0.0;
+    x.setpos(oi, oj, ok, tile, kn.g.i0[tile], kn.g.j0[tile]);
+    S::eval(x, kn.p);
+    AdScatter<S, n, 0>::run(x.acc, acc);
+  }
   template <class K> DEV static void run(const K& kn, int ii, int jj, int kk, int tile, double* acc) {
     if constexpr (n < S::NT) {
-      constexpr Tap t = S::taps[n];
-      int oi = ii - t.di, oj = jj - t.dj;
-      if (oi >= 0 && oi < kn.g.NX && oj >= 0 && oj < kn.g.NY) {
-        if (t.dk == KLAST) {
-          // every output level reads the last level of this input: its owner sums over them
-          if (kk == kn.in.nk[t.f] - 1) {
-            for (int ok = 0; ok < kn.nk_fwd; ok++) {
-              CtxAD<S> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in; x.outad_ = kn.outad;
-              x.sf = t.f; x.sdi = t.di; x.sdj = t.dj; x.sdk = t.dk; x.acc = 0.0;
-              x.setpos(oi, oj, ok, tile, kn.g.i0[tile], kn.g.j0[tile]);
-              S::eval(x, kn.p);
-              acc[t.f] += x.acc;
-            }
-          }
-        } else {
-          int ok = kk - t.dk;
-          if (ok >= 0 && ok < kn.nk_fwd) {
-            CtxAD<S> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in; x.outad_ = kn.outad;
-            x.sf = t.f; x.sdi = t.di; x.sdj = t.dj; x.sdk = t.dk; x.acc = 0.0;
-            x.setpos(oi, oj, ok, tile, kn.g.i0[tile], kn.g.j0[tile]);
-            S::eval(x, kn.p);
-            acc[t.f] += x.acc;
+      if constexpr (TapInfo<S>::leader(n)) {
+        constexpr Tap t = S::taps[n];
+        int oi = ii - t.di, oj = jj - t.dj;
+        if (oi >= 0 && oi < kn.g.NX && oj >= 0 && oj < kn.g.NY) {
+          if (t.dk == KLAST) {
+            // every output level reads the last level of this input: its owner sums over them
+            if (kk == kn.in.nk[t.f] - 1)
+              for (int ok = 0; ok < kn.nk_fwd; ok++) eval_at(kn, oi, oj, ok, tile, acc);
+          } else {
+            int ok = kk - t.dk;
+            if (ok >= 0 && ok < kn.nk_fwd) eval_at(kn, oi, oj, ok, tile, acc);
           }
         }
       }
@@ -207,6 +266,11 @@ template <class S, int n> struct AdTaps {
   }
 };
 
+// a stage may replace the generic seeded evaluations by a hand-derived gather adjoint:
+//   static constexpr bool custom_ad = true;  template<class K> static void adjoint(kn, ii, jj, kk, tile, acc)
+template <class S, class = void> struct HasCustomAd { static constexpr bool value = false; };
+template <class S> struct HasCustomAd<S, std::enable_if_t<S::custom_ad>> { static constexpr bool value = true; };
+
 template <class S> struct KernAD {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in, inad; FArr<S::NO> outad; int nk, nk_fwd;
   DEV void operator()(int ii, int jj, int z) const {
@@ -214,7 +278,8 @@ template <class S> struct KernAD {
 #pragma unroll
     for (int f = 0; f < S::NI; f++) acc[f] = 0.0;
     int kk = z % nk, tile = z / nk;
-    AdTaps<S, 0>::run(*this, ii, jj, kk, tile, acc);
+    if constexpr (HasCustomAd<S>::value) S::adjoint(*this, ii, jj, kk, tile, acc);
+    else AdTaps<S, 0>::run(*this, ii, jj, kk, tile, acc);
 #pragma unroll
     for (int f = 0; f < S::NI; f++) {
       if (inad.p[f] && kk < inad.nk[f]) {
