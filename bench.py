@@ -13,6 +13,7 @@ with the H2D/D2H copies of trajectory and increments inside the timed region.
 import argparse
 import json
 import os
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the single JSON line
 import subprocess
 import sys
 import threading
@@ -169,6 +170,11 @@ def run_gpu(args):
         rows.append((nm, int(n), float(ms), float(b)))
     rows.sort(key=lambda r: -r[2])
     tot = sum(r[2] for r in rows)
+    if args.profile_out and rank == 0:
+        with open(args.profile_out, "w") as fh:
+            fh.write("# per-op CUDA-event profile of one TL+AD step pair (serialised pass): name launches total_ms alg_GB/s share\n")
+            for r in rows:
+                fh.write("%-28s %5d %10.3f %9.1f %6.2f%%\n" % (r[0], r[1], r[2], (r[3] / (r[2] * 1e-3) / 1e9 if r[2] > 0 else 0.0), 100.0 * r[2] / tot))
     peak, pk_src = peaks()
     top = rows[0]
     ach = top[3] / top[1] / (top[2] / top[1] * 1e-3) / 1e9 if top[2] > 0 else 0.0
@@ -284,6 +290,7 @@ def main():
     ap.add_argument("--cpu-res", type=int, default=12)
     ap.add_argument("--nonhydro", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the full per-op profile table to this file")
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: only the device-resident timed loop (used under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
