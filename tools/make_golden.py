@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.npz: outputs of the ORACLE (torch fp64 restatement) for one C12 fv3jedi_lm dynamics
+step, hydrostatic and non-hydrostatic: NL result, TL result (jvp) for a seeded increment and AD result (vjp) for a
+seeded adjoint vector.  The reference itself cannot be run here (no Fortran/FMS/MPI), so these fixtures pin the
+oracle against silent regressions between rounds -- they are NOT reference outputs (parity unpinned).
+  python tools/make_golden.py
+"""
+import os
+import sys
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "fv3-jedi-linearmodel_b200")):
+    sys.path.insert(0, p)
+
+
+def case(nonhydro):
+    from test_multirank import _inputs
+    from oracle import fv_dynamics as ofv
+    from common import ograd
+    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro)
+    g = ograd(N)
+    cfg = dict(p); cfg["hydrostatic"] = not nonhydro
+    phis = torch.from_numpy(f["phis"])
+    def fn(*a):
+        o = ofv.step_nl(dict(zip(act, a)), g, ak, bk, cfg, phis)
+        return tuple(o[k] for k in act)
+    x = tuple(torch.from_numpy(f[k]) for k in act)
+    nl, tl = torch.func.jvp(fn, x, tuple(torch.from_numpy(dx[k]) for k in act))
+    _, vjp = torch.func.vjp(fn, *x)
+    ad = vjp(tuple(torch.from_numpy(y[k + "_n"]) for k in act))
+    out = {}
+    o = 2
+    for k, a, b, c in zip(act, nl, tl, ad):
+        out["nl." + k] = a.numpy()[:, :, o + 1:o + 1 + N, o + 1:o + 1 + N]
+        out["tl." + k] = b.numpy()[:, :, o + 1:o + 1 + N, o + 1:o + 1 + N]
+        out["ad." + k] = c.numpy()[:, :, o + 1:o + 1 + N, o + 1:o + 1 + N]
+    return out
+
+
+if __name__ == "__main__":
+    torch.set_default_dtype(torch.float64)
+    for nh in (False, True):
+        out = case(nh)
+        path = os.path.join(ROOT, "tests", "golden", "step_c12_%s.npz" % ("nonhydro" if nh else "hydro"))
+        np.savez_compressed(path, **out)
+        print(path, os.path.getsize(path))
