@@ -50,6 +50,7 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
   g.NX = dc.nxl + 2 * g.ng + 1; g.NY = dc.nyl + 2 * g.ng + 1;
   g.pitch = (g.NX + 3) / 4 * 4;
   g.ntile = dc.per_rank; g.K = cfg->npz; g.slab = g.pitch * g.NY;
+  if ((double)g.ntile * (g.K + 1) * g.slab >= 2147483647.0) throw std::runtime_error("fv3lm_create: a field on this rank would exceed 2^31 elements (kernels use 32-bit offsets): use more ranks");
   if (g.slab < g.N + 2 * g.ng + 1) throw std::runtime_error("fv3lm_create: sub-domain slab smaller than a tile edge");
   for (int l = 0; l < MAXSUB; l++) { g.i0[l] = 0; g.j0[l] = 0; g.tile_of[l] = 0; }
   for (int l = 0; l < dc.per_rank; l++) {

@@ -85,31 +85,34 @@ struct CtxBase {
   int ii, jj, kk, tile;   // array column/row, level, resident sub-domain
   int i, j;               // Fortran tile-global indices
   int il, jl;             // local-frame indices (compute domain 1..nxl, 1..nyl)
+  int pos;                // jj * pitch + ii : all offsets are 32-bit (a rank's array has < 2^31 elements)
   // i0 / j0: origin of the sub-domain, read by the caller from the kernel parameter (constant bank);
   // indexing the per-thread copy of Geom dynamically would force it into local memory
   DEV void setpos(int ii_, int jj_, int kk_, int tile_, int i0_, int j0_) {
     ii = ii_; jj = jj_; kk = kk_; tile = tile_; il = ii_ - (g.ng - 1); jl = jj_ - (g.ng - 1);
     i = il + i0_; j = jl + j0_;
+    pos = jj_ * g.pitch + ii_;
   }
   // metric at relative offset
   DEV double M(const double* a, int di = 0, int dj = 0) const {
-    return a[(size_t)tile * g.slab + (size_t)(jj + dj) * g.pitch + (ii + di)];
+    return a[tile * g.slab + pos + dj * g.pitch + di];
   }
   // metric at absolute Fortran index
   DEV double Mabs(const double* a, int ai, int aj) const {
-    return a[(size_t)tile * g.slab + (size_t)(aj - (j - jl) + g.ng - 1) * g.pitch + (ai - (i - il) + g.ng - 1)];
+    return a[tile * g.slab + (aj - (j - jl) + g.ng - 1) * g.pitch + (ai - (i - il) + g.ng - 1)];
   }
   // 1-D edge array (stored whole-tile in the head of the slab), tile-global Fortran index
-  DEV double M1(const double* a, int ai) const { return a[(size_t)tile * g.slab + (ai + g.ng - 1)]; }
+  DEV double M1(const double* a, int ai) const { return a[tile * g.slab + (ai + g.ng - 1)]; }
   // loop ranges are given in the local frame
   DEV bool in_rect(int i0, int i1, int j0, int j1) const { return il >= i0 && il <= i1 && jl >= j0 && jl <= j1; }
   // tile-global rectangle (whole-tile operators such as a2b_ord4)
   DEV bool in_tile(int i0, int i1, int j0, int j1) const { return i >= i0 && i <= i1 && j >= j0 && j <= j1; }
-  DEV size_t off(int nkf, int di, int dj, int dk) const {
-    int k = (dk == KLAST) ? nkf - 1 : kk + dk;
-    if (k > nkf - 1) k = nkf - 1;
-    if (k < 0) k = 0;
-    return ((size_t)tile * nkf + k) * g.slab + (size_t)(jj + dj) * g.pitch + (ii + di);
+  DEV int off(int nkf, int di, int dj, int dk) const {
+    int k;
+    if (dk == 0) k = kk < nkf ? kk : nkf - 1;          // (2-D fields read inside a 3-D launch)
+    else if (dk == KLAST) k = nkf - 1;
+    else { k = kk + dk; k = k > nkf - 1 ? nkf - 1 : k; k = k < 0 ? 0 : k; }
+    return (tile * nkf + k) * g.slab + pos + dj * g.pitch + di;
   }
 };
 
@@ -126,11 +129,11 @@ template <class S> struct CtxTL : CtxBase {
   static constexpr int mode = 1;
   FArr<S::NI> in_, ind_; FArr<S::NO> out_, outd_;
   DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const {
-    size_t o = off(in_.nk[f], di, dj, dk);
+    const int o = off(in_.nk[f], di, dj, dk);
     return Dual(in_.p[f][o], ind_.p[f] ? ind_.p[f][o] : 0.0);
   }
   DEV void out(int o, T v) const {
-    size_t q = off(out_.nk[o], 0, 0, 0);
+    const int q = off(out_.nk[o], 0, 0, 0);
     out_.p[o][q] = v.v;
     if (outd_.p[o]) outd_.p[o][q] = v.d;
   }
@@ -283,7 +286,7 @@ template <class S> struct KernAD {
 #pragma unroll
     for (int f = 0; f < S::NI; f++) {
       if (inad.p[f] && kk < inad.nk[f]) {
-        size_t o = ((size_t)tile * inad.nk[f] + kk) * g.slab + (size_t)jj * g.pitch + ii;
+        const int o = (tile * inad.nk[f] + kk) * g.slab + jj * g.pitch + ii;
         inad.p[f][o] += acc[f];
       }
     }
@@ -402,7 +405,7 @@ struct Program {
 template <class S> struct ColNL : CtxBase {
   using T = double;
   FArr<S::NI> in_; FArr<S::NO> out_;
-  DEV size_t o2(int nkf, int k, int di, int dj) const { return ((size_t)tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + (size_t)(jj + dj) * g.pitch + (ii + di); }
+  DEV int o2(int nkf, int k, int di, int dj) const { return (tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + pos + dj * g.pitch + di; }
   DEV T in(int f, int k, int di = 0, int dj = 0) const { return in_.p[f][o2(in_.nk[f], k, di, dj)]; }
   DEV void out(int o, int k, T v) const { out_.p[o][o2(out_.nk[o], k, 0, 0)] = v; }
   DEV T rd(int o, int k) const { return out_.p[o][o2(out_.nk[o], k, 0, 0)]; }   // read back own output
@@ -410,21 +413,21 @@ template <class S> struct ColNL : CtxBase {
 template <class S> struct ColTL : CtxBase {
   using T = Dual;
   FArr<S::NI> in_, ind_; FArr<S::NO> out_, outd_;
-  DEV size_t o2(int nkf, int k, int di, int dj) const { return ((size_t)tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + (size_t)(jj + dj) * g.pitch + (ii + di); }
+  DEV int o2(int nkf, int k, int di, int dj) const { return (tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + pos + dj * g.pitch + di; }
   DEV T in(int f, int k, int di = 0, int dj = 0) const {
-    size_t o = o2(in_.nk[f], k, di, dj);
+    const int o = o2(in_.nk[f], k, di, dj);
     return Dual(in_.p[f][o], ind_.p[f] ? ind_.p[f][o] : 0.0);
   }
   DEV void out(int o, int k, T v) const {
-    size_t q = o2(out_.nk[o], k, 0, 0);
+    const int q = o2(out_.nk[o], k, 0, 0);
     out_.p[o][q] = v.v;
     if (outd_.p[o]) outd_.p[o][q] = v.d;
   }
-  DEV T rd(int o, int k) const { size_t q = o2(out_.nk[o], k, 0, 0); return Dual(out_.p[o][q], outd_.p[o] ? outd_.p[o][q] : 0.0); }
+  DEV T rd(int o, int k) const { const int q = o2(out_.nk[o], k, 0, 0); return Dual(out_.p[o][q], outd_.p[o] ? outd_.p[o][q] : 0.0); }
 };
 template <class S> struct ColAD : CtxBase {
   FArr<S::NI> in_, inad_; FArr<S::NO> out_, outad_;
-  DEV size_t o2(int nkf, int k) const { return ((size_t)tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + (size_t)jj * g.pitch + ii; }
+  DEV int o2(int nkf, int k) const { return (tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + pos; }
   DEV double in(int f, int k) const { return in_.p[f][o2(in_.nk[f], k)]; }
   DEV double outv(int o, int k) const { return out_.p[o][o2(out_.nk[o], k)]; }          // stored forward value
   DEV double oad(int o, int k) const { return outad_.p[o] ? outad_.p[o][o2(outad_.nk[o], k)] : 0.0; }
