@@ -28,6 +28,7 @@ void d2d(void* d, const void* s, size_t b) { ck(cudaMemcpyAsync(d, s, b, cudaMem
 void zero(void* d, size_t b) { ck(cudaMemsetAsync(d, 0, b, stream()), "memset"); }
 void sync() { ck(cudaStreamSynchronize(stream()), "sync"); }
 void check(const char* what) { ck(cudaGetLastError(), what); }
+double free_bytes() { size_t f = 0, t = 0; ck(cudaMemGetInfo(&f, &t), "cudaMemGetInfo"); return (double)f; }
 #else
 void* alloc(size_t bytes) { void* p = malloc(bytes); if (!p) throw std::runtime_error("malloc"); return p; }
 void free_(void* p) { free(p); }
@@ -37,6 +38,7 @@ void d2d(void* d, const void* s, size_t b) { memcpy(d, s, b); }
 void zero(void* d, size_t b) { memset(d, 0, b); }
 void sync() {}
 void check(const char*) {}
+double free_bytes() { const char* e = getenv("FV3LM_EMU_FREE_BYTES"); return e ? atof(e) : 0.0; }
 #endif
 }  // namespace dev
 
@@ -177,6 +179,20 @@ void Program::run_op(Op& op, int mode) {
   r.n++; r.ms += ms; r.alg_bytes += b;
 }
 
+// The adjoint can skip the per-segment recomputation (one whole nonlinear sweep) when the complete forward sweep
+// fits in device memory -- the case once the cube is sharded over several GPUs.
+bool Program::ad_fits_store_all() {
+  double need = 0.0;
+  for (int id = 0; id < (int)vals.size(); id++) {
+    if (vals[id].external) continue;
+    need += (double)val_doubles(id) * 8.0 * (vals[id].active ? 2.0 : 1.0);
+  }
+  double budget = dv->ad_store_budget;
+  if (const char* e = getenv("FV3LM_AD_STORE_BUDGET")) budget = atof(e);   // tests force either path
+  if (budget < 0.0) budget = 0.85 * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
+  return need <= budget;
+}
+
 void Program::run(Mode mode) {
   analyse();
   const int nop = (int)ops.size();
@@ -189,7 +205,7 @@ void Program::run(Mode mode) {
       for (int i : op.in) if (vals[i].last_use == n) release(i);
       for (int o : op.out) if (vals[o].last_use == n) release(o);
     }
-  } else if (!seg_start.empty()) {
+  } else if (!seg_start.empty() && !ad_fits_store_all()) {
     // ---- segmented adjoint: checkpoint at segment boundaries, recompute one segment at a time
     // (replaces the reference's global tape, utils/tapenade/adStack.c: only the values that
     // cross a segment boundary stay in HBM, the rest is recomputed in the reverse sweep)
@@ -242,7 +258,7 @@ void Program::run(Mode mode) {
     for (int n = 0; n < nop; n++) {
       Op& op = ops[n];
       for (int o : op.out) ensure_traj(o);
-      op.run(*this, op, MODE_ADFWD);
+      run_op(op, MODE_ADFWD);
     }
     // reverse sweep
     for (int n = nop - 1; n >= 0; n--) {
@@ -252,7 +268,7 @@ void Program::run(Mode mode) {
       if (any_out || op.inplace) {
         for (int o : op.out) ensure_pert(o, true);
         for (int i : op.in) ensure_pert(i, true);
-        op.run(*this, op, MODE_AD);
+        run_op(op, MODE_AD);
       }
       if (!op.inplace)
         for (int o : op.out) if (vals[o].first_def == n) release(o);

@@ -95,14 +95,14 @@ struct CtxBase {
   }
   // metric at relative offset
   DEV double M(const double* a, int di = 0, int dj = 0) const {
-    return a[tile * g.slab + pos + dj * g.pitch + di];
+    return LDG(a + (tile * g.slab + pos + dj * g.pitch + di));
   }
   // metric at absolute Fortran index
   DEV double Mabs(const double* a, int ai, int aj) const {
-    return a[tile * g.slab + (aj - (j - jl) + g.ng - 1) * g.pitch + (ai - (i - il) + g.ng - 1)];
+    return LDG(a + (tile * g.slab + (aj - (j - jl) + g.ng - 1) * g.pitch + (ai - (i - il) + g.ng - 1)));
   }
   // 1-D edge array (stored whole-tile in the head of the slab), tile-global Fortran index
-  DEV double M1(const double* a, int ai) const { return a[tile * g.slab + (ai + g.ng - 1)]; }
+  DEV double M1(const double* a, int ai) const { return LDG(a + (tile * g.slab + (ai + g.ng - 1))); }
   // loop ranges are given in the local frame
   DEV bool in_rect(int i0, int i1, int j0, int j1) const { return il >= i0 && il <= i1 && jl >= j0 && jl <= j1; }
   // tile-global rectangle (whole-tile operators such as a2b_ord4)
@@ -120,7 +120,7 @@ template <class S> struct CtxNL : CtxBase {
   using T = double;
   static constexpr int mode = 0;
   FArr<S::NI> in_; FArr<S::NO> out_;
-  DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const { return in_.p[f][off(in_.nk[f], di, dj, dk)]; }
+  DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const { return LDG(in_.p[f] + off(in_.nk[f], di, dj, dk)); }
   DEV void out(int o, T v) const { out_.p[o][off(out_.nk[o], 0, 0, 0)] = v; }
 };
 
@@ -130,7 +130,7 @@ template <class S> struct CtxTL : CtxBase {
   FArr<S::NI> in_, ind_; FArr<S::NO> out_, outd_;
   DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const {
     const int o = off(in_.nk[f], di, dj, dk);
-    return Dual(in_.p[f][o], ind_.p[f] ? ind_.p[f][o] : 0.0);
+    return Dual(LDG(in_.p[f] + o), ind_.p[f] ? LDG(ind_.p[f] + o) : 0.0);
   }
   DEV void out(int o, T v) const {
     const int q = off(out_.nk[o], 0, 0, 0);
@@ -146,13 +146,13 @@ template <class S> struct CtxAD : CtxBase {
   int sf, sdi, sdj, sdk;  // the seeded tap
   double acc;
   DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const {
-    return Dual(in_.p[f][off(in_.nk[f], di, dj, dk)], (f == sf && di == sdi && dj == sdj && dk == sdk) ? 1.0 : 0.0);
+    return Dual(LDG(in_.p[f] + off(in_.nk[f], di, dj, dk)), (f == sf && di == sdi && dj == sdj && dk == sdk) ? 1.0 : 0.0);
   }
   DEV void out(int o, T v) {
     if (outad_.p[o]) {
       // an output cell nobody consumed has a zero adjoint; its value may be computed from cells that were
       // never written (generous loop ranges), so it must not enter the sum as 0 * garbage
-      const double a = outad_.p[o][off(outad_.nk[o], 0, 0, 0)];
+      const double a = LDG(outad_.p[o] + off(outad_.nk[o], 0, 0, 0));
       if (a != 0.0) acc += v.d * a;
     }
   }
@@ -212,7 +212,7 @@ template <class S, int n> struct CtxADN : CtxBase {
   }
   DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const {
     constexpr Tap t = S::taps[n];
-    T r(in_.p[f][off(in_.nk[f], di, dj, dk)]);
+    T r(LDG(in_.p[f] + off(in_.nk[f], di, dj, dk)));
     if (di == t.di && dj == t.dj && dk == t.dk) seed<0>(r, f);
     return r;
   }
@@ -220,7 +220,7 @@ template <class S, int n> struct CtxADN : CtxBase {
     if (outad_.p[o]) {
       // an output cell nobody consumed has a zero adjoint; its value may be computed from cells that were
       // never written (generous loop ranges), so it must not enter the sum as 0 * garbage
-      const double a = outad_.p[o][off(outad_.nk[o], 0, 0, 0)];
+      const double a = LDG(outad_.p[o] + off(outad_.nk[o], 0, 0, 0));
       if (a != 0.0) {
 #pragma unroll
         for (int m = 0; m < NM; m++) acc[m] += v.d[m] * a;
@@ -305,6 +305,7 @@ void d2d(void* d, const void* s, size_t bytes);
 void zero(void* d, size_t bytes);
 void sync();
 void check(const char* what);
+double free_bytes();         // free device memory
 extern long long launches;   // number of kernels launched (bench.py gpu_launches)
 // optional per-op profile (CUDA events around every op; serialises, so only used in a
 // dedicated profiling pass, never inside a timed region)
@@ -328,7 +329,34 @@ template <class F> void launch3d(const F& f, int nx, int ny, int nz) {
   kern3d<F><<<gr, b, 0, dev::stream()>>>(f, nx, ny);
   dev::launches++;
 }
+// stencil stages: every thread handles KPT consecutive levels of one (i, j): the 2-D metric loads, the
+// cube-edge branch conditions and the index set-up are level-invariant and get shared across them
+constexpr int KPT = 1;   // (2 was tried: ptxas does not share work across the unrolled levels, no gain)
+template <class F> GLOBAL void kern_stage(F f, int nx, int ny, int nk, int nkc) {
+  int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  int jj = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ii >= nx || jj >= ny) return;
+  const int tile = blockIdx.z / nkc, k0 = (blockIdx.z % nkc) * KPT;
+#pragma unroll
+  for (int q = 0; q < KPT; q++) {
+    const int k = k0 + q;
+    if (k < nk) f(ii, jj, tile * nk + k);
+  }
+}
+template <class F> void launch_stage(const F& f, int nx, int ny, int ntile, int nk) {
+  if (ntile * nk <= 0) return;
+  const int nkc = (nk + KPT - 1) / KPT;
+  dim3 b(32, 8, 1), gr((nx + 31) / 32, (ny + 7) / 8, ntile * nkc);
+  kern_stage<F><<<gr, b, 0, dev::stream()>>>(f, nx, ny, nk, nkc);
+  dev::launches++;
+}
 #else
+template <class F> void launch_stage(const F& f, int nx, int ny, int ntile, int nk) {
+  for (int z = 0; z < ntile * nk; z++)
+    for (int jj = 0; jj < ny; jj++)
+      for (int ii = 0; ii < nx; ii++) f(ii, jj, z);
+  dev::launches++;
+}
 template <class F> void launch3d(const F& f, int nx, int ny, int nz) {
   for (int z = 0; z < nz; z++)
     for (int jj = 0; jj < ny; jj++)
@@ -387,6 +415,7 @@ struct Program {
   }
   size_t val_doubles(int id) const;
   void analyse();                    // activity + liveness
+  bool ad_fits_store_all();
   void run(Mode mode);               // NL, TL, or AD (forward store-all + reverse)
   void run_op(Op& op, int mode);     // one op, optionally profiled
   void ensure_traj(int id);
@@ -467,6 +496,7 @@ template <class S> struct KernColAD {
 struct Device {
   Geom g;
   Metrics m;
+  double ad_store_budget = -1.0;   // bytes the adjoint may use to keep the whole forward sweep (< 0: ask the device)
   std::vector<double*> metric_bufs;
   Pool pool;
   std::string err;
@@ -485,10 +515,10 @@ void Program::add(const char* nm, const typename S::P& prm, std::vector<int> ins
       for (int f = 0; f < S::NO; f++) { Value& v = P.vals[o.out[f]]; out.p[f] = v.traj; out.nk[f] = v.nk; outd.p[f] = v.active ? v.pert : nullptr; outd.nk[f] = v.nk; }
       if (mode != MODE_TL) {
         KernNL<S> k{p, g, P.dv->m, in, out, o.nk_launch};
-        launch3d(k, g.NX, g.NY, g.ntile * o.nk_launch);
+        launch_stage(k, g.NX, g.NY, g.ntile, o.nk_launch);
       } else {
         KernTL<S> k{p, g, P.dv->m, in, ind, out, outd, o.nk_launch};
-        launch3d(k, g.NX, g.NY, g.ntile * o.nk_launch);
+        launch_stage(k, g.NX, g.NY, g.ntile, o.nk_launch);
       }
     } else {  // AD reverse
       FArr<S::NI> in, inad; FArr<S::NO> outad;
@@ -497,7 +527,7 @@ void Program::add(const char* nm, const typename S::P& prm, std::vector<int> ins
       for (int f = 0; f < S::NO; f++) { Value& v = P.vals[o.out[f]]; outad.p[f] = v.active ? v.pert : nullptr; outad.nk[f] = v.nk; }
       if (!any) return;
       KernAD<S> k{p, g, P.dv->m, in, inad, outad, nk, o.nk_launch};
-      launch3d(k, g.NX, g.NY, g.ntile * nk);
+      launch_stage(k, g.NX, g.NY, g.ntile, nk);
     }
   };
   ops.push_back(op);

@@ -8,9 +8,12 @@
 #define HD inline
 #define DEV inline
 #define GLOBAL
+#define LDG(p) (*(p))
 #else
 #include <cuda_runtime.h>
 #define HD __host__ __device__ __forceinline__
 #define DEV __device__ __forceinline__
 #define GLOBAL __global__
+// read-only data (metrics, stage inputs): ld.global.nc lets the compiler keep / reorder loads across the stores of the stage
+#define LDG(p) __ldg(p)
 #endif

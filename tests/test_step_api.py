@@ -97,3 +97,15 @@ def test_program_stats_emu():
 @pytest.mark.parametrize("nonhydro", [False, True])
 def test_step_api_gpu(nonhydro):
     print(_run(False, nonhydro))
+
+
+@pytest.mark.gpu
+def test_step_api_gpu_segmented_adjoint(monkeypatch):
+    """force the checkpoint / recompute adjoint (what a whole C180 sphere on one GPU uses) instead of store-all"""
+    monkeypatch.setenv("FV3LM_AD_STORE_BUDGET", "0")
+    print(_run(False, True))
+
+
+def test_step_api_emu_store_all_adjoint(monkeypatch):
+    monkeypatch.setenv("FV3LM_AD_STORE_BUDGET", "1e18")
+    print(_run(True, True))
