@@ -99,7 +99,7 @@ def run_gpu(args):
     mc = model_config(N, K, hydro, dt)
     ak, bk = S.eta_levels(K)
     M = G.build_metrics(N)
-    cfg = fv3lm.default_config(N, K, rank=rank, nranks=world, **mc)
+    cfg = fv3lm.default_config(N, K, rank=rank, nranks=world, layout_x=args.layout[0], layout_y=args.layout[1], **mc)
     h = fv3lm.FV3LM(cfg, ak, bk)
     if world > 1:
         # the cube is sharded: every rank owns 6*lx*ly/world sub-domains; halos move over NCCL p2p
@@ -294,6 +294,7 @@ def main():
     ap.add_argument("--nonhydro", action="store_true", default=True, help="non-hydrostatic (riem_solver3) path: the headline config (default)")
     ap.add_argument("--hydrostatic", dest="nonhydro", action="store_false", help="hydrostatic variant")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--layout", type=int, nargs=2, default=[0, 0], help="force the tile layout (default: chosen from the number of ranks)")
     ap.add_argument("--profile-out", default=None, help="write the full per-op profile table to this file")
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: only the device-resident timed loop (used under ncu)")
     args = ap.parse_args()

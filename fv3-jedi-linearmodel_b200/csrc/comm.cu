@@ -43,12 +43,15 @@ void Comm::destroy() { if (nccl && g_nccl.destroy) g_nccl.destroy(nccl); nccl = 
 void Comm::exchange(int npeers, const int* peers, double* const* sbuf, const size_t* scount, double* const* rbuf, const size_t* rcount) {
   if (npeers == 0) return;
   if (!nccl) throw std::runtime_error("fv3lm: halo exchange between ranks before fv3lm_comm_init_nccl");
+  static const int sync_mode = getenv("FV3LM_SYNC_EXCHANGE") ? atoi(getenv("FV3LM_SYNC_EXCHANGE")) : 0;   // debugging aid
+  if (sync_mode & 1) { if (cudaStreamSynchronize(dev::stream()) != cudaSuccess) throw std::runtime_error(std::string("fv3lm: CUDA error before exchange: ") + cudaGetErrorString(cudaGetLastError())); }
   g_nccl.ck(g_nccl.gstart(), "ncclGroupStart");
   for (int p = 0; p < npeers; p++) {
     if (scount[p]) { g_nccl.ck(g_nccl.send(sbuf[p], scount[p], kNcclDouble, peers[p], nccl, dev::stream()), "ncclSend"); bytes_sent += 8.0 * scount[p]; }
     if (rcount[p]) g_nccl.ck(g_nccl.recv(rbuf[p], rcount[p], kNcclDouble, peers[p], nccl, dev::stream()), "ncclRecv");
   }
   g_nccl.ck(g_nccl.gend(), "ncclGroupEnd");
+  if (sync_mode & 2) { if (cudaStreamSynchronize(dev::stream()) != cudaSuccess) throw std::runtime_error(std::string("fv3lm: CUDA error after exchange: ") + cudaGetErrorString(cudaGetLastError())); }
   n_exchanges++;
 }
 #else

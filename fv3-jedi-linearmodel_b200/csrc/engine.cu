@@ -153,6 +153,16 @@ void Program::run_op(Op& op, int mode) {
     return;
   }
 #endif
+#ifndef FV3LM_HOST_EMU
+  static const bool synccheck = getenv("FV3LM_SYNC_CHECK") != nullptr;   // debugging aid: localise a faulting kernel
+  if (synccheck) {
+    op.run(*this, op, mode);
+    cudaError_t e = cudaStreamSynchronize(dev::stream());
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error("fv3lm: CUDA error after op '" + op.name + "' (mode " + std::to_string(mode) + "): " + cudaGetErrorString(e));
+    return;
+  }
+#endif
   if (!dev::profiling) { op.run(*this, op, mode); return; }
 #ifndef FV3LM_HOST_EMU
   static cudaEvent_t e0 = nullptr, e1 = nullptr;

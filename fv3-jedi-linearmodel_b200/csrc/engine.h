@@ -94,7 +94,19 @@ struct CtxBase {
     pos = jj_ * g.pitch + ii_;
   }
   // metric at relative offset
+  // TEST-ONLY build: every stencil access is bounds-checked against the sub-domain array (an out-of-slab tap is
+  // silent on the GPU as long as it stays inside the allocation)
+  DEV void bounds(int di, int dj, const char* what) const {
+#ifdef FV3LM_HOST_EMU
+    if (ii + di < 0 || ii + di >= g.NX || jj + dj < 0 || jj + dj >= g.NY)
+      throw std::runtime_error(std::string("fv3lm emu: out-of-slab ") + what + " access at ii=" + std::to_string(ii) + " jj=" + std::to_string(jj) +
+                               " di=" + std::to_string(di) + " dj=" + std::to_string(dj));
+#else
+    (void)di; (void)dj; (void)what;
+#endif
+  }
   DEV double M(const double* a, int di = 0, int dj = 0) const {
+    bounds(di, dj, "metric");
     return LDG(a + (tile * g.slab + pos + dj * g.pitch + di));
   }
   // metric at absolute Fortran index
@@ -112,6 +124,7 @@ struct CtxBase {
     if (dk == 0) k = kk < nkf ? kk : nkf - 1;          // (2-D fields read inside a 3-D launch)
     else if (dk == KLAST) k = nkf - 1;
     else { k = kk + dk; k = k > nkf - 1 ? nkf - 1 : k; k = k < 0 ? 0 : k; }
+    bounds(di, dj, "field");
     return (tile * nkf + k) * g.slab + pos + dj * g.pitch + di;
   }
 };
@@ -434,7 +447,7 @@ struct Program {
 template <class S> struct ColNL : CtxBase {
   using T = double;
   FArr<S::NI> in_; FArr<S::NO> out_;
-  DEV int o2(int nkf, int k, int di, int dj) const { return (tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + pos + dj * g.pitch + di; }
+  DEV int o2(int nkf, int k, int di, int dj) const { bounds(di, dj, "column field"); return (tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + pos + dj * g.pitch + di; }
   DEV T in(int f, int k, int di = 0, int dj = 0) const { return in_.p[f][o2(in_.nk[f], k, di, dj)]; }
   DEV void out(int o, int k, T v) const { out_.p[o][o2(out_.nk[o], k, 0, 0)] = v; }
   DEV T rd(int o, int k) const { return out_.p[o][o2(out_.nk[o], k, 0, 0)]; }   // read back own output
@@ -442,7 +455,7 @@ template <class S> struct ColNL : CtxBase {
 template <class S> struct ColTL : CtxBase {
   using T = Dual;
   FArr<S::NI> in_, ind_; FArr<S::NO> out_, outd_;
-  DEV int o2(int nkf, int k, int di, int dj) const { return (tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + pos + dj * g.pitch + di; }
+  DEV int o2(int nkf, int k, int di, int dj) const { bounds(di, dj, "column field"); return (tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + pos + dj * g.pitch + di; }
   DEV T in(int f, int k, int di = 0, int dj = 0) const {
     const int o = o2(in_.nk[f], k, di, dj);
     return Dual(in_.p[f][o], ind_.p[f] ? ind_.p[f][o] : 0.0);

@@ -29,14 +29,16 @@ struct S_d2a {
     const int isd = g.is - g.ng, ied = g.ie + g.ng, jsd = g.js - g.ng, jed = g.je + g.ng;
     if (!x.in_rect(isd, ied, jsd, jed)) return;
     const int npt = 4;
-    bool inner = x.i >= npt && x.i <= g.npx - npt && x.j >= npt && x.j <= g.npy - npt;
-    if (inner) {
-      x.out(0, csw::a2 * (x.in(0, 0, -1) + x.in(0, 0, 2)) + csw::a1 * (x.in(0, 0, 0) + x.in(0, 0, 1)));
-      x.out(1, csw::a2 * (x.in(1, -1, 0) + x.in(1, 2, 0)) + csw::a1 * (x.in(1, 0, 0) + x.in(1, 1, 0)));
-    } else {
-      x.out(0, 0.5 * (x.in(0, 0, 0) + x.in(0, 0, 1)));
-      x.out(1, 0.5 * (x.in(1, 0, 0) + x.in(1, 1, 0)));
-    }
+    const bool inner = x.i >= npt && x.i <= g.npx - npt && x.j >= npt && x.j <= g.npy - npt;
+    // 4th-order interior formula only on the rows / columns the reference computes it on
+    // (utmp: j = max(npt,js-1)..min(npy-npt,je+1); vtmp: i = max(npt,is-1)..min(npx-npt,ie+1), sw_core_nlm.F90:2815-2826);
+    // on a sub-domain the remaining halo rows have no neighbours two cells out and are never consumed
+    const bool inner_u = inner && x.jl >= g.js - 1 && x.jl <= g.je + 1;
+    const bool inner_v = inner && x.il >= g.is - 1 && x.il <= g.ie + 1;
+    if (inner_u) x.out(0, csw::a2 * (x.in(0, 0, -1) + x.in(0, 0, 2)) + csw::a1 * (x.in(0, 0, 0) + x.in(0, 0, 1)));
+    else x.out(0, 0.5 * (x.in(0, 0, 0) + x.in(0, 0, 1)));
+    if (inner_v) x.out(1, csw::a2 * (x.in(1, -1, 0) + x.in(1, 2, 0)) + csw::a1 * (x.in(1, 0, 0) + x.in(1, 1, 0)));
+    else x.out(1, 0.5 * (x.in(1, 0, 0) + x.in(1, 1, 0)));
   }
 };
 
