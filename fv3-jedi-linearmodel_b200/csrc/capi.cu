@@ -77,6 +77,9 @@ int fv3lm_destroy(fv3lm_handle* h) {
     for (int f = 0; f < NFIELD; f++) dev::free_(r->pert[f]);
     dev::free_(r->phis);
     for (auto& s : r->slots) for (double* p : s) dev::free_(p);
+#ifndef FV3LM_HOST_EMU
+    for (auto& sg : r->graph) if (sg.exec) cudaGraphExecDestroy((cudaGraphExec_t)sg.exec);
+#endif
     delete r;
   }
   h->mo.destroy();

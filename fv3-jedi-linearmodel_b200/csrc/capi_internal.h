@@ -9,7 +9,17 @@
 
 constexpr int NFIELD = 10;
 
+// CUDA-graph replay of a step program: the op list is static, so after one eager (pool-warming) run the whole
+// TL or AD sweep -- stage kernels, memsets, NCCL exchanges -- is captured once and replayed with one launch.
+struct StepGraph {
+  int state = 0;            // 0: never run, 1: pool warmed, 2: captured
+  void* exec = nullptr;     // cudaGraphExec_t
+  long long launches = 0;   // kernels per replay
+  long long exchanges = 0; double bytes_sent = 0.0;
+};
+
 struct StepRunner {
+  StepGraph graph[3];
   fv3lm::Program P;
   fv3lm::ModuleIO io;
   int nf = 8;                                     // prognostic fields: 8 hydrostatic, 10 with w, delz

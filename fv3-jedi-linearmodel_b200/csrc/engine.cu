@@ -192,6 +192,7 @@ void Program::run_op(Op& op, int mode) {
 // The adjoint can skip the per-segment recomputation (one whole nonlinear sweep) when the complete forward sweep
 // fits in device memory -- the case once the cube is sharded over several GPUs.
 bool Program::ad_fits_store_all() {
+  if (ad_store_all_cached >= 0) return ad_store_all_cached != 0;     // decided once: the sweep structure must not change between runs
   double need = 0.0;
   for (int id = 0; id < (int)vals.size(); id++) {
     if (vals[id].external) continue;
@@ -200,7 +201,8 @@ bool Program::ad_fits_store_all() {
   double budget = dv->ad_store_budget;
   if (const char* e = getenv("FV3LM_AD_STORE_BUDGET")) budget = atof(e);   // tests force either path
   if (budget < 0.0) budget = 0.85 * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
-  return need <= budget;
+  ad_store_all_cached = (need <= budget) ? 1 : 0;
+  return ad_store_all_cached != 0;
 }
 
 void Program::run(Mode mode) {

@@ -429,6 +429,7 @@ struct Program {
   size_t val_doubles(int id) const;
   void analyse();                    // activity + liveness
   bool ad_fits_store_all();
+  int ad_store_all_cached = -1;
   void run(Mode mode);               // NL, TL, or AD (forward store-all + reverse)
   void run_op(Op& op, int mode);     // one op, optionally profiled
   void ensure_traj(int id);

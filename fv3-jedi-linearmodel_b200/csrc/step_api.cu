@@ -96,13 +96,46 @@ void load_traj(fv3lm_handle* h, int slot) {
   expand(h, r->phis, r->P.vals[r->in_id["phis"]].traj, 1);
 }
 
+// run the program eagerly, or (product build, default) through a captured CUDA graph
+void run_program(fv3lm_handle* h, int mode) {
+  StepRunner* r = h->step;
+#ifndef FV3LM_HOST_EMU
+  static const bool no_graph = getenv("FV3LM_NO_GRAPH") != nullptr || getenv("FV3LM_SYNC_CHECK") != nullptr;
+  StepGraph& sg = r->graph[mode];
+  if (no_graph || dev::profiling || mode == MODE_NL) { r->P.run((Mode)mode); return; }
+  if (sg.state == 0) { r->P.run((Mode)mode); sg.state = 1; return; }          // eager: lets the pool reach its peak
+  if (sg.state == 1) {
+    // identical second run, recorded instead of executed: the pool hands out the same buffers in the same order
+    const long long l0 = dev::launches, e0 = h->comm.n_exchanges; const double b0 = h->comm.bytes_sent;
+    const size_t pool0 = h->dv.pool.bytes_total;
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(dev::stream(), cudaStreamCaptureModeThreadLocal) != cudaSuccess) throw std::runtime_error("fv3lm: cudaStreamBeginCapture failed");
+    try { r->P.run((Mode)mode); }
+    catch (...) { cudaStreamEndCapture(dev::stream(), &g); if (g) cudaGraphDestroy(g); throw; }
+    if (cudaStreamEndCapture(dev::stream(), &g) != cudaSuccess || !g) throw std::runtime_error("fv3lm: stream capture of the step program failed");
+    if (h->dv.pool.bytes_total != pool0) { cudaGraphDestroy(g); throw std::runtime_error("fv3lm: device pool grew during graph capture"); }
+    cudaGraphExec_t ex = nullptr;
+    if (cudaGraphInstantiate(&ex, g, 0) != cudaSuccess) { cudaGraphDestroy(g); throw std::runtime_error("fv3lm: cudaGraphInstantiate failed"); }
+    cudaGraphDestroy(g);
+    sg.exec = ex; sg.launches = dev::launches - l0; sg.exchanges = h->comm.n_exchanges - e0; sg.bytes_sent = h->comm.bytes_sent - b0;
+    sg.state = 2;
+    dev::launches = l0; h->comm.n_exchanges = e0; h->comm.bytes_sent = b0;     // nothing ran yet: the replay below counts
+  }
+  if (cudaGraphLaunch((cudaGraphExec_t)sg.exec, dev::stream()) != cudaSuccess) throw std::runtime_error("fv3lm: cudaGraphLaunch failed");
+  dev::launches += sg.launches; h->comm.n_exchanges += sg.exchanges; h->comm.bytes_sent += sg.bytes_sent;
+#else
+  r->P.run((Mode)mode);
+#endif
+}
+
 void run_step(fv3lm_handle* h, int slot, int mode) {
   StepRunner* r = h->step; const Geom& g = h->dv.g;
   load_traj(h, slot);
+  // activity pattern is fixed per mode (the captured graphs depend on it)
   for (auto& kv : r->in_id) r->P.vals[kv.second].active = false;
   if (mode == MODE_TL) {
     for (int f = 0; f < r->nf; f++) { Value& v = r->P.vals[r->in_id[kFieldNames[f]]]; v.active = true; expand(h, r->pert[f], v.pert, g.K); }
-    r->P.run(MODE_TL);
+    run_program(h, MODE_TL);
     for (int f = 0; f < r->nf; f++) compact(h, r->pert[f], r->P.vals[r->out_id[std::string(kFieldNames[f]) + "_n"]].pert, g.K);
   } else if (mode == MODE_AD) {
     for (int f = 0; f < r->nf; f++) {
@@ -110,10 +143,10 @@ void run_step(fv3lm_handle* h, int slot, int mode) {
       dev::zero(vi.pert, r->P.val_doubles(r->in_id[kFieldNames[f]]) * sizeof(double));
       expand(h, r->pert[f], r->P.vals[r->out_id[std::string(kFieldNames[f]) + "_n"]].pert, g.K);
     }
-    r->P.run(MODE_AD);
+    run_program(h, MODE_AD);
     for (int f = 0; f < r->nf; f++) compact(h, r->pert[f], r->P.vals[r->in_id[kFieldNames[f]]].pert, g.K);
   } else {
-    r->P.run(MODE_NL);
+    run_program(h, MODE_NL);
   }
 }
 

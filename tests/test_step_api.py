@@ -109,3 +109,37 @@ def test_step_api_gpu_segmented_adjoint(monkeypatch):
 def test_step_api_emu_store_all_adjoint(monkeypatch):
     monkeypatch.setenv("FV3LM_AD_STORE_BUDGET", "1e18")
     print(_run(True, True))
+
+
+def _repeat(emu, nonhydro):
+    """repeated step_tl / step_ad calls on one handle: run 1 is eager, run 2 is captured into a CUDA graph and
+    launched, later runs replay it (product build) -- every repetition must return the same bits"""
+    N, K = 12, 4
+    h, f, comp, rng, cfg, ak, bk = make(emu, N, K, nonhydro=nonhydro)
+    dx = {k: rng.standard_normal(comp[k].shape) * (np.abs(comp[k]).mean() * 1e-3) for k in ACT}
+    y = {k: rng.standard_normal(comp[k].shape) for k in ACT}
+    ref_tl = ref_ad = None
+    for it in range(4):
+        a = {k: dx[k].copy() for k in ACT}
+        h.step_tl(0, a)
+        b = {k: y[k].copy() for k in ACT}
+        h.step_ad(0, b)
+        if it == 0:
+            ref_tl, ref_ad = a, b
+        else:
+            for k in ACT:
+                assert np.array_equal(a[k], ref_tl[k]), ("tl", it, k)
+                assert np.array_equal(b[k], ref_ad[k]), ("ad", it, k)
+    lhs = sum((ref_tl[k] * y[k]).sum() for k in ACT)
+    rhs = sum((dx[k] * ref_ad[k]).sum() for k in ACT)
+    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
+
+
+def test_step_repeat_emu():
+    _repeat(True, True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nonhydro", [False, True])
+def test_step_repeat_graph_gpu(nonhydro):
+    _repeat(False, nonhydro)
