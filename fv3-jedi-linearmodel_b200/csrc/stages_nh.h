@@ -262,159 +262,152 @@ struct S_riem {
     }
   }
 
-  // Hand-written adjoint.  The per-level work arrays live in local memory and every one of them is streamed through
-  // HBM (ncu, C180: 27 GB per launch with the first 45-array version), so only what cannot be rebuilt from a
-  // neighbouring array is stored: cheap quantities (dm, dz, g, bb, dd, gamC, gam2, dz_new) are recomputed from the
-  // inputs, and the adjoints of the Thomas back-substitutions are propagated in place.
+  // Hand-written adjoint (forward recomputation in double keeping the elimination intermediates, then the reverse
+  // sweep).  A leaner variant that recomputes dm/dz/g/bb/dd/gam from the inputs and propagates the Thomas
+  // back-substitution adjoints in place (26 instead of 45 work arrays) measured SLOWER on B200 (69 vs 61 ms per 9
+  // launches at C180: 116 registers and longer dependent chains), so the store-everything form is kept; see git history.
   template <class X> DEV static void eval_ad(X& x, const P& p) {
     const Geom& g = x.g;
     if (!x.in_rect(g.is - p.halo, g.ie + p.halo, g.js - p.halo, g.je + p.halo)) return;
     const int K = p.K;
     const double gama = 1.0 / (1.0 - p.akap), rgrav = 1.0 / p.grav, t1g = gama * 2.0 * p.dt * p.dt, rdt = 1.0 / p.dt, capa1 = p.akap - 1.0, r3 = rmp::r3;
-    auto DP = [&](int k) { return x.in(0, k); };
-    auto PT = [&](int k) { return x.in(1, k); };
-    auto W1 = [&](int k) { return x.in(3, k); };
-    auto DM = [&](int k) { return x.in(0, k) * rgrav; };
-    auto DZ = [&](int k) { return x.in(2, k + 1) - x.in(2, k); };
-    auto G_ = [&](int k) { return k < K - 1 ? x.in(0, k) / x.in(0, k + 1) : 0.0; };     // dm(k)/dm(k+1)
-    auto BB = [&](int k) { return k < K - 1 ? 2.0 * (1.0 + G_(k)) : 2.0; };
-    // ---- forward recomputation keeping the elimination intermediates
-    double pm2[KMAX], pem[KMAX + 1], pe[KMAX], ppt[KMAX + 1], pp[KMAX + 1], betC[KMAX], aa[KMAX + 1], betE[KMAX], w2t[KMAX], w2[KMAX], pe2[KMAX + 1], p1v[KMAX];
+    // ---- forward recomputation (double) keeping the elimination intermediates
+    double dp[KMAX], dm[KMAX], pm2[KMAX], pem[KMAX + 1], dz[KMAX], pt[KMAX], w1[KMAX], pe[KMAX], g_[KMAX], bb[KMAX], dd[KMAX];
+    double ppt[KMAX + 1], pp[KMAX + 1], gamC[KMAX], betC[KMAX], aa[KMAX + 1], gam2[KMAX], betE[KMAX], w2t[KMAX], w2[KMAX], pe2[KMAX + 1], p1v[KMAX], dzn[KMAX];
     pem[0] = p.ptop;
-    for (int k = 0; k < K; k++) pem[k + 1] = pem[k] + DP(k);
+    for (int k = 0; k < K; k++) { dp[k] = x.in(0, k); pem[k + 1] = pem[k] + dp[k]; pt[k] = x.in(1, k); w1[k] = x.in(3, k); }
     for (int k = 0; k < K; k++) {
-      pm2[k] = (p.mode == 0) ? DP(k) / log(pem[k + 1] / pem[k]) : DP(k) / (log(pem[k + 1]) - log(pem[k]));
-      pe[k] = exp(gama * log(-DM(k) / DZ(k) * p.rdgas * PT(k))) - pm2[k];
+      dz[k] = x.in(2, k + 1) - x.in(2, k);
+      pm2[k] = (p.mode == 0) ? dp[k] / log(pem[k + 1] / pem[k]) : dp[k] / (log(pem[k + 1]) - log(pem[k]));
+      dm[k] = dp[k] * rgrav;
     }
-    auto DD = [&](int k) { return k < K - 1 ? 3.0 * (pe[k] + G_(k) * pe[k + 1]) : 3.0 * pe[K - 1]; };
-    auto GAMC = [&](int k) { return G_(k - 1) / betC[k - 1]; };
-    betC[0] = BB(0); ppt[0] = 0.0; ppt[1] = DD(0) / betC[0];
-    for (int k = 1; k < K; k++) { betC[k] = BB(k) - GAMC(k); ppt[k + 1] = (DD(k) - ppt[k]) / betC[k]; }
-    pp[K] = ppt[K]; pp[0] = 0.0;
-    for (int k = K - 1; k >= 1; k--) pp[k] = ppt[k] - GAMC(k) * pp[k + 1];
-    aa[0] = 0.0; aa[K] = 0.0;
-    for (int k = 1; k < K; k++) aa[k] = t1g / (DZ(k - 1) + DZ(k)) * (pem[k] + pp[k]);
-    auto GAM2 = [&](int k) { return aa[k] / betE[k - 1]; };
     const double ws = x.in(4, 0);
-    betE[0] = DM(0) - aa[1];
-    w2t[0] = (DM(0) * W1(0) + p.dt * pp[1]) / betE[0];
+    for (int k = 0; k < K; k++) pe[k] = exp(gama * log(-dm[k] / dz[k] * p.rdgas * pt[k])) - pm2[k];
+    for (int k = 0; k < K - 1; k++) { g_[k] = dm[k] / dm[k + 1]; bb[k] = 2.0 * (1.0 + g_[k]); dd[k] = 3.0 * (pe[k] + g_[k] * pe[k + 1]); }
+    bb[K - 1] = 2.0; dd[K - 1] = 3.0 * pe[K - 1]; g_[K - 1] = 0.0;
+    betC[0] = bb[0]; ppt[0] = 0.0; ppt[1] = dd[0] / betC[0];
+    for (int k = 1; k < K; k++) { gamC[k] = g_[k - 1] / betC[k - 1]; betC[k] = bb[k] - gamC[k]; ppt[k + 1] = (dd[k] - ppt[k]) / betC[k]; }
+    pp[K] = ppt[K]; pp[0] = 0.0;
+    for (int k = K - 1; k >= 1; k--) pp[k] = ppt[k] - gamC[k] * pp[k + 1];
+    for (int k = 1; k < K; k++) aa[k] = t1g / (dz[k - 1] + dz[k]) * (pem[k] + pp[k]);
+    betE[0] = dm[0] - aa[1];
+    w2t[0] = (dm[0] * w1[0] + p.dt * pp[1]) / betE[0];
     for (int k = 1; k < K - 1; k++) {
-      betE[k] = DM(k) - (aa[k] + aa[k + 1] + aa[k] * GAM2(k));
-      w2t[k] = (DM(k) * W1(k) + p.dt * (pp[k + 1] - pp[k]) - aa[k] * w2t[k - 1]) / betE[k];
+      gam2[k] = aa[k] / betE[k - 1];
+      betE[k] = dm[k] - (aa[k] + aa[k + 1] + aa[k] * gam2[k]);
+      w2t[k] = (dm[k] * w1[k] + p.dt * (pp[k + 1] - pp[k]) - aa[k] * w2t[k - 1]) / betE[k];
     }
-    const double p1b = t1g / DZ(K - 1) * (pem[K] + pp[K]);
-    betE[K - 1] = DM(K - 1) - (aa[K - 1] + p1b + aa[K - 1] * GAM2(K - 1));
-    w2t[K - 1] = (DM(K - 1) * W1(K - 1) + p.dt * (pp[K] - pp[K - 1]) - p1b * ws - aa[K - 1] * w2t[K - 2]) / betE[K - 1];
+    const double p1b = t1g / dz[K - 1] * (pem[K] + pp[K]);
+    gam2[K - 1] = aa[K - 1] / betE[K - 2];
+    betE[K - 1] = dm[K - 1] - (aa[K - 1] + p1b + aa[K - 1] * gam2[K - 1]);
+    w2t[K - 1] = (dm[K - 1] * w1[K - 1] + p.dt * (pp[K] - pp[K - 1]) - p1b * ws - aa[K - 1] * w2t[K - 2]) / betE[K - 1];
     w2[K - 1] = w2t[K - 1];
-    for (int k = K - 2; k >= 0; k--) w2[k] = w2t[k] - GAM2(k + 1) * w2[k + 1];
+    for (int k = K - 2; k >= 0; k--) w2[k] = w2t[k] - gam2[k + 1] * w2[k + 1];
     pe2[0] = 0.0;
-    for (int k = 0; k < K; k++) pe2[k + 1] = pe2[k] + DM(k) * (w2[k] - W1(k)) * rdt;
+    for (int k = 0; k < K; k++) pe2[k + 1] = pe2[k] + dm[k] * (w2[k] - w1[k]) * rdt;
     p1v[K - 1] = (pe2[K - 1] + 2.0 * pe2[K]) * r3;
-    for (int k = K - 2; k >= 0; k--) p1v[k] = (pe2[k] + BB(k) * pe2[k + 1] + G_(k) * pe2[k + 2]) * r3 - G_(k) * p1v[k + 1];
-    // ---- adjoint accumulators
+    for (int k = K - 2; k >= 0; k--) p1v[k] = (pe2[k] + bb[k] * pe2[k + 1] + g_[k] * pe2[k + 2]) * r3 - g_[k] * p1v[k + 1];
+    for (int k = 0; k < K; k++) dzn[k] = -dm[k] * p.rdgas * pt[k] * exp(capa1 * log(fmax(p.p_fac * pm2[k], p1v[k] + pm2[k])));
+    // ---- adjoint seeds from the outputs
     double dm_ad[KMAX], pm2_ad[KMAX], pem_ad[KMAX + 1], dz_ad[KMAX], pt_ad[KMAX], w1_ad[KMAX], pe_ad[KMAX], g_ad[KMAX], bb_ad[KMAX], dd_ad[KMAX];
-    double pp_ad[KMAX + 1], aa_ad[KMAX + 1], w2_ad[KMAX], pe2_ad[KMAX + 1];
-    for (int k = 0; k < K; k++) { dm_ad[k] = pm2_ad[k] = dz_ad[k] = pt_ad[k] = w1_ad[k] = pe_ad[k] = g_ad[k] = bb_ad[k] = dd_ad[k] = 0.0; w2_ad[k] = 0.0; aa_ad[k] = 0.0; }
-    for (int k = 0; k <= K; k++) { pem_ad[k] = pp_ad[k] = pe2_ad[k] = 0.0; }
+    double pp_ad[KMAX + 1], ppt_ad[KMAX + 1], gamC_ad[KMAX], betC_ad[KMAX], aa_ad[KMAX + 1], gam2_ad[KMAX], betE_ad[KMAX], w2_ad[KMAX], w2t_ad[KMAX], pe2_ad[KMAX + 1], dzn_ad[KMAX];
+    for (int k = 0; k < K; k++) { dm_ad[k] = pm2_ad[k] = dz_ad[k] = pt_ad[k] = w1_ad[k] = pe_ad[k] = g_ad[k] = bb_ad[k] = dd_ad[k] = 0.0; gamC_ad[k] = betC_ad[k] = gam2_ad[k] = betE_ad[k] = w2_ad[k] = w2t_ad[k] = dzn_ad[k] = 0.0; aa_ad[k] = 0.0; }
+    for (int k = 0; k <= K; k++) { pem_ad[k] = pp_ad[k] = ppt_ad[k] = pe2_ad[k] = 0.0; }
     aa_ad[K] = 0.0;
     double ws_ad = 0.0, zb_ad = 0.0;   // zb: bottom boundary height (hs or zs)
-    if (p.mode == 0) { for (int k = 1; k <= K; k++) { double o = x.oad(0, k); pe2_ad[k] += o; pem_ad[k] += o; } }
-    else { for (int k = 0; k <= K; k++) pe2_ad[k] += x.oad(0, k); for (int k = 0; k < K; k++) w2_ad[k] += x.oad(2, k); }
-    // ---- G: height recurrence z(K) = zb, z(k) = z(k+1) - c dz_new(k); dz_new and the p1 recursion (k ascending)
     {
+      // height recurrence  z(K) = zb ; z(k) = z(k+1) - c dz(k)
       const double c = (p.mode == 0) ? p.grav : 1.0;
-      double za = 0.0;      // running adjoint of the height recurrence
-      double p1_ad = 0.0;   // adjoint of p1v[k], carried downwards
+      double a = 0.0;
+      for (int k = 0; k < K; k++) { a += x.oad(1, k); dzn_ad[k] -= a * c; }
+      a += x.oad(1, K);
+      zb_ad = a;
+      if (p.mode == 0) { for (int k = 1; k <= K; k++) { double o = x.oad(0, k); pe2_ad[k] += o; pem_ad[k] += o; } }
+      else { for (int k = 0; k <= K; k++) pe2_ad[k] += x.oad(0, k); for (int k = 0; k < K; k++) { w2_ad[k] += x.oad(2, k); dzn_ad[k] += x.oad(3, k); } }
+    }
+    // ---- G: dz_new and the p1 recursion
+    {
+      double p1_ad = 0.0;   // adjoint of p1v[k], carried downwards (k increasing)
       for (int k = 0; k < K; k++) {
-        za += x.oad(1, k);
-        const double a = -za * c + (p.mode == 0 ? 0.0 : x.oad(3, k));       // adjoint of dz_new(k)
         const double M = fmax(p.p_fac * pm2[k], p1v[k] + pm2[k]);
-        const double dzn = -DM(k) * p.rdgas * PT(k) * exp(capa1 * log(M));
-        dm_ad[k] += a * dzn / DM(k); pt_ad[k] += a * dzn / PT(k);
-        const double M_ad = a * dzn * capa1 / M;
-        double Pk = p1_ad;
+        const double a = dzn_ad[k];
+        dm_ad[k] += a * dzn[k] / dm[k]; pt_ad[k] += a * dzn[k] / pt[k];
+        const double M_ad = a * dzn[k] * capa1 / M;
+        double P = p1_ad;
         if (p.p_fac * pm2[k] > p1v[k] + pm2[k]) pm2_ad[k] += M_ad * p.p_fac;
-        else { Pk += M_ad; pm2_ad[k] += M_ad; }
+        else { P += M_ad; pm2_ad[k] += M_ad; }
         if (k < K - 1) {
-          pe2_ad[k] += Pk * r3; bb_ad[k] += Pk * r3 * pe2[k + 1]; pe2_ad[k + 1] += Pk * r3 * BB(k);
-          g_ad[k] += Pk * (r3 * pe2[k + 2] - p1v[k + 1]); pe2_ad[k + 2] += Pk * r3 * G_(k);
-          p1_ad = -G_(k) * Pk;
+          pe2_ad[k] += P * r3; bb_ad[k] += P * r3 * pe2[k + 1]; pe2_ad[k + 1] += P * r3 * bb[k];
+          g_ad[k] += P * (r3 * pe2[k + 2] - p1v[k + 1]); pe2_ad[k + 2] += P * r3 * g_[k];
+          p1_ad = -g_[k] * P;
         } else {
-          pe2_ad[K - 1] += Pk * r3; pe2_ad[K] += 2.0 * Pk * r3;
+          pe2_ad[K - 1] += P * r3; pe2_ad[K] += 2.0 * P * r3;
         }
       }
-      zb_ad = za + x.oad(1, K);
     }
     // ---- F: pe2 prefix sum
     for (int k = K - 1; k >= 0; k--) {
       const double a = pe2_ad[k + 1];
-      pe2_ad[k] += a; dm_ad[k] += a * (w2[k] - W1(k)) * rdt; w2_ad[k] += a * DM(k) * rdt; w1_ad[k] -= a * DM(k) * rdt;
+      pe2_ad[k] += a; dm_ad[k] += a * (w2[k] - w1[k]) * rdt; w2_ad[k] += a * dm[k] * rdt; w1_ad[k] -= a * dm[k] * rdt;
     }
-    // ---- E: tridiagonal solve for w.  Back-substitution adjoint in place: afterwards w2_ad[k] is the adjoint of
-    // w2t[k] and the adjoint of gam2[k+1] is -w2_ad[k] w2[k+1]
-    for (int k = 0; k <= K - 2; k++) w2_ad[k + 1] -= GAM2(k + 1) * w2_ad[k];
-    double p1b_ad = 0.0, betE_ad = 0.0;   // betE_ad: adjoint of betE[k-1] carried to the next (lower k) iteration
+    // ---- E: tridiagonal solve for w
+    for (int k = 0; k <= K - 2; k++) { w2t_ad[k] += w2_ad[k]; gam2_ad[k + 1] -= w2_ad[k] * w2[k + 1]; w2_ad[k + 1] -= gam2[k + 1] * w2_ad[k]; }
+    w2t_ad[K - 1] += w2_ad[K - 1];
+    double p1b_ad = 0.0;
     {
       const int k = K - 1;
-      const double gam2k = GAM2(k), gam2_ad = -w2_ad[k - 1] * w2[k];
-      const double n_ad = w2_ad[k] / betE[k]; double b_ad = -w2_ad[k] * w2t[k] / betE[k];
-      dm_ad[k] += n_ad * W1(k); w1_ad[k] += n_ad * DM(k); pp_ad[K] += n_ad * p.dt; pp_ad[K - 1] -= n_ad * p.dt;
-      p1b_ad -= n_ad * ws; ws_ad -= n_ad * p1b; aa_ad[k] -= n_ad * w2t[k - 1]; w2_ad[k - 1] -= n_ad * aa[k];
-      dm_ad[k] += b_ad; aa_ad[k] -= b_ad * (1.0 + gam2k); p1b_ad -= b_ad;
-      const double gtot = gam2_ad - b_ad * aa[k];
-      aa_ad[k] += gtot / betE[k - 1]; betE_ad = -gtot * gam2k / betE[k - 1];
-      dz_ad[K - 1] -= p1b_ad * p1b / DZ(K - 1); pem_ad[K] += p1b_ad * t1g / DZ(K - 1); pp_ad[K] += p1b_ad * t1g / DZ(K - 1);
+      const double n_ad = w2t_ad[k] / betE[k]; double b_ad = -w2t_ad[k] * w2t[k] / betE[k];
+      dm_ad[k] += n_ad * w1[k]; w1_ad[k] += n_ad * dm[k]; pp_ad[K] += n_ad * p.dt; pp_ad[K - 1] -= n_ad * p.dt;
+      p1b_ad -= n_ad * ws; ws_ad -= n_ad * p1b; aa_ad[k] -= n_ad * w2t[k - 1]; w2t_ad[k - 1] -= n_ad * aa[k];
+      dm_ad[k] += b_ad; aa_ad[k] -= b_ad * (1.0 + gam2[k]); p1b_ad -= b_ad; gam2_ad[k] -= b_ad * aa[k];
+      aa_ad[k] += gam2_ad[k] / betE[k - 1]; betE_ad[k - 1] -= gam2_ad[k] * gam2[k] / betE[k - 1];
+      dz_ad[K - 1] -= p1b_ad * p1b / dz[K - 1]; pem_ad[K] += p1b_ad * t1g / dz[K - 1]; pp_ad[K] += p1b_ad * t1g / dz[K - 1];
     }
     for (int k = K - 2; k >= 1; k--) {
-      const double gam2k = GAM2(k), gam2_ad = -w2_ad[k - 1] * w2[k];
-      const double n_ad = w2_ad[k] / betE[k]; const double b_ad = betE_ad - w2_ad[k] * w2t[k] / betE[k];
-      dm_ad[k] += n_ad * W1(k) + b_ad; w1_ad[k] += n_ad * DM(k); pp_ad[k + 1] += n_ad * p.dt; pp_ad[k] -= n_ad * p.dt;
-      aa_ad[k] -= n_ad * w2t[k - 1] + b_ad * (1.0 + gam2k); w2_ad[k - 1] -= n_ad * aa[k]; aa_ad[k + 1] -= b_ad;
-      const double gtot = gam2_ad - b_ad * aa[k];
-      aa_ad[k] += gtot / betE[k - 1]; betE_ad = -gtot * gam2k / betE[k - 1];
+      const double n_ad = w2t_ad[k] / betE[k]; const double b_ad = betE_ad[k] - w2t_ad[k] * w2t[k] / betE[k];
+      dm_ad[k] += n_ad * w1[k] + b_ad; w1_ad[k] += n_ad * dm[k]; pp_ad[k + 1] += n_ad * p.dt; pp_ad[k] -= n_ad * p.dt;
+      aa_ad[k] -= n_ad * w2t[k - 1] + b_ad * (1.0 + gam2[k]); w2t_ad[k - 1] -= n_ad * aa[k]; aa_ad[k + 1] -= b_ad; gam2_ad[k] -= b_ad * aa[k];
+      aa_ad[k] += gam2_ad[k] / betE[k - 1]; betE_ad[k - 1] -= gam2_ad[k] * gam2[k] / betE[k - 1];
     }
     {
-      const double n_ad = w2_ad[0] / betE[0]; const double b_ad = betE_ad - w2_ad[0] * w2t[0] / betE[0];
-      dm_ad[0] += n_ad * W1(0) + b_ad; w1_ad[0] += n_ad * DM(0); pp_ad[1] += n_ad * p.dt; aa_ad[1] -= b_ad;
+      const double n_ad = w2t_ad[0] / betE[0]; const double b_ad = betE_ad[0] - w2t_ad[0] * w2t[0] / betE[0];
+      dm_ad[0] += n_ad * w1[0] + b_ad; w1_ad[0] += n_ad * dm[0]; pp_ad[1] += n_ad * p.dt; aa_ad[1] -= b_ad;
     }
     // ---- D: aa
     for (int k = 1; k < K; k++) {
-      const double a = aa_ad[k], sdz = DZ(k - 1) + DZ(k);
-      dz_ad[k - 1] -= a * aa[k] / sdz; dz_ad[k] -= a * aa[k] / sdz; pem_ad[k] += a * t1g / sdz; pp_ad[k] += a * t1g / sdz;
+      const double a = aa_ad[k], s = dz[k - 1] + dz[k];
+      dz_ad[k - 1] -= a * aa[k] / s; dz_ad[k] -= a * aa[k] / s; pem_ad[k] += a * t1g / s; pp_ad[k] += a * t1g / s;
     }
-    // ---- C: tridiagonal solve for pp (same in-place treatment: pp_ad[k] becomes the adjoint of ppt[k])
-    for (int k = 1; k <= K - 1; k++) pp_ad[k + 1] -= GAMC(k) * pp_ad[k];
-    {
-      double betC_ad = 0.0;
-      for (int k = K - 1; k >= 1; k--) {
-        const double gamCk = GAMC(k), gamC_ad0 = -pp_ad[k] * pp[k + 1];
-        const double n_ad = pp_ad[k + 1] / betC[k]; const double b_ad = betC_ad - pp_ad[k + 1] * ppt[k + 1] / betC[k];
-        dd_ad[k] += n_ad; pp_ad[k] -= n_ad; bb_ad[k] += b_ad;
-        const double gtot = gamC_ad0 - b_ad;
-        g_ad[k - 1] += gtot / betC[k - 1]; betC_ad = -gtot * gamCk / betC[k - 1];
-      }
-      dd_ad[0] += pp_ad[1] / betC[0]; bb_ad[0] += betC_ad - pp_ad[1] * ppt[1] / betC[0];
+    // ---- C: tridiagonal solve for pp
+    for (int k = 1; k <= K - 1; k++) { ppt_ad[k] += pp_ad[k]; gamC_ad[k] -= pp_ad[k] * pp[k + 1]; pp_ad[k + 1] -= gamC[k] * pp_ad[k]; }
+    ppt_ad[K] += pp_ad[K];
+    for (int k = K - 1; k >= 1; k--) {
+      const double n_ad = ppt_ad[k + 1] / betC[k]; const double b_ad = betC_ad[k] - ppt_ad[k + 1] * ppt[k + 1] / betC[k];
+      dd_ad[k] += n_ad; ppt_ad[k] -= n_ad; bb_ad[k] += b_ad; gamC_ad[k] -= b_ad;
+      g_ad[k - 1] += gamC_ad[k] / betC[k - 1]; betC_ad[k - 1] -= gamC_ad[k] * gamC[k] / betC[k - 1];
     }
+    dd_ad[0] += ppt_ad[1] / betC[0]; bb_ad[0] += betC_ad[0] - ppt_ad[1] * ppt[1] / betC[0];
     // ---- B
     for (int k = 0; k < K - 1; k++) {
-      pe_ad[k] += 3.0 * dd_ad[k]; g_ad[k] += 3.0 * dd_ad[k] * pe[k + 1] + 2.0 * bb_ad[k]; pe_ad[k + 1] += 3.0 * dd_ad[k] * G_(k);
-      dm_ad[k] += g_ad[k] / DM(k + 1); dm_ad[k + 1] -= g_ad[k] * G_(k) / DM(k + 1);
+      pe_ad[k] += 3.0 * dd_ad[k]; g_ad[k] += 3.0 * dd_ad[k] * pe[k + 1] + 2.0 * bb_ad[k]; pe_ad[k + 1] += 3.0 * dd_ad[k] * g_[k];
+      dm_ad[k] += g_ad[k] / dm[k + 1]; dm_ad[k + 1] -= g_ad[k] * g_[k] / dm[k + 1];
     }
     pe_ad[K - 1] += 3.0 * dd_ad[K - 1];
     // ---- A
     for (int k = 0; k < K; k++) {
       const double a = pe_ad[k], Ek = pe[k] + pm2[k];
-      pm2_ad[k] -= a; dm_ad[k] += a * Ek * gama / DM(k); dz_ad[k] -= a * Ek * gama / DZ(k); pt_ad[k] += a * Ek * gama / PT(k);
+      pm2_ad[k] -= a; dm_ad[k] += a * Ek * gama / dm[k]; dz_ad[k] -= a * Ek * gama / dz[k]; pt_ad[k] += a * Ek * gama / pt[k];
     }
     // ---- wrappers: dm = dp rgrav ; pm2 = dp / (log pem(k+1) - log pem(k)) ; dz = z(k+1) - z(k) ; pem prefix sum
+    double dp_ad[KMAX];
     for (int k = 0; k < K; k++) {
       const double dl = log(pem[k + 1]) - log(pem[k]);
+      dp_ad[k] = dm_ad[k] * rgrav + pm2_ad[k] / dl;
       const double dl_ad = -pm2_ad[k] * pm2[k] / dl;
-      dm_ad[k] = dm_ad[k] * rgrav + pm2_ad[k] / dl;          // now the adjoint of dp (without the prefix-sum part)
       pem_ad[k + 1] += dl_ad / pem[k + 1]; pem_ad[k] -= dl_ad / pem[k];
     }
-    { double a = 0.0; for (int k = K; k >= 1; k--) { a += pem_ad[k]; dm_ad[k - 1] += a; } }
-    for (int k = 0; k < K; k++) { x.add(0, k, dm_ad[k]); x.add(1, k, pt_ad[k]); x.add(3, k, w1_ad[k]); x.add(2, k + 1, dz_ad[k]); x.add(2, k, -dz_ad[k]); }
+    { double a = 0.0; for (int k = K; k >= 1; k--) { a += pem_ad[k]; dp_ad[k - 1] += a; } }
+    for (int k = 0; k < K; k++) { x.add(0, k, dp_ad[k]); x.add(1, k, pt_ad[k]); x.add(3, k, w1_ad[k]); x.add(2, k + 1, dz_ad[k]); x.add(2, k, -dz_ad[k]); }
     x.add(4, 0, ws_ad);
     x.add(5, 0, zb_ad);
   }
