@@ -52,6 +52,28 @@ template <int DIR> struct S_a2b_q1 {
     } else r = gen(x, 0);
     x.out(0, r);
   }
+  // gather adjoint: away from the tile edges the operator is the uniform 4-point stencil b2, b1, b1, b2 --
+  // four loads instead of six seeded evaluations; near the edges the generic path is used
+  static constexpr bool custom_ad = true;
+  template <class K> DEV static void adjoint(const K& kn, int ii, int jj, int kk, int tile, double* acc) {
+    if (kk >= kn.nk_fwd || !kn.outad.p[0]) return;
+    const Geom& g = kn.g;
+    CtxNL<S_a2b_q1<DIR>> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in;
+    x.setpos(ii, jj, kk, tile, g.i0[tile], g.j0[tile]);
+    const int pos = DIR == 0 ? x.i : x.j, np = DIR == 0 ? g.npx : g.npy;
+    const int loc = DIR == 0 ? x.il : x.jl, cl = DIR == 0 ? x.jl : x.il, cg = DIR == 0 ? x.j : x.i;
+    const int lo = DIR == 0 ? g.is : g.js, hi = (DIR == 0 ? g.ie : g.je) + 1;          // output range along DIR
+    const int clo = (DIR == 0 ? g.js : g.is) - 2, chi = (DIR == 0 ? g.je : g.ie) + 2;  // across DIR
+    const int ncross = DIR == 0 ? g.npy : g.npx;
+    // (the faces 2 and np-1 also read the generic value of their inner neighbour: stay one more cell away)
+    if (pos - 1 >= 4 && pos + 2 <= np - 3 && loc - 1 >= lo && loc + 2 <= hi && cl >= clo && cl <= chi && cg >= 1 && cg <= ncross - 1) {
+      const int stride = DIR == 0 ? 1 : g.pitch;
+      const double* ap = kn.outad.p[0] + x.off(kn.outad.nk[0], 0, 0, 0);
+      acc[0] += a2b::b2 * (LDG(ap - stride) + LDG(ap + 2 * stride)) + a2b::b1 * (LDG(ap) + LDG(ap + stride));
+    } else {
+      AdTaps<S_a2b_q1<DIR>, 0>::run(kn, ii, jj, kk, tile, acc);
+    }
+  }
 };
 
 // qout on the tile boundary: 3-way corner extrapolation (:73-106) and edge interpolation
@@ -94,6 +116,14 @@ struct S_a2b_edge {
     }
     x.out(0, r);
   }
+  // gather adjoint: only outputs on the tile boundary exist and they read at most two cells inwards
+  static constexpr bool custom_ad = true;
+  template <class K> DEV static void adjoint(const K& kn, int ii, int jj, int kk, int tile, double* acc) {
+    const Geom& g = kn.g;
+    const int i = ii - (g.ng - 1) + g.i0[tile], j = jj - (g.ng - 1) + g.j0[tile];
+    if (i > 3 && i < g.npx - 3 && j > 3 && j < g.npy - 3) return;
+    AdTaps<S_a2b_edge, 0>::run(kn, ii, jj, kk, tile, acc);
+  }
 };
 
 // second sweep and averaging (:196-227).  in: qx qy qe ; out: qout
@@ -124,6 +154,24 @@ struct S_a2b_q2 {
     else if (i == npx - 1) qyy = a2b::c1 * (x.in(1, -1, 0) + x.in(1)) + a2b::c2 * (x.in(2, 1, 0) + yy(x, -1));
     else qyy = yy(x, 0);
     x.out(0, 0.5 * (qxx + qyy));
+  }
+  // gather adjoint: five or more cells away from the tile edges the operator is 0.5 * (a2, a1, a1, a2) along j for qx
+  // and along i for qy, and the edge values qe are not read at all
+  static constexpr bool custom_ad = true;
+  template <class K> DEV static void adjoint(const K& kn, int ii, int jj, int kk, int tile, double* acc) {
+    if (kk >= kn.nk_fwd || !kn.outad.p[0]) return;
+    const Geom& g = kn.g;
+    CtxNL<S_a2b_q2> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in;
+    x.setpos(ii, jj, kk, tile, g.i0[tile], g.j0[tile]);
+    if (x.i >= 5 && x.i <= g.npx - 5 && x.j >= 5 && x.j <= g.npy - 5 &&
+        x.il - 1 >= g.is && x.il + 2 <= g.ie + 1 && x.jl - 1 >= g.js && x.jl + 2 <= g.je + 1) {
+      const double* ap = kn.outad.p[0] + x.off(kn.outad.nk[0], 0, 0, 0);
+      const int st = g.pitch;
+      acc[0] += 0.5 * (a2b::a2 * (LDG(ap - st) + LDG(ap + 2 * st)) + a2b::a1 * (LDG(ap) + LDG(ap + st)));
+      acc[1] += 0.5 * (a2b::a2 * (LDG(ap - 1) + LDG(ap + 2)) + a2b::a1 * (LDG(ap) + LDG(ap + 1)));
+    } else {
+      AdTaps<S_a2b_q2, 0>::run(kn, ii, jj, kk, tile, acc);
+    }
   }
 };
 

@@ -96,25 +96,52 @@ template <int DIR> struct S_ppm {
     const int ord = p.ord.v[kk];
     CtxNL<S_ppm<DIR>> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in;
     const int nko = kn.outad.nk[0];
-    for (int s = -2; s <= 3; s++) {           // face f = p + s reads this cell at offset d = -s
-      const int fi = ii + (DIR == 0 ? s : 0), fj = jj + (DIR == 1 ? s : 0);
-      if (fi < 0 || fi >= kn.g.NX || fj < 0 || fj >= kn.g.NY) continue;
-      x.setpos(fi, fj, kk, tile, kn.g.i0[tile], kn.g.j0[tile]);
-      if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) continue;
-      const double a = kn.outad.p[0][x.off(nko, 0, 0, 0)];
-      if (a == 0.0) continue;
-      const double c = x.in(1);
-      const int d = -s;
-      double coef;
-      if (ord == 1) coef = (c > 0.0) ? (d == -1 ? 1.0 : 0.0) : (d == 0 ? 1.0 : 0.0);
-      else if (c > 0.0) {
-        const double dqt = 1.0 + (1.0 - c) * (2.0 * c - 1.0), dal0 = (1.0 - c) * (1.0 - c), dalm = -(1.0 - c) * c;
-        coef = (d == -1 ? dqt : 0.0) + dal0 * al_w(x, 0, d + 2) + dalm * al_w(x, -1, d + 3);
-      } else {
-        const double dqt = 1.0 - (1.0 + c) * (1.0 + 2.0 * c), dal0 = (1.0 + c) * (1.0 + c), dalp = (1.0 + c) * c;
-        coef = (d == 0 ? dqt : 0.0) + dal0 * al_w(x, 0, d + 2) + dalp * al_w(x, 1, d + 1);
+    x.setpos(ii, jj, kk, tile, kn.g.i0[tile], kn.g.j0[tile]);
+    const int pos = DIR == 0 ? x.i : x.j, np = DIR == 0 ? kn.g.npx : kn.g.npy;
+    const int loc = DIR == 0 ? x.il : x.jl, len = DIR == 0 ? kn.g.NX : kn.g.NY, arr = DIR == 0 ? ii : jj;
+    // fast path: all six faces p-2..p+3 are regular (their three edge values use the uniform PPM weights), lie
+    // inside the flux rectangle and inside the array -- true for every cell away from the cube edges
+    const int f0 = DIR == 0 ? p.i0 : p.j0, f1 = DIR == 0 ? p.i1 : p.j1;
+    const bool cross_ok = DIR == 0 ? (x.jl >= p.j0 && x.jl <= p.j1) : (x.il >= p.i0 && x.il <= p.i1);
+    if (ord != 1 && cross_ok && pos - 3 >= 3 && pos + 4 <= np - 2 && loc - 2 >= f0 && loc + 3 <= f1 && arr - 2 >= 0 && arr + 3 < len) {
+      const int stride = DIR == 0 ? 1 : kn.g.pitch;
+      const int oc = x.off(kn.in.nk[1], 0, 0, 0), oa = x.off(nko, 0, 0, 0);
+      const double* cp = kn.in.p[1]; const double* ap = kn.outad.p[0];
+      double sum = 0.0;
+#pragma unroll
+      for (int s = -2; s <= 3; s++) {
+        const double a = LDG(ap + oa + s * stride);
+        const double c = LDG(cp + oc + s * stride);
+        const int d = -s;
+        // W = [p2, p1, p1, p2] at n = 0..3, zero outside
+        auto W = [](int n) { return (n == 0 || n == 3) ? tp::p2 : ((n == 1 || n == 2) ? tp::p1 : 0.0); };
+        double coef;
+        if (c > 0.0) coef = (d == -1 ? 1.0 + (1.0 - c) * (2.0 * c - 1.0) : 0.0) + (1.0 - c) * (1.0 - c) * W(d + 2) - (1.0 - c) * c * W(d + 3);
+        else coef = (d == 0 ? 1.0 - (1.0 + c) * (1.0 + 2.0 * c) : 0.0) + (1.0 + c) * (1.0 + c) * W(d + 2) + (1.0 + c) * c * W(d + 1);
+        sum += coef * a;
       }
-      acc[0] += coef * a;
+      acc[0] += sum;
+    } else {
+      for (int s = -2; s <= 3; s++) {           // face f = p + s reads this cell at offset d = -s
+        const int fi = ii + (DIR == 0 ? s : 0), fj = jj + (DIR == 1 ? s : 0);
+        if (fi < 0 || fi >= kn.g.NX || fj < 0 || fj >= kn.g.NY) continue;
+        x.setpos(fi, fj, kk, tile, kn.g.i0[tile], kn.g.j0[tile]);
+        if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) continue;
+        const double a = kn.outad.p[0][x.off(nko, 0, 0, 0)];
+        if (a == 0.0) continue;
+        const double c = x.in(1);
+        const int d = -s;
+        double coef;
+        if (ord == 1) coef = (c > 0.0) ? (d == -1 ? 1.0 : 0.0) : (d == 0 ? 1.0 : 0.0);
+        else if (c > 0.0) {
+          const double dqt = 1.0 + (1.0 - c) * (2.0 * c - 1.0), dal0 = (1.0 - c) * (1.0 - c), dalm = -(1.0 - c) * c;
+          coef = (d == -1 ? dqt : 0.0) + dal0 * al_w(x, 0, d + 2) + dalm * al_w(x, -1, d + 3);
+        } else {
+          const double dqt = 1.0 - (1.0 + c) * (1.0 + 2.0 * c), dal0 = (1.0 + c) * (1.0 + c), dalp = (1.0 + c) * c;
+          coef = (d == 0 ? dqt : 0.0) + dal0 * al_w(x, 0, d + 2) + dalp * al_w(x, 1, d + 1);
+        }
+        acc[0] += coef * a;
+      }
     }
     // Courant number: the face at this cell
     if (kn.inad.p[1] && ord != 1) {
