@@ -212,12 +212,14 @@ struct S_riem {
     auto G_ = [&](int k) -> T { return x.in(0, k) / x.in(0, k + 1); };
     pem[0] = T(p.ptop);
     for (int k = 0; k < K; k++) pem[k + 1] = pem[k] + x.in(0, k);
+#pragma unroll 4
     for (int k = 0; k < K; k++) {
       T dp = x.in(0, k);
       pm2[k] = (p.mode == 0) ? dp / m_log(pem[k + 1] / pem[k]) : dp / (m_log(pem[k + 1]) - m_log(pem[k]));
     }
     T ws = x.in(4, 0);
     // ---- SIM1_solver
+#pragma unroll 4
     for (int k = 0; k < K; k++) pe[k] = m_exp(gama * m_log(-DM(k) / DZ(k) * p.rdgas * x.in(1, k))) - pm2[k];
     auto BB = [&](int k) -> T { return k < K - 1 ? 2.0 * (1.0 + G_(k)) : T(2.0); };
     auto DD = [&](int k) -> T { return k < K - 1 ? 3.0 * (pe[k] + G_(k) * pe[k + 1]) : 3.0 * pe[K - 1]; };
@@ -225,6 +227,7 @@ struct S_riem {
     pp[0] = T(0.0); pp[1] = DD(0) / bet;
     for (int k = 1; k < K; k++) { gam[k] = G_(k - 1) / bet; bet = BB(k) - gam[k]; pp[k + 1] = (DD(k) - pp[k]) / bet; }
     for (int k = K - 1; k >= 1; k--) pp[k] = pp[k] - gam[k] * pp[k + 1];
+#pragma unroll 4
     for (int k = 1; k < K; k++) aa[k] = t1g / (DZ(k - 1) + DZ(k)) * (pem[k] + pp[k]);
     bet = DM(0) - aa[1];
     w2[0] = (DM(0) * x.in(3, 0) + p.dt * pp[1]) / bet;
