@@ -58,6 +58,7 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
     g.i0[l] = (short)dc.i0_of(d); g.j0[l] = (short)dc.j0_of(d); g.tile_of[l] = (short)dc.tile_of(d);
   }
   h->comm.rank = dc.rank; h->comm.nranks = dc.nranks;
+  h->dv.comm = &h->comm;
   if (ak && bk) { h->ak.assign(ak, ak + cfg->npz + 1); h->bk.assign(bk, bk + cfg->npz + 1); }
   memset(&h->dv.m, 0, sizeof(Metrics));
   h->mo.build(g, dc, &h->comm);

@@ -1,6 +1,7 @@
 #include "comm.h"
 #include "engine.h"
 #include <dlfcn.h>
+#include <vector>
 
 namespace fv3lm {
 
@@ -66,5 +67,24 @@ void Comm::exchange(int npeers, const int* peers, double* const* sbuf, const siz
   n_exchanges++;
 }
 #endif
+
+double Comm::min_over_ranks(double v) {
+  if (nranks <= 1) return v;
+  const int np = nranks - 1;
+  double* buf = (double*)dev::alloc(sizeof(double) * (size_t)(nranks + 1));
+  dev::h2d(buf, &v, sizeof(double));
+  std::vector<int> peers; std::vector<double*> sb, rb; std::vector<size_t> sc, rc;
+  for (int r = 0, k = 0; r < nranks; r++) {
+    if (r == rank) continue;
+    peers.push_back(r); sb.push_back(buf); rb.push_back(buf + 1 + k); sc.push_back(1); rc.push_back(1); k++;
+  }
+  exchange(np, peers.data(), sb.data(), sc.data(), rb.data(), rc.data());
+  std::vector<double> h(nranks);
+  dev::d2h(h.data(), buf, sizeof(double) * (size_t)nranks);     // (synchronises the stream)
+  dev::free_(buf);
+  double m = h[0];
+  for (int k = 1; k < nranks; k++) m = h[k] < m ? h[k] : m;
+  return m;
+}
 
 }  // namespace fv3lm

@@ -21,6 +21,7 @@ struct Comm {
   double bytes_sent = 0.0;
   // every rank calls this with its peer lists (matching counts on both sides); stream ordered
   void exchange(int npeers, const int* peers, double* const* sbuf, const size_t* scount, double* const* rbuf, const size_t* rcount);
+  double min_over_ranks(double v);   // tiny collective built on exchange(): decisions that shape the sweep must agree on all ranks
   void init_nccl(const void* unique_id_128);
   void destroy();
   static void nccl_unique_id(void* out128);

@@ -1,5 +1,6 @@
 // Device layer, buffer pool and the program executor (NL / TL / AD sweeps).
 #include "engine.h"
+#include "comm.h"
 #include <algorithm>
 
 namespace fv3lm {
@@ -201,6 +202,7 @@ bool Program::ad_fits_store_all() {
   double budget = dv->ad_store_budget;
   if (const char* e = getenv("FV3LM_AD_STORE_BUDGET")) budget = atof(e);   // tests force either path
   if (budget < 0.0) budget = 0.85 * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
+  if (dv->comm) budget = dv->comm->min_over_ranks(budget);     // every rank must take the same path (same exchange sequence)
   ad_store_all_cached = (need <= budget) ? 1 : 0;
   return ad_store_all_cached != 0;
 }
@@ -229,13 +231,29 @@ void Program::run(Mode mode) {
     const int nseg = seg_of[nop - 1] + 1;
     auto def_seg = [&](int id) { return vals[id].first_def < 0 ? -1 : seg_of[vals[id].first_def]; };
     auto last_seg = [&](int id) { return vals[id].last_use < 0 ? -1 : seg_of[vals[id].last_use]; };
+    // How many trailing segments can be kept whole during pass 1 (no recomputation for them)?  Decided once from the
+    // device memory that is free beyond what one segment's recomputation + reversal needs.
+    if (ad_keep_from < 0) {
+      std::vector<double> seg_bytes(nseg, 0.0);
+      for (int id = 0; id < (int)vals.size(); id++)
+        if (!vals[id].external && vals[id].first_def >= 0) seg_bytes[seg_of[vals[id].first_def]] += (double)val_doubles(id) * 8.0;
+      double largest = 0.0; for (double b : seg_bytes) largest = std::max(largest, b);
+      double budget = dv->ad_store_budget;
+      if (const char* e = getenv("FV3LM_AD_STORE_BUDGET")) budget = atof(e);
+      if (budget < 0.0) budget = 0.75 * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
+      if (dv->comm) budget = dv->comm->min_over_ranks(budget);   // same decision on every rank
+      budget -= 3.0 * largest;                      // a segment being reversed holds trajectory + adjoints, plus the boundary values
+      ad_keep_from = nseg - 1;                      // the last segment is always kept
+      while (ad_keep_from > 0 && seg_bytes[ad_keep_from - 1] <= budget) { budget -= seg_bytes[ad_keep_from - 1]; ad_keep_from--; }
+    }
+    const int keep_from = ad_keep_from;
     // pass 1: plain forward; segment-local values are freed at their last use, boundary-crossing ones stay
     for (int n = 0; n < nop; n++) {
       Op& op = ops[n];
       for (int o : op.out) ensure_traj(o);
-      // the last segment is reversed first: keep it whole and let its patch ops save what they overwrite
-      run_op(op, seg_of[n] == nseg - 1 ? MODE_ADFWD : MODE_NL);
-      if (seg_of[n] == nseg - 1) continue;
+      // kept segments (at least the last, reversed first) stay whole; their patch ops save what they overwrite
+      run_op(op, seg_of[n] >= keep_from ? MODE_ADFWD : MODE_NL);
+      if (seg_of[n] >= keep_from) continue;
       for (int i : op.in) if (vals[i].last_use == n && def_seg(i) == seg_of[n]) release(i);
       for (int o : op.out) if (vals[o].last_use == n && def_seg(o) == seg_of[n]) release(o);
     }
@@ -244,7 +262,7 @@ void Program::run(Mode mode) {
       while (seg_of[n0] != s) n0++;
       while (seg_of[n1] != s) n1--;
       // recompute the segment keeping every value (patch ops save what they overwrite)
-      for (int n = n0; n <= n1 && s != nseg - 1; n++) {
+      for (int n = n0; n <= n1 && s < keep_from; n++) {
         Op& op = ops[n];
         for (int o : op.out) ensure_traj(o);
         run_op(op, MODE_ADFWD);

@@ -430,6 +430,7 @@ struct Program {
   void analyse();                    // activity + liveness
   bool ad_fits_store_all();
   int ad_store_all_cached = -1;
+  int ad_keep_from = -1;             // first segment kept whole by the adjoint's forward pass (decided once)
   void run(Mode mode);               // NL, TL, or AD (forward store-all + reverse)
   void run_op(Op& op, int mode);     // one op, optionally profiled
   void ensure_traj(int id);
@@ -511,6 +512,7 @@ struct Device {
   Geom g;
   Metrics m;
   double ad_store_budget = -1.0;   // bytes the adjoint may use to keep the whole forward sweep (< 0: ask the device)
+  struct Comm* comm = nullptr;     // for the collective (min over ranks) version of that budget
   std::vector<double*> metric_bufs;
   Pool pool;
   std::string err;
