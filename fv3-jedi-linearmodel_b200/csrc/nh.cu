@@ -1,6 +1,7 @@
 // Non-hydrostatic program builders: update_dz_c / update_dz_d, Riem solvers, and the
 // non-hydrostatic branch of dyn_core (model/dyn_core_nlm.F90:78-1040).
 #include "nh.h"
+#include "stages_riem.h"
 #include "modules.h"
 
 namespace fv3lm {
@@ -9,6 +10,49 @@ static LevD dp_ref_of(const std::vector<double>& ak, const std::vector<double>& 
   LevD d; for (int k = 0; k < 96; k++) d.v[k] = 0.0;
   for (int k = 0; k < K; k++) d.v[k] = (ak[k + 1] - ak[k]) + (bk[k + 1] - bk[k]) * 1.e5;   // dyn_core_nlm.F90:213-215
   return d;
+}
+
+// Riem_Solver_c / Riem_Solver3 as level-parallel stages + thin column recurrences (stages_riem.h).
+// FV3LM_RIEM_MONO=1 selects the monolithic one-thread-per-column kernel S_riem instead (kept for A/B measurements).
+static bool riem_mono() { static const bool m = getenv("FV3LM_RIEM_MONO") != nullptr; return m; }
+
+RiemOut build_riem(Program& P, const RiemPrm& r, int delp, int pt, int z, int w, int ws, int zb, const std::string& tag) {
+  const int K = r.K, h = r.halo;
+  auto nm = [&](const char* s) { return tag + "." + s; };
+  if (riem_mono()) {
+    int o0 = P.val(nm("pp"), K + 1), o1 = P.val(nm("z"), K + 1), o2 = P.val(nm("w"), K), o3 = P.val(nm("dz"), K);
+    add_col<S_riem>(P, r.mode == 0 ? "riem_solver_c" : "riem_solver3", {K, r.mode, h, r.dt, r.akap, r.ptop, r.rdgas, r.grav, r.p_fac}, {delp, pt, z, w, ws, zb}, {o0, o1, o2, o3});
+    return {o0, o1, o2, o3};
+  }
+  const double gama = 1.0 / (1.0 - r.akap), rgrav = 1.0 / r.grav, t1g = gama * 2.0 * r.dt * r.dt, rdt = 1.0 / r.dt, capa1 = r.akap - 1.0;
+  int pem = P.val(nm("pem"), K + 1);
+  add_col<S_cum>(P, "rs_pem", {K, 0, h, r.ptop, 1.0}, {delp, delp}, {pem});
+  int pm2 = P.val(nm("pm2"), K), pe = P.val(nm("pe"), K);
+  P.add<S_rs_pe>("rs_pe", {r.mode, h, gama, rgrav, r.rdgas}, {delp, pt, z, pem}, {pm2, pe}, K);
+  int bb = P.val(nm("bb"), K), gg = P.val(nm("g"), K), dd = P.val(nm("dd"), K);
+  P.add<S_rs_cpp>("rs_cpp", {K, h}, {delp, pe}, {bb, gg, dd}, K);
+  int pp = P.val(nm("ppi"), K + 1);
+  add_col<S_tri>(P, "rs_tri_pp", {K, 1, 0, 0, 1, h}, {bb, bb, gg, dd}, {pp});
+  int A = P.val(nm("aa"), K + 1);
+  P.add<S_rs_aa>("rs_aa", {K, h, t1g}, {z, pem, pp}, {A}, K + 1);
+  int di = P.val(nm("di"), K), rhs = P.val(nm("rhs"), K);
+  P.add<S_rs_rw>("rs_rw", {K, h, rgrav, r.dt}, {delp, w, pp, A, ws}, {di, rhs}, K);
+  int w2 = P.val(nm("w2"), K);
+  add_col<S_tri>(P, "rs_tri_w", {K, 0, 0, 1, 0, h}, {A, di, A, rhs}, {w2});
+  int pe2 = P.val(nm("pe2"), K + 1);
+  add_col<S_rs_pe2>(P, "rs_pe2", {K, h, rgrav, rdt}, {delp, w2, w}, {pe2});
+  int p1 = P.val(nm("p1"), K);
+  add_col<S_rs_p1>(P, "rs_p1", {K, h}, {pe2, bb, gg}, {p1});
+  int dzn = P.val(nm("dzn"), K);
+  P.add<S_rs_dz>("rs_dz", {h, rgrav, r.rdgas, capa1, r.p_fac}, {delp, pt, pm2, p1}, {dzn}, K);
+  int zn = P.val(nm("zn"), K + 1);
+  add_col<S_cum>(P, "rs_z", {K, 1, h, 0.0, r.mode == 0 ? r.grav : 1.0}, {dzn, zb}, {zn});
+  if (r.mode == 0) {
+    int pef = P.val(nm("pef"), K + 1);
+    P.add<S_rs_pef>("rs_pef", {h, r.ptop}, {pe2, pem}, {pef}, K + 1);
+    return {pef, zn, -1, -1};
+  }
+  return {pe2, zn, w2, dzn};
 }
 
 // update_dz_c (model/nh_utils_nlm.F90:43-182).  gz is patched in place (fill_4corners); returns {gz_new, ws}
@@ -89,8 +133,8 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
     CswOut cs = build_c_sw(P, mo, delp, pt, u, v, w, dt2, false, c.nord, K, tg + ".csw");
     if (c.nord > 0) add_patch(P, "halo_divgd", &mo.h_corner, {cs.divg_d});
     auto dzc = build_update_dz_c(P, mo, dp0, dt2, zs, cs.ut, cs.vt, gz, tg + ".dzc");
-    int pef = P.val(tg + ".pef", K + 1), gzr = P.val(tg + ".gzr", K + 1), d0 = P.val(tg + ".rc_w", K), d1 = P.val(tg + ".rc_dz", K);
-    add_col<S_riem>(P, "riem_solver_c", {K, 0, 1, dt2, c.akap, c.ptop, c.rdgas, c.grav, c.p_fac}, {cs.delpc, cs.ptc, dzc.first, cs.wc, dzc.second, s.phis}, {pef, gzr, d0, d1});
+    RiemOut rc = build_riem(P, {K, 0, 1, dt2, c.akap, c.ptop, c.rdgas, c.grav, c.p_fac}, cs.delpc, cs.ptc, dzc.first, cs.wc, dzc.second, s.phis, tg + ".rsc");
+    const int pef = rc.pp, gzr = rc.z;
     int uc = P.val(tg + ".uc", K), vc = P.val(tg + ".vc", K);
     P.add<S_pgrad_c>("p_grad_c", {dt2, 0}, {cs.uc, cs.vc, pef, gzr, cs.delpc}, {uc, vc}, K);
     add_patch(P, "halo_ucvc", &mo.h_cgrid, {uc, vc});
@@ -109,9 +153,9 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
     add_patch(P, "halo_pt", &mo.h_center, {pt});
     auto dzd = build_update_dz_d(P, mo, dp0, dp, c.hord_tm, rdt, zs, zh, ds.crx, ds.cry, ds.xfx, ds.yfx, tg + ".dzd");
     ws_d = dzd.second;
-    int ppe = P.val(tg + ".ppe", K + 1), zhn = P.val(tg + ".zh", K + 1);
-    w = P.val(tg + ".w", K); delz = P.val(tg + ".delz", K);
-    add_col<S_riem>(P, "riem_solver3", {K, 1, 0, dt, c.akap, c.ptop, c.rdgas, c.grav, c.p_fac}, {delp, pt, dzd.first, ds.w, dzd.second, zs}, {ppe, zhn, w, delz});
+    RiemOut r3 = build_riem(P, {K, 1, 0, dt, c.akap, c.ptop, c.rdgas, c.grav, c.p_fac}, delp, pt, dzd.first, ds.w, dzd.second, zs, tg + ".rs3");
+    const int ppe = r3.pp, zhn = r3.z;
+    w = r3.w; delz = r3.dz;
     zh = zhn;
     add_patch(P, "halo_zh", &mo.h_center, {zh});
     add_patch(P, "halo_ppe", &mo.h_center, {ppe});
@@ -140,10 +184,9 @@ void mod_riem(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
   DynConfig c; dyn_config_from(c, prm);
   const int mode = prm.geti("mode", 0);
   int delp = io.in(P, "delp", K), pt = io.in(P, "pt", K), z = io.in(P, "z", K + 1), w = io.in(P, "w", K), ws = io.in(P, "ws", 1), zb = io.in(P, "zb", 1);
-  int o0 = P.val("pp", K + 1), o1 = P.val("z_n", K + 1), o2 = P.val("w_n", K), o3 = P.val("dz_n", K);
-  add_col<S_riem>(P, "riem", {K, mode, mode == 0 ? 1 : 0, prm.get("dts", 100.0), c.akap, c.ptop, c.rdgas, c.grav, c.p_fac}, {delp, pt, z, w, ws, zb}, {o0, o1, o2, o3});
-  io.out(P, "pp", o0); io.out(P, "z_n", o1);
-  if (mode == 1) { io.out(P, "w_n", o2); io.out(P, "dz_n", o3); }
+  RiemOut r = build_riem(P, {K, mode, mode == 0 ? 1 : 0, prm.get("dts", 100.0), c.akap, c.ptop, c.rdgas, c.grav, c.p_fac}, delp, pt, z, w, ws, zb, "riem");
+  io.out(P, "pp", r.pp); io.out(P, "z_n", r.z);
+  if (mode == 1) { io.out(P, "w_n", r.w); io.out(P, "dz_n", r.dz); }
 }
 
 void mod_update_dz_c(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
