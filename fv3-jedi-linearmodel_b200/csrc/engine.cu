@@ -240,9 +240,9 @@ void Program::run(Mode mode) {
       double largest = 0.0; for (double b : seg_bytes) largest = std::max(largest, b);
       double budget = dv->ad_store_budget;
       if (const char* e = getenv("FV3LM_AD_STORE_BUDGET")) budget = atof(e);
-      if (budget < 0.0) budget = 0.75 * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
+      if (budget < 0.0) budget = 0.85 * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
       if (dv->comm) budget = dv->comm->min_over_ranks(budget);   // same decision on every rank
-      budget -= 3.0 * largest;                      // a segment being reversed holds trajectory + adjoints, plus the boundary values
+      budget -= 2.0 * largest;                      // a segment being reversed holds trajectory + adjoints, plus the boundary values
       ad_keep_from = nseg - 1;                      // the last segment is always kept
       while (ad_keep_from > 0 && seg_bytes[ad_keep_from - 1] <= budget) { budget -= seg_bytes[ad_keep_from - 1]; ad_keep_from--; }
     }

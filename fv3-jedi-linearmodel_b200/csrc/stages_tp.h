@@ -44,6 +44,20 @@ template <int DIR, class X> DEV typename X::T edge_al(const X& x, int f, int d) 
 template <int DIR, class X> DEV typename X::T ppm_flux(const X& x, int fq, typename X::T c, int ord) {
   using T = typename X::T;
   if (ord == 1) return val(c) > 0.0 ? Q<DIR>(x, fq, -1) : Q<DIR>(x, fq, 0);
+  {
+    // regular faces (all three edge values use the uniform weights): straight-line code, no edge tests
+    const int ia = DIR == 0 ? x.i : x.j, np = DIR == 0 ? x.g.npx : x.g.npy;
+    if (ia >= 4 && ia <= np - 3) {
+      T qm2 = Q<DIR>(x, fq, -2), qm1 = Q<DIR>(x, fq, -1), q0 = Q<DIR>(x, fq, 0), q1 = Q<DIR>(x, fq, 1);
+      T al0 = p1 * (qm1 + q0) + p2 * (qm2 + q1);
+      if (val(c) > 0.0) {
+        T alm = p1 * (qm2 + qm1) + p2 * (Q<DIR>(x, fq, -3) + q0);
+        return qm1 + (1.0 - c) * (al0 - qm1 - c * (alm + al0 - (qm1 + qm1)));
+      }
+      T alp = p1 * (q0 + q1) + p2 * (qm1 + Q<DIR>(x, fq, 2));
+      return q0 + (1.0 + c) * (al0 - q0 + c * (al0 + alp - (q0 + q0)));
+    }
+  }
   T al0 = edge_al<DIR>(x, fq, 0);
   if (val(c) > 0.0) {
     T qt = Q<DIR>(x, fq, -1);
@@ -150,15 +164,20 @@ template <int DIR> struct S_ppm {
         const double a = kn.outad.p[0][x.off(nko, 0, 0, 0)];
         if (a != 0.0) {
           const double c = x.in(1);
-          const double al0 = tp::edge_al<DIR>(x, 0, 0);
-          double dc;
-          if (c > 0.0) {
-            const double qt = tp::Q<DIR>(x, 0, -1), alm = tp::edge_al<DIR>(x, 0, -1), b = alm + al0 - (qt + qt);
-            dc = -(al0 - qt - c * b) - (1.0 - c) * b;
+          double al0, qt, al2;      // al2: the upwind-side second edge value (alm for c > 0, alp otherwise)
+          if (pos >= 4 && pos <= np - 3) {
+            const double qm2 = tp::Q<DIR>(x, 0, -2), qm1 = tp::Q<DIR>(x, 0, -1), q0 = tp::Q<DIR>(x, 0, 0), q1 = tp::Q<DIR>(x, 0, 1);
+            al0 = tp::p1 * (qm1 + q0) + tp::p2 * (qm2 + q1);
+            if (c > 0.0) { qt = qm1; al2 = tp::p1 * (qm2 + qm1) + tp::p2 * (tp::Q<DIR>(x, 0, -3) + q0); }
+            else { qt = q0; al2 = tp::p1 * (q0 + q1) + tp::p2 * (qm1 + tp::Q<DIR>(x, 0, 2)); }
           } else {
-            const double qt = tp::Q<DIR>(x, 0, 0), alp = tp::edge_al<DIR>(x, 0, 1), b = al0 + alp - (qt + qt);
-            dc = (al0 - qt + c * b) + (1.0 + c) * b;
+            al0 = tp::edge_al<DIR>(x, 0, 0);
+            if (c > 0.0) { qt = tp::Q<DIR>(x, 0, -1); al2 = tp::edge_al<DIR>(x, 0, -1); }
+            else { qt = tp::Q<DIR>(x, 0, 0); al2 = tp::edge_al<DIR>(x, 0, 1); }
           }
+          double dc;
+          if (c > 0.0) { const double b = al2 + al0 - (qt + qt); dc = -(al0 - qt - c * b) - (1.0 - c) * b; }
+          else { const double b = al0 + al2 - (qt + qt); dc = (al0 - qt + c * b) + (1.0 + c) * b; }
           acc[1] += dc * a;
         }
       }
