@@ -33,7 +33,13 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
   FV3LM_TRY
   if (!cfg || !out) throw std::runtime_error("fv3lm_create: null argument");
   if (cfg->ntiles != 6 || cfg->npx != cfg->npy || cfg->ng != 3) throw std::runtime_error("fv3lm_create: need 6 square tiles and ng = 3");
-  if (cfg->npz > 127) throw std::runtime_error("fv3lm_create: npz > 127 unsupported");
+  if (cfg->npz > 95 || cfg->npz < 3) throw std::runtime_error("fv3lm_create: npz must be in 3..95");
+  for (int ho : {cfg->hord_mt, cfg->hord_vt, cfg->hord_tm, cfg->hord_dp, cfg->hord_tr})
+    if (ho != 1 && ho != 2) throw std::runtime_error("fv3lm_create: hord_* must be 1 or 2 (the linear schemes the TL/AD implement, tp_core_tlm.F90:2431-2466)");
+  if (cfg->nq != 4) throw std::runtime_error("fv3lm_create: nq must be 4 (qv, ql, qi, o3)");
+  if (cfg->n_split < 1 || cfg->k_split < 1 || !(cfg->dt > 0.0)) throw std::runtime_error("fv3lm_create: n_split, k_split and dt must be positive");
+  if (cfg->nord < 0 || cfg->nord > 3) throw std::runtime_error("fv3lm_create: nord must be in 0..3");
+  if (cfg->npx < 9) throw std::runtime_error("fv3lm_create: need at least 8 cells per tile edge");
 #ifndef FV3LM_HOST_EMU
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
