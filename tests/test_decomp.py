@@ -17,6 +17,7 @@ CASES = {
     "dyn_core_nh": lambda emu: test_nh._run_dyn_nh(emu, 2),
     "step_hydro": lambda emu: test_fv_dynamics._run_step(emu, 1, 2),
     "step_nonhydro": lambda emu: test_fv_dynamics._run_step(emu, 1, 2, nonhydro=True),
+    "step_nonhydro_c24": lambda emu: test_fv_dynamics._run_step(emu, 1, 1, K=3, nonhydro=True, N=24),
 }
 
 

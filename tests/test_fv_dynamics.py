@@ -67,8 +67,7 @@ def api_state(N, K, seed, ak, bk, nonhydro=False):
     return f, rng
 
 
-def _run_step(emu, k_split, n_split, K=4, nonhydro=False):
-    N = 12
+def _run_step(emu, k_split, n_split, K=4, nonhydro=False, N=12):
     ptop = CFG["ptop"]
     ak, bk = eta(K, ptop)
     f, rng = api_state(N, K, 31, ak, bk, nonhydro)
@@ -106,6 +105,11 @@ def test_step_hydro_emu():
 
 def test_step_nonhydro_emu():
     print(_run_step(True, 1, 2, nonhydro=True))
+
+
+def test_step_nonhydro_c24_emu():
+    """a second resolution (cube-edge special cases sit at different distances from each other)"""
+    print(_run_step(True, 1, 1, K=5, nonhydro=True, N=24))
 
 
 @pytest.mark.gpu
