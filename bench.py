@@ -273,7 +273,7 @@ def run_reference(args):
     hydro = not args.nonhydro
     mc = model_config(N, K, hydro, 450.0 * 180.0 / N)
     out = {"impl": "reference", "metric": "TL+AD model steps/sec", "value": b["value"], "unit": b["unit"], "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / b["value"], "higher_is_better": True, "scaling": "weak",
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / b["value"], "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "C%d L%d %s dynamics-only TL+AD step, dt=%gs, n_split=%d, k_split=1, nq=4, linear schemes (hord=2, kord=17), whole sphere (CPU arm: bounded C%d sample scaled by cells x sub-steps, see cpu_baseline.sample)"
                                   % (N, K, "hydrostatic" if hydro else "non-hydrostatic", 450.0 * 180.0 / N, mc["n_split"], args.cpu_res)},

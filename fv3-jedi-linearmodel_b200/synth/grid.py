@@ -356,7 +356,7 @@ def build_metrics(N, radius=RADIUS, omega=OMEGA, shift_fac=18.0):
     i, j = 1, 1
     area_c[:, j + o, i + o] = 3.0 * get_area(G(i, j), mid_ll(G(i, j), G(i, j + 1)), mid_ll(G(i, j), G(i + 1, j)), Ag(i, j), radius)
     i, j = npx, 1
-    area_c[:, j + o, i + o] = 3.0 * get_area(mid_ll(G(i - 1, j), G(i, j)), Ag(i, j), G(i, j), mid_ll(G(i, j), G(i, j + 1)), radius)
+    area_c[:, j + o, i + o] = 3.0 * get_area(mid_ll(G(i - 1, j), G(i, j)), Ag(i - 1, j), G(i, j), mid_ll(G(i, j), G(i, j + 1)), radius)
     i, j = npx, npy
     area_c[:, j + o, i + o] = 3.0 * get_area(Ag(i - 1, j - 1), mid_ll(G(i - 1, j), G(i, j)), mid_ll(G(i, j - 1), G(i, j)), G(i, j), radius)
     i, j = 1, npy
