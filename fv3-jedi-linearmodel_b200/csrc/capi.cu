@@ -5,6 +5,7 @@ using namespace fv3lm;
 namespace fv3lm { void a2b_corner_weights(const Geom& g, const double* glon, const double* glat, const double* alon, const double* alat, double* out); }
 
 thread_local std::string fv3lm_g_err;
+static_assert(sizeof(fv3lm_config) == 256, "fv3lm_config is mirrored field by field in fv3lm.py and fortran/fv3lm_b200_capi_mod.F90");
 
 // host [rows][NX] contiguous <-> device [rows][pitch]
 static void up2d(const Geom& g, double* d, const double* h, size_t rows) {
@@ -39,6 +40,8 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
   if (cfg->nq != 4) throw std::runtime_error("fv3lm_create: nq must be 4 (qv, ql, qi, o3)");
   if (cfg->n_split < 1 || cfg->k_split < 1 || !(cfg->dt > 0.0)) throw std::runtime_error("fv3lm_create: n_split, k_split and dt must be positive");
   if (cfg->nord < 0 || cfg->nord > 3) throw std::runtime_error("fv3lm_create: nord must be in 0..3");
+  if (!cfg->hydrostatic && cfg->a_imp != 0.0 && !(cfg->a_imp > 0.5))
+    throw std::runtime_error("fv3lm_create: a_imp <= 0.5 selects the RIM_2D / SIM3 solvers (model/nh_core_nlm.F90:136-146), which are not built; use 0.5 < a_imp <= 1");
   if (cfg->npx < 9) throw std::runtime_error("fv3lm_create: need at least 8 cells per tile edge");
 #ifndef FV3LM_HOST_EMU
   int ndev = 0;

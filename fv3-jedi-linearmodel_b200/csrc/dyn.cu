@@ -102,6 +102,9 @@ void dyn_config_from(DynConfig& c, const ModuleParams& prm) {
   c.rdgas = prm.get("rdgas", f->rdgas); c.grav = prm.get("grav", f->grav);
   c.zvir = prm.get("zvir", f->zvir); c.k_split = prm.geti("k_split", f->k_split); c.nq = prm.geti("nq", f->nq);
   c.hord_tr = prm.geti("hord_tr", f->hord_tr);
+  // 0 in the config = "not set": the library defaults (fully implicit SIM1 solver, p_fac = 0.05)
+  c.a_imp = prm.get("a_imp", f->a_imp != 0.0 ? f->a_imp : 1.0);
+  c.p_fac = prm.get("p_fac", f->p_fac != 0.0 ? f->p_fac : 0.05);
 }
 
 void mod_dyn_core(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {

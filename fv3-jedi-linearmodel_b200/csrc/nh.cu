@@ -19,12 +19,17 @@ static bool riem_mono() { static const bool m = getenv("FV3LM_RIEM_MONO") != nul
 RiemOut build_riem(Program& P, const RiemPrm& r, int delp, int pt, int z, int w, int ws, int zb, const std::string& tag) {
   const int K = r.K, h = r.halo;
   auto nm = [&](const char* s) { return tag + "." + s; };
-  if (riem_mono()) {
+  if (!(r.a_imp > 0.5)) throw std::runtime_error("riem: a_imp <= 0.5 (RIM_2D / SIM3 solvers) is not supported");
+  // Riem_Solver3 with 0.5 < a_imp <= 0.999: SIM_solver, off-centring alpha = a_imp (scale_m = 0); everything else: SIM1_solver
+  const bool sim = r.mode == 1 && !(r.a_imp > 0.999);
+  if (riem_mono() && !sim) {   // (the monolithic A/B kernel implements SIM1 only)
     int o0 = P.val(nm("pp"), K + 1), o1 = P.val(nm("z"), K + 1), o2 = P.val(nm("w"), K), o3 = P.val(nm("dz"), K);
     add_col<S_riem>(P, r.mode == 0 ? "riem_solver_c" : "riem_solver3", {K, r.mode, h, r.dt, r.akap, r.ptop, r.rdgas, r.grav, r.p_fac}, {delp, pt, z, w, ws, zb}, {o0, o1, o2, o3});
     return {o0, o1, o2, o3};
   }
-  const double gama = 1.0 / (1.0 - r.akap), rgrav = 1.0 / r.grav, t1g = gama * 2.0 * r.dt * r.dt, rdt = 1.0 / r.dt, capa1 = r.akap - 1.0;
+  const double alpha = sim ? r.a_imp : 1.0, beta = 1.0 - alpha, ra = 1.0 / alpha, t2 = beta / alpha;
+  const double gama = 1.0 / (1.0 - r.akap), rgrav = 1.0 / r.grav, t1g = sim ? 2.0 * gama * (alpha * r.dt) * (alpha * r.dt) : gama * 2.0 * r.dt * r.dt,
+               rdt = 1.0 / r.dt, capa1 = r.akap - 1.0;
   int pem = P.val(nm("pem"), K + 1);
   add_col<S_cum>(P, "rs_pem", {K, 0, h, r.ptop, 1.0}, {delp, delp}, {pem});
   int pm2 = P.val(nm("pm2"), K), pe = P.val(nm("pe"), K);
@@ -36,11 +41,13 @@ RiemOut build_riem(Program& P, const RiemPrm& r, int delp, int pt, int z, int w,
   int A = P.val(nm("aa"), K + 1);
   P.add<S_rs_aa>("rs_aa", {K, h, t1g}, {z, pem, pp}, {A}, K + 1);
   int di = P.val(nm("di"), K), rhs = P.val(nm("rhs"), K);
-  P.add<S_rs_rw>("rs_rw", {K, h, rgrav, r.dt}, {delp, w, pp, A, ws}, {di, rhs}, K);
+  if (sim) P.add<S_rs_rw_t<true>>("rs_rw_sim", {K, h, rgrav, r.dt, t2, ra}, {delp, w, pp, A, ws}, {di, rhs}, K);
+  else P.add<S_rs_rw>("rs_rw", {K, h, rgrav, r.dt, 0.0, 1.0}, {delp, w, pp, A, ws}, {di, rhs}, K);
   int w2 = P.val(nm("w2"), K);
   add_col<S_tri>(P, "rs_tri_w", {K, 0, 0, 1, 0, h}, {A, di, A, rhs}, {w2});
   int pe2 = P.val(nm("pe2"), K + 1);
-  add_col<S_rs_pe2>(P, "rs_pe2", {K, h, rgrav, rdt}, {delp, w2, w}, {pe2});
+  if (sim) add_col<S_rs_pe2_t<true>>(P, "rs_pe2_sim", {K, h, rgrav, rdt, beta, ra}, {delp, w2, w, pp}, {pe2});
+  else add_col<S_rs_pe2>(P, "rs_pe2", {K, h, rgrav, rdt, 0.0, 1.0}, {delp, w2, w}, {pe2});
   int p1 = P.val(nm("p1"), K);
   add_col<S_rs_p1>(P, "rs_p1", {K, h}, {pe2, bb, gg}, {p1});
   int dzn = P.val(nm("dzn"), K);
@@ -51,6 +58,11 @@ RiemOut build_riem(Program& P, const RiemPrm& r, int delp, int pt, int z, int w,
     int pef = P.val(nm("pef"), K + 1);
     P.add<S_rs_pef>("rs_pef", {h, r.ptop}, {pe2, pem}, {pef}, K + 1);
     return {pef, zn, -1, -1};
+  }
+  if (sim) {
+    int ppe = P.val(nm("ppe"), K + 1);
+    P.add<S_rs_blend>("rs_blend", {h, beta}, {pe2, pp}, {ppe}, K + 1);
+    return {ppe, zn, w2, dzn};
   }
   return {pe2, zn, w2, dzn};
 }
@@ -133,7 +145,7 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
     CswOut cs = build_c_sw(P, mo, delp, pt, u, v, w, dt2, false, c.nord, K, tg + ".csw");
     if (c.nord > 0) add_patch(P, "halo_divgd", &mo.h_corner, {cs.divg_d});
     auto dzc = build_update_dz_c(P, mo, dp0, dt2, zs, cs.ut, cs.vt, gz, tg + ".dzc");
-    RiemOut rc = build_riem(P, {K, 0, 1, dt2, c.akap, c.ptop, c.rdgas, c.grav, c.p_fac}, cs.delpc, cs.ptc, dzc.first, cs.wc, dzc.second, s.phis, tg + ".rsc");
+    RiemOut rc = build_riem(P, {K, 0, 1, dt2, c.akap, c.ptop, c.rdgas, c.grav, c.p_fac, c.a_imp}, cs.delpc, cs.ptc, dzc.first, cs.wc, dzc.second, s.phis, tg + ".rsc");
     const int pef = rc.pp, gzr = rc.z;
     int uc = P.val(tg + ".uc", K), vc = P.val(tg + ".vc", K);
     P.add<S_pgrad_c>("p_grad_c", {dt2, 0}, {cs.uc, cs.vc, pef, gzr, cs.delpc}, {uc, vc}, K);
@@ -153,7 +165,7 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
     add_patch(P, "halo_pt", &mo.h_center, {pt});
     auto dzd = build_update_dz_d(P, mo, dp0, dp, c.hord_tm, rdt, zs, zh, ds.crx, ds.cry, ds.xfx, ds.yfx, tg + ".dzd");
     ws_d = dzd.second;
-    RiemOut r3 = build_riem(P, {K, 1, 0, dt, c.akap, c.ptop, c.rdgas, c.grav, c.p_fac}, delp, pt, dzd.first, ds.w, dzd.second, zs, tg + ".rs3");
+    RiemOut r3 = build_riem(P, {K, 1, 0, dt, c.akap, c.ptop, c.rdgas, c.grav, c.p_fac, c.a_imp}, delp, pt, dzd.first, ds.w, dzd.second, zs, tg + ".rs3");
     const int ppe = r3.pp, zhn = r3.z;
     w = r3.w; delz = r3.dz;
     zh = zhn;
@@ -184,7 +196,7 @@ void mod_riem(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
   DynConfig c; dyn_config_from(c, prm);
   const int mode = prm.geti("mode", 0);
   int delp = io.in(P, "delp", K), pt = io.in(P, "pt", K), z = io.in(P, "z", K + 1), w = io.in(P, "w", K), ws = io.in(P, "ws", 1), zb = io.in(P, "zb", 1);
-  RiemOut r = build_riem(P, {K, mode, mode == 0 ? 1 : 0, prm.get("dts", 100.0), c.akap, c.ptop, c.rdgas, c.grav, c.p_fac}, delp, pt, z, w, ws, zb, "riem");
+  RiemOut r = build_riem(P, {K, mode, mode == 0 ? 1 : 0, prm.get("dts", 100.0), c.akap, c.ptop, c.rdgas, c.grav, c.p_fac, c.a_imp}, delp, pt, z, w, ws, zb, "riem");
   io.out(P, "pp", r.pp); io.out(P, "z_n", r.z);
   if (mode == 1) { io.out(P, "w_n", r.w); io.out(P, "dz_n", r.dz); }
 }

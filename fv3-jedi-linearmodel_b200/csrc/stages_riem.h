@@ -1,4 +1,4 @@
-// Riem_Solver_c / Riem_Solver3 (SIM1_solver, model/nh_utils_nlm.F90:297-401, :1177-1308, model/nh_core_nlm.F90:40-206)
+// Riem_Solver_c / Riem_Solver3 (SIM1_solver and SIM_solver, model/nh_utils_nlm.F90:297-401, :1177-1308, :1310-1466, model/nh_core_nlm.F90:40-206)
 // decomposed into level-parallel stencil stages and thin column recurrences.
 //
 // The monolithic one-thread-per-column kernel (S_riem, stages_nh.h) keeps 13-45 work arrays of 72 levels in local
@@ -105,16 +105,22 @@ struct S_tri {
 };
 
 // ---- column: pe2(0) = 0 ; pe2(k+1) = pe2(k) + dm(k) (w2(k) - w1(k)) / dt.   in: delp w2 w1 ; out: pe2 (K+1)
-struct S_rs_pe2 {
-  static constexpr int NI = 3, NO = 1;
-  struct P { int K, halo; double rgrav, rdt; };
+// SIM (SIM_solver, off-centred, model/nh_utils_nlm.F90:1434-1444): in: delp w2 w1 pp ;
+//   pe2(k+1) = pe2(k) + (dm(k) (w2(k) - w1(k)) / dt - beta (pp(k+1) - pp(k))) ra
+template <bool SIM> struct S_rs_pe2_t {
+  static constexpr int NI = SIM ? 4 : 3, NO = 1;
+  struct P { int K, halo; double rgrav, rdt, beta, ra; };
   template <class X> DEV static void eval(X& x, const P& p) {
     using T = typename X::T;
     const Geom& g = x.g;
     if (!x.in_rect(g.is - p.halo, g.ie + p.halo, g.js - p.halo, g.je + p.halo)) return;
     T s = T(0.0);
     x.out(0, 0, s);
-    for (int k = 0; k < p.K; k++) { s = s + (x.in(0, k) * p.rgrav) * (x.in(1, k) - x.in(2, k)) * p.rdt; x.out(0, k + 1, s); }
+    for (int k = 0; k < p.K; k++) {
+      if constexpr (SIM) s = s + ((x.in(0, k) * p.rgrav) * (x.in(1, k) - x.in(2, k)) * p.rdt - p.beta * (x.in(3, k + 1) - x.in(3, k))) * p.ra;
+      else s = s + (x.in(0, k) * p.rgrav) * (x.in(1, k) - x.in(2, k)) * p.rdt;
+      x.out(0, k + 1, s);
+    }
   }
   template <class X> DEV static void eval_ad(X& x, const P& p) {
     const Geom& g = x.g;
@@ -123,10 +129,13 @@ struct S_rs_pe2 {
     for (int k = p.K - 1; k >= 0; k--) {
       a += x.oad(0, k + 1);
       const double dm = x.in(0, k) * p.rgrav, dw = x.in(1, k) - x.in(2, k);
-      x.add(0, k, a * p.rgrav * dw * p.rdt); x.add(1, k, a * dm * p.rdt); x.add(2, k, -a * dm * p.rdt);
+      const double b = SIM ? a * p.ra : a;
+      x.add(0, k, b * p.rgrav * dw * p.rdt); x.add(1, k, b * dm * p.rdt); x.add(2, k, -b * dm * p.rdt);
+      if constexpr (SIM) { x.add(3, k + 1, -b * p.beta); x.add(3, k, b * p.beta); }
     }
   }
 };
+using S_rs_pe2 = S_rs_pe2_t<false>;
 
 // ---- column: p1(K-1) = (pe2(K-1) + 2 pe2(K))/3 ; p1(k) = (pe2(k) + bb(k) pe2(k+1) + g(k) pe2(k+2))/3 - g(k) p1(k+1)
 // in: pe2 bb g ; out: p1 (K)
@@ -219,22 +228,33 @@ struct S_rs_aa {
 };
 
 // ---- stencil: diagonal and right-hand side of the w system.  in: delp w pp A ws ; out: di rhs   (nk = K)
-struct S_rs_rw {
+// SIM (SIM_solver, model/nh_utils_nlm.F90:1396-1427): the explicit part of the off-centred scheme enters the right-hand side,
+//   wk(k) = t2 A(k) (w(k-1) - w(k)) on interior interfaces, rhs(k) += wk(k+1) - wk(k) ; bottom layer: - wk(K-1) + A(K) (t2 w - ra ws)
+template <bool SIM> struct S_rs_rw_t {
   static constexpr int NI = 5, NO = 2;
-  struct P { int K, halo; double rgrav, dt; };
-  static constexpr int NT = 7;
-  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}, {2, 0, 0, 1}, {3, 0, 0, 0}, {3, 0, 0, 1}, {4, 0, 0, KLAST}};   // ws is 2-D: read by level K-1, owned by its single level
+  struct P { int K, halo; double rgrav, dt, t2, ra; };
+  static constexpr int NT = SIM ? 9 : 7;
+  static constexpr Tap taps[9] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}, {2, 0, 0, 1}, {3, 0, 0, 0}, {3, 0, 0, 1}, {4, 0, 0, KLAST},   // ws is 2-D: read by level K-1, owned by its single level
+                                  {1, 0, 0, -1}, {1, 0, 0, 1}};
   template <class X> DEV static void eval(X& x, const P& p) {
     using T = typename X::T;
     const Geom& g = x.g;
     if (!x.in_rect(g.is - p.halo, g.ie + p.halo, g.js - p.halo, g.je + p.halo)) return;
     T dm = x.in(0) * p.rgrav, a0 = x.in(3), a1 = x.in(3, 0, 0, 1);
     x.out(0, dm - (a0 + a1));
-    T r = dm * x.in(1) + p.dt * (x.in(2, 0, 0, 1) - x.in(2));
-    if (x.kk == p.K - 1) r = r - a1 * x.in(4, 0, 0, KLAST);
+    T wc = x.in(1);
+    T r = dm * wc + p.dt * (x.in(2, 0, 0, 1) - x.in(2));
+    if constexpr (SIM) {
+      if (x.kk < p.K - 1) r = r + p.t2 * a1 * (wc - x.in(1, 0, 0, 1));
+      if (x.kk > 0) r = r - p.t2 * a0 * (x.in(1, 0, 0, -1) - wc);
+      if (x.kk == p.K - 1) r = r + a1 * (p.t2 * wc - p.ra * x.in(4, 0, 0, KLAST));
+    } else {
+      if (x.kk == p.K - 1) r = r - a1 * x.in(4, 0, 0, KLAST);
+    }
     x.out(1, r);
   }
 };
+using S_rs_rw = S_rs_rw_t<false>;
 
 // ---- stencil: new layer thickness.  in: delp pt pm2 p1 ; out: dz   (nk = K)
 struct S_rs_dz {
@@ -264,8 +284,23 @@ struct S_rs_pef {
   }
 };
 
+// ---- stencil: SIM_solver's final blend  pe2 <- pe2 + beta (pp - pe2)  (model/nh_utils_nlm.F90:1460-1464).  in: pe2 pp ; out: ppe (nk = K+1)
+struct S_rs_blend {
+  static constexpr int NI = 2, NO = 1;
+  struct P { int halo; double beta; };
+  static constexpr int NT = 2;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is - p.halo, g.ie + p.halo, g.js - p.halo, g.je + p.halo)) return;
+    auto pe2 = x.in(0);
+    x.out(0, pe2 + p.beta * (x.in(1) - pe2));
+  }
+};
+
 struct RiemOut { int pp, z, w, dz; };
-struct RiemPrm { int K, mode, halo; double dt, akap, ptop, rdgas, grav, p_fac; };
+// a_imp: Riem_Solver3 only (model/nh_core_nlm.F90:136-152): > 0.999 SIM1_solver, (0.5, 0.999] SIM_solver; Riem_Solver_c uses SIM1 for every a_imp > 0.5
+struct RiemPrm { int K, mode, halo; double dt, akap, ptop, rdgas, grav, p_fac; double a_imp = 1.0; };
 RiemOut build_riem(Program& P, const RiemPrm& r, int delp, int pt, int z, int w, int ws, int zb, const std::string& tag);
 
 }  // namespace fv3lm

@@ -129,7 +129,8 @@ subroutine create(self,conf)
  cfg%do_vort_damp = merge(1, 0, self%FV_AtmP(1)%flagstruct%do_vort_damp_pert)
  cfg%rank = mpp_pe() - mpp_root_pe(); cfg%nranks = mpp_npes()
  cfg%layout_x = A%layout(1); cfg%layout_y = A%layout(2)
- cfg%reserved = 0
+ cfg%reserved0 = 0; cfg%reserved = 0
+ cfg%a_imp = A%flagstruct%a_imp; cfg%p_fac = A%flagstruct%p_fac
 
  call check(self, fv3lm_create(cfg, conf%ak, conf%bk, self%handle), 'create')
 

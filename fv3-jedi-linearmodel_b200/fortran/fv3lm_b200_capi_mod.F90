@@ -19,7 +19,9 @@ type, bind(c) :: fv3lm_config
   real(c_double) :: zvir, kappa, cp, rdgas, grav
   integer(c_int) :: do_vort_damp
   integer(c_int) :: rank, nranks, layout_x, layout_y
-  integer(c_int) :: reserved(12)
+  integer(c_int) :: reserved0
+  real(c_double) :: a_imp, p_fac
+  integer(c_int) :: reserved(8)
 end type fv3lm_config
 
 !> mirror of `struct fv3lm_fields`: ten pointers to (isc:iec, jsc:jec, npz) REAL64 arrays

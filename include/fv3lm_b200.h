@@ -46,7 +46,13 @@ typedef struct fv3lm_config {
    * (one process per GPU); each tile is split layout_x x layout_y (0 = choose automatically) and
    * the 6*layout_x*layout_y sub-domains are dealt out in consecutive blocks.  nranks = 0 means 1. */
   int rank, nranks, layout_x, layout_y;
-  int reserved[12];
+  int reserved0;          /* 0; keeps the doubles below 8-byte aligned                              */
+  /* non-hydrostatic solver (model/nh_core_nlm.F90:136-152).  0 = not set -> library default.
+   * a_imp > 0.999: SIM1_solver (default 1.0); 0.5 < a_imp <= 0.999: SIM_solver in Riem_Solver3
+   * (Riem_Solver_c keeps SIM1, model/nh_utils_nlm.F90:366-376); a_imp <= 0.5 (RIM_2D / SIM3) is an error.
+   * p_fac: lower bound of the gas pressure relative to the hydrostatic one (default 0.05).        */
+  double a_imp, p_fac;
+  int reserved[8];
 } fv3lm_config;
 
 int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv3lm_handle** out);

@@ -1,12 +1,12 @@
 """ORACLE (test infrastructure only).  Non-hydrostatic pieces restated in torch float64:
 
   model/nh_utils_nlm.F90   update_dz_c :43-182, update_dz_d :183-296, Riem_Solver_c :297-401,
-                           SIM1_solver :1177-1308, edge_profile :1519-1625 (non-uniform branch)
+                           SIM1_solver :1177-1308, SIM_solver :1310-1466, edge_profile :1519-1625 (non-uniform branch)
   model/nh_core_nlm.F90    Riem_Solver3 :40-206 (a_imp > 0.999 -> SIM1_solver, use_logp = F, fp_out = F)
   model/dyn_core_nlm.F90   the non-hydrostatic branch of dyn_core :78-1040, pk3_halo :1129, pe_halo :1232
   (TL: model_tlmadm/nh_utils_tlm.F90, nh_core_tlm.F90; AD: nh_utils_adm.F90, nh_core_adm.F90)
 
-Configuration: a_imp = 1 (fully implicit SIM1), p_fac = 0.05, no MOIST_CAPPA / USE_COND,
+Configuration: a_imp = 1 (fully implicit SIM1) or 0.5 < a_imp <= 0.999 (SIM_solver, Riem_Solver3 only; scale_m = 0), p_fac = 0.05, no MOIST_CAPPA / USE_COND,
 beta = 0 (nh_p_grad), use_logp = F.   parity unpinned (no reference vectors).
 """
 import numpy as np
@@ -74,6 +74,68 @@ def sim1_solver(dt, dm2, pm2, pem, w1, dz2, pt2, ws, rgas, gama, kappa, p_fac):
     return w2, pe2, dzn
 
 
+def sim_solver(dt, dm2, pm2, pem, w1, dz2, pt2, ws, rgas, gama, kappa, p_fac, alpha, scale_m=0.):
+    """SIM_solver (model/nh_utils_nlm.F90:1310-1466): off-centred (alpha = a_imp in (0.5, 0.999]) semi-implicit
+    solver; lists over k of tensors.  Returns w2 (K), pe2 (K+1, blended with pp at the end), dz2_new (K)"""
+    K = len(dm2)
+    beta = 1. - alpha
+    ra = 1. / alpha
+    t2 = beta / alpha
+    t1g = 2. * gama * (alpha * dt) ** 2
+    rdt = 1. / dt
+    capa1 = kappa - 1.
+    pe = [torch.exp(gama * torch.log(-dm2[k] / dz2[k] * rgas * pt2[k])) - pm2[k] for k in range(K)]
+    g_rat = [None] * K; bb = [None] * K; dd = [None] * K
+    for k in range(K - 1):
+        g_rat[k] = dm2[k] / dm2[k + 1]
+        bb[k] = 2. * (1. + g_rat[k])
+        dd[k] = 3. * (pe[k] + g_rat[k] * pe[k + 1])
+    bb[K - 1] = 2. + 0. * dm2[0]
+    dd[K - 1] = 3. * pe[K - 1]
+    pp = [None] * (K + 1); gam = [None] * K
+    bet = bb[0]
+    pp[0] = 0. * dm2[0]
+    pp[1] = dd[0] / bet
+    for k in range(1, K):
+        gam[k] = g_rat[k - 1] / bet
+        bet = bb[k] - gam[k]
+        pp[k + 1] = (dd[k] - pp[k]) / bet
+    for k in range(K - 1, 0, -1):
+        pp[k] = pp[k] - gam[k] * pp[k + 1]
+    pef = [pem[k] + pp[k] for k in range(K + 1)]          # "pe2 is Full p"
+    aa = [None] * K; wk = [None] * K
+    for k in range(1, K):
+        aa[k] = t1g / (dz2[k - 1] + dz2[k]) * pef[k]
+        wk[k] = t2 * aa[k] * (w1[k - 1] - w1[k])
+        aa[k] = aa[k] - scale_m * dm2[0]
+    w2 = [None] * K
+    bet = dm2[0] - aa[1]
+    w2[0] = (dm2[0] * w1[0] + dt * pp[1] + wk[1]) / bet
+    for k in range(1, K - 1):
+        gam[k] = aa[k] / bet
+        bet = dm2[k] - (aa[k] + aa[k + 1] + aa[k] * gam[k])
+        w2[k] = (dm2[k] * w1[k] + dt * (pp[k + 1] - pp[k]) + wk[k + 1] - wk[k] - aa[k] * w2[k - 1]) / bet
+    wk1 = t1g / dz2[K - 1] * pef[K]
+    gam[K - 1] = aa[K - 1] / bet
+    bet = dm2[K - 1] - (aa[K - 1] + wk1 + aa[K - 1] * gam[K - 1])
+    w2[K - 1] = (dm2[K - 1] * w1[K - 1] + dt * (pp[K] - pp[K - 1]) - wk[K - 1] + wk1 * (t2 * w1[K - 1] - ra * ws)
+                 - aa[K - 1] * w2[K - 2]) / bet
+    for k in range(K - 2, -1, -1):
+        w2[k] = w2[k] - gam[k + 1] * w2[k + 1]
+    pe2 = [None] * (K + 1)
+    pe2[0] = 0. * dm2[0]
+    for k in range(K):
+        pe2[k + 1] = pe2[k] + (dm2[k] * (w2[k] - w1[k]) * rdt - beta * (pp[k + 1] - pp[k])) * ra
+    dzn = [None] * K
+    p1 = (pe2[K - 1] + 2. * pe2[K]) * R3
+    dzn[K - 1] = -dm2[K - 1] * rgas * pt2[K - 1] * torch.exp(capa1 * torch.log(torch.maximum(p_fac * pm2[K - 1], p1 + pm2[K - 1])))
+    for k in range(K - 2, -1, -1):
+        p1 = (pe2[k] + bb[k] * pe2[k + 1] + g_rat[k] * pe2[k + 2]) * R3 - g_rat[k] * p1
+        dzn[k] = -dm2[k] * rgas * pt2[k] * torch.exp(capa1 * torch.log(torch.maximum(p_fac * pm2[k], p1 + pm2[k])))
+    pe2 = [pe2[k] + beta * (pp[k] - pe2[k]) for k in range(K + 1)]
+    return w2, pe2, dzn
+
+
 def riem_solver_c(dt, delp, pt, gz, w3, ws, hs, cfg):
     """Riem_Solver_c: returns pef (full pressure) and the new gz; [6,K(+1),..] arrays (all points)"""
     K = delp.shape[1]
@@ -106,7 +168,13 @@ def riem_solver3(dt, delp, pt, zh, w, ws, zs, cfg):
     dm = delp * rgrav
     dz2 = zh[:, 1:] - zh[:, :-1]
     L = lambda a: list(torch.unbind(a, dim=1))
-    w2, pe2, dzn = sim1_solver(dt, L(dm), L(pm2), L(pem), L(w), L(dz2), L(pt), ws[:, 0], rdgas, gama, akap, p_fac)
+    a_imp = cfg.get("a_imp", 1.0)
+    if a_imp > 0.999:
+        w2, pe2, dzn = sim1_solver(dt, L(dm), L(pm2), L(pem), L(w), L(dz2), L(pt), ws[:, 0], rdgas, gama, akap, p_fac)
+    elif a_imp > 0.5:       # model/nh_core_nlm.F90:136-152
+        w2, pe2, dzn = sim_solver(dt, L(dm), L(pm2), L(pem), L(w), L(dz2), L(pt), ws[:, 0], rdgas, gama, akap, p_fac, a_imp)
+    else:
+        raise NotImplementedError("a_imp <= 0.5 (RIM_2D / SIM3 solvers)")
     zl = [None] * (K + 1)
     zl[K] = zs[:, 0] + 0. * dzn[0]
     for k in range(K - 1, -1, -1):

@@ -32,12 +32,12 @@ def column_state(N, K, seed):
     return dict(delp=delp, pt=pt, z=z, w=w, ws=ws, zb=zb), rng, ak, bk
 
 
-def _run_riem(emu, mode):
+def _run_riem(emu, mode, a_imp=1.0):
     N, K = 12, 5
     f, rng, ak, bk = column_state(N, K, 3 + mode)
     dts = 150.0
     g = ograd(N)
-    cfg = dict(NHCFG)
+    cfg = dict(NHCFG); cfg["a_imp"] = a_imp
     if mode == 0:
         f["z"] = f["z"] * cfg["grav"]; f["zb"] = f["zb"] * cfg["grav"]   # Riem_Solver_c works on gz and phis
         def fn(delp, pt, z, w, ws, zb):
@@ -54,7 +54,7 @@ def _run_riem(emu, mode):
     C = (0, N + 1, 0, N + 1) if mode == 0 else (1, N, 1, N)
     outs = {o: C for o in onames}
     h = handle(N, K, emu, ak, bk)
-    p = dict(mode=mode, dts=dts, ptop=cfg["ptop"], akap=cfg["akap"], rdgas=cfg["rdgas"], grav=cfg["grav"])
+    p = dict(mode=mode, dts=dts, ptop=cfg["ptop"], akap=cfg["akap"], rdgas=cfg["rdgas"], grav=cfg["grav"], a_imp=a_imp)
     return check_module(h, "riem", N, K, f, list(f.keys()), outs, fn, p, rng, tol=1e-10, dot_tol=1e-11, pert_scale=1e-3, out_nk=nk)
 
 
@@ -122,12 +122,12 @@ def nh_state(N, K, seed, ak, bk):
     return {k: a.numpy().copy() for k, a in t.items()}, rng
 
 
-def _run_dyn_nh(emu, n_split):
+def _run_dyn_nh(emu, n_split, a_imp=1.0):
     N, K = 12, 4
     ak, bk = eta(K, CFG["ptop"])
     f, rng = nh_state(N, K, 17, ak, bk)
     g = ograd(N)
-    cfg = dict(NHCFG); cfg.update(n_split=n_split, bdt=600.0)
+    cfg = dict(NHCFG); cfg.update(n_split=n_split, bdt=600.0, a_imp=a_imp)
     act = ["u", "v", "pt", "delp", "w", "delz"]
     onames = ["u_n", "v_n", "pt_n", "delp_n", "w_n", "delz_n", "mfx", "cx"]
     key = dict(u_n="u", v_n="v", pt_n="pt", delp_n="delp", w_n="w", delz_n="delz")
@@ -148,6 +148,21 @@ def test_riem_emu(mode):
     print(_run_riem(True, mode))
 
 
+@pytest.mark.parametrize("a_imp", [0.75, 0.999])
+def test_riem3_sim_solver_emu(a_imp):
+    """Riem_Solver3 with the off-centred SIM_solver (reference default a_imp = 0.75, model/fv_arrays_nlm.F90:357)"""
+    print(_run_riem(True, 1, a_imp))
+
+
+def test_riem_c_keeps_sim1_emu():
+    """Riem_Solver_c calls SIM1_solver for every a_imp > 0.5 (model/nh_utils_nlm.F90:366-376)"""
+    print(_run_riem(True, 0, 0.75))
+
+
+def test_dyn_core_nh_sim_solver_emu():
+    print(_run_dyn_nh(True, 2, 0.75))
+
+
 def test_update_dz_c_emu():
     print(_run_dzc(True))
 
@@ -164,6 +179,12 @@ def test_dyn_core_nh_emu():
 @pytest.mark.parametrize("mode", [0, 1])
 def test_riem_gpu(mode):
     _run_riem(False, mode)
+
+
+@pytest.mark.gpu
+def test_riem3_sim_solver_gpu():
+    _run_riem(False, 1, 0.75)
+    _run_dyn_nh(False, 2, 0.75)
 
 
 @pytest.mark.gpu

@@ -14,7 +14,8 @@ from test_fv_dynamics import eta, api_state, ZVIR
 ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"]
 
 
-def make(emu, N=12, K=4, n_split=2, k_split=1, nonhydro=False):
+def make(emu, N=12, K=4, n_split=2, k_split=1, nonhydro=False, extra=None):
+    """extra: fv3lm_config members that the oracle takes under the same name (a_imp ...)"""
     global ACT
     ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"] + (["w", "delz"] if nonhydro else [])
     ptop = CFG["ptop"]
@@ -22,6 +23,7 @@ def make(emu, N=12, K=4, n_split=2, k_split=1, nonhydro=False):
     f, rng = api_state(N, K, 41, ak, bk, nonhydro)
     kw = dict(n_split=n_split, k_split=k_split, dt=900.0, ptop=ptop, d2_bg_k1=CFG["d2_bg_k1"], d2_bg_k2=CFG["d2_bg_k2"],
               kappa=CFG["akap"], cp=CFG["cp_air"], zvir=ZVIR, hydrostatic=0 if nonhydro else 1)
+    kw.update(extra or {})
     h = handle(N, K, emu, ak, bk, **kw)
     C = (slice(None), slice(None), R(1, N), R(1, N))
     comp = {k: np.ascontiguousarray(f[k][C]) for k in ACT}
@@ -29,12 +31,13 @@ def make(emu, N=12, K=4, n_split=2, k_split=1, nonhydro=False):
     h.traj_set(0, comp)
     cfg = dict(CFG); cfg.update(zvir=ZVIR, hydrostatic=not nonhydro, k_split=k_split, n_split=n_split, dt=900.0, hord_tr=2,
                                 rdgas=8314.47 / 28.965, grav=9.80665, p_fac=0.05)
+    cfg.update(extra or {})
     return h, f, comp, rng, cfg, ak, bk
 
 
-def _run(emu, nonhydro=False):
+def _run(emu, nonhydro=False, extra=None):
     N, K = 12, 4
-    h, f, comp, rng, cfg, ak, bk = make(emu, N, K, nonhydro=nonhydro)
+    h, f, comp, rng, cfg, ak, bk = make(emu, N, K, nonhydro=nonhydro, extra=extra)
     tol = 2e-9 if nonhydro else 2e-10
     g = ograd(N)
     # ---- step_nl against the oracle
@@ -84,6 +87,11 @@ def test_step_api_emu():
 
 def test_step_api_nonhydro_emu():
     print(_run(True, nonhydro=True))
+
+
+def test_step_api_sim_solver_emu():
+    """a_imp = 0.75 (the reference's default, model/fv_arrays_nlm.F90:357) through fv3lm_config: Riem_Solver3 uses SIM_solver"""
+    print(_run(True, nonhydro=True, extra=dict(a_imp=0.75)))
 
 
 def test_program_stats_emu():
