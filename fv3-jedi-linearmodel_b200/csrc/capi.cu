@@ -36,7 +36,7 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
   if (cfg->ntiles != 6 || cfg->npx != cfg->npy || cfg->ng != 3) throw std::runtime_error("fv3lm_create: need 6 square tiles and ng = 3");
   if (cfg->npz > 95 || cfg->npz < 1) throw std::runtime_error("fv3lm_create: npz must be in 1..95");
   for (int ho : {cfg->hord_mt, cfg->hord_vt, cfg->hord_tm, cfg->hord_dp, cfg->hord_tr})
-    if (ho != 1 && ho != 2) throw std::runtime_error("fv3lm_create: hord_* must be 1 or 2 (the linear schemes the TL/AD implement, tp_core_tlm.F90:2431-2466)");
+    if (ho != 1 && ho != 2 && ho != 333) throw std::runtime_error("fv3lm_create: hord_* must be 1, 2 or 333 (the linear schemes the TL/AD implement, tp_core_tlm.F90:2431-2488)");
   if (cfg->nq != 4) throw std::runtime_error("fv3lm_create: nq must be 4 (qv, ql, qi, o3)");
   if (cfg->n_split < 1 || cfg->k_split < 1 || !(cfg->dt > 0.0)) throw std::runtime_error("fv3lm_create: n_split, k_split and dt must be positive");
   if (cfg->nord < 0 || cfg->nord > 3) throw std::runtime_error("fv3lm_create: nord must be in 0..3");

@@ -139,10 +139,11 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
 }
 
 void fill_dsw_params(DswParams& d, const ModuleParams& prm, int K) {
-  auto LO = [&](const char* base, int dflt) {
+  auto LO = [&](const char* base, int dflt, bool is_hord = false) {
+    auto enc = [&](int v) { return is_hord ? enc_hord(v) : v; };
     LevOrd o; int v = prm.geti(base, dflt);
-    for (int k = 0; k < 128; k++) o.v[k] = (signed char)v;
-    for (int k = 0; k < K; k++) { std::string key = std::string(base) + "@" + std::to_string(k); if (prm.v.count(key)) o.v[k] = (signed char)prm.geti(key, v); }
+    for (int k = 0; k < 128; k++) o.v[k] = (signed char)enc(v);
+    for (int k = 0; k < K; k++) { std::string key = std::string(base) + "@" + std::to_string(k); if (prm.v.count(key)) o.v[k] = (signed char)enc(prm.geti(key, v)); }
     return o;
   };
   auto LD = [&](const char* base, double dflt) {
@@ -151,7 +152,7 @@ void fill_dsw_params(DswParams& d, const ModuleParams& prm, int K) {
     for (int k = 0; k < K; k++) { std::string key = std::string(base) + "@" + std::to_string(k); if (prm.v.count(key)) o.v[k] = prm.get(key, v); }
     return o;
   };
-  d.hord_mt = LO("hord_mt", 2); d.hord_vt = LO("hord_vt", 2); d.hord_tm = LO("hord_tm", 2); d.hord_dp = LO("hord_dp", 2);
+  d.hord_mt = LO("hord_mt", 2, true); d.hord_vt = LO("hord_vt", 2, true); d.hord_tm = LO("hord_tm", 2, true); d.hord_dp = LO("hord_dp", 2, true);
   d.nord = LO("nord", 1); d.nord_v = LO("nord_v", 1); d.nord_w = LO("nord_w", 1); d.nord_t = LO("nord_t", 1);
   d.d2_bg = LD("d2_bg", 0.015); d.damp_v = LD("damp_v", 0.0005); d.damp_w = LD("damp_w", 0.0005); d.damp_t = LD("damp_t", 0.0005);
   d.dddmp = prm.get("dddmp", 0.2); d.d4_bg = prm.get("d4_bg", 0.15); d.dt = prm.get("dt", 450.0);

@@ -30,8 +30,8 @@ void level_params(const DynConfig& c, int K, DswParams& d) {
       }
     }
     const bool sp = k <= c.n_sponge_ord;
-    d.hord_mt.v[k - 1] = sp ? 1 : c.hord_mt; d.hord_vt.v[k - 1] = sp ? 1 : c.hord_vt;
-    d.hord_tm.v[k - 1] = sp ? 1 : c.hord_tm; d.hord_dp.v[k - 1] = sp ? 1 : c.hord_dp;
+    d.hord_mt.v[k - 1] = sp ? 1 : enc_hord(c.hord_mt); d.hord_vt.v[k - 1] = sp ? 1 : enc_hord(c.hord_vt);
+    d.hord_tm.v[k - 1] = sp ? 1 : enc_hord(c.hord_tm); d.hord_dp.v[k - 1] = sp ? 1 : enc_hord(c.hord_dp);
     d.nord.v[k - 1] = nord_k; d.nord_v.v[k - 1] = nord_v; d.nord_w.v[k - 1] = nord_w; d.nord_t.v[k - 1] = nord_t;
     d.d2_bg.v[k - 1] = d2; d.damp_v.v[k - 1] = damp_vt; d.damp_w.v[k - 1] = damp_w; d.damp_t.v[k - 1] = damp_t;
   }

@@ -63,7 +63,7 @@ std::vector<int> build_tracer_2d(Program& P, Mosaic& mo, std::vector<int> q, int
   P.add<S_trc_fx>("trc_fx", {0}, {cx, cy}, {xfx, yfx}, K);
   P.add<S_ra>("trc_ra", {0}, {xfx, yfx}, {ra_x, ra_y}, K);
   P.add<S_trc_dp2>("trc_dp2", {0}, {dp1, mfx, mfy}, {dp2}, K);
-  LevOrd ho; for (int k = 0; k < 128; k++) ho.v[k] = (signed char)hord_tr;
+  LevOrd ho; for (int k = 0; k < 128; k++) ho.v[k] = (signed char)enc_hord(hord_tr);
   std::vector<int> out;
   for (size_t n = 0; n < q.size(); n++) {
     TpOut f = build_fv_tp_2d(P, mo, q[n], cx, cy, xfx, yfx, ra_x, ra_y, mfx, mfy, ho, K, nm("tp_q" + std::to_string(n)));

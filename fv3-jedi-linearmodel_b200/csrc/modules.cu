@@ -5,7 +5,7 @@ namespace fv3lm {
 
 static LevOrd lev_ord(int K, int ord, int n_sponge, int ord_sponge) {
   LevOrd o;
-  for (int k = 0; k < 128; k++) o.v[k] = (signed char)((k < n_sponge) ? ord_sponge : ord);
+  for (int k = 0; k < 128; k++) o.v[k] = (signed char)enc_hord((k < n_sponge) ? ord_sponge : ord);
   (void)K;
   return o;
 }

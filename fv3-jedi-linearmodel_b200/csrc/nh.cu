@@ -96,7 +96,7 @@ std::pair<int, int> build_update_dz_d(Program& P, Mosaic& mo, const LevD& dp0, c
   add_col<S_edge_profile>(P, "edge_profile_yfx", {dp0, K, is - ng, ie + ng, js, je + 1}, {yfx}, {yfxa});
   int ra_x = P.val(nm("ra_x"), K + 1), ra_y = P.val(nm("ra_y"), K + 1);
   P.add<S_ra>("dzd_ra", {0}, {xfxa, yfxa}, {ra_x, ra_y}, K + 1);
-  LevOrd ho; for (int k = 0; k < 128; k++) ho.v[k] = (signed char)hord_tm;
+  LevOrd ho; for (int k = 0; k < 128; k++) ho.v[k] = (signed char)enc_hord(hord_tm);
   TpOut f = build_fv_tp_2d(P, mo, zh, crxa, crya, xfxa, yfxa, ra_x, ra_y, -1, -1, ho, K + 1, tag + ".tp_zh");
   // del6_vt_flux(ndif(k), damp(k)) with ndif = nord_v, damp = damp_vt; level K+1 repeats level K (:220-221)
   LevOrd nv; LevD dm, on; bool any = false;

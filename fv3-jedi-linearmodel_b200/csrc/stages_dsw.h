@@ -332,6 +332,13 @@ template <int DIR> struct S_tpuv {
     const int dc = pos ? -1 : 0;                 // upwind cell offset
     T uc = Q(x, dc);
     if (ord == 1) { x.out(0, uc); return; }
+    if (ord == ORD333) {   // sw_core_tlm.F90:7332-7356 (xtp_u), :7552-7577 (ytp_v): no cube-edge special cases
+      double rd3 = DIR == 0 ? x.M(x.m.rdx, dc, 0) : x.M(x.m.rdy, 0, dc);
+      T cf = c * rd3, um1 = Q(x, -1), u0 = Q(x, 0);
+      if (pos) { T um2 = Q(x, -2); x.out(0, (2.0 * u0 + 5.0 * um1 - um2) / 6.0 - 0.5 * cf * (u0 - um1) + cf * cf / 6.0 * (u0 - 2.0 * um1 + um2)); }
+      else { T u1 = Q(x, 1); x.out(0, (2.0 * um1 + 5.0 * u0 - u1) / 6.0 - 0.5 * cf * (u0 - um1) + cf * cf / 6.0 * (u1 - 2.0 * u0 + um1)); }
+      return;
+    }
     const int ic = (DIR == 0 ? x.i : x.j) + dc;  // upwind cell index along the sweep
     const int np = DIR == 0 ? g.npx : g.npy;
     const int jt = DIR == 0 ? x.j : x.i;         // index across the sweep

@@ -1,8 +1,8 @@
 // tp_core: 1-D PPM fluxes and the Lin-Rood 2-D flux-form transport operator fv_tp_2d.
 // Reference: model_tlmadm/tp_core_tlm.F90  FV_TP_2D_TLM :2123, XPPM_TLM :2328, YPPM_TLM :2496,
 // COPY_CORNERS_TLM :2843 (primal model/tp_core_nlm.F90:78-289, 291-420).  Only the linear
-// orders the TL/AD implement are provided: iord = 1 (upwind) and 2 (unlimited PPM)
-// (tp_core_tlm.F90:2431-2466).
+// orders the TL/AD implement are provided: iord = 1 (upwind), 2 (unlimited PPM) and 333 (third-order
+// linear, Holdaway & Kent 2015) (tp_core_tlm.F90:2431-2488).
 #pragma once
 #include "engine.h"
 #include "mosaic.h"
@@ -10,6 +10,13 @@
 namespace fv3lm {
 
 struct LevOrd { signed char v[128]; };   // per-level scheme order (sponge layers differ)
+// hord = 333 (third-order linear scheme, tp_core_tlm.F90:2467-2488) is stored as ORD333 in a LevOrd
+constexpr int ORD333 = 3;
+inline int enc_hord(int hord) {
+  if (hord == 1 || hord == 2) return hord;
+  if (hord == 333) return ORD333;
+  throw std::runtime_error("hord must be 1, 2 or 333 (the linear schemes the TL/AD implement, tp_core_tlm.F90:2431-2488)");
+}
 
 namespace tp {
 constexpr double p1 = 7.0 / 12.0, p2 = -1.0 / 12.0;
@@ -44,6 +51,16 @@ template <int DIR, class X> DEV typename X::T edge_al(const X& x, int f, int d) 
 template <int DIR, class X> DEV typename X::T ppm_flux(const X& x, int fq, typename X::T c, int ord) {
   using T = typename X::T;
   if (ord == 1) return val(c) > 0.0 ? Q<DIR>(x, fq, -1) : Q<DIR>(x, fq, 0);
+  if (ord == ORD333) {
+    // perfectly linear third-order scheme, no cube-edge special cases (tp_core_tlm.F90:2467-2488, :2638-2660)
+    T qm1 = Q<DIR>(x, fq, -1), q0 = Q<DIR>(x, fq, 0);
+    if (val(c) > 0.0) {
+      T qm2 = Q<DIR>(x, fq, -2);
+      return (2.0 * q0 + 5.0 * qm1 - qm2) / 6.0 - 0.5 * c * (q0 - qm1) + c * c / 6.0 * (q0 - 2.0 * qm1 + qm2);
+    }
+    T q1 = Q<DIR>(x, fq, 1);
+    return (2.0 * qm1 + 5.0 * q0 - q1) / 6.0 - 0.5 * c * (q0 - qm1) + c * c / 6.0 * (q1 - 2.0 * q0 + qm1);
+  }
   {
     // regular faces (all three edge values use the uniform weights): straight-line code, no edge tests
     const int ia = DIR == 0 ? x.i : x.j, np = DIR == 0 ? x.g.npx : x.g.npy;
@@ -117,7 +134,7 @@ template <int DIR> struct S_ppm {
     // inside the flux rectangle and inside the array -- true for every cell away from the cube edges
     const int f0 = DIR == 0 ? p.i0 : p.j0, f1 = DIR == 0 ? p.i1 : p.j1;
     const bool cross_ok = DIR == 0 ? (x.jl >= p.j0 && x.jl <= p.j1) : (x.il >= p.i0 && x.il <= p.i1);
-    if (ord != 1 && cross_ok && pos - 3 >= 3 && pos + 4 <= np - 2 && loc - 2 >= f0 && loc + 3 <= f1 && arr - 2 >= 0 && arr + 3 < len) {
+    if (ord == 2 && cross_ok && pos - 3 >= 3 && pos + 4 <= np - 2 && loc - 2 >= f0 && loc + 3 <= f1 && arr - 2 >= 0 && arr + 3 < len) {
       const int stride = DIR == 0 ? 1 : kn.g.pitch;
       const int oc = x.off(kn.in.nk[1], 0, 0, 0), oa = x.off(nko, 0, 0, 0);
       const double* cp = kn.in.p[1]; const double* ap = kn.outad.p[0];
@@ -147,7 +164,11 @@ template <int DIR> struct S_ppm {
         const int d = -s;
         double coef;
         if (ord == 1) coef = (c > 0.0) ? (d == -1 ? 1.0 : 0.0) : (d == 0 ? 1.0 : 0.0);
-        else if (c > 0.0) {
+        else if (ord == ORD333) {
+          const double c2 = c * c / 6.0;
+          if (c > 0.0) coef = d == 0 ? 2.0 / 6.0 - 0.5 * c + c2 : d == -1 ? 5.0 / 6.0 + 0.5 * c - 2.0 * c2 : d == -2 ? -1.0 / 6.0 + c2 : 0.0;
+          else coef = d == -1 ? 2.0 / 6.0 + 0.5 * c + c2 : d == 0 ? 5.0 / 6.0 - 0.5 * c - 2.0 * c2 : d == 1 ? -1.0 / 6.0 + c2 : 0.0;
+        } else if (c > 0.0) {
           const double dqt = 1.0 + (1.0 - c) * (2.0 * c - 1.0), dal0 = (1.0 - c) * (1.0 - c), dalm = -(1.0 - c) * c;
           coef = (d == -1 ? dqt : 0.0) + dal0 * al_w(x, 0, d + 2) + dalm * al_w(x, -1, d + 3);
         } else {
@@ -164,6 +185,12 @@ template <int DIR> struct S_ppm {
         const double a = kn.outad.p[0][x.off(nko, 0, 0, 0)];
         if (a != 0.0) {
           const double c = x.in(1);
+          if (ord == ORD333) {
+            const double qm1 = tp::Q<DIR>(x, 0, -1), q0 = tp::Q<DIR>(x, 0, 0);
+            const double curv = c > 0.0 ? q0 - 2.0 * qm1 + tp::Q<DIR>(x, 0, -2) : tp::Q<DIR>(x, 0, 1) - 2.0 * q0 + qm1;
+            acc[1] += (-0.5 * (q0 - qm1) + c / 3.0 * curv) * a;
+            return;
+          }
           double al0, qt, al2;      // al2: the upwind-side second edge value (alm for c > 0, alp otherwise)
           if (pos >= 4 && pos <= np - 3) {
             const double qm2 = tp::Q<DIR>(x, 0, -2), qm1 = tp::Q<DIR>(x, 0, -1), q0 = tp::Q<DIR>(x, 0, 0), q1 = tp::Q<DIR>(x, 0, 1);

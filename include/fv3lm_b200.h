@@ -34,7 +34,7 @@ typedef struct fv3lm_config {
   int hydrostatic;        /* 1 = hydrostatic                                                   */
   int n_split, k_split;   /* acoustic / remap sub-cycling                                      */
   int nq;                 /* number of tracers (4: qv ql qi o3)                                */
-  int hord_mt, hord_vt, hord_tm, hord_dp, hord_tr;   /* must be 1 or 2 (linear schemes)       */
+  int hord_mt, hord_vt, hord_tm, hord_dp, hord_tr;   /* 1, 2 or 333 (the linear schemes)      */
   int n_sponge;           /* layers using first-order (hord_*_ks = 1) transport                */
   int nord;               /* divergence damping order                                          */
   double dt;              /* model time step [s]                                               */

@@ -125,7 +125,7 @@ def courant_fluxes(ut, vt, g, dt):
 
 
 def xtp_u(c, u, g, iord):
-    """sw_core_nlm.F90:1970-2309 (iord 1, 2).  flux(is:ie+1, js:je+1); u is the D-grid u.
+    """sw_core_nlm.F90:1970-2309 (iord 1, 2) and sw_core_tlm.F90:7332-7356 (iord 333).  flux(is:ie+1, js:je+1); u is the D-grid u.
     iord: int or per-level list."""
     N, npx, npy = g.N, g.npx, g.npy
     is_, ie, js, je = 1, N, 1, N
@@ -172,12 +172,11 @@ def xtp_u(c, u, g, iord):
     f_pos = um + (1. - cfl_p) * (br[..., is_ - 1: ie + 1] - cfl_p * b0[..., is_ - 1: ie + 1])
     f_neg = up_ + (1. + cfl_n) * (bl[..., is_: ie + 2] + cfl_n * b0[..., is_: ie + 2])
     f2 = torch.where(cc > 0., f_pos, f_neg)
-    if isinstance(iord, int):
-        fl = f1 if iord == 1 else f2
-    else:
-        sel = torch.tensor([o == 1 for o in iord], dtype=torch.bool).view(1, -1, 1, 1)
-        fl = torch.where(sel, f1, f2)
-    return put(Z(u), is_, ie + 1, j0, j1, fl)
+    # iord = 333 (sw_core_tlm.F90:7332-7356): third-order linear, Courant number c * rdx of the upwind cell
+    umm = S(u, is_ - 2, ie - 1, j0, j1); upp = S(u, is_ + 1, ie + 2, j0, j1)
+    f3 = torch.where(cc > 0., (2.0 * up_ + 5.0 * um - umm) / 6.0 - 0.5 * cfl_p * (up_ - um) + cfl_p * cfl_p / 6.0 * (up_ - 2.0 * um + umm),
+                     (2.0 * um + 5.0 * up_ - upp) / 6.0 - 0.5 * cfl_n * (up_ - um) + cfl_n * cfl_n / 6.0 * (upp - 2.0 * up_ + um))
+    return put(Z(u), is_, ie + 1, j0, j1, tp.select_ord(iord, {1: f1, 2: f2, 333: f3}))
 
 
 def ytp_v(c, v, g, jord):

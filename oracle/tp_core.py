@@ -8,7 +8,7 @@ torch float64 from the reference's TL-module primal
 The code is differentiable: the TL oracle is torch.func.jvp of these functions and the
 AD oracle is torch.func.vjp -- exactly what Tapenade's tangent / reverse modes compute
 for the same primal.  Only the linear orders the reference TL/AD
-implement are restated (iord = 1, 2; tp_core_tlm.F90:2431-2466).
+implement are restated (iord = 1, 2, 333; tp_core_tlm.F90:2431-2488).
 
 parity unpinned: the reference holds no test vectors for this routine.
 
@@ -89,13 +89,24 @@ def xppm(q, c, iord, g, j0, j1):
     f_pos = qm + (1. - cc) * (al_0 - qm - cc * (al_m + al_0 - (qm + qm)))
     f_neg = qp + (1. + cc) * (al_0 - qp + cc * (al_0 + al_p - (qp + qp)))
     f2 = torch.where(cc > 0., f_pos, f_neg)
-    if isinstance(iord, int):
-        fl = up if iord == 1 else f2
-    else:
-        sel = torch.tensor([o == 1 for o in iord], dtype=torch.bool).view(1, -1, 1, 1)
-        fl = torch.where(sel, up, f2)
-    out[..., R(j0, j1), R(is_, ie + 1)] = fl
+    # iord = 333: perfectly linear third-order scheme, no cube-edge special cases (tp_core_tlm.F90:2467-2488)
+    qmm = q[..., R(j0, j1), R(is_ - 2, ie - 1)]
+    qpp = q[..., R(j0, j1), R(is_ + 1, ie + 2)]
+    f3 = torch.where(cc > 0., (2.0 * qp + 5.0 * qm - qmm) / 6.0 - 0.5 * cc * (qp - qm) + cc * cc / 6.0 * (qp - 2.0 * qm + qmm),
+                     (2.0 * qm + 5.0 * qp - qpp) / 6.0 - 0.5 * cc * (qp - qm) + cc * cc / 6.0 * (qpp - 2.0 * qp + qm))
+    out[..., R(j0, j1), R(is_, ie + 1)] = select_ord(iord, {1: up, 2: f2, 333: f3})
     return out
+
+
+def select_ord(iord, table):
+    """iord: python int or per-level list (len K); table: order -> tensor [6, K, ...]"""
+    if isinstance(iord, int):
+        return table[iord]
+    fl = None
+    for o in sorted(set(iord)):
+        sel = torch.tensor([x == o for x in iord], dtype=torch.bool).view(1, -1, 1, 1)
+        fl = table[o] if fl is None else torch.where(sel, table[o], fl)
+    return fl
 
 
 def _T(a):

@@ -23,9 +23,9 @@ def dsw_inputs(N, K, seed):
     return f, rng
 
 
-def level_params(K, sponge):
+def level_params(K, sponge, hord=2):
     """per-level switches like dyn_core_nlm.F90:579-625 with a 1-layer sponge at k=0"""
-    p = dict(hord_mt=[2] * K, hord_vt=[2] * K, hord_tm=[2] * K, hord_dp=[2] * K, nord=[1] * K, nord_v=[1] * K,
+    p = dict(hord_mt=[hord] * K, hord_vt=[hord] * K, hord_tm=[hord] * K, hord_dp=[hord] * K, nord=[1] * K, nord_v=[1] * K,
              nord_w=[1] * K, nord_t=[1] * K, d2_bg=[0.015] * K, damp_v=[0.0005] * K, damp_w=[0.0005] * K, damp_t=[0.0005] * K)
     if sponge:
         for n in ("hord_mt", "hord_vt", "hord_tm", "hord_dp"):
@@ -50,12 +50,12 @@ def flat_params(p, K):
     return out
 
 
-def _run_dsw(emu, hydrostatic, sponge):
+def _run_dsw(emu, hydrostatic, sponge, hord=2):
     N, K = 12, 2
     f, rng = dsw_inputs(N, K, 11)
     g = ograd(N)
     dt = 450.0
-    prm = level_params(K, sponge)
+    prm = level_params(K, sponge, hord)
     prm.update(dddmp=0.2, d4_bg=0.15, hydrostatic=hydrostatic)
     names = list(f.keys())
     act = [n for n in names if not (hydrostatic and n == "w")]
@@ -92,6 +92,16 @@ def test_a2b_ord4_emu():
 @pytest.mark.parametrize("hydrostatic,sponge", [(True, False), (False, True)])
 def test_d_sw_emu(hydrostatic, sponge):
     _run_dsw(True, hydrostatic, sponge)
+
+
+def test_d_sw_hord333_emu():
+    """third-order linear scheme (hord = 333) in fv_tp_2d and xtp_u / ytp_v, first-order sponge layer on top"""
+    _run_dsw(True, False, True, 333)
+
+
+@pytest.mark.gpu
+def test_d_sw_hord333_gpu():
+    _run_dsw(False, False, True, 333)
 
 
 @pytest.mark.gpu

@@ -94,6 +94,11 @@ def test_step_api_sim_solver_emu():
     print(_run(True, nonhydro=True, extra=dict(a_imp=0.75)))
 
 
+def test_step_api_hord333_emu():
+    """hord_* = 333 (third-order linear scheme of the TL/AD, tp_core_tlm.F90:2467) for every transport of a hydrostatic step"""
+    print(_run(True, extra=dict(hord_mt=333, hord_vt=333, hord_tm=333, hord_dp=333, hord_tr=333)))
+
+
 def test_program_stats_emu():
     h, *_ = make(True)
     s = h.program_stats("step")

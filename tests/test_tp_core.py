@@ -73,12 +73,12 @@ def _run(emu, hord):
     assert abs(lhs - rhs) <= 1e-13 * max(abs(lhs), abs(rhs))
 
 
-@pytest.mark.parametrize("hord", [1, 2])
+@pytest.mark.parametrize("hord", [1, 2, 333])
 def test_fv_tp_2d_emu(hord):
     _run(True, hord)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("hord", [1, 2])
+@pytest.mark.parametrize("hord", [1, 2, 333])
 def test_fv_tp_2d_gpu(hord):
     _run(False, hord)
