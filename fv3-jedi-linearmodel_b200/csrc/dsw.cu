@@ -135,6 +135,16 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
   }
   o.u = P.val(nm("u"), nk); o.v = P.val(nm("v"), nk);
   P.add<S_duv>("duv", {vd_on}, {u, v, ke, vd, fv.fx, fv.fy, ut3, vt3}, {o.u, o.v}, nk);
+  if (prm.heat) {
+    // the reference reads the del6_vt_flux output whether or not the vorticity damping ran (:1496-1506): without it the arrays
+    // hold unrelated winds, so that combination is refused
+    for (int k = 0; k < nk; k++)
+      if (prm.d_con.v[k] > 1.e-5 && vd_on.v[k] == 0.0) throw std::runtime_error("d_sw: d_con > 0 needs the vorticity damping (do_vort_damp, vtdm4 > 1e-5) on every level outside the sponge");
+    int ubh = P.val(nm("ubh"), nk), fyh = P.val(nm("fyh"), nk), vbh = P.val(nm("vbh"), nk), fxh = P.val(nm("fxh"), nk);
+    P.add<S_dheat_edge>("dheat_edge", {0}, {u, v, ke, vd, fv.fx, fv.fy, ut3, vt3}, {ubh, fyh, vbh, fxh}, nk);
+    o.heat = P.val(nm("heat_s"), nk);
+    P.add<S_dheat>("dheat", {nh, dw_on, prm.d_con}, {o.delp, ubh, fyh, vbh, fxh, w, fx2w, fy2w}, {o.heat}, nk);
+  }
   return o;
 }
 
@@ -155,6 +165,8 @@ void fill_dsw_params(DswParams& d, const ModuleParams& prm, int K) {
   d.hord_mt = LO("hord_mt", 2, true); d.hord_vt = LO("hord_vt", 2, true); d.hord_tm = LO("hord_tm", 2, true); d.hord_dp = LO("hord_dp", 2, true);
   d.nord = LO("nord", 1); d.nord_v = LO("nord_v", 1); d.nord_w = LO("nord_w", 1); d.nord_t = LO("nord_t", 1);
   d.d2_bg = LD("d2_bg", 0.015); d.damp_v = LD("damp_v", 0.0005); d.damp_w = LD("damp_w", 0.0005); d.damp_t = LD("damp_t", 0.0005);
+  d.d_con = LD("d_con", 0.0);
+  d.heat = false; for (int k = 0; k < K; k++) if (d.d_con.v[k] > 1.e-5) d.heat = true;
   d.dddmp = prm.get("dddmp", 0.2); d.d4_bg = prm.get("d4_bg", 0.15); d.dt = prm.get("dt", 450.0);
   d.hydrostatic = prm.geti("hydrostatic", 1) != 0;
 }
@@ -167,6 +179,7 @@ void mod_d_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
   DswOut o = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, ua, va, divg_d, d, K, "dsw");
   io.out(P, "delp_n", o.delp); io.out(P, "pt_n", o.pt); io.out(P, "u_n", o.u); io.out(P, "v_n", o.v); io.out(P, "w_n", o.w);
   io.out(P, "fx", o.fx); io.out(P, "fy", o.fy); io.out(P, "crx", o.crx); io.out(P, "cry", o.cry); io.out(P, "xfx", o.xfx); io.out(P, "yfx", o.yfx);
+  if (o.heat >= 0) io.out(P, "heat", o.heat);
 }
 
 }  // namespace fv3lm

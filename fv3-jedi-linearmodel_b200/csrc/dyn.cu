@@ -10,32 +10,73 @@ namespace fv3lm {
 // TL module's first-order sponge transport (dyn_core_tlm.F90:740-926)
 void level_params(const DynConfig& c, int K, DswParams& d) {
   for (int k = 0; k < 128; k++) { d.hord_mt.v[k] = d.hord_vt.v[k] = d.hord_tm.v[k] = d.hord_dp.v[k] = 2; d.nord.v[k] = d.nord_v.v[k] = d.nord_w.v[k] = d.nord_t.v[k] = 0; }
-  for (int k = 0; k < 96; k++) d.d2_bg.v[k] = d.damp_v.v[k] = d.damp_w.v[k] = d.damp_t.v[k] = 0.0;
+  for (int k = 0; k < 96; k++) d.d2_bg.v[k] = d.damp_v.v[k] = d.damp_w.v[k] = d.damp_t.v[k] = d.d_con.v[k] = 0.0;
+  d.heat = c.d_con > 1.e-5;
   for (int k = 1; k <= K; k++) {
     int nord_k = c.nord, nord_v = std::min(2, c.nord);
     double d2 = std::min(0.20, c.d2_bg);
     double damp_vt = c.do_vort_damp ? c.vtdm4 : 0.0;
     int nord_w = nord_v, nord_t = nord_v; double damp_w = damp_vt, damp_t = damp_vt;
+    double d_con_k = c.d_con;
     if (K == 1 || c.n_sponge < 0) {
       d2 = c.d2_bg;
     } else {
       if (k == 1) {
         nord_k = 0; d2 = std::max(0.01, std::max(c.d2_bg, c.d2_bg_k1)); nord_w = 0; damp_w = d2;
         if (c.do_vort_damp) { nord_v = 0; damp_vt = 0.5 * d2; }
+        d_con_k = 0.0;
       } else if (k == std::max(2, c.n_sponge - 1) && c.d2_bg_k2 > 0.01) {
         nord_k = 0; d2 = std::max(c.d2_bg, c.d2_bg_k2); nord_w = 0; damp_w = d2;
         if (c.do_vort_damp) { nord_v = 0; damp_vt = 0.5 * d2; }
+        d_con_k = 0.0;
       } else if (k == std::max(3, c.n_sponge) && c.d2_bg_k2 > 0.05) {
         nord_k = 0; d2 = std::max(c.d2_bg, 0.2 * c.d2_bg_k2); nord_w = 0; damp_w = d2;
+        d_con_k = 0.0;
       }
     }
     const bool sp = k <= c.n_sponge_ord;
     d.hord_mt.v[k - 1] = sp ? 1 : enc_hord(c.hord_mt); d.hord_vt.v[k - 1] = sp ? 1 : enc_hord(c.hord_vt);
     d.hord_tm.v[k - 1] = sp ? 1 : enc_hord(c.hord_tm); d.hord_dp.v[k - 1] = sp ? 1 : enc_hord(c.hord_dp);
     d.nord.v[k - 1] = nord_k; d.nord_v.v[k - 1] = nord_v; d.nord_w.v[k - 1] = nord_w; d.nord_t.v[k - 1] = nord_t;
+    d.d_con.v[k - 1] = d.heat ? d_con_k : 0.0;
     d.d2_bg.v[k - 1] = d2; d.damp_v.v[k - 1] = damp_vt; d.damp_w.v[k - 1] = damp_w; d.damp_t.v[k - 1] = damp_t;
   }
   d.dddmp = c.dddmp; d.d4_bg = c.d4_bg; d.hydrostatic = c.hydrostatic;
+}
+
+int build_del2_cubed(Program& P, Mosaic& mo, int q, double cd, int nmax, int nk, const std::string& tag) {
+  const int ntimes = std::min(3, nmax);
+  add_patch(P, "halo_d2c", &mo.h_center, {q});
+  for (int n = 1; n <= ntimes; n++) {
+    const int nt = ntimes - n;
+    const std::string tg = tag + ".n" + std::to_string(n);
+    LevOrd lv; for (int k = 0; k < 128; k++) lv.v[k] = (signed char)nt;
+    int qa = P.val(tg + ".qa", nk), fx = P.val(tg + ".fx", nk), fy = P.val(tg + ".fy", nk), qn = P.val(tg + ".q", nk);
+    P.add<S_d2c_corner>("d2c_corner", {nt}, {q}, {qa}, nk);
+    if (nt > 0) add_patch(P, "d2c_cc1", &mo.cc1, {qa});
+    P.add<S_del_flux<0>>("d2c_fx", {lv, 0}, {qa, qa}, {fx}, nk);     // fx = del6_v (q(i-1) - q(i)) on the domain widened by nt
+    if (nt > 0) add_patch(P, "d2c_cc2", &mo.cc2, {qa});
+    P.add<S_del_flux<1>>("d2c_fy", {lv, 0}, {qa, qa}, {fy}, nk);
+    P.add<S_d2c_upd>("d2c_upd", {nt, cd}, {qa, fx, fy}, {qn}, nk);
+    q = qn;
+  }
+  return q;
+}
+
+int build_heat_update(Program& P, Mosaic& mo, const DynConfig& c, int heat, int pt, int delp, int aux, const std::string& tag) {
+  const int K = P.dv->g.K;
+  // n_con (model/dyn_core_nlm.F90:272-285; convert_ke = F)
+  int n_con;
+  if (c.vtdm4 > 1.e-4) n_con = K;
+  else if (c.d2_bg_k1 < 1.e-3) n_con = 0;
+  else n_con = c.d2_bg_k2 < 1.e-3 ? 1 : 2;
+  if (n_con == 0) return pt;
+  const int nf_ke = std::min(3, c.nord + 1);
+  int hs = build_del2_cubed(P, mo, heat, 0.20 * P.dv->m.da_min, nf_ke, K, tag + ".d2c");
+  int ptn = P.val(tag + ".pt_heat", K);
+  P.add<S_heat_pt>("heat_pt", {std::min(n_con, K), c.hydrostatic ? 1 : 0, c.cp_air, c.cp_air - c.rdgas, fabs(c.bdt * c.delt_max), -c.rdgas / c.grav, c.akap / (1.0 - c.akap)},
+                   {pt, hs, delp, aux}, {ptn}, K);
+  return ptn;
 }
 
 DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, const std::string& tag) {
@@ -47,7 +88,7 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, co
   DswParams dp; level_params(c, K, dp); dp.dt = dt;
   DynOut o;
   int u = s.u, v = s.v, pt = s.pt, delp = s.delp, w = s.w;
-  int mfx = -1, mfy = -1, cx = -1, cy = -1;
+  int mfx = -1, mfy = -1, cx = -1, cy = -1, heat = -1;
   for (int it = 1; it <= c.n_split; it++) {
     const std::string tg = tag + ".it" + std::to_string(it);
     P.mark_segment();
@@ -69,6 +110,10 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, co
       P.add<S_add2>("acc_cy", {isd, ied, js, je + 1}, {cy, ds.cry}, {d}, K);
       mfx = a; mfy = b; cx = cc; cy = d;
     }
+    if (ds.heat >= 0) {   // heat_source += heat_s (:685-692)
+      if (heat < 0) heat = ds.heat;
+      else { int hn = P.val(tg + ".heat", K); P.add<S_add2>("acc_heat", {is, ie, js, je}, {heat, ds.heat}, {hn}, K); heat = hn; }
+    }
     delp = ds.delp; pt = ds.pt;
     add_patch(P, "halo_delp", &mo.h_center, {delp});
     add_patch(P, "halo_pt", &mo.h_center, {pt});
@@ -82,6 +127,7 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, co
     if (it == c.n_split) add_patch(P, "get_boundary_uv", &mo.gb_dgrid, {u, v});
     else add_patch(P, "halo_uv", &mo.h_dgrid, {u, v});
   }
+  if (heat >= 0) pt = build_heat_update(P, mo, c, heat, pt, delp, o.pkz, tag + ".heat");
   o.u = u; o.v = v; o.pt = pt; o.delp = delp; o.w = w; o.mfx = mfx; o.mfy = mfy; o.cx = cx; o.cy = cy;
   return o;
 }
@@ -105,6 +151,20 @@ void dyn_config_from(DynConfig& c, const ModuleParams& prm) {
   // 0 in the config = "not set": the library defaults (fully implicit SIM1 solver, p_fac = 0.05)
   c.a_imp = prm.get("a_imp", f->a_imp != 0.0 ? f->a_imp : 1.0);
   c.p_fac = prm.get("p_fac", f->p_fac != 0.0 ? f->p_fac : 0.05);
+  c.d_con = prm.get("d_con", f->d_con);
+}
+
+void mod_del2_cubed(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
+  const int K = P.dv->g.K;
+  int q = io.in(P, "q", K);
+  io.out(P, "q_n", build_del2_cubed(P, mo, q, prm.get("cd", 0.20) * P.dv->m.da_min, prm.geti("nmax", 3), K, "d2c"));
+}
+
+void mod_heat_update(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
+  const int K = P.dv->g.K;
+  DynConfig c; dyn_config_from(c, prm);
+  int heat = io.in(P, "heat", K), pt = io.in(P, "pt", K), delp = io.in(P, "delp", K), aux = io.in(P, "aux", K);
+  io.out(P, "pt_n", build_heat_update(P, mo, c, heat, pt, delp, aux, "heat"));
 }
 
 void mod_dyn_core(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {

@@ -19,12 +19,17 @@ struct DynConfig {
   bool do_vort_damp = true;
   double ptop = 1.0, akap = 2.0 / 7.0, cp_air = 1004.6, rdgas = 287.05, grav = 9.80665, zvir = 0.6078;
   double a_imp = 1.0, p_fac = 0.05;
+  double d_con = 0.0, delt_max = 1.0;   // dissipative heating (model/fv_arrays_nlm.F90:409-411); convert_ke = F, ke_bg = 0
 };
 
 struct DynState { int u, v, w, delz, pt, delp, phis; };
 struct DynOut { int u, v, w, delz, pt, delp, mfx, mfy, cx, cy, pkz, pe, peln, pk, ws; };
 
 void level_params(const DynConfig& c, int K, DswParams& d);
+// del2_cubed(q, cd, nmax): returns the filtered field (q's halo is exchanged in place first)
+int build_del2_cubed(Program& P, Mosaic& mo, int q, double cd, int nmax, int nk, const std::string& tag);
+// end of dyn_core (model/dyn_core_nlm.F90:1052-1099): filter the accumulated heat source, add it to pt.  aux = pkz (hydrostatic) or delz
+int build_heat_update(Program& P, Mosaic& mo, const DynConfig& c, int heat, int pt, int delp, int aux, const std::string& tag);
 DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, const std::string& tag = "dyn");
 struct ModuleParams;
 void dyn_config_from(DynConfig& c, const ModuleParams& prm);

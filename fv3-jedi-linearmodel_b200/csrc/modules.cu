@@ -64,6 +64,8 @@ static void mod_halo(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& p
 }
 
 void mod_c_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
+void mod_del2_cubed(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
+void mod_heat_update(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_dyn_core(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_remap(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_step(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
@@ -87,6 +89,8 @@ static const ModEntry g_mods[] = {
     {"update_dz_c", mod_update_dz_c, "in: ut vt gz zs; out: gz_n ws; params: dts"},
     {"update_dz_d", mod_update_dz_d, "in: zh zs crx cry xfx yfx; out: zh_n ws; params: dts"},
     {"dyn_core_nh", mod_dyn_core_nh, "in: u v pt delp w delz phis; out: u_n v_n pt_n delp_n w_n delz_n mfx mfy cx cy"},
+    {"del2_cubed", mod_del2_cubed, "in: q; out: q_n; params: cd (coefficient relative to da_min) nmax"},
+    {"heat_update", mod_heat_update, "in: heat pt delp aux (pkz if hydrostatic, else delz); out: pt_n; params: hydrostatic bdt nord vtdm4 d2_bg_k1 d2_bg_k2 + constants"},
     {"halo", mod_halo, "in/out: q qc u v uc vc; params: corners"},
 };
 

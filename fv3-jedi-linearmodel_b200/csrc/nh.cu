@@ -124,7 +124,7 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
   const LevD dp0 = dp_ref_of(ak, bk, K);
   DynOut o;
   int u = s.u, v = s.v, pt = s.pt, delp = s.delp, w = s.w, delz = s.delz;
-  int mfx = -1, mfy = -1, cx = -1, cy = -1;
+  int mfx = -1, mfy = -1, cx = -1, cy = -1, heat = -1;
   int zs = P.val(tag + ".zs", 1);
   P.add<S_scale>("zs", {1.0 / c.grav, ng}, {s.phis}, {zs}, 1);
   int zh = -1, ws_d = -1;
@@ -160,6 +160,10 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
       P.add<S_add2>("acc_cy", {isd, ied, js, je + 1}, {cy, ds.cry}, {d}, K);
       mfx = a; mfy = b; cx = cc; cy = d;
     }
+    if (ds.heat >= 0) {   // heat_source += heat_s (model/dyn_core_nlm.F90:685-692)
+      if (heat < 0) heat = ds.heat;
+      else { int hn = P.val(tg + ".heat", K); P.add<S_add2>("acc_heat", {is, ie, js, je}, {heat, ds.heat}, {hn}, K); heat = hn; }
+    }
     delp = ds.delp; pt = ds.pt;
     add_patch(P, "halo_delp", &mo.h_center, {delp});
     add_patch(P, "halo_pt", &mo.h_center, {pt});
@@ -185,6 +189,7 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
     if (it == c.n_split) add_patch(P, "get_boundary_uv", &mo.gb_dgrid, {u, v});
     else add_patch(P, "halo_uv", &mo.h_dgrid, {u, v});
   }
+  if (heat >= 0) pt = build_heat_update(P, mo, c, heat, pt, delp, delz, tag + ".heat");
   o.u = u; o.v = v; o.pt = pt; o.delp = delp; o.w = w; o.delz = delz; o.mfx = mfx; o.mfy = mfy; o.cx = cx; o.cy = cy; o.ws = ws_d;
   return o;
 }

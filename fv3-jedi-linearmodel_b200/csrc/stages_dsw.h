@@ -530,14 +530,75 @@ struct S_duv {
   }
 };
 
+// ---- dissipative heating, d_con > 0 (:1436-1446, :1494-1525).  Edge quantities first:
+//   ubh = (vd(i,j) - vd(i+1,j) + vt3) rdx , fyh = u' rdx   on (is:ie, js:je+1),  u' = the wind before the diffusive flux is added
+//   vbh = (vd(i,j) - vd(i,j+1) - ut3) rdy , fxh = v' rdy   on (is:ie+1, js:je)
+// in: u v ke vd fxv fyv ut3 vt3 (as S_duv) ; out: ubh fyh vbh fxh
+struct S_dheat_edge {
+  static constexpr int NI = 8, NO = 4;
+  struct P { int dummy; };
+  static constexpr int NT = 12;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}, {2, 1, 0, 0}, {2, 0, 1, 0},
+                                   {3, 0, 0, 0}, {3, 1, 0, 0}, {3, 0, 1, 0}, {4, 0, 0, 0}, {5, 0, 0, 0}, {6, 0, 0, 0}, {7, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P&) {
+    const Geom& g = x.g;
+    if (x.in_rect(g.is, g.ie, g.js, g.je + 1)) {
+      auto ke0 = x.in(2) + x.in(3), ke1 = x.in(2, 1, 0) + x.in(3, 1, 0);
+      const double rdx = x.M(x.m.rdx);
+      x.out(0, ((x.in(3) - x.in(3, 1, 0)) + x.in(7)) * rdx);
+      x.out(1, (x.in(0) * x.M(x.m.dx) + (ke0 - ke1) + x.in(5)) * rdx);
+    }
+    if (x.in_rect(g.is, g.ie + 1, g.js, g.je)) {
+      auto ke0 = x.in(2) + x.in(3), ke1 = x.in(2, 0, 1) + x.in(3, 0, 1);
+      const double rdy = x.M(x.m.rdy);
+      x.out(2, ((x.in(3) - x.in(3, 0, 1)) - x.in(6)) * rdy);
+      x.out(3, (x.in(1) * x.M(x.m.dy) + (ke0 - ke1) - x.in(4)) * rdy);
+    }
+  }
+};
+// heat_s of one level: the w-damping part (:938-951, ke_bg = 0) and, where d_con_k > 1e-5, the kinetic energy lost to the
+// divergence / vorticity damping converted to heat (:1494-1525); levels with d_con_k = 0 (sponge layers, dyn_core_nlm.F90:595-628)
+// keep the w part as it is -- not multiplied by delp, like the reference.
+// in: delp_new ubh fyh vbh fxh w fx2w fy2w ; out: heat_s
+struct S_dheat {
+  static constexpr int NI = 8, NO = 1;
+  struct P { int nonhydro; LevD dw_on, d_con; };
+  static constexpr int NT = 14;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {1, 0, 1, 0}, {2, 0, 0, 0}, {2, 0, 1, 0}, {3, 0, 0, 0}, {3, 1, 0, 0},
+                                   {4, 0, 0, 0}, {4, 1, 0, 0}, {5, 0, 0, 0}, {6, 0, 0, 0}, {6, 1, 0, 0}, {7, 0, 0, 0}, {7, 0, 1, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    T heat = T(0.0);
+    if (p.nonhydro && p.dw_on.v[x.kk] != 0.0) {
+      T dw = ((x.in(6) - x.in(6, 1, 0)) + (x.in(7) - x.in(7, 0, 1))) * x.M(x.m.rarea);
+      heat = T(0.0) - dw * (x.in(5) + 0.5 * dw);
+    }
+    const double dcon = p.d_con.v[x.kk];
+    if (dcon > 1.e-5) {
+      const double damp = 0.25 * dcon;
+      T ub0 = x.in(1), ub1 = x.in(1, 0, 1), fy0 = x.in(2), fy1 = x.in(2, 0, 1);
+      T vb0 = x.in(3), vb1 = x.in(3, 1, 0), fx0 = x.in(4), fx1 = x.in(4, 1, 0);
+      T u2 = fy0 + fy1, du2 = ub0 + ub1, v2 = fx0 + fx1, dv2 = vb0 + vb1;
+      heat = x.in(0) * (heat - damp * x.M(x.m.rsin2) * ((ub0 * ub0 + ub1 * ub1 + vb0 * vb0 + vb1 * vb1) +
+                                                        2.0 * (fy0 * ub0 + fy1 * ub1 + fx0 * vb0 + fx1 * vb1) -
+                                                        x.M(x.m.cosa_s) * (u2 * dv2 + v2 * du2 + du2 * dv2)));
+    }
+    x.out(0, heat);
+  }
+};
+
 struct DswParams {
   LevOrd hord_mt, hord_vt, hord_tm, hord_dp;
   LevOrd nord, nord_v, nord_w, nord_t;
   LevD d2_bg, damp_v, damp_w, damp_t;
   double dddmp, d4_bg, dt;
   bool hydrostatic;
+  bool heat = false;   // d_con > 1e-5: build the dissipative-heating stages
+  LevD d_con;          // d_con_k per level (0 in the sponge layers)
 };
-struct DswOut { int delp, pt, u, v, w, fx, fy, crx, cry, xfx, yfx; };
+struct DswOut { int delp, pt, u, v, w, fx, fy, crx, cry, xfx, yfx; int heat = -1; };
 DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w, int uc, int vc, int ua, int va, int divg_d,
                   const DswParams& prm, int nk, const std::string& tag);
 // a2b_ord4 (a2b.cu)

@@ -151,6 +151,80 @@ struct S_add2 {
   }
 };
 
+// ---------------------------------------------------------------------------------
+// del2_cubed (model/dyn_core_nlm.F90:2090-2199; TL model_tlmadm/dyn_core_tlm.F90 DEL2_CUBED_TLM :4909): up to three
+// passes of a 5-point Laplacian filter; pass n works on the compute domain widened by nt = ntimes - n cells.
+// ---------------------------------------------------------------------------------
+// corner averaging (:2146-2165): the three cells around each cube vertex take their mean (q(1,1)+q(0,1)+q(1,0))/3, ... ;
+// every other cell of the region the pass reads is copied.   in: q ; out: q'
+struct S_d2c_corner {
+  static constexpr int NI = 1, NO = 1;
+  struct P { int nt; };
+  static constexpr int NT = 9;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {0, -1, 0, 0}, {0, 1, 0, 0}, {0, 0, -1, 0}, {0, 0, 1, 0}, {0, 1, -1, 0}, {0, -1, 1, 0}, {0, -1, -1, 0}, {0, 1, 1, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    const int h = p.nt + 1;
+    if (!x.in_rect(g.is - h, g.ie + h, g.js - h, g.je + h)) return;
+    const int i = x.i, j = x.j, ie = g.npx - 1, je = g.npy - 1, npx = g.npx, npy = g.npy;
+    const double r3 = 1.0 / 3.0;
+    // offsets of (A, B, C) = (interior corner cell, its x ghost, its y ghost) relative to this cell; the sum is (A + B) + C
+    int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0; bool cor = true;
+    if (i == 1 && j == 1)          { bx = -1; cy = -1; }
+    else if (i == 0 && j == 1)     { ax = 1; cx = 1; cy = -1; }
+    else if (i == 1 && j == 0)     { ay = 1; bx = -1; by = 1; }
+    else if (i == ie && j == 1)    { bx = 1; cy = -1; }
+    else if (i == npx && j == 1)   { ax = -1; cx = -1; cy = -1; }
+    else if (i == ie && j == 0)    { ay = 1; bx = 1; by = 1; }
+    else if (i == ie && j == je)   { bx = 1; cy = 1; }
+    else if (i == npx && j == je)  { ax = -1; cx = -1; cy = 1; }
+    else if (i == ie && j == npy)  { ay = -1; bx = 1; by = -1; }
+    else if (i == 1 && j == je)    { bx = -1; cy = 1; }
+    else if (i == 0 && j == je)    { ax = 1; cx = 1; cy = 1; }
+    else if (i == 1 && j == npy)   { ay = -1; bx = -1; by = -1; }
+    else cor = false;
+    if (cor) { T a = x.in(0, ax, ay), b = x.in(0, bx, by), c = x.in(0, cx, cy); x.out(0, (a + b + c) * r3); }
+    else x.out(0, x.in(0));
+  }
+};
+// q <- q + cd rarea (fx(i) - fx(i+1) + fy(j) - fy(j+1))  on the domain widened by nt (:2189-2193).  in: q fx fy ; out: q'
+struct S_d2c_upd {
+  static constexpr int NI = 3, NO = 1;
+  struct P { int nt; double cd; };
+  static constexpr int NT = 5;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {1, 1, 0, 0}, {2, 0, 0, 0}, {2, 0, 1, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is - p.nt, g.ie + p.nt, g.js - p.nt, g.je + p.nt)) return;
+    x.out(0, x.in(0) + p.cd * x.M(x.m.rarea) * (x.in(1) - x.in(1, 1, 0) + x.in(2) - x.in(2, 0, 1)));
+  }
+};
+
+// dissipative heating added to pt on the top n_con layers (model/dyn_core_nlm.F90:1052-1099; pt is cp * virtual temperature / pkz).
+//   hydrostatic: layers 1, 2: pt += hs / (cp delp pkz) ; below: dtmp = hs / (cp delp), pt += sign(min(delt, |dtmp|), dtmp) / pkz
+//   otherwise  : pkz = exp(k1k log(rdg delp / delz pt)), dtmp = hs / (cv delp), pt += sign(min(delt, |dtmp|), dtmp) / pkz
+// in: pt hs delp pkz|delz ; out: pt'
+struct S_heat_pt {
+  static constexpr int NI = 4, NO = 1;
+  struct P { int n_con, hydrostatic; double cp_air, cv_air, delt, rdg, k1k; };
+  static constexpr int NT = 4;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}, {3, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    T pt = x.in(0);
+    if (x.kk >= p.n_con) { x.out(0, pt); return; }
+    T hs = x.in(1), dp = x.in(2);
+    if (p.hydrostatic && x.kk < 2) { x.out(0, pt + hs / (p.cp_air * dp * x.in(3))); return; }
+    T pkz = p.hydrostatic ? x.in(3) : m_exp(p.k1k * m_log(p.rdg * dp / x.in(3) * pt));
+    T dtmp = hs / ((p.hydrostatic ? p.cp_air : p.cv_air) * dp);
+    T mn = m_min(T(p.delt), m_abs(dtmp));
+    x.out(0, pt + (val(dtmp) >= 0.0 ? mn : T(0.0) - mn) / pkz);
+  }
+};
+
 struct DynParams;  // dyn.cu
 
 }  // namespace fv3lm

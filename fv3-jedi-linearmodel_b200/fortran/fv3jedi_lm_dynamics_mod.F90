@@ -130,7 +130,7 @@ subroutine create(self,conf)
  cfg%rank = mpp_pe() - mpp_root_pe(); cfg%nranks = mpp_npes()
  cfg%layout_x = A%layout(1); cfg%layout_y = A%layout(2)
  cfg%reserved0 = 0; cfg%reserved = 0
- cfg%a_imp = A%flagstruct%a_imp; cfg%p_fac = A%flagstruct%p_fac
+ cfg%a_imp = A%flagstruct%a_imp; cfg%p_fac = A%flagstruct%p_fac; cfg%d_con = A%flagstruct%d_con
 
  call check(self, fv3lm_create(cfg, conf%ak, conf%bk, self%handle), 'create')
 

@@ -20,8 +20,8 @@ type, bind(c) :: fv3lm_config
   integer(c_int) :: do_vort_damp
   integer(c_int) :: rank, nranks, layout_x, layout_y
   integer(c_int) :: reserved0
-  real(c_double) :: a_imp, p_fac
-  integer(c_int) :: reserved(8)
+  real(c_double) :: a_imp, p_fac, d_con
+  integer(c_int) :: reserved(6)
 end type fv3lm_config
 
 !> mirror of `struct fv3lm_fields`: ten pointers to (isc:iec, jsc:jec, npz) REAL64 arrays

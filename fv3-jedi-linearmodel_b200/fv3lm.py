@@ -26,7 +26,7 @@ class Config(C.Structure):
                 ("zvir", C.c_double), ("kappa", C.c_double), ("cp", C.c_double), ("rdgas", C.c_double),
                 ("grav", C.c_double), ("do_vort_damp", C.c_int),
                 ("rank", C.c_int), ("nranks", C.c_int), ("layout_x", C.c_int), ("layout_y", C.c_int), ("reserved0", C.c_int),
-                ("a_imp", C.c_double), ("p_fac", C.c_double), ("reserved", C.c_int * 8)]
+                ("a_imp", C.c_double), ("p_fac", C.c_double), ("d_con", C.c_double), ("reserved", C.c_int * 6)]
 
 
 class Fields(C.Structure):

@@ -52,7 +52,11 @@ typedef struct fv3lm_config {
    * (Riem_Solver_c keeps SIM1, model/nh_utils_nlm.F90:366-376); a_imp <= 0.5 (RIM_2D / SIM3) is an error.
    * p_fac: lower bound of the gas pressure relative to the hydrostatic one (default 0.05).        */
   double a_imp, p_fac;
-  int reserved[8];
+  /* d_con > 1e-5: the kinetic energy removed by the divergence / vorticity / w damping returns as heat
+   * (model/sw_core_nlm.F90:1494-1525, model/dyn_core_nlm.F90:1052-1099; needs do_vort_damp with vtdm4 > 1e-5).
+   * convert_ke = F, ke_bg = 0, delt_max = 1 (model/fv_arrays_nlm.F90:312, :409-412).                */
+  double d_con;
+  int reserved[6];
 } fv3lm_config;
 
 int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv3lm_handle** out);

@@ -380,6 +380,7 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm):
     un = S(vt2, i0, i1, j0, j1) + (S(ke, i0, i1, j0, j1) - S(ke, i0 + 1, i1 + 1, j0, j1)) + S(fyv, i0, i1, j0, j1)
     i0, i1, j0, j1 = is_, ie + 1, js, je
     vn = S(ut2, i0, i1, j0, j1) + (S(ke, i0, i1, j0, j1) - S(ke, i0, i1, j0 + 1, j1 + 1)) - S(fxv, i0, i1, j0, j1)
+    un_pre, vn_pre = un, vn
     # ---- vorticity damping (:1487-1539)
     dmpv = prm["damp_v"]; nordv = prm["nord_v"]
     if any(d > 1.e-5 for d in dmpv):
@@ -390,4 +391,27 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm):
         vn = vn - on * S(ut3, is_, ie + 1, js, je)
     u_new = put(u, is_, ie, js, je + 1, un)
     v_new = put(v, is_, ie + 1, js, je, vn)
-    return dict(delp=delp_new, pt=pt_new, u=u_new, v=v_new, w=w_new, fx=fx, fy=fy, crx=crx, cry=cry, xfx=xfx, yfx=yfx)
+    out = dict(delp=delp_new, pt=pt_new, u=u_new, v=v_new, w=w_new, fx=fx, fy=fy, crx=crx, cry=cry, xfx=xfx, yfx=yfx)
+    # ---- dissipative heating (:938-951 the w part with ke_bg = 0, :1436-1446, :1494-1525).  prm["d_con"]: d_con_k per level
+    dcon = prm.get("d_con")
+    if dcon is not None and any(d > 1.e-5 for d in dcon):
+        assert all(dmpv[k] > 1.e-5 for k in range(K) if dcon[k] > 1.e-5)
+        heat0 = torch.zeros_like(delp_new_v)
+        if not hydro:
+            heat0 = -(dw * (S(w, is_, ie, js, je) + 0.5 * dw))
+        i0, i1, j0, j1 = is_, ie, js, je + 1
+        ubh = put(Z(u), i0, i1, j0, j1, ((S(vort_d, i0, i1, j0, j1) - S(vort_d, i0 + 1, i1 + 1, j0, j1)) + S(vt3, i0, i1, j0, j1)) * S(g.rdx, i0, i1, j0, j1))
+        fyh = put(Z(u), i0, i1, j0, j1, un_pre * S(g.rdx, i0, i1, j0, j1))
+        i0, i1, j0, j1 = is_, ie + 1, js, je
+        vbh = put(Z(u), i0, i1, j0, j1, ((S(vort_d, i0, i1, j0, j1) - S(vort_d, i0, i1, j0 + 1, j1 + 1)) - S(ut3, i0, i1, j0, j1)) * S(g.rdy, i0, i1, j0, j1))
+        fxh = put(Z(u), i0, i1, j0, j1, vn_pre * S(g.rdy, i0, i1, j0, j1))
+        C0 = (is_, ie, js, je); CN = (is_, ie, js + 1, je + 1); CE = (is_ + 1, ie + 1, js, je)
+        ub0, ub1, fy0, fy1 = S(ubh, *C0), S(ubh, *CN), S(fyh, *C0), S(fyh, *CN)
+        vb0, vb1, fx0, fx1 = S(vbh, *C0), S(vbh, *CE), S(fxh, *C0), S(fxh, *CE)
+        u2 = fy0 + fy1; du2 = ub0 + ub1; v2 = fx0 + fx1; dv2 = vb0 + vb1
+        dk = _lv(dcon)
+        hs = delp_new_v * (heat0 - 0.25 * dk * S(g.rsin2, *C0) * ((ub0 ** 2 + ub1 ** 2 + vb0 ** 2 + vb1 ** 2) +
+                                                               2. * (fy0 * ub0 + fy1 * ub1 + fx0 * vb0 + fx1 * vb1) -
+                                                               S(g.cosa_s, *C0) * (u2 * dv2 + v2 * du2 + du2 * dv2)))
+        out["heat"] = put(Z(u), *C0, torch.where(dk > 1.e-5, hs, heat0))
+    return out

@@ -10,8 +10,9 @@ parity unpinned (no reference vectors).
 """
 import numpy as np
 import torch
-from .cubed_sphere import R, NG, Halo, neighbour, to_neighbour, STAG
+from .cubed_sphere import R, NG, Halo, neighbour, to_neighbour, STAG, copy_corners
 from .sw_core import c_sw, S, put, Z, O
+from .sw_core import P as Pt
 from .d_sw import d_sw
 from .a2b_edge import a2b_ord4
 
@@ -141,7 +142,7 @@ def level_params(cfg, K):
     hord_mt hord_vt hord_tm hord_dp nord d2_bg d2_bg_k1 d2_bg_k2 n_sponge vtdm4 do_vort_damp dddmp d4_bg
     (the TL module additionally uses first-order transport in the sponge, hord_*_ks = 1,
     model_tlmadm/dyn_core_tlm.F90:740-926: n_sponge_ord layers)"""
-    p = {k: [] for k in ("hord_mt", "hord_vt", "hord_tm", "hord_dp", "nord", "nord_v", "nord_w", "nord_t", "d2_bg", "damp_v", "damp_w", "damp_t")}
+    p = {k: [] for k in ("hord_mt", "hord_vt", "hord_tm", "hord_dp", "nord", "nord_v", "nord_w", "nord_t", "d2_bg", "damp_v", "damp_w", "damp_t", "d_con")}
     ns = cfg.get("n_sponge", 0)
     for k in range(1, K + 1):
         nord_k = cfg["nord"]
@@ -149,6 +150,7 @@ def level_params(cfg, K):
         d2 = min(0.20, cfg["d2_bg"])
         damp_vt = cfg["vtdm4"] if cfg["do_vort_damp"] else 0.0
         nord_w = nord_v; nord_t = nord_v; damp_w = damp_vt; damp_t = damp_vt
+        d_con_k = cfg.get("d_con", 0.0)
         if K == 1 or ns < 0:
             d2 = cfg["d2_bg"]
         else:
@@ -156,19 +158,88 @@ def level_params(cfg, K):
                 nord_k = 0; d2 = max(0.01, cfg["d2_bg"], cfg["d2_bg_k1"]); nord_w = 0; damp_w = d2
                 if cfg["do_vort_damp"]:
                     nord_v = 0; damp_vt = 0.5 * d2
+                d_con_k = 0.0
             elif k == max(2, ns - 1) and cfg["d2_bg_k2"] > 0.01:
                 nord_k = 0; d2 = max(cfg["d2_bg"], cfg["d2_bg_k2"]); nord_w = 0; damp_w = d2
                 if cfg["do_vort_damp"]:
                     nord_v = 0; damp_vt = 0.5 * d2
+                d_con_k = 0.0
             elif k == max(3, ns) and cfg["d2_bg_k2"] > 0.05:
                 nord_k = 0; d2 = max(cfg["d2_bg"], 0.2 * cfg["d2_bg_k2"]); nord_w = 0; damp_w = d2
+                d_con_k = 0.0
         ho = 1 if k <= cfg.get("n_sponge_ord", 0) else None
         for n in ("hord_mt", "hord_vt", "hord_tm", "hord_dp"):
             p[n].append(ho if ho else cfg[n])
         p["nord"].append(nord_k); p["nord_v"].append(nord_v); p["nord_w"].append(nord_w); p["nord_t"].append(nord_t)
         p["d2_bg"].append(d2); p["damp_v"].append(damp_vt); p["damp_w"].append(damp_w); p["damp_t"].append(damp_t)
+        p["d_con"].append(d_con_k)
     p["dddmp"] = cfg["dddmp"]; p["d4_bg"] = cfg["d4_bg"]
+    if not cfg.get("d_con", 0.0) > 1.e-5:
+        del p["d_con"]
     return p
+
+
+def del2_cubed(q, cd, g, nmax, halo):
+    """model/dyn_core_nlm.F90:2090-2199.  q: [6,K,..] full array (halo exchanged here); returns the filtered array
+    (valid on the compute domain)."""
+    N, npx, npy = g.N, g.npx, g.npy
+    is_, ie, js, je = 1, N, 1, N
+    ntimes = min(3, nmax)
+    q = halo.scalar(q)
+    for n in range(1, ntimes + 1):
+        nt = ntimes - n
+        q = q.clone()
+        for (a, b, c) in (((1, 1), (0, 1), (1, 0)), ((ie, 1), (npx, 1), (ie, 0)), ((ie, je), (npx, je), (ie, npy)), ((1, je), (0, je), (1, npy))):
+            m = (Pt(q, *a) + Pt(q, *b) + Pt(q, *c)) * (1. / 3.)
+            for (i, j) in (a, b, c):
+                q[..., j + O, i + O] = m
+        if nt > 0:
+            q = copy_corners(q, npx, npy, 1)
+        i0, i1, j0, j1 = is_ - nt, ie + 1 + nt, js - nt, je + nt
+        fx = put(Z(q), i0, i1, j0, j1, S(g.del6_v, i0, i1, j0, j1) * (S(q, i0 - 1, i1 - 1, j0, j1) - S(q, i0, i1, j0, j1)))
+        if nt > 0:
+            q = copy_corners(q, npx, npy, 2)
+        i0, i1, j0, j1 = is_ - nt, ie + nt, js - nt, je + 1 + nt
+        fy = put(Z(q), i0, i1, j0, j1, S(g.del6_u, i0, i1, j0, j1) * (S(q, i0, i1, j0 - 1, j1 - 1) - S(q, i0, i1, j0, j1)))
+        i0, i1, j0, j1 = is_ - nt, ie + nt, js - nt, je + nt
+        q = put(q, i0, i1, j0, j1, S(q, i0, i1, j0, j1) + cd * S(g.rarea, i0, i1, j0, j1) *
+                (S(fx, i0, i1, j0, j1) - S(fx, i0 + 1, i1 + 1, j0, j1) + S(fy, i0, i1, j0, j1) - S(fy, i0, i1, j0 + 1, j1 + 1)))
+    return q
+
+
+def heat_update(heat, pt, delp, aux, g, cfg, halo, hydrostatic):
+    """end of dyn_core (model/dyn_core_nlm.F90:1052-1099): filter the accumulated heat source and add it to pt on the top
+    n_con layers.  aux = pkz (hydrostatic) or delz.  convert_ke = F, delt_max = 1."""
+    N = g.N
+    K = pt.shape[1]
+    if cfg["vtdm4"] > 1.e-4:
+        n_con = K
+    elif cfg["d2_bg_k1"] < 1.e-3:
+        n_con = 0
+    else:
+        n_con = 1 if cfg["d2_bg_k2"] < 1.e-3 else 2
+    if n_con == 0:
+        return pt
+    n_con = min(n_con, K)
+    hs = del2_cubed(heat, 0.20 * g.da_min, g, min(3, cfg["nord"] + 1), halo)
+    C = (1, N, 1, N)
+    delt = abs(cfg["bdt"] * 1.0)
+    ptc, hsc, dpc, ax = S(pt, *C), S(hs, *C), S(delp, *C), S(aux, *C)
+    if hydrostatic:
+        dtmp = hsc / (cfg["cp_air"] * dpc)
+        lim = torch.where(dtmp >= 0., torch.minimum(torch.full_like(dtmp, delt), dtmp.abs()), -torch.minimum(torch.full_like(dtmp, delt), dtmp.abs())) / ax
+        top = hsc / (cfg["cp_air"] * dpc * ax)
+        kk = torch.arange(K).view(1, -1, 1, 1)
+        inc = torch.where(kk < 2, top, lim)
+    else:
+        rdg = -cfg["rdgas"] / cfg["grav"]; k1k = cfg["akap"] / (1. - cfg["akap"]); cv_air = cfg["cp_air"] - cfg["rdgas"]
+        pkz = torch.exp(k1k * torch.log(rdg * dpc / ax * ptc))
+        dtmp = hsc / (cv_air * dpc)
+        mn = torch.minimum(torch.full_like(dtmp, delt), dtmp.abs())
+        inc = torch.where(dtmp >= 0., mn, -mn) / pkz
+        kk = torch.arange(K).view(1, -1, 1, 1)
+    inc = torch.where(kk < n_con, inc, torch.zeros_like(inc))
+    return put(pt, *C, ptc + inc)
 
 
 def dyn_core_hydro(st, g, cfg):
@@ -189,6 +260,7 @@ def dyn_core_hydro(st, g, cfg):
     w = Z(u)
     hs = st["phis"]
     mfx = Z(u); mfy = Z(u); cx = Z(u); cy = Z(u)
+    heat = None
     ptop, akap, cp_air = cfg["ptop"], cfg["akap"], cfg["cp_air"]
     for it in range(1, n_split + 1):
         c = c_sw(delp, pt, u, v, w, g, dt2, True, cfg["nord"])
@@ -201,6 +273,8 @@ def dyn_core_hydro(st, g, cfg):
         mfy = put(mfy, is_, ie, js, je + 1, S(mfy, is_, ie, js, je + 1) + S(d["fy"], is_, ie, js, je + 1))
         cx = put(cx, is_, ie + 1, jsd, jed, S(cx, is_, ie + 1, jsd, jed) + S(d["crx"], is_, ie + 1, jsd, jed))
         cy = put(cy, isd, ied, js, je + 1, S(cy, isd, ied, js, je + 1) + S(d["cry"], isd, ied, js, je + 1))
+        if "heat" in d:
+            heat = d["heat"] if heat is None else heat + d["heat"]
         delp = halo.scalar(d["delp"]); pt = halo.scalar(d["pt"])
         pkc, gz, pe, peln, pkz = geopk(delp, pt, hs, g, ptop, akap, cp_air, 2, False)
         u, v = grad_p(d["u"], d["v"], pkc, gz, g, dt, ptop ** akap)
@@ -208,4 +282,6 @@ def dyn_core_hydro(st, g, cfg):
             u, v = getb(u, v)
         else:
             u, v = halo.dgrid(u, v)
+    if heat is not None:
+        pt = heat_update(heat, pt, delp, pkz, g, cfg, halo, True)
     return dict(u=u, v=v, pt=pt, delp=delp, mfx=mfx, mfy=mfy, cx=cx, cy=cy, pkz=pkz, pe=pe, peln=peln, pk=pkc)

@@ -15,7 +15,7 @@ from .cubed_sphere import R, fill_4corners
 from .sw_core import c_sw, S, put, Z, O, sg
 from .d_sw import d_sw, del6_vt_flux
 from . import tp_core as tp
-from .dyn_core import halo_of, p_grad_c, grad_p, level_params, geopk
+from .dyn_core import halo_of, p_grad_c, grad_p, level_params, geopk, heat_update
 
 DZ_MIN = 2.0
 R3 = 1. / 3.
@@ -301,6 +301,7 @@ def dyn_core_nh(st, g, cfg, ak, bk, first_call=True):
     zs = hs / grav
     mfx = Z(u); mfy = Z(u); cx = Z(u); cy = Z(u)
     zh = None
+    heat = None
     C = (slice(None), slice(None), R(js, je), R(is_, ie))
     for it in range(1, n_split + 1):
         w = halo.scalar(w)
@@ -331,6 +332,8 @@ def dyn_core_nh(st, g, cfg, ak, bk, first_call=True):
         mfy = put(mfy, is_, ie, js, je + 1, S(mfy, is_, ie, js, je + 1) + S(d["fy"], is_, ie, js, je + 1))
         cx = put(cx, is_, ie + 1, jsd, jed, S(cx, is_, ie + 1, jsd, jed) + S(d["crx"], is_, ie + 1, jsd, jed))
         cy = put(cy, isd, ied, js, je + 1, S(cy, isd, ied, js, je + 1) + S(d["cry"], isd, ied, js, je + 1))
+        if "heat" in d:
+            heat = d["heat"] if heat is None else heat + d["heat"]
         delp = halo.scalar(d["delp"]); pt = halo.scalar(d["pt"]); w = d["w"]
         zh, ws = update_dz_d(prm["nord_v"], prm["damp_v"], cfg["hord_tm"], dp_ref, zs, zh, d["crx"], d["cry"], d["xfx"], d["yfx"], g, rdt)
         wn, dzn, zhn, ppe = riem_solver3(dt, delp[C], pt[C], zh[C], w[C], ws[C], zs[C], cfg)
@@ -347,5 +350,7 @@ def dyn_core_nh(st, g, cfg, ak, bk, first_call=True):
             u, v = getb(u, v)
         else:
             u, v = halo.dgrid(u, v)
+    if heat is not None:
+        pt = heat_update(heat, pt, delp, delz, g, cfg, halo, False)
     return dict(u=u, v=v, w=w, delz=delz, pt=pt, delp=delp, mfx=mfx, mfy=mfy, cx=cx, cy=cy, pe=pe, pk=pk3, peln=peln,
                 pkz=torch.zeros_like(delp), ws=ws)

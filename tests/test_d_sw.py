@@ -50,16 +50,18 @@ def flat_params(p, K):
     return out
 
 
-def _run_dsw(emu, hydrostatic, sponge, hord=2):
+def _run_dsw(emu, hydrostatic, sponge, hord=2, d_con=0.0):
     N, K = 12, 2
     f, rng = dsw_inputs(N, K, 11)
     g = ograd(N)
     dt = 450.0
     prm = level_params(K, sponge, hord)
     prm.update(dddmp=0.2, d4_bg=0.15, hydrostatic=hydrostatic)
+    if d_con > 0.0:
+        prm["d_con"] = [0.0 if (sponge and k == 0) else d_con for k in range(K)]     # d_con_k = 0 in sponge layers (dyn_core_nlm.F90:595-628)
     names = list(f.keys())
     act = [n for n in names if not (hydrostatic and n == "w")]
-    onames = ["delp_n", "pt_n", "u_n", "v_n", "fx", "fy", "crx", "cry", "xfx", "yfx"] + ([] if hydrostatic else ["w_n"])
+    onames = ["delp_n", "pt_n", "u_n", "v_n", "fx", "fy", "crx", "cry", "xfx", "yfx"] + ([] if hydrostatic else ["w_n"]) + (["heat"] if d_con > 0.0 else [])
     key = dict(delp_n="delp", pt_n="pt", u_n="u", v_n="v", w_n="w")
     def fn(*a):
         d = {n: torch.from_numpy(f[n]) for n in names}
@@ -68,7 +70,7 @@ def _run_dsw(emu, hydrostatic, sponge, hord=2):
         return tuple(o[key.get(k, k)] for k in onames)
     npx = N + 1
     C = (1, N, 1, N)
-    outs = dict(delp_n=C, pt_n=C, w_n=C, u_n=(1, N, 1, npx), v_n=(1, npx, 1, N), fx=(1, npx, 1, N), fy=(1, N, 1, npx),
+    outs = dict(delp_n=C, pt_n=C, w_n=C, heat=C, u_n=(1, N, 1, npx), v_n=(1, npx, 1, N), fx=(1, npx, 1, N), fy=(1, N, 1, npx),
                 crx=(1, npx, -2, N + 3), xfx=(1, npx, -2, N + 3), cry=(-2, N + 3, 1, npx), yfx=(-2, N + 3, 1, npx))
     outs = {k: outs[k] for k in onames}
     h = handle(N, K, emu)
@@ -92,6 +94,17 @@ def test_a2b_ord4_emu():
 @pytest.mark.parametrize("hydrostatic,sponge", [(True, False), (False, True)])
 def test_d_sw_emu(hydrostatic, sponge):
     _run_dsw(True, hydrostatic, sponge)
+
+
+@pytest.mark.parametrize("hydrostatic,sponge", [(True, False), (False, True)])
+def test_d_sw_heat_emu(hydrostatic, sponge):
+    """d_con > 0: kinetic energy lost to the damping returned as heat_s (sw_core_nlm.F90:1494-1525)"""
+    _run_dsw(True, hydrostatic, sponge, d_con=1.0)
+
+
+@pytest.mark.gpu
+def test_d_sw_heat_gpu():
+    _run_dsw(False, False, True, d_con=1.0)
 
 
 def test_d_sw_hord333_emu():

@@ -41,11 +41,12 @@ def hydro_state(N, K, seed):
     return {k: a.numpy().copy() for k, a in t.items()}, rng
 
 
-def _run(emu, n_split, K=3, modes=("nl", "tl", "ad")):
+def _run(emu, n_split, K=3, modes=("nl", "tl", "ad"), extra=None):
     N = 12
     f, rng = hydro_state(N, K, 5)
     g = ograd(N)
     cfg = dict(CFG); cfg["n_split"] = n_split; cfg["bdt"] = 900.0
+    cfg.update(extra or {})
     act = ["u", "v", "pt", "delp"]
     onames = ["u_n", "v_n", "pt_n", "delp_n", "mfx", "mfy", "cx", "cy", "pkz"]
     key = dict(u_n="u", v_n="v", pt_n="pt", delp_n="delp")
@@ -67,6 +68,64 @@ def _run(emu, n_split, K=3, modes=("nl", "tl", "ad")):
 def test_dyn_core_hydro_emu(n_split):
     r = _run(True, n_split)
     print(r)
+
+
+def _run_del2_cubed(emu, nmax):
+    """del2_cubed (model/dyn_core_nlm.F90:2090-2199): nmax passes of the 5-point filter with corner averaging"""
+    N, K = 12, 2
+    rng = np.random.default_rng(77)
+    halo, _ = odyn.halo_of(N)
+    g = ograd(N)
+    f = {"q": rnd(rng, N, K)}
+    h = handle(N, K, emu)
+    def fn(q):
+        return (odyn.del2_cubed(q, 0.18 * g.da_min, g, nmax, halo),)
+    return check_module(h, "del2_cubed", N, K, f, ["q"], {"q_n": (1, N, 1, N)}, fn, dict(cd=0.18, nmax=nmax), rng, tol=1e-12, dot_tol=1e-12)
+
+
+@pytest.mark.parametrize("nmax", [1, 2, 3])
+def test_del2_cubed_emu(nmax):
+    print(_run_del2_cubed(True, nmax))
+
+
+def _run_heat_update(emu, hydrostatic):
+    """the end of dyn_core on its own (dyn_core_nlm.F90:1052-1099) with a heat source large enough to reach the delt_max limiter"""
+    N, K = 12, 4
+    rng = np.random.default_rng(78)
+    halo, _ = odyn.halo_of(N)
+    g = ograd(N)
+    RD = 8314.47 / 28.965
+    cfg = dict(CFG); cfg.update(bdt=2.0e-3, hydrostatic=hydrostatic, rdgas=RD, grav=9.80665)
+    delp = 1000.0 + 50.0 * rnd(rng, N, K)
+    f = dict(heat=3.0e3 * rnd(rng, N, K), pt=300.0 + 5.0 * rnd(rng, N, K), delp=delp)
+    f["aux"] = (1.0 + 0.1 * rnd(rng, N, K)) if hydrostatic else -(800.0 + 20.0 * rnd(rng, N, K))
+    def fn(heat, pt, delp, aux):
+        return (odyn.heat_update(heat, pt, delp, aux, g, cfg, halo, hydrostatic),)
+    h = handle(N, K, emu)
+    p = dict(cfg); p["hydrostatic"] = int(hydrostatic); p["do_vort_damp"] = 1
+    r = check_module(h, "heat_update", N, K, f, ["heat", "pt", "delp", "aux"], {"pt_n": (1, N, 1, N)}, fn, p, rng, tol=1e-12, dot_tol=1e-12, pert_scale=1e-4)
+    # both branches of the limiter are exercised
+    dtmp = f["heat"] / ((cfg["cp_air"] if hydrostatic else cfg["cp_air"] - RD) * f["delp"])
+    frac = float((np.abs(dtmp) > abs(cfg["bdt"])).mean())
+    assert 0.1 < frac < 0.9, frac
+    return r
+
+
+@pytest.mark.parametrize("hydrostatic", [True, False])
+def test_heat_update_emu(hydrostatic):
+    print(_run_heat_update(True, hydrostatic))
+
+
+def test_dyn_core_hydro_heat_emu():
+    """d_con = 1: heat source accumulated over the acoustic steps, filtered by del2_cubed, added to pt (dyn_core_nlm.F90:1052-1075)"""
+    print(_run(True, 2, K=5, extra=dict(d_con=1.0)))     # layers 1-3 are sponge layers (d_con_k = 0): K = 5 leaves two heated ones
+
+
+@pytest.mark.gpu
+def test_del2_cubed_and_heat_gpu():
+    _run_del2_cubed(False, 3)
+    _run_heat_update(False, True); _run_heat_update(False, False)
+    _run(False, 2, K=5, extra=dict(d_con=1.0))
 
 
 @pytest.mark.gpu

@@ -122,12 +122,13 @@ def nh_state(N, K, seed, ak, bk):
     return {k: a.numpy().copy() for k, a in t.items()}, rng
 
 
-def _run_dyn_nh(emu, n_split, a_imp=1.0):
+def _run_dyn_nh(emu, n_split, a_imp=1.0, extra=None):
     N, K = 12, 4
     ak, bk = eta(K, CFG["ptop"])
     f, rng = nh_state(N, K, 17, ak, bk)
     g = ograd(N)
     cfg = dict(NHCFG); cfg.update(n_split=n_split, bdt=600.0, a_imp=a_imp)
+    cfg.update(extra or {})
     act = ["u", "v", "pt", "delp", "w", "delz"]
     onames = ["u_n", "v_n", "pt_n", "delp_n", "w_n", "delz_n", "mfx", "cx"]
     key = dict(u_n="u", v_n="v", pt_n="pt", delp_n="delp", w_n="w", delz_n="delz")
@@ -163,6 +164,11 @@ def test_dyn_core_nh_sim_solver_emu():
     print(_run_dyn_nh(True, 2, 0.75))
 
 
+def test_dyn_core_nh_heat_emu():
+    """d_con = 1 in the non-hydrostatic loop: w-damping and KE-damping heat, pkz from delz (dyn_core_nlm.F90:1078-1099)"""
+    print(_run_dyn_nh(True, 2, extra=dict(d_con=1.0)))
+
+
 def test_update_dz_c_emu():
     print(_run_dzc(True))
 
@@ -179,6 +185,11 @@ def test_dyn_core_nh_emu():
 @pytest.mark.parametrize("mode", [0, 1])
 def test_riem_gpu(mode):
     _run_riem(False, mode)
+
+
+@pytest.mark.gpu
+def test_dyn_core_nh_heat_gpu():
+    _run_dyn_nh(False, 2, extra=dict(d_con=1.0))
 
 
 @pytest.mark.gpu

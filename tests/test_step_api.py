@@ -99,6 +99,11 @@ def test_step_api_hord333_emu():
     print(_run(True, extra=dict(hord_mt=333, hord_vt=333, hord_tm=333, hord_dp=333, hord_tr=333)))
 
 
+def test_step_api_d_con_emu():
+    """d_con = 1 through fv3lm_config: dissipative heating in a non-hydrostatic step (NL vs oracle, dot product, Taylor)"""
+    print(_run(True, nonhydro=True, extra=dict(d_con=1.0)))
+
+
 def test_program_stats_emu():
     h, *_ = make(True)
     s = h.program_stats("step")
