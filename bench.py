@@ -177,6 +177,16 @@ def run_gpu(args):
                 fh.write("%-28s %5d %10.3f %9.1f %6.2f%%\n" % (r[0], r[1], r[2], (r[3] / (r[2] * 1e-3) / 1e9 if r[2] > 0 else 0.0), 100.0 * r[2] / tot))
     peak, pk_src = peaks()
     top = rows[0]
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of the same workload (profiles/ncu_traffic.json:
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch); null when no capture exists for this kernel / resolution / GPU count
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = tj.get(top[0])
+        if e and e.get("res") == N and e.get("hydrostatic") == bool(hydro) and e.get("n_gpus") == world:
+            traffic = e["dram_bytes_per_launch"]
+    except (OSError, ValueError):
+        pass
     ach = top[3] / top[1] / (top[2] / top[1] * 1e-3) / 1e9 if top[2] > 0 else 0.0
     field_bytes = 6.0 * N * N * K * 8.0
     p_tl, p_ad = alg_passes(mc["n_split"], hydro)
@@ -196,7 +206,7 @@ def run_gpu(args):
         "clocks": ck.summary(),
         "e2e": {"value": 1000.0 / e2e_ms, "unit": "TL+AD step pairs/s", "h2d_bytes_per_step": int(4 * fb), "d2h_bytes_per_step": int(2 * fb),
                 "note": "trajectory (8 fields) re-sent before each of step_tl and step_ad like the reference API; increments up and down"},
-        "roofline": {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                      "peak_source": pk_src, "share_of_step": top[2] / tot if tot > 0 else None,
                      "note": "algorithmic bytes = 8 B x cells x distinct arrays read+written by that launch (halo excluded)"},
         "step_roofline": {"alg_gb_per_step_pair": step_alg_gb, "achieved": step_alg_gb / (ms_step * 1e-3), "peak": peak, "unit": "GB/s",
