@@ -5,7 +5,7 @@ using namespace fv3lm;
 namespace fv3lm { void a2b_corner_weights(const Geom& g, const double* glon, const double* glat, const double* alon, const double* alat, double* out); }
 
 thread_local std::string fv3lm_g_err;
-static_assert(sizeof(fv3lm_config) == 256, "fv3lm_config is mirrored field by field in fv3lm.py and fortran/fv3lm_b200_capi_mod.F90");
+static_assert(sizeof(fv3lm_config) == 344, "fv3lm_config is mirrored field by field in fv3lm.py and fortran/fv3lm_b200_capi_mod.F90");
 
 // host [rows][NX] contiguous <-> device [rows][pitch]
 static void up2d(const Geom& g, double* d, const double* h, size_t rows) {
@@ -37,6 +37,9 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
   if (cfg->npz > 95 || cfg->npz < 1) throw std::runtime_error("fv3lm_create: npz must be in 1..95");
   for (int ho : {cfg->hord_mt, cfg->hord_vt, cfg->hord_tm, cfg->hord_dp, cfg->hord_tr})
     if (ho != 1 && ho != 2 && ho != 333) throw std::runtime_error("fv3lm_create: hord_* must be 1, 2 or 333 (the linear schemes the TL/AD implement, tp_core_tlm.F90:2431-2488)");
+  if (cfg->two_sided)
+    for (int ho : {cfg->traj.hord_mt, cfg->traj.hord_vt, cfg->traj.hord_tm, cfg->traj.hord_dp, cfg->traj.hord_tr})
+      if (ho != 1 && ho != 2 && ho != 333) throw std::runtime_error("fv3lm_create: traj.hord_* must be 1, 2 or 333: the monotone schemes of the nonlinear model (hord 5-13) are not built");
   if (cfg->nq != 4) throw std::runtime_error("fv3lm_create: nq must be 4 (qv, ql, qi, o3)");
   if (cfg->n_split < 1 || cfg->k_split < 1 || !(cfg->dt > 0.0)) throw std::runtime_error("fv3lm_create: n_split, k_split and dt must be positive");
   if (cfg->nord < 0 || cfg->nord > 3) throw std::runtime_error("fv3lm_create: nord must be in 0..3");

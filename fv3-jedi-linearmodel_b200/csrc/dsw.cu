@@ -53,10 +53,24 @@ static TpOut build_tp_damped(Program& P, Mosaic& mo, int q, int crx, int cry, in
   return {fx, fy};
 }
 
+static bool same_ord(const LevOrd& a, const LevOrd& b, int nk) { for (int k = 0; k < nk; k++) if (a.v[k] != b.v[k]) return false; return true; }
+static bool same_lev(const LevD& a, const LevD& b, int nk) { for (int k = 0; k < nk; k++) if (a.v[k] != b.v[k]) return false; return true; }
+
+// prm: the switches of the nonlinear model (trajectory).  pp (optional): the perturbation-side switches of the TL/AD model
+// (model_tlmadm/sw_core_tlm.F90 D_SW_TLM :1047): where the two differ, the operator is evaluated twice -- with pp for the
+// perturbation (linearised about the same inputs) and with prm, on detached inputs, for the trajectory -- and spliced.
 DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w, int uc, int vc, int ua, int va, int divg_d,
-                  const DswParams& prm, int nk, const std::string& tag) {
+                  const DswParams& prm, int nk, const std::string& tag, const DswParams* pp_) {
   auto nm = [&](const char* s) { return tag + "." + s; };
   const double da_min_c = P.dv->m.da_min_c;
+  const DswParams& pp = pp_ ? *pp_ : prm;
+  const bool split_damp = pp_ && pp_->split_damp;
+  auto D = [&](int id) { return P.detached(id); };
+  auto splice = [&](int a, int b, const std::string& name) {
+    int o = P.val(name, P.vals[a].nk);
+    P.add<S_splice>("splice", {0}, {a, b}, {o}, P.vals[a].nk);
+    return o;
+  };
   DswOut o;
   // contravariant winds, Courant numbers, flux areas
   int ut0 = P.val(nm("ut0"), nk), vt0 = P.val(nm("vt0"), nk), ut = P.val(nm("ut"), nk), vt = P.val(nm("vt"), nk);
@@ -67,7 +81,19 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
   int ra_x = P.val(nm("ra_x"), nk), ra_y = P.val(nm("ra_y"), nk);
   P.add<S_ra>("ra", {0}, {o.xfx, o.yfx}, {ra_x, ra_y}, nk);
   // mass
-  TpOut fdp = build_tp_damped(P, mo, delp, o.crx, o.cry, o.xfx, o.yfx, ra_x, ra_y, -1, -1, -1, prm.hord_dp, prm.nord_v, prm.damp_v, nk, tag + ".tp_dp");
+  // one transport site (:1664-1682): q is transported once when both sides use the same scheme, else twice
+  auto tp_site = [&](int q, int mfx, int mfy, int mass, bool same, const LevOrd& ho_p, const LevOrd& no_p, const LevD& da_p,
+                     const LevOrd& ho_t, const LevOrd& no_t, const LevD& da_t, const std::string& tg) -> TpOut {
+    if (same) return build_tp_damped(P, mo, q, o.crx, o.cry, o.xfx, o.yfx, ra_x, ra_y, mfx, mfy, mass, ho_t, no_t, da_t, nk, tg);
+    P.tl_only = true;
+    TpOut a = build_tp_damped(P, mo, q, o.crx, o.cry, o.xfx, o.yfx, ra_x, ra_y, mfx, mfy, mass, ho_p, no_p, da_p, nk, tg + ".p");
+    P.tl_only = false;
+    TpOut b = build_tp_damped(P, mo, D(q), D(o.crx), D(o.cry), D(o.xfx), D(o.yfx), D(ra_x), D(ra_y), D(mfx), D(mfy), D(mass), ho_t, no_t, da_t, nk, tg + ".t");
+    return {splice(a.fx, b.fx, tg + ".fx"), splice(a.fy, b.fy, tg + ".fy")};
+  };
+  LevD nodamp; for (int k = 0; k < 96; k++) nodamp.v[k] = 0.0;
+  TpOut fdp = tp_site(delp, -1, -1, -1, same_ord(prm.hord_dp, pp.hord_dp, nk) && !split_damp, pp.hord_dp, pp.nord_v, pp.damp_v,
+                      prm.hord_dp, prm.nord_v, prm.damp_v, tag + ".tp_dp");
   o.fx = fdp.fx; o.fy = fdp.fy;
   // w
   const int nh = prm.hydrostatic ? 0 : 1;
@@ -81,57 +107,97 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
     for (int k = 0; k < nk; k++)
       if (prm.damp_w.v[k] > 1.e-5) { nw.v[k] = prm.nord_w.v[k]; d4.v[k] = pow(prm.damp_w.v[k] * da_min_c, (double)(prm.nord_w.v[k] + 1)); dw_on.v[k] = 1.0; any = true; }
     if (any) { auto f = build_deln(P, mo, w, nw, d4, nk, tag + ".del6w"); fx2w = f.first; fy2w = f.second; }
-    TpOut fw = build_fv_tp_2d(P, mo, w, o.crx, o.cry, o.xfx, o.yfx, ra_x, ra_y, o.fx, o.fy, prm.hord_vt, nk, tag + ".tp_w");
+    TpOut fw = tp_site(w, o.fx, o.fy, -1, same_ord(prm.hord_vt, pp.hord_vt, nk), pp.hord_vt, pp.nord_v, nodamp, prm.hord_vt, prm.nord_v, nodamp, tag + ".tp_w");
     gxw = fw.fx; gyw = fw.fy;
   }
   // pt
-  TpOut fpt = build_tp_damped(P, mo, pt, o.crx, o.cry, o.xfx, o.yfx, ra_x, ra_y, o.fx, o.fy, delp, prm.hord_tm, prm.nord_t, prm.damp_t, nk, tag + ".tp_pt");
+  TpOut fpt = tp_site(pt, o.fx, o.fy, delp, same_ord(prm.hord_tm, pp.hord_tm, nk) && !split_damp, pp.hord_tm, pp.nord_t, pp.damp_t,
+                      prm.hord_tm, prm.nord_t, prm.damp_t, tag + ".tp_pt");
   o.delp = P.val(nm("delp"), nk); o.pt = P.val(nm("pt"), nk); o.w = P.val(nm("w"), nk);
   P.add<S_dupd>("dupd", {nh, dw_on}, {delp, pt, w, o.fx, o.fy, fpt.fx, fpt.fy, gxw, gyw, fx2w, fy2w}, {o.delp, o.pt, o.w}, nk);
   // kinetic energy
   int vb = P.val(nm("vb"), nk), ub = P.val(nm("ub"), nk), ubf = P.val(nm("ubf"), nk), vbf = P.val(nm("vbf"), nk), ke = P.val(nm("ke"), nk);
   P.add<S_dvbub>("dvbub", {prm.dt}, {ut, vt, uc, vc}, {vb, ub}, nk);
-  P.add<S_tpuv<1>>("ytp_v", {prm.hord_mt}, {vb, v}, {ubf}, nk);
-  P.add<S_tpuv<0>>("xtp_u", {prm.hord_mt}, {ub, u}, {vbf}, nk);
+  if (same_ord(prm.hord_mt, pp.hord_mt, nk)) {
+    P.add<S_tpuv<1>>("ytp_v", {prm.hord_mt}, {vb, v}, {ubf}, nk);
+    P.add<S_tpuv<0>>("xtp_u", {prm.hord_mt}, {ub, u}, {vbf}, nk);
+  } else {   // :1987-1997, :2059-2068
+    int ya = P.val(nm("ubf.p"), nk), yb = P.val(nm("ubf.t"), nk), xa = P.val(nm("vbf.p"), nk), xb = P.val(nm("vbf.t"), nk);
+    P.tl_only = true;
+    P.add<S_tpuv<1>>("ytp_v", {pp.hord_mt}, {vb, v}, {ya}, nk);
+    P.add<S_tpuv<0>>("xtp_u", {pp.hord_mt}, {ub, u}, {xa}, nk);
+    P.tl_only = false;
+    P.add<S_tpuv<1>>("ytp_v", {prm.hord_mt}, {D(vb), D(v)}, {yb}, nk);
+    P.add<S_tpuv<0>>("xtp_u", {prm.hord_mt}, {D(ub), D(u)}, {xb}, nk);
+    P.add<S_splice>("splice", {0}, {ya, yb}, {ubf}, nk);
+    P.add<S_splice>("splice", {0}, {xa, xb}, {vbf}, nk);
+  }
   P.add<S_dke>("dke", {prm.dt}, {vb, ubf, ub, vbf, ut, vt, u, v}, {ke}, nk);
   // relative vorticity
   int wk = P.val(nm("wk"), nk);
   P.add<S_relvort>("relvort", {0}, {u, v}, {wk}, nk);
-  // divergence damping
-  int delpc0 = P.val(nm("delpc0"), nk), vq = P.val(nm("vq0"), nk), dd = divg_d;
-  bool any0 = false; int nmax = 0;
-  for (int k = 0; k < nk; k++) { if (prm.nord.v[k] == 0) any0 = true; nmax = std::max(nmax, (int)prm.nord.v[k]); }
-  if (any0) P.add<S_ddiv0>("ddiv0", {prm.nord}, {u, v, ua, va, uc, vc}, {delpc0}, nk);
-  if (nmax > 0) {
-    for (int it = 1; it <= nmax; it++) {
-      const bool fill_c = (nmax - it) != 0;
-      int vcw = P.val(nm("dd_vc"), nk), ucw = P.val(nm("dd_uc"), nk), ddn = P.val(nm("dd"), nk);
-      if (fill_c) add_patch(P, "fill_corners_bx", &mo.fcb_x, {dd});
-      P.add<S_dd_grad<0>>("dd_vc", {prm.nord, it}, {dd}, {vcw}, nk);
-      if (fill_c) add_patch(P, "fill_corners_by", &mo.fcb_y, {dd});
-      P.add<S_dd_grad<1>>("dd_uc", {prm.nord, it}, {dd}, {ucw}, nk);
-      if (fill_c) add_patch(P, "fill_corners_dvec", &mo.fc_dgrid_vec, {vcw, ucw});
-      P.add<S_dd_div>("dd_div", {prm.nord, it}, {ucw, vcw, dd}, {ddn}, nk);
-      dd = ddn;
+  // divergence damping (compute_divergence_damping, :1264-1434; split_damp: :2341-2366)
+  auto div_damp = [&](const DswParams& q, int u, int v, int ua, int va, int uc, int vc, int divg_d, int wk, const std::string& tg) -> int {
+    auto nm = [&](const char* s) { return tg + "." + s; };
+    int delpc0 = P.val(nm("delpc0"), nk), vq = P.val(nm("vq0"), nk), dd = divg_d;
+    bool any0 = false; int nmax = 0;
+    for (int k = 0; k < nk; k++) { if (q.nord.v[k] == 0) any0 = true; nmax = std::max(nmax, (int)q.nord.v[k]); }
+    if (any0) P.add<S_ddiv0>("ddiv0", {q.nord}, {u, v, ua, va, uc, vc}, {delpc0}, nk);
+    if (nmax > 0) {
+      for (int it = 1; it <= nmax; it++) {
+        const bool fill_c = (nmax - it) != 0;
+        int vcw = P.val(nm("dd_vc"), nk), ucw = P.val(nm("dd_uc"), nk), ddn = P.val(nm("dd"), nk);
+        if (fill_c) add_patch(P, "fill_corners_bx", &mo.fcb_x, {dd});
+        P.add<S_dd_grad<0>>("dd_vc", {q.nord, it}, {dd}, {vcw}, nk);
+        if (fill_c) add_patch(P, "fill_corners_by", &mo.fcb_y, {dd});
+        P.add<S_dd_grad<1>>("dd_uc", {q.nord, it}, {dd}, {ucw}, nk);
+        if (fill_c) add_patch(P, "fill_corners_dvec", &mo.fc_dgrid_vec, {vcw, ucw});
+        P.add<S_dd_div>("dd_div", {q.nord, it}, {ucw, vcw, dd}, {ddn}, nk);
+        dd = ddn;
+      }
+      if (q.dddmp >= 1.e-5) vq = build_a2b_ord4(P, mo, wk, nk, tg + ".a2b");
     }
-    if (prm.dddmp >= 1.e-5) vq = build_a2b_ord4(P, mo, wk, nk, tag + ".a2b");
+    int vd = P.val(nm("vd"), nk);
+    P.add<S_ddamp>("ddamp", {q.nord, q.d2_bg, q.dddmp, q.d4_bg, q.dt}, {delpc0, divg_d, vq, dd}, {vd}, nk);
+    return vd;
+  };
+  int vd;
+  if (!split_damp) vd = div_damp(prm, u, v, ua, va, uc, vc, divg_d, wk, tag);
+  else {
+    P.tl_only = true;
+    int a = div_damp(pp, u, v, ua, va, uc, vc, divg_d, wk, tag + ".dd_p");
+    P.tl_only = false;
+    int b = div_damp(prm, D(u), D(v), D(ua), D(va), D(uc), D(vc), D(divg_d), D(wk), tag + ".dd_t");
+    vd = splice(a, b, tag + ".vd");
   }
-  int vd = P.val(nm("vd"), nk);
-  P.add<S_ddamp>("ddamp", {prm.nord, prm.d2_bg, prm.dddmp, prm.d4_bg, prm.dt}, {delpc0, divg_d, vq, dd}, {vd}, nk);
   // vorticity transport
   int avort = P.val(nm("avort"), nk);
   P.add<S_absvort>("absvort", {0}, {wk}, {avort}, nk);
-  TpOut fv = build_fv_tp_2d(P, mo, avort, o.crx, o.cry, o.xfx, o.yfx, ra_x, ra_y, -1, -1, prm.hord_vt, nk, tag + ".tp_vort");
-  // vorticity damping
+  TpOut fv = tp_site(avort, -1, -1, -1, same_ord(prm.hord_vt, pp.hord_vt, nk), pp.hord_vt, pp.nord_v, nodamp, prm.hord_vt, prm.nord_v, nodamp, tag + ".tp_vort");
+  // vorticity damping: the trajectory with (nord_v, damp_v), the perturbation with the perturbation-side pair (:2436-2451)
   int ut3 = wk, vt3 = wk;
   LevD vd_on; for (int k = 0; k < 96; k++) vd_on.v[k] = 0.0;
   {
-    LevOrd nv; LevD d4; bool any = false;
-    for (int k = 0; k < 128; k++) nv.v[k] = -1;
-    for (int k = 0; k < 96; k++) d4.v[k] = 0.0;
-    for (int k = 0; k < nk; k++)
-      if (prm.damp_v.v[k] > 1.e-5) { nv.v[k] = prm.nord_v.v[k]; d4.v[k] = pow(prm.damp_v.v[k] * da_min_c, (double)(prm.nord_v.v[k] + 1)); vd_on.v[k] = 1.0; any = true; }
-    if (any) { auto f = build_deln(P, mo, wk, nv, d4, nk, tag + ".del6v"); ut3 = f.first; vt3 = f.second; }
+    auto del6v = [&](const DswParams& q, int wk, LevD* on, const std::string& tg) -> std::pair<int, int> {
+      LevOrd nv; LevD d4; bool any = false;
+      for (int k = 0; k < 128; k++) nv.v[k] = -1;
+      for (int k = 0; k < 96; k++) d4.v[k] = 0.0;
+      for (int k = 0; k < nk; k++)
+        if (q.damp_v.v[k] > 1.e-5) { nv.v[k] = q.nord_v.v[k]; d4.v[k] = pow(q.damp_v.v[k] * da_min_c, (double)(q.nord_v.v[k] + 1)); on->v[k] = 1.0; any = true; }
+      if (!any) return {wk, wk};
+      return build_deln(P, mo, wk, nv, d4, nk, tg);
+    };
+    if (same_ord(prm.nord_v, pp.nord_v, nk) && same_lev(prm.damp_v, pp.damp_v, nk)) {
+      auto f = del6v(prm, wk, &vd_on, tag + ".del6v"); ut3 = f.first; vt3 = f.second;
+    } else {
+      LevD on_p; for (int k = 0; k < 96; k++) on_p.v[k] = 0.0;
+      P.tl_only = true;
+      auto a = del6v(pp, wk, &on_p, tag + ".del6v_p");
+      P.tl_only = false;
+      auto b = del6v(prm, D(wk), &vd_on, tag + ".del6v_t");
+      if (!same_lev(on_p, vd_on, nk)) throw std::runtime_error("d_sw: vorticity damping must be switched on for the same levels on the trajectory and perturbation sides");
+      if (a.first != wk) { ut3 = splice(a.first, b.first, tag + ".ut3"); vt3 = splice(a.second, b.second, tag + ".vt3"); }
+    }
   }
   o.u = P.val(nm("u"), nk); o.v = P.val(nm("v"), nk);
   P.add<S_duv>("duv", {vd_on}, {u, v, ke, vd, fv.fx, fv.fy, ut3, vt3}, {o.u, o.v}, nk);
@@ -148,18 +214,31 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
   return o;
 }
 
-void fill_dsw_params(DswParams& d, const ModuleParams& prm, int K) {
-  auto LO = [&](const char* base, int dflt, bool is_hord = false) {
+// pre: "" for the trajectory-side switches, "p." for the perturbation side (which default to the trajectory's)
+void fill_dsw_params(DswParams& d, const ModuleParams& prm, int K, const std::string& pre = "") {
+  auto LO = [&](const char* base0, int dflt, bool is_hord = false) {
     auto enc = [&](int v) { return is_hord ? enc_hord(v) : v; };
+    const std::string bs = pre + base0; const char* base = bs.c_str();
+    if (!pre.empty()) dflt = prm.geti(base0, dflt);
     LevOrd o; int v = prm.geti(base, dflt);
     for (int k = 0; k < 128; k++) o.v[k] = (signed char)enc(v);
-    for (int k = 0; k < K; k++) { std::string key = std::string(base) + "@" + std::to_string(k); if (prm.v.count(key)) o.v[k] = (signed char)enc(prm.geti(key, v)); }
+    for (int k = 0; k < K; k++) {
+      std::string key = std::string(base) + "@" + std::to_string(k), key0 = std::string(base0) + "@" + std::to_string(k);
+      if (prm.v.count(key)) o.v[k] = (signed char)enc(prm.geti(key, v));
+      else if (!pre.empty() && !prm.v.count(base) && prm.v.count(key0)) o.v[k] = (signed char)enc(prm.geti(key0, v));
+    }
     return o;
   };
-  auto LD = [&](const char* base, double dflt) {
+  auto LD = [&](const char* base0, double dflt) {
+    const std::string bs = pre + base0; const char* base = bs.c_str();
+    if (!pre.empty()) dflt = prm.get(base0, dflt);
     LevD o; double v = prm.get(base, dflt);
     for (int k = 0; k < 96; k++) o.v[k] = v;
-    for (int k = 0; k < K; k++) { std::string key = std::string(base) + "@" + std::to_string(k); if (prm.v.count(key)) o.v[k] = prm.get(key, v); }
+    for (int k = 0; k < K; k++) {
+      std::string key = std::string(base) + "@" + std::to_string(k), key0 = std::string(base0) + "@" + std::to_string(k);
+      if (prm.v.count(key)) o.v[k] = prm.get(key, v);
+      else if (!pre.empty() && !prm.v.count(base) && prm.v.count(key0)) o.v[k] = prm.get(key0, v);
+    }
     return o;
   };
   d.hord_mt = LO("hord_mt", 2, true); d.hord_vt = LO("hord_vt", 2, true); d.hord_tm = LO("hord_tm", 2, true); d.hord_dp = LO("hord_dp", 2, true);
@@ -167,8 +246,9 @@ void fill_dsw_params(DswParams& d, const ModuleParams& prm, int K) {
   d.d2_bg = LD("d2_bg", 0.015); d.damp_v = LD("damp_v", 0.0005); d.damp_w = LD("damp_w", 0.0005); d.damp_t = LD("damp_t", 0.0005);
   d.d_con = LD("d_con", 0.0);
   d.heat = false; for (int k = 0; k < K; k++) if (d.d_con.v[k] > 1.e-5) d.heat = true;
-  d.dddmp = prm.get("dddmp", 0.2); d.d4_bg = prm.get("d4_bg", 0.15); d.dt = prm.get("dt", 450.0);
+  d.dddmp = prm.get(pre + "dddmp", prm.get("dddmp", 0.2)); d.d4_bg = prm.get(pre + "d4_bg", prm.get("d4_bg", 0.15)); d.dt = prm.get("dt", 450.0);
   d.hydrostatic = prm.geti("hydrostatic", 1) != 0;
+  d.split_damp = prm.geti("split_damp", 0) != 0;
 }
 
 void mod_d_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
@@ -176,7 +256,10 @@ void mod_d_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
   int delp = io.in(P, "delp", K), pt = io.in(P, "pt", K), u = io.in(P, "u", K), v = io.in(P, "v", K), w = io.in(P, "w", K);
   int uc = io.in(P, "uc", K), vc = io.in(P, "vc", K), ua = io.in(P, "ua", K), va = io.in(P, "va", K), divg_d = io.in(P, "divg_d", K);
   DswParams d; fill_dsw_params(d, prm, K);
-  DswOut o = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, ua, va, divg_d, d, K, "dsw");
+  bool has_pert = prm.geti("split_damp", 0) != 0;
+  for (auto& kv : prm.v) if (kv.first.rfind("p.", 0) == 0) has_pert = true;
+  DswParams dp; if (has_pert) fill_dsw_params(dp, prm, K, "p.");
+  DswOut o = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, ua, va, divg_d, d, K, "dsw", has_pert ? &dp : nullptr);
   io.out(P, "delp_n", o.delp); io.out(P, "pt_n", o.pt); io.out(P, "u_n", o.u); io.out(P, "v_n", o.v); io.out(P, "w_n", o.w);
   io.out(P, "fx", o.fx); io.out(P, "fy", o.fy); io.out(P, "crx", o.crx); io.out(P, "cry", o.cry); io.out(P, "xfx", o.xfx); io.out(P, "yfx", o.yfx);
   if (o.heat >= 0) io.out(P, "heat", o.heat);

@@ -34,7 +34,9 @@ void level_params(const DynConfig& c, int K, DswParams& d) {
         d_con_k = 0.0;
       }
     }
-    const bool sp = k <= c.n_sponge_ord;
+    // (two-sided mode: hord_ks_traj puts first-order transport into the top n_sponge_pert - 1 layers of the trajectory too,
+    // dyn_core_tlm.F90:862-869)
+    const bool sp = k <= c.n_sponge_ord || (c.pert.on && c.pert.hord_ks_traj && k <= c.pert.n_sponge - 1);
     d.hord_mt.v[k - 1] = sp ? 1 : enc_hord(c.hord_mt); d.hord_vt.v[k - 1] = sp ? 1 : enc_hord(c.hord_vt);
     d.hord_tm.v[k - 1] = sp ? 1 : enc_hord(c.hord_tm); d.hord_dp.v[k - 1] = sp ? 1 : enc_hord(c.hord_dp);
     d.nord.v[k - 1] = nord_k; d.nord_v.v[k - 1] = nord_v; d.nord_w.v[k - 1] = nord_w; d.nord_t.v[k - 1] = nord_t;
@@ -42,6 +44,33 @@ void level_params(const DynConfig& c, int K, DswParams& d) {
     d.d2_bg.v[k - 1] = d2; d.damp_v.v[k - 1] = damp_vt; d.damp_w.v[k - 1] = damp_w; d.damp_t.v[k - 1] = damp_t;
   }
   d.dddmp = c.dddmp; d.d4_bg = c.d4_bg; d.hydrostatic = c.hydrostatic;
+}
+
+bool level_params_pert(const DynConfig& c, int K, DswParams& d) {
+  if (!c.pert.on) return false;
+  const DynConfig::PertSide& q = c.pert;
+  level_params(c, K, d);                 // dt, hydrostatic, d_con follow the trajectory side
+  d.split_damp = q.split_damp;
+  d.dddmp = q.dddmp; d.d4_bg = q.d4_bg;
+  for (int k = 1; k <= K; k++) {
+    int hm = q.hord_mt, hv = q.hord_vt, ht = q.hord_tm, hp = q.hord_dp;
+    int nord_k = q.nord, nord_v = std::min(2, q.nord);
+    double d2 = std::min(0.20, q.d2_bg);
+    double damp_vt = q.do_vort_damp ? q.vtdm4 : 0.0;
+    int nord_w = nord_v, nord_t = nord_v; double damp_w = damp_vt, damp_t = damp_vt;
+    if (k <= q.n_sponge) {               // sponge layers of the perturbation
+      if (k <= q.n_sponge - 1 && q.hord_ks_pert) hm = hv = ht = hp = 1;
+      nord_k = 0;
+      const double dk = k == 1 ? q.d2_bg_k1 : k == 2 ? q.d2_bg_k2 : q.d2_bg_ks;
+      d2 = std::max(0.01, std::max(q.d2_bg, dk));
+      nord_w = 0; damp_w = d2;
+      if (q.do_vort_damp) { nord_v = 0; damp_vt = 0.5 * d2; }
+    }
+    d.hord_mt.v[k - 1] = enc_hord(hm); d.hord_vt.v[k - 1] = enc_hord(hv); d.hord_tm.v[k - 1] = enc_hord(ht); d.hord_dp.v[k - 1] = enc_hord(hp);
+    d.nord.v[k - 1] = nord_k; d.nord_v.v[k - 1] = nord_v; d.nord_w.v[k - 1] = nord_w; d.nord_t.v[k - 1] = nord_t;
+    d.d2_bg.v[k - 1] = d2; d.damp_v.v[k - 1] = damp_vt; d.damp_w.v[k - 1] = damp_w; d.damp_t.v[k - 1] = damp_t;
+  }
+  return true;
 }
 
 int build_del2_cubed(Program& P, Mosaic& mo, int q, double cd, int nmax, int nk, const std::string& tag) {
@@ -86,6 +115,7 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, co
   const double dt = c.bdt / c.n_split, dt2 = 0.5 * dt;
   if (!c.hydrostatic) throw std::runtime_error("build_dyn_core: non-hydrostatic path is built by build_dyn_core_nh");
   DswParams dp; level_params(c, K, dp); dp.dt = dt;
+  DswParams dpp; const bool two = level_params_pert(c, K, dpp); dpp.dt = dt;
   DynOut o;
   int u = s.u, v = s.v, pt = s.pt, delp = s.delp, w = s.w;
   int mfx = -1, mfy = -1, cx = -1, cy = -1, heat = -1;
@@ -99,7 +129,7 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, co
     int uc = P.val(tg + ".uc", K), vc = P.val(tg + ".vc", K);
     P.add<S_pgrad_c>("p_grad_c", {dt2, 1}, {cs.uc, cs.vc, pkc, gz, cs.delpc}, {uc, vc}, K);
     add_patch(P, "halo_ucvc", &mo.h_cgrid, {uc, vc});
-    DswOut ds = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, cs.ua, cs.va, cs.divg_d, dp, K, tg + ".dsw");
+    DswOut ds = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, cs.ua, cs.va, cs.divg_d, dp, K, tg + ".dsw", two ? &dpp : nullptr);
     // flux capacitors (d_sw :913-931)
     if (mfx < 0) { mfx = ds.fx; mfy = ds.fy; cx = ds.crx; cy = ds.cry; }
     else {
@@ -152,6 +182,25 @@ void dyn_config_from(DynConfig& c, const ModuleParams& prm) {
   c.a_imp = prm.get("a_imp", f->a_imp != 0.0 ? f->a_imp : 1.0);
   c.p_fac = prm.get("p_fac", f->p_fac != 0.0 ? f->p_fac : 0.05);
   c.d_con = prm.get("d_con", f->d_con);
+  if (prm.geti("two_sided", f->two_sided)) {
+    // the main fields are the perturbation model's switches; the trajectory side comes from cfg.traj (module params: "t.<name>")
+    DynConfig::PertSide& q = c.pert;
+    q.on = true;
+    q.split_damp = prm.geti("split_damp", f->split_damp) != 0;
+    q.hord_ks_pert = prm.geti("hord_ks_pert", f->hord_ks_pert) != 0; q.hord_ks_traj = prm.geti("hord_ks_traj", f->hord_ks_traj) != 0;
+    q.hord_mt = c.hord_mt; q.hord_vt = c.hord_vt; q.hord_tm = c.hord_tm; q.hord_dp = c.hord_dp; q.hord_tr = c.hord_tr;
+    q.nord = c.nord; q.n_sponge = c.n_sponge; q.do_vort_damp = c.do_vort_damp;
+    q.d2_bg = c.d2_bg; q.d2_bg_k1 = c.d2_bg_k1; q.d2_bg_k2 = c.d2_bg_k2; q.d2_bg_ks = prm.get("d2_bg_ks", f->d2_bg_ks);
+    q.d4_bg = c.d4_bg; q.dddmp = c.dddmp; q.vtdm4 = c.vtdm4;
+    c.hord_mt = prm.geti("t.hord_mt", f->traj.hord_mt); c.hord_vt = prm.geti("t.hord_vt", f->traj.hord_vt);
+    c.hord_tm = prm.geti("t.hord_tm", f->traj.hord_tm); c.hord_dp = prm.geti("t.hord_dp", f->traj.hord_dp);
+    c.hord_tr = prm.geti("t.hord_tr", f->traj.hord_tr);
+    c.nord = prm.geti("t.nord", f->traj.nord); c.do_vort_damp = prm.geti("t.do_vort_damp", f->traj.do_vort_damp) != 0;
+    c.n_sponge = prm.geti("t.n_sponge", f->traj.n_sponge);
+    c.dddmp = prm.get("t.dddmp", f->traj.dddmp); c.d2_bg = prm.get("t.d2_bg", f->traj.d2_bg); c.d4_bg = prm.get("t.d4_bg", f->traj.d4_bg);
+    c.vtdm4 = prm.get("t.vtdm4", f->traj.vtdm4); c.d2_bg_k1 = prm.get("t.d2_bg_k1", f->traj.d2_bg_k1); c.d2_bg_k2 = prm.get("t.d2_bg_k2", f->traj.d2_bg_k2);
+    c.n_sponge_ord = 0;
+  }
 }
 
 void mod_del2_cubed(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {

@@ -20,12 +20,21 @@ struct DynConfig {
   double ptop = 1.0, akap = 2.0 / 7.0, cp_air = 1004.6, rdgas = 287.05, grav = 9.80665, zvir = 0.6078;
   double a_imp = 1.0, p_fac = 0.05;
   double d_con = 0.0, delt_max = 1.0;   // dissipative heating (model/fv_arrays_nlm.F90:409-411); convert_ke = F, ke_bg = 0
+  // Two-sided mode: the members above are the nonlinear model's switches (trajectory), `pert` the perturbation model's
+  // (model_tlmadm/fv_arrays_tlmadm.F90:37-92)
+  struct PertSide {
+    bool on = false, split_damp = false, hord_ks_pert = true, hord_ks_traj = true, do_vort_damp = true;
+    int hord_mt = 2, hord_vt = 2, hord_tm = 2, hord_dp = 2, hord_tr = 2, nord = 1, n_sponge = 0;
+    double d2_bg = 0.015, d2_bg_k1 = 4.0, d2_bg_k2 = 2.0, d2_bg_ks = 2.0, d4_bg = 0.15, dddmp = 0.2, vtdm4 = 0.0005;
+  } pert;
 };
 
 struct DynState { int u, v, w, delz, pt, delp, phis; };
 struct DynOut { int u, v, w, delz, pt, delp, mfx, mfy, cx, cy, pkz, pe, peln, pk, ws; };
 
 void level_params(const DynConfig& c, int K, DswParams& d);
+// perturbation-side per-level switches (model_tlmadm/dyn_core_tlm.F90:835-921); false when the configuration is one-sided
+bool level_params_pert(const DynConfig& c, int K, DswParams& d);
 // del2_cubed(q, cd, nmax): returns the filtered field (q's halo is exchanged in place first)
 int build_del2_cubed(Program& P, Mosaic& mo, int q, double cd, int nmax, int nk, const std::string& tag);
 // end of dyn_core (model/dyn_core_nlm.F90:1052-1099): filter the accumulated heat source, add it to pt.  aux = pkz (hydrostatic) or delz

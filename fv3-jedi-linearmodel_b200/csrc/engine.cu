@@ -101,10 +101,19 @@ void Program::analyse() {
     for (int i : ops[n].in) vals[i].last_use = n;
     for (int o : ops[n].out) { if (vals[o].first_def < 0) vals[o].first_def = n; vals[o].last_use = std::max(vals[o].last_use, n); }
   }
+  // a detached view never carries a perturbation and keeps its target alive (it borrows the storage): the ops reading a view
+  // count as uses of the target, which is released with them
+  for (auto& v : vals) if (v.alias >= 0) v.active = false;
+  for (int n = 0; n < (int)ops.size(); n++) {
+    ops[n].hold.clear();
+    for (int i : ops[n].in)
+      if (vals[i].alias >= 0) { ops[n].hold.push_back(vals[i].alias); vals[vals[i].alias].last_use = std::max(vals[vals[i].alias].last_use, n); }
+  }
 }
 
 void Program::ensure_traj(int id) {
   Value& v = vals[id];
+  if (v.alias >= 0) { v.traj = vals[v.alias].traj; return; }
   if (!v.traj) {
     if (v.external) throw std::runtime_error("external value without storage: " + v.name);
     // intermediates are only defined on the range their producer writes and consumers only read
@@ -129,11 +138,14 @@ void Program::ensure_pert(int id, bool zero_it) {
 void Program::release(int id) {
   Value& v = vals[id];
   if (v.external) return;
+  if (v.alias >= 0) { v.traj = nullptr; return; }   // borrowed storage
   if (v.traj) { dv->pool.put(v.traj); v.traj = nullptr; }
   if (v.pert) { dv->pool.put(v.pert); v.pert = nullptr; }
 }
 
 void Program::run_op(Op& op, int mode) {
+  if (op.tl_only && mode == MODE_NL) return;          // perturbation-scheme chain: nothing of it is needed by a trajectory sweep
+  for (int i : op.in) if (vals[i].alias >= 0) vals[i].traj = vals[vals[i].alias].traj;
 #ifdef FV3LM_HOST_EMU
   static const bool nancheck = getenv("FV3LM_NANCHECK") != nullptr;
   if (nancheck && mode == MODE_AD) {
@@ -196,7 +208,7 @@ bool Program::ad_fits_store_all() {
   if (ad_store_all_cached >= 0) return ad_store_all_cached != 0;     // decided once: the sweep structure must not change between runs
   double need = 0.0;
   for (int id = 0; id < (int)vals.size(); id++) {
-    if (vals[id].external) continue;
+    if (vals[id].external || vals[id].alias >= 0) continue;
     need += (double)val_doubles(id) * 8.0 * (vals[id].active ? 2.0 : 1.0);
   }
   double budget = dv->ad_store_budget;
@@ -213,10 +225,13 @@ void Program::run(Mode mode) {
   if (mode == MODE_NL || mode == MODE_TL) {
     for (int n = 0; n < nop; n++) {
       Op& op = ops[n];
-      for (int o : op.out) { ensure_traj(o); if (mode == MODE_TL) ensure_pert(o, false); }
-      run_op(op, mode);
+      if (!(op.tl_only && mode == MODE_NL)) {     // (a skipped op still ends the life of its inputs)
+        for (int o : op.out) { ensure_traj(o); if (mode == MODE_TL) ensure_pert(o, false); }
+        run_op(op, mode);
+      }
       // free values whose last use was this op
       for (int i : op.in) if (vals[i].last_use == n) release(i);
+      for (int i : op.hold) if (vals[i].last_use == n) release(i);
       for (int o : op.out) if (vals[o].last_use == n) release(o);
     }
   } else if (!seg_start.empty() && !ad_fits_store_all()) {
@@ -236,7 +251,7 @@ void Program::run(Mode mode) {
     if (ad_keep_from < 0) {
       std::vector<double> seg_bytes(nseg, 0.0);
       for (int id = 0; id < (int)vals.size(); id++)
-        if (!vals[id].external && vals[id].first_def >= 0) seg_bytes[seg_of[vals[id].first_def]] += (double)val_doubles(id) * 8.0;
+        if (!vals[id].external && vals[id].alias < 0 && vals[id].first_def >= 0) seg_bytes[seg_of[vals[id].first_def]] += (double)val_doubles(id) * 8.0;
       double largest = 0.0; for (double b : seg_bytes) largest = std::max(largest, b);
       double budget = dv->ad_store_budget;
       if (const char* e = getenv("FV3LM_AD_STORE_BUDGET")) budget = atof(e);
@@ -250,11 +265,14 @@ void Program::run(Mode mode) {
     // pass 1: plain forward; segment-local values are freed at their last use, boundary-crossing ones stay
     for (int n = 0; n < nop; n++) {
       Op& op = ops[n];
-      for (int o : op.out) ensure_traj(o);
-      // kept segments (at least the last, reversed first) stay whole; their patch ops save what they overwrite
-      run_op(op, seg_of[n] >= keep_from ? MODE_ADFWD : MODE_NL);
+      if (!(op.tl_only && seg_of[n] < keep_from)) {        // (else: recomputed with its segment)
+        for (int o : op.out) ensure_traj(o);
+        // kept segments (at least the last, reversed first) stay whole; their patch ops save what they overwrite
+        run_op(op, seg_of[n] >= keep_from ? MODE_ADFWD : MODE_NL);
+      }
       if (seg_of[n] >= keep_from) continue;
       for (int i : op.in) if (vals[i].last_use == n && def_seg(i) == seg_of[n]) release(i);
+      for (int i : op.hold) if (vals[i].last_use == n && def_seg(i) == seg_of[n]) release(i);
       for (int o : op.out) if (vals[o].last_use == n && def_seg(o) == seg_of[n]) release(o);
     }
     for (int s = nseg - 1; s >= 0; s--) {

@@ -401,6 +401,10 @@ struct Value {
   double* traj = nullptr;
   double* pert = nullptr;  // TL tangent, or AD adjoint
   int first_def = -1, last_use = -1;
+  // >= 0: a DETACHED view of that value -- same trajectory storage, never active.  The trajectory-scheme chain of a split
+  // transport (model_tlmadm/sw_core_tlm.F90:1664-1682: linear scheme for the perturbation, the nonlinear model's scheme
+  // for the trajectory) reads its inputs through such views, so no perturbation / adjoint flows through it.
+  int alias = -1;
 };
 
 struct Device;  // per-handle state (geometry, metrics, pool)
@@ -409,6 +413,8 @@ struct Op {
   std::string name;
   std::vector<int> in, out;
   bool inplace = false;    // patch op: out == in, mutates cells that were dead
+  std::vector<int> hold;   // targets of the detached views among `in`: kept alive up to this op (filled by Program::analyse)
+  bool tl_only = false;    // perturbation-scheme chain of a split transport: its trajectory values are only needed by TL / AD sweeps
   int nk_launch = 1;
   std::function<void(struct Program&, Op&, int /*Mode or 3 = AD reverse*/)> run;
 };
@@ -420,6 +426,17 @@ struct Program {
   std::string name;
   std::vector<int> seg_start;        // op indices where a recompute segment of the adjoint begins
   void mark_segment() { seg_start.push_back((int)ops.size()); }
+  bool tl_only = false;              // builders set this around the ops of a perturbation-scheme chain (copied into Op::tl_only)
+  std::map<int, int> detached_of;
+  int detached(int id) {             // detached view of a value (cached); negative ids (absent optional inputs) pass through
+    if (id < 0) return id;
+    if (vals[id].alias >= 0) return id;
+    auto it = detached_of.find(id);
+    if (it != detached_of.end()) return it->second;
+    Value v; v.name = vals[id].name + "~"; v.nk = vals[id].nk; v.alias = id;
+    vals.push_back(v);
+    return detached_of[id] = (int)vals.size() - 1;
+  }
 
   int val(const std::string& nm, int nk, bool external = false) {
     Value v; v.name = nm; v.nk = nk; v.external = external;
@@ -508,6 +525,22 @@ template <class S> struct KernColAD {
   }
 };
 
+// splice of a split transport: trajectory from the trajectory-scheme chain (input 1, detached), perturbation / adjoint from the
+// perturbation-scheme chain (input 0).  Whole array.   in: a b ; out: (traj b, pert a)
+HD double with_val(double, double v) { return v; }
+HD Dual with_val(Dual a, double v) { a.v = v; return a; }
+template <int M> HD DualN<M> with_val(DualN<M> a, double v) { a.v = v; return a; }
+struct S_splice {
+  static constexpr int NI = 2, NO = 1;
+  struct P { int dummy; };
+  static constexpr int NT = 2;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P&) {
+    if constexpr (X::mode == 0) x.out(0, x.in(1));      // the perturbation chain is skipped in pure trajectory sweeps: input 0 has no storage
+    else x.out(0, with_val(x.in(0), val(x.in(1))));
+  }
+};
+
 struct Device {
   Geom g;
   Metrics m;
@@ -521,7 +554,7 @@ struct Device {
 template <class S>
 void Program::add(const char* nm, const typename S::P& prm, std::vector<int> ins, std::vector<int> outs, int nk_launch) {
   if ((int)ins.size() != S::NI || (int)outs.size() != S::NO) throw std::runtime_error(std::string("arity mismatch in ") + nm);
-  Op op; op.name = nm; op.in = ins; op.out = outs; op.nk_launch = nk_launch;
+  Op op; op.name = nm; op.in = ins; op.out = outs; op.nk_launch = nk_launch; op.tl_only = tl_only;
   typename S::P p = prm;
   op.run = [p](Program& P, Op& o, int mode) {
     const Geom& g = P.dv->g;
@@ -552,7 +585,7 @@ void Program::add(const char* nm, const typename S::P& prm, std::vector<int> ins
 template <class S>
 void add_col(Program& P, const char* nm, const typename S::P& prm, std::vector<int> ins, std::vector<int> outs) {
   if ((int)ins.size() != S::NI || (int)outs.size() != S::NO) throw std::runtime_error(std::string("arity mismatch in ") + nm);
-  Op op; op.name = nm; op.in = ins; op.out = outs; op.nk_launch = 1;
+  Op op; op.name = nm; op.in = ins; op.out = outs; op.nk_launch = 1; op.tl_only = P.tl_only;
   typename S::P p = prm;
   op.run = [p](Program& P, Op& o, int mode) {
     const Geom& g = P.dv->g;

@@ -56,7 +56,8 @@ struct S_trc_upd {
   }
 };
 
-std::vector<int> build_tracer_2d(Program& P, Mosaic& mo, std::vector<int> q, int dp1, int mfx, int mfy, int cx, int cy, int hord_tr, const std::string& tag) {
+std::vector<int> build_tracer_2d(Program& P, Mosaic& mo, std::vector<int> q, int dp1, int mfx, int mfy, int cx, int cy, int hord_tr, const std::string& tag,
+                                 int hord_tr_pert) {
   const int K = P.dv->g.K;
   auto nm = [&](const std::string& s) { return tag + "." + s; };
   int xfx = P.val(nm("xfx"), K), yfx = P.val(nm("yfx"), K), ra_x = P.val(nm("ra_x"), K), ra_y = P.val(nm("ra_y"), K), dp2 = P.val(nm("dp2"), K);
@@ -66,7 +67,19 @@ std::vector<int> build_tracer_2d(Program& P, Mosaic& mo, std::vector<int> q, int
   LevOrd ho; for (int k = 0; k < 128; k++) ho.v[k] = (signed char)enc_hord(hord_tr);
   std::vector<int> out;
   for (size_t n = 0; n < q.size(); n++) {
-    TpOut f = build_fv_tp_2d(P, mo, q[n], cx, cy, xfx, yfx, ra_x, ra_y, mfx, mfy, ho, K, nm("tp_q" + std::to_string(n)));
+    TpOut f;
+    if (hord_tr_pert == 0 || hord_tr_pert == hord_tr) f = build_fv_tp_2d(P, mo, q[n], cx, cy, xfx, yfx, ra_x, ra_y, mfx, mfy, ho, K, nm("tp_q" + std::to_string(n)));
+    else {   // model_tlmadm/fv_tracer2d_tlm.F90:1060-1090: perturbation with hord_tr_pert, trajectory with hord_tr
+      LevOrd hp; for (int k = 0; k < 128; k++) hp.v[k] = (signed char)enc_hord(hord_tr_pert);
+      auto D = [&](int id) { return P.detached(id); };
+      P.tl_only = true;
+      TpOut a = build_fv_tp_2d(P, mo, q[n], cx, cy, xfx, yfx, ra_x, ra_y, mfx, mfy, hp, K, nm("tp_q" + std::to_string(n) + "_p"));
+      P.tl_only = false;
+      TpOut b = build_fv_tp_2d(P, mo, D(q[n]), D(cx), D(cy), D(xfx), D(yfx), D(ra_x), D(ra_y), D(mfx), D(mfy), ho, K, nm("tp_q" + std::to_string(n) + "_t"));
+      f.fx = P.val(nm("fx_q" + std::to_string(n)), K); f.fy = P.val(nm("fy_q" + std::to_string(n)), K);
+      P.add<S_splice>("splice", {0}, {a.fx, b.fx}, {f.fx}, K);
+      P.add<S_splice>("splice", {0}, {a.fy, b.fy}, {f.fy}, K);
+    }
     int qn = P.val(nm("q" + std::to_string(n)), K);
     P.add<S_trc_upd>("trc_upd", {0}, {q[n], dp1, f.fx, f.fy, dp2}, {qn}, K);
     out.push_back(qn);
@@ -299,7 +312,7 @@ FvOut build_fv_dynamics(Program& P, Mosaic& mo, const DynConfig& c, const std::v
     DynOut d = c.hydrostatic ? build_dyn_core(P, mo, cd, ds, tg) : build_dyn_core_nh(P, mo, cd, ak, bk, ds, tg);
     P.mark_segment();
     for (int& x : q) add_patch(P, "halo_q", &mo.h_center, {x});
-    q = build_tracer_2d(P, mo, q, dp1, d.mfx, d.mfy, d.cx, d.cy, c.hord_tr, tg + ".trc");
+    q = build_tracer_2d(P, mo, q, dp1, d.mfx, d.mfy, d.cx, d.cy, c.hord_tr, tg + ".trc", c.pert.on ? c.pert.hord_tr : 0);
     P.mark_segment();
     RemapOut r = build_remap(P, mo, c, ak, bk, d.pe, d.pk, d.peln, d.pt, q, d.u, d.v, n_map == c.k_split, tg + ".rm",
                              d.delp, c.hydrostatic ? -1 : d.w, c.hydrostatic ? -1 : d.delz, c.hydrostatic ? -1 : d.ws);

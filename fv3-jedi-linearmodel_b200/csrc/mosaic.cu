@@ -456,7 +456,7 @@ static void remote_adjoint(Program& P, PatchMap* map, Comm* comm, double* const 
 
 void add_patch(Program& P, const char* nm, PatchMap* map, std::vector<int> fields) {
   Comm* comm = map->comm;
-  Op op; op.name = nm; op.in = fields; op.out = fields; op.inplace = true; op.nk_launch = 1;
+  Op op; op.name = nm; op.in = fields; op.out = fields; op.inplace = true; op.nk_launch = 1; op.tl_only = P.tl_only;
   auto scratch = std::make_shared<double*>(nullptr);
   op.run = [map, scratch, comm](Program& P, Op& o, int mode) {
     const Geom& g = P.dv->g;

@@ -85,7 +85,7 @@ std::pair<int, int> build_update_dz_c(Program& P, Mosaic& mo, const LevD& dp0, d
 
 // update_dz_d (model/nh_utils_nlm.F90:183-296).  zh is patched in place (copy_corners); returns {zh_new, ws}
 std::pair<int, int> build_update_dz_d(Program& P, Mosaic& mo, const LevD& dp0, const DswParams& dp, int hord_tm, double rdt, int zs, int zh,
-                                      int crx, int cry, int xfx, int yfx, const std::string& tag) {
+                                      int crx, int cry, int xfx, int yfx, const std::string& tag, int hord_tm_pert) {
   const Geom& g = P.dv->g;
   const int K = g.K, is = g.is, ie = g.ie, js = g.js, je = g.je, ng = g.ng;
   auto nm = [&](const char* s) { return tag + "." + s; };
@@ -97,7 +97,19 @@ std::pair<int, int> build_update_dz_d(Program& P, Mosaic& mo, const LevD& dp0, c
   int ra_x = P.val(nm("ra_x"), K + 1), ra_y = P.val(nm("ra_y"), K + 1);
   P.add<S_ra>("dzd_ra", {0}, {xfxa, yfxa}, {ra_x, ra_y}, K + 1);
   LevOrd ho; for (int k = 0; k < 128; k++) ho.v[k] = (signed char)enc_hord(hord_tm);
-  TpOut f = build_fv_tp_2d(P, mo, zh, crxa, crya, xfxa, yfxa, ra_x, ra_y, -1, -1, ho, K + 1, tag + ".tp_zh");
+  TpOut f;
+  if (hord_tm_pert == 0 || hord_tm_pert == hord_tm) f = build_fv_tp_2d(P, mo, zh, crxa, crya, xfxa, yfxa, ra_x, ra_y, -1, -1, ho, K + 1, tag + ".tp_zh");
+  else {   // model_tlmadm/nh_utils_tlm.F90:496-560: perturbation with hord_tm_pert, trajectory with hord_tm
+    LevOrd hp; for (int k = 0; k < 128; k++) hp.v[k] = (signed char)enc_hord(hord_tm_pert);
+    P.tl_only = true;
+    TpOut a = build_fv_tp_2d(P, mo, zh, crxa, crya, xfxa, yfxa, ra_x, ra_y, -1, -1, hp, K + 1, tag + ".tp_zh_p");
+    P.tl_only = false;
+    TpOut b = build_fv_tp_2d(P, mo, P.detached(zh), P.detached(crxa), P.detached(crya), P.detached(xfxa), P.detached(yfxa), P.detached(ra_x), P.detached(ra_y),
+                             -1, -1, ho, K + 1, tag + ".tp_zh_t");
+    f.fx = P.val(tag + ".fx", K + 1); f.fy = P.val(tag + ".fy", K + 1);
+    P.add<S_splice>("splice", {0}, {a.fx, b.fx}, {f.fx}, K + 1);
+    P.add<S_splice>("splice", {0}, {a.fy, b.fy}, {f.fy}, K + 1);
+  }
   // del6_vt_flux(ndif(k), damp(k)) with ndif = nord_v, damp = damp_vt; level K+1 repeats level K (:220-221)
   LevOrd nv; LevD dm, on; bool any = false;
   for (int k = 0; k < 128; k++) nv.v[k] = -1;
@@ -121,6 +133,7 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
   const int isd = is - ng, ied = ie + ng, jsd = js - ng, jed = je + ng;
   const double dt = c.bdt / c.n_split, dt2 = 0.5 * dt, rdt = 1.0 / dt;
   DswParams dp; level_params(c, K, dp); dp.dt = dt; dp.hydrostatic = false;
+  DswParams dpp; const bool two = level_params_pert(c, K, dpp); dpp.dt = dt; dpp.hydrostatic = false;
   const LevD dp0 = dp_ref_of(ak, bk, K);
   DynOut o;
   int u = s.u, v = s.v, pt = s.pt, delp = s.delp, w = s.w, delz = s.delz;
@@ -150,7 +163,7 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
     int uc = P.val(tg + ".uc", K), vc = P.val(tg + ".vc", K);
     P.add<S_pgrad_c>("p_grad_c", {dt2, 0}, {cs.uc, cs.vc, pef, gzr, cs.delpc}, {uc, vc}, K);
     add_patch(P, "halo_ucvc", &mo.h_cgrid, {uc, vc});
-    DswOut ds = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, cs.ua, cs.va, cs.divg_d, dp, K, tg + ".dsw");
+    DswOut ds = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, cs.ua, cs.va, cs.divg_d, dp, K, tg + ".dsw", two ? &dpp : nullptr);
     if (mfx < 0) { mfx = ds.fx; mfy = ds.fy; cx = ds.crx; cy = ds.cry; }
     else {
       int a = P.val(tg + ".mfx", K), b = P.val(tg + ".mfy", K), cc = P.val(tg + ".cx", K), d = P.val(tg + ".cy", K);
@@ -167,7 +180,7 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
     delp = ds.delp; pt = ds.pt;
     add_patch(P, "halo_delp", &mo.h_center, {delp});
     add_patch(P, "halo_pt", &mo.h_center, {pt});
-    auto dzd = build_update_dz_d(P, mo, dp0, dp, c.hord_tm, rdt, zs, zh, ds.crx, ds.cry, ds.xfx, ds.yfx, tg + ".dzd");
+    auto dzd = build_update_dz_d(P, mo, dp0, dp, c.hord_tm, rdt, zs, zh, ds.crx, ds.cry, ds.xfx, ds.yfx, tg + ".dzd", two ? c.pert.hord_tm : 0);
     ws_d = dzd.second;
     RiemOut r3 = build_riem(P, {K, 1, 0, dt, c.akap, c.ptop, c.rdgas, c.grav, c.p_fac, c.a_imp}, delp, pt, dzd.first, ds.w, dzd.second, zs, tg + ".rs3");
     const int ppe = r3.pp, zhn = r3.z;

@@ -595,12 +595,13 @@ struct DswParams {
   LevD d2_bg, damp_v, damp_w, damp_t;
   double dddmp, d4_bg, dt;
   bool hydrostatic;
+  bool split_damp = false;   // perturbation side only: divergence damping evaluated separately for trajectory and perturbation
   bool heat = false;   // d_con > 1e-5: build the dissipative-heating stages
   LevD d_con;          // d_con_k per level (0 in the sponge layers)
 };
 struct DswOut { int delp, pt, u, v, w, fx, fy, crx, cry, xfx, yfx; int heat = -1; };
 DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w, int uc, int vc, int ua, int va, int divg_d,
-                  const DswParams& prm, int nk, const std::string& tag);
+                  const DswParams& prm, int nk, const std::string& tag, const DswParams* pert = nullptr);
 // a2b_ord4 (a2b.cu)
 int build_a2b_ord4(Program& P, Mosaic& mo, int qin, int nk, const std::string& tag);
 

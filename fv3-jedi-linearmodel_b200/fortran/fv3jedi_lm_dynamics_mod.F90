@@ -130,6 +130,19 @@ subroutine create(self,conf)
  cfg%rank = mpp_pe() - mpp_root_pe(); cfg%nranks = mpp_npes()
  cfg%layout_x = A%layout(1); cfg%layout_y = A%layout(2)
  cfg%reserved0 = 0; cfg%reserved = 0
+ ! two-sided mode: the fields above carry the perturbation model's switches, cfg%traj the nonlinear model's
+ ! (already forced to the perturbation's by fv_control_tlmadm.F90:219-253 where split_hord / split_damp are false)
+ cfg%two_sided = 1
+ cfg%split_damp = merge(1, 0, self%FV_AtmP(1)%flagstruct%split_damp)
+ cfg%hord_ks_pert = merge(1, 0, self%FV_AtmP(1)%flagstruct%hord_ks_pert)
+ cfg%hord_ks_traj = merge(1, 0, self%FV_AtmP(1)%flagstruct%hord_ks_traj)
+ cfg%d2_bg_ks = self%FV_AtmP(1)%flagstruct%d2_bg_ks_pert
+ cfg%traj%hord_mt = A%flagstruct%hord_mt; cfg%traj%hord_vt = A%flagstruct%hord_vt; cfg%traj%hord_tm = A%flagstruct%hord_tm
+ cfg%traj%hord_dp = A%flagstruct%hord_dp; cfg%traj%hord_tr = A%flagstruct%hord_tr
+ cfg%traj%nord = A%flagstruct%nord; cfg%traj%do_vort_damp = merge(1, 0, A%flagstruct%do_vort_damp)
+ cfg%traj%n_sponge = A%flagstruct%n_sponge
+ cfg%traj%dddmp = A%flagstruct%dddmp; cfg%traj%d2_bg = A%flagstruct%d2_bg; cfg%traj%d4_bg = A%flagstruct%d4_bg
+ cfg%traj%vtdm4 = A%flagstruct%vtdm4; cfg%traj%d2_bg_k1 = A%flagstruct%d2_bg_k1; cfg%traj%d2_bg_k2 = A%flagstruct%d2_bg_k2
  cfg%a_imp = A%flagstruct%a_imp; cfg%p_fac = A%flagstruct%p_fac; cfg%d_con = A%flagstruct%d_con
 
  call check(self, fv3lm_create(cfg, conf%ak, conf%bk, self%handle), 'create')

@@ -8,6 +8,12 @@ use iso_c_binding
 implicit none
 public
 
+!> mirror of the `traj` member of `struct fv3lm_config`: the nonlinear model's switches in two-sided mode
+type, bind(c) :: fv3lm_traj_flags
+  integer(c_int) :: hord_mt, hord_vt, hord_tm, hord_dp, hord_tr, nord, do_vort_damp, n_sponge
+  real(c_double) :: dddmp, d2_bg, d4_bg, vtdm4, d2_bg_k1, d2_bg_k2
+end type fv3lm_traj_flags
+
 !> mirror of `struct fv3lm_config` (include/fv3lm_b200.h); bind(c) keeps the C layout
 type, bind(c) :: fv3lm_config
   integer(c_int) :: npx, npy, npz, ng, ntiles
@@ -21,7 +27,10 @@ type, bind(c) :: fv3lm_config
   integer(c_int) :: rank, nranks, layout_x, layout_y
   integer(c_int) :: reserved0
   real(c_double) :: a_imp, p_fac, d_con
-  integer(c_int) :: reserved(6)
+  integer(c_int) :: two_sided, split_damp, hord_ks_pert, hord_ks_traj
+  integer(c_int) :: reserved(2)
+  type(fv3lm_traj_flags) :: traj
+  real(c_double) :: d2_bg_ks
 end type fv3lm_config
 
 !> mirror of `struct fv3lm_fields`: ten pointers to (isc:iec, jsc:jec, npz) REAL64 arrays

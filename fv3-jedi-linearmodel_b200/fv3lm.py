@@ -15,6 +15,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 MODE_NL, MODE_TL, MODE_AD = 0, 1, 2
 
 
+class TrajFlags(C.Structure):
+    """the nonlinear model's switches in two-sided mode (fv3lm_config.traj)"""
+    _fields_ = [("hord_mt", C.c_int), ("hord_vt", C.c_int), ("hord_tm", C.c_int), ("hord_dp", C.c_int), ("hord_tr", C.c_int),
+                ("nord", C.c_int), ("do_vort_damp", C.c_int), ("n_sponge", C.c_int),
+                ("dddmp", C.c_double), ("d2_bg", C.c_double), ("d4_bg", C.c_double), ("vtdm4", C.c_double),
+                ("d2_bg_k1", C.c_double), ("d2_bg_k2", C.c_double)]
+
+
 class Config(C.Structure):
     _fields_ = [("npx", C.c_int), ("npy", C.c_int), ("npz", C.c_int), ("ng", C.c_int), ("ntiles", C.c_int),
                 ("hydrostatic", C.c_int), ("n_split", C.c_int), ("k_split", C.c_int), ("nq", C.c_int),
@@ -26,7 +34,9 @@ class Config(C.Structure):
                 ("zvir", C.c_double), ("kappa", C.c_double), ("cp", C.c_double), ("rdgas", C.c_double),
                 ("grav", C.c_double), ("do_vort_damp", C.c_int),
                 ("rank", C.c_int), ("nranks", C.c_int), ("layout_x", C.c_int), ("layout_y", C.c_int), ("reserved0", C.c_int),
-                ("a_imp", C.c_double), ("p_fac", C.c_double), ("d_con", C.c_double), ("reserved", C.c_int * 6)]
+                ("a_imp", C.c_double), ("p_fac", C.c_double), ("d_con", C.c_double),
+                ("two_sided", C.c_int), ("split_damp", C.c_int), ("hord_ks_pert", C.c_int), ("hord_ks_traj", C.c_int),
+                ("reserved", C.c_int * 2), ("traj", TrajFlags), ("d2_bg_ks", C.c_double)]
 
 
 class Fields(C.Structure):
@@ -77,7 +87,12 @@ def default_config(N, npz, **kw):
     cfg.zvir = (8314.47 / 18.015) / rdgas - 1.0; cfg.grav = 9.80665
     cfg.do_vort_damp = 1
     for k, v in kw.items():
-        setattr(cfg, k, v)
+        if k == "traj":                       # dict of the nonlinear model's switches -> two-sided mode
+            cfg.two_sided = 1
+            for kk, vv in v.items():
+                setattr(cfg.traj, kk, vv)
+        else:
+            setattr(cfg, k, v)
     return cfg
 
 

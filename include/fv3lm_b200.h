@@ -56,7 +56,22 @@ typedef struct fv3lm_config {
    * (model/sw_core_nlm.F90:1494-1525, model/dyn_core_nlm.F90:1052-1099; needs do_vort_damp with vtdm4 > 1e-5).
    * convert_ke = F, ke_bg = 0, delt_max = 1 (model/fv_arrays_nlm.F90:312, :409-412).                */
   double d_con;
-  int reserved[6];
+  /* Two-sided mode (the TL/AD model as fv3-jedi-linearmodel runs it, model_tlmadm/fv_arrays_tlmadm.F90:37-92): two_sided = 1
+   * means the fields ABOVE (hord_*, nord, dddmp, d2_bg, d4_bg, vtdm4, do_vort_damp, d2_bg_k1, d2_bg_k2, n_sponge) are the
+   * PERTURBATION model's switches (hord_*_pert, nord_pert, ..., n_sponge_pert) and `traj` holds the nonlinear model's
+   * (fv_flags_type, after fv_control_tlmadm.F90:219-253 has applied split_hord / split_damp).  Per-level coefficients then
+   * follow model_tlmadm/dyn_core_tlm.F90:740-926 separately for each side, and every operator whose switches differ is
+   * evaluated twice -- perturbation scheme for the increment, nonlinear model's scheme for the trajectory
+   * (model_tlmadm/sw_core_tlm.F90:1664-1682, 1987-1997, 2341-2366, 2436-2451).  two_sided = 0: one set of switches for both
+   * (TL = exact derivative of the nonlinear step).  traj.hord_* must be 1, 2 or 333 (monotone schemes are not built).      */
+  int two_sided, split_damp;
+  int hord_ks_pert, hord_ks_traj;   /* first-order transport in the top n_sponge - 1 layers (hord_*_ks_* = 1), per side        */
+  int reserved[2];
+  struct {
+    int hord_mt, hord_vt, hord_tm, hord_dp, hord_tr, nord, do_vort_damp, n_sponge;
+    double dddmp, d2_bg, d4_bg, vtdm4, d2_bg_k1, d2_bg_k2;
+  } traj;
+  double d2_bg_ks;                  /* d2_bg_ks_pert: divergence damping of the remaining perturbation sponge layers           */
 } fv3lm_config;
 
 int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv3lm_handle** out);

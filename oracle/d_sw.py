@@ -17,6 +17,32 @@ from .a2b_edge import a2b_ord4
 from .sw_core import S, P, put, Z, sg, O, C1, C2, C3, P1, P2
 
 
+class _Splice(torch.autograd.Function):
+    """value of b (trajectory-scheme chain), derivative of a (perturbation-scheme chain): the split_hord / split_damp
+    semantics of the TL/AD model (model_tlmadm/sw_core_tlm.F90:1664-1682, 2341-2366, 2436-2451)"""
+    generate_vmap_rule = True
+
+    @staticmethod
+    def forward(a, b):
+        return b.clone()
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+    @staticmethod
+    def jvp(ctx, ta, tb):
+        return ta
+
+
+def splice(a, b):
+    return _Splice.apply(a, b)
+
+
 def _lv(vals, dtype=torch.float64):
     return torch.tensor(vals, dtype=dtype).view(1, -1, 1, 1)
 
@@ -227,10 +253,22 @@ def del6_by_level(nord_l, damp_l, q, g):
     return tp.lev_select(sk, fxv), tp.lev_select(sk, fyv)
 
 
-def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm):
+def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm, pp=None):
     """prm: dict with per-level lists hord_mt, hord_vt, hord_tm, hord_dp, nord, nord_v, nord_w,
     nord_t, d2_bg, damp_v, damp_w, damp_t and scalars dddmp, d4_bg, hydrostatic.
+    pp: the perturbation-side switches (same keys + split_damp) of D_SW_TLM (model_tlmadm/sw_core_tlm.F90:1047); where they
+    differ from prm the operator is evaluated with both and spliced (value from prm, derivative from pp).
     Returns dict(delp, pt, u, v, w, fx, fy, crx, cry, xfx, yfx)."""
+    if pp is None:
+        pp = prm
+    split_damp = bool(pp.get("split_damp", False))
+
+    def tp_site(same, fn):
+        """fn(p) -> (fx, fy, q) with the switches p"""
+        if same:
+            return fn(prm)
+        a = fn(pp); b = fn(prm)
+        return splice(a[0], b[0]), splice(a[1], b[1]), b[2]
     N, npx, npy = g.N, g.npx, g.npy
     is_, ie, js, je = 1, N, 1, N
     isd, ied, jsd, jed = g.isd, g.ied, g.jsd, g.jed
@@ -245,7 +283,8 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm):
     def div(fx_, fy_, i0=is_, i1=ie, j0=js, j1=je):
         return ((S(fx_, i0, i1, j0, j1) - S(fx_, i0 + 1, i1 + 1, j0, j1)) + (S(fy_, i0, i1, j0, j1) - S(fy_, i0, i1, j0 + 1, j1 + 1))) * S(rarea, i0, i1, j0, j1)
 
-    fx, fy, delp_c = tp.fv_tp_2d_damp(delp, crx, cry, prm["hord_dp"], xfx, yfx, g, ra_x, ra_y, nord=prm["nord_v"], damp_c=prm["damp_v"])
+    fx, fy, delp_c = tp_site(prm["hord_dp"] == pp["hord_dp"] and not split_damp,
+                             lambda p: tp.fv_tp_2d_damp(delp, crx, cry, p["hord_dp"], xfx, yfx, g, ra_x, ra_y, nord=p["nord_v"], damp_c=p["damp_v"]))
 
     w_new = w
     if not hydro:
@@ -254,11 +293,12 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm):
         fx2, fy2 = del6_by_level(nordw, damp4, w, g)
         on = _lv([1.0 if dmpw[k] > 1.e-5 else 0.0 for k in range(K)])
         dw = div(fx2, fy2) * on
-        gx, gy, _ = tp.fv_tp_2d(w, crx, cry, prm["hord_vt"], xfx, yfx, g, ra_x, ra_y, mfx=fx, mfy=fy)
+        gx, gy, _ = tp_site(prm["hord_vt"] == pp["hord_vt"], lambda p: tp.fv_tp_2d(w, crx, cry, p["hord_vt"], xfx, yfx, g, ra_x, ra_y, mfx=fx, mfy=fy))
         w_new = put(w, is_, ie, js, je, S(delp, is_, ie, js, je) * S(w, is_, ie, js, je) + div(gx, gy))
 
-    gx, gy, pt_c = tp.fv_tp_2d_damp(pt, crx, cry, prm["hord_tm"], xfx, yfx, g, ra_x, ra_y, mfx=fx, mfy=fy, mass=delp,
-                                    nord=prm["nord_t"], damp_c=prm["damp_t"])
+    gx, gy, pt_c = tp_site(prm["hord_tm"] == pp["hord_tm"] and not split_damp,
+                           lambda p: tp.fv_tp_2d_damp(pt, crx, cry, p["hord_tm"], xfx, yfx, g, ra_x, ra_y, mfx=fx, mfy=fy, mass=delp,
+                                                      nord=p["nord_t"], damp_c=p["damp_t"]))
     ptd = S(pt, is_, ie, js, je) * S(delp, is_, ie, js, je) + div(gx, gy)
     delp_new_v = S(delp, is_, ie, js, je) + div(fx, fy)
     delp_new = put(delp, is_, ie, js, je, delp_new_v)
@@ -273,7 +313,8 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm):
     for i in (1, npx):
         vb = put(vb, i, i, j0, j1, dt4 * (-S(vt, i - 2, i - 2, j0, j1) + 3. * (S(vt, i - 1, i - 1, j0, j1) + S(vt, i, i, j0, j1)) - S(vt, i + 1, i + 1, j0, j1)))
     vb = put(vb, is_, ie + 1, npy, npy, dt5 * (S(vt, is_ - 1, ie, npy, npy) + S(vt, is_, ie + 1, npy, npy)))
-    ub = ytp_v(vb, v, g, prm["hord_mt"])
+    same_mt = prm["hord_mt"] == pp["hord_mt"]
+    ub = ytp_v(vb, v, g, prm["hord_mt"]) if same_mt else splice(ytp_v(vb, v, g, pp["hord_mt"]), ytp_v(vb, v, g, prm["hord_mt"]))
     ke = vb * ub
     ub2 = Z(u)
     ub2 = put(ub2, 1, 1, js, je + 1, dt5 * (S(ut, 1, 1, js - 1, je) + S(ut, 1, 1, js, je + 1)))
@@ -281,7 +322,7 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm):
     for j in (1, npy):
         ub2 = put(ub2, i0, i1, j, j, dt4 * (-S(ut, i0, i1, j - 2, j - 2) + 3. * (S(ut, i0, i1, j - 1, j - 1) + S(ut, i0, i1, j, j)) - S(ut, i0, i1, j + 1, j + 1)))
     ub2 = put(ub2, npx, npx, js, je + 1, dt5 * (S(ut, npx, npx, js - 1, je) + S(ut, npx, npx, js, je + 1)))
-    vb2 = xtp_u(ub2, u, g, prm["hord_mt"])
+    vb2 = xtp_u(ub2, u, g, prm["hord_mt"]) if same_mt else splice(xtp_u(ub2, u, g, pp["hord_mt"]), xtp_u(ub2, u, g, prm["hord_mt"]))
     ke = 0.5 * (ke + ub2 * vb2)
     ke = ke.clone()
     U_, V_, UT, VT = (lambda i, j: P(u, i, j)), (lambda i, j: P(v, i, j)), (lambda i, j: P(ut, i, j)), (lambda i, j: P(vt, i, j))
@@ -302,80 +343,84 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm):
         w_new = put(w_new, is_, ie, js, je, wv)
 
     # ---- divergence damping (:1264-1434), per level nord = 0 or > 0
-    nord_l = prm["nord"]; d2bg = _lv(prm["d2_bg"]); dddmp = prm["dddmp"]; d4_bg = prm["d4_bg"]
-    da_min_c = g.da_min_c
     C = (is_, ie + 1, js, je + 1)
-    ke_damp = {}
-    if any(n == 0 for n in nord_l):
-        # nord == 0 :  del-2 on the divergence computed from the D-grid winds
-        ptc = Z(u)
-        j0, j1 = 2, npy - 1
-        ptc = put(ptc, is_ - 1, ie + 1, j0, j1, (S(u, is_ - 1, ie + 1, j0, j1) - 0.5 * (S(va, is_ - 1, ie + 1, j0 - 1, j1 - 1) + S(va, is_ - 1, ie + 1, j0, j1)) * S(g.cosa_v, is_ - 1, ie + 1, j0, j1)) *
-                  S(g.dyc, is_ - 1, ie + 1, j0, j1) * S(g.sina_v, is_ - 1, ie + 1, j0, j1))
-        for j in (1, npy):
-            vcv = S(vc, is_ - 1, ie + 1, j, j)
-            ptc = put(ptc, is_ - 1, ie + 1, j, j, S(u, is_ - 1, ie + 1, j, j) * S(g.dyc, is_ - 1, ie + 1, j, j) *
-                      torch.where(vcv > 0, S(sin4, is_ - 1, ie + 1, j - 1, j - 1), S(sin2, is_ - 1, ie + 1, j, j)))
-        vo = Z(u)
-        i0, i1 = 2, npx - 1
-        vo = put(vo, i0, i1, js - 1, je + 1, (S(v, i0, i1, js - 1, je + 1) - 0.5 * (S(ua, i0 - 1, i1 - 1, js - 1, je + 1) + S(ua, i0, i1, js - 1, je + 1)) * S(g.cosa_u, i0, i1, js - 1, je + 1)) *
-                 S(g.dxc, i0, i1, js - 1, je + 1) * S(g.sina_u, i0, i1, js - 1, je + 1))
-        for i in (1, npx):
-            ucv = S(uc, i, i, js - 1, je + 1)
-            vo = put(vo, i, i, js - 1, je + 1, S(v, i, i, js - 1, je + 1) * S(g.dxc, i, i, js - 1, je + 1) *
-                     torch.where(ucv > 0, S(sin3, i - 1, i - 1, js - 1, je + 1), S(sin1, i, i, js - 1, je + 1)))
-        dpc = (S(vo, C[0], C[1], C[2] - 1, C[3] - 1) - S(vo, *C)) + (S(ptc, C[0] - 1, C[1] - 1, C[2], C[3]) - S(ptc, *C))
-        dpc = put(Z(u), *C, dpc).clone()
-        dpc[..., 1 + O, 1 + O] = P(dpc, 1, 1) - P(vo, 1, 0)
-        dpc[..., 1 + O, npx + O] = P(dpc, npx, 1) - P(vo, npx, 0)
-        dpc[..., npy + O, npx + O] = P(dpc, npx, npy) + P(vo, npx, npy)
-        dpc[..., npy + O, 1 + O] = P(dpc, 1, npy) + P(vo, 1, npy)
-        dpcv = S(g.rarea_c, *C) * S(dpc, *C)
-        damp = da_min_c * torch.maximum(d2bg, torch.clamp(dddmp * torch.abs(dpcv * dt), max=0.20))
-        ke_damp["0"] = put(Z(u), *C, damp * dpcv)
-    if any(n > 0 for n in nord_l):
-        nmax = max(nord_l)
-        variants = {}
-        for nord in sorted(set(n for n in nord_l if n > 0)):
-            delpc = put(Z(u), *C, S(divg_d, *C))
-            dd = divg_d
-            ucw, vcw = None, None
-            for n in range(1, nord + 1):
-                nt = nord - n
-                fill_c = nt != 0
-                if fill_c:
-                    dd = fill_corners_bgrid(dd, npx, npy, "x")
-                i0, i1, j0, j1 = is_ - 1 - nt, ie + 1 + nt, js - nt, je + 1 + nt
-                vcw = put(Z(u), i0, i1, j0, j1, (S(dd, i0 + 1, i1 + 1, j0, j1) - S(dd, i0, i1, j0, j1)) * S(g.divg_u, i0, i1, j0, j1))
-                if fill_c:
-                    dd = fill_corners_bgrid(dd, npx, npy, "y")
-                i0, i1, j0, j1 = is_ - nt, ie + 1 + nt, js - 1 - nt, je + 1 + nt
-                ucw = put(Z(u), i0, i1, j0, j1, (S(dd, i0, i1, j0 + 1, j1 + 1) - S(dd, i0, i1, j0, j1)) * S(g.divg_v, i0, i1, j0, j1))
-                if fill_c:
-                    vcw, ucw = fill_corners_dgrid(vcw, ucw, npx, npy, -1.0)
-                i0, i1, j0, j1 = is_ - nt, ie + 1 + nt, js - nt, je + 1 + nt
-                ddn = (S(ucw, i0, i1, j0 - 1, j1 - 1) - S(ucw, i0, i1, j0, j1)) + (S(vcw, i0 - 1, i1 - 1, j0, j1) - S(vcw, i0, i1, j0, j1))
-                ddn = put(Z(u), i0, i1, j0, j1, ddn).clone()
-                ddn[..., 1 + O, 1 + O] = P(ddn, 1, 1) - P(ucw, 1, 0)
-                ddn[..., 1 + O, npx + O] = P(ddn, npx, 1) - P(ucw, npx, 0)
-                ddn[..., npy + O, npx + O] = P(ddn, npx, npy) + P(ucw, npx, npy)
-                ddn[..., npy + O, 1 + O] = P(ddn, 1, npy) + P(ucw, 1, npy)
-                dd = put(Z(u), i0, i1, j0, j1, S(ddn, i0, i1, j0, j1) * S(g.rarea_c, i0, i1, j0, j1))
-            if dddmp < 1.e-5:
-                vort = Z(u)
-            else:
-                vq = a2b_ord4(wk, g)
-                vort = put(Z(u), *C, abs(dt) * torch.sqrt(S(delpc, *C) ** 2 + S(vq, *C) ** 2))
-            dd8 = (da_min_c * d4_bg) ** (nord + 1)
-            damp2 = da_min_c * torch.maximum(d2bg, torch.clamp(dddmp * S(vort, *C), max=0.20))
-            variants[str(nord)] = put(Z(u), *C, damp2 * S(delpc, *C) + dd8 * S(dd, *C))
-        ke_damp.update(variants)
-    vort_d = tp.lev_select([str(n) for n in nord_l], ke_damp)
+    def div_damp(p):
+        nord_l = p["nord"]; d2bg = _lv(p["d2_bg"]); dddmp = p["dddmp"]; d4_bg = p["d4_bg"]
+        da_min_c = g.da_min_c
+        C = (is_, ie + 1, js, je + 1)
+        ke_damp = {}
+        if any(n == 0 for n in nord_l):
+            # nord == 0 :  del-2 on the divergence computed from the D-grid winds
+            ptc = Z(u)
+            j0, j1 = 2, npy - 1
+            ptc = put(ptc, is_ - 1, ie + 1, j0, j1, (S(u, is_ - 1, ie + 1, j0, j1) - 0.5 * (S(va, is_ - 1, ie + 1, j0 - 1, j1 - 1) + S(va, is_ - 1, ie + 1, j0, j1)) * S(g.cosa_v, is_ - 1, ie + 1, j0, j1)) *
+                      S(g.dyc, is_ - 1, ie + 1, j0, j1) * S(g.sina_v, is_ - 1, ie + 1, j0, j1))
+            for j in (1, npy):
+                vcv = S(vc, is_ - 1, ie + 1, j, j)
+                ptc = put(ptc, is_ - 1, ie + 1, j, j, S(u, is_ - 1, ie + 1, j, j) * S(g.dyc, is_ - 1, ie + 1, j, j) *
+                          torch.where(vcv > 0, S(sin4, is_ - 1, ie + 1, j - 1, j - 1), S(sin2, is_ - 1, ie + 1, j, j)))
+            vo = Z(u)
+            i0, i1 = 2, npx - 1
+            vo = put(vo, i0, i1, js - 1, je + 1, (S(v, i0, i1, js - 1, je + 1) - 0.5 * (S(ua, i0 - 1, i1 - 1, js - 1, je + 1) + S(ua, i0, i1, js - 1, je + 1)) * S(g.cosa_u, i0, i1, js - 1, je + 1)) *
+                     S(g.dxc, i0, i1, js - 1, je + 1) * S(g.sina_u, i0, i1, js - 1, je + 1))
+            for i in (1, npx):
+                ucv = S(uc, i, i, js - 1, je + 1)
+                vo = put(vo, i, i, js - 1, je + 1, S(v, i, i, js - 1, je + 1) * S(g.dxc, i, i, js - 1, je + 1) *
+                         torch.where(ucv > 0, S(sin3, i - 1, i - 1, js - 1, je + 1), S(sin1, i, i, js - 1, je + 1)))
+            dpc = (S(vo, C[0], C[1], C[2] - 1, C[3] - 1) - S(vo, *C)) + (S(ptc, C[0] - 1, C[1] - 1, C[2], C[3]) - S(ptc, *C))
+            dpc = put(Z(u), *C, dpc).clone()
+            dpc[..., 1 + O, 1 + O] = P(dpc, 1, 1) - P(vo, 1, 0)
+            dpc[..., 1 + O, npx + O] = P(dpc, npx, 1) - P(vo, npx, 0)
+            dpc[..., npy + O, npx + O] = P(dpc, npx, npy) + P(vo, npx, npy)
+            dpc[..., npy + O, 1 + O] = P(dpc, 1, npy) + P(vo, 1, npy)
+            dpcv = S(g.rarea_c, *C) * S(dpc, *C)
+            damp = da_min_c * torch.maximum(d2bg, torch.clamp(dddmp * torch.abs(dpcv * dt), max=0.20))
+            ke_damp["0"] = put(Z(u), *C, damp * dpcv)
+        if any(n > 0 for n in nord_l):
+            nmax = max(nord_l)
+            variants = {}
+            for nord in sorted(set(n for n in nord_l if n > 0)):
+                delpc = put(Z(u), *C, S(divg_d, *C))
+                dd = divg_d
+                ucw, vcw = None, None
+                for n in range(1, nord + 1):
+                    nt = nord - n
+                    fill_c = nt != 0
+                    if fill_c:
+                        dd = fill_corners_bgrid(dd, npx, npy, "x")
+                    i0, i1, j0, j1 = is_ - 1 - nt, ie + 1 + nt, js - nt, je + 1 + nt
+                    vcw = put(Z(u), i0, i1, j0, j1, (S(dd, i0 + 1, i1 + 1, j0, j1) - S(dd, i0, i1, j0, j1)) * S(g.divg_u, i0, i1, j0, j1))
+                    if fill_c:
+                        dd = fill_corners_bgrid(dd, npx, npy, "y")
+                    i0, i1, j0, j1 = is_ - nt, ie + 1 + nt, js - 1 - nt, je + 1 + nt
+                    ucw = put(Z(u), i0, i1, j0, j1, (S(dd, i0, i1, j0 + 1, j1 + 1) - S(dd, i0, i1, j0, j1)) * S(g.divg_v, i0, i1, j0, j1))
+                    if fill_c:
+                        vcw, ucw = fill_corners_dgrid(vcw, ucw, npx, npy, -1.0)
+                    i0, i1, j0, j1 = is_ - nt, ie + 1 + nt, js - nt, je + 1 + nt
+                    ddn = (S(ucw, i0, i1, j0 - 1, j1 - 1) - S(ucw, i0, i1, j0, j1)) + (S(vcw, i0 - 1, i1 - 1, j0, j1) - S(vcw, i0, i1, j0, j1))
+                    ddn = put(Z(u), i0, i1, j0, j1, ddn).clone()
+                    ddn[..., 1 + O, 1 + O] = P(ddn, 1, 1) - P(ucw, 1, 0)
+                    ddn[..., 1 + O, npx + O] = P(ddn, npx, 1) - P(ucw, npx, 0)
+                    ddn[..., npy + O, npx + O] = P(ddn, npx, npy) + P(ucw, npx, npy)
+                    ddn[..., npy + O, 1 + O] = P(ddn, 1, npy) + P(ucw, 1, npy)
+                    dd = put(Z(u), i0, i1, j0, j1, S(ddn, i0, i1, j0, j1) * S(g.rarea_c, i0, i1, j0, j1))
+                if dddmp < 1.e-5:
+                    vort = Z(u)
+                else:
+                    vq = a2b_ord4(wk, g)
+                    vort = put(Z(u), *C, abs(dt) * torch.sqrt(S(delpc, *C) ** 2 + S(vq, *C) ** 2))
+                dd8 = (da_min_c * d4_bg) ** (nord + 1)
+                damp2 = da_min_c * torch.maximum(d2bg, torch.clamp(dddmp * S(vort, *C), max=0.20))
+                variants[str(nord)] = put(Z(u), *C, damp2 * S(delpc, *C) + dd8 * S(dd, *C))
+            ke_damp.update(variants)
+        vort_d = tp.lev_select([str(n) for n in nord_l], ke_damp)
+        return vort_d
+    vort_d = div_damp(prm) if not split_damp else splice(div_damp(pp), div_damp(prm))
     ke = put(ke, *C, S(ke, *C) + S(vort_d, *C))
 
     # ---- vorticity transport and wind update (:1449-1483)
     vort = put(Z(u), isd, ied, jsd, jed, S(wk, isd, ied, jsd, jed) + S(g.f0, isd, ied, jsd, jed))
-    fxv, fyv, _ = tp.fv_tp_2d(vort, crx, cry, prm["hord_vt"], xfx, yfx, g, ra_x, ra_y)
+    fxv, fyv, _ = tp_site(prm["hord_vt"] == pp["hord_vt"], lambda p: tp.fv_tp_2d(vort, crx, cry, p["hord_vt"], xfx, yfx, g, ra_x, ra_y))
     i0, i1, j0, j1 = is_, ie, js, je + 1
     un = S(vt2, i0, i1, j0, j1) + (S(ke, i0, i1, j0, j1) - S(ke, i0 + 1, i1 + 1, j0, j1)) + S(fyv, i0, i1, j0, j1)
     i0, i1, j0, j1 = is_, ie + 1, js, je
@@ -384,8 +429,14 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm):
     # ---- vorticity damping (:1487-1539)
     dmpv = prm["damp_v"]; nordv = prm["nord_v"]
     if any(d > 1.e-5 for d in dmpv):
-        damp4 = [(dmpv[k] * g.da_min_c) ** (nordv[k] + 1) if dmpv[k] > 1.e-5 else 0.0 for k in range(K)]
-        ut3, vt3 = del6_by_level(nordv, damp4, wk, g)
+        def del6v(p):
+            d4 = [(p["damp_v"][k] * g.da_min_c) ** (p["nord_v"][k] + 1) if p["damp_v"][k] > 1.e-5 else 0.0 for k in range(K)]
+            return del6_by_level(p["nord_v"], d4, wk, g)
+        ut3, vt3 = del6v(prm)
+        if pp["nord_v"] != nordv or pp["damp_v"] != dmpv:      # the perturbation always uses its own pair (:2436-2451)
+            assert [d > 1.e-5 for d in pp["damp_v"]] == [d > 1.e-5 for d in dmpv]
+            ua3, va3 = del6v(pp)
+            ut3, vt3 = splice(ua3, ut3), splice(va3, vt3)
         on = _lv([1.0 if dmpv[k] > 1.e-5 else 0.0 for k in range(K)])
         un = un + on * S(vt3, is_, ie, js, je + 1)
         vn = vn - on * S(ut3, is_, ie + 1, js, je)

@@ -167,7 +167,7 @@ def level_params(cfg, K):
             elif k == max(3, ns) and cfg["d2_bg_k2"] > 0.05:
                 nord_k = 0; d2 = max(cfg["d2_bg"], 0.2 * cfg["d2_bg_k2"]); nord_w = 0; damp_w = d2
                 d_con_k = 0.0
-        ho = 1 if k <= cfg.get("n_sponge_ord", 0) else None
+        ho = 1 if (k <= cfg.get("n_sponge_ord", 0) or k <= cfg.get("n_sponge_ks", 0)) else None
         for n in ("hord_mt", "hord_vt", "hord_tm", "hord_dp"):
             p[n].append(ho if ho else cfg[n])
         p["nord"].append(nord_k); p["nord_v"].append(nord_v); p["nord_w"].append(nord_w); p["nord_t"].append(nord_t)
@@ -176,6 +176,48 @@ def level_params(cfg, K):
     p["dddmp"] = cfg["dddmp"]; p["d4_bg"] = cfg["d4_bg"]
     if not cfg.get("d_con", 0.0) > 1.e-5:
         del p["d_con"]
+    return p
+
+
+def sides(cfg):
+    """two-sided mode (cfg["traj"] = dict of the nonlinear model's switches; the top-level ones are then the perturbation
+    model's, model_tlmadm/fv_arrays_tlmadm.F90:37-92).  Returns (trajectory cfg, perturbation cfg or None)."""
+    if not cfg.get("traj"):
+        return cfg, None
+    ct = dict(cfg); ct.update(cfg["traj"]); ct["traj"] = None
+    if cfg.get("hord_ks_traj", True):
+        ct["n_sponge_ks"] = cfg.get("n_sponge", 0) - 1       # hord_*_ks_traj = 1 in the top n_sponge_pert - 1 layers
+    ct["n_sponge_ord"] = 0
+    return ct, cfg
+
+
+def level_params_pert(cfg, K, prm_traj):
+    """perturbation-side per-level switches (model_tlmadm/dyn_core_tlm.F90:835-921); cfg: the perturbation model's flags"""
+    p = {k: [] for k in ("hord_mt", "hord_vt", "hord_tm", "hord_dp", "nord", "nord_v", "nord_w", "nord_t", "d2_bg", "damp_v", "damp_w", "damp_t")}
+    ns = cfg.get("n_sponge", 0)
+    for k in range(1, K + 1):
+        ho = {n: cfg[n] for n in ("hord_mt", "hord_vt", "hord_tm", "hord_dp")}
+        nord_k = cfg["nord"]; nord_v = min(2, cfg["nord"])
+        d2 = min(0.20, cfg["d2_bg"])
+        damp_vt = cfg["vtdm4"] if cfg["do_vort_damp"] else 0.0
+        nord_w = nord_v; nord_t = nord_v; damp_w = damp_vt; damp_t = damp_vt
+        if k <= ns:
+            if k <= ns - 1 and cfg.get("hord_ks_pert", True):
+                ho = {n: 1 for n in ho}
+            nord_k = 0
+            dk = cfg["d2_bg_k1"] if k == 1 else cfg["d2_bg_k2"] if k == 2 else cfg.get("d2_bg_ks", 2.0)
+            d2 = max(0.01, cfg["d2_bg"], dk)
+            nord_w = 0; damp_w = d2
+            if cfg["do_vort_damp"]:
+                nord_v = 0; damp_vt = 0.5 * d2
+        for n in ho:
+            p[n].append(ho[n])
+        p["nord"].append(nord_k); p["nord_v"].append(nord_v); p["nord_w"].append(nord_w); p["nord_t"].append(nord_t)
+        p["d2_bg"].append(d2); p["damp_v"].append(damp_vt); p["damp_w"].append(damp_w); p["damp_t"].append(damp_t)
+    p["dddmp"] = cfg["dddmp"]; p["d4_bg"] = cfg["d4_bg"]; p["split_damp"] = bool(cfg.get("split_damp", False))
+    for n in ("hydrostatic", "d_con"):
+        if n in prm_traj:
+            p[n] = prm_traj[n]
     return p
 
 
@@ -254,8 +296,10 @@ def dyn_core_hydro(st, g, cfg):
     n_split = cfg["n_split"]
     dt = cfg["bdt"] / n_split
     dt2 = 0.5 * dt
+    cfg, cfgp = sides(cfg)
     prm = level_params(cfg, K)
     prm["hydrostatic"] = True
+    pp = level_params_pert(cfgp, K, prm) if cfgp else None
     u, v, pt, delp = st["u"], st["v"], st["pt"], st["delp"]
     w = Z(u)
     hs = st["phis"]
@@ -268,7 +312,7 @@ def dyn_core_hydro(st, g, cfg):
         pkc, gz, _, _, _ = geopk(c["delpc"], c["ptc"], hs, g, ptop, akap, cp_air, 1, True)
         uc, vc = p_grad_c(dt2, c["delpc"], pkc, gz, c["uc"], c["vc"], g, True)
         uc, vc = halo.cgrid(uc, vc)
-        d = d_sw(delp, pt, u, v, w, uc, vc, c["ua"], c["va"], divgd, g, dt, prm)
+        d = d_sw(delp, pt, u, v, w, uc, vc, c["ua"], c["va"], divgd, g, dt, prm, pp)
         mfx = put(mfx, is_, ie + 1, js, je, S(mfx, is_, ie + 1, js, je) + S(d["fx"], is_, ie + 1, js, je))
         mfy = put(mfy, is_, ie, js, je + 1, S(mfy, is_, ie, js, je + 1) + S(d["fy"], is_, ie, js, je + 1))
         cx = put(cx, is_, ie + 1, jsd, jed, S(cx, is_, ie + 1, jsd, jed) + S(d["crx"], is_, ie + 1, jsd, jed))

@@ -25,7 +25,7 @@ from .dyn_core import halo_of, dyn_core_hydro
 from .fv_mapz import lagrangian_to_eulerian
 
 
-def tracer_2d(qs, dp1, mfx, mfy, cx, cy, g, hord):
+def tracer_2d(qs, dp1, mfx, mfy, cx, cy, g, hord, hord_pert=None):
     """fv_tracer2d_nlm.F90:275-516 with nsplt = 1.  qs: list of tracers (halo valid)."""
     N = g.N
     is_, ie, js, je = 1, N, 1, N
@@ -46,6 +46,10 @@ def tracer_2d(qs, dp1, mfx, mfy, cx, cy, g, hord):
     out = []
     for q in qs:
         fx, fy, _ = tp.fv_tp_2d(q, cx, cy, hord, xfx, yfx, g, ra_x, ra_y, mfx=mfx, mfy=mfy)
+        if hord_pert is not None and hord_pert != hord:      # model_tlmadm/fv_tracer2d_tlm.F90:1060-1090
+            from .d_sw import splice
+            fxp, fyp, _ = tp.fv_tp_2d(q, cx, cy, hord_pert, xfx, yfx, g, ra_x, ra_y, mfx=mfx, mfy=mfy)
+            fx, fy = splice(fxp, fx), splice(fyp, fy)
         qn = (S(q, is_, ie, js, je) * S(dp1, is_, ie, js, je) +
               ((S(fx, is_, ie, js, je) - S(fx, is_ + 1, ie + 1, js, je)) + (S(fy, is_, ie, js, je) - S(fy, is_, ie, js + 1, je + 1))) * rar) / dp2
         out.append(put4(q, is_, ie, js, je, qn))
@@ -93,7 +97,9 @@ def fv_dynamics(st, g, ak, bk, cfg):
             w, delz = d["w"], d["delz"]
         u, v, pt, delp = d["u"], d["v"], d["pt"], d["delp"]
         q = [halo.scalar(x) for x in q]
-        q = tracer_2d(q, dp1, d["mfx"], d["mfy"], d["cx"], d["cy"], g, cfg["hord_tr"])
+        two = bool(cfg.get("traj"))
+        q = tracer_2d(q, dp1, d["mfx"], d["mfy"], d["cx"], d["cy"], g, cfg["traj"]["hord_tr"] if two else cfg["hord_tr"],
+                      cfg["hord_tr"] if two else None)
         r = dict(pe=d["pe"], pk=d["pk"], peln=d["peln"], pkz=d["pkz"], delp=delp, pt=pt, u=u, v=v, q=q)
         if not hydro:
             r.update(w=w, delz=delz, ws=d["ws"])

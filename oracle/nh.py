@@ -15,7 +15,7 @@ from .cubed_sphere import R, fill_4corners
 from .sw_core import c_sw, S, put, Z, O, sg
 from .d_sw import d_sw, del6_vt_flux
 from . import tp_core as tp
-from .dyn_core import halo_of, p_grad_c, grad_p, level_params, geopk, heat_update
+from .dyn_core import halo_of, p_grad_c, grad_p, level_params, geopk, heat_update, sides, level_params_pert
 
 DZ_MIN = 2.0
 R3 = 1. / 3.
@@ -245,7 +245,7 @@ def update_dz_c(dt, dp0, zs, ut, vt, gz, g):
     return gz_out, ws_out
 
 
-def update_dz_d(ndif, damp, hord, dp0, zs, zh, crx, cry, xfx, yfx, g, rdt):
+def update_dz_d(ndif, damp, hord, dp0, zs, zh, crx, cry, xfx, yfx, g, rdt, hord_pert=None):
     """update_dz_d: ndif, damp per-level lists (length K; K+1-th = K-th).  Returns zh, ws"""
     N, npx, npy = g.N, g.npx, g.npy
     is_, ie, js, je = 1, N, 1, N
@@ -258,6 +258,10 @@ def update_dz_d(ndif, damp, hord, dp0, zs, zh, crx, cry, xfx, yfx, g, rdt):
     ra_y = put(Z(zh), isd, ied, js, je, S(g.area, isd, ied, js, je) + (S(yfx_a, isd, ied, js, je) - S(yfx_a, isd, ied, js + 1, je + 1)))
     hl = [hord] * (K + 1) if isinstance(hord, int) else list(hord) + [hord[-1]]
     fx, fy, z2 = tp.fv_tp_2d(zh, crx_a, cry_a, hl if len(set(hl)) > 1 else hl[0], xfx_a, yfx_a, g, ra_x, ra_y)
+    if hord_pert is not None and hord_pert != hord:      # model_tlmadm/nh_utils_tlm.F90:496-560
+        from .d_sw import splice
+        fxp, fyp, _ = tp.fv_tp_2d(zh, crx_a, cry_a, hord_pert, xfx_a, yfx_a, g, ra_x, ra_y)
+        fx, fy = splice(fxp, fx), splice(fyp, fy)
     C = (is_, ie, js, je)
     base = (S(zh, *C) * S(g.area, *C) + (S(fx, *C) - S(fx, is_ + 1, ie + 1, js, je)) + (S(fy, *C) - S(fy, is_, ie, js + 1, je + 1))) / \
         ((S(ra_x, *C) + S(ra_y, *C)) - S(g.area, *C))
@@ -293,8 +297,10 @@ def dyn_core_nh(st, g, cfg, ak, bk, first_call=True):
     dt2 = 0.5 * dt
     rdt = 1. / dt
     grav = cfg["grav"]; ptop, akap = cfg["ptop"], cfg["akap"]
+    cfg, cfgp = sides(cfg)
     prm = level_params(cfg, K)
     prm["hydrostatic"] = False
+    pp = level_params_pert(cfgp, K, prm) if cfgp else None
     dp_ref = [(ak[k + 1] - ak[k]) + (bk[k + 1] - bk[k]) * 1.e5 for k in range(K)]
     u, v, w, delz, pt, delp = st["u"], st["v"], st["w"], st["delz"], st["pt"], st["delp"]
     hs = st["phis"]
@@ -327,7 +333,7 @@ def dyn_core_nh(st, g, cfg, ak, bk, first_call=True):
         gz = gzn
         uc, vc = p_grad_c(dt2, c["delpc"], pkc, gz, c["uc"], c["vc"], g, False)
         uc, vc = halo.cgrid(uc, vc)
-        d = d_sw(delp, pt, u, v, w, uc, vc, c["ua"], c["va"], divgd, g, dt, prm)
+        d = d_sw(delp, pt, u, v, w, uc, vc, c["ua"], c["va"], divgd, g, dt, prm, pp)
         mfx = put(mfx, is_, ie + 1, js, je, S(mfx, is_, ie + 1, js, je) + S(d["fx"], is_, ie + 1, js, je))
         mfy = put(mfy, is_, ie, js, je + 1, S(mfy, is_, ie, js, je + 1) + S(d["fy"], is_, ie, js, je + 1))
         cx = put(cx, is_, ie + 1, jsd, jed, S(cx, is_, ie + 1, jsd, jed) + S(d["crx"], is_, ie + 1, jsd, jed))
@@ -335,7 +341,8 @@ def dyn_core_nh(st, g, cfg, ak, bk, first_call=True):
         if "heat" in d:
             heat = d["heat"] if heat is None else heat + d["heat"]
         delp = halo.scalar(d["delp"]); pt = halo.scalar(d["pt"]); w = d["w"]
-        zh, ws = update_dz_d(prm["nord_v"], prm["damp_v"], cfg["hord_tm"], dp_ref, zs, zh, d["crx"], d["cry"], d["xfx"], d["yfx"], g, rdt)
+        zh, ws = update_dz_d(prm["nord_v"], prm["damp_v"], cfg["hord_tm"], dp_ref, zs, zh, d["crx"], d["cry"], d["xfx"], d["yfx"], g, rdt,
+                             hord_pert=cfgp["hord_tm"] if cfgp else None)
         wn, dzn, zhn, ppe = riem_solver3(dt, delp[C], pt[C], zh[C], w[C], ws[C], zs[C], cfg)
         w = torch.zeros_like(w); w[C] = wn
         delz = torch.zeros_like(delz); delz[C] = dzn

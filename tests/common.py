@@ -28,7 +28,7 @@ LAYOUT = None      # tests/test_decomp.py sets (lx, ly): check_module then compa
 def handle(N, K, emu, ak=None, bk=None, **kw):
     key = (N, K, emu, tuple(sorted(kw.items())), None if ak is None else tuple(ak))
     if key not in _handles:
-        cfg = fv3lm.default_config(N, K, **kw)
+        cfg = fv3lm.default_config(N, K, **{k: (dict(v) if k == "traj" else v) for k, v in kw.items()})
         h = fv3lm.FV3LM(cfg, ak, bk, emu=emu)
         h.set_metrics(metrics(N))
         h._args = (N, K, emu, ak, bk, dict(kw))

@@ -50,7 +50,8 @@ def flat_params(p, K):
     return out
 
 
-def _run_dsw(emu, hydrostatic, sponge, hord=2, d_con=0.0):
+def _run_dsw(emu, hydrostatic, sponge, hord=2, d_con=0.0, pert=None):
+    """pert: perturbation-side overrides of level_params (split_hord / split_damp of the TL/AD model)"""
     N, K = 12, 2
     f, rng = dsw_inputs(N, K, 11)
     g = ograd(N)
@@ -59,6 +60,9 @@ def _run_dsw(emu, hydrostatic, sponge, hord=2, d_con=0.0):
     prm.update(dddmp=0.2, d4_bg=0.15, hydrostatic=hydrostatic)
     if d_con > 0.0:
         prm["d_con"] = [0.0 if (sponge and k == 0) else d_con for k in range(K)]     # d_con_k = 0 in sponge layers (dyn_core_nlm.F90:595-628)
+    pp = None
+    if pert is not None:
+        pp = dict(prm); pp.update(pert)
     names = list(f.keys())
     act = [n for n in names if not (hydrostatic and n == "w")]
     onames = ["delp_n", "pt_n", "u_n", "v_n", "fx", "fy", "crx", "cry", "xfx", "yfx"] + ([] if hydrostatic else ["w_n"]) + (["heat"] if d_con > 0.0 else [])
@@ -66,7 +70,7 @@ def _run_dsw(emu, hydrostatic, sponge, hord=2, d_con=0.0):
     def fn(*a):
         d = {n: torch.from_numpy(f[n]) for n in names}
         d.update(dict(zip(act, a)))
-        o = odsw.d_sw(d["delp"], d["pt"], d["u"], d["v"], d["w"], d["uc"], d["vc"], d["ua"], d["va"], d["divg_d"], g, dt, prm)
+        o = odsw.d_sw(d["delp"], d["pt"], d["u"], d["v"], d["w"], d["uc"], d["vc"], d["ua"], d["va"], d["divg_d"], g, dt, prm, pp)
         return tuple(o[key.get(k, k)] for k in onames)
     npx = N + 1
     C = (1, N, 1, N)
@@ -75,6 +79,9 @@ def _run_dsw(emu, hydrostatic, sponge, hord=2, d_con=0.0):
     outs = {k: outs[k] for k in onames}
     h = handle(N, K, emu)
     p = flat_params(prm, K); p["dt"] = dt; p["hydrostatic"] = int(hydrostatic)
+    if pert is not None:
+        for k_, v_ in flat_params({k: pp[k] for k in pert}, K).items():
+            p[k_ if k_ == "split_damp" else "p." + k_] = v_
     return check_module(h, "d_sw", N, K, f, act, outs, fn, p, rng, tol=2e-12, dot_tol=1e-12)
 
 
@@ -105,6 +112,29 @@ def test_d_sw_heat_emu(hydrostatic, sponge):
 @pytest.mark.gpu
 def test_d_sw_heat_gpu():
     _run_dsw(False, False, True, d_con=1.0)
+
+
+SPLIT_HORD = dict(hord_mt=[1, 333], hord_vt=[1, 333], hord_tm=[1, 1], hord_dp=[1, 333])
+SPLIT_DAMP = dict(split_damp=1, nord=[0, 0], d2_bg=[0.05, 0.02], nord_v=[0, 1], damp_v=[0.03, 0.001], nord_t=[0, 0], damp_t=[0.02, 0.001], dddmp=0.1, d4_bg=0.12)
+
+
+def test_d_sw_split_hord_emu():
+    """split_hord: the perturbation is transported with its own (different) linear scheme, linearised about the same inputs, while
+    the trajectory keeps the nonlinear model's scheme (model_tlmadm/sw_core_tlm.F90:1664-1682, 1987-1997)"""
+    _run_dsw(True, False, False, pert=SPLIT_HORD)
+
+
+def test_d_sw_split_damp_emu():
+    """split_damp: divergence / vorticity / tracer damping with the perturbation-side coefficients (sw_core_tlm.F90:2341-2366, 2436-2451)"""
+    _run_dsw(True, False, True, pert=SPLIT_DAMP)
+    both = dict(SPLIT_HORD); both.update(SPLIT_DAMP)
+    _run_dsw(True, True, False, pert=both)
+
+
+@pytest.mark.gpu
+def test_d_sw_split_gpu():
+    both = dict(SPLIT_HORD); both.update(SPLIT_DAMP)
+    _run_dsw(False, False, True, pert=both)
 
 
 def test_d_sw_hord333_emu():

@@ -41,6 +41,25 @@ def hydro_state(N, K, seed):
     return {k: a.numpy().copy() for k, a in t.items()}, rng
 
 
+def two_sided_params(cfg):
+    """oracle cfg -> module parameters: in two-sided mode the top-level switches are the perturbation model's and cfg["traj"]
+    the nonlinear model's ("t.<name>" parameters)"""
+    p = {k: v for k, v in cfg.items() if k != "traj"}
+    if cfg.get("traj"):
+        p["two_sided"] = 1
+        for k, v in cfg["traj"].items():
+            p["t." + k] = int(v) if isinstance(v, bool) else v
+    return p
+
+
+# perturbation-side switches like the defaults of fv_flags_pert_type (fv_arrays_tlmadm.F90:37-92) on a coarse test grid, with a
+# different set for the nonlinear model: split_hord (333 / 1 vs 2), split_damp (nord, coefficients, sponge depth)
+TWO_SIDED = dict(hord_mt=333, hord_vt=1, hord_tm=333, hord_dp=1, hord_tr=1, nord=1, dddmp=0.2, d2_bg=0.015, d4_bg=0.12, vtdm4=0.0008,
+                 do_vort_damp=True, d2_bg_k1=0.3, d2_bg_k2=0.2, d2_bg_ks=0.1, n_sponge=3, split_damp=True, hord_ks_pert=True, hord_ks_traj=True,
+                 traj=dict(hord_mt=2, hord_vt=2, hord_tm=2, hord_dp=2, hord_tr=2, nord=2, dddmp=0.1, d2_bg=0.01, d4_bg=0.15, vtdm4=0.0005,
+                           do_vort_damp=True, d2_bg_k1=0.2, d2_bg_k2=0.1, n_sponge=0))
+
+
 def _run(emu, n_split, K=3, modes=("nl", "tl", "ad"), extra=None):
     N = 12
     f, rng = hydro_state(N, K, 5)
@@ -60,7 +79,7 @@ def _run(emu, n_split, K=3, modes=("nl", "tl", "ad"), extra=None):
     outs = dict(u_n=(1, N, 1, npx), v_n=(1, npx, 1, N), pt_n=C, delp_n=C, mfx=(1, npx, 1, N), mfy=(1, N, 1, npx),
                 cx=(1, npx, -2, N + 3), cy=(-2, N + 3, 1, npx), pkz=C)
     h = handle(N, K, emu)
-    p = dict(cfg); p["do_vort_damp"] = 1; p["hydrostatic"] = 1
+    p = two_sided_params(cfg); p["do_vort_damp"] = int(cfg["do_vort_damp"]); p["hydrostatic"] = 1
     return check_module(h, "dyn_core", N, K, f, act, outs, fn, p, rng, tol=5e-11, dot_tol=1e-11, pert_scale=1e-3)
 
 
@@ -114,6 +133,17 @@ def _run_heat_update(emu, hydrostatic):
 @pytest.mark.parametrize("hydrostatic", [True, False])
 def test_heat_update_emu(hydrostatic):
     print(_run_heat_update(True, hydrostatic))
+
+
+def test_dyn_core_hydro_two_sided_emu():
+    """the TL/AD model's two sets of switches: perturbation schemes / damping for the increment, the nonlinear model's for the
+    trajectory (dyn_core_tlm.F90:740-926, sw_core_tlm.F90:1664-1682, 2341-2366)"""
+    print(_run(True, 2, K=5, extra=TWO_SIDED))
+
+
+@pytest.mark.gpu
+def test_dyn_core_hydro_two_sided_gpu():
+    _run(False, 2, K=5, extra=TWO_SIDED)
 
 
 def test_dyn_core_hydro_heat_emu():

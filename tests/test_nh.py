@@ -6,7 +6,7 @@ import torch
 from oracle import nh as onh
 from oracle.dyn_core import halo_of
 from common import metrics, ograd, handle, rnd, check_module
-from test_dyn_core import CFG, smooth
+from test_dyn_core import CFG, smooth, two_sided_params, TWO_SIDED
 from test_fv_dynamics import eta
 
 RD = 8314.47 / 28.965
@@ -140,7 +140,7 @@ def _run_dyn_nh(emu, n_split, a_imp=1.0, extra=None):
     C = (1, N, 1, N); npx = N + 1
     outs = dict(u_n=(1, N, 1, npx), v_n=(1, npx, 1, N), pt_n=C, delp_n=C, w_n=C, delz_n=C, mfx=(1, npx, 1, N), cx=(1, npx, -2, N + 3))
     h = handle(N, K, emu, ak, bk)
-    p = dict(cfg); p.update(do_vort_damp=1, hydrostatic=0)
+    p = two_sided_params(cfg); p.update(do_vort_damp=int(cfg["do_vort_damp"]), hydrostatic=0)
     return check_module(h, "dyn_core_nh", N, K, f, act, outs, fn, p, rng, tol=1e-9, dot_tol=1e-10, pert_scale=1e-3)
 
 
@@ -162,6 +162,16 @@ def test_riem_c_keeps_sim1_emu():
 
 def test_dyn_core_nh_sim_solver_emu():
     print(_run_dyn_nh(True, 2, 0.75))
+
+
+def test_dyn_core_nh_two_sided_emu():
+    """two sets of switches in the non-hydrostatic loop (adds the w transport and the zh transport of update_dz_d, nh_utils_tlm.F90:496)"""
+    print(_run_dyn_nh(True, 2, extra=TWO_SIDED))
+
+
+@pytest.mark.gpu
+def test_dyn_core_nh_two_sided_gpu():
+    _run_dyn_nh(False, 2, extra=TWO_SIDED)
 
 
 def test_dyn_core_nh_heat_emu():

@@ -10,6 +10,7 @@ from oracle.cubed_sphere import R
 from common import metrics, ograd, handle, rnd
 from test_dyn_core import CFG
 from test_fv_dynamics import eta, api_state, ZVIR
+from test_dyn_core import TWO_SIDED
 
 ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"]
 
@@ -23,7 +24,8 @@ def make(emu, N=12, K=4, n_split=2, k_split=1, nonhydro=False, extra=None):
     f, rng = api_state(N, K, 41, ak, bk, nonhydro)
     kw = dict(n_split=n_split, k_split=k_split, dt=900.0, ptop=ptop, d2_bg_k1=CFG["d2_bg_k1"], d2_bg_k2=CFG["d2_bg_k2"],
               kappa=CFG["akap"], cp=CFG["cp_air"], zvir=ZVIR, hydrostatic=0 if nonhydro else 1)
-    kw.update(extra or {})
+    for k_, v_ in (extra or {}).items():
+        kw[k_] = (tuple(sorted(v_.items())) if k_ == "traj" else int(v_) if isinstance(v_, bool) else v_)
     h = handle(N, K, emu, ak, bk, **kw)
     C = (slice(None), slice(None), R(1, N), R(1, N))
     comp = {k: np.ascontiguousarray(f[k][C]) for k in ACT}
@@ -35,7 +37,7 @@ def make(emu, N=12, K=4, n_split=2, k_split=1, nonhydro=False, extra=None):
     return h, f, comp, rng, cfg, ak, bk
 
 
-def _run(emu, nonhydro=False, extra=None):
+def _run(emu, nonhydro=False, extra=None, taylor=True):
     N, K = 12, 4
     h, f, comp, rng, cfg, ak, bk = make(emu, N, K, nonhydro=nonhydro, extra=extra)
     tol = 2e-9 if nonhydro else 2e-10
@@ -60,6 +62,8 @@ def _run(emu, nonhydro=False, extra=None):
     lhs = sum((mdx[k] * y[k]).sum() for k in ACT)
     rhs = sum((dx[k] * mty[k]).sum() for k in ACT)
     assert abs(lhs - rhs) <= (1e-10 if nonhydro else 1e-11) * max(abs(lhs), abs(rhs)), (lhs, rhs)
+    if not taylor:
+        return dict(dot=abs(lhs - rhs) / max(abs(lhs), abs(rhs)))
     # ---- Taylor test:  || N(x + e dx) - N(x) - e M dx || / || e M dx ||  = O(e)
     base = {k: np.zeros_like(comp[k]) for k in ACT}
     h.traj_get(1, base)
@@ -104,6 +108,12 @@ def test_step_api_d_con_emu():
     print(_run(True, nonhydro=True, extra=dict(d_con=1.0)))
 
 
+def test_step_api_two_sided_emu():
+    """fv3lm_config.two_sided: perturbation-model switches + the nonlinear model's in cfg.traj, through a whole non-hydrostatic step
+    (NL vs oracle, dot-product test; the Taylor test does not apply -- the TL is by design not the derivative of the trajectory scheme)"""
+    print(_run(True, nonhydro=True, extra=TWO_SIDED, taylor=False))
+
+
 def test_program_stats_emu():
     h, *_ = make(True)
     s = h.program_stats("step")
@@ -129,11 +139,11 @@ def test_step_api_emu_store_all_adjoint(monkeypatch):
     print(_run(True, True))
 
 
-def _repeat(emu, nonhydro):
+def _repeat(emu, nonhydro, extra=None):
     """repeated step_tl / step_ad calls on one handle: run 1 is eager, run 2 is captured into a CUDA graph and
     launched, later runs replay it (product build) -- every repetition must return the same bits"""
     N, K = 12, 4
-    h, f, comp, rng, cfg, ak, bk = make(emu, N, K, nonhydro=nonhydro)
+    h, f, comp, rng, cfg, ak, bk = make(emu, N, K, nonhydro=nonhydro, extra=extra)
     dx = {k: rng.standard_normal(comp[k].shape) * (np.abs(comp[k]).mean() * 1e-3) for k in ACT}
     y = {k: rng.standard_normal(comp[k].shape) for k in ACT}
     ref_tl = ref_ad = None
@@ -155,6 +165,17 @@ def _repeat(emu, nonhydro):
 
 def test_step_repeat_emu():
     _repeat(True, True)
+
+
+def test_step_repeat_two_sided_emu():
+    """detached views / skipped perturbation chains must not leave stale buffers behind between calls"""
+    _repeat(True, True, extra=TWO_SIDED)
+
+
+@pytest.mark.gpu
+def test_step_two_sided_gpu():
+    print(_run(False, nonhydro=True, extra=TWO_SIDED, taylor=False))
+    _repeat(False, True, extra=TWO_SIDED)
 
 
 @pytest.mark.gpu
