@@ -562,7 +562,9 @@ void Program::add(const char* nm, const typename S::P& prm, std::vector<int> ins
       FArr<S::NI> in, ind; FArr<S::NO> out, outd;
       for (int f = 0; f < S::NI; f++) { Value& v = P.vals[o.in[f]]; in.p[f] = v.traj; in.nk[f] = v.nk; ind.p[f] = v.active ? v.pert : nullptr; ind.nk[f] = v.nk; }
       for (int f = 0; f < S::NO; f++) { Value& v = P.vals[o.out[f]]; out.p[f] = v.traj; out.nk[f] = v.nk; outd.p[f] = v.active ? v.pert : nullptr; outd.nk[f] = v.nk; }
-      if (mode != MODE_TL) {
+      bool any_active = false;
+      for (int f = 0; f < S::NI; f++) any_active = any_active || ind.p[f];
+      if (mode != MODE_TL || !any_active) {      // nothing to propagate (e.g. the trajectory-scheme chain of a split transport): values only
         KernNL<S> k{p, g, P.dv->m, in, out, o.nk_launch};
         launch_stage(k, g.NX, g.NY, g.ntile, o.nk_launch);
       } else {

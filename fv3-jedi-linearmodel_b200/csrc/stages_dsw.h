@@ -322,6 +322,54 @@ template <int DIR> struct S_tpuv {
     }
     return tp::p1 * (Q(x, d - 1) + Q(x, d)) + tp::p2 * (Q(x, d - 2) + Q(x, d + 1));
   }
+  // bl, br of the cell at offset co (tile index ic) for iord >= 8; edge_row: the row / column is a cube edge (bl = br = 0 next to it)
+  template <class X> DEV static void mono(const X& x, int co, int ic, int np, bool edge_row, int ord, typename X::T& bl, typename X::T& br) {
+    using T = typename X::T;
+    using namespace tp;
+    constexpr double nz = 1.e-9;     // near_zero of sw_core (:37)
+    auto q = [&](int d) { return Q(x, co + d); };
+    auto dq = [&](int d) { return q(d + 1) - q(d); };
+    auto dm = [&](int d) {
+      T qm = q(d - 1), q0 = q(d), qp = q(d + 1);
+      T xt = 0.25 * (qp - qm);
+      return sgn_of(min3(m_abs(xt), max3(qm, q0, qp) - q0, q0 - min3(qm, q0, qp)), xt);
+    };
+    auto al = [&](int d) { return 0.5 * (q(d - 1) + q(d)) + r3 * (dm(d - 1) - dm(d)); };
+    auto two = [&](int d) {          // x0L + x0R at the cube edge between cells ic + d - 1 and ic + d
+      const double am = DD(x, co + d - 2), a0 = DD(x, co + d - 1), a1 = DD(x, co + d), a2 = DD(x, co + d + 1);
+      return 0.5 * ((2.0 * a0 + am) * q(d - 1) - a0 * q(d - 2)) / (a0 + am) + 0.5 * ((2.0 * a1 + a2) * q(d) - a1 * q(d + 1)) / (a1 + a2);
+    };
+    const T q0 = q(0);
+    if (ic >= 3 && ic <= np - 3) {
+      if (ord == 8) {
+        T xt = 2.0 * dm(0);
+        bl = T(0.0) - sgn_of(m_min(m_abs(xt), m_abs(al(0) - q0)), xt);
+        br = sgn_of(m_min(m_abs(xt), m_abs(al(1) - q0)), xt);
+      } else if (ord == 9 || ord == 10) {
+        bl = al(0) - q0; br = al(1) - q0;
+        bool lim = true;
+        if (ord == 10) {
+          lim = false;
+          if (val(m_abs(dm(0))) < nz) { if (val(m_abs(dm(-1))) + val(m_abs(dm(1))) < nz) { bl = T(0.0); br = T(0.0); } }
+          else if (fabs(3.0 * (val(bl) + val(br))) > fabs(val(bl) - val(br))) lim = true;
+        }
+        if (lim) {
+          T pmp_1 = T(0.0) - 2.0 * dq(0), lac_1 = pmp_1 + 1.5 * dq(1);
+          bl = m_min(max3(T(0.0), pmp_1, lac_1), m_max(bl, min3(T(0.0), pmp_1, lac_1)));
+          T pmp_2 = 2.0 * dq(-1), lac_2 = pmp_2 - 1.5 * dq(-2);
+          br = m_min(max3(T(0.0), pmp_2, lac_2), m_max(br, min3(T(0.0), pmp_2, lac_2)));
+        }
+      } else { bl = al(0) - q0; br = al(1) - q0; }
+      return;
+    }
+    if (ic == 2) { bl = (s15 * q(-1) + s11 * q0 - s14 * dm(0)) - q0; br = al(1) - q0; pert_ppm(q0, bl, br, -1); }
+    else if (ic == np - 2) { bl = al(0) - q0; br = (s15 * q(1) + s11 * q0 + s14 * dm(0)) - q0; pert_ppm(q0, bl, br, -1); }
+    else if (edge_row) { bl = T(0.0); br = T(0.0); }
+    else if (ic == 1) { bl = two(0) - q0; br = (s15 * q0 + s11 * q(1) - s14 * dm(1)) - q0; }
+    else if (ic == 0) { bl = s14 * dm(-1) - s11 * dq(-1); br = two(1) - q0; }
+    else if (ic == np - 1) { bl = (s15 * q0 + s11 * q(-1) + s14 * dm(-1)) - q0; br = two(1) - q0; }
+    else { bl = two(0) - q0; br = s11 * dq(0) - s14 * dm(1); }    // ic == np
+  }
   template <class X> DEV static void eval(X& x, const P& p) {
     using T = typename X::T;
     const Geom& g = x.g;
@@ -344,6 +392,14 @@ template <int DIR> struct S_tpuv {
     const int jt = DIR == 0 ? x.j : x.i;         // index across the sweep
     const int npt = DIR == 0 ? g.npy : g.npx;
     T bl, br;
+    if (ord >= 8) {
+      // monotone schemes of the nonlinear model (sw_core_nlm.F90 xtp_u :2166-2306, ytp_v :2548-2735): iord 8, 9, 10, else unlimited
+      mono(x, dc, ic, np, jt == 1 || jt == npt, ord, bl, br);
+      double rdm = DIR == 0 ? x.M(x.m.rdx, dc, 0) : x.M(x.m.rdy, 0, dc);
+      T cf = c * rdm;
+      x.out(0, pos ? uc + (1.0 - cf) * (br - cf * (bl + br)) : uc + (1.0 + cf) * (bl + cf * (bl + br)));
+      return;
+    }
     if ((ic == 0 || ic == 1 || ic == np - 1 || ic == np) && (jt == 1 || jt == npt)) { bl = T(0.0); br = T(0.0); }
     else { bl = face(x, dc) - uc; br = face(x, dc + 1) - uc; }
     T b0 = bl + br;

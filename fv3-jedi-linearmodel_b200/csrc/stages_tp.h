@@ -12,10 +12,15 @@ namespace fv3lm {
 struct LevOrd { signed char v[128]; };   // per-level scheme order (sponge layers differ)
 // hord = 333 (third-order linear scheme, tp_core_tlm.F90:2467-2488) is stored as ORD333 in a LevOrd
 constexpr int ORD333 = 3;
-inline int enc_hord(int hord) {
+// hord = 8 .. 13: the monotone PPM schemes of the nonlinear model (tp_core_nlm.F90:470-578), stored as they are.  They are only
+// legal on the trajectory side of a two-sided configuration: nothing is ever differentiated through them.
+inline bool hord_is_mono(int hord) { return hord >= 8 && hord <= 13; }
+inline int enc_hord(int hord, bool allow_mono = true) {
   if (hord == 1 || hord == 2) return hord;
   if (hord == 333) return ORD333;
-  throw std::runtime_error("hord must be 1, 2 or 333 (the linear schemes the TL/AD implement, tp_core_tlm.F90:2431-2488)");
+  if (allow_mono && hord_is_mono(hord)) return hord;
+  throw std::runtime_error("hord must be 1, 2 or 333 (the linear schemes the TL/AD implement, tp_core_tlm.F90:2431-2488)"
+                           " or, for the trajectory of a two-sided configuration, 8..13 (monotone PPM, tp_core_nlm.F90:470)");
 }
 
 namespace tp {
@@ -47,10 +52,89 @@ template <int DIR, class X> DEV typename X::T edge_al(const X& x, int f, int d) 
   return p1 * (Q<DIR>(x, f, d - 1) + Q<DIR>(x, f, d)) + p2 * (Q<DIR>(x, f, d - 2) + Q<DIR>(x, f, d + 1));
 }
 
+// ---- monotone PPM (iord = 8 .. 13) in perturbation form: bl = AL - q, br = AR - q of the cell at offset co from the current face
+// position.  tp_core_nlm.F90 xppm :470-569, yppm :780-893, pert_ppm :953-1012.  (dimensionless weights s11, s14, s15 :56)
+constexpr double s11 = 11.0 / 14.0, s14 = 4.0 / 7.0, s15 = 3.0 / 14.0, r3 = 1.0 / 3.0, near_zero = 1.e-25, ppm_fac = 1.5;
+template <class T> DEV T sgn_of(T a, T b) { T m = m_abs(a); return val(b) >= 0.0 ? m : T(0.0) - m; }      // Fortran SIGN(a, b)
+template <class T> DEV T max3(T a, T b, T c) { return m_max(m_max(a, b), c); }
+template <class T> DEV T min3(T a, T b, T c) { return m_min(m_min(a, b), c); }
+// pert_ppm: iv = 0 positive-definite constraint, else the standard PPM monotonicity constraint
+template <class T> DEV void pert_ppm(T a0, T& al, T& ar, int iv) {
+  if (iv == 0) {
+    if (val(a0) <= 0.0) { al = T(0.0); ar = T(0.0); return; }
+    T a4 = -3.0 * (ar + al), da1 = ar - al;
+    if (val(m_abs(da1)) < -val(a4)) {
+      T fmin = a0 + 0.25 / a4 * (da1 * da1) + a4 * (1.0 / 12.0);
+      if (val(fmin) < 0.0) {
+        if (val(ar) > 0.0 && val(al) > 0.0) { ar = T(0.0); al = T(0.0); }
+        else if (val(da1) > 0.0) ar = -2.0 * al;
+        else al = -2.0 * ar;
+      }
+    }
+  } else {
+    if (val(al) * val(ar) < 0.0) {
+      T da1 = al - ar, da2 = da1 * da1, a6da = 3.0 * (al + ar) * da1;
+      if (val(a6da) < -val(da2)) ar = -2.0 * al;
+      else if (val(a6da) > val(da2)) al = -2.0 * ar;
+    } else { al = T(0.0); ar = T(0.0); }
+  }
+}
+template <int DIR, class X> DEV void mono_blbr(const X& x, int fq, int co, int ord, typename X::T& bl, typename X::T& br) {
+  using T = typename X::T;
+  const int ia = (DIR == 0 ? x.i : x.j) + co, np = DIR == 0 ? x.g.npx : x.g.npy;
+  auto q = [&](int d) { return Q<DIR>(x, fq, co + d); };                      // q of cell ia + d
+  auto dm = [&](int d) {
+    T qm = q(d - 1), q0 = q(d), qp = q(d + 1);
+    T xt = 0.25 * (qp - qm);
+    return sgn_of(min3(m_abs(xt), max3(qm, q0, qp) - q0, q0 - min3(qm, q0, qp)), xt);
+  };
+  auto al = [&](int d) { return 0.5 * (q(d - 1) + q(d)) + r3 * (dm(d - 1) - dm(d)); };   // west / south edge value of cell ia + d
+  // mean of the two one-sided extrapolations to the cube edge between cells ia + d - 1 and ia + d, limited by the 4 cells around it
+  auto edge = [&](int d) {
+    const double am = DA<DIR>(x, co + d - 2), a0 = DA<DIR>(x, co + d - 1), a1 = DA<DIR>(x, co + d), a2 = DA<DIR>(x, co + d + 1);
+    T xt = 0.5 * (((2.0 * a0 + am) * q(d - 1) - a0 * q(d - 2)) / (am + a0) + ((2.0 * a1 + a2) * q(d) - a1 * q(d + 1)) / (a1 + a2));
+    xt = m_max(xt, m_min(m_min(q(d - 2), q(d - 1)), m_min(q(d), q(d + 1))));
+    xt = m_min(xt, m_max(m_max(q(d - 2), q(d - 1)), m_max(q(d), q(d + 1))));
+    return xt;
+  };
+  const T q0 = q(0);
+  if (ia >= 3 && ia <= np - 3) {
+    if (ord == 8 || ord == 11) {
+      T xt = (ord == 8 ? 2.0 : ppm_fac) * dm(0);
+      bl = T(0.0) - sgn_of(m_min(m_abs(xt), m_abs(al(0) - q0)), xt);
+      br = sgn_of(m_min(m_abs(xt), m_abs(al(1) - q0)), xt);
+    } else {
+      bl = al(0) - q0; br = al(1) - q0;
+      if (val(m_abs(dm(-1))) + val(m_abs(dm(0))) + val(m_abs(dm(1))) < near_zero) { bl = T(0.0); br = T(0.0); }
+      else if (fabs(3.0 * (val(bl) + val(br))) > fabs(val(bl) - val(br))) {
+        T pmp_2 = 2.0 * (q0 - q(-1)), lac_2 = pmp_2 - 0.75 * (2.0 * (q(-1) - q(-2)));
+        br = m_min(max3(T(0.0), pmp_2, lac_2), m_max(br, min3(T(0.0), pmp_2, lac_2)));
+        T pmp_1 = T(0.0) - 2.0 * (q(1) - q0), lac_1 = pmp_1 + 0.75 * (2.0 * (q(2) - q(1)));
+        bl = m_min(max3(T(0.0), pmp_1, lac_1), m_max(bl, min3(T(0.0), pmp_1, lac_1)));
+      }
+    }
+    if (ord == 9 || ord == 13) pert_ppm(q0, bl, br, 0);
+    return;
+  }
+  if (ia == 0) { bl = s14 * dm(-1) + s11 * (q(-1) - q0); br = edge(1) - q0; }
+  else if (ia == 1) { bl = edge(0) - q0; br = (s15 * q0 + s11 * q(1) - s14 * dm(1)) - q0; }
+  else if (ia == 2) { bl = (s15 * q(-1) + s11 * q0 - s14 * dm(0)) - q0; br = al(1) - q0; }
+  else if (ia == np - 2) { bl = al(0) - q0; br = (s15 * q(1) + s11 * q0 + s14 * dm(0)) - q0; }
+  else if (ia == np - 1) { bl = (s15 * q0 + s11 * q(-1) + s14 * dm(-1)) - q0; br = edge(1) - q0; }
+  else { bl = edge(0) - q0; br = s11 * (q(1) - q0) - s14 * dm(1); }     // ia == np
+  pert_ppm(q0, bl, br, 1);
+}
+
 // 1-D flux at the current face from q (input fq) and Courant number c
 template <int DIR, class X> DEV typename X::T ppm_flux(const X& x, int fq, typename X::T c, int ord) {
   using T = typename X::T;
   if (ord == 1) return val(c) > 0.0 ? Q<DIR>(x, fq, -1) : Q<DIR>(x, fq, 0);
+  if (ord >= 8) {
+    T bl, br;
+    if (val(c) > 0.0) { mono_blbr<DIR>(x, fq, -1, ord, bl, br); return Q<DIR>(x, fq, -1) + (1.0 - c) * (br - c * (bl + br)); }
+    mono_blbr<DIR>(x, fq, 0, ord, bl, br);
+    return Q<DIR>(x, fq, 0) + (1.0 + c) * (bl + c * (bl + br));
+  }
   if (ord == ORD333) {
     // perfectly linear third-order scheme, no cube-edge special cases (tp_core_tlm.F90:2467-2488, :2638-2660)
     T qm1 = Q<DIR>(x, fq, -1), q0 = Q<DIR>(x, fq, 0);

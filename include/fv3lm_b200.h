@@ -63,7 +63,8 @@ typedef struct fv3lm_config {
    * follow model_tlmadm/dyn_core_tlm.F90:740-926 separately for each side, and every operator whose switches differ is
    * evaluated twice -- perturbation scheme for the increment, nonlinear model's scheme for the trajectory
    * (model_tlmadm/sw_core_tlm.F90:1664-1682, 1987-1997, 2341-2366, 2436-2451).  two_sided = 0: one set of switches for both
-   * (TL = exact derivative of the nonlinear step).  traj.hord_* must be 1, 2 or 333 (monotone schemes are not built).      */
+   * (TL = exact derivative of the nonlinear step).  traj.hord_*: 1, 2, 333 or the monotone PPM schemes 8..13 of the nonlinear
+   * model (model/tp_core_nlm.F90:470-578, model/sw_core_nlm.F90:2166-2306); hord 3-7 are not built.                          */
   int two_sided, split_damp;
   int hord_ks_pert, hord_ks_traj;   /* first-order transport in the top n_sponge - 1 layers (hord_*_ks_* = 1), per side        */
   int reserved[2];

@@ -198,11 +198,66 @@ def xtp_u(c, u, g, iord):
     f_pos = um + (1. - cfl_p) * (br[..., is_ - 1: ie + 1] - cfl_p * b0[..., is_ - 1: ie + 1])
     f_neg = up_ + (1. + cfl_n) * (bl[..., is_: ie + 2] + cfl_n * b0[..., is_: ie + 2])
     f2 = torch.where(cc > 0., f_pos, f_neg)
+    table = {1: f1, 2: f2}
+    for o in set([iord] if isinstance(iord, int) else iord):
+        if 8 <= o <= 13:
+            # monotone schemes of the nonlinear model (sw_core_nlm.F90:2166-2306): iord 8, 9, 10, else unlimited
+            near_zero = 1.e-9
+            def DM(a, b):
+                xt = 0.25 * (U(a + 1, b + 1) - U(a - 1, b - 1)); c0 = U(a, b)
+                return tp._sign(tp._min3(xt.abs(), tp._max3(U(a - 1, b - 1), c0, U(a + 1, b + 1)) - c0, c0 - tp._min3(U(a - 1, b - 1), c0, U(a + 1, b + 1))), xt)
+            DQ = lambda a, b: U(a + 1, b + 1) - U(a, b)
+            alm = 0.5 * (U(lo - 1, hi) + U(lo, hi + 1)) + tp.R3 * (DM(lo - 1, hi) - DM(lo, hi + 1))
+            u0 = U(lo, hi)
+            mbl, mbr = alm[..., :-1] - u0, alm[..., 1:] - u0
+            z = torch.zeros_like(mbl)
+            if o == 8:
+                xt = 2. * DM(lo, hi)
+                mbl, mbr = -tp._sign(torch.minimum(xt.abs(), mbl.abs()), xt), tp._sign(torch.minimum(xt.abs(), mbr.abs()), xt)
+            elif o in (9, 10):
+                pmp_1 = -2. * DQ(lo, hi); lac_1 = pmp_1 + 1.5 * DQ(lo + 1, hi + 1)
+                bl_l = torch.minimum(tp._max3(z, pmp_1, lac_1), torch.maximum(mbl, tp._min3(z, pmp_1, lac_1)))
+                pmp_2 = 2. * DQ(lo - 1, hi - 1); lac_2 = pmp_2 - 1.5 * DQ(lo - 2, hi - 2)
+                br_l = torch.minimum(tp._max3(z, pmp_2, lac_2), torch.maximum(mbr, tp._min3(z, pmp_2, lac_2)))
+                if o == 9:
+                    mbl, mbr = bl_l, br_l
+                else:
+                    small = DM(lo, hi).abs() < near_zero
+                    flat = (DM(lo - 1, hi - 1).abs() + DM(lo + 1, hi + 1).abs()) < near_zero
+                    lim = (3. * (mbl + mbr)).abs() > (mbl - mbr).abs()
+                    mbl, mbr = (torch.where(small, torch.where(flat, z, mbl), torch.where(lim, bl_l, mbl)),
+                                torch.where(small, torch.where(flat, z, mbr), torch.where(lim, br_l, mbr)))
+            mbl = list(torch.unbind(mbl, -1)); mbr = list(torch.unbind(mbr, -1))
+            dmv = list(torch.unbind(DM(-1, npx + 1), -1)); dm = lambda i: dmv[i + 1]
+            def x0(i):      # x0L + x0R at the cube edge between cells i-1 and i (no limiter here)
+                return (0.5 * ((2. * d1(i - 1) + d1(i - 2)) * u1(i - 1) - d1(i - 1) * u1(i - 2)) / (d1(i - 1) + d1(i - 2)) +
+                        0.5 * ((2. * d1(i) + d1(i + 1)) * u1(i) - d1(i) * u1(i + 1)) / (d1(i) + d1(i + 1)))
+            mbr[2] = alm[..., 3] - u1(2)
+            xt = tp.S15 * u1(1) + tp.S11 * u1(2) - tp.S14 * dm(2)
+            mbl[2] = xt - u1(2); mbr[1] = xt - u1(1)
+            mbl[0] = tp.S14 * dm(-1) - tp.S11 * (u1(0) - u1(-1))
+            xt = x0(1)
+            mbr[0] = xt - u1(0); mbl[1] = xt - u1(1)
+            mbl[npx - 2] = alm[..., npx - 2] - u1(npx - 2)
+            xt = tp.S15 * u1(npx - 1) + tp.S11 * u1(npx - 2) + tp.S14 * dm(npx - 2)
+            mbr[npx - 2] = xt - u1(npx - 2); mbl[npx - 1] = xt - u1(npx - 1)
+            mbr[npx] = tp.S11 * (u1(npx + 1) - u1(npx)) - tp.S14 * dm(npx + 1)
+            xt = x0(npx)
+            mbr[npx - 1] = xt - u1(npx - 1); mbl[npx] = xt - u1(npx)
+            for i in (0, 1, npx - 1, npx):
+                mbl[i] = zrow(mbl[i]); mbr[i] = zrow(mbr[i])
+            for i in (2, npx - 2):
+                mbl[i], mbr[i] = tp.pert_ppm(u1(i), mbl[i], mbr[i], -1)
+            mbl = torch.stack(mbl, -1); mbr = torch.stack(mbr, -1)
+            fp = um + (1. - cfl_p) * (mbr[..., is_ - 1: ie + 1] - cfl_p * (mbl[..., is_ - 1: ie + 1] + mbr[..., is_ - 1: ie + 1]))
+            fn_ = up_ + (1. + cfl_n) * (mbl[..., is_: ie + 2] + cfl_n * (mbl[..., is_: ie + 2] + mbr[..., is_: ie + 2]))
+            table[o] = torch.where(cc > 0., fp, fn_)
     # iord = 333 (sw_core_tlm.F90:7332-7356): third-order linear, Courant number c * rdx of the upwind cell
     umm = S(u, is_ - 2, ie - 1, j0, j1); upp = S(u, is_ + 1, ie + 2, j0, j1)
     f3 = torch.where(cc > 0., (2.0 * up_ + 5.0 * um - umm) / 6.0 - 0.5 * cfl_p * (up_ - um) + cfl_p * cfl_p / 6.0 * (up_ - 2.0 * um + umm),
                      (2.0 * um + 5.0 * up_ - upp) / 6.0 - 0.5 * cfl_n * (up_ - um) + cfl_n * cfl_n / 6.0 * (upp - 2.0 * up_ + um))
-    return put(Z(u), is_, ie + 1, j0, j1, tp.select_ord(iord, {1: f1, 2: f2, 333: f3}))
+    table[333] = f3
+    return put(Z(u), is_, ie + 1, j0, j1, tp.select_ord(iord, table))
 
 
 def ytp_v(c, v, g, jord):

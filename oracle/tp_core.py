@@ -72,6 +72,102 @@ def _al_x(q, dxa, npx, i0, i1, j0, j1):
     return torch.stack(cols, dim=-1)     # [..., nj, npx+2]
 
 
+S11, S14, S15, R3 = 11. / 14., 4. / 7., 3. / 14., 1. / 3.
+
+
+def _sign(a, b):
+    """Fortran SIGN(a, b)"""
+    return torch.where(b >= 0., a.abs(), -a.abs())
+
+
+def _max3(a, b, c):
+    return torch.maximum(torch.maximum(a, b), c)
+
+
+def _min3(a, b, c):
+    return torch.minimum(torch.minimum(a, b), c)
+
+
+def pert_ppm(a0, al, ar, iv):
+    """tp_core_nlm.F90:953-1012"""
+    z = torch.zeros_like(al)
+    if iv == 0:
+        a4 = -3. * (ar + al); da1 = ar - al
+        fmin = a0 + 0.25 / torch.where(a4 == 0., torch.ones_like(a4), a4) * da1 ** 2 + a4 * (1. / 12.)
+        act = (da1.abs() < -a4) & (fmin < 0.)
+        both = (ar > 0.) & (al > 0.)
+        ar_n = torch.where(act, torch.where(both, z, torch.where(da1 > 0., -2. * al, ar)), ar)
+        al_n = torch.where(act, torch.where(both, z, torch.where(da1 > 0., al, -2. * ar)), al)
+        neg = a0 <= 0.
+        return torch.where(neg, z, al_n), torch.where(neg, z, ar_n)
+    da1 = al - ar; da2 = da1 ** 2; a6da = 3. * (al + ar) * da1
+    ar_n = torch.where(a6da < -da2, -2. * al, ar)
+    al_n = torch.where((a6da >= -da2) & (a6da > da2), -2. * ar, al)
+    opp = al * ar < 0.
+    return torch.where(opp, al_n, z), torch.where(opp, ar_n, z)
+
+
+def _mono_blbr_x(q, dxa, npx, j0, j1, iord):
+    """monotone PPM (iord 8..13) in perturbation form, tp_core_nlm.F90:470-569: bl, br of the cells i = 0 .. npx (last dim index = i)"""
+    near_zero, ppm_fac = 1.e-25, 1.5
+    def Q(a, b):
+        return q[..., R(j0, j1), R(a, b)]
+    def q1(i): return q[..., R(j0, j1), i + NG - 1]
+    def d1(i): return dxa[..., R(j0, j1), i + NG - 1]
+    def DM(a, b):       # dm(a..b)
+        xt = 0.25 * (Q(a + 1, b + 1) - Q(a - 1, b - 1))
+        c0 = Q(a, b)
+        return _sign(_min3(xt.abs(), _max3(Q(a - 1, b - 1), c0, Q(a + 1, b + 1)) - c0, c0 - _min3(Q(a - 1, b - 1), c0, Q(a + 1, b + 1))), xt)
+    lo, hi = 0, npx
+    al = 0.5 * (Q(lo - 1, hi) + Q(lo, hi + 1)) + R3 * (DM(lo - 1, hi) - DM(lo, hi + 1))      # al(lo .. hi+1)
+    q0 = Q(lo, hi)
+    al0, al1 = al[..., :-1], al[..., 1:]
+    dm0 = DM(lo, hi)
+    if iord in (8, 11):
+        xt = (2. if iord == 8 else ppm_fac) * dm0
+        bl = -_sign(torch.minimum(xt.abs(), (al0 - q0).abs()), xt)
+        br = _sign(torch.minimum(xt.abs(), (al1 - q0).abs()), xt)
+    else:
+        bl = al0 - q0; br = al1 - q0
+        dq = lambda a, b: 2. * (Q(a + 1, b + 1) - Q(a, b))
+        pmp_2 = dq(lo - 1, hi - 1); lac_2 = pmp_2 - 0.75 * dq(lo - 2, hi - 2)
+        z = torch.zeros_like(bl)
+        br_l = torch.minimum(_max3(z, pmp_2, lac_2), torch.maximum(br, _min3(z, pmp_2, lac_2)))
+        pmp_1 = -dq(lo, hi); lac_1 = pmp_1 + 0.75 * dq(lo + 1, hi + 1)
+        bl_l = torch.minimum(_max3(z, pmp_1, lac_1), torch.maximum(bl, _min3(z, pmp_1, lac_1)))
+        flat = (DM(lo - 1, hi - 1).abs() + dm0.abs() + DM(lo + 1, hi + 1).abs()) < near_zero
+        lim = (3. * (bl + br)).abs() > (bl - br).abs()
+        bl, br = torch.where(flat, z, torch.where(lim, bl_l, bl)), torch.where(flat, z, torch.where(lim, br_l, br))
+    if iord in (9, 13):
+        bl, br = pert_ppm(q0, bl, br, 0)
+    bl = list(torch.unbind(bl, -1)); br = list(torch.unbind(br, -1))
+    dmv = list(torch.unbind(DM(-1, npx + 1), -1))
+    dm = lambda i: dmv[i + 1]
+    alv = lambda i: al[..., i - lo]
+    def two_sided(i):   # edge between cells i-1 and i, limited by the four cells around it
+        xt = 0.5 * (((2. * d1(i - 1) + d1(i - 2)) * q1(i - 1) - d1(i - 1) * q1(i - 2)) / (d1(i - 2) + d1(i - 1)) +
+                    ((2. * d1(i) + d1(i + 1)) * q1(i) - d1(i) * q1(i + 1)) / (d1(i) + d1(i + 1)))
+        xt = torch.maximum(xt, torch.minimum(torch.minimum(q1(i - 2), q1(i - 1)), torch.minimum(q1(i), q1(i + 1))))
+        return torch.minimum(xt, torch.maximum(torch.maximum(q1(i - 2), q1(i - 1)), torch.maximum(q1(i), q1(i + 1))))
+    # west edge
+    bl[0] = S14 * dm(-1) + S11 * (q1(-1) - q1(0))
+    xt = two_sided(1)
+    br[0] = xt - q1(0); bl[1] = xt - q1(1)
+    xt = S15 * q1(1) + S11 * q1(2) - S14 * dm(2)
+    br[1] = xt - q1(1); bl[2] = xt - q1(2)
+    br[2] = alv(3) - q1(2)
+    # east edge
+    bl[npx - 2] = alv(npx - 2) - q1(npx - 2)
+    xt = S15 * q1(npx - 1) + S11 * q1(npx - 2) + S14 * dm(npx - 2)
+    br[npx - 2] = xt - q1(npx - 2); bl[npx - 1] = xt - q1(npx - 1)
+    xt = two_sided(npx)
+    br[npx - 1] = xt - q1(npx - 1); bl[npx] = xt - q1(npx)
+    br[npx] = S11 * (q1(npx + 1) - q1(npx)) - S14 * dm(npx + 1)
+    for i in (0, 1, 2, npx - 2, npx - 1, npx):
+        bl[i], br[i] = pert_ppm(q1(i), bl[i], br[i], 1)
+    return torch.stack(bl, -1), torch.stack(br, -1)
+
+
 def xppm(q, c, iord, g, j0, j1):
     """flux(is:ie+1, j0:j1).  q, c: full arrays.  iord: python int or per-level list (len K).
     Returns a full-size array with the flux stored on its range (zero elsewhere)."""
@@ -94,7 +190,14 @@ def xppm(q, c, iord, g, j0, j1):
     qpp = q[..., R(j0, j1), R(is_ + 1, ie + 2)]
     f3 = torch.where(cc > 0., (2.0 * qp + 5.0 * qm - qmm) / 6.0 - 0.5 * cc * (qp - qm) + cc * cc / 6.0 * (qp - 2.0 * qm + qmm),
                      (2.0 * qm + 5.0 * qp - qpp) / 6.0 - 0.5 * cc * (qp - qm) + cc * cc / 6.0 * (qpp - 2.0 * qp + qm))
-    out[..., R(j0, j1), R(is_, ie + 1)] = select_ord(iord, {1: up, 2: f2, 333: f3})
+    table = {1: up, 2: f2, 333: f3}
+    for o in set([iord] if isinstance(iord, int) else iord):
+        if 8 <= o <= 13:       # monotone schemes of the nonlinear model (trajectory side of a two-sided configuration)
+            bl, br = _mono_blbr_x(q, g.dxa, npx, j0, j1, o)          # index = Fortran i (0..npx)
+            blm, brm = bl[..., is_ - 1: ie + 1], br[..., is_ - 1: ie + 1]
+            bl0, br0 = bl[..., is_: ie + 2], br[..., is_: ie + 2]
+            table[o] = torch.where(cc > 0., qm + (1. - cc) * (brm - cc * (blm + brm)), qp + (1. + cc) * (bl0 + cc * (bl0 + br0)))
+    out[..., R(j0, j1), R(is_, ie + 1)] = select_ord(iord, table)
     return out
 
 

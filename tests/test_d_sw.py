@@ -131,6 +131,22 @@ def test_d_sw_split_damp_emu():
     _run_dsw(True, True, False, pert=both)
 
 
+LIN2 = dict(hord_mt=[2, 2], hord_vt=[2, 2], hord_tm=[2, 2], hord_dp=[2, 2])
+
+
+@pytest.mark.parametrize("hord", [8, 9, 10])
+def test_d_sw_monotone_trajectory_emu(hord):
+    """operational-like split: the trajectory runs the nonlinear model's monotone PPM (hord 8 / 9 / 10 in fv_tp_2d and xtp_u / ytp_v),
+    the perturbation the linear scheme hord_pert = 2 linearised about it (fv_arrays_tlmadm.F90:40-46)"""
+    _run_dsw(True, False, True, hord=hord, pert=LIN2)
+
+
+@pytest.mark.gpu
+def test_d_sw_monotone_trajectory_gpu():
+    _run_dsw(False, False, True, hord=10, pert=LIN2)
+    _run_dsw(False, True, False, hord=9, pert=LIN2)
+
+
 @pytest.mark.gpu
 def test_d_sw_split_gpu():
     both = dict(SPLIT_HORD); both.update(SPLIT_DAMP)

@@ -60,6 +60,15 @@ TWO_SIDED = dict(hord_mt=333, hord_vt=1, hord_tm=333, hord_dp=1, hord_tr=1, nord
                            do_vort_damp=True, d2_bg_k1=0.2, d2_bg_k2=0.1, n_sponge=0))
 
 
+# operational-like: perturbation flags at the defaults of fv_flags_pert_type (linear hord 2, first-order sponge transport) around a
+# trajectory that runs the nonlinear model's default monotone schemes (hord_mt = hord_vt = hord_tm = hord_dp = 9, hord_tr = 12,
+# model/fv_arrays_nlm.F90:264-277)
+TWO_SIDED_MONO = dict(hord_mt=2, hord_vt=2, hord_tm=2, hord_dp=2, hord_tr=2, nord=1, dddmp=0.2, d2_bg=0.015, d4_bg=0.15, vtdm4=0.0005,
+                      do_vort_damp=True, d2_bg_k1=0.3, d2_bg_k2=0.2, d2_bg_ks=0.1, n_sponge=2, split_damp=True, hord_ks_pert=True, hord_ks_traj=True,
+                      traj=dict(hord_mt=9, hord_vt=9, hord_tm=9, hord_dp=9, hord_tr=12, nord=1, dddmp=0.0, d2_bg=0.0, d4_bg=0.16, vtdm4=0.0005,
+                                do_vort_damp=True, d2_bg_k1=0.2, d2_bg_k2=0.1, n_sponge=1))
+
+
 def _run(emu, n_split, K=3, modes=("nl", "tl", "ad"), extra=None):
     N = 12
     f, rng = hydro_state(N, K, 5)

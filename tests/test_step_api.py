@@ -10,7 +10,7 @@ from oracle.cubed_sphere import R
 from common import metrics, ograd, handle, rnd
 from test_dyn_core import CFG
 from test_fv_dynamics import eta, api_state, ZVIR
-from test_dyn_core import TWO_SIDED
+from test_dyn_core import TWO_SIDED, TWO_SIDED_MONO
 
 ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"]
 
@@ -112,6 +112,18 @@ def test_step_api_two_sided_emu():
     """fv3lm_config.two_sided: perturbation-model switches + the nonlinear model's in cfg.traj, through a whole non-hydrostatic step
     (NL vs oracle, dot-product test; the Taylor test does not apply -- the TL is by design not the derivative of the trajectory scheme)"""
     print(_run(True, nonhydro=True, extra=TWO_SIDED, taylor=False))
+
+
+@pytest.mark.parametrize("nonhydro", [False, True])
+def test_step_api_monotone_trajectory_emu(nonhydro):
+    """operational-like configuration: the nonlinear model's default monotone schemes for the trajectory (hord 9 / 12), linear
+    perturbation schemes; step_nl vs the oracle and the dot-product test of TL / AD"""
+    print(_run(True, nonhydro=nonhydro, extra=TWO_SIDED_MONO, taylor=False))
+
+
+@pytest.mark.gpu
+def test_step_api_monotone_trajectory_gpu():
+    print(_run(False, nonhydro=True, extra=TWO_SIDED_MONO, taylor=False))
 
 
 def test_program_stats_emu():

@@ -73,6 +73,36 @@ def _run(emu, hord):
     assert abs(lhs - rhs) <= 1e-13 * max(abs(lhs), abs(rhs))
 
 
+def _run_mono(emu, hord, seed=1234, positive=True):
+    """monotone PPM schemes of the nonlinear model (hord 8..13, tp_core_nlm.F90:470-578): trajectory values only"""
+    N, K = 12, 3
+    f, rng = _inputs(N, K, seed)
+    if not positive:
+        f["q"] = f["q"] - 10.0          # sign changes: exercises the positive-definite constraint of hord 9 / 13
+    f["q"][:, 0] = np.round(f["q"][:, 0])   # plateaus: dm = 0, bl * br >= 0 branches
+    names, fn = _oracle(f, N, hord)
+    tin = [torch.from_numpy(f[n].copy()) for n in names]
+    h = handle(N, K, emu)
+    traj = {n: f[n].copy() for n in names}; traj.update(fx=np.zeros_like(f["q"]), fy=np.zeros_like(f["q"]))
+    h.module_run("fv_tp_2d", fv3lm.MODE_NL, traj, params={"hord": hord})
+    fx_o, fy_o = fn(*tin)
+    assert relerr(region(traj["fx"], 1, N + 1, 1, N), region(fx_o.numpy(), 1, N + 1, 1, N)) < TOL
+    assert relerr(region(traj["fy"], 1, N, 1, N + 1), region(fy_o.numpy(), 1, N, 1, N + 1)) < TOL
+
+
+@pytest.mark.parametrize("hord", [8, 9, 10, 11, 12, 13])
+def test_fv_tp_2d_monotone_emu(hord):
+    _run_mono(True, hord)
+    _run_mono(True, hord, seed=99, positive=False)
+
+
+@pytest.mark.gpu
+def test_fv_tp_2d_monotone_gpu():
+    for hord in (8, 9, 10, 13):
+        _run_mono(False, hord)
+        _run_mono(False, hord, seed=99, positive=False)
+
+
 @pytest.mark.parametrize("hord", [1, 2, 333])
 def test_fv_tp_2d_emu(hord):
     _run(True, hord)
