@@ -99,6 +99,12 @@ def run_gpu(args):
     mc = model_config(N, K, hydro, dt)
     ak, bk = S.eta_levels(K)
     M = G.build_metrics(N)
+    if args.two_sided:
+        # perturbation side = defaults of fv_flags_pert_type, trajectory side = defaults of fv_flags_type with the
+        # synthetic run's sponge coefficients
+        mc.update(split_damp=1, hord_ks_pert=1, hord_ks_traj=1, n_sponge=9, d2_bg_ks=2.0, d2_bg_k1=4.0, d2_bg_k2=2.0,
+                  traj=dict(hord_mt=9, hord_vt=9, hord_tm=9, hord_dp=9, hord_tr=12, nord=1, do_vort_damp=0, n_sponge=1,
+                            dddmp=0.0, d2_bg=0.0, d4_bg=0.16, vtdm4=0.0, d2_bg_k1=0.20, d2_bg_k2=0.10))
     cfg = fv3lm.default_config(N, K, rank=rank, nranks=world, layout_x=args.layout[0], layout_y=args.layout[1], **mc)
     h = fv3lm.FV3LM(cfg, ak, bk)
     if world > 1:
@@ -138,7 +144,7 @@ def run_gpu(args):
     ms_step = ms_tl + ms_ad
     if args.kernel_only:
         if rank == 0:
-            print(json.dumps({"kernel_only": True, "tl_ms": ms_tl, "ad_ms": ms_ad, "gpu_launches": int(launches)}))
+            print(json.dumps({"kernel_only": True, "two_sided": bool(args.two_sided), "res": N, "tl_ms": ms_tl, "ad_ms": ms_ad, "gpu_launches": int(launches)}))
         return
     # ---- end to end through the host-pointer ABI: trajectory + increments cross PCIe every step
     hp = {k: pinned(st[k].shape) for k in fields}
@@ -307,6 +313,9 @@ def main():
     ap.add_argument("--layout", type=int, nargs=2, default=[0, 0], help="force the tile layout (default: chosen from the number of ranks)")
     ap.add_argument("--profile-out", default=None, help="write the full per-op profile table to this file")
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: only the device-resident timed loop (used under ncu)")
+    ap.add_argument("--two-sided", action="store_true",
+                    help="side measurement (not the headline): the reference's default split configuration -- monotone hord 9 / 12 trajectory, "
+                         "linear hord 2 perturbation with its own damping and a 9-layer first-order sponge (fv_arrays_tlmadm.F90:37-92)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -176,7 +176,7 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
   TpOut fv = tp_site(avort, -1, -1, -1, same_ord(prm.hord_vt, pp.hord_vt, nk), pp.hord_vt, pp.nord_v, nodamp, prm.hord_vt, prm.nord_v, nodamp, tag + ".tp_vort");
   // vorticity damping: the trajectory with (nord_v, damp_v), the perturbation with the perturbation-side pair (:2436-2451)
   int ut3 = wk, vt3 = wk;
-  LevD vd_on; for (int k = 0; k < 96; k++) vd_on.v[k] = 0.0;
+  LevD vd_on, on_traj; for (int k = 0; k < 96; k++) vd_on.v[k] = on_traj.v[k] = 0.0;
   {
     auto del6v = [&](const DswParams& q, int wk, LevD* on, const std::string& tg) -> std::pair<int, int> {
       LevOrd nv; LevD d4; bool any = false;
@@ -189,14 +189,21 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
     };
     if (same_ord(prm.nord_v, pp.nord_v, nk) && same_lev(prm.damp_v, pp.damp_v, nk)) {
       auto f = del6v(prm, wk, &vd_on, tag + ".del6v"); ut3 = f.first; vt3 = f.second;
+      on_traj = vd_on;
     } else {
+      // each side adds its flux only on the levels where its own damping is on (:2506-2530): the reference's defaults have it on
+      // for the perturbation (do_vort_damp_pert = T) and off for the trajectory (do_vort_damp = F)
       LevD on_p; for (int k = 0; k < 96; k++) on_p.v[k] = 0.0;
       P.tl_only = true;
       auto a = del6v(pp, wk, &on_p, tag + ".del6v_p");
       P.tl_only = false;
-      auto b = del6v(prm, D(wk), &vd_on, tag + ".del6v_t");
-      if (!same_lev(on_p, vd_on, nk)) throw std::runtime_error("d_sw: vorticity damping must be switched on for the same levels on the trajectory and perturbation sides");
-      if (a.first != wk) { ut3 = splice(a.first, b.first, tag + ".ut3"); vt3 = splice(a.second, b.second, tag + ".vt3"); }
+      auto b = del6v(prm, D(wk), &on_traj, tag + ".del6v_t");
+      LevMask ma, mb;
+      for (int k = 0; k < 128; k++) { ma.v[k] = (k < 96 && on_p.v[k] != 0.0) ? 1 : 0; mb.v[k] = (k < 96 && on_traj.v[k] != 0.0) ? 1 : 0; }
+      for (int k = 0; k < 96; k++) vd_on.v[k] = (on_p.v[k] != 0.0 || on_traj.v[k] != 0.0) ? 1.0 : 0.0;
+      ut3 = P.val(tag + ".ut3", nk); vt3 = P.val(tag + ".vt3", nk);
+      P.add<S_splice_lev>("splice_lev", {ma, mb}, {a.first, b.first}, {ut3}, nk);
+      P.add<S_splice_lev>("splice_lev", {ma, mb}, {a.second, b.second}, {vt3}, nk);
     }
   }
   o.u = P.val(nm("u"), nk); o.v = P.val(nm("v"), nk);
@@ -205,7 +212,7 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
     // the reference reads the del6_vt_flux output whether or not the vorticity damping ran (:1496-1506): without it the arrays
     // hold unrelated winds, so that combination is refused
     for (int k = 0; k < nk; k++)
-      if (prm.d_con.v[k] > 1.e-5 && vd_on.v[k] == 0.0) throw std::runtime_error("d_sw: d_con > 0 needs the vorticity damping (do_vort_damp, vtdm4 > 1e-5) on every level outside the sponge");
+      if (prm.d_con.v[k] > 1.e-5 && on_traj.v[k] == 0.0) throw std::runtime_error("d_sw: d_con > 0 needs the vorticity damping (do_vort_damp, vtdm4 > 1e-5) on every level outside the sponge");
     int ubh = P.val(nm("ubh"), nk), fyh = P.val(nm("fyh"), nk), vbh = P.val(nm("vbh"), nk), fxh = P.val(nm("fxh"), nk);
     P.add<S_dheat_edge>("dheat_edge", {0}, {u, v, ke, vd, fv.fx, fv.fy, ut3, vt3}, {ubh, fyh, vbh, fxh}, nk);
     o.heat = P.val(nm("heat_s"), nk);

@@ -146,6 +146,8 @@ void Program::release(int id) {
 void Program::run_op(Op& op, int mode) {
   if (op.tl_only && mode == MODE_NL) return;          // perturbation-scheme chain: nothing of it is needed by a trajectory sweep
   for (int i : op.in) if (vals[i].alias >= 0) vals[i].traj = vals[vals[i].alias].traj;
+  static const bool trace = getenv("FV3LM_TRACE") != nullptr;      // debugging aid: the op sequence on stderr
+  if (trace) fprintf(stderr, "fv3lm op %-24s mode %d\n", op.name.c_str(), mode);
 #ifdef FV3LM_HOST_EMU
   static const bool nancheck = getenv("FV3LM_NANCHECK") != nullptr;
   if (nancheck && mode == MODE_AD) {

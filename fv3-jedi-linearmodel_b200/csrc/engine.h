@@ -540,6 +540,21 @@ struct S_splice {
     else x.out(0, with_val(x.in(0), val(x.in(1))));
   }
 };
+// the same with per-level switches: a side that is switched off on a level contributes an exact zero there (its chain wrote
+// nothing on that level).  Vorticity damping fluxes, model_tlmadm/sw_core_tlm.F90:2436-2451, 2506-2530.
+struct LevMask { unsigned char v[128]; };
+struct S_splice_lev {
+  static constexpr int NI = 2, NO = 1;
+  struct P { LevMask on_a, on_b; };
+  static constexpr int NT = 2;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const bool a = p.on_a.v[x.kk] != 0, b = p.on_b.v[x.kk] != 0;
+    if constexpr (X::mode == 0) x.out(0, b ? x.in(1) : T(0.0));
+    else x.out(0, with_val(a ? x.in(0) : T(0.0), b ? val(x.in(1)) : 0.0));
+  }
+};
 
 struct Device {
   Geom g;

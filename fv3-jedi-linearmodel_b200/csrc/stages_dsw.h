@@ -264,8 +264,9 @@ struct S_dupd {
     x.out(1, ptd / dpn);
     if (p.nonhydro) {
       T wd = dp * x.in(2) + ((x.in(7) - x.in(7, 1, 0)) + (x.in(8) - x.in(8, 0, 1))) * ra;
-      T dw = ((x.in(9) - x.in(9, 1, 0)) + (x.in(10) - x.in(10, 0, 1))) * ra * p.dw_on.v[x.kk];
-      x.out(2, wd / dpn + dw);
+      // (levels without w damping: the del6 flux arrays were not written there -- or do not exist at all -- and are not read)
+      if (p.dw_on.v[x.kk] != 0.0) x.out(2, wd / dpn + ((x.in(9) - x.in(9, 1, 0)) + (x.in(10) - x.in(10, 0, 1))) * ra);
+      else x.out(2, wd / dpn);
     }
   }
 };

@@ -483,18 +483,17 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm, pp=None):
     un_pre, vn_pre = un, vn
     # ---- vorticity damping (:1487-1539)
     dmpv = prm["damp_v"]; nordv = prm["nord_v"]
-    if any(d > 1.e-5 for d in dmpv):
-        def del6v(p):
+    if any(d > 1.e-5 for d in dmpv) or any(d > 1.e-5 for d in pp["damp_v"]):
+        def del6v(p):       # levels whose damping is off get damp4 = 0: exact zero fluxes there
             d4 = [(p["damp_v"][k] * g.da_min_c) ** (p["nord_v"][k] + 1) if p["damp_v"][k] > 1.e-5 else 0.0 for k in range(K)]
-            return del6_by_level(p["nord_v"], d4, wk, g)
+            return del6_by_level([p["nord_v"][k] if p["damp_v"][k] > 1.e-5 else 0 for k in range(K)], d4, wk, g)
         ut3, vt3 = del6v(prm)
-        if pp["nord_v"] != nordv or pp["damp_v"] != dmpv:      # the perturbation always uses its own pair (:2436-2451)
-            assert [d > 1.e-5 for d in pp["damp_v"]] == [d > 1.e-5 for d in dmpv]
+        if pp["nord_v"] != nordv or pp["damp_v"] != dmpv:
+            # the perturbation always uses its own pair, each side only on the levels where its damping is on (:2436-2451, 2506-2530)
             ua3, va3 = del6v(pp)
             ut3, vt3 = splice(ua3, ut3), splice(va3, vt3)
-        on = _lv([1.0 if dmpv[k] > 1.e-5 else 0.0 for k in range(K)])
-        un = un + on * S(vt3, is_, ie, js, je + 1)
-        vn = vn - on * S(ut3, is_, ie + 1, js, je)
+        un = un + S(vt3, is_, ie, js, je + 1)
+        vn = vn - S(ut3, is_, ie + 1, js, je)
     u_new = put(u, is_, ie, js, je + 1, un)
     v_new = put(v, is_, ie + 1, js, je, vn)
     out = dict(delp=delp_new, pt=pt_new, u=u_new, v=v_new, w=w_new, fx=fx, fy=fy, crx=crx, cry=cry, xfx=xfx, yfx=yfx)

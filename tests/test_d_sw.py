@@ -50,7 +50,7 @@ def flat_params(p, K):
     return out
 
 
-def _run_dsw(emu, hydrostatic, sponge, hord=2, d_con=0.0, pert=None):
+def _run_dsw(emu, hydrostatic, sponge, hord=2, d_con=0.0, pert=None, traj_over=None):
     """pert: perturbation-side overrides of level_params (split_hord / split_damp of the TL/AD model)"""
     N, K = 12, 2
     f, rng = dsw_inputs(N, K, 11)
@@ -60,6 +60,7 @@ def _run_dsw(emu, hydrostatic, sponge, hord=2, d_con=0.0, pert=None):
     prm.update(dddmp=0.2, d4_bg=0.15, hydrostatic=hydrostatic)
     if d_con > 0.0:
         prm["d_con"] = [0.0 if (sponge and k == 0) else d_con for k in range(K)]     # d_con_k = 0 in sponge layers (dyn_core_nlm.F90:595-628)
+    prm.update(traj_over or {})
     pp = None
     if pert is not None:
         pp = dict(prm); pp.update(pert)
@@ -145,6 +146,15 @@ def test_d_sw_monotone_trajectory_emu(hord):
 def test_d_sw_monotone_trajectory_gpu():
     _run_dsw(False, False, True, hord=10, pert=LIN2)
     _run_dsw(False, True, False, hord=9, pert=LIN2)
+
+
+def test_d_sw_split_damp_vort_damp_one_side_emu():
+    """the reference's defaults: do_vort_damp = F for the trajectory, do_vort_damp_pert = T for the increment
+    (model/fv_arrays_nlm.F90 vs fv_arrays_tlmadm.F90:37-92): the diffusive flux is added on one side only (sw_core_tlm.F90:2506-2530)"""
+    N, K = 12, 2
+    pert = dict(SPLIT_DAMP)
+    _run_dsw(True, False, False, pert=pert, traj_over=dict(damp_v=[0.0, 0.0], damp_t=[0.0, 0.0], damp_w=[0.0, 0.0]))
+    _run_dsw(True, False, False, pert=dict(split_damp=1, damp_v=[0.0, 0.0]))        # and the other way round
 
 
 @pytest.mark.gpu

@@ -10,7 +10,7 @@ from oracle.cubed_sphere import R
 from common import metrics, ograd, handle, rnd
 from test_dyn_core import CFG
 from test_fv_dynamics import eta, api_state, ZVIR
-from test_dyn_core import TWO_SIDED, TWO_SIDED_MONO
+from test_dyn_core import TWO_SIDED, TWO_SIDED_MONO, REF_DEFAULTS
 
 ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"]
 
@@ -119,6 +119,12 @@ def test_step_api_monotone_trajectory_emu(nonhydro):
     """operational-like configuration: the nonlinear model's default monotone schemes for the trajectory (hord 9 / 12), linear
     perturbation schemes; step_nl vs the oracle and the dot-product test of TL / AD"""
     print(_run(True, nonhydro=nonhydro, extra=TWO_SIDED_MONO, taylor=False))
+
+
+def test_step_api_reference_defaults_emu():
+    """both flag structures at the reference's defaults (bench.py --two-sided): vorticity damping on the perturbation side only,
+    whole column inside the perturbation sponge"""
+    print(_run(True, nonhydro=True, extra=REF_DEFAULTS, taylor=False))
 
 
 @pytest.mark.gpu
