@@ -39,8 +39,8 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
     if (ho != 1 && ho != 2 && ho != 333) throw std::runtime_error("fv3lm_create: hord_* must be 1, 2 or 333 (the linear schemes the TL/AD implement, tp_core_tlm.F90:2431-2488)");
   if (cfg->two_sided)
     for (int ho : {cfg->traj.hord_mt, cfg->traj.hord_vt, cfg->traj.hord_tm, cfg->traj.hord_dp, cfg->traj.hord_tr})
-      if (ho != 1 && ho != 2 && ho != 333 && !(ho >= 8 && ho <= 13))
-        throw std::runtime_error("fv3lm_create: traj.hord_* must be 1, 2, 333 or 8..13 (monotone PPM); the hord 3-7 schemes of the nonlinear model are not built");
+      if (ho != 333 && !(ho >= 1 && ho <= 13))
+        throw std::runtime_error("fv3lm_create: traj.hord_* must be in 1..13 or 333");
   if (cfg->nq != 4) throw std::runtime_error("fv3lm_create: nq must be 4 (qv, ql, qi, o3)");
   if (cfg->n_split < 1 || cfg->k_split < 1 || !(cfg->dt > 0.0)) throw std::runtime_error("fv3lm_create: n_split, k_split and dt must be positive");
   if (cfg->nord < 0 || cfg->nord > 3) throw std::runtime_error("fv3lm_create: nord must be in 0..3");

@@ -393,12 +393,45 @@ template <int DIR> struct S_tpuv {
     const int jt = DIR == 0 ? x.j : x.i;         // index across the sweep
     const int npt = DIR == 0 ? g.npy : g.npx;
     T bl, br;
-    if (ord >= 8) {
+    if (ord >= 8 && ord <= 13) {
       // monotone schemes of the nonlinear model (sw_core_nlm.F90 xtp_u :2166-2306, ytp_v :2548-2735): iord 8, 9, 10, else unlimited
       mono(x, dc, ic, np, jt == 1 || jt == npt, ord, bl, br);
       double rdm = DIR == 0 ? x.M(x.m.rdx, dc, 0) : x.M(x.m.rdy, 0, dc);
       T cf = c * rdm;
       x.out(0, pos ? uc + (1.0 - cf) * (br - cf * (bl + br)) : uc + (1.0 + cf) * (bl + cf * (bl + br)));
+      return;
+    }
+    if (ord >= 3 && ord <= 7) {
+      // smoothness-switch schemes of the nonlinear model (sw_core_nlm.F90 xtp_u :2082-2160, ytp_v): need bl, br of both cells
+      auto lin = [&](int co, T& l, T& r) {
+        const int icc = (DIR == 0 ? x.i : x.j) + co;
+        T uu = Q(x, co);
+        if ((icc == 0 || icc == 1 || icc == np - 1 || icc == np) && (jt == 1 || jt == npt)) { l = T(0.0); r = T(0.0); }
+        else { l = face(x, co) - uu; r = face(x, co + 1) - uu; }
+      };
+      T blm, brm, blp, brp; lin(-1, blm, brm); lin(0, blp, brp);
+      T b0m = blm + brm, b0p = blp + brp, um = Q(x, -1), up = Q(x, 0);
+      const double rdc = DIR == 0 ? x.M(x.m.rdx, dc, 0) : x.M(x.m.rdy, 0, dc);
+      T cf = c * rdc;
+      bool s5m, s5p, s6m = false, s6p = false;
+      if (ord <= 4) {
+        s5m = fabs(val(b0m)) < fabs(val(blm) - val(brm)); s6m = 3.0 * fabs(val(b0m)) < fabs(val(blm) - val(brm));
+        s5p = fabs(val(b0p)) < fabs(val(blp) - val(brp)); s6p = 3.0 * fabs(val(b0p)) < fabs(val(blp) - val(brp));
+        if (ord == 3) {
+          T f0 = T(0.0);
+          if (pos) { if (s6m || s5p) f0 = brm - cf * b0m; else if (s5m) f0 = tp::sgn_of(m_min(m_abs(blm), m_abs(brm)), brm); x.out(0, um + (1.0 - cf) * f0); }
+          else { if (s6p || s5m) f0 = blp + cf * b0p; else if (s5p) f0 = tp::sgn_of(m_min(m_abs(blp), m_abs(brp)), blp); x.out(0, up + (1.0 + cf) * f0); }
+          return;
+        }
+        if (pos) x.out(0, (s6m || s5p) ? um + (1.0 - cf) * (brm - cf * b0m) : um);
+        else x.out(0, (s6p || s5m) ? up + (1.0 + cf) * (blp + cf * b0p) : up);
+        return;
+      }
+      if (ord == 5) { s5m = val(blm) * val(brm) < 0.0; s5p = val(blp) * val(brp) < 0.0; }
+      else { s5m = fabs(3.0 * val(b0m)) < fabs(val(blm) - val(brm)); s5p = fabs(3.0 * val(b0p)) < fabs(val(blp) - val(brp)); }
+      (void)s6m; (void)s6p;
+      if (pos) x.out(0, (s5m || s5p) ? um + (1.0 - cf) * (brm - cf * b0m) : um);
+      else x.out(0, (s5m || s5p) ? up + (1.0 + cf) * (blp + cf * b0p) : up);
       return;
     }
     if ((ic == 0 || ic == 1 || ic == np - 1 || ic == np) && (jt == 1 || jt == npt)) { bl = T(0.0); br = T(0.0); }

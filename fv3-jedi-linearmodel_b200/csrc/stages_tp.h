@@ -11,16 +11,16 @@ namespace fv3lm {
 
 struct LevOrd { signed char v[128]; };   // per-level scheme order (sponge layers differ)
 // hord = 333 (third-order linear scheme, tp_core_tlm.F90:2467-2488) is stored as ORD333 in a LevOrd
-constexpr int ORD333 = 3;
-// hord = 8 .. 13: the monotone PPM schemes of the nonlinear model (tp_core_nlm.F90:470-578), stored as they are.  They are only
-// legal on the trajectory side of a two-sided configuration: nothing is ever differentiated through them.
-inline bool hord_is_mono(int hord) { return hord >= 8 && hord <= 13; }
+constexpr int ORD333 = 33;
+// hord = 8 .. 13: the monotone PPM schemes of the nonlinear model (tp_core_nlm.F90:470-578), hord = 3 .. 7: its "smoothness-switch"
+// schemes on the unlimited edge values (:327-467), stored as they are.  They are only legal on the trajectory side of a two-sided configuration: nothing is ever differentiated through them.
+inline bool hord_is_mono(int hord) { return hord >= 3 && hord <= 13; }
 inline int enc_hord(int hord, bool allow_mono = true) {
   if (hord == 1 || hord == 2) return hord;
   if (hord == 333) return ORD333;
   if (allow_mono && hord_is_mono(hord)) return hord;
   throw std::runtime_error("hord must be 1, 2 or 333 (the linear schemes the TL/AD implement, tp_core_tlm.F90:2431-2488)"
-                           " or, for the trajectory of a two-sided configuration, 8..13 (monotone PPM, tp_core_nlm.F90:470)");
+                           " or, for the trajectory of a two-sided configuration, 3..13 (tp_core_nlm.F90:327-578)");
 }
 
 namespace tp {
@@ -129,11 +129,49 @@ template <int DIR, class X> DEV void mono_blbr(const X& x, int fq, int co, int o
 template <int DIR, class X> DEV typename X::T ppm_flux(const X& x, int fq, typename X::T c, int ord) {
   using T = typename X::T;
   if (ord == 1) return val(c) > 0.0 ? Q<DIR>(x, fq, -1) : Q<DIR>(x, fq, 0);
-  if (ord >= 8) {
+  if (ord >= 8 && ord <= 13) {
     T bl, br;
     if (val(c) > 0.0) { mono_blbr<DIR>(x, fq, -1, ord, bl, br); return Q<DIR>(x, fq, -1) + (1.0 - c) * (br - c * (bl + br)); }
     mono_blbr<DIR>(x, fq, 0, ord, bl, br);
     return Q<DIR>(x, fq, 0) + (1.0 + c) * (bl + c * (bl + br));
+  }
+  if (ord >= 3 && ord <= 7) {
+    // iord = 3 .. 7 (tp_core_nlm.F90:386-467): unlimited edge values, the second-order increment only where the profile is smooth
+    auto AL = [&](int d) {
+      T a = edge_al<DIR>(x, fq, d);
+      if (ord == 7 && val(a) < 0.0) {       // :343-346, :358-362, :369-373: positivity of the edge values
+        const int ia = (DIR == 0 ? x.i : x.j) + d, np = DIR == 0 ? x.g.npx : x.g.npy;
+        const bool edge = ia <= 2 || ia >= np - 1;
+        a = edge ? T(0.0) : 0.5 * (Q<DIR>(x, fq, d - 1) + Q<DIR>(x, fq, d));
+      }
+      return a;
+    };
+    T qm = Q<DIR>(x, fq, -1), qp = Q<DIR>(x, fq, 0), a0 = AL(0);
+    T blm = AL(-1) - qm, brm = a0 - qm, blp = a0 - qp, brp = AL(1) - qp;
+    T b0m = blm + brm, b0p = blp + brp;
+    bool sm5m, sm5p, sm6m = false, sm6p = false;
+    if (ord == 3 || ord == 4) {
+      sm5m = fabs(val(b0m)) < fabs(val(blm) - val(brm)); sm6m = 3.0 * fabs(val(b0m)) < fabs(val(blm) - val(brm));
+      sm5p = fabs(val(b0p)) < fabs(val(blp) - val(brp)); sm6p = 3.0 * fabs(val(b0p)) < fabs(val(blp) - val(brp));
+      if (ord == 3) {      // :386-414: falls back to the piece-wise linear increment before first order
+        T fx1 = T(0.0);
+        if (val(c) > 0.0) {
+          if (sm6m || sm5p) fx1 = brm - c * b0m;
+          else if (sm5m) fx1 = sgn_of(m_min(m_abs(blm), m_abs(brm)), brm);
+          return qm + (1.0 - m_abs(c)) * fx1;
+        }
+        if (sm6p || sm5m) fx1 = blp + c * b0p;
+        else if (sm5p) fx1 = sgn_of(m_min(m_abs(blp), m_abs(brp)), blp);
+        return qp + (1.0 - m_abs(c)) * fx1;
+      }
+      if (val(c) > 0.0) return (sm6m || sm5p) ? qm + (1.0 - c) * (brm - c * b0m) : qm;
+      return (sm6p || sm5m) ? qp + (1.0 + c) * (blp + c * b0p) : qp;
+    }
+    if (ord == 5) { sm5m = val(blm) * val(brm) < 0.0; sm5p = val(blp) * val(brp) < 0.0; }
+    else { sm5m = fabs(3.0 * val(b0m)) < fabs(val(blm) - val(brm)); sm5p = fabs(3.0 * val(b0p)) < fabs(val(blp) - val(brp)); }
+    (void)sm6m; (void)sm6p;
+    if (val(c) > 0.0) return (sm5m || sm5p) ? qm + (1.0 - c) * (brm - c * b0m) : qm;
+    return (sm5m || sm5p) ? qp + (1.0 + c) * (blp + c * b0p) : qp;
   }
   if (ord == ORD333) {
     // perfectly linear third-order scheme, no cube-edge special cases (tp_core_tlm.F90:2467-2488, :2638-2660)

@@ -252,6 +252,25 @@ def xtp_u(c, u, g, iord):
             fp = um + (1. - cfl_p) * (mbr[..., is_ - 1: ie + 1] - cfl_p * (mbl[..., is_ - 1: ie + 1] + mbr[..., is_ - 1: ie + 1]))
             fn_ = up_ + (1. + cfl_n) * (mbl[..., is_: ie + 2] + cfl_n * (mbl[..., is_: ie + 2] + mbr[..., is_: ie + 2]))
             table[o] = torch.where(cc > 0., fp, fn_)
+        if 3 <= o <= 7:        # smoothness-switch schemes (sw_core_nlm.F90:2082-2160) on the bl / br of the linear scheme
+            sl = lambda a, d: a[..., is_ + d: ie + 2 + d]
+            blm, brm, b0m, blp, brp, b0p = sl(bl, -1), sl(br, -1), sl(b0, -1), sl(bl, 0), sl(br, 0), sl(b0, 0)
+            z = torch.zeros_like(cc)
+            if o in (3, 4):
+                s5 = b0.abs() < (bl - br).abs(); s6 = 3. * b0.abs() < (bl - br).abs()
+                s5m, s5p, s6m, s6p = sl(s5, -1), sl(s5, 0), sl(s6, -1), sl(s6, 0)
+                if o == 3:
+                    f0p = torch.where(s6m | s5p, brm - cfl_p * b0m, torch.where(s5m, tp._sign(torch.minimum(blm.abs(), brm.abs()), brm), z))
+                    f0n = torch.where(s6p | s5m, blp + cfl_n * b0p, torch.where(s5p, tp._sign(torch.minimum(blp.abs(), brp.abs()), blp), z))
+                    table[o] = torch.where(cc > 0., um + (1. - cfl_p) * f0p, up_ + (1. + cfl_n) * f0n)
+                else:
+                    table[o] = torch.where(cc > 0., um + torch.where(s6m | s5p, (1. - cfl_p) * (brm - cfl_p * b0m), z),
+                                           up_ + torch.where(s6p | s5m, (1. + cfl_n) * (blp + cfl_n * b0p), z))
+            else:
+                s5 = (bl * br < 0.) if o == 5 else ((3. * b0).abs() < (bl - br).abs())
+                on = sl(s5, -1) | sl(s5, 0)
+                f0 = torch.where(cc > 0., (1. - cfl_p) * (brm - cfl_p * b0m), (1. + cfl_n) * (blp + cfl_n * b0p))
+                table[o] = f1 + torch.where(on, f0, z)
     # iord = 333 (sw_core_tlm.F90:7332-7356): third-order linear, Courant number c * rdx of the upwind cell
     umm = S(u, is_ - 2, ie - 1, j0, j1); upp = S(u, is_ + 1, ie + 2, j0, j1)
     f3 = torch.where(cc > 0., (2.0 * up_ + 5.0 * um - umm) / 6.0 - 0.5 * cfl_p * (up_ - um) + cfl_p * cfl_p / 6.0 * (up_ - 2.0 * um + umm),

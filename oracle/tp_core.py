@@ -197,6 +197,33 @@ def xppm(q, c, iord, g, j0, j1):
             blm, brm = bl[..., is_ - 1: ie + 1], br[..., is_ - 1: ie + 1]
             bl0, br0 = bl[..., is_: ie + 2], br[..., is_: ie + 2]
             table[o] = torch.where(cc > 0., qm + (1. - cc) * (brm - cc * (blm + brm)), qp + (1. + cc) * (bl0 + cc * (bl0 + br0)))
+        if 3 <= o <= 7:        # smoothness-switch schemes on the unlimited edge values (tp_core_nlm.F90:327-467)
+            alo = al
+            if o == 7:         # positivity of the edge values: interior -> mean of the two cells, cube-edge values -> 0
+                mean = 0.5 * (q[..., R(j0, j1), R(-1, npx)] + q[..., R(j0, j1), R(0, npx + 1)])
+                ii = torch.arange(0, npx + 2)
+                edge = ((ii <= 2) | (ii >= npx - 1)).view(1, 1, 1, -1)
+                alo = torch.where(al < 0., torch.where(edge, torch.zeros_like(al), mean), al)
+            qc = q[..., R(j0, j1), R(0, npx)]
+            bl = alo[..., 0: npx + 1] - qc; br = alo[..., 1: npx + 2] - qc; b0 = bl + br
+            sl = lambda a, d: a[..., is_ + d: ie + 2 + d]          # cell i + d for faces i = is .. ie+1
+            blm, brm, b0m, blp, brp, b0p = sl(bl, -1), sl(br, -1), sl(b0, -1), sl(bl, 0), sl(br, 0), sl(b0, 0)
+            if o in (3, 4):
+                s5 = b0.abs() < (bl - br).abs(); s6 = 3. * b0.abs() < (bl - br).abs()
+                s5m, s5p, s6m, s6p = sl(s5, -1), sl(s5, 0), sl(s6, -1), sl(s6, 0)
+                z = torch.zeros_like(cc)
+                if o == 3:
+                    f1p = torch.where(s6m | s5p, brm - cc * b0m, torch.where(s5m, _sign(torch.minimum(blm.abs(), brm.abs()), brm), z))
+                    f1n = torch.where(s6p | s5m, blp + cc * b0p, torch.where(s5p, _sign(torch.minimum(blp.abs(), brp.abs()), blp), z))
+                    table[o] = torch.where(cc > 0., qm + (1. - cc.abs()) * f1p, qp + (1. - cc.abs()) * f1n)
+                else:
+                    table[o] = torch.where(cc > 0., qm + torch.where(s6m | s5p, (1. - cc) * (brm - cc * b0m), z),
+                                           qp + torch.where(s6p | s5m, (1. + cc) * (blp + cc * b0p), z))
+            else:
+                s5 = (bl * br < 0.) if o == 5 else ((3. * b0).abs() < (bl - br).abs())
+                on = sl(s5, -1) | sl(s5, 0)
+                f1 = torch.where(cc > 0., (1. - cc) * (brm - cc * b0m), (1. + cc) * (blp + cc * b0p))
+                table[o] = up + torch.where(on, f1, torch.zeros_like(f1))
     out[..., R(j0, j1), R(is_, ie + 1)] = select_ord(iord, table)
     return out
 

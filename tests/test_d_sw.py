@@ -135,7 +135,7 @@ def test_d_sw_split_damp_emu():
 LIN2 = dict(hord_mt=[2, 2], hord_vt=[2, 2], hord_tm=[2, 2], hord_dp=[2, 2])
 
 
-@pytest.mark.parametrize("hord", [8, 9, 10])
+@pytest.mark.parametrize("hord", [3, 4, 5, 6, 7, 8, 9, 10])
 def test_d_sw_monotone_trajectory_emu(hord):
     """operational-like split: the trajectory runs the nonlinear model's monotone PPM (hord 8 / 9 / 10 in fv_tp_2d and xtp_u / ytp_v),
     the perturbation the linear scheme hord_pert = 2 linearised about it (fv_arrays_tlmadm.F90:40-46)"""

@@ -18,6 +18,11 @@ CASES = {
     "step_hydro": lambda emu: test_fv_dynamics._run_step(emu, 1, 2),
     "step_nonhydro": lambda emu: test_fv_dynamics._run_step(emu, 1, 2, nonhydro=True),
     "step_nonhydro_c24": lambda emu: test_fv_dynamics._run_step(emu, 1, 1, K=3, nonhydro=True, N=24),
+    # two-sided mode (detached views, spliced chains, monotone trajectory schemes), the heat source path with del2_cubed
+    "dyn_core_nh_two_sided": lambda emu: test_nh._run_dyn_nh(emu, 2, extra=test_dyn_core.TWO_SIDED),
+    "dyn_core_two_sided_monotone": lambda emu: test_dyn_core._run(emu, 2, K=4, extra=test_dyn_core.TWO_SIDED_MONO),
+    "dyn_core_heat": lambda emu: test_dyn_core._run(emu, 2, K=5, extra=dict(d_con=1.0)),
+    "del2_cubed": lambda emu: test_dyn_core._run_del2_cubed(emu, 3),
 }
 
 

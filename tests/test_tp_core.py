@@ -90,7 +90,7 @@ def _run_mono(emu, hord, seed=1234, positive=True):
     assert relerr(region(traj["fy"], 1, N, 1, N + 1), region(fy_o.numpy(), 1, N, 1, N + 1)) < TOL
 
 
-@pytest.mark.parametrize("hord", [8, 9, 10, 11, 12, 13])
+@pytest.mark.parametrize("hord", [3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13])
 def test_fv_tp_2d_monotone_emu(hord):
     _run_mono(True, hord)
     _run_mono(True, hord, seed=99, positive=False)
