@@ -118,17 +118,22 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
   // kinetic energy
   int vb = P.val(nm("vb"), nk), ub = P.val(nm("ub"), nk), ubf = P.val(nm("ubf"), nk), vbf = P.val(nm("vbf"), nk), ke = P.val(nm("ke"), nk);
   P.add<S_dvbub>("dvbub", {prm.dt}, {ut, vt, uc, vc}, {vb, ub}, nk);
+  auto tpuv = [&](int dir, const LevOrd& ho, int cc, int uu, int out) {   // lean kernels for the linear orders, S_tpuv_nl otherwise
+    const bool lin = ord_is_linear(ho, nk);
+    if (dir == 1) { if (lin) P.add<S_tpuv<1>>("ytp_v", {ho}, {cc, uu}, {out}, nk); else P.add<S_tpuv_nl<1>>("ytp_v", {ho}, {cc, uu}, {out}, nk); }
+    else { if (lin) P.add<S_tpuv<0>>("xtp_u", {ho}, {cc, uu}, {out}, nk); else P.add<S_tpuv_nl<0>>("xtp_u", {ho}, {cc, uu}, {out}, nk); }
+  };
   if (same_ord(prm.hord_mt, pp.hord_mt, nk)) {
-    P.add<S_tpuv<1>>("ytp_v", {prm.hord_mt}, {vb, v}, {ubf}, nk);
-    P.add<S_tpuv<0>>("xtp_u", {prm.hord_mt}, {ub, u}, {vbf}, nk);
+    tpuv(1, prm.hord_mt, vb, v, ubf);
+    tpuv(0, prm.hord_mt, ub, u, vbf);
   } else {   // :1987-1997, :2059-2068
     int ya = P.val(nm("ubf.p"), nk), yb = P.val(nm("ubf.t"), nk), xa = P.val(nm("vbf.p"), nk), xb = P.val(nm("vbf.t"), nk);
     P.tl_only = true;
-    P.add<S_tpuv<1>>("ytp_v", {pp.hord_mt}, {vb, v}, {ya}, nk);
-    P.add<S_tpuv<0>>("xtp_u", {pp.hord_mt}, {ub, u}, {xa}, nk);
+    tpuv(1, pp.hord_mt, vb, v, ya);
+    tpuv(0, pp.hord_mt, ub, u, xa);
     P.tl_only = false;
-    P.add<S_tpuv<1>>("ytp_v", {prm.hord_mt}, {D(vb), D(v)}, {yb}, nk);
-    P.add<S_tpuv<0>>("xtp_u", {prm.hord_mt}, {D(ub), D(u)}, {xb}, nk);
+    tpuv(1, prm.hord_mt, D(vb), D(v), yb);
+    tpuv(0, prm.hord_mt, D(ub), D(u), xb);
     P.add<S_splice>("splice", {0}, {ya, yb}, {ubf}, nk);
     P.add<S_splice>("splice", {0}, {xa, xb}, {vbf}, nk);
   }

@@ -22,14 +22,21 @@ TpOut build_fv_tp_2d(Program& P, Mosaic& mo, int q, int crx, int cry, int xfx, i
   int fy2 = P.val(nm("fy2"), nk), q_i = P.val(nm("q_i"), nk), fxo = P.val(nm("fx_ou"), nk);
   int fx2 = P.val(nm("fx2"), nk), q_j = P.val(nm("q_j"), nk), fyo = P.val(nm("fy_ou"), nk);
   int fx = P.val(nm("fx"), nk), fy = P.val(nm("fy"), nk);
+  // the linear orders of the TL / AD run the lean S_ppm kernels; any order of the nonlinear model (trajectory side) S_ppm_nl
+  const bool lin = ord_is_linear(hord, nk);
+  auto ppm = [&](int dir, const char* nm_, const S_ppm<0>::P& p0, int qq, int cc, int out) {
+    S_ppm<1>::P p1{p0.i0, p0.i1, p0.j0, p0.j1, p0.ord};
+    if (dir == 0) { if (lin) P.add<S_ppm<0>>(nm_, p0, {qq, cc}, {out}, nk); else P.add<S_ppm_nl<0>>(nm_, p0, {qq, cc}, {out}, nk); }
+    else { if (lin) P.add<S_ppm<1>>(nm_, p1, {qq, cc}, {out}, nk); else P.add<S_ppm_nl<1>>(nm_, p1, {qq, cc}, {out}, nk); }
+  };
   add_patch(P, "copy_corners_y", &mo.cc2, {q});
-  P.add<S_ppm<1>>("yppm_in", {isd, ied, js, je + 1, hord}, {q, cry}, {fy2}, nk);
+  ppm(1, "yppm_in", {isd, ied, js, je + 1, hord}, q, cry, fy2);
   P.add<S_inner<1>>("q_i", {isd, ied, js, je}, {q, fy2, yfx, ra_y}, {q_i}, nk);
-  P.add<S_ppm<0>>("xppm_ou", {is, ie + 1, js, je, hord}, {q_i, crx}, {fxo}, nk);
+  ppm(0, "xppm_ou", {is, ie + 1, js, je, hord}, q_i, crx, fxo);
   add_patch(P, "copy_corners_x", &mo.cc1, {q});
-  P.add<S_ppm<0>>("xppm_in", {is, ie + 1, jsd, jed, hord}, {q, crx}, {fx2}, nk);
+  ppm(0, "xppm_in", {is, ie + 1, jsd, jed, hord}, q, crx, fx2);
   P.add<S_inner<0>>("q_j", {is, ie, jsd, jed}, {q, fx2, xfx, ra_x}, {q_j}, nk);
-  P.add<S_ppm<1>>("yppm_ou", {is, ie, js, je + 1, hord}, {q_j, cry}, {fyo}, nk);
+  ppm(1, "yppm_ou", {is, ie, js, je + 1, hord}, q_j, cry, fyo);
   P.add<S_favg>("fx_avg", {is, ie + 1, js, je}, {fxo, fx2, mfx >= 0 ? mfx : xfx}, {fx}, nk);
   P.add<S_favg>("fy_avg", {is, ie, js, je + 1}, {fyo, fy2, mfy >= 0 ? mfy : yfx}, {fy}, nk);
   return {fx, fy};

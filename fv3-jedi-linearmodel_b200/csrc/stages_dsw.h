@@ -298,7 +298,8 @@ struct S_dvbub {
 };
 
 // xtp_u / ytp_v (linear orders).  DIR 0 = xtp_u: in: c(=ub) u ; out: flux.   (:1970-2100)
-template <int DIR> struct S_tpuv {
+// FULL = false: linear orders only (1, 2, 333; the TL / AD kernels); FULL = true (S_tpuv_nl): every order of the nonlinear model
+template <int DIR, bool FULL = false> struct S_tpuv {
   static constexpr int NI = 2, NO = 1;
   struct P { LevOrd ord; };
   static constexpr int NT = 7;
@@ -393,6 +394,7 @@ template <int DIR> struct S_tpuv {
     const int jt = DIR == 0 ? x.j : x.i;         // index across the sweep
     const int npt = DIR == 0 ? g.npy : g.npx;
     T bl, br;
+    if constexpr (FULL) {
     if (ord >= 8 && ord <= 13) {
       // monotone schemes of the nonlinear model (sw_core_nlm.F90 xtp_u :2166-2306, ytp_v :2548-2735): iord 8, 9, 10, else unlimited
       mono(x, dc, ic, np, jt == 1 || jt == npt, ord, bl, br);
@@ -434,6 +436,7 @@ template <int DIR> struct S_tpuv {
       else x.out(0, (s5m || s5p) ? up + (1.0 + cf) * (blp + cf * b0p) : up);
       return;
     }
+    }   // FULL
     if ((ic == 0 || ic == 1 || ic == np - 1 || ic == np) && (jt == 1 || jt == npt)) { bl = T(0.0); br = T(0.0); }
     else { bl = face(x, dc) - uc; br = face(x, dc + 1) - uc; }
     T b0 = bl + br;
@@ -442,6 +445,8 @@ template <int DIR> struct S_tpuv {
     x.out(0, pos ? uc + (1.0 - cfl) * (br - cfl * b0) : uc + (1.0 + cfl) * (bl + cfl * b0));
   }
 };
+
+template <int DIR> using S_tpuv_nl = S_tpuv<DIR, true>;
 
 // kinetic energy at corners (:1111-1202).  in: vb ubf ub vbf ut vt u v ; out: ke
 struct S_dke {

@@ -126,9 +126,12 @@ template <int DIR, class X> DEV void mono_blbr(const X& x, int fq, int co, int o
 }
 
 // 1-D flux at the current face from q (input fq) and Courant number c
-template <int DIR, class X> DEV typename X::T ppm_flux(const X& x, int fq, typename X::T c, int ord) {
+// FULL = false: only the linear orders (1, 2, 333) -- the hot TL / AD kernels stay free of the nonlinear model's scheme code
+// (which costs 10-20 registers per thread); FULL = true: all orders, used by the trajectory-only stages S_ppm_nl.
+template <int DIR, bool FULL, class X> DEV typename X::T ppm_flux(const X& x, int fq, typename X::T c, int ord) {
   using T = typename X::T;
   if (ord == 1) return val(c) > 0.0 ? Q<DIR>(x, fq, -1) : Q<DIR>(x, fq, 0);
+  if constexpr (FULL) {
   if (ord >= 8 && ord <= 13) {
     T bl, br;
     if (val(c) > 0.0) { mono_blbr<DIR>(x, fq, -1, ord, bl, br); return Q<DIR>(x, fq, -1) + (1.0 - c) * (br - c * (bl + br)); }
@@ -173,6 +176,7 @@ template <int DIR, class X> DEV typename X::T ppm_flux(const X& x, int fq, typen
     if (val(c) > 0.0) return (sm5m || sm5p) ? qm + (1.0 - c) * (brm - c * b0m) : qm;
     return (sm5m || sm5p) ? qp + (1.0 + c) * (blp + c * b0p) : qp;
   }
+  }   // FULL
   if (ord == ORD333) {
     // perfectly linear third-order scheme, no cube-edge special cases (tp_core_tlm.F90:2467-2488, :2638-2660)
     T qm1 = Q<DIR>(x, fq, -1), q0 = Q<DIR>(x, fq, 0);
@@ -222,7 +226,7 @@ template <int DIR> struct S_ppm {
       {1, 0, 0, 0}};
   template <class X> DEV static void eval(X& x, const P& p) {
     if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
-    x.out(0, tp::ppm_flux<DIR>(x, 0, x.in(1), p.ord.v[x.kk]));
+    x.out(0, tp::ppm_flux<DIR, false>(x, 0, x.in(1), p.ord.v[x.kk]));
   }
 
   // ---- hand-derived gather adjoint (replaces 7 seeded evaluations per cell).  The flux is linear in q:
@@ -333,6 +337,27 @@ template <int DIR> struct S_ppm {
     }
   }
 };
+
+// the same flux with every order of the nonlinear model (hord 1 .. 13, 333): trajectory side of a two-sided configuration.
+// Its inputs are detached views, so only the value-only kernel ever runs; the taps merely describe the footprint.
+template <int DIR> struct S_ppm_nl {
+  static constexpr int NI = 2, NO = 1;
+  using P = typename S_ppm<DIR>::P;
+  static constexpr int NT = 7;
+  static constexpr Tap taps[NT] = {
+      {0, DIR == 0 ? -3 : 0, DIR == 0 ? 0 : -3, 0}, {0, DIR == 0 ? -2 : 0, DIR == 0 ? 0 : -2, 0},
+      {0, DIR == 0 ? -1 : 0, DIR == 0 ? 0 : -1, 0}, {0, 0, 0, 0},
+      {0, DIR == 0 ? 1 : 0, DIR == 0 ? 0 : 1, 0},   {0, DIR == 0 ? 2 : 0, DIR == 0 ? 0 : 2, 0},
+      {1, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
+    x.out(0, tp::ppm_flux<DIR, true>(x, 0, x.in(1), p.ord.v[x.kk]));
+  }
+};
+inline bool ord_is_linear(const LevOrd& o, int nk) {
+  for (int k = 0; k < nk; k++) if (o.v[k] != 1 && o.v[k] != 2 && o.v[k] != ORD333) return false;
+  return true;
+}
 
 // inner update  q_i = (q*area + fyy(j) - fyy(j+1)) / ra_y ,  fyy = yfx * fy2   (DIR = 1)
 //               q_j = (q*area + fx1(i) - fx1(i+1)) / ra_x ,  fx1 = xfx * fx2   (DIR = 0)
