@@ -103,7 +103,8 @@ def run_gpu(args):
         # perturbation side = defaults of fv_flags_pert_type, trajectory side = defaults of fv_flags_type with the
         # synthetic run's sponge coefficients
         mc.update(split_damp=1, hord_ks_pert=1, hord_ks_traj=1, n_sponge=9, d2_bg_ks=2.0, d2_bg_k1=4.0, d2_bg_k2=2.0,
-                  traj=dict(hord_mt=9, hord_vt=9, hord_tm=9, hord_dp=9, hord_tr=12, nord=1, do_vort_damp=0, n_sponge=1,
+                  traj=dict(hord_mt=9, hord_vt=9, hord_tm=9, hord_dp=9, hord_tr=12, kord_mt=8, kord_wz=8, kord_tm=8, kord_tr=8,
+                            nord=1, do_vort_damp=0, n_sponge=1,
                             dddmp=0.0, d2_bg=0.0, d4_bg=0.16, vtdm4=0.0, d2_bg_k1=0.20, d2_bg_k2=0.10))
     cfg = fv3lm.default_config(N, K, rank=rank, nranks=world, layout_x=args.layout[0], layout_y=args.layout[1], **mc)
     h = fv3lm.FV3LM(cfg, ak, bk)

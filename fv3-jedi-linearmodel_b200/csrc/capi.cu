@@ -5,7 +5,7 @@ using namespace fv3lm;
 namespace fv3lm { void a2b_corner_weights(const Geom& g, const double* glon, const double* glat, const double* alon, const double* alat, double* out); }
 
 thread_local std::string fv3lm_g_err;
-static_assert(sizeof(fv3lm_config) == 344, "fv3lm_config is mirrored field by field in fv3lm.py and fortran/fv3lm_b200_capi_mod.F90");
+static_assert(sizeof(fv3lm_config) == 360, "fv3lm_config is mirrored field by field in fv3lm.py and fortran/fv3lm_b200_capi_mod.F90");
 
 // host [rows][NX] contiguous <-> device [rows][pitch]
 static void up2d(const Geom& g, double* d, const double* h, size_t rows) {
@@ -41,6 +41,11 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
     for (int ho : {cfg->traj.hord_mt, cfg->traj.hord_vt, cfg->traj.hord_tm, cfg->traj.hord_dp, cfg->traj.hord_tr})
       if (ho != 333 && !(ho >= 1 && ho <= 13))
         throw std::runtime_error("fv3lm_create: traj.hord_* must be in 1..13 or 333");
+  if (cfg->two_sided)
+    for (int ko : {cfg->traj.kord_mt, cfg->traj.kord_wz, cfg->traj.kord_tm, cfg->traj.kord_tr}) {
+      const int a = ko < 0 ? -ko : ko;
+      if (!(a == 0 || a == 17 || (a >= 8 && a <= 14))) throw std::runtime_error("fv3lm_create: traj.kord_* must be 8..14 (monotone profiles of the nonlinear model), 17 or 0 (linear)");
+    }
   if (cfg->nq != 4) throw std::runtime_error("fv3lm_create: nq must be 4 (qv, ql, qi, o3)");
   if (cfg->n_split < 1 || cfg->k_split < 1 || !(cfg->dt > 0.0)) throw std::runtime_error("fv3lm_create: n_split, k_split and dt must be positive");
   if (cfg->nord < 0 || cfg->nord > 3) throw std::runtime_error("fv3lm_create: nord must be in 0..3");

@@ -200,6 +200,9 @@ void dyn_config_from(DynConfig& c, const ModuleParams& prm) {
     c.dddmp = prm.get("t.dddmp", f->traj.dddmp); c.d2_bg = prm.get("t.d2_bg", f->traj.d2_bg); c.d4_bg = prm.get("t.d4_bg", f->traj.d4_bg);
     c.vtdm4 = prm.get("t.vtdm4", f->traj.vtdm4); c.d2_bg_k1 = prm.get("t.d2_bg_k1", f->traj.d2_bg_k1); c.d2_bg_k2 = prm.get("t.d2_bg_k2", f->traj.d2_bg_k2);
     c.n_sponge_ord = 0;
+    auto kd = [&](const char* n, int v) { int k = prm.geti(n, v); return k == 0 ? 17 : k; };     // 0 = not set -> linear
+    c.kord_mt = kd("t.kord_mt", f->traj.kord_mt); c.kord_wz = kd("t.kord_wz", f->traj.kord_wz);
+    c.kord_tm = kd("t.kord_tm", f->traj.kord_tm); c.kord_tr = kd("t.kord_tr", f->traj.kord_tr);
   }
 }
 

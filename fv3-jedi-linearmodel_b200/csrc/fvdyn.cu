@@ -243,27 +243,42 @@ RemapOut build_remap(Program& P, Mosaic& mo, const DynConfig& c, const std::vect
   else P.add<S_rm_tv>("rm_tv", {c.akap}, {pt, pk, peln, pe2, pk2, pn2}, {tv, dp2, pkz}, K);
   int dummy2d = P.val(nm("qs0"), 1);
   int tn = P.val(nm("tn"), K);
-  add_col<S_remap>(P, "map_scalar_T", {K, 1, 0, is, ie, js, je}, {tv, peln, pn2, dummy2d, dp2}, {tn});
+  // one remap call site.  Two-sided mode with a monotone trajectory kord (split_kord, model_tlmadm/fv_mapz_tlm.F90:494-506, 611-655):
+  // the increment is remapped with the linear |kord| = 17 scheme about the same inputs, the trajectory with the nonlinear model's kord
+  auto remap_site = [&](const char* nm_, int iv, int use_dp2, int i0, int i1, int j0, int j1, int kord_t, bool cs, double qmin,
+                        std::vector<int> ins, int out) {
+    const int ak = kord_t < 0 ? -kord_t : kord_t;
+    if (!c.pert.on || ak > 16) { add_col<S_remap>(P, nm_, {K, iv, use_dp2, i0, i1, j0, j1}, ins, {out}); return; }
+    int a = P.val(P.vals[out].name + ".p", K), b = P.val(P.vals[out].name + ".t", K);
+    P.tl_only = true;
+    add_col<S_remap>(P, nm_, {K, iv, use_dp2, i0, i1, j0, j1}, ins, {a});
+    P.tl_only = false;
+    std::vector<int> dins; for (int i : ins) dins.push_back(P.detached(i));
+    add_col<S_remap_nl>(P, (std::string(nm_) + "_traj").c_str(), {K, iv, use_dp2, i0, i1, j0, j1, ak, cs ? 1 : 0, qmin}, dins, {b});
+    P.add<S_splice>("splice", {0}, {a, b}, {out}, K);
+  };
+  constexpr double t_min = 184.0;    // model/fv_mapz_nlm.F90:40
+  remap_site("map_scalar_T", 1, 0, is, ie, js, je, c.kord_tm, false, t_min, {tv, peln, pn2, dummy2d, dp2}, tn);
   o.w = -1; o.delz = -1;
   if (nh) {
     o.w = P.val(nm("w"), K);
-    add_col<S_remap>(P, "map1_ppm_w", {K, -2, 0, is, ie, js, je}, {w, pe, pe2, ws, dp2}, {o.w});
+    remap_site("map1_ppm_w", -2, 0, is, ie, js, je, c.kord_wz, true, 0.0, {w, pe, pe2, ws, dp2}, o.w);
     int dzn = P.val(nm("dzr_n"), K);
-    add_col<S_remap>(P, "map1_ppm_delz", {K, 1, 0, is, ie, js, je}, {dzr, pe, pe2, dummy2d, dp2}, {dzn});
+    remap_site("map1_ppm_delz", 1, 0, is, ie, js, je, c.kord_tm, true, 0.0, {dzr, pe, pe2, dummy2d, dp2}, dzn);
     o.delz = P.val(nm("delz"), K);
     P.add<S_rm_post_nh>("rm_post_nh", {c.akap, rrg}, {dzn, dp2, tn}, {o.delz, pkz}, K);
   }
   for (size_t n = 0; n < q.size(); n++) {
     int qn = P.val(nm("q" + std::to_string(n)), K);
-    add_col<S_remap>(P, "map1_q2", {K, 0, 1, is, ie, js, je}, {q[n], pe, pe2, dummy2d, dp2}, {qn});
+    remap_site("map1_q2", 0, 1, is, ie, js, je, c.kord_tr, false, 0.0, {q[n], pe, pe2, dummy2d, dp2}, qn);
     o.q.push_back(qn);
   }
   int pe0u = P.val(nm("pe0u"), K + 1), pe3u = P.val(nm("pe3u"), K + 1), pe0v = P.val(nm("pe0v"), K + 1), pe3v = P.val(nm("pe3v"), K + 1);
   P.add<S_rm_pew<0>>("rm_pe_u", {AK, BK}, {pe}, {pe0u, pe3u}, K + 1);
   P.add<S_rm_pew<1>>("rm_pe_v", {AK, BK}, {pe}, {pe0v, pe3v}, K + 1);
   o.u = P.val(nm("u"), K); o.v = P.val(nm("v"), K);
-  add_col<S_remap>(P, "map1_ppm_u", {K, -1, 0, is, ie, js, je + 1}, {u, pe0u, pe3u, dummy2d, dp2}, {o.u});
-  add_col<S_remap>(P, "map1_ppm_v", {K, -1, 0, is, ie + 1, js, je}, {v, pe0v, pe3v, dummy2d, dp2}, {o.v});
+  remap_site("map1_ppm_u", -1, 0, is, ie, js, je + 1, c.kord_mt, true, 0.0, {u, pe0u, pe3u, dummy2d, dp2}, o.u);
+  remap_site("map1_ppm_v", -1, 0, is, ie + 1, js, je, c.kord_mt, true, 0.0, {v, pe0v, pe3v, dummy2d, dp2}, o.v);
   o.pt = P.val(nm("pt"), K);
   P.add<S_rm_pt>("rm_pt", {c.zvir, last_step ? 1 : 0}, {tn, o.q.empty() ? tn : o.q[0], pkz}, {o.pt}, K);
   o.delp = dp2; o.pkz = pkz; o.pe = pe2; o.pk = pk2; o.peln = pn2;

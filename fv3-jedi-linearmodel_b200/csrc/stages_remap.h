@@ -266,4 +266,143 @@ struct S_remap {
   }
 };
 
+// ---------------------------------------------------------------------------------
+// Monotone remap of the nonlinear model (|kord| = 8 .. 14): the limited sub-grid profile of scalar_profile / cs_profile
+// (model/fv_mapz_nlm.F90:1814-2109, :2197-2463) and cs_limiters (:2467-2542).  Trajectory side of a two-sided configuration only
+// (split_kord, model_tlmadm/fv_arrays_tlmadm.F90:69): its inputs are detached views, nothing is differentiated through it.
+// ---------------------------------------------------------------------------------
+namespace rmp {
+template <class T> DEV T mn3(T a, T b, T c) { return m_min(m_min(a, b), c); }
+template <class T> DEV T mx3(T a, T b, T c) { return m_max(m_max(a, b), c); }
+template <class T> DEV void cs_limiters(bool extm, T a, T& a2, T& a3, T& a4, int iv) {
+  if (iv == 0) {            // positive definite
+    if (val(a) <= 0.0) { a2 = a; a3 = a; a4 = T(0.0); return; }
+    if (fabs(val(a3) - val(a2)) < -val(a4)) {
+      if (val(a) + 0.25 * (val(a3) - val(a2)) * (val(a3) - val(a2)) / val(a4) + val(a4) * (1.0 / 12.0) < 0.0) {
+        if (val(a) < val(a3) && val(a) < val(a2)) { a3 = a; a2 = a; a4 = T(0.0); }
+        else if (val(a3) > val(a2)) { a4 = 3.0 * (a2 - a); a3 = a2 - a4; }
+        else { a4 = 3.0 * (a3 - a); a2 = a3 - a4; }
+      }
+    }
+    return;
+  }
+  const bool flat = iv == 1 ? ((val(a) - val(a2)) * (val(a) - val(a3)) >= 0.0) : extm;
+  if (flat) { a2 = a; a3 = a; a4 = T(0.0); return; }
+  const double da1 = val(a3) - val(a2), da2 = da1 * da1, a6da = val(a4) * da1;
+  if (a6da < -da2) { a4 = 3.0 * (a2 - a); a3 = a2 - a4; }
+  else if (a6da > da2) { a4 = 3.0 * (a3 - a); a2 = a3 - a4; }
+}
+// q[0..K]: interface values of the cubic spline (modified in place by the large-scale constraints); out: A2, A3, A4 per layer.
+// cs = true: cs_profile (no qmin tests; winds, w, delz), false: scalar_profile (T, tracers)
+template <class T> DEV void limit_profile(const T* a, T* q, int K, int iv, int kord, double qmin, bool cs, T* A2, T* A3, T* A4) {
+  T gm[KMAX]; bool extm[KMAX];
+  const int ak = kord < 0 ? -kord : kord;
+  q[1] = m_min(q[1], m_max(a[0], a[1])); q[1] = m_max(q[1], m_min(a[0], a[1]));
+  gm[0] = T(0.0);
+  for (int k = 1; k < K; k++) gm[k] = a[k] - a[k - 1];
+  for (int k = 2; k <= K - 2; k++) {
+    if (val(gm[k - 1]) * val(gm[k + 1]) > 0.0) { q[k] = m_min(q[k], m_max(a[k - 1], a[k])); q[k] = m_max(q[k], m_min(a[k - 1], a[k])); }
+    else if (val(gm[k - 1]) > 0.0) q[k] = m_max(q[k], m_min(a[k - 1], a[k]));
+    else { q[k] = m_min(q[k], m_max(a[k - 1], a[k])); if (iv == 0) q[k] = m_max(T(0.0), q[k]); }
+  }
+  q[K - 1] = m_min(q[K - 1], m_max(a[K - 2], a[K - 1])); q[K - 1] = m_max(q[K - 1], m_min(a[K - 2], a[K - 1]));
+  for (int k = 0; k < K; k++) { A2[k] = q[k]; A3[k] = q[k + 1]; }
+  for (int k = 0; k < K; k++)
+    extm[k] = (k == 0 || k == K - 1) ? ((val(A2[k]) - val(a[k])) * (val(A3[k]) - val(a[k])) > 0.0) : (val(gm[k]) * val(gm[k + 1]) < 0.0);
+  auto A4of = [&](int k) { return 3.0 * (2.0 * a[k] - (A2[k] + A3[k])); };
+  auto A4of6 = [&](int k) { return 6.0 * a[k] - 3.0 * (A2[k] + A3[k]); };
+  auto flat = [&](int k) { A2[k] = a[k]; A3[k] = a[k]; A4[k] = T(0.0); };
+  auto huynh = [&](int k) {      // Huynh's second constraint on both edges
+    T pmp_1 = a[k] - 2.0 * gm[k + 1], lac_1 = pmp_1 + 1.5 * gm[k + 2];
+    A2[k] = m_min(m_max(A2[k], mn3(a[k], pmp_1, lac_1)), mx3(a[k], pmp_1, lac_1));
+    T pmp_2 = a[k] + 2.0 * gm[k], lac_2 = pmp_2 - 1.5 * gm[k - 1];
+    A3[k] = m_min(m_max(A3[k], mn3(a[k], pmp_2, lac_2)), mx3(a[k], pmp_2, lac_2));
+  };
+  // top two layers
+  if (iv == 0) A2[0] = m_max(T(0.0), A2[0]);
+  else if (iv == -1) { if (val(A2[0]) * val(a[0]) <= 0.0) A2[0] = T(0.0); }
+  A4[0] = A4of(0); cs_limiters(extm[0], a[0], A2[0], A3[0], A4[0], 1);
+  A4[1] = A4of(1); cs_limiters(extm[1], a[1], A2[1], A3[1], A4[1], 2);
+  // interior
+  for (int k = 2; k <= K - 3; k++) {
+    const bool small = !cs && val(a[k]) < qmin;
+    if (ak < 9) { huynh(k); A4[k] = A4of(k); }
+    else if (ak == 9) {
+      if (extm[k] && (extm[k - 1] || extm[k + 1] || small)) flat(k);
+      else {
+        A4[k] = cs ? A4of6(k) : A4of(k);
+        if (fabs(val(A4[k])) > fabs(val(A2[k]) - val(A3[k]))) { huynh(k); A4[k] = cs ? A4of6(k) : A4of(k); }
+      }
+    } else if (ak == 10) {
+      if (extm[k]) { if (small || extm[k - 1] || extm[k + 1]) flat(k); else A4[k] = A4of6(k); }
+      else { A4[k] = A4of6(k); if (fabs(val(A4[k])) > fabs(val(A2[k]) - val(A3[k]))) { huynh(k); A4[k] = A4of6(k); } }
+    } else if (ak == 12) {
+      if (extm[k]) flat(k);
+      else { A4[k] = A4of6(k); if (fabs(val(A4[k])) > fabs(val(A2[k]) - val(A3[k]))) { huynh(k); A4[k] = A4of6(k); } }
+    } else if (ak == 13) {
+      if (extm[k]) { if (extm[k - 1] && extm[k + 1]) flat(k); else { huynh(k); A4[k] = A4of(k); } }
+      else A4[k] = A4of(k);
+    } else if (ak == 14) A4[k] = A4of(k);
+    else {                  // 11
+      if (extm[k] && (extm[k - 1] || extm[k + 1] || small)) flat(k); else A4[k] = A4of(k);
+    }
+    if (iv == 0) cs_limiters(extm[k], a[k], A2[k], A3[k], A4[k], 0);
+  }
+  // bottom two layers
+  if (iv == 0) A3[K - 1] = m_max(T(0.0), A3[K - 1]);
+  else if (iv == -1) { if (val(A3[K - 1]) * val(a[K - 1]) <= 0.0) A3[K - 1] = T(0.0); }
+  A4[K - 2] = A4of(K - 2); cs_limiters(extm[K - 2], a[K - 2], A2[K - 2], A3[K - 2], A4[K - 2], 2);
+  A4[K - 1] = A4of(K - 1); cs_limiters(extm[K - 1], a[K - 1], A2[K - 1], A3[K - 1], A4[K - 1], 1);
+}
+}  // namespace rmp
+
+// Remap one field with the nonlinear model's kord (8 .. 14; > 16 falls back to the unlimited profile).  Same inputs as S_remap.
+struct S_remap_nl {
+  static constexpr int NI = 5, NO = 1;
+  struct P { int K, iv, use_dp2; int i0, i1, j0, j1; int kord, cs; double qmin; };
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
+    const int K = p.K;
+    T a[KMAX], pe1[KMAX + 1], pe2[KMAX + 1], dp[KMAX], q[KMAX + 1], gam[KMAX + 1], A2[KMAX], A3[KMAX], A4[KMAX];
+    double pe1v[KMAX + 1];
+    for (int k = 0; k <= K; k++) { pe1[k] = x.in(1, k); pe2[k] = x.in(2, k); pe1v[k] = val(pe1[k]); }
+    for (int k = 0; k < K; k++) { a[k] = x.in(0, k); dp[k] = pe1[k + 1] - pe1[k]; }
+    T qs = (p.iv == -2) ? x.in(3, 0) : T(0.0);
+    rmp::cs_profile(a, dp, q, gam, K, p.iv, qs);
+    const int ak = p.kord < 0 ? -p.kord : p.kord;
+    if (ak > 16) for (int k = 0; k < K; k++) { A2[k] = q[k]; A3[k] = q[k + 1]; A4[k] = 3.0 * (2.0 * a[k] - (A2[k] + A3[k])); }
+    else rmp::limit_profile(a, q, K, p.iv, p.kord, p.qmin, p.cs != 0, A2, A3, A4);
+    int k0 = 0;
+    for (int k = 0; k < K; k++) {
+      int l = rmp::find_layer(pe1v, val(pe2[k]), k0, K);
+      T a2 = A2[l], a3 = A3[l], a4 = A4[l];
+      T pl = (pe2[k] - pe1[l]) / dp[l];
+      T res;
+      if (val(pe2[k + 1]) <= pe1v[l + 1]) {
+        T pr = (pe2[k + 1] - pe1[l]) / dp[l];
+        res = a2 + 0.5 * (a4 + a3 - a2) * (pr + pl) - a4 * rmp::r3 * (pr * (pr + pl) + pl * pl);
+        k0 = l;
+      } else {
+        T qsum = (pe1[l + 1] - pe2[k]) * (a2 + 0.5 * (a4 + a3 - a2) * (1.0 + pl) - a4 * (rmp::r3 * (1.0 + pl * (1.0 + pl))));
+        for (int m = l + 1; m < K; m++) {
+          if (val(pe2[k + 1]) > pe1v[m + 1]) qsum = qsum + dp[m] * a[m];
+          else {
+            T dpl = pe2[k + 1] - pe1[m];
+            T esl = dpl / dp[m];
+            qsum = qsum + dpl * (A2[m] + 0.5 * esl * (A3[m] - A2[m] + A4[m] * (1.0 - rmp::r23 * esl)));
+            k0 = m;
+            break;
+          }
+        }
+        T den = p.use_dp2 ? x.in(4, k) : pe2[k + 1] - pe2[k];
+        res = qsum / den;
+      }
+      x.out(0, k, res);
+    }
+  }
+  template <class X> DEV static void eval_ad(X&, const P&) {}    // never active (detached inputs)
+};
+
+
 }  // namespace fv3lm

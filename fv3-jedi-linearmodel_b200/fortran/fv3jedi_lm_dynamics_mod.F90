@@ -141,6 +141,8 @@ subroutine create(self,conf)
  cfg%traj%hord_dp = A%flagstruct%hord_dp; cfg%traj%hord_tr = A%flagstruct%hord_tr
  cfg%traj%nord = A%flagstruct%nord; cfg%traj%do_vort_damp = merge(1, 0, A%flagstruct%do_vort_damp)
  cfg%traj%n_sponge = A%flagstruct%n_sponge
+ cfg%traj%kord_mt = A%flagstruct%kord_mt; cfg%traj%kord_wz = A%flagstruct%kord_wz
+ cfg%traj%kord_tm = A%flagstruct%kord_tm; cfg%traj%kord_tr = A%flagstruct%kord_tr
  cfg%traj%dddmp = A%flagstruct%dddmp; cfg%traj%d2_bg = A%flagstruct%d2_bg; cfg%traj%d4_bg = A%flagstruct%d4_bg
  cfg%traj%vtdm4 = A%flagstruct%vtdm4; cfg%traj%d2_bg_k1 = A%flagstruct%d2_bg_k1; cfg%traj%d2_bg_k2 = A%flagstruct%d2_bg_k2
  cfg%a_imp = A%flagstruct%a_imp; cfg%p_fac = A%flagstruct%p_fac; cfg%d_con = A%flagstruct%d_con

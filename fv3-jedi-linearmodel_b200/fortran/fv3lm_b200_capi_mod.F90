@@ -11,6 +11,7 @@ public
 !> mirror of the `traj` member of `struct fv3lm_config`: the nonlinear model's switches in two-sided mode
 type, bind(c) :: fv3lm_traj_flags
   integer(c_int) :: hord_mt, hord_vt, hord_tm, hord_dp, hord_tr, nord, do_vort_damp, n_sponge
+  integer(c_int) :: kord_mt, kord_wz, kord_tm, kord_tr
   real(c_double) :: dddmp, d2_bg, d4_bg, vtdm4, d2_bg_k1, d2_bg_k2
 end type fv3lm_traj_flags
 

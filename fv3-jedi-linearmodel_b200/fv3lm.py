@@ -19,6 +19,7 @@ class TrajFlags(C.Structure):
     """the nonlinear model's switches in two-sided mode (fv3lm_config.traj)"""
     _fields_ = [("hord_mt", C.c_int), ("hord_vt", C.c_int), ("hord_tm", C.c_int), ("hord_dp", C.c_int), ("hord_tr", C.c_int),
                 ("nord", C.c_int), ("do_vort_damp", C.c_int), ("n_sponge", C.c_int),
+                ("kord_mt", C.c_int), ("kord_wz", C.c_int), ("kord_tm", C.c_int), ("kord_tr", C.c_int),
                 ("dddmp", C.c_double), ("d2_bg", C.c_double), ("d4_bg", C.c_double), ("vtdm4", C.c_double),
                 ("d2_bg_k1", C.c_double), ("d2_bg_k2", C.c_double)]
 

@@ -64,12 +64,15 @@ typedef struct fv3lm_config {
    * evaluated twice -- perturbation scheme for the increment, nonlinear model's scheme for the trajectory
    * (model_tlmadm/sw_core_tlm.F90:1664-1682, 1987-1997, 2341-2366, 2436-2451).  two_sided = 0: one set of switches for both
    * (TL = exact derivative of the nonlinear step).  traj.hord_*: 1, 2, 333 or the monotone PPM schemes 8..13 of the nonlinear
-   * model (model/tp_core_nlm.F90:470-578, model/sw_core_nlm.F90:2166-2306); hord 3-7 are not built.                          */
+   * model and its smoothness-switch schemes 3..7 (model/tp_core_nlm.F90:327-578, model/sw_core_nlm.F90:2000-2306).             */
   int two_sided, split_damp;
   int hord_ks_pert, hord_ks_traj;   /* first-order transport in the top n_sponge - 1 layers (hord_*_ks_* = 1), per side        */
   int reserved[2];
   struct {
     int hord_mt, hord_vt, hord_tm, hord_dp, hord_tr, nord, do_vort_damp, n_sponge;
+    /* vertical remap of the trajectory (split_kord): |kord| 8 .. 14 = the limited profiles of the nonlinear model
+     * (model/fv_mapz_nlm.F90:1814-2109, 2197-2463), 17 or 0 = the linear scheme; the increment always uses |kord| = 17 */
+    int kord_mt, kord_wz, kord_tm, kord_tr;
     double dddmp, d2_bg, d4_bg, vtdm4, d2_bg_k1, d2_bg_k2;
   } traj;
   double d2_bg_ks;                  /* d2_bg_ks_pert: divergence damping of the remaining perturbation sponge layers           */

@@ -56,13 +56,123 @@ def cs_profile(a, dp, iv=0, qs=None):
     return torch.stack(q[1:K + 2], dim=1)
 
 
-def remap_integrate(a, qi, pe1, pe2, dp2=None):
+def cs_limiters(extm, a, a2, a3, a4, iv):
+    """model/fv_mapz_nlm.F90:2467-2542 on tensors (one layer)"""
+    z = torch.zeros_like(a)
+    if iv == 0:
+        safe = torch.where(a4 == 0., torch.ones_like(a4), a4)
+        neg = ((a3 - a2).abs() < -a4) & ((a + 0.25 * (a3 - a2) ** 2 / safe + a4 * (1. / 12.)) < 0.)
+        c1 = (a < a3) & (a < a2)
+        c2 = a3 > a2
+        a4n = torch.where(c1, z, torch.where(c2, 3. * (a2 - a), 3. * (a3 - a)))
+        a3n = torch.where(c1, a, torch.where(c2, a2 - a4n, a3))
+        a2n = torch.where(c1, a, torch.where(c2, a2, a3 - a4n))
+        a2o = torch.where(neg, a2n, a2); a3o = torch.where(neg, a3n, a3); a4o = torch.where(neg, a4n, a4)
+        le = a <= 0.
+        return torch.where(le, a, a2o), torch.where(le, a, a3o), torch.where(le, z, a4o)
+    flat = ((a - a2) * (a - a3) >= 0.) if iv == 1 else extm
+    da1 = a3 - a2; da2 = da1 ** 2; a6da = a4 * da1
+    lo = a6da < -da2; hi = (~lo) & (a6da > da2)
+    a4n = torch.where(lo, 3. * (a2 - a), torch.where(hi, 3. * (a3 - a), a4))
+    a3n = torch.where(lo, a2 - a4n, a3)
+    a2n = torch.where(hi, a3 - a4n, a2)
+    return torch.where(flat, a, a2n), torch.where(flat, a, a3n), torch.where(flat, z, a4n)
+
+
+def limited_profile(a, qi, iv, kord, qmin=0., cs=False):
+    """the monotone sub-grid profiles of the nonlinear model, |kord| = 8 .. 14: scalar_profile (:1814-2109; cs = False) and
+    cs_profile (:2197-2463; cs = True, no qmin tests).  a [6,K,..] layer means, qi [6,K+1,..] spline interface values.
+    Returns a42, a43, a44 [6,K,..]."""
+    K = a.shape[1]
+    ak = abs(kord)
+    A = [a[:, k] for k in range(K)]
+    q = [qi[:, k] for k in range(K + 1)]
+    mx, mn = torch.maximum, torch.minimum
+    q[1] = mn(q[1], mx(A[0], A[1])); q[1] = mx(q[1], mn(A[0], A[1]))
+    gm = [None] + [A[k] - A[k - 1] for k in range(1, K)]
+    for k in range(2, K - 1):
+        lo, hi = mn(A[k - 1], A[k]), mx(A[k - 1], A[k])
+        both = mx(mn(q[k], hi), lo)
+        lmax = mx(q[k], lo)
+        lmin = mn(q[k], hi)
+        if iv == 0:
+            lmin = mx(torch.zeros_like(lmin), lmin)
+        q[k] = torch.where(gm[k - 1] * gm[k + 1] > 0., both, torch.where(gm[k - 1] > 0., lmax, lmin))
+    q[K - 1] = mn(q[K - 1], mx(A[K - 2], A[K - 1])); q[K - 1] = mx(q[K - 1], mn(A[K - 2], A[K - 1]))
+    A2 = [q[k] for k in range(K)]; A3 = [q[k + 1] for k in range(K)]; A4 = [None] * K
+    extm = [((A2[k] - A[k]) * (A3[k] - A[k]) > 0.) if k in (0, K - 1) else (gm[k] * gm[k + 1] < 0.) for k in range(K)]
+    f3 = lambda k: 3. * (2. * A[k] - (A2[k] + A3[k]))
+    f6 = lambda k: 6. * A[k] - 3. * (A2[k] + A3[k])
+    z = torch.zeros_like(A[0])
+    def huynh(k):
+        pmp_1 = A[k] - 2. * gm[k + 1]; lac_1 = pmp_1 + 1.5 * gm[k + 2]
+        l = mn(mx(A2[k], mn(mn(A[k], pmp_1), lac_1)), mx(mx(A[k], pmp_1), lac_1))
+        pmp_2 = A[k] + 2. * gm[k]; lac_2 = pmp_2 - 1.5 * gm[k - 1]
+        r = mn(mx(A3[k], mn(mn(A[k], pmp_2), lac_2)), mx(mx(A[k], pmp_2), lac_2))
+        return l, r
+    if iv == 0:
+        A2[0] = mx(z, A2[0])
+    elif iv == -1:
+        A2[0] = torch.where(A2[0] * A[0] <= 0., z, A2[0])
+    A4[0] = f3(0); A2[0], A3[0], A4[0] = cs_limiters(extm[0], A[0], A2[0], A3[0], A4[0], 1)
+    A4[1] = f3(1); A2[1], A3[1], A4[1] = cs_limiters(extm[1], A[1], A2[1], A3[1], A4[1], 2)
+    for k in range(2, K - 2):
+        small = (A[k] < qmin) if not cs else torch.zeros_like(extm[k])
+        if ak < 9:
+            A2[k], A3[k] = huynh(k); A4[k] = f3(k)
+        elif ak in (9, 10, 12):
+            f = (f6 if (cs or ak != 9) else f3)
+            a4u = f(k)
+            l, r = huynh(k)
+            need = a4u.abs() > (A2[k] - A3[k]).abs()
+            a2s = torch.where(need, l, A2[k]); a3s = torch.where(need, r, A3[k])
+            a4s = (6. * A[k] - 3. * (a2s + a3s)) if f is f6 else 3. * (2. * A[k] - (a2s + a3s))
+            if ak == 9:
+                fl = extm[k] & (extm[k - 1] | extm[k + 1] | small)
+                A2[k] = torch.where(fl, A[k], a2s); A3[k] = torch.where(fl, A[k], a3s); A4[k] = torch.where(fl, z, a4s)
+            elif ak == 10:
+                fl = extm[k] & (small | extm[k - 1] | extm[k + 1])
+                ex = extm[k] & ~fl         # true local extremum: unlimited
+                A2[k] = torch.where(fl, A[k], torch.where(ex, A2[k], a2s)); A3[k] = torch.where(fl, A[k], torch.where(ex, A3[k], a3s))
+                A4[k] = torch.where(fl, z, torch.where(ex, a4u, a4s))
+            else:
+                fl = extm[k]
+                A2[k] = torch.where(fl, A[k], a2s); A3[k] = torch.where(fl, A[k], a3s); A4[k] = torch.where(fl, z, a4s)
+        elif ak == 13:
+            fl = extm[k] & extm[k - 1] & extm[k + 1]
+            l, r = huynh(k)
+            lim = extm[k] & ~fl
+            a2s = torch.where(lim, l, A2[k]); a3s = torch.where(lim, r, A3[k])
+            A2[k] = torch.where(fl, A[k], a2s); A3[k] = torch.where(fl, A[k], a3s)
+            A4[k] = torch.where(fl, z, 3. * (2. * A[k] - (a2s + a3s)))
+        elif ak == 14:
+            A4[k] = f3(k)
+        else:       # 11
+            fl = extm[k] & (extm[k - 1] | extm[k + 1] | small)
+            a4u = f3(k)
+            A2[k] = torch.where(fl, A[k], A2[k]); A3[k] = torch.where(fl, A[k], A3[k]); A4[k] = torch.where(fl, z, a4u)
+        if iv == 0:
+            A2[k], A3[k], A4[k] = cs_limiters(extm[k], A[k], A2[k], A3[k], A4[k], 0)
+    if iv == 0:
+        A3[K - 1] = mx(z, A3[K - 1])
+    elif iv == -1:
+        A3[K - 1] = torch.where(A3[K - 1] * A[K - 1] <= 0., z, A3[K - 1])
+    A4[K - 2] = f3(K - 2); A2[K - 2], A3[K - 2], A4[K - 2] = cs_limiters(extm[K - 2], A[K - 2], A2[K - 2], A3[K - 2], A4[K - 2], 2)
+    A4[K - 1] = f3(K - 1); A2[K - 1], A3[K - 1], A4[K - 1] = cs_limiters(extm[K - 1], A[K - 1], A2[K - 1], A3[K - 1], A4[K - 1], 1)
+    return torch.stack(A2, 1), torch.stack(A3, 1), torch.stack(A4, 1)
+
+
+def remap_integrate(a, qi, pe1, pe2, dp2=None, a4=None):
     """mean of the piecewise-parabolic profile (a4(1)=a, a4(2)=qi(k), a4(3)=qi(k+1),
     a4(4)=3(2a-(a4(2)+a4(3)))) of the source layers pe1 over each target layer pe2.
     map_scalar / map1_ppm divide by (pe2(k+1)-pe2(k)); map1_q2 by the given dp2."""
     K = a.shape[1]
-    a41 = a; a42 = qi[:, :-1]; a43 = qi[:, 1:]
-    a44 = 3. * (2. * a41 - (a42 + a43))
+    a41 = a
+    if a4 is None:
+        a42 = qi[:, :-1]; a43 = qi[:, 1:]
+        a44 = 3. * (2. * a41 - (a42 + a43))
+    else:
+        a42, a43, a44 = a4
     dp1 = pe1[:, 1:] - pe1[:, :-1]
     # layer index (0-based) of each target interface: number of interior source edges strictly below it
     with torch.no_grad():
@@ -96,10 +206,20 @@ def remap_integrate(a, qi, pe1, pe2, dp2=None):
     return torch.where(same2, one_v, qsum / den)
 
 
-def remap(a, pe1, pe2, iv=0, qs=None, dp2=None):
+def remap(a, pe1, pe2, iv=0, qs=None, dp2=None, kord=17, qmin=0., cs=False, kord_pert=None):
+    """kord: the mapping order (|kord| > 16: unlimited cubic spline; 8 .. 14: limited profiles of the nonlinear model).
+    kord_pert (two-sided mode, split_kord, model_tlmadm/fv_mapz_tlm.F90:494-506): the increment is remapped with kord_pert
+    about the same inputs, the trajectory with kord."""
     dp1 = pe1[:, 1:] - pe1[:, :-1]
     qi = cs_profile(a, dp1, iv, qs)
-    return remap_integrate(a, qi, pe1, pe2, dp2)
+    def one(ko):
+        if abs(ko) > 16:
+            return remap_integrate(a, qi, pe1, pe2, dp2)
+        return remap_integrate(a, qi, pe1, pe2, dp2, a4=limited_profile(a, qi, iv, ko, qmin, cs))
+    if kord_pert is None or abs(kord_pert) == abs(kord):
+        return one(kord)
+    from .d_sw import splice
+    return splice(one(kord_pert), one(kord))
 
 
 def put(a, sl, v):
@@ -136,12 +256,15 @@ def lagrangian_to_eulerian(st, g, ak, bk, cfg, last_step):
         delz = -delz / delp0
     pn2 = torch.cat([pn1[:, :1], torch.log(pe2[:, 1:K]), pn1[:, K:]], dim=1)
     pk2 = torch.cat([pk1[:, :1], torch.exp(akap * pn2[:, 1:K]), pk1[:, K:]], dim=1)
-    pt = remap(pt, pn1, pn2, iv=1)
-    qn = [remap(q[C], pe1, pe2, iv=0, dp2=dp2) for q in st["q"]]
+    tj = cfg.get("traj") or {}
+    kp = 17 if tj else None                                   # the increment always uses the linear |kord| = 17
+    k_mt, k_wz, k_tm, k_tr = (tj.get(n, 17) or 17 for n in ("kord_mt", "kord_wz", "kord_tm", "kord_tr"))
+    pt = remap(pt, pn1, pn2, iv=1, kord=k_tm, qmin=184., kord_pert=kp)
+    qn = [remap(q[C], pe1, pe2, iv=0, dp2=dp2, kord=k_tr, qmin=0., kord_pert=kp) for q in st["q"]]
     out = dict(st)
     if not hydro:
-        w = remap(st["w"][C], pe1, pe2, iv=-2, qs=st["ws"][C][:, 0])
-        delz = remap(delz, pe1, pe2, iv=1)
+        w = remap(st["w"][C], pe1, pe2, iv=-2, qs=st["ws"][C][:, 0], kord=k_wz, cs=True, kord_pert=kp)
+        delz = remap(delz, pe1, pe2, iv=1, kord=k_tm, cs=True, kord_pert=kp)
         delz = -delz * dp2
         out["w"] = put(st["w"], C, w); out["delz"] = put(st["delz"], C, delz)
         pkz = torch.exp(akap * torch.log(rrg * dp2 / delz * pt))
@@ -153,14 +276,14 @@ def lagrangian_to_eulerian(st, g, ak, bk, cfg, last_step):
     pe0 = 0.5 * (pe[Cum] + pe[Cu])
     pe0 = torch.cat([pe[Cu][:, :1], pe0[:, 1:]], dim=1)
     pe3 = AK + 0.5 * BK * (pe[Cum][:, K:] + pe[Cu][:, K:])
-    u = remap(st["u"][Cu], pe0, pe3, iv=-1)
+    u = remap(st["u"][Cu], pe0, pe3, iv=-1, kord=k_mt, cs=True, kord_pert=kp)
     Cv = (slice(None), slice(None), R(js, je), R(is_, ie + 1))
     Cvm = (slice(None), slice(None), R(js, je), R(is_ - 1, ie))
     pe0 = 0.5 * (pe[Cvm] + pe[Cv])
     pe0 = torch.cat([pe[Cv][:, :1] * 0 + pe[Cv][:, :1], pe0[:, 1:]], dim=1)
     pe3 = AK + 0.5 * BK * (pe[Cvm][:, K:] + pe[Cv][:, K:])
     pe3 = torch.cat([0 * pe3[:, :1] + float(ak[0]), pe3[:, 1:]], dim=1)
-    v = remap(st["v"][Cv], pe0, pe3, iv=-1)
+    v = remap(st["v"][Cv], pe0, pe3, iv=-1, kord=k_mt, cs=True, kord_pert=kp)
     if last_step:
         pt = pt / (1. + zvir * qn[0])
     else:

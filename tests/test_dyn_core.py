@@ -66,7 +66,7 @@ TWO_SIDED = dict(hord_mt=333, hord_vt=1, hord_tm=333, hord_dp=1, hord_tr=1, nord
 TWO_SIDED_MONO = dict(hord_mt=2, hord_vt=2, hord_tm=2, hord_dp=2, hord_tr=2, nord=1, dddmp=0.2, d2_bg=0.015, d4_bg=0.15, vtdm4=0.0005,
                       do_vort_damp=True, d2_bg_k1=0.3, d2_bg_k2=0.2, d2_bg_ks=0.1, n_sponge=2, split_damp=True, hord_ks_pert=True, hord_ks_traj=True,
                       traj=dict(hord_mt=9, hord_vt=9, hord_tm=9, hord_dp=9, hord_tr=12, nord=1, dddmp=0.0, d2_bg=0.0, d4_bg=0.16, vtdm4=0.0005,
-                                do_vort_damp=True, d2_bg_k1=0.2, d2_bg_k2=0.1, n_sponge=1))
+                                do_vort_damp=True, d2_bg_k1=0.2, d2_bg_k2=0.1, n_sponge=1, kord_mt=10, kord_wz=10, kord_tm=9, kord_tr=9))
 
 
 # the reference's own defaults on both sides: trajectory without vorticity damping and with dddmp = d2_bg = 0,
@@ -74,7 +74,7 @@ TWO_SIDED_MONO = dict(hord_mt=2, hord_vt=2, hord_tm=2, hord_dp=2, hord_tr=2, nor
 REF_DEFAULTS = dict(hord_mt=2, hord_vt=2, hord_tm=2, hord_dp=2, hord_tr=2, nord=1, dddmp=0.2, d2_bg=0.015, d4_bg=0.15, vtdm4=0.0005,
                     do_vort_damp=True, d2_bg_k1=4.0, d2_bg_k2=2.0, d2_bg_ks=2.0, n_sponge=9, split_damp=True, hord_ks_pert=True, hord_ks_traj=True,
                     traj=dict(hord_mt=9, hord_vt=9, hord_tm=9, hord_dp=9, hord_tr=12, nord=1, dddmp=0.0, d2_bg=0.0, d4_bg=0.16, vtdm4=0.0,
-                              do_vort_damp=False, d2_bg_k1=0.2, d2_bg_k2=0.1, n_sponge=1))
+                              do_vort_damp=False, d2_bg_k1=0.2, d2_bg_k2=0.1, n_sponge=1, kord_mt=8, kord_wz=8, kord_tm=8, kord_tr=8))
 
 
 def _run(emu, n_split, K=3, modes=("nl", "tl", "ad"), extra=None):

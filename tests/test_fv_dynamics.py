@@ -19,9 +19,10 @@ def eta(K, ptop):
     return ak, bk
 
 
-def _run_remap(emu, last_step):
-    N, K = 12, 6
-    rng = np.random.default_rng(21)
+def _run_remap(emu, last_step, kord=None, K=6, seed=21):
+    """kord: two-sided mode with that (monotone) remap order for the trajectory, linear |kord| = 17 for the increment (split_kord)"""
+    N = 12
+    rng = np.random.default_rng(seed)
     g = ograd(N)
     ptop = CFG["ptop"]
     ak, bk = eta(K, ptop)
@@ -33,6 +34,10 @@ def _run_remap(emu, last_step):
     f = dict(pe=pe, pk=np.exp(CFG["akap"] * np.log(pe)), peln=np.log(pe), pt=300.0 + 10.0 * rnd(rng, N, K),
              q0=0.01 * (1.0 + 0.3 * rnd(rng, N, K)), u=10.0 * rnd(rng, N, K), v=10.0 * rnd(rng, N, K))
     cfg = dict(CFG); cfg.update(zvir=ZVIR, hydrostatic=True)
+    if kord is not None:
+        cfg["traj"] = dict(kord_mt=kord, kord_wz=kord, kord_tm=kord, kord_tr=kord)
+        f["q0"] = 0.01 * (0.4 + rnd(rng, N, K))                 # sign changes: positive-definite limiter of the tracer profile
+        f["pt"] = 190.0 + 8.0 * rnd(rng, N, K)                  # straddles t_min = 184 K (stricter constraint below it)
     act = list(f.keys())
     onames = ["pt_n", "q0_n", "u_n", "v_n", "delp_n", "pkz_n"]
     def fn(*a):
@@ -45,6 +50,8 @@ def _run_remap(emu, last_step):
     outs = dict(pt_n=C, q0_n=C, u_n=(1, N, 1, N + 1), v_n=(1, N + 1, 1, N), delp_n=C, pkz_n=C)
     h = handle(N, K, emu, ak, bk)
     p = dict(ptop=ptop, akap=CFG["akap"], zvir=ZVIR, last_step=int(last_step))
+    if kord is not None:
+        p.update(two_sided=1, **{"t.kord_" + n: kord for n in ("mt", "wz", "tm", "tr")})
     return check_module(h, "remap", N, K, f, act, outs, fn, p, rng, tol=1e-11, dot_tol=1e-12, pert_scale=1e-3)
 
 
@@ -97,6 +104,14 @@ def _run_step(emu, k_split, n_split, K=4, nonhydro=False, N=12):
 @pytest.mark.parametrize("last_step", [True, False])
 def test_remap_emu(last_step):
     print(_run_remap(True, last_step))
+
+
+@pytest.mark.parametrize("kord", [8, 9, 10, 11, 12, 13, 14])
+def test_remap_monotone_trajectory_emu(kord):
+    """split_kord: limited sub-grid profiles of the nonlinear model for the trajectory (scalar_profile / cs_profile + cs_limiters,
+    model/fv_mapz_nlm.F90:1814-2542), linear profile for the increment"""
+    print(_run_remap(True, True, kord=kord, K=10))
+    print(_run_remap(True, False, kord=kord, K=9, seed=22))
 
 
 def test_step_hydro_emu():
