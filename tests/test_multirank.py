@@ -15,11 +15,13 @@ import torch.multiprocessing as mp
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _inputs(nonhydro):
-    from test_dyn_core import CFG
+def _inputs(nonhydro, two_sided=False):
+    """two_sided: both flag structures at the reference's defaults (monotone hord 9 / 12 and kord 8 trajectory, linear increment with
+    its own damping and sponge), see test_dyn_core.REF_DEFAULTS"""
+    from test_dyn_core import CFG, REF_DEFAULTS, two_sided_params
     from test_fv_dynamics import eta, api_state, ZVIR, RD
     from oracle.cubed_sphere import R
-    N, K = 12, 3
+    N, K = 12, (4 if two_sided else 3)
     ak, bk = eta(K, CFG["ptop"])
     f, rng = api_state(N, K, 77, ak, bk, nonhydro)
     act = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3"] + (["w", "delz"] if nonhydro else [])
@@ -28,7 +30,11 @@ def _inputs(nonhydro):
     names = act + ([] if nonhydro else ["w"]) + ["phis"]
     f = {k: f[k] for k in names}
     cfg = dict(CFG); cfg.update(zvir=ZVIR, k_split=1, n_split=2, dt=900.0, hord_tr=2, rdgas=RD, grav=9.80665, p_fac=0.05)
-    p = dict(cfg); p.update(do_vort_damp=1, hydrostatic=0 if nonhydro else 1, nq=4, bdt=900.0)
+    if two_sided:
+        cfg.update(REF_DEFAULTS)
+    p = two_sided_params(cfg); p.update(do_vort_damp=1, hydrostatic=0 if nonhydro else 1, nq=4, bdt=900.0)
+    if two_sided:
+        p["_oracle_cfg"] = cfg          # (make_golden reads it; removed before the parameters reach the library)
     dx = {k: rng.standard_normal(f[k].shape) * (np.abs(f[k]).mean() * 1e-3 + 1e-30) for k in act}
     y = {k + "_n": np.zeros_like(f[k]) for k in act}
     for k in act:
@@ -39,6 +45,7 @@ def _inputs(nonhydro):
 def _run_all(h, N, K, f, act, p, dx, y):
     """NL / TL / AD of module 'step' on handle h (any decomposition); returns global arrays"""
     import fv3lm
+    p = {k: (int(v) if isinstance(v, bool) else v) for k, v in p.items() if not k.startswith("_")}
     NX = N + 7
     outs = [k + "_n" for k in act]
     zero = lambda: np.zeros((6, K, NX, NX))
@@ -65,14 +72,14 @@ def _run_all(h, N, K, f, act, p, dx, y):
     return res
 
 
-def _worker(rank, world, port, nonhydro, outdir):
+def _worker(rank, world, port, nonhydro, outdir, two_sided=False):
     sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.join(os.path.dirname(HERE), "fv3-jedi-linearmodel_b200"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     import fv3lm
     from common import metrics
-    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro)
+    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro, two_sided)
     cfg = fv3lm.default_config(N, K, rank=rank, nranks=world)
     h = fv3lm.FV3LM(cfg, ak, bk, emu=True)
     h.set_metrics(metrics(N))
@@ -100,17 +107,17 @@ def _worker(rank, world, port, nonhydro, outdir):
     dist.destroy_process_group()
 
 
-def _check(world, nonhydro):
+def _check(world, nonhydro, two_sided=False):
     sys.path.insert(0, HERE)
     import fv3lm
     from common import metrics
-    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro)
+    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro, two_sided)
     h = fv3lm.FV3LM(fv3lm.default_config(N, K), ak, bk, emu=True)
     h.set_metrics(metrics(N))
     ref = _run_all(h, N, K, f, act, p, dx, y)
     port = 29600 + (os.getpid() % 200)
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, port, nonhydro, d), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, nonhydro, d, two_sided), nprocs=world, join=True)
         parts = [np.load(os.path.join(d, "rank%d.npz" % r)) for r in range(world)]
         tot = {k: sum(pt[k] for pt in parts) for k in ref}    # every rank wrote only its own cells (zeros elsewhere)
     for k in ref:
@@ -126,6 +133,11 @@ def _check(world, nonhydro):
 @pytest.mark.parametrize("world,nonhydro", [(2, False), (2, True), (4, True)])
 def test_multirank_step_gloo(world, nonhydro):
     _check(world, nonhydro)
+
+
+def test_multirank_step_two_sided_gloo():
+    """two-sided mode (detached views, spliced chains, monotone trajectory schemes) sharded over two ranks"""
+    _check(2, True, two_sided=True)
 
 
 @pytest.mark.gpu

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Regenerates tests/golden/*.npz: outputs of the ORACLE (torch fp64 restatement) for one C12 fv3jedi_lm dynamics
-step, hydrostatic and non-hydrostatic: NL result, TL result (jvp) for a seeded increment and AD result (vjp) for a
+step, hydrostatic, non-hydrostatic and non-hydrostatic in two-sided mode (both flag structures at the reference's defaults): NL result, TL result (jvp) for a seeded increment and AD result (vjp) for a
 seeded adjoint vector.  The reference itself cannot be run here (no Fortran/FMS/MPI), so these fixtures pin the
 oracle against silent regressions between rounds -- they are NOT reference outputs (parity unpinned).
   python tools/make_golden.py
@@ -15,13 +15,14 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "fv3-jedi-linear
     sys.path.insert(0, p)
 
 
-def case(nonhydro):
+def case(nonhydro, two_sided=False):
     from test_multirank import _inputs
     from oracle import fv_dynamics as ofv
     from common import ograd
-    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro)
+    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro, two_sided)
     g = ograd(N)
-    cfg = dict(p); cfg["hydrostatic"] = not nonhydro
+    cfg = dict(p["_oracle_cfg"]) if two_sided else dict(p)
+    cfg.update(hydrostatic=not nonhydro, nq=4, bdt=900.0)
     phis = torch.from_numpy(f["phis"])
     def fn(*a):
         o = ofv.step_nl(dict(zip(act, a)), g, ak, bk, cfg, phis)
@@ -41,8 +42,10 @@ def case(nonhydro):
 
 if __name__ == "__main__":
     torch.set_default_dtype(torch.float64)
-    for nh in (False, True):
-        out = case(nh)
-        path = os.path.join(ROOT, "tests", "golden", "step_c12_%s.npz" % ("nonhydro" if nh else "hydro"))
+    for nh, two in ((False, False), (True, False), (True, True)):
+        if len(sys.argv) > 1 and sys.argv[1] == "two_sided" and not two:
+            continue                        # (regenerate only the new fixture)
+        out = case(nh, two)
+        path = os.path.join(ROOT, "tests", "golden", "step_c12_%s%s.npz" % ("nonhydro" if nh else "hydro", "_two_sided" if two else ""))
         np.savez_compressed(path, **out)
         print(path, os.path.getsize(path))
