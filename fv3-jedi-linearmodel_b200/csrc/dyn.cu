@@ -182,6 +182,8 @@ void dyn_config_from(DynConfig& c, const ModuleParams& prm) {
   c.a_imp = prm.get("a_imp", f->a_imp != 0.0 ? f->a_imp : 1.0);
   c.p_fac = prm.get("p_fac", f->p_fac != 0.0 ? f->p_fac : 0.05);
   c.d_con = prm.get("d_con", f->d_con);
+  c.q_split = prm.geti("q_split", f->q_split_dynamic ? 0 : 1);
+  c.q_split_max = prm.geti("q_split_max", f->q_split_max > 0 ? f->q_split_max : 3);
   if (prm.geti("two_sided", f->two_sided)) {
     // the main fields are the perturbation model's switches; the trajectory side comes from cfg.traj (module params: "t.<name>")
     DynConfig::PertSide& q = c.pert;

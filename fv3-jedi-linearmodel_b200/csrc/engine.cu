@@ -143,6 +143,14 @@ void Program::release(int id) {
   if (v.pert) { dv->pool.put(v.pert); v.pert = nullptr; }
 }
 
+void Program::check_status_flags() {
+  for (const StatusFlag& f : status_flags) {
+    double v = 0.0;
+    dev::d2h(&v, f.flag, sizeof(double));
+    if (v != 0.0) throw std::runtime_error("fv3lm: " + f.what + " " + std::to_string((long long)v));
+  }
+}
+
 void Program::run_op(Op& op, int mode) {
   if (op.tl_only && mode == MODE_NL) return;          // perturbation-scheme chain: nothing of it is needed by a trajectory sweep
   for (int i : op.in) if (vals[i].alias >= 0) vals[i].traj = vals[vals[i].alias].traj;

@@ -20,6 +20,7 @@
 #include <string.h>
 #include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 #include <stdexcept>
@@ -426,6 +427,12 @@ struct Program {
   std::string name;
   std::vector<int> seg_start;        // op indices where a recompute segment of the adjoint begins
   void mark_segment() { seg_start.push_back((int)ops.size()); }
+  // device-side status flags raised by ops (value != 0 = error; checked by the step API after a sweep) and small device tables
+  // that live as long as the program
+  struct StatusFlag { const double* flag; std::string what; };
+  std::vector<StatusFlag> status_flags;
+  std::vector<std::shared_ptr<void>> keep_alive;
+  void check_status_flags();
   bool tl_only = false;              // builders set this around the ops of a perturbation-scheme chain (copied into Op::tl_only)
   std::map<int, int> detached_of;
   int detached(int id) {             // detached view of a value (cached); negative ids (absent optional inputs) pass through

@@ -5,6 +5,8 @@
 #include "fvdyn.h"
 #include "nh.h"
 #include "modules.h"
+#include "comm.h"
+#include <memory>
 
 namespace fv3lm {
 
@@ -56,10 +58,170 @@ struct S_trc_upd {
   }
 };
 
+// ---------------------------------------------------------------------------------
+// q_split = 0: the reference chooses the number of tracer sub-steps from the accumulated Courant numbers at run time
+// (fv_tracer2d_nlm.F90:351-420: cmax(k) -> mp_reduce_max -> nsplt = int(1 + max_k cmax), ksplt(k) = int(1 + cmax(k)), fluxes
+// scaled by 1/ksplt(k)).  Here the program stays static (q_split_max sub-steps are always issued, so it replays as one CUDA
+// graph and needs no host synchronisation): a small device table holds frac(k), ksplt(k) and nsplt, and the stages of a sub-step
+// `it` pass a level through unchanged when it > ksplt(k).  nsplt > q_split_max raises a flag that fv3lm_step_* turns into an error.
+// The table is trajectory-only (the TL/AD scale the flux increments by the same 1/ksplt(k), fv_tracer2d_tlm.F90:240-242).
+// ---------------------------------------------------------------------------------
+struct TrcTable {      // device doubles: [0,K) frac ; [K,2K) ksplt ; [2K] nsplt ; [2K+1] overflow ; [2K+2, 3K+2) cmax ; then (nranks-1) K received
+  double* p = nullptr; int K = 0;
+  ~TrcTable() { dev::free_(p); }
+};
+struct KTrcCmax {      // per-level maximum of the Courant numbers over the cells this rank owns (:353-371)
+  Geom g; Metrics m; const double* cx; const double* cy; double* cmax; int K;
+  DEV void operator()(int ii, int jj, int z) const {
+    const int il = ii - (g.ng - 1), jl = jj - (g.ng - 1);
+    if (il < g.is || il > g.ie || jl < g.js || jl > g.je) return;
+    const int k = z % K, tile = z / K;
+    const int o = (tile * K + k) * g.slab + jj * g.pitch + ii;
+    double v = fmax(fabs(cx[o]), fabs(cy[o]));
+    if (!(k + 1 < K / 6)) v += 1.0 - 1.0 / sqrt(m.rsin2[tile * g.slab + jj * g.pitch + ii]);     // + 1 - sin_sg(5)
+#ifdef FV3LM_HOST_EMU
+    if (v > cmax[k]) cmax[k] = v;
+#else
+    atomicMax((unsigned long long*)(cmax + k), (unsigned long long)__double_as_longlong(v));      // v >= 0: the bit patterns order like the values
+#endif
+  }
+};
+struct KTrcKsplt {     // one thread: global maximum, nsplt, ksplt(k), frac(k) (:374-420)
+  double* t; int K, nother, nmax;
+  DEV void operator()(int ii, int, int) const {
+    if (ii != 0) return;
+    double* cmax = t + 2 * K + 2;
+    double cg = 0.0;
+    for (int k = 0; k < K; k++) {
+      double c = cmax[k];
+      for (int r = 0; r < nother; r++) c = fmax(c, cmax[(r + 1) * K + k]);
+      cmax[k] = c; cg = fmax(cg, c);
+    }
+    const int nsplt = (int)(1.0 + cg);
+    for (int k = 0; k < K; k++) {
+      const int ks = nsplt != 1 ? (int)(1.0 + cmax[k]) : 1;
+      t[K + k] = (double)ks; t[k] = 1.0 / (double)ks;
+    }
+    t[2 * K] = (double)nsplt;
+    t[2 * K + 1] = nsplt > nmax ? (double)nsplt : 0.0;
+  }
+};
+// a * frac(k) over the whole array.   in: a ; out: a frac
+struct S_lev_scale {
+  static constexpr int NI = 1, NO = 1;
+  struct P { const double* frac; };
+  static constexpr int NT = 1;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) { x.out(0, x.in(0) * LDG(p.frac + x.kk)); }
+};
+// sub-step `it` of the tracer update: levels with it > ksplt(k) pass through.  in: q dp1 fx fy dp2 ; out: q_new
+struct S_trc_upd_dyn {
+  static constexpr int NI = 5, NO = 1;
+  struct P { const double* tab; int K, it; };
+  static constexpr int NT = 7;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, 0, 0, 0}, {2, 1, 0, 0}, {3, 0, 0, 0}, {3, 0, 1, 0}, {4, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    if ((double)p.it > LDG(p.tab + p.K + x.kk)) { x.out(0, x.in(0)); return; }
+    x.out(0, (x.in(0) * x.in(1) + ((x.in(2) - x.in(2, 1, 0)) + (x.in(3) - x.in(3, 0, 1))) * x.M(x.m.rarea)) / x.in(4));
+  }
+};
+// dp1 for the next sub-step (:488-494): dp2 where this level took sub-step `it` and it is not the last one.  in: dp1 dp2 ; out: dp1'
+struct S_trc_dp1_dyn {
+  static constexpr int NI = 2, NO = 1;
+  struct P { const double* tab; int K, it; };
+  static constexpr int NT = 2;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie, g.js, g.je)) return;
+    const bool take = (double)p.it <= LDG(p.tab + p.K + x.kk) && (double)p.it != LDG(p.tab + 2 * p.K);
+    x.out(0, take ? x.in(1) : x.in(0));
+  }
+};
+
+static std::shared_ptr<TrcTable> add_trc_table(Program& P, int cx, int cy, int nmax) {
+  const Geom& g = P.dv->g;
+  const int K = g.K;
+  Comm* comm = P.dv->comm;
+  const int nother = comm && comm->nranks > 1 ? comm->nranks - 1 : 0;
+  auto tab = std::make_shared<TrcTable>();
+  tab->K = K;
+  const size_t n = (size_t)(2 * K + 2) + (size_t)(1 + nother) * K;
+  tab->p = (double*)dev::alloc(n * sizeof(double));
+  dev::zero(tab->p, n * sizeof(double));
+  Op op; op.name = "trc_cmax"; op.in = {cx, cy}; op.nk_launch = 1; op.tl_only = false;
+  op.run = [tab, comm, nother, nmax, n](Program& P, Op& o, int mode) {
+    if (mode == MODE_AD) return;                 // trajectory-only: the table of the forward sweep is still valid
+    const Geom& g = P.dv->g;
+    const int K = tab->K;
+    double* cmax = tab->p + 2 * K + 2;
+    dev::zero(cmax, (size_t)(1 + nother) * K * sizeof(double));
+    launch3d(KTrcCmax{g, P.dv->m, P.vals[o.in[0]].traj, P.vals[o.in[1]].traj, cmax, K}, g.NX, g.NY, g.ntile * K);
+    if (nother) {                                // mp_reduce_max: every rank sends its K maxima to every other rank
+      std::vector<int> peers; std::vector<double*> sb, rb; std::vector<size_t> sc, rc;
+      for (int r = 0, k = 0; r < comm->nranks; r++) {
+        if (r == comm->rank) continue;
+        peers.push_back(r); sb.push_back(cmax); rb.push_back(cmax + (size_t)(1 + k) * K); sc.push_back(K); rc.push_back(K); k++;
+      }
+      comm->exchange(nother, peers.data(), sb.data(), sc.data(), rb.data(), rc.data());
+    }
+    launch3d(KTrcKsplt{tab->p, K, nother, nmax}, 1, 1, 1);
+    (void)n;
+  };
+  P.ops.push_back(op);
+  P.status_flags.push_back({tab->p + 2 * K + 1, "tracer_2d (q_split = 0) needs more sub-steps than fv3lm_config.q_split_max: nsplt ="});
+  P.keep_alive.push_back(tab);
+  return tab;
+}
+
 std::vector<int> build_tracer_2d(Program& P, Mosaic& mo, std::vector<int> q, int dp1, int mfx, int mfy, int cx, int cy, int hord_tr, const std::string& tag,
-                                 int hord_tr_pert) {
+                                 int hord_tr_pert, int q_split, int q_split_max) {
   const int K = P.dv->g.K;
   auto nm = [&](const std::string& s) { return tag + "." + s; };
+  if (q_split != 0 && q_split != 1) throw std::runtime_error("tracer_2d: a fixed q_split > 1 is not built (1 = one sub-step, 0 = from the Courant numbers)");
+  if (q_split == 0) {
+    const int nmax = q_split_max > 0 ? q_split_max : 3;
+    int xfx0 = P.val(nm("xfx0"), K), yfx0 = P.val(nm("yfx0"), K);
+    P.add<S_trc_fx>("trc_fx", {0}, {cx, cy}, {xfx0, yfx0}, K);
+    auto tab = add_trc_table(P, cx, cy, nmax);
+    auto scaled = [&](int a, const char* n) { int o = P.val(nm(n), K); P.add<S_lev_scale>("trc_scale", {tab->p}, {a}, {o}, K); return o; };
+    const int cxs = scaled(cx, "cx_s"), cys = scaled(cy, "cy_s"), xfx = scaled(xfx0, "xfx"), yfx = scaled(yfx0, "yfx"), mfxs = scaled(mfx, "mfx_s"), mfys = scaled(mfy, "mfy_s");
+    int ra_x = P.val(nm("ra_x"), K), ra_y = P.val(nm("ra_y"), K);
+    P.add<S_ra>("trc_ra", {0}, {xfx, yfx}, {ra_x, ra_y}, K);
+    LevOrd ho; for (int k = 0; k < 128; k++) ho.v[k] = (signed char)enc_hord(hord_tr);
+    LevOrd hp = ho; if (hord_tr_pert) for (int k = 0; k < 128; k++) hp.v[k] = (signed char)enc_hord(hord_tr_pert);
+    const bool split = hord_tr_pert != 0 && hord_tr_pert != hord_tr;
+    auto D = [&](int id) { return P.detached(id); };
+    for (int it = 1; it <= nmax; it++) {
+      const std::string ti = "it" + std::to_string(it) + ".";
+      int dp2 = P.val(nm(ti + "dp2"), K);
+      P.add<S_trc_dp2>("trc_dp2", {0}, {dp1, mfxs, mfys}, {dp2}, K);
+      std::vector<int> out;
+      for (size_t n = 0; n < q.size(); n++) {
+        const std::string tq = ti + "tp_q" + std::to_string(n);
+        if (it > 1) add_patch(P, "halo_q", &mo.h_center, {q[n]});       // (:403-407: the update of the previous sub-step completes here)
+        TpOut f;
+        if (!split) f = build_fv_tp_2d(P, mo, q[n], cxs, cys, xfx, yfx, ra_x, ra_y, mfxs, mfys, ho, K, nm(tq));
+        else {
+          P.tl_only = true;
+          TpOut a = build_fv_tp_2d(P, mo, q[n], cxs, cys, xfx, yfx, ra_x, ra_y, mfxs, mfys, hp, K, nm(tq + "_p"));
+          P.tl_only = false;
+          TpOut b = build_fv_tp_2d(P, mo, D(q[n]), D(cxs), D(cys), D(xfx), D(yfx), D(ra_x), D(ra_y), D(mfxs), D(mfys), ho, K, nm(tq + "_t"));
+          f.fx = P.val(nm(tq + ".fx"), K); f.fy = P.val(nm(tq + ".fy"), K);
+          P.add<S_splice>("splice", {0}, {a.fx, b.fx}, {f.fx}, K);
+          P.add<S_splice>("splice", {0}, {a.fy, b.fy}, {f.fy}, K);
+        }
+        int qn = P.val(nm(ti + "q" + std::to_string(n)), K);
+        P.add<S_trc_upd_dyn>("trc_upd", {tab->p, K, it}, {q[n], dp1, f.fx, f.fy, dp2}, {qn}, K);
+        out.push_back(qn);
+      }
+      q = out;
+      if (it < nmax) { int d1 = P.val(nm(ti + "dp1"), K); P.add<S_trc_dp1_dyn>("trc_dp1", {tab->p, K, it}, {dp1, dp2}, {d1}, K); dp1 = d1; }
+    }
+    return q;
+  }
   int xfx = P.val(nm("xfx"), K), yfx = P.val(nm("yfx"), K), ra_x = P.val(nm("ra_x"), K), ra_y = P.val(nm("ra_y"), K), dp2 = P.val(nm("dp2"), K);
   P.add<S_trc_fx>("trc_fx", {0}, {cx, cy}, {xfx, yfx}, K);
   P.add<S_ra>("trc_ra", {0}, {xfx, yfx}, {ra_x, ra_y}, K);
@@ -327,7 +489,7 @@ FvOut build_fv_dynamics(Program& P, Mosaic& mo, const DynConfig& c, const std::v
     DynOut d = c.hydrostatic ? build_dyn_core(P, mo, cd, ds, tg) : build_dyn_core_nh(P, mo, cd, ak, bk, ds, tg);
     P.mark_segment();
     for (int& x : q) add_patch(P, "halo_q", &mo.h_center, {x});
-    q = build_tracer_2d(P, mo, q, dp1, d.mfx, d.mfy, d.cx, d.cy, c.hord_tr, tg + ".trc", c.pert.on ? c.pert.hord_tr : 0);
+    q = build_tracer_2d(P, mo, q, dp1, d.mfx, d.mfy, d.cx, d.cy, c.hord_tr, tg + ".trc", c.pert.on ? c.pert.hord_tr : 0, c.q_split, c.q_split_max);
     P.mark_segment();
     RemapOut r = build_remap(P, mo, c, ak, bk, d.pe, d.pk, d.peln, d.pt, q, d.u, d.v, n_map == c.k_split, tg + ".rm",
                              d.delp, c.hydrostatic ? -1 : d.w, c.hydrostatic ? -1 : d.delz, c.hydrostatic ? -1 : d.ws);
@@ -349,6 +511,19 @@ void mod_remap(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
   RemapOut r = build_remap(P, mo, c, *prm.ak, *prm.bk, pe, pk, peln, pt, {q0}, u, v, prm.geti("last_step", 1) != 0, "rm", -1, -1, -1, -1);
   io.out(P, "pt_n", r.pt); io.out(P, "q0_n", r.q[0]); io.out(P, "u_n", r.u); io.out(P, "v_n", r.v); io.out(P, "delp_n", r.delp);
   io.out(P, "pkz_n", r.pkz); io.out(P, "pe_n", r.pe);
+}
+
+void mod_tracer_2d(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
+  // tracer_2d alone (fv_tracer2d_nlm.F90:275-516) on two tracers: the sub-step logic of q_split = 0 needs Courant numbers a
+  // model step at test sizes never reaches
+  const int K = P.dv->g.K;
+  DynConfig c; dyn_config_from(c, prm);
+  int q0 = io.in(P, "q0", K), q1 = io.in(P, "q1", K), dp1 = io.in(P, "dp1", K);
+  int mfx = io.in(P, "mfx", K), mfy = io.in(P, "mfy", K), cx = io.in(P, "cx", K), cy = io.in(P, "cy", K);
+  std::vector<int> q = {q0, q1};
+  for (int& x : q) add_patch(P, "halo_q", &mo.h_center, {x});
+  q = build_tracer_2d(P, mo, q, dp1, mfx, mfy, cx, cy, c.hord_tr, "trc", c.pert.on ? c.pert.hord_tr : 0, c.q_split, c.q_split_max);
+  io.out(P, "q0_n", q[0]); io.out(P, "q1_n", q[1]);
 }
 
 void mod_step(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {

@@ -129,7 +129,9 @@ subroutine create(self,conf)
  cfg%do_vort_damp = merge(1, 0, self%FV_AtmP(1)%flagstruct%do_vort_damp_pert)
  cfg%rank = mpp_pe() - mpp_root_pe(); cfg%nranks = mpp_npes()
  cfg%layout_x = A%layout(1); cfg%layout_y = A%layout(2)
- cfg%reserved0 = 0; cfg%reserved = 0
+ cfg%reserved0 = 0
+ ! q_split = 0 in fv_core_nml: tracer sub-steps chosen from the Courant numbers at run time
+ cfg%q_split_dynamic = merge(1, 0, A%flagstruct%q_split == 0); cfg%q_split_max = 4
  ! two-sided mode: the fields above carry the perturbation model's switches, cfg%traj the nonlinear model's
  ! (already forced to the perturbation's by fv_control_tlmadm.F90:219-253 where split_hord / split_damp are false)
  cfg%two_sided = 1

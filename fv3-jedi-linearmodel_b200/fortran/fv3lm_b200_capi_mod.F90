@@ -29,7 +29,7 @@ type, bind(c) :: fv3lm_config
   integer(c_int) :: reserved0
   real(c_double) :: a_imp, p_fac, d_con
   integer(c_int) :: two_sided, split_damp, hord_ks_pert, hord_ks_traj
-  integer(c_int) :: reserved(2)
+  integer(c_int) :: q_split_dynamic, q_split_max
   type(fv3lm_traj_flags) :: traj
   real(c_double) :: d2_bg_ks
 end type fv3lm_config

@@ -2,7 +2,7 @@
 fv3jedi_lm dynamics-component step, restated in torch float64 from
 
   model/fv_dynamics_nlm.F90 :70-760  (TL model_tlmadm/fv_dynamics_tlm.F90:87, AD fv_dynamics_adm.F90:110/874)
-  model/fv_tracer2d_nlm.F90 :275-516 tracer_2d (q_split = 1: one sub-split, no allreduce R1)
+  model/fv_tracer2d_nlm.F90 :275-516 tracer_2d (q_split = 1: one sub-step; q_split = 0: sub-steps from the Courant numbers)
   src/dynamics/fv3jedi_lm_dynamics_mod.F90  step_nl/tl/ad :268/:347/:460, traj_to_fv3 :717,
                                             pert_to_fv3 :848, fv3_to_pert :893
   model_tlmadm/fv_pressure.F90 :22-69 compute_fv3_pressures
@@ -25,8 +25,14 @@ from .dyn_core import halo_of, dyn_core_hydro
 from .fv_mapz import lagrangian_to_eulerian
 
 
-def tracer_2d(qs, dp1, mfx, mfy, cx, cy, g, hord, hord_pert=None):
-    """fv_tracer2d_nlm.F90:275-516 with nsplt = 1.  qs: list of tracers (halo valid)."""
+def tracer_2d(qs, dp1, mfx, mfy, cx, cy, g, hord, hord_pert=None, q_split=1, q_split_max=3, halo=None):
+    """fv_tracer2d_nlm.F90:275-516.  qs: list of tracers (halo valid).
+    q_split = 1: one sub-step (nsplt = 1).
+    q_split = 0: nsplt = int(1 + max_k cmax(k)) and ksplt(k) = int(1 + cmax(k)) from the Courant numbers (:351-378), the
+    transport terms scaled by 1/ksplt(k) (:384-420), level k advanced only in sub-steps it <= ksplt(k) (:433), dp1 carried forward
+    except after the last sub-step (:482-488), halo of q renewed between sub-steps (:496-502, `halo`).  ksplt / frac are not
+    differentiated (fv_tracer2d_tlm.F90:964-996 scales cx_tl ... by the same frac).  The loop here always runs q_split_max
+    sub-steps with a level mask (sub-steps beyond nsplt change nothing), so the function stays traceable by torch.func."""
     N = g.N
     is_, ie, js, je = 1, N, 1, N
     isd, ied, jsd, jed = g.isd, g.ied, g.jsd, g.jed
@@ -40,20 +46,45 @@ def tracer_2d(qs, dp1, mfx, mfy, cx, cy, g, hord, hord_pert=None):
     yfx = put4(Z(cx), i0, i1, j0, j1, torch.where(c > 0., c * S(g.dya, i0, i1, j0 - 1, j1 - 1) * S(g.dx, i0, i1, j0, j1) * S(sin4, i0, i1, j0 - 1, j1 - 1),
                                                  c * S(g.dya, i0, i1, j0, j1) * S(g.dx, i0, i1, j0, j1) * S(sin2, i0, i1, j0, j1)))
     rar = S(g.rarea, is_, ie, js, je)
-    dp2 = S(dp1, is_, ie, js, je) + ((S(mfx, is_, ie, js, je) - S(mfx, is_ + 1, ie + 1, js, je)) + (S(mfy, is_, ie, js, je) - S(mfy, is_, ie, js + 1, je + 1))) * rar
+    nit = 1
+    ksplt = nsplt = None
+    if q_split == 0:
+        K = cx.shape[1]
+        cm = torch.maximum(S(cx, is_, ie, js, je).detach().abs(), S(cy, is_, ie, js, je).detach().abs())
+        lower = (torch.arange(1, K + 1) >= K // 6).to(cm.dtype)[None, :, None, None]          # k < npz/6: plain maximum (:353-365)
+        cm = cm + lower * (1. - S(g.sin_sg[..., 5], is_, ie, js, je))
+        cmax = cm.amax(dim=(0, 2, 3))                                                          # all tiles = mp_reduce_max (:374)
+        nsplt = torch.floor(1. + cmax.max())
+        ksplt = torch.where(nsplt != 1., torch.floor(1. + cmax), torch.ones_like(cmax))[None, :, None, None]
+        frac = 1. / ksplt
+        cx, cy, xfx, yfx, mfx, mfy = cx * frac, cy * frac, xfx * frac, yfx * frac, mfx * frac, mfy * frac
+        nit = q_split_max
     ra_x = put4(Z(cx), is_, ie, jsd, jed, S(g.area, is_, ie, jsd, jed) + (S(xfx, is_, ie, jsd, jed) - S(xfx, is_ + 1, ie + 1, jsd, jed)))
     ra_y = put4(Z(cx), isd, ied, js, je, S(g.area, isd, ied, js, je) + (S(yfx, isd, ied, js, je) - S(yfx, isd, ied, js + 1, je + 1)))
-    out = []
-    for q in qs:
-        fx, fy, _ = tp.fv_tp_2d(q, cx, cy, hord, xfx, yfx, g, ra_x, ra_y, mfx=mfx, mfy=mfy)
-        if hord_pert is not None and hord_pert != hord:      # model_tlmadm/fv_tracer2d_tlm.F90:1060-1090
-            from .d_sw import splice
-            fxp, fyp, _ = tp.fv_tp_2d(q, cx, cy, hord_pert, xfx, yfx, g, ra_x, ra_y, mfx=mfx, mfy=mfy)
-            fx, fy = splice(fxp, fx), splice(fyp, fy)
-        qn = (S(q, is_, ie, js, je) * S(dp1, is_, ie, js, je) +
-              ((S(fx, is_, ie, js, je) - S(fx, is_ + 1, ie + 1, js, je)) + (S(fy, is_, ie, js, je) - S(fy, is_, ie, js + 1, je + 1))) * rar) / dp2
-        out.append(put4(q, is_, ie, js, je, qn))
-    return out
+    qs = list(qs)
+    for it in range(1, nit + 1):
+        if it > 1:
+            qs = [halo.scalar(q) for q in qs]
+        dp2 = S(dp1, is_, ie, js, je) + ((S(mfx, is_, ie, js, je) - S(mfx, is_ + 1, ie + 1, js, je)) + (S(mfy, is_, ie, js, je) - S(mfy, is_, ie, js + 1, je + 1))) * rar
+        out = []
+        for q in qs:
+            fx, fy, _ = tp.fv_tp_2d(q, cx, cy, hord, xfx, yfx, g, ra_x, ra_y, mfx=mfx, mfy=mfy)
+            if hord_pert is not None and hord_pert != hord:      # model_tlmadm/fv_tracer2d_tlm.F90:1060-1090
+                from .d_sw import splice
+                fxp, fyp, _ = tp.fv_tp_2d(q, cx, cy, hord_pert, xfx, yfx, g, ra_x, ra_y, mfx=mfx, mfy=mfy)
+                fx, fy = splice(fxp, fx), splice(fyp, fy)
+            qn = (S(q, is_, ie, js, je) * S(dp1, is_, ie, js, je) +
+                  ((S(fx, is_, ie, js, je) - S(fx, is_ + 1, ie + 1, js, je)) + (S(fy, is_, ie, js, je) - S(fy, is_, ie, js + 1, je + 1))) * rar) / dp2
+            if ksplt is not None:
+                qn = torch.where(it <= ksplt, qn, S(q, is_, ie, js, je))
+            out.append(put4(q, is_, ie, js, je, qn))
+        qs = out
+        if ksplt is not None:
+            take = (it <= ksplt) & (nsplt != it)
+            dp1 = put4(dp1, is_, ie, js, je, torch.where(take, dp2, S(dp1, is_, ie, js, je)))
+    if q_split == 0:
+        tracer_2d.last_nsplt = int(nsplt)            # (tests: which branch the inputs exercised, and the overflow condition)
+    return qs
 
 
 def compute_pressures(delp, ptop, kappa):
@@ -99,7 +130,7 @@ def fv_dynamics(st, g, ak, bk, cfg):
         q = [halo.scalar(x) for x in q]
         two = bool(cfg.get("traj"))
         q = tracer_2d(q, dp1, d["mfx"], d["mfy"], d["cx"], d["cy"], g, cfg["traj"]["hord_tr"] if two else cfg["hord_tr"],
-                      cfg["hord_tr"] if two else None)
+                      cfg["hord_tr"] if two else None, q_split=cfg.get("q_split", 1), q_split_max=cfg.get("q_split_max", 3), halo=halo)
         r = dict(pe=d["pe"], pk=d["pk"], peln=d["peln"], pkz=d["pkz"], delp=delp, pt=pt, u=u, v=v, q=q)
         if not hydro:
             r.update(w=w, delz=delz, ws=d["ws"])

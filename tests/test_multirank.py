@@ -42,12 +42,12 @@ def _inputs(nonhydro, two_sided=False):
     return N, K, ak, bk, f, act, p, dx, y
 
 
-def _run_all(h, N, K, f, act, p, dx, y):
-    """NL / TL / AD of module 'step' on handle h (any decomposition); returns global arrays"""
+def _run_all(h, N, K, f, act, p, dx, y, module="step"):
+    """NL / TL / AD of a module on handle h (any decomposition); returns global arrays"""
     import fv3lm
     p = {k: (int(v) if isinstance(v, bool) else v) for k, v in p.items() if not k.startswith("_")}
     NX = N + 7
-    outs = [k + "_n" for k in act]
+    outs = list(y.keys())
     zero = lambda: np.zeros((6, K, NX, NX))
     res = {}
     traj = {k: h.scatter(f[k]) for k in f}
@@ -56,7 +56,7 @@ def _run_all(h, N, K, f, act, p, dx, y):
     pert = {k: h.scatter(dx[k]) for k in act}
     for o in outs:
         pert[o] = h.scatter(zero())
-    h.module_run("step", fv3lm.MODE_TL, traj, pert, params=p)
+    h.module_run(module, fv3lm.MODE_TL, traj, pert, params=p)
     for o in outs:
         res["nl." + o] = h.gather(traj[o], zero(), closed=False)
         res["tl." + o] = h.gather(pert[o], zero(), closed=False)
@@ -66,10 +66,30 @@ def _run_all(h, N, K, f, act, p, dx, y):
     pert = {k: h.scatter(np.zeros_like(f[k])) for k in act}
     for o in outs:
         pert[o] = h.scatter_owned(y[o])
-    h.module_run("step", fv3lm.MODE_AD, traj, pert, params=p)
+    h.module_run(module, fv3lm.MODE_AD, traj, pert, params=p)
     for k in act:
         res["ad." + k] = h.gather_add(pert[k], np.zeros_like(f[k]))
     return res
+
+
+def _inputs_tracer():
+    """tracer_2d with q_split = 0; the Courant numbers that set ksplt(k) = 2 and 3 sit on tiles 5 and 6 only, so with two ranks
+    (tiles 1-3 / 4-6) rank 0 gets the sub-step counts from the exchange of the level maxima (mp_reduce_max)"""
+    import test_tracer_2d as tt
+    from test_dyn_core import CFG
+    from oracle.cubed_sphere import R
+    N, K = 12, 6
+    f, rng = tt.fields(N, K, [0.5, 0.3, 0.6, 0.2, 0.4, 0.7], 5)
+    for tile, k, fac in ((4, 1, 4.5), (5, 3, 12.0), (5, 4, 3.0)):
+        for n in ("cx", "cy", "mfx", "mfy"):
+            f[n][tile, k] *= fac
+    act = list(f.keys())
+    p = dict(CFG); p.update(hord_tr=2, q_split=0, q_split_max=3)
+    dx = {k: rng.standard_normal(f[k].shape) * (np.abs(f[k]).mean() * 1e-3 + 1e-30) for k in act}
+    y = {o: np.zeros((6, K, N + 7, N + 7)) for o in ("q0_n", "q1_n")}
+    for o in y:
+        y[o][..., R(1, N), R(1, N)] = rng.standard_normal((6, K, N, N))
+    return N, K, None, None, f, act, p, dx, y
 
 
 def _worker(rank, world, port, nonhydro, outdir, two_sided=False):
@@ -79,7 +99,8 @@ def _worker(rank, world, port, nonhydro, outdir, two_sided=False):
     torch.set_num_threads(1)
     import fv3lm
     from common import metrics
-    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro, two_sided)
+    module = "tracer_2d" if nonhydro == "tracer_2d" else "step"
+    N, K, ak, bk, f, act, p, dx, y = _inputs_tracer() if module == "tracer_2d" else _inputs(nonhydro, two_sided)
     cfg = fv3lm.default_config(N, K, rank=rank, nranks=world)
     h = fv3lm.FV3LM(cfg, ak, bk, emu=True)
     h.set_metrics(metrics(N))
@@ -99,7 +120,7 @@ def _worker(rank, world, port, nonhydro, outdir, two_sided=False):
             if r.numel():
                 dst[...] = r.numpy()
     h.comm_set_callback(exchange)
-    res = _run_all(h, N, K, f, act, p, dx, y)
+    res = _run_all(h, N, K, f, act, p, dx, y, module)
     nex, nbytes = h.comm_stats()
     assert nex > 0 and nbytes > 0
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), **res)
@@ -111,10 +132,11 @@ def _check(world, nonhydro, two_sided=False):
     sys.path.insert(0, HERE)
     import fv3lm
     from common import metrics
-    N, K, ak, bk, f, act, p, dx, y = _inputs(nonhydro, two_sided)
+    module = "tracer_2d" if nonhydro == "tracer_2d" else "step"
+    N, K, ak, bk, f, act, p, dx, y = _inputs_tracer() if module == "tracer_2d" else _inputs(nonhydro, two_sided)
     h = fv3lm.FV3LM(fv3lm.default_config(N, K), ak, bk, emu=True)
     h.set_metrics(metrics(N))
-    ref = _run_all(h, N, K, f, act, p, dx, y)
+    ref = _run_all(h, N, K, f, act, p, dx, y, module)
     port = 29600 + (os.getpid() % 200)
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_worker, args=(world, port, nonhydro, d, two_sided), nprocs=world, join=True)
@@ -125,7 +147,7 @@ def _check(world, nonhydro, two_sided=False):
         e = np.abs(tot[k] - ref[k]).max() / den
         assert e < 1e-11, (k, e)
     # distributed dot-product test
-    lhs = sum((tot["tl." + k + "_n"] * y[k + "_n"]).sum() for k in act)
+    lhs = sum((tot["tl." + o] * y[o]).sum() for o in y)
     rhs = sum((dx[k] * tot["ad." + k]).sum() for k in act)
     assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs)), (lhs, rhs)
 
@@ -150,3 +172,16 @@ def test_multirank_step_nccl_gpu():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py"), "--nonhydro"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_multirank_tracer_sub_steps_gloo():
+    """q_split = 0: the per-level Courant maxima are exchanged between the ranks before the sub-step counts are fixed"""
+    _check(2, "tracer_2d")
+    import oracle.fv_dynamics as ofv, test_tracer_2d as tt
+    from oracle.dyn_core import halo_of
+    N, K, _, _, f, act, p, dx, y = _inputs_tracer()
+    from common import ograd
+    halo, _ = halo_of(N)
+    t = {k: torch.from_numpy(v) for k, v in f.items()}
+    ofv.tracer_2d([halo.scalar(t["q0"]), halo.scalar(t["q1"])], t["dp1"], t["mfx"], t["mfy"], t["cx"], t["cy"], ograd(N), 2, q_split=0, halo=halo)
+    assert ofv.tracer_2d.last_nsplt == 3          # the inputs do need the sub-steps

@@ -34,6 +34,8 @@ def make(emu, N=12, K=4, n_split=2, k_split=1, nonhydro=False, extra=None):
     cfg = dict(CFG); cfg.update(zvir=ZVIR, hydrostatic=not nonhydro, k_split=k_split, n_split=n_split, dt=900.0, hord_tr=2,
                                 rdgas=8314.47 / 28.965, grav=9.80665, p_fac=0.05)
     cfg.update(extra or {})
+    if cfg.get("q_split_dynamic"):          # fv_core_nml q_split = 0
+        cfg["q_split"] = 0
     return h, f, comp, rng, cfg, ak, bk
 
 
@@ -125,6 +127,23 @@ def test_step_api_reference_defaults_emu():
     """both flag structures at the reference's defaults (bench.py --two-sided): vorticity damping on the perturbation side only,
     whole column inside the perturbation sponge"""
     print(_run(True, nonhydro=True, extra=REF_DEFAULTS, taylor=False))
+
+
+def test_step_api_q_split_dynamic_emu():
+    """fv3lm_config.q_split_dynamic (the reference's q_split = 0): the step program carries the Courant-number table, the masked
+    sub-steps and the run-time check; at these Courant numbers one sub-step is taken, so the Taylor test applies as well.
+    (Levels on 2 and 3 sub-steps: tests/test_tracer_2d.py.)"""
+    r = _run(True, nonhydro=True, extra=dict(q_split_dynamic=1))
+    print(r)
+    assert ofv.tracer_2d.last_nsplt == 1
+    _repeat(True, True, extra=dict(q_split_dynamic=1, q_split_max=2))
+
+
+@pytest.mark.gpu
+def test_step_api_q_split_dynamic_gpu():
+    """as above on the device; the repeated calls replay the CUDA graph that holds the table kernels and the masked sub-steps"""
+    print(_run(False, nonhydro=True, extra=dict(q_split_dynamic=1)))
+    _repeat(False, True, extra=dict(q_split_dynamic=1))
 
 
 @pytest.mark.gpu
