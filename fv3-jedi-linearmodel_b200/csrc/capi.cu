@@ -96,6 +96,7 @@ int fv3lm_destroy(fv3lm_handle* h) {
     for (int f = 0; f < NFIELD; f++) dev::free_(r->pert[f]);
     dev::free_(r->phis);
     for (auto& s : r->slots) for (double* p : s) dev::free_(p);
+    for (auto& lt : r->turb) for (double* p : lt.d) dev::free_(p);
 #ifndef FV3LM_HOST_EMU
     for (auto& sg : r->graph) if (sg.exec) cudaGraphExecDestroy((cudaGraphExec_t)sg.exec);
 #endif
@@ -222,6 +223,7 @@ int fv3lm_module_run(fv3lm_handle* h, const char* module, int mode, int nfields,
   }
   dev::sync();
   for (int id : ext) { Value& v = P.vals[id]; h->dv.pool.put(v.traj); h->dv.pool.put(v.pert); v.traj = v.pert = nullptr; }
+  P.check_status_flags();
   FV3LM_CATCH(h)
 }
 

@@ -4,6 +4,7 @@
 #include "engine.h"
 #include "mosaic.h"
 #include "modules.h"
+#include "turb.h"
 #include <map>
 #include <memory>
 
@@ -27,6 +28,7 @@ struct StepRunner {
   double* pert[NFIELD];                           // device-resident perturbation / adjoint state (compact)
   double* phis = nullptr;
   std::vector<std::vector<double*>> slots;        // device-resident trajectory window (compact)
+  std::vector<fv3lm::TurbLtraj> turb;             // local trajectory of the turbulence scheme, per window slot
 };
 
 struct fv3lm_handle {

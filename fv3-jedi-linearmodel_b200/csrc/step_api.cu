@@ -148,6 +148,7 @@ void run_step(fv3lm_handle* h, int slot, int mode) {
   } else {
     run_program(h, MODE_NL);
   }
+  if (!r->P.status_flags.empty()) r->P.check_status_flags();     // (one small device-to-host read; only programs with run-time checks)
 }
 
 }  // namespace
@@ -235,6 +236,85 @@ int fv3lm_step_ad(fv3lm_handle* h, int slot, fv3lm_fields* pert) {
   if (!rc) rc = fv3lm_step_ad_dev(h, slot);
   if (!rc) rc = fv3lm_pert_download(h, pert);
   return rc;
+}
+
+// ---- linearised boundary-layer turbulence (src/physics/turbulence/fv3jedi_lm_turbulence_mod.F90) -----------------------
+// set_ltraj :375-533 keeps BL_DRIVER (the nonlinear scheme that produces the diagonals, once per trajectory time level) on the
+// caller's side of the boundary; the decomposition, p^kappa and every TL / AD / NL application run here.
+int fv3lm_turb_set_ltraj(fv3lm_handle* h, int slot, const fv3lm_turb_coeffs* co) {
+  FV3LM_TRY
+  ensure_runner(h);
+  StepRunner* r = h->step; const Geom& g = h->dv.g;
+  if (!co) throw std::runtime_error("fv3lm_turb_set_ltraj: null coefficients");
+  if (g.K < 2) throw std::runtime_error("fv3lm_turb_set_ltraj: needs npz >= 2");
+  if (slot < 0) throw std::runtime_error("fv3lm: negative trajectory slot");
+  if ((int)r->turb.size() <= slot) r->turb.resize(slot + 1);
+  TurbLtraj& lt = r->turb[slot];
+  const size_t n = compact_doubles(g, g.K);
+  const double* src[TURB_NARR] = {co->akv, co->bkv, co->ckv, co->aks, co->bks, co->cks, co->akq, co->bkq, co->ckq, co->pk};
+  static const char* nm[TURB_NARR] = {"akv", "bkv", "ckv", "aks", "bks", "cks", "akq", "bkq", "ckq", "pk"};
+  for (int a = 0; a < TURB_NARR; a++) {
+    if (!lt.d[a]) lt.d[a] = (double*)dev::alloc(n * sizeof(double));
+    if (src[a]) dev::h2d(lt.d[a], src[a], n * sizeof(double));
+    else if (a != TURB_PK) throw std::runtime_error(std::string("fv3lm_turb_set_ltraj: missing array ") + nm[a]);
+  }
+  const TurbDims s{g.ie, g.je, g.ntile, g.K};
+  if (!co->pk) {
+    if ((int)r->slots.size() <= slot || r->slots[slot].empty())
+      throw std::runtime_error("fv3lm_turb_set_ltraj: pk not given and trajectory slot not set (delp is needed)");
+    turb_pk(s, slot_field(h, slot, 3), lt.d[TURB_PK], h->cfg.ptop, h->cfg.kappa);
+  }
+  if (!co->decomposed) turb_lu(s, lt);
+  lt.set = true;
+  dev::sync();
+  FV3LM_CATCH(h)
+}
+
+static void turb_apply(fv3lm_handle* h, int slot, double* const* f10, bool adjoint) {
+  StepRunner* r = h->step; const Geom& g = h->dv.g;
+  if (slot < 0 || (int)r->turb.size() <= slot || !r->turb[slot].set)
+    throw std::runtime_error("fv3lm_turb_step: fv3lm_turb_set_ltraj was not called for this slot");
+  double* f7[7] = {f10[0], f10[1], f10[2], f10[4], f10[6], f10[5], f10[7]};      // u v t qv qi ql o3 (order of step_tl :259-265)
+  turb_solve(TurbDims{g.ie, g.je, g.ntile, g.K}, r->turb[slot], f7, pow(1.0e5, h->cfg.kappa), adjoint);
+}
+
+int fv3lm_turb_step_tl_dev(fv3lm_handle* h, int slot) {
+  FV3LM_TRY
+  ensure_runner(h);
+  turb_apply(h, slot, h->step->pert, false);
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_turb_step_ad_dev(fv3lm_handle* h, int slot) {
+  FV3LM_TRY
+  ensure_runner(h);
+  turb_apply(h, slot, h->step->pert, true);
+  FV3LM_CATCH(h)
+}
+
+int fv3lm_turb_step_tl(fv3lm_handle* h, int slot, fv3lm_fields* pert) {
+  int rc = fv3lm_pert_upload(h, pert);
+  if (!rc) rc = fv3lm_turb_step_tl_dev(h, slot);
+  if (!rc) rc = fv3lm_pert_download(h, pert);
+  return rc;
+}
+
+int fv3lm_turb_step_ad(fv3lm_handle* h, int slot, fv3lm_fields* pert) {
+  int rc = fv3lm_pert_upload(h, pert);
+  if (!rc) rc = fv3lm_turb_step_ad_dev(h, slot);
+  if (!rc) rc = fv3lm_pert_download(h, pert);
+  return rc;
+}
+
+// step_nl :149-213: the same solves applied to the trajectory fields of the slot, in place (coefficients of the same slot)
+int fv3lm_turb_step_nl(fv3lm_handle* h, int slot) {
+  FV3LM_TRY
+  ensure_runner(h);
+  StepRunner* r = h->step;
+  if (slot < 0 || (int)r->slots.size() <= slot || r->slots[slot].empty()) throw std::runtime_error("fv3lm_turb_step_nl: trajectory slot not set");
+  turb_apply(h, slot, r->slots[slot].data(), false);
+  dev::sync();
+  FV3LM_CATCH(h)
 }
 
 // Timed loop on the library's own stream (CUDA events): `iters` repetitions of one TL step followed

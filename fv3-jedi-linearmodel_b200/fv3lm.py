@@ -37,7 +37,7 @@ class Config(C.Structure):
                 ("rank", C.c_int), ("nranks", C.c_int), ("layout_x", C.c_int), ("layout_y", C.c_int), ("reserved0", C.c_int),
                 ("a_imp", C.c_double), ("p_fac", C.c_double), ("d_con", C.c_double),
                 ("two_sided", C.c_int), ("split_damp", C.c_int), ("hord_ks_pert", C.c_int), ("hord_ks_traj", C.c_int),
-                ("reserved", C.c_int * 2), ("traj", TrajFlags), ("d2_bg_ks", C.c_double)]
+                ("q_split_dynamic", C.c_int), ("q_split_max", C.c_int), ("traj", TrajFlags), ("d2_bg_ks", C.c_double)]
 
 
 class Fields(C.Structure):
@@ -48,7 +48,16 @@ EXPORTS = ["fv3lm_decomp_info", "fv3lm_nccl_unique_id", "fv3lm_comm_init_nccl", 
            "fv3lm_profile_steps", "fv3lm_set_phis", "fv3lm_traj_set", "fv3lm_traj_get", "fv3lm_step_nl", "fv3lm_step_tl", "fv3lm_step_ad",
            "fv3lm_pert_upload", "fv3lm_pert_download", "fv3lm_step_tl_dev", "fv3lm_step_ad_dev", "fv3lm_time_steps",
            "fv3lm_program_stats", "fv3lm_create", "fv3lm_destroy", "fv3lm_last_error", "fv3lm_set_metric", "fv3lm_set_metric_scalar",
-           "fv3lm_module_run", "fv3lm_module_list", "fv3lm_launch_count", "fv3lm_pool_peak_bytes", "fv3lm_sync"]
+           "fv3lm_module_run", "fv3lm_module_list", "fv3lm_launch_count", "fv3lm_pool_peak_bytes", "fv3lm_sync",
+           "fv3lm_turb_set_ltraj", "fv3lm_turb_step_nl", "fv3lm_turb_step_tl", "fv3lm_turb_step_ad", "fv3lm_turb_step_tl_dev",
+           "fv3lm_turb_step_ad_dev"]
+
+TURB_ARRAYS = ["akv", "bkv", "ckv", "aks", "bks", "cks", "akq", "bkq", "ckq", "pk"]
+
+
+class TurbCoeffs(C.Structure):
+    """mirror of fv3lm_turb_coeffs (include/fv3lm_b200.h)"""
+    _fields_ = [(n, C.POINTER(C.c_double)) for n in TURB_ARRAYS] + [("decomposed", C.c_int)]
 
 METRICS_2D = ["area", "rarea", "area_c", "rarea_c", "dx", "dy", "rdx", "rdy", "dxa", "dya", "rdxa", "rdya", "dxc",
               "dyc", "rdxc", "rdyc", "cosa", "sina", "rsina", "cosa_u", "sina_u", "rsin_u", "cosa_v", "sina_v",
@@ -294,6 +303,38 @@ class FV3LM:
 
     def step_ad_dev(self, slot):
         self._check(self.lib.fv3lm_step_ad_dev(self.h, int(slot)), "step_ad_dev")
+
+    # ---- linearised boundary-layer turbulence (fv3jedi_lm_turbulence_mod.F90) ----
+    def turb_set_ltraj(self, slot, coeffs, decomposed=False):
+        """coeffs: dict akv bkv ckv aks bks cks akq bkq ckq [pk] of compact float64 arrays (BL_DRIVER's diagonals)"""
+        st = TurbCoeffs()
+        keep = []
+        for n in TURB_ARRAYS:
+            a = coeffs.get(n)
+            if a is None:
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            setattr(st, n, a.ctypes.data_as(C.POINTER(C.c_double)))
+        st.decomposed = int(decomposed)
+        self._check(self.lib.fv3lm_turb_set_ltraj(self.h, int(slot), C.byref(st)), "turb_set_ltraj")
+
+    def turb_step_nl(self, slot):
+        self._check(self.lib.fv3lm_turb_step_nl(self.h, int(slot)), "turb_step_nl")
+
+    def turb_step_tl(self, slot, pert):
+        st, _k = self._fields(pert)
+        self._check(self.lib.fv3lm_turb_step_tl(self.h, int(slot), C.byref(st)), "turb_step_tl")
+
+    def turb_step_ad(self, slot, pert):
+        st, _k = self._fields(pert)
+        self._check(self.lib.fv3lm_turb_step_ad(self.h, int(slot), C.byref(st)), "turb_step_ad")
+
+    def turb_step_tl_dev(self, slot):
+        self._check(self.lib.fv3lm_turb_step_tl_dev(self.h, int(slot)), "turb_step_tl_dev")
+
+    def turb_step_ad_dev(self, slot):
+        self._check(self.lib.fv3lm_turb_step_ad_dev(self.h, int(slot)), "turb_step_ad_dev")
 
     def time_steps(self, slot, warmup, iters):
         ms = (C.c_double * 2)()

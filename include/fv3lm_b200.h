@@ -67,7 +67,11 @@ typedef struct fv3lm_config {
    * model and its smoothness-switch schemes 3..7 (model/tp_core_nlm.F90:327-578, model/sw_core_nlm.F90:2000-2306).             */
   int two_sided, split_damp;
   int hord_ks_pert, hord_ks_traj;   /* first-order transport in the top n_sponge - 1 layers (hord_*_ks_* = 1), per side        */
-  int reserved[2];
+  /* tracer sub-cycling.  q_split_dynamic = 0 (default): one tracer step per remap cycle (the reference's q_split = 1).
+   * q_split_dynamic = 1: the reference's q_split = 0 -- the number of sub-steps follows the accumulated Courant numbers of the
+   * trajectory, per level (model/fv_tracer2d_nlm.F90:351-420), up to q_split_max (0 = 3); a trajectory that needs more makes
+   * fv3lm_step_* return an error.                                                                                              */
+  int q_split_dynamic, q_split_max;
   struct {
     int hord_mt, hord_vt, hord_tm, hord_dp, hord_tr, nord, do_vort_damp, n_sponge;
     /* vertical remap of the trajectory (split_kord): |kord| 8 .. 14 = the limited profiles of the nonlinear model
@@ -117,6 +121,25 @@ int fv3lm_pert_upload(fv3lm_handle* h, const fv3lm_fields* pert);
 int fv3lm_pert_download(fv3lm_handle* h, fv3lm_fields* pert);
 int fv3lm_step_tl_dev(fv3lm_handle* h, int slot);
 int fv3lm_step_ad_dev(fv3lm_handle* h, int slot);
+/* ---- linearised boundary-layer turbulence: replaces step_nl / step_tl / step_ad of
+ * src/physics/turbulence/fv3jedi_lm_turbulence_mod.F90 (:149 / :218 / :285) and the device part of set_ltraj (:375-533).
+ * BL_DRIVER (bldriver.F90), which turns the trajectory into the three tridiagonal systems once per time level, stays with the
+ * caller; its output goes in here.  Arrays are compact (isc:iec, jsc:jec, npz) like fv3lm_fields.                             */
+typedef struct fv3lm_turb_coeffs {
+  const double *akv, *bkv, *ckv;   /* lower / main / upper diagonal for the winds                                   (:494-496) */
+  const double *aks, *bks, *cks;   /* ... for potential temperature                                                            */
+  const double *akq, *bkq, *ckq;   /* ... for specific humidity and the tracers qi, ql, o3                                     */
+  const double *pk;                /* p^kappa at mid levels (ltraj%pk); NULL: computed on the device from the delp of the
+                                      trajectory slot, fv3lm_config.ptop and .kappa (utils/fv3jedi_lm_utils_mod.F90:359-391)   */
+  int decomposed;                  /* 0: diagonals as BL_DRIVER returns them, VTRILUPERT (:562-579) runs on the device;
+                                      1: already LU-decomposed by the caller                                                   */
+} fv3lm_turb_coeffs;
+int fv3lm_turb_set_ltraj(fv3lm_handle* h, int slot, const fv3lm_turb_coeffs* coeffs);
+int fv3lm_turb_step_nl(fv3lm_handle* h, int slot);                                /* trajectory fields of the slot, in place */
+int fv3lm_turb_step_tl(fv3lm_handle* h, int slot, fv3lm_fields* pert);            /* pert in/out on the host; u v t qv qi ql o3 change */
+int fv3lm_turb_step_ad(fv3lm_handle* h, int slot, fv3lm_fields* pert);
+int fv3lm_turb_step_tl_dev(fv3lm_handle* h, int slot);                            /* on the device-resident increments */
+int fv3lm_turb_step_ad_dev(fv3lm_handle* h, int slot);
 /* bench helpers: CUDA-event timing of TL+AD steps on resident data; program statistics */
 int fv3lm_time_steps(fv3lm_handle* h, int slot, int warmup, int iters, double* ms_tl_ad);
 int fv3lm_program_stats(fv3lm_handle* h, const char* module, double* out4);
