@@ -306,13 +306,15 @@ int fv3lm_turb_step_ad(fv3lm_handle* h, int slot, fv3lm_fields* pert) {
   return rc;
 }
 
-// step_nl :149-213: the same solves applied to the trajectory fields of the slot, in place (coefficients of the same slot)
-int fv3lm_turb_step_nl(fv3lm_handle* h, int slot) {
+// step_nl :149-213: the same solves applied to the trajectory fields of slot_state, in place, with the local trajectory of
+// slot_ltraj (fv3jedi_lm_mod calls the physics after the dynamics: the state has moved on, src/fv3jedi_lm_mod.F90:153-156)
+int fv3lm_turb_step_nl(fv3lm_handle* h, int slot_ltraj, int slot_state) {
   FV3LM_TRY
   ensure_runner(h);
   StepRunner* r = h->step;
-  if (slot < 0 || (int)r->slots.size() <= slot || r->slots[slot].empty()) throw std::runtime_error("fv3lm_turb_step_nl: trajectory slot not set");
-  turb_apply(h, slot, r->slots[slot].data(), false);
+  if (slot_state < 0 || (int)r->slots.size() <= slot_state || r->slots[slot_state].empty())
+    throw std::runtime_error("fv3lm_turb_step_nl: trajectory slot not set");
+  turb_apply(h, slot_ltraj, r->slots[slot_state].data(), false);
   dev::sync();
   FV3LM_CATCH(h)
 }

@@ -150,6 +150,7 @@ subroutine create(self,conf)
  cfg%a_imp = A%flagstruct%a_imp; cfg%p_fac = A%flagstruct%p_fac; cfg%d_con = A%flagstruct%d_con
 
  call check(self, fv3lm_create(cfg, conf%ak, conf%bk, self%handle), 'create')
+ fv3lm_shared_handle = self%handle      ! the physics shims (fv3lm_b200_turbulence_mod) work on the same device state
 
  ! NCCL bootstrap: the root PE draws the id, FMS broadcasts it
  if (mpp_npes() > 1) then
@@ -348,6 +349,7 @@ subroutine delete(self,conf)
  integer(c_int) :: rc
  rc = fv3lm_destroy(self%handle)
  self%handle = c_null_ptr
+ fv3lm_shared_handle = c_null_ptr
  call deallocate_fv_atmos_type(self%FV_Atm(1))
  deallocate(self%FV_Atm)
  call deallocate_fv_atmos_pert_type(self%FV_AtmP(1))

@@ -39,6 +39,15 @@ type, bind(c) :: fv3lm_fields
   type(c_ptr) :: u, v, t, delp, qv, ql, qi, o3, w, delz
 end type fv3lm_fields
 
+!> mirror of `struct fv3lm_turb_coeffs`: the diagonals BL_DRIVER returns (+ optional pk), (isc:iec, jsc:jec, npz) REAL64
+type, bind(c) :: fv3lm_turb_coeffs
+  type(c_ptr) :: akv, bkv, ckv, aks, bks, cks, akq, bkq, ckq, pk
+  integer(c_int) :: decomposed
+end type fv3lm_turb_coeffs
+
+!> the handle created by fv3jedi_lm_dynamics_mod::create, shared with the physics shims (one handle per MPI rank / GPU)
+type(c_ptr), save :: fv3lm_shared_handle = c_null_ptr
+
 interface
 
   integer(c_int) function fv3lm_create(cfg, ak, bk, handle) bind(c, name='fv3lm_create')
@@ -143,6 +152,45 @@ interface
   end function
 
   integer(c_int) function fv3lm_step_ad_dev(handle, slot) bind(c, name='fv3lm_step_ad_dev')
+    import :: c_int, c_ptr
+    type(c_ptr), value :: handle
+    integer(c_int), value :: slot
+  end function
+
+  integer(c_int) function fv3lm_turb_set_ltraj(handle, slot, coeffs) bind(c, name='fv3lm_turb_set_ltraj')
+    import :: c_int, c_ptr, fv3lm_turb_coeffs
+    type(c_ptr), value :: handle
+    integer(c_int), value :: slot
+    type(fv3lm_turb_coeffs), intent(in) :: coeffs
+  end function
+
+  integer(c_int) function fv3lm_turb_step_nl(handle, slot_ltraj, slot_state) bind(c, name='fv3lm_turb_step_nl')
+    import :: c_int, c_ptr
+    type(c_ptr), value :: handle
+    integer(c_int), value :: slot_ltraj, slot_state
+  end function
+
+  integer(c_int) function fv3lm_turb_step_tl(handle, slot, pert) bind(c, name='fv3lm_turb_step_tl')
+    import :: c_int, c_ptr, fv3lm_fields
+    type(c_ptr), value :: handle
+    integer(c_int), value :: slot
+    type(fv3lm_fields), intent(in) :: pert
+  end function
+
+  integer(c_int) function fv3lm_turb_step_ad(handle, slot, pert) bind(c, name='fv3lm_turb_step_ad')
+    import :: c_int, c_ptr, fv3lm_fields
+    type(c_ptr), value :: handle
+    integer(c_int), value :: slot
+    type(fv3lm_fields), intent(in) :: pert
+  end function
+
+  integer(c_int) function fv3lm_turb_step_tl_dev(handle, slot) bind(c, name='fv3lm_turb_step_tl_dev')
+    import :: c_int, c_ptr
+    type(c_ptr), value :: handle
+    integer(c_int), value :: slot
+  end function
+
+  integer(c_int) function fv3lm_turb_step_ad_dev(handle, slot) bind(c, name='fv3lm_turb_step_ad_dev')
     import :: c_int, c_ptr
     type(c_ptr), value :: handle
     integer(c_int), value :: slot

@@ -319,8 +319,9 @@ class FV3LM:
         st.decomposed = int(decomposed)
         self._check(self.lib.fv3lm_turb_set_ltraj(self.h, int(slot), C.byref(st)), "turb_set_ltraj")
 
-    def turb_step_nl(self, slot):
-        self._check(self.lib.fv3lm_turb_step_nl(self.h, int(slot)), "turb_step_nl")
+    def turb_step_nl(self, slot_ltraj, slot_state=None):
+        slot_state = slot_ltraj if slot_state is None else slot_state
+        self._check(self.lib.fv3lm_turb_step_nl(self.h, int(slot_ltraj), int(slot_state)), "turb_step_nl")
 
     def turb_step_tl(self, slot, pert):
         st, _k = self._fields(pert)

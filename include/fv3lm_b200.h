@@ -135,7 +135,7 @@ typedef struct fv3lm_turb_coeffs {
                                       1: already LU-decomposed by the caller                                                   */
 } fv3lm_turb_coeffs;
 int fv3lm_turb_set_ltraj(fv3lm_handle* h, int slot, const fv3lm_turb_coeffs* coeffs);
-int fv3lm_turb_step_nl(fv3lm_handle* h, int slot);                                /* trajectory fields of the slot, in place */
+int fv3lm_turb_step_nl(fv3lm_handle* h, int slot_ltraj, int slot_state);          /* trajectory fields of slot_state, in place */
 int fv3lm_turb_step_tl(fv3lm_handle* h, int slot, fv3lm_fields* pert);            /* pert in/out on the host; u v t qv qi ql o3 change */
 int fv3lm_turb_step_ad(fv3lm_handle* h, int slot, fv3lm_fields* pert);
 int fv3lm_turb_step_tl_dev(fv3lm_handle* h, int slot);                            /* on the device-resident increments */

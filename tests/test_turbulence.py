@@ -125,12 +125,14 @@ def _run(emu, **kw):
     rhs = sum((dx[n] * b[n]).sum() for n in FLD)
     res["dot"] = abs(lhs - rhs) / max(abs(lhs), abs(rhs))
     assert res["dot"] < 1e-13, res
-    # NL: the same solves on the trajectory of the slot, in place
-    h.turb_step_nl(0)
+    # NL: the same solves on the trajectory fields of another slot (the state after the dynamics step), in place
+    tr2 = {k: (v if k == "delp" else 1.7 * v) for k, v in traj.items()}
+    h.traj_set(2, up(h, tr2))
+    h.turb_step_nl(0, 2)
     out = {n: np.zeros_like(v) for n, v in up(h, traj).items()}
-    h.traj_get(0, out)
+    h.traj_get(2, out)
     out = down(h, out, shape)
-    ref = otb.step(lt, traj, KAPPA, 1)
+    ref = otb.step(lt, tr2, KAPPA, 1)
     for n in FLD:
         res["nl." + n] = err(out[n], ref[n]); assert res["nl." + n] < 1e-12, ("nl", n, res)
     # coefficients decomposed by the caller + pk given: same result
