@@ -106,6 +106,8 @@ def run_gpu(args):
                   traj=dict(hord_mt=9, hord_vt=9, hord_tm=9, hord_dp=9, hord_tr=12, kord_mt=8, kord_wz=8, kord_tm=8, kord_tr=8,
                             nord=1, do_vort_damp=0, n_sponge=1,
                             dddmp=0.0, d2_bg=0.0, d4_bg=0.16, vtdm4=0.0, d2_bg_k1=0.20, d2_bg_k2=0.10))
+    if args.q_split_dynamic:
+        mc.update(q_split_dynamic=1, q_split_max=args.q_split_dynamic)   # the reference's q_split = 0 with that many issued sub-steps
     cfg = fv3lm.default_config(N, K, rank=rank, nranks=world, layout_x=args.layout[0], layout_y=args.layout[1], **mc)
     h = fv3lm.FV3LM(cfg, ak, bk)
     if world > 1:
@@ -144,8 +146,29 @@ def run_gpu(args):
     ck.stop = True; ck.join()
     ms_step = ms_tl + ms_ad
     if args.kernel_only:
+        side = {}
+        if args.turbulence:
+            # side measurement (not the bench metric): the seven tridiagonal solves of the linearised turbulence on the resident
+            # increments; synthetic diagonally dominant systems, decomposition and p^kappa on the device
+            rng = np.random.default_rng(7)
+            shp = st[fields[0]].shape
+            co = {}
+            for s_ in "vsq":
+                al = 0.05 + 2.0 * rng.random(shp)
+                a_ = -al.copy(); a_[:, 0] = 0.0
+                c_ = np.zeros(shp); c_[:, :-1] = -al[:, 1:]
+                co["ak" + s_] = a_; co["ck" + s_] = c_; co["bk" + s_] = 1.0 - a_ - c_ + 0.1 * rng.random(shp)
+            h.turb_set_ltraj(0, co)
+            del co
+            tb_tl, tb_ad = h.time_turb(0, args.warmup, args.steps)
+            cells = float(np.prod(shp)) * world
+            side = {"turb_tl_ms": tb_tl, "turb_ad_ms": tb_ad, "turb_alg_gb": 24 * 8 * cells / 1e9,
+                    "turb_tl_alg_gbs": 24 * 8 * cells / 1e9 / (tb_tl * 1e-3)}
         if rank == 0:
-            print(json.dumps({"kernel_only": True, "two_sided": bool(args.two_sided), "res": N, "tl_ms": ms_tl, "ad_ms": ms_ad, "gpu_launches": int(launches)}))
+            out = {"kernel_only": True, "two_sided": bool(args.two_sided), "q_split_dynamic": int(args.q_split_dynamic), "res": N,
+                   "tl_ms": ms_tl, "ad_ms": ms_ad, "gpu_launches": int(launches)}
+            out.update(side)
+            print(json.dumps(out))
         return
     # ---- end to end through the host-pointer ABI: trajectory + increments cross PCIe every step
     hp = {k: pinned(st[k].shape) for k in fields}
@@ -314,6 +337,9 @@ def main():
     ap.add_argument("--layout", type=int, nargs=2, default=[0, 0], help="force the tile layout (default: chosen from the number of ranks)")
     ap.add_argument("--profile-out", default=None, help="write the full per-op profile table to this file")
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: only the device-resident timed loop (used under ncu)")
+    ap.add_argument("--q-split-dynamic", type=int, default=0, metavar="NMAX",
+                    help="side measurement: tracer sub-steps from the Courant numbers (q_split = 0) with NMAX issued sub-steps")
+    ap.add_argument("--turbulence", action="store_true", help="side measurement with --kernel-only: time the linearised turbulence solves")
     ap.add_argument("--two-sided", action="store_true",
                     help="side measurement (not the headline): the reference's default split configuration -- monotone hord 9 / 12 trajectory, "
                          "linear hord 2 perturbation with its own damping and a 9-layer first-order sponge (fv_arrays_tlmadm.F90:37-92)")

@@ -350,6 +350,36 @@ int fv3lm_time_steps(fv3lm_handle* h, int slot, int warmup, int iters, double* m
   FV3LM_CATCH(h)
 }
 
+// The same for the turbulence solves: ms[0] = TL ms/call, ms[1] = AD ms/call on the device-resident increments.
+int fv3lm_time_turb(fv3lm_handle* h, int slot, int warmup, int iters, double* ms) {
+  FV3LM_TRY
+  ensure_runner(h);
+#ifndef FV3LM_HOST_EMU
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  for (int n = 0; n < warmup; n++) { turb_apply(h, slot, h->step->pert, false); turb_apply(h, slot, h->step->pert, true); }
+  dev::sync();
+  double tl = 0.0, ad = 0.0;
+  for (int n = 0; n < iters; n++) {
+    cudaEventRecord(e0, dev::stream());
+    turb_apply(h, slot, h->step->pert, false);
+    cudaEventRecord(e1, dev::stream());
+    turb_apply(h, slot, h->step->pert, true);
+    cudaEventRecord(e2, dev::stream());
+    cudaEventSynchronize(e2);
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2);
+    tl += a; ad += b;
+  }
+  ms[0] = tl / iters; ms[1] = ad / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+#else
+  (void)slot; (void)warmup; (void)iters; ms[0] = ms[1] = 0.0;
+  throw std::runtime_error("fv3lm_time_turb: host emulation build has no timer");
+#endif
+  FV3LM_CATCH(h)
+}
+
 // Profiling pass: per-op CUDA-event times of `iters` TL+AD steps (serialised; not a bench number).
 // Writes lines "name launches total_ms alg_bytes" into buf.
 int fv3lm_profile_steps(fv3lm_handle* h, int slot, int iters, char* buf, int buflen) {

@@ -50,7 +50,7 @@ EXPORTS = ["fv3lm_decomp_info", "fv3lm_nccl_unique_id", "fv3lm_comm_init_nccl", 
            "fv3lm_program_stats", "fv3lm_create", "fv3lm_destroy", "fv3lm_last_error", "fv3lm_set_metric", "fv3lm_set_metric_scalar",
            "fv3lm_module_run", "fv3lm_module_list", "fv3lm_launch_count", "fv3lm_pool_peak_bytes", "fv3lm_sync",
            "fv3lm_turb_set_ltraj", "fv3lm_turb_step_nl", "fv3lm_turb_step_tl", "fv3lm_turb_step_ad", "fv3lm_turb_step_tl_dev",
-           "fv3lm_turb_step_ad_dev"]
+           "fv3lm_turb_step_ad_dev", "fv3lm_time_turb"]
 
 TURB_ARRAYS = ["akv", "bkv", "ckv", "aks", "bks", "cks", "akq", "bkq", "ckq", "pk"]
 
@@ -336,6 +336,11 @@ class FV3LM:
 
     def turb_step_ad_dev(self, slot):
         self._check(self.lib.fv3lm_turb_step_ad_dev(self.h, int(slot)), "turb_step_ad_dev")
+
+    def time_turb(self, slot, warmup, iters):
+        ms = (C.c_double * 2)()
+        self._check(self.lib.fv3lm_time_turb(self.h, int(slot), int(warmup), int(iters), ms), "time_turb")
+        return float(ms[0]), float(ms[1])
 
     def time_steps(self, slot, warmup, iters):
         ms = (C.c_double * 2)()

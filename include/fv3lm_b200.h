@@ -142,6 +142,7 @@ int fv3lm_turb_step_tl_dev(fv3lm_handle* h, int slot);                          
 int fv3lm_turb_step_ad_dev(fv3lm_handle* h, int slot);
 /* bench helpers: CUDA-event timing of TL+AD steps on resident data; program statistics */
 int fv3lm_time_steps(fv3lm_handle* h, int slot, int warmup, int iters, double* ms_tl_ad);
+int fv3lm_time_turb(fv3lm_handle* h, int slot, int warmup, int iters, double* ms_tl_ad);   /* turbulence solves, same convention */
 int fv3lm_program_stats(fv3lm_handle* h, const char* module, double* out4);
 int fv3lm_profile_steps(fv3lm_handle* h, int slot, int iters, char* buf, int buflen);   /* per-op event times, text */
 

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Round 2, first GPU call (prepared at the end of round 1, when the GPU minutes were spent):
+#   1. the whole -m gpu suite (includes the q_split = 0 and turbulence tests added last);
+#   2. default bench line;
+#   3. side measurements that have never been timed: tracer sub-cycling (q_split = 0, 3 issued sub-steps) and the
+#      linearised turbulence solves (24 array passes of algorithmic traffic);
+#   4. ncu --set full of the turbulence solve kernel (only after its command exited 0 without ncu).
+# usage: gpurun --timeout 1500 -- 'bash tools/gpu_jobs_r02/job1_first_call.sh'
+mkdir -p gpurun_out
+T=r02a
+( time python -m pytest tests -m gpu -q -p no:cacheprovider ) > gpurun_out/${T}_pytest_gpu.txt 2>&1; tail -3 gpurun_out/${T}_pytest_gpu.txt
+python bench.py > gpurun_out/${T}_bench_default_1gpu.json 2> gpurun_out/${T}_bench.err; tail -c 300 gpurun_out/${T}_bench.err
+python bench.py --kernel-only --turbulence --steps 5 --warmup 3 > gpurun_out/${T}_side_turbulence.json 2> gpurun_out/${T}_side_turb.err
+rc=$?; cat gpurun_out/${T}_side_turbulence.json
+python bench.py --kernel-only --q-split-dynamic 3 --steps 3 --warmup 3 > gpurun_out/${T}_side_qsplit0.json 2> gpurun_out/${T}_side_q.err
+cat gpurun_out/${T}_side_qsplit0.json
+if [ $rc -eq 0 ]; then
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:KTurbSolve -c 2 \
+      -o gpurun_out/${T}_KTurbSolve_c180 python bench.py --kernel-only --turbulence --steps 1 --warmup 1 > gpurun_out/${T}_ncu_turb.log 2>&1
+  ls -la gpurun_out/${T}_KTurbSolve_c180.ncu-rep
+fi
