@@ -97,6 +97,11 @@ int fv3lm_destroy(fv3lm_handle* h) {
     dev::free_(r->phis);
     for (auto& s : r->slots) for (double* p : s) dev::free_(p);
     for (auto& lt : r->turb) for (double* p : lt.d) dev::free_(p);
+    if (r->c2l) {
+      for (const char* n : {"a11", "a12", "a21", "a22", "ua", "va"}) dev::free_(r->c2l->P.vals[r->c2l->id[n]].traj);
+      dev::free_(r->c2l->ua); dev::free_(r->c2l->va);
+      delete r->c2l;
+    }
 #ifndef FV3LM_HOST_EMU
     for (auto& sg : r->graph) if (sg.exec) cudaGraphExecDestroy((cudaGraphExec_t)sg.exec);
 #endif

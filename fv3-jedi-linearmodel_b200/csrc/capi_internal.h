@@ -19,6 +19,14 @@ struct StepGraph {
   long long exchanges = 0; double bytes_sent = 0.0;
 };
 
+// cubed_to_latlon after step_nl (traj%ua, traj%va): a two-op program on the u / v output arrays of the step program
+struct C2lRunner {
+  fv3lm::Program P;
+  fv3lm::ModuleIO io;
+  std::map<std::string, int> id;
+  double* ua = nullptr; double* va = nullptr;     // compact results of the last step_nl
+};
+
 struct StepRunner {
   StepGraph graph[3];
   fv3lm::Program P;
@@ -29,6 +37,7 @@ struct StepRunner {
   double* phis = nullptr;
   std::vector<std::vector<double*>> slots;        // device-resident trajectory window (compact)
   std::vector<fv3lm::TurbLtraj> turb;             // local trajectory of the turbulence scheme, per window slot
+  C2lRunner* c2l = nullptr;                       // set by fv3lm_set_c2l
 };
 
 struct fv3lm_handle {

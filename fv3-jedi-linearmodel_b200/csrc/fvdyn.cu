@@ -6,6 +6,7 @@
 #include "nh.h"
 #include "modules.h"
 #include "comm.h"
+#include "stages_c2l.h"
 #include <memory>
 
 namespace fv3lm {
@@ -511,6 +512,16 @@ void mod_remap(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {
   RemapOut r = build_remap(P, mo, c, *prm.ak, *prm.bk, pe, pk, peln, pt, {q0}, u, v, prm.geti("last_step", 1) != 0, "rm", -1, -1, -1, -1);
   io.out(P, "pt_n", r.pt); io.out(P, "q0_n", r.q[0]); io.out(P, "u_n", r.u); io.out(P, "v_n", r.v); io.out(P, "delp_n", r.delp);
   io.out(P, "pkz_n", r.pkz); io.out(P, "pe_n", r.pe);
+}
+
+void mod_c2l_ord4(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams&) {
+  const int K = P.dv->g.K;
+  int u = io.in(P, "u", K), v = io.in(P, "v", K);
+  int a11 = io.in(P, "a11", 1), a12 = io.in(P, "a12", 1), a21 = io.in(P, "a21", 1), a22 = io.in(P, "a22", 1);
+  add_patch(P, "halo_dgrid", &mo.h_dgrid, {u, v});            // cubed_to_latlon(..., mode = 1): mpp_update_domains(u, v, DGRID_NE)
+  int ua = P.val("ua", K), va = P.val("va", K);
+  P.add<S_c2l>("c2l_ord4", {0}, {u, v, a11, a12, a21, a22}, {ua, va}, K);
+  io.out(P, "ua", ua); io.out(P, "va", va);
 }
 
 void mod_tracer_2d(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {

@@ -77,6 +77,7 @@ void mod_dyn_core(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm)
 void mod_remap(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_step(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_tracer_2d(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
+void mod_c2l_ord4(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_riem(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_update_dz_c(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_update_dz_d(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
@@ -94,6 +95,7 @@ static const ModEntry g_mods[] = {
     {"remap", mod_remap, "in: pe pk peln pt q0 u v; out: pt_n q0_n u_n v_n delp_n pkz_n pe_n; params: last_step"},
     {"step", mod_step, "in: u v t delp qv ql qi o3 w phis; out: u_n v_n t_n delp_n qv_n ql_n qi_n o3_n (one fv3jedi_lm dynamics step)"},
     {"tracer_2d", mod_tracer_2d, "in: q0 q1 dp1 mfx mfy cx cy; out: q0_n q1_n; params: hord_tr q_split (0 = sub-steps from the Courant numbers) q_split_max"},
+    {"c2l_ord4", mod_c2l_ord4, "in: u v a11 a12 a21 a22; out: ua va (cubed_to_latlon, c2l_ord = 4, mode = 1)"},
     {"riem", mod_riem, "in: delp pt z w ws zb; out: pp z_n [w_n dz_n]; params: mode (0 = Riem_Solver_c, 1 = Riem_Solver3) dts"},
     {"update_dz_c", mod_update_dz_c, "in: ut vt gz zs; out: gz_n ws; params: dts"},
     {"update_dz_d", mod_update_dz_d, "in: zh zs crx cry xfx yfx; out: zh_n ws; params: dts"},

@@ -188,7 +188,66 @@ int fv3lm_step_nl(fv3lm_handle* h, int slot_in, int slot_out) {
   run_step(h, slot_in, MODE_NL);
   StepRunner* r = h->step;
   for (int f = 0; f < r->nf; f++) compact(h, slot_field(h, slot_out, f), r->P.vals[r->out_id[std::string(kFieldNames[f]) + "_n"]].traj, h->dv.g.K);
+  if (r->c2l) {
+    // cubed_to_latlon at the end of fv_dynamics (model/fv_dynamics_nlm.F90:738): the program reads the step's u / v output arrays in
+    // place (rows je + 1 / columns ie + 1 are part of them; its halo update only touches their halo)
+    C2lRunner* c = r->c2l;
+    c->P.vals[c->id["u"]].traj = r->P.vals[r->out_id["u_n"]].traj;
+    c->P.vals[c->id["v"]].traj = r->P.vals[r->out_id["v_n"]].traj;
+    for (auto& kv : c->io.inputs) c->P.vals[kv.second].active = false;
+    c->P.run(MODE_NL);
+    compact(h, c->ua, c->P.vals[c->id["ua"]].traj, h->dv.g.K);
+    compact(h, c->va, c->P.vals[c->id["va"]].traj, h->dv.g.K);
+  }
   dev::sync();
+  FV3LM_CATCH(h)
+}
+
+// gridstruct%a11 .. a22 (init_cubed_to_latlon, model/fv_grid_utils_nlm.F90:2248-2310), compact (isc:iec, jsc:jec).  Once set, every
+// fv3lm_step_nl also produces the A-grid lon / lat winds of its result (fv3jedi_lm_dynamics_mod.F90:839-840: traj%ua, traj%va).
+int fv3lm_set_c2l(fv3lm_handle* h, const double* a11, const double* a12, const double* a21, const double* a22) {
+  FV3LM_TRY
+  ensure_runner(h);
+  StepRunner* r = h->step; const Geom& g = h->dv.g;
+  if (!a11 || !a12 || !a21 || !a22) throw std::runtime_error("fv3lm_set_c2l: null array");
+  if (!r->c2l) {
+    auto* c = new C2lRunner();
+    c->P.dv = &h->dv; c->P.name = "c2l";
+    ModuleParams prm; prm.cfg = &h->cfg; prm.ak = &h->ak; prm.bk = &h->bk;
+    build_module("c2l_ord4", c->P, h->mo, c->io, prm);
+    for (auto& kv : c->io.inputs) c->id[kv.first] = kv.second;
+    for (auto& kv : c->io.outputs) c->id[kv.first] = kv.second;
+    for (const char* n : {"a11", "a12", "a21", "a22", "ua", "va"}) {
+      const int id = c->id[n];
+      c->P.vals[id].traj = (double*)dev::alloc(c->P.val_doubles(id) * sizeof(double));
+      dev::zero(c->P.vals[id].traj, c->P.val_doubles(id) * sizeof(double));
+    }
+    c->ua = (double*)dev::alloc(compact_doubles(g, g.K) * sizeof(double));
+    c->va = (double*)dev::alloc(compact_doubles(g, g.K) * sizeof(double));
+    dev::zero(c->ua, compact_doubles(g, g.K) * sizeof(double));
+    dev::zero(c->va, compact_doubles(g, g.K) * sizeof(double));
+    r->c2l = c;
+  }
+  double* tmp = (double*)dev::alloc(compact_doubles(g, 1) * sizeof(double));
+  const double* src[4] = {a11, a12, a21, a22};
+  static const char* nm[4] = {"a11", "a12", "a21", "a22"};
+  for (int n = 0; n < 4; n++) {
+    dev::h2d(tmp, src[n], compact_doubles(g, 1) * sizeof(double));
+    expand(h, tmp, r->c2l->P.vals[r->c2l->id[nm[n]]].traj, 1);
+  }
+  dev::sync();
+  dev::free_(tmp);
+  FV3LM_CATCH(h)
+}
+
+// ua, va of the last fv3lm_step_nl (compact, like the fields)
+int fv3lm_traj_get_winds(fv3lm_handle* h, double* ua, double* va) {
+  FV3LM_TRY
+  ensure_runner(h);
+  StepRunner* r = h->step; const Geom& g = h->dv.g;
+  if (!r->c2l) throw std::runtime_error("fv3lm_traj_get_winds: fv3lm_set_c2l was not called");
+  if (ua) dev::d2h(ua, r->c2l->ua, compact_doubles(g, g.K) * sizeof(double));
+  if (va) dev::d2h(va, r->c2l->va, compact_doubles(g, g.K) * sizeof(double));
   FV3LM_CATCH(h)
 }
 

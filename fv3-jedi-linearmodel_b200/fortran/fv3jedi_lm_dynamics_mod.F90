@@ -230,7 +230,16 @@ subroutine upload_metrics(self)
  call up1d(self, 'edge_vect_s', A%gridstruct%edge_vect_s); call up1d(self, 'edge_vect_n', A%gridstruct%edge_vect_n)
  call check(self, fv3lm_set_metric_scalar(self%handle, 'da_min'//c_null_char, real(A%gridstruct%da_min, c_double)), 'da_min')
  call check(self, fv3lm_set_metric_scalar(self%handle, 'da_min_c'//c_null_char, real(A%gridstruct%da_min_c, c_double)), 'da_min_c')
+ ! cubed_to_latlon coefficients (init_cubed_to_latlon): from now on step_nl also returns the A-grid winds
+ call up_c2l(self, A%gridstruct%a11(self%isc:self%iec, self%jsc:self%jec), A%gridstruct%a12(self%isc:self%iec, self%jsc:self%jec), &
+                   A%gridstruct%a21(self%isc:self%iec, self%jsc:self%jec), A%gridstruct%a22(self%isc:self%iec, self%jsc:self%jec))
 end subroutine upload_metrics
+
+subroutine up_c2l(self, a11, a12, a21, a22)
+ class(fv3jedi_lm_dynamics_type), intent(inout) :: self
+ real(kind_real), intent(in) :: a11(:,:), a12(:,:), a21(:,:), a22(:,:)      ! contiguous copies of the compute-domain sections
+ call check(self, fv3lm_set_c2l(self%handle, a11, a12, a21, a22), 'set_c2l')
+end subroutine up_c2l
 
 subroutine up1d(self, name, arr)
  class(fv3jedi_lm_dynamics_type), intent(inout) :: self
@@ -319,6 +328,7 @@ subroutine step_nl(self,conf,traj)
  call send_traj(self, conf, traj)
  call check(self, fv3lm_step_nl(self%handle, int(conf%n, c_int), int(conf%n+1, c_int)), 'step_nl')
  call check(self, fv3lm_traj_get(self%handle, int(conf%n+1, c_int), traj_fields(traj, conf%hydrostatic)), 'traj_get')
+ call check(self, fv3lm_traj_get_winds(self%handle, traj%ua, traj%va), 'traj_get_winds')      ! reference fv3_to_traj :839-840
 endsubroutine step_nl
 
 subroutine step_tl(self,conf,traj,pert)

@@ -157,6 +157,18 @@ interface
     integer(c_int), value :: slot
   end function
 
+  integer(c_int) function fv3lm_set_c2l(handle, a11, a12, a21, a22) bind(c, name='fv3lm_set_c2l')
+    import :: c_int, c_double, c_ptr
+    type(c_ptr), value :: handle
+    real(c_double), intent(in) :: a11(*), a12(*), a21(*), a22(*)
+  end function
+
+  integer(c_int) function fv3lm_traj_get_winds(handle, ua, va) bind(c, name='fv3lm_traj_get_winds')
+    import :: c_int, c_double, c_ptr
+    type(c_ptr), value :: handle
+    real(c_double), intent(out) :: ua(*), va(*)
+  end function
+
   integer(c_int) function fv3lm_turb_set_ltraj(handle, slot, coeffs) bind(c, name='fv3lm_turb_set_ltraj')
     import :: c_int, c_ptr, fv3lm_turb_coeffs
     type(c_ptr), value :: handle

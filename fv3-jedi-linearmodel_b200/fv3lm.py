@@ -50,7 +50,7 @@ EXPORTS = ["fv3lm_decomp_info", "fv3lm_nccl_unique_id", "fv3lm_comm_init_nccl", 
            "fv3lm_program_stats", "fv3lm_create", "fv3lm_destroy", "fv3lm_last_error", "fv3lm_set_metric", "fv3lm_set_metric_scalar",
            "fv3lm_module_run", "fv3lm_module_list", "fv3lm_launch_count", "fv3lm_pool_peak_bytes", "fv3lm_sync",
            "fv3lm_turb_set_ltraj", "fv3lm_turb_step_nl", "fv3lm_turb_step_tl", "fv3lm_turb_step_ad", "fv3lm_turb_step_tl_dev",
-           "fv3lm_turb_step_ad_dev", "fv3lm_time_turb"]
+           "fv3lm_turb_step_ad_dev", "fv3lm_time_turb", "fv3lm_set_c2l", "fv3lm_traj_get_winds"]
 
 TURB_ARRAYS = ["akv", "bkv", "ckv", "aks", "bks", "cks", "akq", "bkq", "ckq", "pk"]
 
@@ -281,6 +281,17 @@ class FV3LM:
 
     def step_nl(self, slot_in, slot_out):
         self._check(self.lib.fv3lm_step_nl(self.h, int(slot_in), int(slot_out)), "step_nl")
+
+    def set_c2l(self, a11, a12, a21, a22):
+        """gridstruct%a11 .. a22 on the compute domain of this handle's sub-domains ([nsub, nyl, nxl])"""
+        dp = C.POINTER(C.c_double)
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (a11, a12, a21, a22)]
+        self._check(self.lib.fv3lm_set_c2l(self.h, *[a.ctypes.data_as(dp) for a in arrs]), "set_c2l")
+
+    def traj_get_winds(self, ua, va):
+        dp = C.POINTER(C.c_double)
+        assert ua.dtype == np.float64 and va.dtype == np.float64 and ua.flags["C_CONTIGUOUS"] and va.flags["C_CONTIGUOUS"]
+        self._check(self.lib.fv3lm_traj_get_winds(self.h, ua.ctypes.data_as(dp), va.ctypes.data_as(dp)), "traj_get_winds")
 
     def step_tl(self, slot, pert):
         st, _k = self._fields(pert)

@@ -524,6 +524,17 @@ def build_metrics(N, radius=RADIUS, omega=OMEGA, shift_fac=18.0):
         arr[:, npx + o] = arr[:, N + o]
     M.update(edge_vect_w=ev_w, edge_vect_e=ev_e, edge_vect_s=ev_s, edge_vect_n=ev_n)
 
+    # ---- init_cubed_to_latlon (model/fv_grid_utils_nlm.F90:2248-2310): local cell-centre winds -> lon / lat components
+    lon_c, lat_c = agrid[:, :-1, :-1, 0], agrid[:, :-1, :-1, 1]
+    vlon = np.stack([-np.sin(lon_c), np.cos(lon_c), np.zeros_like(lon_c)], axis=-1)                       # unit_vect_latlon :2213
+    vlat = np.stack([-np.sin(lat_c) * np.cos(lon_c), -np.sin(lat_c) * np.sin(lon_c), np.cos(lat_c)], axis=-1)
+    z11 = (ec1 * vlon).sum(-1); z12 = (ec1 * vlat).sum(-1); z21 = (ec2 * vlon).sum(-1); z22 = (ec2 * vlat).sum(-1)
+    s5 = sin_sg[:, :-1, :-1, 5]
+    for nm, z, sgn in (("a11", z22, 0.5), ("a12", z12, -0.5), ("a21", z21, -0.5), ("a22", z11, 0.5)):
+        a = np.zeros((6, NXP, NXP))
+        a[:, :-1, :-1] = np.where(s5 > 1e-10, sgn * z / np.maximum(s5, 1e-10), 0.0)       # (ghost corners hold sin = tiny: unused)
+        M[nm] = a
+
     # ---- Coriolis (fv3jedi_lm_dynamics_mod.F90:126-139, f_coriolis_angle = 0)
     M["fC"] = 2.0 * omega * np.sin(grid[..., 1])
     M["f0"] = 2.0 * omega * np.sin(agrid[..., 1])

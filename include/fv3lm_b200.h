@@ -114,6 +114,12 @@ int fv3lm_set_phis(fv3lm_handle* h, const double* phis);                       /
 int fv3lm_traj_set(fv3lm_handle* h, int slot, const fv3lm_fields* traj);       /* host -> window slot */
 int fv3lm_traj_get(fv3lm_handle* h, int slot, fv3lm_fields* traj);
 int fv3lm_step_nl(fv3lm_handle* h, int slot_in, int slot_out);                 /* slot_out = N(slot_in), on device */
+/* A-grid lon / lat winds of the propagated trajectory: cubed_to_latlon with c2l_ord = 4 at the end of fv_dynamics
+ * (model/fv_dynamics_nlm.F90:738, model/fv_grid_utils_nlm.F90:2334-2472), returned by the reference's step_nl in traj%ua, traj%va
+ * (src/dynamics/fv3jedi_lm_dynamics_mod.F90:839-840).  fv3lm_set_c2l takes gridstruct%a11 .. a22 (compact 2-D); from then on every
+ * fv3lm_step_nl also computes them, fv3lm_traj_get_winds copies those of the last step to the host.                            */
+int fv3lm_set_c2l(fv3lm_handle* h, const double* a11, const double* a12, const double* a21, const double* a22);
+int fv3lm_traj_get_winds(fv3lm_handle* h, double* ua, double* va);
 int fv3lm_step_tl(fv3lm_handle* h, int slot, fv3lm_fields* pert);              /* pert in/out on the host */
 int fv3lm_step_ad(fv3lm_handle* h, int slot, fv3lm_fields* pert);              /* adjoint variables in/out */
 /* device-resident increments: a whole window without PCIe round trips */

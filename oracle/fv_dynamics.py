@@ -145,10 +145,10 @@ def fv_dynamics(st, g, ak, bk, cfg):
     return out
 
 
-def step_nl(x, g, ak, bk, cfg, phis):
+def step_nl(x, g, ak, bk, cfg, phis, winds=False):
     """fv3jedi_lm dynamics step (fv3jedi_lm_dynamics_mod.F90:268-345): x = dict of compute-domain
     prognostics u v t delp qv ql qi o3 [w delz] stored in full-size arrays (halo ignored).
-    Returns the same dict after one model step."""
+    Returns the same dict after one model step (winds: + the A-grid lon / lat winds ua, va, :839-840)."""
     N = g.N
     halo, getb = halo_of(N)
     hydro = cfg["hydrostatic"]
@@ -170,4 +170,8 @@ def step_nl(x, g, ak, bk, cfg, phis):
         out[n] = dom(qq)
     if not hydro:
         out["w"] = dom(o["w"]); out["delz"] = dom(o["delz"])
+    if winds:       # cubed_to_latlon(..., mode = 1, c2l_ord = 4) at the end of fv_dynamics (fv_dynamics_nlm.F90:738) -> traj%ua, va
+        from .c2l import c2l_ord4
+        uh, vh = halo.dgrid(o["u"], o["v"])
+        out["ua"], out["va"] = c2l_ord4(uh, vh, g)
     return out

@@ -3,7 +3,7 @@ layout(lx, ly) sub-domains (24 sub-domains batched on one rank) must agree for N
 inter-rank transport itself is covered by tests/test_multirank.py (world_size 2, gloo)."""
 import pytest
 import common
-import test_tp_core, test_c_sw, test_d_sw, test_dyn_core, test_fv_dynamics, test_nh, test_tracer_2d
+import test_tp_core, test_c_sw, test_d_sw, test_dyn_core, test_fv_dynamics, test_nh, test_tracer_2d, test_c2l
 
 CASES = {
     "fv_tp_2d": lambda emu: test_tp_core._run(emu, 2),
@@ -24,6 +24,7 @@ CASES = {
     "dyn_core_heat": lambda emu: test_dyn_core._run(emu, 2, K=5, extra=dict(d_con=1.0)),
     "del2_cubed": lambda emu: test_dyn_core._run_del2_cubed(emu, 3),
     # q_split = 0: level maxima of the Courant numbers over 24 sub-domains, masked sub-steps with a halo update of q in between
+    "c2l_ord4": lambda emu: test_c2l._run(emu),
     "tracer_2d_sub_steps": lambda emu: test_tracer_2d._run(emu, K=6, expect_nsplt=None),
 }
 
