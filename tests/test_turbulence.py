@@ -85,6 +85,16 @@ def make(emu, N=12, K=6, seed=3, **kw):
     return h, rng, shape, co, traj, lt
 
 
+def golden_inputs(N=12, K=3, seed=9):
+    """seeded inputs of the committed fixture tests/golden/physics_c12.npz (tools/make_golden.py)"""
+    rng = np.random.default_rng(seed)
+    shape = (6, K, N, N)
+    co = coeffs(rng, shape)
+    traj = state(rng, shape)
+    traj["delp"] = delp_of(rng, shape, CFG["ptop"])
+    return shape, co, traj, state(rng, shape), state(rng, shape)
+
+
 def up(h, d):
     """whole-cube compute-domain arrays -> this handle's sub-domains (contiguous)"""
     return {k: h.scatter_c(v).copy() for k, v in d.items()}

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Regenerates tests/golden/*.npz: outputs of the ORACLE (torch fp64 restatement) for one C12 fv3jedi_lm dynamics
 step, hydrostatic, non-hydrostatic and non-hydrostatic in two-sided mode (both flag structures at the reference's defaults): NL result, TL result (jvp) for a seeded increment and AD result (vjp) for a
-seeded adjoint vector.  The reference itself cannot be run here (no Fortran/FMS/MPI), so these fixtures pin the
+seeded adjoint vector; physics_c12.npz: turbulence TL / AD, cubed_to_latlon, tracer_2d with q_split = 0.  The reference itself cannot be run here (no Fortran/FMS/MPI), so these fixtures pin the
 oracle against silent regressions between rounds -- they are NOT reference outputs (parity unpinned).
   python tools/make_golden.py
 """
@@ -40,9 +40,46 @@ def case(nonhydro, two_sided=False):
     return out
 
 
+def case_physics():
+    """the pieces added around the dynamics step: linearised turbulence (TL, AD), cubed_to_latlon, tracer_2d with q_split = 0"""
+    import test_turbulence as tt
+    import test_tracer_2d as ttr
+    from test_dyn_core import CFG
+    from oracle import turbulence as otb, c2l as oc, fv_dynamics as ofv
+    from oracle.dyn_core import halo_of
+    from common import ograd, rnd
+    out = {}
+    shape, co, traj, dx, y = tt.golden_inputs()
+    lt = otb.set_ltraj(co, traj["delp"], CFG["ptop"], tt.KAPPA)
+    tl = otb.step(lt, dx, tt.KAPPA, 1); ad = otb.step(lt, y, tt.KAPPA, 2)
+    for n in tt.FLD:
+        out["turb.tl." + n] = tl[n]; out["turb.ad." + n] = ad[n]
+    N, K = 12, 2
+    halo, _ = halo_of(N)
+    rng = np.random.default_rng(5)
+    u, v = 10.0 * rnd(rng, N, K), 10.0 * rnd(rng, N, K)
+    uh, vh = halo.dgrid(torch.from_numpy(u), torch.from_numpy(v))
+    ua, va = oc.c2l_ord4(uh, vh, ograd(N))
+    o = 2
+    out["c2l.ua"] = ua.numpy()[:, :, o + 1:o + 1 + N, o + 1:o + 1 + N]; out["c2l.va"] = va.numpy()[:, :, o + 1:o + 1 + N, o + 1:o + 1 + N]
+    f, _ = ttr.fields(N, 6, ttr.AMP3, 77)
+    t = {k: torch.from_numpy(a) for k, a in f.items()}
+    q = ofv.tracer_2d([halo.scalar(t["q0"]), halo.scalar(t["q1"])], t["dp1"], t["mfx"], t["mfy"], t["cx"], t["cy"], ograd(N), 2,
+                      q_split=0, q_split_max=3, halo=halo)
+    for n, a in zip(("q0", "q1"), q):
+        out["trc." + n] = a.numpy()[:, :, o + 1:o + 1 + N, o + 1:o + 1 + N]
+    return out
+
+
 if __name__ == "__main__":
     torch.set_default_dtype(torch.float64)
+    if len(sys.argv) < 2 or sys.argv[1] == "physics":
+        path = os.path.join(ROOT, "tests", "golden", "physics_c12.npz")
+        np.savez_compressed(path, **case_physics())
+        print(path, os.path.getsize(path))
     for nh, two in ((False, False), (True, False), (True, True)):
+        if len(sys.argv) > 1 and sys.argv[1] == "physics":
+            break
         if len(sys.argv) > 1 and sys.argv[1] == "two_sided" and not two:
             continue                        # (regenerate only the new fixture)
         out = case(nh, two)
