@@ -85,6 +85,11 @@ class fv3jedi_lm_type:
         self.pert = {k: np.zeros(shape) for k in self._names + ["ua", "va"]}       # allocate_pert (utils :75-100)
         self._phis_sent = False
 
+    @property
+    def handle(self):
+        """the fv3lm.FV3LM behind this object (multi-rank callers attach the transport: comm_init_nccl / comm_set_callback)"""
+        return self._h
+
     def delete(self):
         if self._h is not None:
             self._h.close() if hasattr(self._h, "close") else None

@@ -92,6 +92,27 @@ def _inputs_tracer():
     return N, K, None, None, f, act, p, dx, y
 
 
+def _inputs_c2l():
+    """cubed_to_latlon: the D-grid halo update (mode = 1) crosses the rank boundary; a11 .. a22 are inputs without increments"""
+    from common import metrics, rnd
+    from oracle.cubed_sphere import R
+    N, K = 12, 2
+    rng = np.random.default_rng(8)
+    M = metrics(N)
+    f = dict(u=10.0 * rnd(rng, N, K), v=10.0 * rnd(rng, N, K))
+    for n in ("a11", "a12", "a21", "a22"):
+        f[n] = np.ascontiguousarray(M[n][:, None])
+    act = ["u", "v"]
+    dx = {k: rng.standard_normal(f[k].shape) for k in act}
+    y = {o: np.zeros((6, K, N + 7, N + 7)) for o in ("ua", "va")}
+    for o in y:
+        y[o][..., R(1, N), R(1, N)] = rng.standard_normal((6, K, N, N))
+    return N, K, None, None, f, act, {}, dx, y
+
+
+_MODULE_INPUTS = {"tracer_2d": _inputs_tracer, "c2l_ord4": _inputs_c2l}
+
+
 def _worker(rank, world, port, nonhydro, outdir, two_sided=False):
     sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.join(os.path.dirname(HERE), "fv3-jedi-linearmodel_b200"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
@@ -99,8 +120,8 @@ def _worker(rank, world, port, nonhydro, outdir, two_sided=False):
     torch.set_num_threads(1)
     import fv3lm
     from common import metrics
-    module = "tracer_2d" if nonhydro == "tracer_2d" else "step"
-    N, K, ak, bk, f, act, p, dx, y = _inputs_tracer() if module == "tracer_2d" else _inputs(nonhydro, two_sided)
+    module = nonhydro if nonhydro in _MODULE_INPUTS else "step"
+    N, K, ak, bk, f, act, p, dx, y = _MODULE_INPUTS[module]() if module != "step" else _inputs(nonhydro, two_sided)
     cfg = fv3lm.default_config(N, K, rank=rank, nranks=world)
     h = fv3lm.FV3LM(cfg, ak, bk, emu=True)
     h.set_metrics(metrics(N))
@@ -132,8 +153,8 @@ def _check(world, nonhydro, two_sided=False):
     sys.path.insert(0, HERE)
     import fv3lm
     from common import metrics
-    module = "tracer_2d" if nonhydro == "tracer_2d" else "step"
-    N, K, ak, bk, f, act, p, dx, y = _inputs_tracer() if module == "tracer_2d" else _inputs(nonhydro, two_sided)
+    module = nonhydro if nonhydro in _MODULE_INPUTS else "step"
+    N, K, ak, bk, f, act, p, dx, y = _MODULE_INPUTS[module]() if module != "step" else _inputs(nonhydro, two_sided)
     h = fv3lm.FV3LM(fv3lm.default_config(N, K), ak, bk, emu=True)
     h.set_metrics(metrics(N))
     ref = _run_all(h, N, K, f, act, p, dx, y, module)
@@ -185,3 +206,8 @@ def test_multirank_tracer_sub_steps_gloo():
     t = {k: torch.from_numpy(v) for k, v in f.items()}
     ofv.tracer_2d([halo.scalar(t["q0"]), halo.scalar(t["q1"])], t["dp1"], t["mfx"], t["mfy"], t["cx"], t["cy"], ograd(N), 2, q_split=0, halo=halo)
     assert ofv.tracer_2d.last_nsplt == 3          # the inputs do need the sub-steps
+
+
+def test_multirank_c2l_gloo():
+    """cubed_to_latlon over two ranks: the halo update of the D-grid winds is a real exchange"""
+    _check(2, "c2l_ord4")
