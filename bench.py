@@ -191,6 +191,21 @@ def run_gpu(args):
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0])
+    # ---- dot-product (adjoint) test at the bench workload, through the same host-pointer calls (BASELINE.json: "dot-product err").
+    # Guarded: a failure here is reported in the line, it cannot take the throughput numbers down with it.
+    lhs = rhs = float("nan"); dot_note = None
+    try:
+        import checks
+        lhs, rhs = checks.dot_product_partial(h, 0, {k: pert[k] for k in fields}, fields, seed=20261019 + rank)
+    except Exception as e:  # noqa: BLE001
+        dot_note = "dot-product test failed to run: %s" % str(e)[:200]
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([lhs, rhs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        lhs, rhs = float(t[0]), float(t[1])
+    dot = {"rel_err": (abs(lhs - rhs) / max(abs(lhs), abs(rhs), 1e-300)) if lhs == lhs and rhs == rhs else None, "lhs": lhs if lhs == lhs else None,
+           "rhs": rhs if rhs == rhs else None, "note": dot_note or "<M dx, y> vs <dx, M^T y> of one step at the bench workload, seeded y, host-pointer API"}
     # ---- per-kernel profile (separate, serialised pass) -> dominant kernel roofline
     rows = []
     buf = __import__("ctypes").create_string_buffer(1 << 20)
@@ -243,6 +258,7 @@ def run_gpu(args):
                           "frac": step_alg_gb / (ms_step * 1e-3) / (peak * world), "n_gpus": world, "note": "SURVEY 8(d) array-pass contract: TL %d + AD %d passes x %.1f MB" % (p_tl, p_ad, field_bytes / 1e6)},
         "top_kernels": [{"name": r[0], "launches": r[1], "ms": round(r[2], 3), "alg_gbs": (r[3] / (r[2] * 1e-3) / 1e9 if r[2] > 0 else 0)} for r in rows[:12]],
         "pool_peak_gb": float(h.lib.fv3lm_pool_peak_bytes(h.h)) / 1e9,
+        "dot_product": dot,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(args, bounded=True)
