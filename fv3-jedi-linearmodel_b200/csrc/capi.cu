@@ -49,6 +49,9 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
   if (cfg->nq != 4) throw std::runtime_error("fv3lm_create: nq must be 4 (qv, ql, qi, o3)");
   if (cfg->n_split < 1 || cfg->k_split < 1 || !(cfg->dt > 0.0)) throw std::runtime_error("fv3lm_create: n_split, k_split and dt must be positive");
   if (cfg->nord < 0 || cfg->nord > 3) throw std::runtime_error("fv3lm_create: nord must be in 0..3");
+  if (cfg->q_split_dynamic != 0 && cfg->q_split_dynamic != 1) throw std::runtime_error("fv3lm_create: q_split_dynamic must be 0 or 1");
+  if (cfg->q_split_max < 0 || cfg->q_split_max > 8)
+    throw std::runtime_error("fv3lm_create: q_split_max must be in 0..8 (0 = 3; every issued tracer sub-step is part of the static program)");
   if (!cfg->hydrostatic && cfg->a_imp != 0.0 && !(cfg->a_imp > 0.5))
     throw std::runtime_error("fv3lm_create: a_imp <= 0.5 selects the RIM_2D / SIM3 solvers (model/nh_core_nlm.F90:136-146), which are not built; use 0.5 < a_imp <= 1");
   if (cfg->npx < 9) throw std::runtime_error("fv3lm_create: need at least 8 cells per tile edge");
