@@ -196,6 +196,7 @@ int fv3lm_module_run(fv3lm_handle* h, const char* module, int mode, int nfields,
     up2d(g, v.traj, ht, (size_t)g.ntile * v.nk * g.NY);
     v.active = (mode != MODE_NL) && host_of(id, true) != nullptr;
   }
+  P.sweep_kind = (mode == MODE_NL || mode == MODE_TL) ? VAR_FWD : VAR_AD;
   P.analyse();
   for (int id : ext) {
     Value& v = P.vals[id];

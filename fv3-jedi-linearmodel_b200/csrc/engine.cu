@@ -92,12 +92,14 @@ void Program::analyse() {
   // activity: propagate from active externals through the op list
   for (auto& v : vals) if (!v.external) v.active = false;
   for (auto& op : ops) {
+    if (skipped(op)) continue;
     bool any = false;
     for (int i : op.in) any = any || vals[i].active;
     if (!op.inplace) for (int o : op.out) vals[o].active = any;
   }
   for (auto& v : vals) { v.first_def = -1; v.last_use = -1; }
   for (int n = 0; n < (int)ops.size(); n++) {
+    if (skipped(ops[n])) continue;
     for (int i : ops[n].in) vals[i].last_use = n;
     for (int o : ops[n].out) { if (vals[o].first_def < 0) vals[o].first_def = n; vals[o].last_use = std::max(vals[o].last_use, n); }
   }
@@ -106,6 +108,7 @@ void Program::analyse() {
   for (auto& v : vals) if (v.alias >= 0) v.active = false;
   for (int n = 0; n < (int)ops.size(); n++) {
     ops[n].hold.clear();
+    if (skipped(ops[n])) continue;
     for (int i : ops[n].in)
       if (vals[i].alias >= 0) { ops[n].hold.push_back(vals[i].alias); vals[vals[i].alias].last_use = std::max(vals[vals[i].alias].last_use, n); }
   }
@@ -230,11 +233,13 @@ bool Program::ad_fits_store_all() {
 }
 
 void Program::run(Mode mode) {
+  sweep_kind = (mode == MODE_NL || mode == MODE_TL) ? VAR_FWD : VAR_AD;
   analyse();
   const int nop = (int)ops.size();
   if (mode == MODE_NL || mode == MODE_TL) {
     for (int n = 0; n < nop; n++) {
       Op& op = ops[n];
+      if (skipped(op)) continue;
       if (!(op.tl_only && mode == MODE_NL)) {     // (a skipped op still ends the life of its inputs)
         for (int o : op.out) { ensure_traj(o); if (mode == MODE_TL) ensure_pert(o, false); }
         run_op(op, mode);
@@ -275,6 +280,7 @@ void Program::run(Mode mode) {
     // pass 1: plain forward; segment-local values are freed at their last use, boundary-crossing ones stay
     for (int n = 0; n < nop; n++) {
       Op& op = ops[n];
+      if (skipped(op)) continue;
       if (!(op.tl_only && seg_of[n] < keep_from)) {        // (else: recomputed with its segment)
         for (int o : op.out) ensure_traj(o);
         // kept segments (at least the last, reversed first) stay whole; their patch ops save what they overwrite
@@ -292,11 +298,13 @@ void Program::run(Mode mode) {
       // recompute the segment keeping every value (patch ops save what they overwrite)
       for (int n = n0; n <= n1 && s < keep_from; n++) {
         Op& op = ops[n];
+        if (skipped(op)) continue;
         for (int o : op.out) ensure_traj(o);
         run_op(op, MODE_ADFWD);
       }
       for (int n = n1; n >= n0; n--) {
         Op& op = ops[n];
+        if (skipped(op)) continue;
         bool any_out = false;
         for (int o : op.out) if (vals[o].active && vals[o].pert) any_out = true;
         if (any_out || op.inplace) {
@@ -315,12 +323,14 @@ void Program::run(Mode mode) {
     // forward sweep, keep everything ("device checkpoint arena")
     for (int n = 0; n < nop; n++) {
       Op& op = ops[n];
+      if (skipped(op)) continue;
       for (int o : op.out) ensure_traj(o);
       run_op(op, MODE_ADFWD);
     }
     // reverse sweep
     for (int n = nop - 1; n >= 0; n--) {
       Op& op = ops[n];
+      if (skipped(op)) continue;
       bool any_out = false;
       for (int o : op.out) if (vals[o].active && vals[o].pert) any_out = true;
       if (any_out || op.inplace) {

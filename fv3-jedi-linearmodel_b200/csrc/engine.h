@@ -383,6 +383,7 @@ template <class F> void launch3d(const F& f, int nx, int ny, int nz) {
 // programs
 // ---------------------------------------------------------------------------------
 enum Mode { MODE_NL = 0, MODE_TL = 1, MODE_AD = 2, MODE_ADFWD = 3 };
+enum Variant { VAR_ALL = 0, VAR_FWD = 1, VAR_AD = 2 };
 
 struct Pool {
   std::map<size_t, std::vector<void*>> free_;
@@ -416,6 +417,10 @@ struct Op {
   bool inplace = false;    // patch op: out == in, mutates cells that were dead
   std::vector<int> hold;   // targets of the detached views among `in`: kept alive up to this op (filled by Program::analyse)
   bool tl_only = false;    // perturbation-scheme chain of a split transport: its trajectory values are only needed by TL / AD sweeps
+  // alternative implementations of the same piece of a program: 0 = always part of it, VAR_FWD = only in NL / TL sweeps (fused
+  // shared-memory-tile kernels that keep their intermediates on chip), VAR_AD = only in adjoint runs (the stage-by-stage chain
+  // whose intermediates the reverse sweep needs in HBM).  Program::analyse / run ignore the ops of the other kind.
+  int variant = 0;
   int nk_launch = 1;
   std::function<void(struct Program&, Op&, int /*Mode or 3 = AD reverse*/)> run;
 };
@@ -451,6 +456,9 @@ struct Program {
     return (int)vals.size() - 1;
   }
   size_t val_doubles(int id) const;
+  int sweep_kind = VAR_FWD;          // which alternative ops (Op::variant) the current run uses: set by run(), or by the caller before analyse()
+  int variant = 0;                   // builders set this around alternative ops (copied into Op::variant)
+  bool skipped(const Op& op) const { return op.variant != VAR_ALL && op.variant != sweep_kind; }
   void analyse();                    // activity + liveness
   bool ad_fits_store_all();
   int ad_store_all_cached = -1;
@@ -576,7 +584,7 @@ struct Device {
 template <class S>
 void Program::add(const char* nm, const typename S::P& prm, std::vector<int> ins, std::vector<int> outs, int nk_launch) {
   if ((int)ins.size() != S::NI || (int)outs.size() != S::NO) throw std::runtime_error(std::string("arity mismatch in ") + nm);
-  Op op; op.name = nm; op.in = ins; op.out = outs; op.nk_launch = nk_launch; op.tl_only = tl_only;
+  Op op; op.name = nm; op.in = ins; op.out = outs; op.nk_launch = nk_launch; op.tl_only = tl_only; op.variant = variant;
   typename S::P p = prm;
   op.run = [p](Program& P, Op& o, int mode) {
     const Geom& g = P.dv->g;
@@ -609,7 +617,7 @@ void Program::add(const char* nm, const typename S::P& prm, std::vector<int> ins
 template <class S>
 void add_col(Program& P, const char* nm, const typename S::P& prm, std::vector<int> ins, std::vector<int> outs) {
   if ((int)ins.size() != S::NI || (int)outs.size() != S::NO) throw std::runtime_error(std::string("arity mismatch in ") + nm);
-  Op op; op.name = nm; op.in = ins; op.out = outs; op.nk_launch = 1; op.tl_only = P.tl_only;
+  Op op; op.name = nm; op.in = ins; op.out = outs; op.nk_launch = 1; op.tl_only = P.tl_only; op.variant = P.variant;
   typename S::P p = prm;
   op.run = [p](Program& P, Op& o, int mode) {
     const Geom& g = P.dv->g;

@@ -1,5 +1,6 @@
 #include "modules.h"
 #include "stages_tp.h"
+#include "fused_tp.h"
 
 namespace fv3lm {
 
@@ -29,16 +30,30 @@ TpOut build_fv_tp_2d(Program& P, Mosaic& mo, int q, int crx, int cry, int xfx, i
     if (dir == 0) { if (lin) P.add<S_ppm<0>>(nm_, p0, {qq, cc}, {out}, nk); else P.add<S_ppm_nl<0>>(nm_, p0, {qq, cc}, {out}, nk); }
     else { if (lin) P.add<S_ppm<1>>(nm_, p1, {qq, cc}, {out}, nk); else P.add<S_ppm_nl<1>>(nm_, p1, {qq, cc}, {out}, nk); }
   };
+  // FV3LM_FUSED_TP=1: forward sweeps (NL, TL) run the two shared-memory-tile kernels of fused_tp.h instead of the eight stages
+  // (opt-in until it has been timed on a B200); adjoint runs always use the stage chain
+  const char* fe = getenv("FV3LM_FUSED_TP");
+  const bool fused = fe && atoi(fe) != 0;
+  const int var0 = P.variant;
+  auto chain = [&]() { if (fused) P.variant = VAR_AD; };
+  auto common = [&]() { P.variant = var0; };
+  const int mx = mfx >= 0 ? mfx : xfx, my = mfy >= 0 ? mfy : yfx;
   add_patch(P, "copy_corners_y", &mo.cc2, {q});
+  chain();
   ppm(1, "yppm_in", {isd, ied, js, je + 1, hord}, q, cry, fy2);
   P.add<S_inner<1>>("q_i", {isd, ied, js, je}, {q, fy2, yfx, ra_y}, {q_i}, nk);
   ppm(0, "xppm_ou", {is, ie + 1, js, je, hord}, q_i, crx, fxo);
+  common();
+  if (fused) ftp::add_fused_a(P, "tp_fused_a", q, cry, yfx, ra_y, crx, fy2, fxo, hord, !lin, nk);
   add_patch(P, "copy_corners_x", &mo.cc1, {q});
+  chain();
   ppm(0, "xppm_in", {is, ie + 1, jsd, jed, hord}, q, crx, fx2);
   P.add<S_inner<0>>("q_j", {is, ie, jsd, jed}, {q, fx2, xfx, ra_x}, {q_j}, nk);
   ppm(1, "yppm_ou", {is, ie, js, je + 1, hord}, q_j, cry, fyo);
-  P.add<S_favg>("fx_avg", {is, ie + 1, js, je}, {fxo, fx2, mfx >= 0 ? mfx : xfx}, {fx}, nk);
-  P.add<S_favg>("fy_avg", {is, ie, js, je + 1}, {fyo, fy2, mfy >= 0 ? mfy : yfx}, {fy}, nk);
+  P.add<S_favg>("fx_avg", {is, ie + 1, js, je}, {fxo, fx2, mx}, {fx}, nk);
+  P.add<S_favg>("fy_avg", {is, ie, js, je + 1}, {fyo, fy2, my}, {fy}, nk);
+  common();
+  if (fused) ftp::add_fused_b(P, "tp_fused_b", q, crx, xfx, ra_x, cry, fy2, fxo, mx, my, fx, fy, hord, !lin, nk);
   return {fx, fy};
 }
 

@@ -1,0 +1,107 @@
+"""(named zz: runs last -- the kernels have not been on a B200 yet and must not mask the rest of the suite under -x)
+fv_tp_2d as two shared-memory-tile kernels (csrc/fused_tp.h, FV3LM_FUSED_TP=1): forward sweeps (NL, TL) must reproduce the
+stage-by-stage chain of model_tlmadm/tp_core_tlm.F90:2123-2324 -- same arithmetic, so the comparison is to round-off -- and the
+adjoint (which keeps the chain) must stay the transpose of the fused tangent."""
+import numpy as np
+import pytest
+import fv3lm
+import common
+from common import metrics, handle, rnd, relerr, region
+import test_tp_core
+import test_step_api
+
+TOL = 1e-13     # identical expressions; the device build may contract multiply-adds differently in the two kernels
+
+
+@pytest.fixture
+def fused(monkeypatch):
+    """programs are built once per handle and read the switch at build time: start from (and leave) an empty handle cache"""
+    common._handles.clear()
+    monkeypatch.setenv("FV3LM_FUSED_TP", "1")
+    yield
+    common._handles.clear()
+
+
+def _fields(N, K, seed):
+    f, rng = test_tp_core._inputs(N, K, seed)
+    f["mfx"] = rnd(rng, N, K, 1.0) * np.abs(metrics(N)["area"][:, None])
+    f["mfy"] = rnd(rng, N, K, 1.0) * np.abs(metrics(N)["area"][:, None])
+    return f, rng
+
+
+def _module(emu, N, K, f, dp, mode, params):
+    h = handle(N, K, emu)
+    names = [n for n in f if n not in ("mfx", "mfy") or params.get("use_mf")]
+    traj = {n: f[n].copy() for n in names}
+    traj.update(fx=np.zeros_like(f["q"]), fy=np.zeros_like(f["q"]))
+    pert = None
+    if mode == fv3lm.MODE_TL:
+        pert = {n: dp[n].copy() for n in names}
+        pert.update(fx=np.zeros_like(f["q"]), fy=np.zeros_like(f["q"]))
+    h.module_run("fv_tp_2d", mode, traj, pert, params=params)
+    return traj, pert
+
+
+def _fused_vs_chain(emu, monkeypatch, N, K, params, tl=True):
+    f, rng = _fields(N, K, 77)
+    dp = {n: rnd(rng, N, K) * (np.abs(f[n]).mean() * 1e-2) for n in f}
+    res = {}
+    for flag in ("0", "1"):
+        common._handles.clear()
+        monkeypatch.setenv("FV3LM_FUSED_TP", flag)
+        res[flag] = [_module(emu, N, K, f, dp, fv3lm.MODE_NL, params)]
+        if tl:
+            res[flag].append(_module(emu, N, K, f, dp, fv3lm.MODE_TL, params))
+    common._handles.clear()
+    for a, b in zip(res["0"], res["1"]):
+        for which in (0, 1):
+            if a[which] is None:
+                continue
+            fx0, fx1 = region(a[which]["fx"], 1, N + 1, 1, N), region(b[which]["fx"], 1, N + 1, 1, N)
+            fy0, fy1 = region(a[which]["fy"], 1, N, 1, N + 1), region(b[which]["fy"], 1, N, 1, N + 1)
+            assert np.abs(fx0).max() > 0 and np.abs(fy0).max() > 0
+            assert relerr(fx1, fx0) <= TOL and relerr(fy1, fy0) <= TOL, (params, which, relerr(fx1, fx0), relerr(fy1, fy0))
+
+
+# N = 40: the padded array (47 x 47) spans two tiles in x and six in y, so footprints cross block boundaries on both axes
+@pytest.mark.parametrize("params", [dict(hord=2), dict(hord=1), dict(hord=333), dict(hord=2, use_mf=1), dict(hord=2, n_sponge=1)])
+def test_fused_vs_chain_emu(monkeypatch, params):
+    _fused_vs_chain(True, monkeypatch, 40, 2, params)
+
+
+@pytest.mark.parametrize("hord", [5, 8, 9, 13])
+def test_fused_vs_chain_trajectory_schemes_emu(monkeypatch, hord):
+    _fused_vs_chain(True, monkeypatch, 40, 2, dict(hord=hord), tl=False)
+
+
+@pytest.mark.parametrize("hord", [1, 2, 333])
+def test_fused_vs_oracle_emu(fused, hord):
+    """NL / TL through the fused kernels and AD through the chain against the oracle, dot-product test across the two"""
+    test_tp_core._run(True, hord)
+
+
+def test_fused_step_emu(fused):
+    """a whole model step: step_nl / step_tl run the fused transports, step_ad the chain -- oracle parity, dot-product and Taylor tests"""
+    print(test_step_api._run(True, nonhydro=True))
+
+
+def test_fused_step_two_sided_emu(fused):
+    """two-sided configuration: the trajectory-side transports (monotone schemes, detached inputs) run the value-only fused kernels"""
+    import test_fv_dynamics  # noqa: F401  (makes sure the shared helpers are importable in isolation)
+    test_step_api.test_step_api_reference_defaults_emu()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("params", [dict(hord=2), dict(hord=333), dict(hord=2, use_mf=1), dict(hord=1, n_sponge=1)])
+def test_fused_vs_chain_gpu(monkeypatch, params):
+    _fused_vs_chain(False, monkeypatch, 40, 2, params)
+
+
+@pytest.mark.gpu
+def test_fused_vs_chain_trajectory_schemes_gpu(monkeypatch):
+    _fused_vs_chain(False, monkeypatch, 40, 2, dict(hord=9), tl=False)
+
+
+@pytest.mark.gpu
+def test_fused_step_gpu(fused):
+    print(test_step_api._run(False, nonhydro=True))
