@@ -191,6 +191,257 @@ template <class K> void launch_tile(const K& k, int nx, int ny, int nz) {
 }
 #endif
 
+
+// =====================================================================================================================
+// Reverse sweep of one half of fv_tp_2d (inner sweep along axis DIN, outer sweep along the other axis) as ONE tile kernel in
+// gather form.  AVG = false is the reverse of kernel A (DIN = 1: y inside, x outside; incoming adjoints: fx_ou and fy2), AVG = true
+// the reverse of kernel B (DIN = 0; incoming adjoints fx, fy; the two flux averages are part of it).  Only the op's INPUT values
+// are read: the intermediates (inner flux Fi, updated field qm, outer flux Fo) are recomputed in the tile, so the forward sweep of
+// the adjoint does not have to keep them in HBM.  With I the inner and O the outer axis, for the cells of the block's tile:
+//   Fo_ad(c)  = adjoint of the outer flux at c                                        tile + (-3..+2 along I, -2..+2 along O)
+//   qm_ad(c)  = sum_s  dFo(c + s eO) / dqm(c) * Fo_ad(c + s eO),  s = -2 .. 3           tile + (-3..+2 along I)
+//   Fi_ad(c)  = Fi_ext_ad(c) + fi(c) * (qm_ad(c) / ra(c) - qm_ad(c - eI) / ra(c - eI))  tile + (-2..+2 along I)
+//   q_ad(c)  += qm_ad(c) area / ra(c) + sum_s dFi(c + s eI) / dq(c) * Fi_ad(c + s eI)
+// and the adjoints of the Courant numbers, flux areas and ra at the cell itself.  Every thread owns the cells it adds to: no
+// atomics, fixed summation order.  The linear orders only (1, 2, 333): nothing is ever differentiated through the others.
+// Hand-derived from tp_core_tlm.F90:2123-2324, 2328-2660 (the coefficient formulas are those of S_ppm::adjoint).
+// =====================================================================================================================
+struct Box {
+  int x0, y0, w, h;
+  DEV int idx(int ii, int jj) const { return (jj - y0) * w + (ii - x0); }
+  DEV bool has(int ii, int jj) const { return ii >= x0 && ii < x0 + w && jj >= y0 && jj < y0 + h; }
+  DEV int n() const { return w * h; }
+};
+// I-range [ia, ib], O-range [oa, ob] (array coordinates along the inner / outer axis) -> box in (ii, jj)
+template <int DIN> DEV Box box_of(int ia, int ib, int oa, int ob) {
+  return DIN == 0 ? Box{ia, oa, ib - ia + 1, ob - oa + 1} : Box{oa, ia, ob - oa + 1, ib - ia + 1};
+}
+
+// d flux(face) / d q(face + d) of the linear PPM fluxes; x is positioned at the face
+template <int DIR, class X> DEV double ppm_coef(const X& x, double c, int ord, int d) {
+  if (ord == 1) return (c > 0.0) ? (d == -1 ? 1.0 : 0.0) : (d == 0 ? 1.0 : 0.0);
+  if (ord == ORD333) {
+    const double c2 = c * c / 6.0;
+    if (c > 0.0) return d == 0 ? 2.0 / 6.0 - 0.5 * c + c2 : d == -1 ? 5.0 / 6.0 + 0.5 * c - 2.0 * c2 : d == -2 ? -1.0 / 6.0 + c2 : 0.0;
+    return d == -1 ? 2.0 / 6.0 + 0.5 * c + c2 : d == 0 ? 5.0 / 6.0 - 0.5 * c - 2.0 * c2 : d == 1 ? -1.0 / 6.0 + c2 : 0.0;
+  }
+  using S = S_ppm<DIR>;
+  if (c > 0.0) {
+    const double dqt = 1.0 + (1.0 - c) * (2.0 * c - 1.0), dal0 = (1.0 - c) * (1.0 - c), dalm = -(1.0 - c) * c;
+    return (d == -1 ? dqt : 0.0) + dal0 * S::al_w(x, 0, d + 2) + dalm * S::al_w(x, -1, d + 3);
+  }
+  const double dqt = 1.0 - (1.0 + c) * (1.0 + 2.0 * c), dal0 = (1.0 + c) * (1.0 + c), dalp = (1.0 + c) * c;
+  return (d == 0 ? dqt : 0.0) + dal0 * S::al_w(x, 0, d + 2) + dalp * S::al_w(x, 1, d + 1);
+}
+// d flux(face) / d c(face); x (positioned at the face) reads the transported field from its tile
+template <int DIR, class X> DEV double ppm_dc(const X& x, double c, int ord) {
+  if (ord == 1) return 0.0;
+  if (ord == ORD333) {
+    const double qm1 = tp::Q<DIR>(x, 0, -1), q0 = tp::Q<DIR>(x, 0, 0);
+    const double curv = c > 0.0 ? q0 - 2.0 * qm1 + tp::Q<DIR>(x, 0, -2) : tp::Q<DIR>(x, 0, 1) - 2.0 * q0 + qm1;
+    return -0.5 * (q0 - qm1) + c / 3.0 * curv;
+  }
+  const double al0 = tp::edge_al<DIR>(x, 0, 0);
+  if (c > 0.0) {
+    const double qt = tp::Q<DIR>(x, 0, -1), b = tp::edge_al<DIR>(x, 0, -1) + al0 - (qt + qt);
+    return -(al0 - qt - c * b) - (1.0 - c) * b;
+  }
+  const double qt = tp::Q<DIR>(x, 0, 0), b = al0 + tp::edge_al<DIR>(x, 0, 1) - (qt + qt);
+  return (al0 - qt + c * b) + (1.0 + c) * b;
+}
+
+template <int DIN, bool AVG> struct KernTpRev {
+  static constexpr int DOUT = 1 - DIN;
+  static constexpr int NPH = 5;
+  static constexpr int TA = DIN == 0 ? TX : TY, TB = DIN == 0 ? TY : TX;
+  Geom g; Metrics m; LevOrd ord; int nk;
+  // values: transported field, inner Courant number / flux area / ra, outer Courant number; AVG: the other two fluxes and the multipliers
+  Fld q, ci, fi, ra, co, fin2, fout2, mI, mO;
+  // incoming adjoints (.v = adjoint array): !AVG: aI = fy2_ad (inner flux), aO = fx_ou_ad (outer flux); AVG: aI = fx_ad, aO = fy_ad
+  Fld aI, aO;
+  // accumulated adjoints (.v = adjoint array, null = inactive)
+  OFld q_ad, ci_ad, fi_ad, ra_ad, co_ad, fin2_ad, fout2_ad, mI_ad, mO_ad;
+  struct Smem {
+    double q[QW * QH], Fi[(TA + 1) * (TB + 6)], qm[TA * (TB + 6)];
+    double Fo_ad[(TA + 6) * (TB + 5)], qm_ad[(TA + 6) * TB], Fi_ad[(TA + 5) * TB];
+  };
+  DEV static int eIx() { return DIN == 0; }
+  DEV static int eIy() { return DIN == 1; }
+  DEV static int eOx() { return DIN == 1; }
+  DEV static int eOy() { return DIN == 0; }
+  DEV bool rect_i(const CtxBase& x) const {   // inner flux: faces along I, the full halo along O
+    return DIN == 0 ? x.in_rect(g.is, g.ie + 1, g.js - g.ng, g.je + g.ng) : x.in_rect(g.is - g.ng, g.ie + g.ng, g.js, g.je + 1);
+  }
+  DEV bool rect_m(const CtxBase& x) const {
+    return DIN == 0 ? x.in_rect(g.is, g.ie, g.js - g.ng, g.je + g.ng) : x.in_rect(g.is - g.ng, g.ie + g.ng, g.js, g.je);
+  }
+  DEV bool rect_o(const CtxBase& x) const {   // outer flux: faces along O, compute domain along I
+    return DIN == 0 ? x.in_rect(g.is, g.ie, g.js, g.je + 1) : x.in_rect(g.is, g.ie + 1, g.js, g.je);
+  }
+  DEV bool rect_fi(const CtxBase& x) const {  // AVG: where the averaged flux along I (fx) lives
+    return x.in_rect(g.is, g.ie + 1, g.js, g.je);
+  }
+  DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
+    const int tile = z / nk, kk = z % nk, ii0 = bx * TX, jj0 = by * TY;
+    const int i0 = g.i0[tile], j0 = g.j0[tile];
+    const int a0 = DIN == 0 ? ii0 : jj0, b0 = DIN == 0 ? jj0 : ii0;
+    const int od = ord.v[kk];
+    const Box bq = box_of<DIN>(a0 - 3, a0 + TA + 2, b0 - 3, b0 + TB + 2);
+    const Box bFi = box_of<DIN>(a0, a0 + TA, b0 - 3, b0 + TB + 2);
+    const Box bqm = box_of<DIN>(a0, a0 + TA - 1, b0 - 3, b0 + TB + 2);
+    const Box bFoad = box_of<DIN>(a0 - 3, a0 + TA + 2, b0 - 2, b0 + TB + 2);
+    const Box bqmad = box_of<DIN>(a0 - 3, a0 + TA + 2, b0, b0 + TB - 1);
+    const Box bFiad = box_of<DIN>(a0 - 2, a0 + TA + 2, b0, b0 + TB - 1);
+    TileCtx<double> x; x.g = g; x.m = m; x.sd = nullptr;
+    auto inside = [&](int ii, int jj) { return ii >= 0 && ii < g.NX && jj >= 0 && jj < g.NY; };
+    auto gl = [&](const Fld& f, int di = 0, int dj = 0) { return LDG(f.v + x.off(f.nk, di, dj, 0)); };
+    if (ph == 0) {
+      // the transported field with its footprint; the adjoint of the outer flux where it exists, zero elsewhere
+      for (int c = tid; c < bq.n(); c += NTHR) {
+        const int ii = bq.x0 + c % bq.w, jj = bq.y0 + c / bq.w;
+        double a = 0.0;
+        if (inside(ii, jj)) { x.setpos(ii, jj, kk, tile, i0, j0); a = gl(q); }
+        s.q[c] = a;
+      }
+      for (int c = tid; c < bFoad.n(); c += NTHR) {
+        const int ii = bFoad.x0 + c % bFoad.w, jj = bFoad.y0 + c / bFoad.w;
+        double a = 0.0;
+        if (inside(ii, jj)) {
+          x.setpos(ii, jj, kk, tile, i0, j0);
+          if (rect_o(x)) { a = gl(aO); if (AVG && a != 0.0) a *= 0.5 * gl(mO); }
+        }
+        s.Fo_ad[c] = a;
+      }
+    } else if (ph == 1) {          // inner flux values
+      for (int c = tid; c < bFi.n(); c += NTHR) {
+        const int ii = bFi.x0 + c % bFi.w, jj = bFi.y0 + c / bFi.w;
+        if (!inside(ii, jj)) continue;
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        if (!rect_i(x)) continue;
+        x.sv = s.q; x.sw = bq.w; x.sp = bq.idx(ii, jj);
+        s.Fi[c] = tp::ppm_flux<DIN, false>(x, 0, gl(ci), od);
+      }
+    } else if (ph == 2) {          // qm values (S_inner); qm_ad by gathering the outer faces that read the cell
+      for (int c = tid; c < bqm.n(); c += NTHR) {
+        const int ii = bqm.x0 + c % bqm.w, jj = bqm.y0 + c / bqm.w;
+        if (!inside(ii, jj)) continue;
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        if (!rect_m(x)) continue;
+        const double f0 = gl(fi) * s.Fi[bFi.idx(ii, jj)], f1 = gl(fi, eIx(), eIy()) * s.Fi[bFi.idx(ii + eIx(), jj + eIy())];
+        s.qm[c] = (s.q[bq.idx(ii, jj)] * x.M(x.m.area) + f0 - f1) / gl(ra);
+      }
+      for (int c = tid; c < bqmad.n(); c += NTHR) {
+        const int ii = bqmad.x0 + c % bqmad.w, jj = bqmad.y0 + c / bqmad.w;
+        double sum = 0.0;
+        bool in_m = false;
+        if (inside(ii, jj)) { x.setpos(ii, jj, kk, tile, i0, j0); in_m = rect_m(x); }
+        if (in_m) {
+          for (int sft = -2; sft <= 3; sft++) {       // face f = cell + sft along O reads the cell at offset d = -sft
+            const int fi_ = ii + sft * eOx(), fj_ = jj + sft * eOy();
+            if (!inside(fi_, fj_) || !bFoad.has(fi_, fj_)) continue;
+            const double a = s.Fo_ad[bFoad.idx(fi_, fj_)];
+            if (a == 0.0) continue;
+            x.setpos(fi_, fj_, kk, tile, i0, j0);
+            sum += ppm_coef<DOUT>(x, gl(co), od, -sft) * a;
+          }
+        }
+        s.qm_ad[c] = sum;
+      }
+    } else if (ph == 3) {          // adjoint of the inner flux
+      for (int c = tid; c < bFiad.n(); c += NTHR) {
+        const int ii = bFiad.x0 + c % bFiad.w, jj = bFiad.y0 + c / bFiad.w;
+        double a = 0.0;
+        if (inside(ii, jj)) {
+          x.setpos(ii, jj, kk, tile, i0, j0);
+          if (rect_i(x)) {
+            if (AVG) { if (rect_fi(x)) { a = gl(aI); if (a != 0.0) a *= 0.5 * gl(mI); } }
+            else a = gl(aI);
+            double t = 0.0;
+            const double qa0 = rect_m(x) ? s.qm_ad[bqmad.idx(ii, jj)] : 0.0;
+            if (qa0 != 0.0) t += qa0 / gl(ra);
+            const int pi = ii - eIx(), pj = jj - eIy();
+            if (inside(pi, pj) && bqmad.has(pi, pj)) {
+              const double qa1 = s.qm_ad[bqmad.idx(pi, pj)];      // (zero outside rect_m)
+              if (qa1 != 0.0) t -= qa1 / gl(ra, -eIx(), -eIy());
+            }
+            if (t != 0.0) a += gl(fi) * t;
+          }
+        }
+        s.Fi_ad[c] = a;
+      }
+    } else if (ph == 4) {          // everything the block's own cells accumulate
+      const int ii = ii0 + tid % TX, jj = jj0 + tid / TX;
+      if (!inside(ii, jj)) return;
+      x.setpos(ii, jj, kk, tile, i0, j0);
+      const bool in_i = rect_i(x), in_m = rect_m(x), in_o = rect_o(x);
+      double aq = 0.0;
+      if (in_m) {
+        const double qa = s.qm_ad[bqmad.idx(ii, jj)];
+        if (qa != 0.0) {
+          const double r = gl(ra);
+          aq += qa * x.M(x.m.area) / r;
+          if (ra_ad.v) ra_ad.v[x.off(ra_ad.nk, 0, 0, 0)] += -s.qm[bqm.idx(ii, jj)] / r * qa;
+        }
+      }
+      if (in_i) {
+        const double fa = s.Fi_ad[bFiad.idx(ii, jj)];
+        if (fi_ad.v) {          // flux area: Fi(c) * (qm_ad(c) / ra(c) - qm_ad(c - eI) / ra(c - eI))
+          double t = 0.0;
+          const double qa0 = in_m ? s.qm_ad[bqmad.idx(ii, jj)] : 0.0;
+          if (qa0 != 0.0) t += qa0 / gl(ra);
+          const int pi = ii - eIx(), pj = jj - eIy();
+          if (inside(pi, pj)) { const double qa1 = s.qm_ad[bqmad.idx(pi, pj)]; if (qa1 != 0.0) t -= qa1 / gl(ra, -eIx(), -eIy()); }
+          if (t != 0.0) fi_ad.v[x.off(fi_ad.nk, 0, 0, 0)] += s.Fi[bFi.idx(ii, jj)] * t;
+        }
+        if (ci_ad.v && fa != 0.0) {
+          x.sv = s.q; x.sw = bq.w; x.sp = bq.idx(ii, jj);
+          ci_ad.v[x.off(ci_ad.nk, 0, 0, 0)] += ppm_dc<DIN>(x, gl(ci), od) * fa;
+        }
+      }
+      if (in_o) {
+        const double oa = s.Fo_ad[bFoad.idx(ii, jj)];
+        if (co_ad.v && oa != 0.0) {
+          x.sv = s.qm; x.sw = bqm.w; x.sp = bqm.idx(ii, jj);
+          co_ad.v[x.off(co_ad.nk, 0, 0, 0)] += ppm_dc<DOUT>(x, gl(co), od) * oa;
+        }
+      }
+      if (AVG) {
+        if (in_o) {             // fy = 0.5 (Fo + fy2) mO
+          const double a = gl(aO);
+          if (a != 0.0) {
+            if (fin2_ad.v) fin2_ad.v[x.off(fin2_ad.nk, 0, 0, 0)] += 0.5 * gl(mO) * a;
+            if (mO_ad.v) {
+              x.sv = s.qm; x.sw = bqm.w; x.sp = bqm.idx(ii, jj);
+              const double Fo = tp::ppm_flux<DOUT, false>(x, 0, gl(co), od);
+              mO_ad.v[x.off(mO_ad.nk, 0, 0, 0)] += 0.5 * (Fo + gl(fin2)) * a;
+            }
+          }
+        }
+        if (rect_fi(x)) {       // fx = 0.5 (fx_ou + Fi) mI
+          const double a = gl(aI);
+          if (a != 0.0) {
+            if (fout2_ad.v) fout2_ad.v[x.off(fout2_ad.nk, 0, 0, 0)] += 0.5 * gl(mI) * a;
+            if (mI_ad.v) mI_ad.v[x.off(mI_ad.nk, 0, 0, 0)] += 0.5 * (gl(fout2) + s.Fi[bFi.idx(ii, jj)]) * a;
+          }
+        }
+      }
+      // the inner faces that read this cell
+      if (q_ad.v) {
+        for (int sft = -2; sft <= 3; sft++) {
+          const int fi_ = ii + sft * eIx(), fj_ = jj + sft * eIy();
+          if (!inside(fi_, fj_)) continue;
+          const double a = s.Fi_ad[bFiad.idx(fi_, fj_)];      // (zero outside rect_i)
+          if (a == 0.0) continue;
+          x.setpos(fi_, fj_, kk, tile, i0, j0);
+          aq += ppm_coef<DIN>(x, gl(ci), od, -sft) * a;
+        }
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        if (aq != 0.0) q_ad.v[x.off(q_ad.nk, 0, 0, 0)] += aq;
+      }
+    }
+  }
+};
+
 inline Fld fld(const Value& v, bool tl) { return Fld{v.traj, (tl && v.active) ? v.pert : nullptr, v.nk}; }
 inline OFld ofld(const Value& v, bool tl) { return OFld{v.traj, (tl && v.active) ? v.pert : nullptr, v.nk}; }
 
@@ -208,12 +459,32 @@ void run_fused(Program& P, Op& o, int mode, bool full, const Fill& fill) {
   else { if (full) go(K<double, true>{}); else go(K<double, false>{}); }
 }
 
-// appends the two fused ops (VAR_FWD) to a program; the caller has already added the copy_corners patches around them
+inline Fld adj_in(const Value& v) { return Fld{v.active ? v.pert : nullptr, nullptr, v.nk}; }
+inline OFld adj_out(const Value& v) { return OFld{v.active ? v.pert : nullptr, nullptr, v.nk}; }
+inline Fld val_in(const Value& v) { return Fld{v.traj, nullptr, v.nk}; }
+
+// appends the two fused ops to a program; the caller has already added the copy_corners patches around them.
+// with_ad = false: forward sweeps only (VAR_FWD, the stage chain stays for adjoint runs); true: the ops also carry the reverse
+// tile kernel (KernTpRev), the stage chain is not built at all and its six intermediates never reach HBM in any sweep.
 inline void add_fused_a(Program& P, const std::string& nm, int q, int cry, int yfx, int ra_y, int crx, int fy2, int fxo,
-                        const LevOrd& hord, bool full, int nk) {
-  Op op; op.name = nm; op.in = {q, cry, yfx, ra_y, crx}; op.out = {fy2, fxo}; op.nk_launch = nk; op.tl_only = P.tl_only; op.variant = VAR_FWD;
-  op.run = [hord, full](Program& P, Op& o, int mode) {
-    if (mode != MODE_NL && mode != MODE_TL) throw std::runtime_error("fused fv_tp_2d kernels run in forward sweeps only");
+                        const LevOrd& hord, bool full, int nk, bool with_ad) {
+  Op op; op.name = nm; op.in = {q, cry, yfx, ra_y, crx}; op.out = {fy2, fxo}; op.nk_launch = nk; op.tl_only = P.tl_only;
+  op.variant = with_ad ? P.variant : (int)VAR_FWD;
+  for (int id : op.in) if (P.vals[id].nk != nk) throw std::runtime_error("fused fv_tp_2d: every field must have the launch's number of levels");
+  op.run = [hord, full, with_ad](Program& P, Op& o, int mode) {
+    if (mode == MODE_AD) {
+      if (!with_ad || full) throw std::runtime_error("fused fv_tp_2d: no reverse kernel for this op");
+      const Geom& g = P.dv->g;
+      KernTpRev<1, false> k{};
+      k.g = g; k.m = P.dv->m; k.ord = hord; k.nk = o.nk_launch;
+      const Value &vq = P.vals[o.in[0]], &vci = P.vals[o.in[1]], &vfi = P.vals[o.in[2]], &vra = P.vals[o.in[3]], &vco = P.vals[o.in[4]];
+      k.q = val_in(vq); k.ci = val_in(vci); k.fi = val_in(vfi); k.ra = val_in(vra); k.co = val_in(vco);
+      k.aI = adj_in(P.vals[o.out[0]]); k.aO = adj_in(P.vals[o.out[1]]);
+      if (!k.aI.v || !k.aO.v) throw std::runtime_error("fused fv_tp_2d: output adjoints missing");
+      k.q_ad = adj_out(vq); k.ci_ad = adj_out(vci); k.fi_ad = adj_out(vfi); k.ra_ad = adj_out(vra); k.co_ad = adj_out(vco);
+      launch_tile(k, g.NX, g.NY, g.ntile * o.nk_launch);
+      return;
+    }
     run_fused<KernTpA>(P, o, mode, full, [&](auto& k, bool tl) {
       k.ord = hord;
       k.q = fld(P.vals[o.in[0]], tl); k.cry = fld(P.vals[o.in[1]], tl); k.yfx = fld(P.vals[o.in[2]], tl);
@@ -224,10 +495,27 @@ inline void add_fused_a(Program& P, const std::string& nm, int q, int cry, int y
   P.ops.push_back(op);
 }
 inline void add_fused_b(Program& P, const std::string& nm, int q, int crx, int xfx, int ra_x, int cry, int fy2, int fxo, int mx, int my,
-                        int fx, int fy, const LevOrd& hord, bool full, int nk) {
-  Op op; op.name = nm; op.in = {q, crx, xfx, ra_x, cry, fy2, fxo, mx, my}; op.out = {fx, fy}; op.nk_launch = nk; op.tl_only = P.tl_only; op.variant = VAR_FWD;
-  op.run = [hord, full](Program& P, Op& o, int mode) {
-    if (mode != MODE_NL && mode != MODE_TL) throw std::runtime_error("fused fv_tp_2d kernels run in forward sweeps only");
+                        int fx, int fy, const LevOrd& hord, bool full, int nk, bool with_ad) {
+  Op op; op.name = nm; op.in = {q, crx, xfx, ra_x, cry, fy2, fxo, mx, my}; op.out = {fx, fy}; op.nk_launch = nk; op.tl_only = P.tl_only;
+  op.variant = with_ad ? P.variant : (int)VAR_FWD;
+  for (int id : op.in) if (P.vals[id].nk != nk) throw std::runtime_error("fused fv_tp_2d: every field must have the launch's number of levels");
+  op.run = [hord, full, with_ad](Program& P, Op& o, int mode) {
+    if (mode == MODE_AD) {
+      if (!with_ad || full) throw std::runtime_error("fused fv_tp_2d: no reverse kernel for this op");
+      const Geom& g = P.dv->g;
+      KernTpRev<0, true> k{};
+      k.g = g; k.m = P.dv->m; k.ord = hord; k.nk = o.nk_launch;
+      const Value &vq = P.vals[o.in[0]], &vci = P.vals[o.in[1]], &vfi = P.vals[o.in[2]], &vra = P.vals[o.in[3]], &vco = P.vals[o.in[4]];
+      const Value &vfy2 = P.vals[o.in[5]], &vfxo = P.vals[o.in[6]], &vmx = P.vals[o.in[7]], &vmy = P.vals[o.in[8]];
+      k.q = val_in(vq); k.ci = val_in(vci); k.fi = val_in(vfi); k.ra = val_in(vra); k.co = val_in(vco);
+      k.fin2 = val_in(vfy2); k.fout2 = val_in(vfxo); k.mI = val_in(vmx); k.mO = val_in(vmy);
+      k.aI = adj_in(P.vals[o.out[0]]); k.aO = adj_in(P.vals[o.out[1]]);
+      if (!k.aI.v || !k.aO.v) throw std::runtime_error("fused fv_tp_2d: output adjoints missing");
+      k.q_ad = adj_out(vq); k.ci_ad = adj_out(vci); k.fi_ad = adj_out(vfi); k.ra_ad = adj_out(vra); k.co_ad = adj_out(vco);
+      k.fin2_ad = adj_out(vfy2); k.fout2_ad = adj_out(vfxo); k.mI_ad = adj_out(vmx); k.mO_ad = adj_out(vmy);
+      launch_tile(k, g.NX, g.NY, g.ntile * o.nk_launch);
+      return;
+    }
     run_fused<KernTpB>(P, o, mode, full, [&](auto& k, bool tl) {
       k.ord = hord;
       k.q = fld(P.vals[o.in[0]], tl); k.crx = fld(P.vals[o.in[1]], tl); k.xfx = fld(P.vals[o.in[2]], tl); k.rax = fld(P.vals[o.in[3]], tl);

@@ -20,9 +20,14 @@ TpOut build_fv_tp_2d(Program& P, Mosaic& mo, int q, int crx, int cry, int xfx, i
   const int is = g.is, ie = g.ie, js = g.js, je = g.je, ng = g.ng;
   const int isd = is - ng, ied = ie + ng, jsd = js - ng, jed = je + ng;
   auto nm = [&](const char* s) { return tag + "." + s; };
-  int fy2 = P.val(nm("fy2"), nk), q_i = P.val(nm("q_i"), nk), fxo = P.val(nm("fx_ou"), nk);
-  int fx2 = P.val(nm("fx2"), nk), q_j = P.val(nm("q_j"), nk), fyo = P.val(nm("fy_ou"), nk);
-  int fx = P.val(nm("fx"), nk), fy = P.val(nm("fy"), nk);
+  const char* fe = getenv("FV3LM_FUSED_TP");
+  const int flevel = fe ? atoi(fe) : 0;
+  const bool fused = flevel != 0;
+  // the reverse kernels cover the linear orders; a transport with a scheme of the nonlinear model has detached inputs and is never reversed
+  const bool with_ad = flevel >= 2;
+  int fy2 = P.val(nm("fy2"), nk), fxo = P.val(nm("fx_ou"), nk), fx = P.val(nm("fx"), nk), fy = P.val(nm("fy"), nk);
+  int q_i = -1, fx2 = -1, q_j = -1, fyo = -1;
+  if (!with_ad) { q_i = P.val(nm("q_i"), nk); fx2 = P.val(nm("fx2"), nk); q_j = P.val(nm("q_j"), nk); fyo = P.val(nm("fy_ou"), nk); }
   // the linear orders of the TL / AD run the lean S_ppm kernels; any order of the nonlinear model (trajectory side) S_ppm_nl
   const bool lin = ord_is_linear(hord, nk);
   auto ppm = [&](int dir, const char* nm_, const S_ppm<0>::P& p0, int qq, int cc, int out) {
@@ -30,30 +35,33 @@ TpOut build_fv_tp_2d(Program& P, Mosaic& mo, int q, int crx, int cry, int xfx, i
     if (dir == 0) { if (lin) P.add<S_ppm<0>>(nm_, p0, {qq, cc}, {out}, nk); else P.add<S_ppm_nl<0>>(nm_, p0, {qq, cc}, {out}, nk); }
     else { if (lin) P.add<S_ppm<1>>(nm_, p1, {qq, cc}, {out}, nk); else P.add<S_ppm_nl<1>>(nm_, p1, {qq, cc}, {out}, nk); }
   };
-  // FV3LM_FUSED_TP=1: forward sweeps (NL, TL) run the two shared-memory-tile kernels of fused_tp.h instead of the eight stages
-  // (opt-in until it has been timed on a B200); adjoint runs always use the stage chain
-  const char* fe = getenv("FV3LM_FUSED_TP");
-  const bool fused = fe && atoi(fe) != 0;
+  // FV3LM_FUSED_TP=1: forward sweeps (NL, TL) run the two shared-memory-tile kernels of fused_tp.h instead of the eight stages,
+  // adjoint runs the stage chain.  FV3LM_FUSED_TP=2: the adjoint too runs tile kernels (forward values + one reverse kernel per half
+  // that recomputes the intermediates on chip); the chain is not built.  Opt-in until timed on a B200.
   const int var0 = P.variant;
   auto chain = [&]() { if (fused) P.variant = VAR_AD; };
   auto common = [&]() { P.variant = var0; };
   const int mx = mfx >= 0 ? mfx : xfx, my = mfy >= 0 ? mfy : yfx;
   add_patch(P, "copy_corners_y", &mo.cc2, {q});
   chain();
-  ppm(1, "yppm_in", {isd, ied, js, je + 1, hord}, q, cry, fy2);
-  P.add<S_inner<1>>("q_i", {isd, ied, js, je}, {q, fy2, yfx, ra_y}, {q_i}, nk);
-  ppm(0, "xppm_ou", {is, ie + 1, js, je, hord}, q_i, crx, fxo);
+  if (!with_ad) {
+    ppm(1, "yppm_in", {isd, ied, js, je + 1, hord}, q, cry, fy2);
+    P.add<S_inner<1>>("q_i", {isd, ied, js, je}, {q, fy2, yfx, ra_y}, {q_i}, nk);
+    ppm(0, "xppm_ou", {is, ie + 1, js, je, hord}, q_i, crx, fxo);
+  }
   common();
-  if (fused) ftp::add_fused_a(P, "tp_fused_a", q, cry, yfx, ra_y, crx, fy2, fxo, hord, !lin, nk);
+  if (fused) ftp::add_fused_a(P, "tp_fused_a", q, cry, yfx, ra_y, crx, fy2, fxo, hord, !lin, nk, with_ad);
   add_patch(P, "copy_corners_x", &mo.cc1, {q});
   chain();
-  ppm(0, "xppm_in", {is, ie + 1, jsd, jed, hord}, q, crx, fx2);
-  P.add<S_inner<0>>("q_j", {is, ie, jsd, jed}, {q, fx2, xfx, ra_x}, {q_j}, nk);
-  ppm(1, "yppm_ou", {is, ie, js, je + 1, hord}, q_j, cry, fyo);
-  P.add<S_favg>("fx_avg", {is, ie + 1, js, je}, {fxo, fx2, mx}, {fx}, nk);
-  P.add<S_favg>("fy_avg", {is, ie, js, je + 1}, {fyo, fy2, my}, {fy}, nk);
+  if (!with_ad) {
+    ppm(0, "xppm_in", {is, ie + 1, jsd, jed, hord}, q, crx, fx2);
+    P.add<S_inner<0>>("q_j", {is, ie, jsd, jed}, {q, fx2, xfx, ra_x}, {q_j}, nk);
+    ppm(1, "yppm_ou", {is, ie, js, je + 1, hord}, q_j, cry, fyo);
+    P.add<S_favg>("fx_avg", {is, ie + 1, js, je}, {fxo, fx2, mx}, {fx}, nk);
+    P.add<S_favg>("fy_avg", {is, ie, js, je + 1}, {fyo, fy2, my}, {fy}, nk);
+  }
   common();
-  if (fused) ftp::add_fused_b(P, "tp_fused_b", q, crx, xfx, ra_x, cry, fy2, fxo, mx, my, fx, fy, hord, !lin, nk);
+  if (fused) ftp::add_fused_b(P, "tp_fused_b", q, crx, xfx, ra_x, cry, fy2, fxo, mx, my, fx, fy, hord, !lin, nk, with_ad);
   return {fx, fy};
 }
 

@@ -14,6 +14,15 @@ TOL = 1e-13     # identical expressions; the device build may contract multiply-
 
 
 @pytest.fixture
+def fused2(monkeypatch):
+    """FV3LM_FUSED_TP=2: the adjoint runs tile kernels as well (no stage chain in the program)"""
+    common._handles.clear()
+    monkeypatch.setenv("FV3LM_FUSED_TP", "2")
+    yield
+    common._handles.clear()
+
+
+@pytest.fixture
 def fused(monkeypatch):
     """programs are built once per handle and read the switch at build time: start from (and leave) an empty handle cache"""
     common._handles.clear()
@@ -61,6 +70,70 @@ def _fused_vs_chain(emu, monkeypatch, N, K, params, tl=True):
             fy0, fy1 = region(a[which]["fy"], 1, N, 1, N + 1), region(b[which]["fy"], 1, N, 1, N + 1)
             assert np.abs(fx0).max() > 0 and np.abs(fy0).max() > 0
             assert relerr(fx1, fx0) <= TOL and relerr(fy1, fy0) <= TOL, (params, which, relerr(fx1, fx0), relerr(fy1, fy0))
+
+
+def _module_ad(emu, N, K, f, y, params):
+    h = handle(N, K, emu)
+    names = [n for n in f if n not in ("mfx", "mfy") or params.get("use_mf")]
+    traj = {n: f[n].copy() for n in names}
+    traj.update(fx=np.zeros_like(f["q"]), fy=np.zeros_like(f["q"]))
+    pert = {n: np.zeros_like(f[n]) for n in names}
+    pert.update(fx=y["fx"].copy(), fy=y["fy"].copy())
+    h.module_run("fv_tp_2d", fv3lm.MODE_AD, traj, pert, params=params)
+    return {n: pert[n] for n in names}
+
+
+def _rev_vs_chain(emu, monkeypatch, N, K, params):
+    """reverse tile kernels (level 2) against the stage chain's gather adjoints, all input adjoints"""
+    f, rng = _fields(N, K, 78)
+    y = dict(fx=np.zeros_like(f["q"]), fy=np.zeros_like(f["q"]))
+    region(y["fx"], 1, N + 1, 1, N)[...] = region(rnd(rng, N, K), 1, N + 1, 1, N)
+    region(y["fy"], 1, N, 1, N + 1)[...] = region(rnd(rng, N, K), 1, N, 1, N + 1)
+    res = {}
+    for flag in ("0", "2"):
+        common._handles.clear()
+        monkeypatch.setenv("FV3LM_FUSED_TP", flag)
+        res[flag] = _module_ad(emu, N, K, f, y, params)
+    common._handles.clear()
+    for n in res["0"]:
+        assert np.abs(res["0"][n]).max() > 0 or (params["hord"] == 1 and n in ("crx", "cry")), n     # (upwind fluxes do not depend on c)
+        assert relerr(res["2"][n], res["0"][n]) <= 1e-12, (params, n, relerr(res["2"][n], res["0"][n]))
+
+
+@pytest.mark.parametrize("params", [dict(hord=2), dict(hord=1), dict(hord=333), dict(hord=2, use_mf=1), dict(hord=2, n_sponge=1)])
+def test_reverse_vs_chain_emu(monkeypatch, params):
+    _rev_vs_chain(True, monkeypatch, 40, 2, params)
+
+
+@pytest.mark.parametrize("hord", [1, 2, 333])
+def test_fused2_vs_oracle_emu(fused2, hord):
+    """NL / TL / AD all through tile kernels against the oracle (jvp / vjp) + dot-product test"""
+    test_tp_core._run(True, hord)
+
+
+def test_fused2_step_emu(fused2):
+    print(test_step_api._run(True, nonhydro=True))
+
+
+def test_fused2_step_hydro_segmented_emu(fused2, monkeypatch):
+    """hydrostatic step with the checkpoint / recompute adjoint forced"""
+    monkeypatch.setenv("FV3LM_AD_STORE_BUDGET", "0")
+    print(test_step_api._run(True, nonhydro=False))
+
+
+def test_fused2_step_two_sided_emu(fused2):
+    test_step_api.test_step_api_reference_defaults_emu()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("params", [dict(hord=2), dict(hord=333), dict(hord=2, use_mf=1), dict(hord=1, n_sponge=1)])
+def test_reverse_vs_chain_gpu(monkeypatch, params):
+    _rev_vs_chain(False, monkeypatch, 40, 2, params)
+
+
+@pytest.mark.gpu
+def test_fused2_step_gpu(fused2):
+    print(test_step_api._run(False, nonhydro=True))
 
 
 # N = 40: the padded array (47 x 47) spans two tiles in x and six in y, so footprints cross block boundaries on both axes
