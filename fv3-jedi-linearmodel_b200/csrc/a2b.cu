@@ -2,6 +2,7 @@
 // extrap_corner :800-810; TL a2b_edge_tlm.F90:546, AD a2b_edge_adm.F90:72).  Linear in qin.
 #include "stages_dsw.h"
 #include "modules.h"
+#include "fused_tp.h"
 
 namespace fv3lm {
 namespace a2b {
@@ -175,9 +176,188 @@ struct S_a2b_q2 {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// a2b_ord4 as ONE tile kernel per sweep direction (FV3LM_FUSED_A2B=1; opt-in until timed on a B200): qin -> qout with qx, qy and
+// the boundary values qe in shared memory (2 array passes instead of 10).  The stages' own eval() run on tile contexts
+// (fused_tp.h, TCtx).  The operator is linear in qin with purely geometric coefficients, so the reverse kernel is the transposed
+// gather: qout_ad tile -> qx_ad, qy_ad, qe_ad tiles -> qin_ad of the block's own cells, with the uniform-stencil fast paths of
+// the stage adjoints above away from the tile edges and seeded evaluations of the stages near them.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace ftp {
+template <class TT> struct KernA2b {
+  static constexpr bool TLM = !std::is_same<TT, double>::value;
+  static constexpr int NPH = 3;
+  Geom g; Metrics m; int nk; Fld qin; OFld qout;
+  struct Smem { SBuf<TLM, QW * QH> q; SBuf<TLM, TX * QH> qx; SBuf<TLM, QW * TY> qy; SBuf<TLM, (TX + 2) * (TY + 2)> qe; };
+  DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
+    using N = Num<TT>;
+    const int tile = z / nk, kk = z % nk, ii0 = bx * TX, jj0 = by * TY;
+    const int i0 = g.i0[tile], j0 = g.j0[tile];
+    const Box bq{ii0 - 3, jj0 - 3, QW, QH}, bqx{ii0, jj0 - 3, TX, QH}, bqy{ii0 - 3, jj0, QW, TY}, bqe{ii0 - 1, jj0 - 1, TX + 2, TY + 2};
+    auto inside = [&](int ii, int jj) { return ii >= 0 && ii < g.NX && jj >= 0 && jj < g.NY; };
+    if (ph == 0) {
+      CtxBase x; x.g = g;
+      for (int c = tid; c < bq.n(); c += NTHR) {
+        const int ii = bq.x0 + c % bq.w, jj = bq.y0 + c / bq.w;
+        TT a = TT(0.0);
+        if (inside(ii, jj)) { x.setpos(ii, jj, kk, tile, i0, j0); a = N::ld(qin, x.off(qin.nk, 0, 0, 0)); }
+        N::sts(s.q.v, s.q.d, c, a);
+      }
+    } else if (ph == 1) {
+      TCtx<TT, 1, 1> x; x.g = g; x.m = m;
+      x.ti[0] = TRef{s.q.v, s.q.d, bq}; x.gi[0] = Fld{nullptr, nullptr, 1}; x.go[0] = OFld{nullptr, nullptr, 1};
+      x.to[0] = TOut{s.qx.v, s.qx.d, bqx};
+      for (int c = tid; c < bqx.n(); c += NTHR) {
+        const int ii = bqx.x0 + c % bqx.w, jj = bqx.y0 + c / bqx.w;
+        if (!inside(ii, jj)) continue;
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        S_a2b_q1<0>::eval(x, {0});
+      }
+      x.to[0] = TOut{s.qy.v, s.qy.d, bqy};
+      for (int c = tid; c < bqy.n(); c += NTHR) {
+        const int ii = bqy.x0 + c % bqy.w, jj = bqy.y0 + c / bqy.w;
+        if (!inside(ii, jj)) continue;
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        S_a2b_q1<1>::eval(x, {0});
+      }
+      x.to[0] = TOut{s.qe.v, s.qe.d, bqe};
+      for (int c = tid; c < bqe.n(); c += NTHR) {
+        const int ii = bqe.x0 + c % bqe.w, jj = bqe.y0 + c / bqe.w;
+        if (!inside(ii, jj)) continue;
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        S_a2b_edge::eval(x, {0});
+      }
+    } else {
+      const int ii = ii0 + tid % TX, jj = jj0 + tid / TX;
+      if (!inside(ii, jj)) return;
+      TCtx<TT, 3, 1> x; x.g = g; x.m = m;
+      x.ti[0] = TRef{s.qx.v, s.qx.d, bqx}; x.ti[1] = TRef{s.qy.v, s.qy.d, bqy}; x.ti[2] = TRef{s.qe.v, s.qe.d, bqe};
+      for (int f = 0; f < 3; f++) x.gi[f] = Fld{nullptr, nullptr, 1};
+      x.to[0] = TOut{nullptr, nullptr, bq}; x.go[0] = qout;
+      x.setpos(ii, jj, kk, tile, i0, j0);
+      S_a2b_q2::eval(x, {0});
+    }
+  }
+};
+
+struct KernA2bRev {
+  static constexpr int NPH = 3;
+  static constexpr int UW = TX + 5, UH = TY + 5;
+  Geom g; Metrics m; int nk; Fld aout; OFld qin_ad;      // .v = adjoint arrays
+  struct Smem { double oad[UW * UH], qx_ad[UW * TY], qy_ad[TX * UH], qe_ad[(TX + 3) * (TY + 3)]; };
+  DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
+    const int tile = z / nk, kk = z % nk, ii0 = bx * TX, jj0 = by * TY;
+    const int i0 = g.i0[tile], j0 = g.j0[tile];
+    const Box bu{ii0 - 2, jj0 - 2, UW, UH}, bqx{ii0 - 2, jj0, UW, TY}, bqy{ii0, jj0 - 2, TX, UH}, bqe{ii0 - 1, jj0 - 1, TX + 3, TY + 3};
+    auto inside = [&](int ii, int jj) { return ii >= 0 && ii < g.NX && jj >= 0 && jj < g.NY; };
+    if (ph == 0) {
+      CtxBase x; x.g = g;
+      for (int c = tid; c < bu.n(); c += NTHR) {
+        const int ii = bu.x0 + c % bu.w, jj = bu.y0 + c / bu.w;
+        double a = 0.0;
+        if (inside(ii, jj)) { x.setpos(ii, jj, kk, tile, i0, j0); a = LDG(aout.v + x.off(aout.nk, 0, 0, 0)); }
+        s.oad[c] = a;
+      }
+    } else if (ph == 1) {
+      // reverse of S_a2b_q2: the adjoints of qx, qy and qe where the last phase needs them
+      TCtxLinAD<S_a2b_q2> x; x.g = g; x.m = m; x.oad[0] = s.oad; x.ob[0] = bu;
+      auto fast = [&](int ii, int jj) {    // (S_a2b_q2::adjoint: uniform weights, qe not read)
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        return x.i >= 5 && x.i <= g.npx - 5 && x.j >= 5 && x.j <= g.npy - 5 && x.il - 1 >= g.is && x.il + 2 <= g.ie + 1 && x.jl - 1 >= g.js && x.jl + 2 <= g.je + 1;
+      };
+      for (int c = tid; c < bqx.n(); c += NTHR) {
+        const int ii = bqx.x0 + c % bqx.w, jj = bqx.y0 + c / bqx.w;
+        double a = 0.0;
+        if (inside(ii, jj)) {
+          if (fast(ii, jj)) {
+            const double* ap = s.oad + bu.idx(ii, jj);
+            a = 0.5 * (a2b::a2 * (ap[-UW] + ap[2 * UW]) + a2b::a1 * (ap[0] + ap[UW]));
+          } else { x.acc = 0.0; TileLinGather<S_a2b_q2, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); a = x.acc; }
+        }
+        s.qx_ad[c] = a;
+      }
+      for (int c = tid; c < bqy.n(); c += NTHR) {
+        const int ii = bqy.x0 + c % bqy.w, jj = bqy.y0 + c / bqy.w;
+        double a = 0.0;
+        if (inside(ii, jj)) {
+          if (fast(ii, jj)) {
+            const double* ap = s.oad + bu.idx(ii, jj);
+            a = 0.5 * (a2b::a2 * (ap[-1] + ap[2]) + a2b::a1 * (ap[0] + ap[1]));
+          } else { x.acc = 0.0; TileLinGather<S_a2b_q2, 1>::run(x, {0}, ii, jj, kk, tile, i0, j0); a = x.acc; }
+        }
+        s.qy_ad[c] = a;
+      }
+      for (int c = tid; c < bqe.n(); c += NTHR) {
+        const int ii = bqe.x0 + c % bqe.w, jj = bqe.y0 + c / bqe.w;
+        double a = 0.0;
+        if (inside(ii, jj)) {
+          x.setpos(ii, jj, kk, tile, i0, j0);
+          if (x.i == 1 || x.i == g.npx || x.j == 1 || x.j == g.npy) {     // qe only exists on the tile boundary
+            x.acc = 0.0; TileLinGather<S_a2b_q2, 2>::run(x, {0}, ii, jj, kk, tile, i0, j0); a = x.acc;
+          }
+        }
+        s.qe_ad[c] = a;
+      }
+    } else {
+      const int ii = ii0 + tid % TX, jj = jj0 + tid / TX;
+      if (!inside(ii, jj) || !qin_ad.v) return;
+      double acc = 0.0;
+      CtxBase xb; xb.g = g; xb.setpos(ii, jj, kk, tile, i0, j0);
+      {   // reverse of qx = S_a2b_q1<0>(qin)  (fast path: S_a2b_q1::adjoint)
+        const bool fast = xb.i - 1 >= 4 && xb.i + 2 <= g.npx - 3 && xb.il - 1 >= g.is && xb.il + 2 <= g.ie + 1 &&
+                          xb.jl >= g.js - 2 && xb.jl <= g.je + 2 && xb.j >= 1 && xb.j <= g.npy - 1;
+        if (fast) { const double* ap = s.qx_ad + bqx.idx(ii, jj); acc += a2b::b2 * (ap[-1] + ap[2]) + a2b::b1 * (ap[0] + ap[1]); }
+        else {
+          TCtxLinAD<S_a2b_q1<0>> x; x.g = g; x.m = m; x.oad[0] = s.qx_ad; x.ob[0] = bqx; x.acc = 0.0;
+          TileLinGather<S_a2b_q1<0>, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); acc += x.acc;
+        }
+      }
+      {
+        const bool fast = xb.j - 1 >= 4 && xb.j + 2 <= g.npy - 3 && xb.jl - 1 >= g.js && xb.jl + 2 <= g.je + 1 &&
+                          xb.il >= g.is - 2 && xb.il <= g.ie + 2 && xb.i >= 1 && xb.i <= g.npx - 1;
+        if (fast) { const double* ap = s.qy_ad + bqy.idx(ii, jj); acc += a2b::b2 * (ap[-TX] + ap[2 * TX]) + a2b::b1 * (ap[0] + ap[TX]); }
+        else {
+          TCtxLinAD<S_a2b_q1<1>> x; x.g = g; x.m = m; x.oad[0] = s.qy_ad; x.ob[0] = bqy; x.acc = 0.0;
+          TileLinGather<S_a2b_q1<1>, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); acc += x.acc;
+        }
+      }
+      if (!(xb.i > 3 && xb.i < g.npx - 3 && xb.j > 3 && xb.j < g.npy - 3)) {      // (S_a2b_edge::adjoint: boundary outputs read at most two cells inwards)
+        TCtxLinAD<S_a2b_edge> x; x.g = g; x.m = m; x.oad[0] = s.qe_ad; x.ob[0] = bqe; x.acc = 0.0;
+        TileLinGather<S_a2b_edge, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); acc += x.acc;
+      }
+      if (acc != 0.0) { xb.setpos(ii, jj, kk, tile, i0, j0); qin_ad.v[xb.off(qin_ad.nk, 0, 0, 0)] += acc; }
+    }
+  }
+};
+}  // namespace ftp
+
 int build_a2b_ord4(Program& P, Mosaic& mo, int qin, int nk, const std::string& tag) {
   (void)mo;
   auto nm = [&](const char* s) { return tag + "." + s; };
+  const char* fe = getenv("FV3LM_FUSED_A2B");
+  if (fe && atoi(fe) != 0) {
+    if (P.vals[qin].nk != nk) throw std::runtime_error("fused a2b_ord4: the field must have the launch's number of levels");
+    int qout = P.val(nm("qout"), nk);
+    Op op; op.name = "a2b_fused"; op.in = {qin}; op.out = {qout}; op.nk_launch = nk; op.tl_only = P.tl_only; op.variant = P.variant;
+    op.run = [](Program& P, Op& o, int mode) {
+      const Geom& g = P.dv->g;
+      const Value &vi = P.vals[o.in[0]], &vo = P.vals[o.out[0]];
+      if (mode == MODE_AD) {
+        if (!vi.active || !vo.active || !vo.pert) return;
+        ftp::KernA2bRev k{}; k.g = g; k.m = P.dv->m; k.nk = o.nk_launch;
+        k.aout = ftp::adj_in(vo); k.qin_ad = ftp::adj_out(vi);
+        ftp::launch_tile(k, g.NX, g.NY, g.ntile * o.nk_launch);
+      } else if (mode == MODE_TL && vi.active && vi.pert) {
+        ftp::KernA2b<Dual> k{}; k.g = g; k.m = P.dv->m; k.nk = o.nk_launch; k.qin = ftp::fld(vi, true); k.qout = ftp::ofld(vo, true);
+        ftp::launch_tile(k, g.NX, g.NY, g.ntile * o.nk_launch);
+      } else {
+        ftp::KernA2b<double> k{}; k.g = g; k.m = P.dv->m; k.nk = o.nk_launch; k.qin = ftp::fld(vi, false); k.qout = ftp::ofld(vo, false);
+        ftp::launch_tile(k, g.NX, g.NY, g.ntile * o.nk_launch);
+      }
+    };
+    P.ops.push_back(op);
+    return qout;
+  }
   int qx = P.val(nm("qx"), nk), qy = P.val(nm("qy"), nk), qe = P.val(nm("qe"), nk), qout = P.val(nm("qout"), nk);
   P.add<S_a2b_q1<0>>("a2b_qx", {0}, {qin}, {qx}, nk);
   P.add<S_a2b_q1<1>>("a2b_qy", {0}, {qin}, {qy}, nk);

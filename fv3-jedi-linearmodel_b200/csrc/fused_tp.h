@@ -442,6 +442,70 @@ template <int DIN, bool AVG> struct KernTpRev {
   }
 };
 
+
+// =====================================================================================================================
+// Generic pieces for fusing a chain of stencil STAGES (engine.h) in a tile: a context whose inputs / outputs are shared-memory
+// tiles or global fields, so that a stage's own eval() runs unchanged, and the gather-form reverse of a LINEAR stage on tiles.
+// =====================================================================================================================
+struct TRef { const double* v; const double* d; Box b; };    // input tile (v == nullptr: the input is the global field gi[f])
+struct TOut { double* v; double* d; Box b; };                // output tile (v == nullptr: not staged)
+template <class TT, int NI, int NO> struct TCtx : CtxBase {
+  using T = TT;
+  static constexpr int mode = std::is_same<TT, double>::value ? 0 : 1;
+  TRef ti[NI]; Fld gi[NI]; TOut to[NO]; OFld go[NO];
+  DEV T in(int f, int di = 0, int dj = 0, int dk = 0) const {
+    if (ti[f].v) {
+#ifdef FV3LM_HOST_EMU
+      if (!ti[f].b.has(ii + di, jj + dj)) throw std::runtime_error("fv3lm emu: tile read outside its box");
+#endif
+      return Num<TT>::lds(ti[f].v, ti[f].d, ti[f].b.idx(ii + di, jj + dj));
+    }
+    return Num<TT>::ld(gi[f], off(gi[f].nk, di, dj, dk));
+  }
+  DEV void out(int o, T v) const {
+    if (to[o].v) Num<TT>::sts(to[o].v, to[o].d, to[o].b.idx(ii, jj), v);
+    if (go[o].v) Num<TT>::st(go[o], off(go[o].nk, 0, 0, 0), v);
+  }
+};
+
+// one seeded evaluation of a LINEAR stage S at an output cell: the inputs are zeros, the tap (F, di, dj) carries the seed, the
+// output adjoints come from tiles.  (The coefficients of a linear stage do not depend on its inputs.)
+template <class S> struct TCtxLinAD : CtxBase {
+  using T = DualN<1>;
+  static constexpr int mode = 2;
+  const double* oad[S::NO]; Box ob[S::NO];
+  int sf, sdi, sdj;
+  double acc;
+  DEV T in(int f, int di = 0, int dj = 0, int = 0) const {
+    T r(0.0);
+    if (f == sf && di == sdi && dj == sdj) r.d[0] = 1.0;
+    return r;
+  }
+  DEV void out(int o, const T& v) {
+    if (oad[o] && ob[o].has(ii, jj)) {
+      const double a = oad[o][ob[o].idx(ii, jj)];
+      if (a != 0.0) acc += v.d[0] * a;
+    }
+  }
+};
+// adjoint of input F at the cell (ii, jj): sum over the taps of F of d out(cell - tap) / d in * out_ad(cell - tap)
+template <class S, int F, int n = 0> struct TileLinGather {
+  template <class C> DEV static void run(C& x, const typename S::P& p, int ii, int jj, int kk, int tile, int i0, int j0) {
+    if constexpr (n < S::NT) {
+      constexpr Tap t = S::taps[n];
+      if constexpr (t.f == F) {
+        const int oi = ii - t.di, oj = jj - t.dj;
+        if (oi >= 0 && oi < x.g.NX && oj >= 0 && oj < x.g.NY) {
+          x.sf = F; x.sdi = t.di; x.sdj = t.dj;
+          x.setpos(oi, oj, kk, tile, i0, j0);
+          S::eval(x, p);
+        }
+      }
+      TileLinGather<S, F, n + 1>::run(x, p, ii, jj, kk, tile, i0, j0);
+    }
+  }
+};
+
 inline Fld fld(const Value& v, bool tl) { return Fld{v.traj, (tl && v.active) ? v.pert : nullptr, v.nk}; }
 inline OFld ofld(const Value& v, bool tl) { return OFld{v.traj, (tl && v.active) ? v.pert : nullptr, v.nk}; }
 

@@ -86,8 +86,8 @@ def _run_dsw(emu, hydrostatic, sponge, hord=2, d_con=0.0, pert=None, traj_over=N
     return check_module(h, "d_sw", N, K, f, act, outs, fn, p, rng, tol=2e-12, dot_tol=1e-12)
 
 
-def _run_a2b(emu):
-    N, K = 12, 2
+def _run_a2b(emu, N=12):
+    K = 2
     rng = np.random.default_rng(3)
     f = {"qin": rnd(rng, N, K)}
     g = ograd(N)

@@ -9,6 +9,8 @@ import common
 from common import metrics, handle, rnd, relerr, region
 import test_tp_core
 import test_step_api
+import test_d_sw
+import test_decomp
 
 TOL = 1e-13     # identical expressions; the device build may contract multiply-adds differently in the two kernels
 
@@ -177,4 +179,44 @@ def test_fused_vs_chain_trajectory_schemes_gpu(monkeypatch):
 
 @pytest.mark.gpu
 def test_fused_step_gpu(fused):
+    print(test_step_api._run(False, nonhydro=True))
+
+
+# ---- a2b_ord4 as one tile kernel per direction (FV3LM_FUSED_A2B=1, csrc/a2b.cu: KernA2b / KernA2bRev) ----------------------
+@pytest.fixture
+def fused_all(monkeypatch):
+    common._handles.clear()
+    monkeypatch.setenv("FV3LM_FUSED_TP", "2")
+    monkeypatch.setenv("FV3LM_FUSED_A2B", "1")
+    yield
+    common._handles.clear()
+
+
+@pytest.mark.parametrize("N", [12, 40])
+def test_fused_a2b_vs_oracle_emu(fused_all, N):
+    """NL, TL (= the operator itself), AD (= its transpose) against the oracle + dot-product test; N = 40 spans two tiles in x"""
+    test_d_sw._run_a2b(True, N)
+
+
+@pytest.mark.parametrize("case", ["a2b_ord4", "fv_tp_2d", "step_nonhydro"])
+def test_fused_layout_2x2_emu(fused_all, case):
+    """tile kernels on layout(2, 2) sub-domains (cube-edge cases keyed on the tile-global index, 24 sub-domains in one launch)"""
+    print(test_decomp._layout(case, True, (2, 2)))
+
+
+def test_fused_all_step_emu(fused_all):
+    print(test_step_api._run(True, nonhydro=True))
+
+
+def test_fused_all_step_hydro_emu(fused_all):
+    print(test_step_api._run(True, nonhydro=False))
+
+
+@pytest.mark.gpu
+def test_fused_a2b_vs_oracle_gpu(fused_all):
+    test_d_sw._run_a2b(False, 40)
+
+
+@pytest.mark.gpu
+def test_fused_all_step_gpu(fused_all):
     print(test_step_api._run(False, nonhydro=True))

@@ -14,6 +14,13 @@ python bench.py --kernel-only --turbulence --steps 5 --warmup 3 > gpurun_out/${T
 rc=$?; cat gpurun_out/${T}_side_turbulence.json
 python bench.py --kernel-only --q-split-dynamic 3 --steps 3 --warmup 3 > gpurun_out/${T}_side_qsplit0.json 2> gpurun_out/${T}_side_q.err
 cat gpurun_out/${T}_side_qsplit0.json
+# 5. fv_tp_2d as shared-memory-tile kernels (csrc/fused_tp.h; built at the end of round 1, CPU-emulation parity only):
+#    level 0 = stage chain (the default bench line above), 1 = fused forward sweeps, 2 = fused forward + reverse kernels.
+#    Same workload, kernel-only (data resident), then the per-op table of the best level for the roofline of KernTpRev / KernTpB.
+for L in 1 2; do
+  FV3LM_FUSED_TP=$L python bench.py --kernel-only --steps 5 --warmup 3 > gpurun_out/${T}_fused_tp_level${L}.json 2> gpurun_out/${T}_fused_tp_level${L}.err
+  echo "fused level $L rc=$?"; cat gpurun_out/${T}_fused_tp_level${L}.json
+done
 if [ $rc -eq 0 ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:KTurbSolve -c 2 \
       -o gpurun_out/${T}_KTurbSolve_c180 python bench.py --kernel-only --turbulence --steps 1 --warmup 1 > gpurun_out/${T}_ncu_turb.log 2>&1
