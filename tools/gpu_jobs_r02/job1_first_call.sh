@@ -16,11 +16,14 @@ python bench.py --kernel-only --q-split-dynamic 3 --steps 3 --warmup 3 > gpurun_
 cat gpurun_out/${T}_side_qsplit0.json
 # 5. fv_tp_2d as shared-memory-tile kernels (csrc/fused_tp.h; built at the end of round 1, CPU-emulation parity only):
 #    level 0 = stage chain (the default bench line above), 1 = fused forward sweeps, 2 = fused forward + reverse kernels.
-#    Same workload, kernel-only (data resident), then the per-op table of the best level for the roofline of KernTpRev / KernTpB.
+#    Same workload, kernel-only (data resident); then the complete bench line + per-op table with every tile kernel on
+#    (FV3LM_FUSED_TP=2 FV3LM_FUSED_A2B=1; the line carries the dot-product test at the bench workload).
 for L in 1 2; do
   FV3LM_FUSED_TP=$L python bench.py --kernel-only --steps 5 --warmup 3 > gpurun_out/${T}_fused_tp_level${L}.json 2> gpurun_out/${T}_fused_tp_level${L}.err
   echo "fused level $L rc=$?"; cat gpurun_out/${T}_fused_tp_level${L}.json
 done
+FV3LM_FUSED_TP=2 FV3LM_FUSED_A2B=1 python bench.py --no-cpu --profile-out gpurun_out/${T}_profile_fused_all.txt > gpurun_out/${T}_bench_fused_all.json 2> gpurun_out/${T}_bench_fused_all.err
+echo "fused all rc=$?"; cat gpurun_out/${T}_bench_fused_all.json
 if [ $rc -eq 0 ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:KTurbSolve -c 2 \
       -o gpurun_out/${T}_KTurbSolve_c180 python bench.py --kernel-only --turbulence --steps 1 --warmup 1 > gpurun_out/${T}_ncu_turb.log 2>&1
