@@ -226,6 +226,15 @@ template <int DIR, class X> DEV double ppm_coef(const X& x, double c, int ord, i
     return d == -1 ? 2.0 / 6.0 + 0.5 * c + c2 : d == 0 ? 5.0 / 6.0 - 0.5 * c - 2.0 * c2 : d == 1 ? -1.0 / 6.0 + c2 : 0.0;
   }
   using S = S_ppm<DIR>;
+  {
+    // regular faces: the three edge values involved use the uniform weights (p2, p1, p1, p2) -- no metric loads, no edge tests
+    const int ia = DIR == 0 ? x.i : x.j, np = DIR == 0 ? x.g.npx : x.g.npy;
+    if (ia >= 4 && ia <= np - 3) {
+      auto W = [](int n) { return (n == 0 || n == 3) ? tp::p2 : ((n == 1 || n == 2) ? tp::p1 : 0.0); };
+      if (c > 0.0) return (d == -1 ? 1.0 + (1.0 - c) * (2.0 * c - 1.0) : 0.0) + (1.0 - c) * (1.0 - c) * W(d + 2) - (1.0 - c) * c * W(d + 3);
+      return (d == 0 ? 1.0 - (1.0 + c) * (1.0 + 2.0 * c) : 0.0) + (1.0 + c) * (1.0 + c) * W(d + 2) + (1.0 + c) * c * W(d + 1);
+    }
+  }
   if (c > 0.0) {
     const double dqt = 1.0 + (1.0 - c) * (2.0 * c - 1.0), dal0 = (1.0 - c) * (1.0 - c), dalm = -(1.0 - c) * c;
     return (d == -1 ? dqt : 0.0) + dal0 * S::al_w(x, 0, d + 2) + dalm * S::al_w(x, -1, d + 3);
