@@ -8,18 +8,20 @@ cd "$(dirname "$0")/csrc"
 SRCS="engine.cu comm.cu mosaic.cu modules.cu csw.cu dsw.cu a2b.cu dyn.cu fvdyn.cu nh.cu capi.cu step_api.cu turb.cu"
 OUT=..
 OBJ=/tmp/fv3lm_obj_$(id -u)
+DEFS=""
+if [ -n "$FV3LM_TILE_TY" ]; then DEFS="-DFV3LM_TILE_TY=$FV3LM_TILE_TY"; fi    # tile height of the shared-memory-tile kernels (csrc/fused_tp.h)
 mkdir -p $OBJ
 pids=""
 if [ "$1" != "emu" ]; then
   for f in $SRCS; do
     nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
-         --expt-relaxed-constexpr -diag-suppress 177 -c $f -o $OBJ/cuda_${f%.cu}.o &
+         --expt-relaxed-constexpr -diag-suppress 177 $DEFS -c $f -o $OBJ/cuda_${f%.cu}.o &
     pids="$pids $!"
   done
 fi
 if [ "$1" != "cuda" ]; then
   for f in $SRCS; do
-    g++ -std=c++17 -O2 -fPIC -DFV3LM_HOST_EMU -x c++ -c $f -o $OBJ/emu_${f%.cu}.o &
+    g++ -std=c++17 -O2 -fPIC -DFV3LM_HOST_EMU $DEFS -x c++ -c $f -o $OBJ/emu_${f%.cu}.o &
     pids="$pids $!"
   done
 fi

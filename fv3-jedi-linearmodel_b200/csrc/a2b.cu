@@ -228,14 +228,16 @@ template <class TT> struct KernA2b {
         S_a2b_edge::eval(x, {0});
       }
     } else {
-      const int ii = ii0 + tid % TX, jj = jj0 + tid / TX;
-      if (!inside(ii, jj)) return;
       TCtx<TT, 3, 1> x; x.g = g; x.m = m;
       x.ti[0] = TRef{s.qx.v, s.qx.d, bqx}; x.ti[1] = TRef{s.qy.v, s.qy.d, bqy}; x.ti[2] = TRef{s.qe.v, s.qe.d, bqe};
       for (int f = 0; f < 3; f++) x.gi[f] = Fld{nullptr, nullptr, 1};
       x.to[0] = TOut{nullptr, nullptr, bq}; x.go[0] = qout;
-      x.setpos(ii, jj, kk, tile, i0, j0);
-      S_a2b_q2::eval(x, {0});
+      for (int c = tid; c < TX * TY; c += NTHR) {
+        const int ii = ii0 + c % TX, jj = jj0 + c / TX;
+        if (!inside(ii, jj)) continue;
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        S_a2b_q2::eval(x, {0});
+      }
     }
   }
 };
@@ -299,7 +301,7 @@ struct KernA2bRev {
         s.qe_ad[c] = a;
       }
     } else {
-      const int ii = ii0 + tid % TX, jj = jj0 + tid / TX;
+      auto own = [&](int ii, int jj) {
       if (!inside(ii, jj) || !qin_ad.v) return;
       double acc = 0.0;
       CtxBase xb; xb.g = g; xb.setpos(ii, jj, kk, tile, i0, j0);
@@ -326,6 +328,8 @@ struct KernA2bRev {
         TileLinGather<S_a2b_edge, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); acc += x.acc;
       }
       if (acc != 0.0) { xb.setpos(ii, jj, kk, tile, i0, j0); qin_ad.v[xb.off(qin_ad.nk, 0, 0, 0)] += acc; }
+      };
+      for (int c = tid; c < TX * TY; c += NTHR) own(ii0 + c % TX, jj0 + c / TX);
     }
   }
 };

@@ -19,7 +19,12 @@
 namespace fv3lm {
 namespace ftp {
 
-constexpr int TX = 32, TY = 8, NTHR = TX * TY;
+// a block of NTHR threads owns TX x TY cells (every phase is a loop over its cell set, so the tile height can be tuned
+// independently of the block size: a taller tile has less footprint overhead, a flatter one more blocks per SM)
+#ifndef FV3LM_TILE_TY
+#define FV3LM_TILE_TY 16     // build.sh passes -DFV3LM_TILE_TY=$FV3LM_TILE_TY for A/B runs (8: 2.1 field cells loaded and 1.8 inner fluxes per owned cell, 16: 1.6 and 1.4)
+#endif
+constexpr int TX = 32, TY = FV3LM_TILE_TY, NTHR = 256;
 constexpr int QW = TX + 6, QH = TY + 6;      // tile of the transported field with the PPM footprint (-3 .. +2) on both axes
 
 struct Fld { const double* v; const double* d; int nk; };
@@ -91,12 +96,14 @@ template <class TT, bool FULL> struct KernTpA {
         N::sts(s.qi.v, s.qi.d, c, (qq * x.M(x.m.area) + f0 - f1) / N::ld(ray, x.off(ray.nk, 0, 0, 0)));
       }
     } else {                       // fx_ou = xppm(q_i, crx) on (is:ie+1, js:je)
-      const int ii = ii0 + tid % TX, jj = jj0 + tid / TX;
-      if (ii >= g.NX || jj >= g.NY) return;
-      x.setpos(ii, jj, kk, tile, i0, j0);
-      if (!x.in_rect(is, ie + 1, js, je)) return;
-      x.sv = s.qi.v; x.sd = s.qi.d; x.sw = QW; x.sp = (jj - jj0) * QW + (ii - ii0 + 3);
-      N::st(fxo, x.off(fxo.nk, 0, 0, 0), tp::ppm_flux<0, FULL>(x, 0, N::ld(crx, x.off(crx.nk, 0, 0, 0)), ord.v[kk]));
+      for (int c = tid; c < TX * TY; c += NTHR) {
+        const int ii = ii0 + c % TX, jj = jj0 + c / TX;
+        if (ii >= g.NX || jj >= g.NY) continue;
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        if (!x.in_rect(is, ie + 1, js, je)) continue;
+        x.sv = s.qi.v; x.sd = s.qi.d; x.sw = QW; x.sp = (jj - jj0) * QW + (ii - ii0 + 3);
+        N::st(fxo, x.off(fxo.nk, 0, 0, 0), tp::ppm_flux<0, FULL>(x, 0, N::ld(crx, x.off(crx.nk, 0, 0, 0)), ord.v[kk]));
+      }
     }
   }
 };
@@ -144,7 +151,7 @@ template <class TT, bool FULL> struct KernTpB {
         N::sts(s.qj.v, s.qj.d, c, (qq * x.M(x.m.area) + f0 - f1) / N::ld(rax, x.off(rax.nk, 0, 0, 0)));
       }
     } else {                       // fy_ou = yppm(q_j, cry) on (is:ie, js:je+1); the two averages (tp_core_tlm.F90:2268-2313)
-      const int ii = ii0 + tid % TX, jj = jj0 + tid / TX;
+      auto own = [&](int ii, int jj) {
       if (ii >= g.NX || jj >= g.NY) return;
       x.setpos(ii, jj, kk, tile, i0, j0);
       if (x.in_rect(is, ie, js, je + 1)) {
@@ -156,6 +163,8 @@ template <class TT, bool FULL> struct KernTpB {
         const TT fx2 = N::lds(s.fx.v, s.fx.d, (jj - jj0 + 3) * FW + (ii - ii0));
         N::st(fx, x.off(fx.nk, 0, 0, 0), 0.5 * (N::ld(fxo, x.off(fxo.nk, 0, 0, 0)) + fx2) * N::ld(mx, x.off(mx.nk, 0, 0, 0)));
       }
+      };
+      for (int c = tid; c < TX * TY; c += NTHR) own(ii0 + c % TX, jj0 + c / TX);
     }
   }
 };
@@ -163,7 +172,7 @@ template <class TT, bool FULL> struct KernTpB {
 #ifndef FV3LM_HOST_EMU
 template <class K> GLOBAL void __launch_bounds__(NTHR) kern_tile(const __grid_constant__ K k) {
   __shared__ typename K::Smem s;
-  const int tid = threadIdx.y * TX + threadIdx.x;
+  const int tid = threadIdx.x;
 #pragma unroll
   for (int ph = 0; ph < K::NPH; ph++) {
     k.phase(ph, tid, blockIdx.x, blockIdx.y, blockIdx.z, s);
@@ -172,7 +181,7 @@ template <class K> GLOBAL void __launch_bounds__(NTHR) kern_tile(const __grid_co
 }
 template <class K> void launch_tile(const K& k, int nx, int ny, int nz) {
   if (nz <= 0) return;
-  dim3 b(TX, TY, 1), gr((nx + TX - 1) / TX, (ny + TY - 1) / TY, nz);
+  dim3 b(NTHR, 1, 1), gr((nx + TX - 1) / TX, (ny + TY - 1) / TY, nz);
   kern_tile<K><<<gr, b, 0, dev::stream()>>>(k);
   dev::launches++;
 }
@@ -379,7 +388,7 @@ template <int DIN, bool AVG> struct KernTpRev {
         s.Fi_ad[c] = a;
       }
     } else if (ph == 4) {          // everything the block's own cells accumulate
-      const int ii = ii0 + tid % TX, jj = jj0 + tid / TX;
+      auto own = [&](int ii, int jj) {
       if (!inside(ii, jj)) return;
       x.setpos(ii, jj, kk, tile, i0, j0);
       const bool in_i = rect_i(x), in_m = rect_m(x), in_o = rect_o(x);
@@ -447,6 +456,8 @@ template <int DIN, bool AVG> struct KernTpRev {
         x.setpos(ii, jj, kk, tile, i0, j0);
         if (aq != 0.0) q_ad.v[x.off(q_ad.nk, 0, 0, 0)] += aq;
       }
+      };
+      for (int c = tid; c < TX * TY; c += NTHR) own(ii0 + c % TX, jj0 + c / TX);
     }
   }
 };
