@@ -212,6 +212,12 @@ def test_fused_all_step_hydro_emu(fused_all):
     print(test_step_api._run(True, nonhydro=False))
 
 
+def test_fused_multirank_gloo(fused_all):
+    """two ranks over gloo (halo exchange + adjoint halo accumulation around the tile kernels): sharded = single-rank results"""
+    import test_multirank
+    test_multirank._check(2, True)
+
+
 @pytest.mark.gpu
 def test_fused_a2b_vs_oracle_gpu(fused_all):
     test_d_sw._run_a2b(False, 40)
