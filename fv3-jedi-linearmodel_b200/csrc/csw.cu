@@ -1,6 +1,7 @@
 // c_sw program builder (model/sw_core_nlm.F90:77-486)
 #include "stages_csw.h"
 #include "modules.h"
+#include "fused_chain.h"
 
 namespace fv3lm {
 
@@ -39,10 +40,21 @@ CswOut build_c_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
   P.add<S_cupd>("cupd", {nh}, {delp, pt, w, fx1, fx, fx2, fy1, fy, fy2}, {o.delpc, o.ptc, o.wc}, nk);
   // KE, absolute vorticity, C-grid wind update
   int ke = P.val(nm("ke"), nk), vort = P.val(nm("vort"), nk);
+  o.uc = P.val(nm("uc"), nk); o.vc = P.val(nm("vc"), nk);
+  // FV3LM_FUSED_CHAIN=1 (opt-in until timed on a B200): in forward sweeps the three stages run as one tile kernel with ke and
+  // vort in shared memory (fused_chain.h); adjoint runs keep the stage-by-stage ops
+  const char* fe = getenv("FV3LM_FUSED_CHAIN");
+  const bool fused = fe && atoi(fe) != 0;
+  const int var0 = P.variant;
+  if (fused) P.variant = VAR_AD;
   P.add<S_cke>("cke", {dt2}, {o.ua, o.va, uc0, vc0, u, v}, {ke}, nk);
   P.add<S_cvort>("cvort", {0}, {uc0, vc0}, {vort}, nk);
-  o.uc = P.val(nm("uc"), nk); o.vc = P.val(nm("vc"), nk);
   P.add<S_cwind>("cwind", {dt2}, {uc0, vc0, u, v, vort, ke}, {o.uc, o.vc}, nk);
+  P.variant = var0;
+  if (fused)
+    ftp::add_chain<S_cke, S_cvort, S_cwind>(P, "csw_tail_fused", ftp::ppack_of<S_cke, S_cvort, S_cwind>(S_cke::P{dt2}, S_cvort::P{0}, S_cwind::P{dt2}),
+                                            {{o.ua, o.va, uc0, vc0, u, v}, {uc0, vc0}, {uc0, vc0, u, v, vort, ke}}, {{ke}, {vort}, {o.uc, o.vc}},
+                                            {o.uc, o.vc}, nk);
   return o;
 }
 

@@ -1,6 +1,7 @@
 // d_sw program builder (model/sw_core_nlm.F90:492-1545) and the shared del-n flux builder.
 #include "stages_dsw.h"
 #include "modules.h"
+#include "fused_chain.h"
 
 namespace fv3lm {
 
@@ -74,12 +75,26 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
   DswOut o;
   // contravariant winds, Courant numbers, flux areas
   int ut0 = P.val(nm("ut0"), nk), vt0 = P.val(nm("vt0"), nk), ut = P.val(nm("ut"), nk), vt = P.val(nm("vt"), nk);
-  P.add<S_dwind1>("dwind1", {prm.dt}, {uc, vc}, {ut0, vt0}, nk);
-  P.add<S_dwind2>("dwind2", {0}, {ut0, vt0, uc, vc}, {ut, vt}, nk);
   o.crx = P.val(nm("crx"), nk); o.xfx = P.val(nm("xfx"), nk); o.cry = P.val(nm("cry"), nk); o.yfx = P.val(nm("yfx"), nk);
-  P.add<S_dcourant>("dcourant", {prm.dt}, {ut, vt}, {o.crx, o.xfx, o.cry, o.yfx}, nk);
   int ra_x = P.val(nm("ra_x"), nk), ra_y = P.val(nm("ra_y"), nk);
-  P.add<S_ra>("ra", {0}, {o.xfx, o.yfx}, {ra_x, ra_y}, nk);
+  {
+    // FV3LM_FUSED_CHAIN=1 (opt-in until timed on a B200): forward sweeps run the four stages as one tile kernel (fused_chain.h),
+    // ut0 / vt0 stay in shared memory; adjoint runs keep the stage-by-stage ops
+    const char* fe = getenv("FV3LM_FUSED_CHAIN");
+    const bool fused = fe && atoi(fe) != 0;
+    const int var0 = P.variant;
+    if (fused) P.variant = VAR_AD;
+    P.add<S_dwind1>("dwind1", {prm.dt}, {uc, vc}, {ut0, vt0}, nk);
+    P.add<S_dwind2>("dwind2", {0}, {ut0, vt0, uc, vc}, {ut, vt}, nk);
+    P.add<S_dcourant>("dcourant", {prm.dt}, {ut, vt}, {o.crx, o.xfx, o.cry, o.yfx}, nk);
+    P.add<S_ra>("ra", {0}, {o.xfx, o.yfx}, {ra_x, ra_y}, nk);
+    P.variant = var0;
+    if (fused)
+      ftp::add_chain<S_dwind1, S_dwind2, S_dcourant, S_ra>(
+          P, "dsw_head_fused", ftp::ppack_of<S_dwind1, S_dwind2, S_dcourant, S_ra>(S_dwind1::P{prm.dt}, S_dwind2::P{0}, S_dcourant::P{prm.dt}, S_ra::P{0}),
+          {{uc, vc}, {ut0, vt0, uc, vc}, {ut, vt}, {o.xfx, o.yfx}}, {{ut0, vt0}, {ut, vt}, {o.crx, o.xfx, o.cry, o.yfx}, {ra_x, ra_y}},
+          {ut, vt, o.crx, o.xfx, o.cry, o.yfx, ra_x, ra_y}, nk);
+  }
   // mass
   // one transport site (:1664-1682): q is transported once when both sides use the same scheme, else twice
   auto tp_site = [&](int q, int mfx, int mfy, int mass, bool same, const LevOrd& ho_p, const LevOrd& no_p, const LevD& da_p,

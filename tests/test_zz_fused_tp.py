@@ -11,6 +11,7 @@ import test_tp_core
 import test_step_api
 import test_d_sw
 import test_decomp
+import test_c_sw
 
 TOL = 1e-13     # identical expressions; the device build may contract multiply-adds differently in the two kernels
 
@@ -188,6 +189,7 @@ def fused_all(monkeypatch):
     common._handles.clear()
     monkeypatch.setenv("FV3LM_FUSED_TP", "2")
     monkeypatch.setenv("FV3LM_FUSED_A2B", "1")
+    monkeypatch.setenv("FV3LM_FUSED_CHAIN", "1")
     yield
     common._handles.clear()
 
@@ -226,3 +228,22 @@ def test_fused_a2b_vs_oracle_gpu(fused_all):
 @pytest.mark.gpu
 def test_fused_all_step_gpu(fused_all):
     print(test_step_api._run(False, nonhydro=True))
+
+
+# ---- automatic tile fusion of patch-free stage chains (FV3LM_FUSED_CHAIN=1, csrc/fused_chain.h): the tail of c_sw
+# (cke, cvort, cwind) and the head of d_sw (dwind1, dwind2, dcourant, ra) in forward sweeps; `fused_all` switches it on as well ----
+@pytest.mark.parametrize("case", ["c_sw", "d_sw", "dyn_core_nh_two_sided"])
+def test_fused_chain_modules_emu(fused_all, case):
+    """module level against the oracle (NL, TL, AD through the stage ops, dot product), whole tiles"""
+    print(test_decomp.CASES[case](True))
+
+
+@pytest.mark.parametrize("case", ["c_sw", "d_sw"])
+def test_fused_chain_layout_2x2_emu(fused_all, case):
+    print(test_decomp._layout(case, True, (2, 2)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["c_sw", "d_sw"])
+def test_fused_chain_modules_gpu(fused_all, case):
+    print(test_decomp.CASES[case](False))

@@ -5,7 +5,7 @@
 #   3. side measurements that have never been timed: tracer sub-cycling (q_split = 0, 3 issued sub-steps) and the
 #      linearised turbulence solves (24 array passes of algorithmic traffic);
 #   4. ncu --set full of the turbulence solve kernel (only after its command exited 0 without ncu).
-# usage: gpurun --timeout 1500 -- 'bash tools/gpu_jobs_r02/job1_first_call.sh'
+# usage: gpurun --timeout 2400 -- 'bash tools/gpu_jobs_r02/job1_first_call.sh'
 mkdir -p gpurun_out
 T=r02a
 ( time python -m pytest tests -m gpu -q -p no:cacheprovider ) > gpurun_out/${T}_pytest_gpu.txt 2>&1; tail -3 gpurun_out/${T}_pytest_gpu.txt
@@ -24,6 +24,16 @@ for L in 1 2; do
 done
 FV3LM_FUSED_TP=2 FV3LM_FUSED_A2B=1 python bench.py --no-cpu --profile-out gpurun_out/${T}_profile_fused_all.txt > gpurun_out/${T}_bench_fused_all.json 2> gpurun_out/${T}_bench_fused_all.err
 echo "fused all rc=$?"; cat gpurun_out/${T}_bench_fused_all.json
+# 6. ncu of the tile kernels (only after the same command exited 0 above): launch list of one TL+AD pair and --set full of the
+#    reverse kernel and kernel B (one launch each is enough: every launch of a kind does the same work)
+if [ -s gpurun_out/${T}_bench_fused_all.json ]; then
+  FV3LM_FUSED_TP=2 FV3LM_FUSED_A2B=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv \
+      --log-file gpurun_out/${T}_ncu_launches_fused.csv python bench.py --kernel-only --steps 1 --warmup 0 > gpurun_out/${T}_ncu_launches_fused.log 2>&1
+  gzip -f gpurun_out/${T}_ncu_launches_fused.csv
+  FV3LM_FUSED_TP=2 FV3LM_FUSED_A2B=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:kern_tile -s 40 -c 12 \
+      -o gpurun_out/${T}_kern_tile_c180 python bench.py --kernel-only --steps 1 --warmup 0 > gpurun_out/${T}_ncu_tile.log 2>&1
+  ls -la gpurun_out/${T}_kern_tile_c180.ncu-rep
+fi
 if [ $rc -eq 0 ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:KTurbSolve -c 2 \
       -o gpurun_out/${T}_KTurbSolve_c180 python bench.py --kernel-only --turbulence --steps 1 --warmup 1 > gpurun_out/${T}_ncu_turb.log 2>&1
