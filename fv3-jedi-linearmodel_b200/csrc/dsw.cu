@@ -132,12 +132,18 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
   P.add<S_dupd>("dupd", {nh, dw_on}, {delp, pt, w, o.fx, o.fy, fpt.fx, fpt.fy, gxw, gyw, fx2w, fy2w}, {o.delp, o.pt, o.w}, nk);
   // kinetic energy
   int vb = P.val(nm("vb"), nk), ub = P.val(nm("ub"), nk), ubf = P.val(nm("ubf"), nk), vbf = P.val(nm("vbf"), nk), ke = P.val(nm("ke"), nk);
-  P.add<S_dvbub>("dvbub", {prm.dt}, {ut, vt, uc, vc}, {vb, ub}, nk);
   auto tpuv = [&](int dir, const LevOrd& ho, int cc, int uu, int out) {   // lean kernels for the linear orders, S_tpuv_nl otherwise
     const bool lin = ord_is_linear(ho, nk);
     if (dir == 1) { if (lin) P.add<S_tpuv<1>>("ytp_v", {ho}, {cc, uu}, {out}, nk); else P.add<S_tpuv_nl<1>>("ytp_v", {ho}, {cc, uu}, {out}, nk); }
     else { if (lin) P.add<S_tpuv<0>>("xtp_u", {ho}, {cc, uu}, {out}, nk); else P.add<S_tpuv_nl<0>>("xtp_u", {ho}, {cc, uu}, {out}, nk); }
   };
+  // FV3LM_FUSED_CHAIN=1: with one linear scheme on both sides the kinetic-energy chain dvbub -> ytp_v, xtp_u -> dke (21 array passes)
+  // runs as one tile kernel in forward sweeps (7 passes; vb, ub and the two transported winds stay in shared memory)
+  const char* fe_ke = getenv("FV3LM_FUSED_CHAIN");
+  const bool fuse_ke = fe_ke && atoi(fe_ke) != 0 && same_ord(prm.hord_mt, pp.hord_mt, nk) && ord_is_linear(prm.hord_mt, nk);
+  const int var_ke = P.variant;
+  if (fuse_ke) P.variant = VAR_AD;     // the stage ops up to and including dke are the adjoint's version of the chain
+  P.add<S_dvbub>("dvbub", {prm.dt}, {ut, vt, uc, vc}, {vb, ub}, nk);
   if (same_ord(prm.hord_mt, pp.hord_mt, nk)) {
     tpuv(1, prm.hord_mt, vb, v, ubf);
     tpuv(0, prm.hord_mt, ub, u, vbf);
@@ -153,6 +159,11 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
     P.add<S_splice>("splice", {0}, {xa, xb}, {vbf}, nk);
   }
   P.add<S_dke>("dke", {prm.dt}, {vb, ubf, ub, vbf, ut, vt, u, v}, {ke}, nk);
+  P.variant = var_ke;
+  if (fuse_ke)
+    ftp::add_chain<S_dvbub, S_tpuv<1>, S_tpuv<0>, S_dke>(
+        P, "dsw_ke_fused", ftp::ppack_of<S_dvbub, S_tpuv<1>, S_tpuv<0>, S_dke>(S_dvbub::P{prm.dt}, S_tpuv<1>::P{prm.hord_mt}, S_tpuv<0>::P{prm.hord_mt}, S_dke::P{prm.dt}),
+        {{ut, vt, uc, vc}, {vb, v}, {ub, u}, {vb, ubf, ub, vbf, ut, vt, u, v}}, {{vb, ub}, {ubf}, {vbf}, {ke}}, {ke}, nk);
   // relative vorticity
   int wk = P.val(nm("wk"), nk);
   P.add<S_relvort>("relvort", {0}, {u, v}, {wk}, nk);
