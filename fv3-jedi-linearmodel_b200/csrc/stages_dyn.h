@@ -137,6 +137,59 @@ struct S_gradp {
       }
     }
   }
+
+  // ---- hand-derived gather adjoint (replaces six multi-seed dual evaluations of the whole stage per cell).  A wind output at
+  // (o, k) reads the B-grid fields at the four corners of its (horizontal edge) x (layer) face:
+  //   a = (o, k)   b = (o + e, k)   c = (o, k+1)   d = (o + e, k+1),   e = (1,0) for u, (0,1) for v
+  //   du = dt (A B + C D) / den,  A = gz_c - gz_b, B = pk_d - pk_a, C = gz_a - gz_d, D = pk_c - pk_b, den = (pk_c - pk_a) + (pk_d - pk_b)
+  //   dn = dt (A (pp_d - pp_a) + C (pp_c - pp_b)) / (dp_a + dp_b)                                           (non-hydrostatic)
+  // so a corner (i, j, k) collects from the u outputs in which it is a, b, c or d and from the four v outputs likewise.
+  static constexpr bool custom_ad = true;
+  template <class K> DEV static void adjoint(const K& kn, int ii, int jj, int kk, int tile, double* acc) {
+    const P& p = kn.p;
+    const Geom& g = kn.g;
+    CtxNL<S_gradp> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in;
+    const int i0 = g.i0[tile], j0 = g.j0[tile];
+    // the winds themselves
+    if (kk < kn.nk_fwd) {
+      x.setpos(ii, jj, kk, tile, i0, j0);
+      if (kn.outad.p[0] && x.in_rect(g.is, g.ie, g.js, g.je + 1)) acc[0] += x.M(x.m.rdx) * kn.outad.p[0][x.off(kn.outad.nk[0], 0, 0, 0)];
+      if (kn.outad.p[1] && x.in_rect(g.is, g.ie + 1, g.js, g.je)) acc[1] += x.M(x.m.rdy) * kn.outad.p[1][x.off(kn.outad.nk[1], 0, 0, 0)];
+    }
+    // role: 0 = a, 1 = b, 2 = c, 3 = d of the output at (oi, oj, ok); isu: a u output (e = (1,0)) or a v output (e = (0,1))
+    auto side = [&](const bool isu, const int role) {
+      const int oi = ii - ((isu && (role & 1)) ? 1 : 0), oj = jj - ((!isu && (role & 1)) ? 1 : 0), ok = kk - (role >> 1);
+      if (oi < 0 || oj < 0 || oi >= g.NX || oj >= g.NY || ok < 0 || ok >= kn.nk_fwd) return;
+      const int o = isu ? 0 : 1;
+      if (!kn.outad.p[o]) return;
+      x.setpos(oi, oj, ok, tile, i0, j0);
+      if (isu ? !x.in_rect(g.is, g.ie, g.js, g.je + 1) : !x.in_rect(g.is, g.ie + 1, g.js, g.je)) return;
+      const double au = kn.outad.p[o][x.off(kn.outad.nk[o], 0, 0, 0)];
+      if (au == 0.0) return;
+      const int ex = isu ? 1 : 0, ey = isu ? 0 : 1;
+      const bool top = ok == 0;
+      const double pa = top ? p.top : x.in(2, 0, 0, 0), pb = top ? p.top : x.in(2, ex, ey, 0), pc = x.in(2, 0, 0, 1), pd = x.in(2, ex, ey, 1);
+      const double ga = x.in(3, 0, 0, 0), gb = x.in(3, ex, ey, 0), gc = x.in(3, 0, 0, 1), gd = x.in(3, ex, ey, 1);
+      const double A = gc - gb, B = pd - pa, C = ga - gd, D = pc - pb, den = (pc - pa) + (pd - pb);
+      const double w = au * (isu ? x.M(x.m.rdx) : x.M(x.m.rdy));
+      const double r = p.dt * w / den, q = (A * B + C * D) / den;
+      // pk: d(num/den)/dx = (dnum/dx - q dden/dx) / den ;  gz: dnum/dx / den
+      const double dpk = role == 0 ? (-A + q) : role == 1 ? (-C + q) : role == 2 ? (C - q) : (A - q);
+      const double dgz = role == 0 ? D : role == 1 ? -B : role == 2 ? B : -D;
+      if (!(top && role < 2)) acc[2] += r * dpk;         // (pk at the top interface is imposed on read, :1689-1693)
+      acc[3] += r * dgz;
+      if (p.nonhydro) {
+        const double qa = top ? 0.0 : x.in(4, 0, 0, 0), qb = top ? 0.0 : x.in(4, ex, ey, 0), qc = x.in(4, 0, 0, 1), qd = x.in(4, ex, ey, 1);
+        const double dsum = x.in(5, 0, 0) + x.in(5, ex, ey);
+        const double s = p.dt * w / dsum;
+        acc[3] += s * (role == 0 ? (qc - qb) : role == 1 ? -(qd - qa) : role == 2 ? (qd - qa) : -(qc - qb));
+        if (!(top && role < 2)) acc[4] += s * (role == 0 ? -A : role == 1 ? -C : role == 2 ? C : A);
+        if (role < 2) acc[5] += -s * (A * (qd - qa) + C * (qc - qb)) / dsum;     // the two dp of the edge share the layer of the output
+      }
+    };
+#pragma unroll
+    for (int role = 0; role < 4; role++) { side(true, role); side(false, role); }
+  }
 };
 
 // out = a + b on a rectangle (flux / Courant-number accumulators, dyn_core/d_sw :913-931)
