@@ -24,6 +24,10 @@ for L in 1 2; do
 done
 FV3LM_FUSED_TP=2 FV3LM_FUSED_A2B=1 FV3LM_FUSED_CHAIN=1 python bench.py --no-cpu --profile-out gpurun_out/${T}_profile_fused_all.txt > gpurun_out/${T}_bench_fused_all.json 2> gpurun_out/${T}_bench_fused_all.err
 echo "fused all rc=$?"; cat gpurun_out/${T}_bench_fused_all.json
+# 5b. the hand-derived adjoint of nh_p_grad (default path since the end of round 1; the committed capture describes its predecessor)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:KernAD.*S_gradp -c 2 \
+    -o gpurun_out/${T}_KernAD_S_gradp_c180 python bench.py --kernel-only --steps 1 --warmup 0 > gpurun_out/${T}_ncu_gradp.log 2>&1
+ls -la gpurun_out/${T}_KernAD_S_gradp_c180.ncu-rep
 # 6. ncu of the tile kernels (only after the same command exited 0 above): launch list of one TL+AD pair and --set full of the
 #    reverse kernel and kernel B (one launch each is enough: every launch of a kind does the same work)
 if [ -s gpurun_out/${T}_bench_fused_all.json ]; then
