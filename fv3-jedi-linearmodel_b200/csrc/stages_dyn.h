@@ -97,6 +97,46 @@ struct S_pgrad_c {
                               (x.in(3, 0, -1, 0) - x.in(3, 0, 0, 1)) * (x.in(2, 0, -1, 1) - x.in(2, 0, 0, 0))));
     }
   }
+
+  // ---- hand-derived gather adjoint, same structure as S_gradp::adjoint below: the output at (o, k) reads the corners
+  //   a = (o - e, k)   b = (o, k)   c = (o - e, k+1)   d = (o, k+1),   e = (1,0) for uc, (0,1) for vc
+  //   out = wind + dt2 rdc (A B + C D) / den,  A = gz_c - gz_b, B = pk_d - pk_a, C = gz_a - gz_d, D = pk_c - pk_b,
+  //   den = (pk_c - pk_a) + (pk_d - pk_b) (hydrostatic)  or  delpc_a + delpc_b
+  static constexpr bool custom_ad = true;
+  template <class K> DEV static void adjoint(const K& kn, int ii, int jj, int kk, int tile, double* acc) {
+    const P& p = kn.p;
+    const Geom& g = kn.g;
+    CtxNL<S_pgrad_c> x; x.g = kn.g; x.m = kn.m; x.in_ = kn.in;
+    const int i0 = g.i0[tile], j0 = g.j0[tile];
+    if (kk < kn.nk_fwd) {
+      x.setpos(ii, jj, kk, tile, i0, j0);
+      if (kn.outad.p[0] && x.in_rect(g.is, g.ie + 1, g.js, g.je)) acc[0] += kn.outad.p[0][x.off(kn.outad.nk[0], 0, 0, 0)];
+      if (kn.outad.p[1] && x.in_rect(g.is, g.ie, g.js, g.je + 1)) acc[1] += kn.outad.p[1][x.off(kn.outad.nk[1], 0, 0, 0)];
+    }
+    // role: 0 = a, 1 = b, 2 = c, 3 = d of the output at (oi, oj, ok)
+    auto side = [&](const bool isu, const int role) {
+      const int oi = ii + ((isu && !(role & 1)) ? 1 : 0), oj = jj + ((!isu && !(role & 1)) ? 1 : 0), ok = kk - (role >> 1);
+      if (oi < 0 || oj < 0 || oi >= g.NX || oj >= g.NY || ok < 0 || ok >= kn.nk_fwd) return;
+      const int o = isu ? 0 : 1;
+      if (!kn.outad.p[o]) return;
+      x.setpos(oi, oj, ok, tile, i0, j0);
+      if (isu ? !x.in_rect(g.is, g.ie + 1, g.js, g.je) : !x.in_rect(g.is, g.ie, g.js, g.je + 1)) return;
+      const double au = kn.outad.p[o][x.off(kn.outad.nk[o], 0, 0, 0)];
+      if (au == 0.0) return;
+      const int ex = isu ? 1 : 0, ey = isu ? 0 : 1;
+      const double pa = x.in(2, -ex, -ey, 0), pb = x.in(2, 0, 0, 0), pc = x.in(2, -ex, -ey, 1), pd = x.in(2, 0, 0, 1);
+      const double ga = x.in(3, -ex, -ey, 0), gb = x.in(3, 0, 0, 0), gc = x.in(3, -ex, -ey, 1), gd = x.in(3, 0, 0, 1);
+      const double A = gc - gb, B = pd - pa, C = ga - gd, D = pc - pb;
+      const double den = p.hydrostatic ? (pc - pa) + (pd - pb) : x.in(4, -ex, -ey) + x.in(4, 0, 0);
+      const double r = p.dt2 * (isu ? x.M(x.m.rdxc) : x.M(x.m.rdyc)) * au / den, q = (A * B + C * D) / den;
+      const double qd = p.hydrostatic ? q : 0.0;         // den depends on pk only in the hydrostatic form
+      acc[2] += r * (role == 0 ? (-A + qd) : role == 1 ? (-C + qd) : role == 2 ? (C - qd) : (A - qd));
+      acc[3] += r * (role == 0 ? D : role == 1 ? -B : role == 2 ? B : -D);
+      if (!p.hydrostatic && role < 2) acc[4] += -r * q;
+    };
+#pragma unroll
+    for (int role = 0; role < 4; role++) { side(true, role); side(false, role); }
+  }
 };
 
 // one_grad_p / nh_p_grad wind update from B-grid (corner) pk, gz [, pp, delp_b]
