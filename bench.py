@@ -164,6 +164,21 @@ def run_gpu(args):
             cells = float(np.prod(shp)) * world
             side = {"turb_tl_ms": tb_tl, "turb_ad_ms": tb_ad, "turb_alg_gb": 24 * 8 * cells / 1e9,
                     "turb_tl_alg_gbs": 24 * 8 * cells / 1e9 / (tb_tl * 1e-3)}
+        if args.profile_out:
+            buf = __import__("ctypes").create_string_buffer(1 << 20)
+            h._check(h.lib.fv3lm_profile_steps(h.h, 0, 1, buf, len(buf)), "profile")
+            prow = []
+            for line in buf.value.decode().splitlines():
+                nm, n, ms, b = line.split()
+                prow.append((nm, int(n), float(ms), float(b)))
+            prow.sort(key=lambda r: -r[2])
+            ptot = sum(r[2] for r in prow)
+            if rank == 0:
+                with open(args.profile_out, "w") as fh:
+                    fh.write("# per-op CUDA-event profile of one TL+AD step pair (serialised pass): name launches total_ms alg_GB/s share\n")
+                    for r in prow:
+                        fh.write("%-28s %5d %10.3f %9.1f %6.2f%%\n" % (r[0], r[1], r[2], (r[3] / (r[2] * 1e-3) / 1e9 if r[2] > 0 else 0.0), 100.0 * r[2] / ptot))
+            side["pool_peak_gb"] = float(h.lib.fv3lm_pool_peak_bytes(h.h)) / 1e9
         if rank == 0:
             out = {"kernel_only": True, "fused_tp": int(os.environ.get("FV3LM_FUSED_TP", "0") or 0), "fused_a2b": int(os.environ.get("FV3LM_FUSED_A2B", "0") or 0),
                    "fused_chain": int(os.environ.get("FV3LM_FUSED_CHAIN", "0") or 0), "two_sided": bool(args.two_sided), "q_split_dynamic": int(args.q_split_dynamic), "res": N,

@@ -111,15 +111,26 @@ template <class K> GLOBAL void __launch_bounds__(NTHR) kern_chain(const __grid_c
     if (ph + 1 < K::NPH) __syncthreads();
   }
 }
+// a B200 SM has 227 KB of shared memory a block may opt in to (the default limit without the attribute is 48 KB)
+constexpr size_t CHAIN_SMEM_MAX = 227 * 1024;
 template <class K> void launch_chain(const K& k, int nx, int ny, int nz, size_t smem_bytes) {
   if (nz <= 0) return;
-  if (smem_bytes > 48 * 1024) throw std::runtime_error("fused chain: tiles exceed 48 KB of shared memory");
+  if (smem_bytes > CHAIN_SMEM_MAX) throw std::runtime_error("fused chain: tiles exceed 227 KB of shared memory");
+  static size_t opted = 0;     // per kernel instantiation
+  if (smem_bytes > 48 * 1024 && smem_bytes > opted) {
+    if (cudaFuncSetAttribute(kern_chain<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX) != cudaSuccess)
+      throw std::runtime_error("fused chain: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+    opted = CHAIN_SMEM_MAX;
+  }
   dim3 b(NTHR, 1, 1), gr((nx + TX - 1) / TX, (ny + TY - 1) / TY, nz);
   kern_chain<K><<<gr, b, smem_bytes, dev::stream()>>>(k);
   dev::launches++;
 }
 #else
+constexpr size_t CHAIN_SMEM_MAX = 227 * 1024;
 template <class K> void launch_chain(const K& k, int nx, int ny, int nz, size_t smem_bytes) {
+  // the same limit as the device launcher, so that the CPU suite fails where the GPU would
+  if (smem_bytes > CHAIN_SMEM_MAX) throw std::runtime_error("fused chain: tiles exceed 227 KB of shared memory");
   std::vector<double> buf(smem_bytes / sizeof(double) + 1);
   typename K::Smem s{buf.data()};
   for (int z = 0; z < nz; z++)
