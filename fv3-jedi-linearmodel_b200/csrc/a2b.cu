@@ -191,7 +191,8 @@ template <class TT> struct KernA2b {
   struct Smem { SBuf<TLM, QW * QH> q; SBuf<TLM, TX * QH> qx; SBuf<TLM, QW * TY> qy; SBuf<TLM, (TX + 2) * (TY + 2)> qe; };
   DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
     using N = Num<TT>;
-    const int tile = z / nk, kk = z % nk, ii0 = bx * TX, jj0 = by * TY;
+    int tile, kk; split_z(z, nk, tile, kk);
+    const int ii0 = bx * TX, jj0 = by * TY;
     const int i0 = g.i0[tile], j0 = g.j0[tile];
     const Box bq{ii0 - 3, jj0 - 3, QW, QH}, bqx{ii0, jj0 - 3, TX, QH}, bqy{ii0 - 3, jj0, QW, TY}, bqe{ii0 - 1, jj0 - 1, TX + 2, TY + 2};
     auto inside = [&](int ii, int jj) { return ii >= 0 && ii < g.NX && jj >= 0 && jj < g.NY; };
@@ -248,7 +249,8 @@ struct KernA2bRev {
   Geom g; Metrics m; int nk; Fld aout; OFld qin_ad;      // .v = adjoint arrays
   struct Smem { double oad[UW * UH], qx_ad[UW * TY], qy_ad[TX * UH], qe_ad[(TX + 3) * (TY + 3)]; };
   DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
-    const int tile = z / nk, kk = z % nk, ii0 = bx * TX, jj0 = by * TY;
+    int tile, kk; split_z(z, nk, tile, kk);
+    const int ii0 = bx * TX, jj0 = by * TY;
     const int i0 = g.i0[tile], j0 = g.j0[tile];
     const Box bu{ii0 - 2, jj0 - 2, UW, UH}, bqx{ii0 - 2, jj0, UW, TY}, bqy{ii0, jj0 - 2, TX, UH}, bqe{ii0 - 1, jj0 - 1, TX + 3, TY + 3};
     auto inside = [&](int ii, int jj) { return ii >= 0 && ii < g.NX && jj >= 0 && jj < g.NY; };

@@ -55,13 +55,26 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
   if (!cfg->hydrostatic && cfg->a_imp != 0.0 && !(cfg->a_imp > 0.5))
     throw std::runtime_error("fv3lm_create: a_imp <= 0.5 selects the RIM_2D / SIM3 solvers (model/nh_core_nlm.F90:136-146), which are not built; use 0.5 < a_imp <= 1");
   if (cfg->npx < 9) throw std::runtime_error("fv3lm_create: need at least 8 cells per tile edge");
+  // switches whose paths are not built change the dynamics in the reference: refuse them rather than ignore them
+  if (cfg->beta != 0.0)
+    throw std::runtime_error("fv3lm_create: beta != 0 selects split_p_grad / grad1_p_update (model/dyn_core_nlm.F90:865-876), which are not built");
+  if (cfg->d_ext > 0.0)
+    throw std::runtime_error("fv3lm_create: d_ext > 0 switches on the external-mode divergence damping (model/dyn_core_nlm.F90:642-720), which is not built");
+  int device = -1;
 #ifndef FV3LM_HOST_EMU
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     throw std::runtime_error("fv3lm_create: no CUDA device -- this library has no CPU fallback");
+  // bind this process to its GPU before anything is allocated (several MPI ranks per node would otherwise all land on device 0)
+  if (cfg->device > ndev) throw std::runtime_error("fv3lm_create: device index out of range");
+  if (cfg->device != 0) {
+    device = cfg->device > 0 ? cfg->device - 1 : (cfg->rank < 0 ? 0 : cfg->rank) % ndev;
+    if (cudaSetDevice(device) != cudaSuccess) throw std::runtime_error("fv3lm_create: cudaSetDevice failed");
+  } else if (cudaGetDevice(&device) != cudaSuccess) throw std::runtime_error("fv3lm_create: cudaGetDevice failed");
 #endif
   h = new fv3lm_handle();
   h->cfg = *cfg;
+  h->device = device;
   Geom& g = h->dv.g;
   g.N = cfg->npx - 1; g.npx = cfg->npx; g.npy = cfg->npy; g.ng = cfg->ng;
   Decomp& dc = h->dc;
@@ -89,7 +102,7 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
 
 int fv3lm_destroy(fv3lm_handle* h) {
   if (!h) return 0;
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   dev::sync();
   for (auto& kv : h->metric_dev) dev::free_(kv.second);
   if (h->step) {
@@ -120,7 +133,7 @@ int fv3lm_destroy(fv3lm_handle* h) {
 const char* fv3lm_last_error(const fv3lm_handle* h) { return h ? h->err.c_str() : fv3lm_g_err.c_str(); }
 
 int fv3lm_set_metric(fv3lm_handle* h, const char* name, const double* host, int is_1d) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   const Geom& g = h->dv.g;
   std::string nm(name);
   double*& d = h->metric_dev[nm];
@@ -156,7 +169,7 @@ int fv3lm_set_metric(fv3lm_handle* h, const char* name, const double* host, int 
 }
 
 int fv3lm_set_metric_scalar(fv3lm_handle* h, const char* name, double value) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   std::string nm(name);
   if (nm == "da_min") h->dv.m.da_min = value;
   else if (nm == "da_min_c") h->dv.m.da_min_c = value;
@@ -169,7 +182,7 @@ const char* fv3lm_module_list(void) { return module_list(); }
 int fv3lm_module_run(fv3lm_handle* h, const char* module, int mode, int nfields, const char* const* names,
                      double* const* traj, double* const* pert, int nparams, const char* const* pnames,
                      const double* pvals) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   const Geom& g = h->dv.g;
   ModuleParams prm;
   for (int n = 0; n < nparams; n++) prm.v[pnames[n]] = pvals[n];
@@ -215,7 +228,9 @@ int fv3lm_module_run(fv3lm_handle* h, const char* module, int mode, int nfields,
       if (v.active && hp) up2d(g, v.pert, hp, (size_t)g.ntile * v.nk * g.NY);
     }
   }
-  P.run((Mode)mode);
+  auto give_back = [&]() { for (int id : ext) { Value& v = P.vals[id]; h->dv.pool.put(v.traj); h->dv.pool.put(v.pert); v.traj = v.pert = nullptr; } };
+  try { P.run((Mode)mode); }
+  catch (...) { give_back(); throw; }       // (Program::run has already released its own intermediates)
   // download
   for (auto& kv : io.outputs) {
     Value& v = P.vals[kv.second];
@@ -231,7 +246,7 @@ int fv3lm_module_run(fv3lm_handle* h, const char* module, int mode, int nfields,
     }
   }
   dev::sync();
-  for (int id : ext) { Value& v = P.vals[id]; h->dv.pool.put(v.traj); h->dv.pool.put(v.pert); v.traj = v.pert = nullptr; }
+  give_back();
   P.check_status_flags();
   FV3LM_CATCH(h)
 }
@@ -256,12 +271,12 @@ int fv3lm_nccl_unique_id(char* out128) {
   FV3LM_CATCH(h)
 }
 int fv3lm_comm_init_nccl(fv3lm_handle* h, const char* id128) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   h->comm.init_nccl(id128);
   FV3LM_CATCH(h)
 }
 int fv3lm_comm_set_callback(fv3lm_handle* h, fv3lm_exchange_fn fn, void* user) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   h->comm.cb = (ExchangeCallback)fn; h->comm.cb_user = user;
   FV3LM_CATCH(h)
 }
@@ -274,7 +289,7 @@ int fv3lm_comm_stats(const fv3lm_handle* h, double* out2) {
 long long fv3lm_launch_count(void) { return dev::launches; }
 double fv3lm_pool_peak_bytes(const fv3lm_handle* h) { return h ? (double)h->dv.pool.bytes_peak : 0.0; }
 int fv3lm_sync(fv3lm_handle* h) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   dev::sync();
   FV3LM_CATCH(h)
 }

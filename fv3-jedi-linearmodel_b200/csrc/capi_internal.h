@@ -51,11 +51,21 @@ struct fv3lm_handle {
   std::map<std::string, std::vector<double>> geo_host;   // grid / agrid lon-lat kept to derive a2b_cw
   std::string err;
   StepRunner* step = nullptr;
+  int device = -1;          // CUDA device bound at create; re-asserted on entry to the ABI (a host thread may have switched devices)
 };
+inline void fv3lm_bind_device(const fv3lm_handle* h) {
+#ifndef FV3LM_HOST_EMU
+  if (h && h->device >= 0) cudaSetDevice(h->device);
+#else
+  (void)h;
+#endif
+}
 
 extern thread_local std::string fv3lm_g_err;
 
+// (entry points that take a handle call fv3lm_bind_device first: see FV3LM_TRY_H)
 #define FV3LM_TRY try {
+#define FV3LM_TRY_H(h) try { fv3lm_bind_device(h);
 #define FV3LM_CATCH(h)                                            \
   }                                                               \
   catch (const std::exception& e) {                               \

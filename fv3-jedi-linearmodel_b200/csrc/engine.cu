@@ -232,7 +232,17 @@ bool Program::ad_fits_store_all() {
   return ad_store_all_cached != 0;
 }
 
+// An exception in the middle of a sweep must not leave intermediates bound: a stale non-null `pert` would make the next adjoint
+// run skip the zeroing of that accumulator (ensure_pert returns early) and add onto old adjoints.
 void Program::run(Mode mode) {
+  try { run_sweeps(mode); }
+  catch (...) {
+    for (int id = 0; id < (int)vals.size(); id++) if (!vals[id].external) release(id);
+    throw;
+  }
+}
+
+void Program::run_sweeps(Mode mode) {
   sweep_kind = (mode == MODE_NL || mode == MODE_TL) ? VAR_FWD : VAR_AD;
   analyse();
   const int nop = (int)ops.size();

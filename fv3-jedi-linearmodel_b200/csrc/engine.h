@@ -177,17 +177,18 @@ template <class S> struct CtxAD : CtxBase {
 // ---------------------------------------------------------------------------------
 template <class S> struct KernNL {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in; FArr<S::NO> out; int nk;
-  DEV void operator()(int ii, int jj, int z) const {
+  // (level and sub-domain come from the launcher: an integer division per thread costs ~20 instructions, as much as a simple stage)
+  DEV void operator()(int ii, int jj, int kk, int tile) const {
     CtxNL<S> x; x.g = g; x.m = m; x.in_ = in; x.out_ = out;
-    x.setpos(ii, jj, z % nk, z / nk, g.i0[z / nk], g.j0[z / nk]);
+    x.setpos(ii, jj, kk, tile, g.i0[tile], g.j0[tile]);
     S::eval(x, p);
   }
 };
 template <class S> struct KernTL {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in, ind; FArr<S::NO> out, outd; int nk;
-  DEV void operator()(int ii, int jj, int z) const {
+  DEV void operator()(int ii, int jj, int kk, int tile) const {
     CtxTL<S> x; x.g = g; x.m = m; x.in_ = in; x.ind_ = ind; x.out_ = out; x.outd_ = outd;
-    x.setpos(ii, jj, z % nk, z / nk, g.i0[z / nk], g.j0[z / nk]);
+    x.setpos(ii, jj, kk, tile, g.i0[tile], g.j0[tile]);
     S::eval(x, p);
   }
 };
@@ -290,11 +291,10 @@ template <class S> struct HasCustomAd<S, std::enable_if_t<S::custom_ad>> { stati
 
 template <class S> struct KernAD {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in, inad; FArr<S::NO> outad; int nk, nk_fwd;
-  DEV void operator()(int ii, int jj, int z) const {
+  DEV void operator()(int ii, int jj, int kk, int tile) const {
     double acc[S::NI];
 #pragma unroll
     for (int f = 0; f < S::NI; f++) acc[f] = 0.0;
-    int kk = z % nk, tile = z / nk;
     if constexpr (HasCustomAd<S>::value) S::adjoint(*this, ii, jj, kk, tile, acc);
     else AdTaps<S, 0>::run(*this, ii, jj, kk, tile, acc);
 #pragma unroll
@@ -346,29 +346,33 @@ template <class F> void launch3d(const F& f, int nx, int ny, int nz) {
 // stencil stages: every thread handles KPT consecutive levels of one (i, j): the 2-D metric loads, the
 // cube-edge branch conditions and the index set-up are level-invariant and get shared across them
 constexpr int KPT = 1;   // (2 was tried: ptxas does not share work across the unrolled levels, no gain)
-template <class F> GLOBAL void kern_stage(F f, int nx, int ny, int nk, int nkc) {
+// blockIdx.z = tile * nkc + level chunk.  The quotient comes from a float multiply: (z + 0.5) / nkc is at least 0.5 / nkc away from
+// an integer and z < 2^16, so the rounding error of the product (< 1e-5) cannot change the truncation -- exact, 3 instructions
+// instead of the ~20 of an integer division by a run-time divisor.
+DEV int fast_div_small(int z, float inv) { return (int)(((float)z + 0.5f) * inv); }
+template <class F> GLOBAL void kern_stage(const __grid_constant__ F f, int nx, int ny, int nk, int nkc, float inv_nkc) {
   int ii = blockIdx.x * blockDim.x + threadIdx.x;
   int jj = blockIdx.y * blockDim.y + threadIdx.y;
   if (ii >= nx || jj >= ny) return;
-  const int tile = blockIdx.z / nkc, k0 = (blockIdx.z % nkc) * KPT;
+  const int tile = fast_div_small(blockIdx.z, inv_nkc), k0 = (blockIdx.z - tile * nkc) * KPT;
 #pragma unroll
   for (int q = 0; q < KPT; q++) {
     const int k = k0 + q;
-    if (k < nk) f(ii, jj, tile * nk + k);
+    if (k < nk) f(ii, jj, k, tile);
   }
 }
 template <class F> void launch_stage(const F& f, int nx, int ny, int ntile, int nk) {
   if (ntile * nk <= 0) return;
   const int nkc = (nk + KPT - 1) / KPT;
   dim3 b(32, 8, 1), gr((nx + 31) / 32, (ny + 7) / 8, ntile * nkc);
-  kern_stage<F><<<gr, b, 0, dev::stream()>>>(f, nx, ny, nk, nkc);
+  kern_stage<F><<<gr, b, 0, dev::stream()>>>(f, nx, ny, nk, nkc, 1.0f / (float)nkc);
   dev::launches++;
 }
 #else
 template <class F> void launch_stage(const F& f, int nx, int ny, int ntile, int nk) {
   for (int z = 0; z < ntile * nk; z++)
     for (int jj = 0; jj < ny; jj++)
-      for (int ii = 0; ii < nx; ii++) f(ii, jj, z);
+      for (int ii = 0; ii < nx; ii++) f(ii, jj, z % nk, z / nk);
   dev::launches++;
 }
 template <class F> void launch3d(const F& f, int nx, int ny, int nz) {
@@ -463,7 +467,8 @@ struct Program {
   bool ad_fits_store_all();
   int ad_store_all_cached = -1;
   int ad_keep_from = -1;             // first segment kept whole by the adjoint's forward pass (decided once)
-  void run(Mode mode);               // NL, TL, or AD (forward store-all + reverse)
+  void run(Mode mode);               // NL, TL, or AD (forward store-all + reverse); releases every intermediate if a sweep throws
+  void run_sweeps(Mode mode);
   void run_op(Op& op, int mode);     // one op, optionally profiled
   void ensure_traj(int id);
   void ensure_pert(int id, bool zero_it);

@@ -96,7 +96,8 @@ template <class TT, class... S> struct KernChain {
     }
   }
   DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
-    dispatch<0>(ph, tid, bx * TX, by * TY, z % nk, z / nk, s.base);
+    int tile, kk; split_z(z, nk, tile, kk);
+    dispatch<0>(ph, tid, bx * TX, by * TY, kk, tile, s.base);
   }
 };
 

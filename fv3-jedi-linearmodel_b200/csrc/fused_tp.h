@@ -62,7 +62,8 @@ template <class TT, bool FULL> struct KernTpA {
   struct Smem { SBuf<TLM, QW * QH> q; SBuf<TLM, QW*(TY + 1)> fy; SBuf<TLM, QW * TY> qi; };
   DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
     using N = Num<TT>;
-    const int tile = z / nk, kk = z % nk, ii0 = bx * TX, jj0 = by * TY;
+    int tile, kk; split_z(z, nk, tile, kk);
+    const int ii0 = bx * TX, jj0 = by * TY;
     const int i0 = g.i0[tile], j0 = g.j0[tile];
     const int is = g.is, ie = g.ie, js = g.js, je = g.je, isd = is - g.ng, ied = ie + g.ng;
     TileCtx<TT> x; x.g = g; x.m = m;
@@ -118,7 +119,8 @@ template <class TT, bool FULL> struct KernTpB {
   struct Smem { SBuf<TLM, QW * QH> q; SBuf<TLM, FW * QH> fx; SBuf<TLM, TX * QH> qj; };
   DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
     using N = Num<TT>;
-    const int tile = z / nk, kk = z % nk, ii0 = bx * TX, jj0 = by * TY;
+    int tile, kk; split_z(z, nk, tile, kk);
+    const int ii0 = bx * TX, jj0 = by * TY;
     const int i0 = g.i0[tile], j0 = g.j0[tile];
     const int is = g.is, ie = g.ie, js = g.js, je = g.je, jsd = js - g.ng, jed = je + g.ng;
     TileCtx<TT> x; x.g = g; x.m = m;
@@ -300,7 +302,8 @@ template <int DIN, bool AVG> struct KernTpRev {
     return x.in_rect(g.is, g.ie + 1, g.js, g.je);
   }
   DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
-    const int tile = z / nk, kk = z % nk, ii0 = bx * TX, jj0 = by * TY;
+    int tile, kk; split_z(z, nk, tile, kk);
+    const int ii0 = bx * TX, jj0 = by * TY;
     const int i0 = g.i0[tile], j0 = g.j0[tile];
     const int a0 = DIN == 0 ? ii0 : jj0, b0 = DIN == 0 ? jj0 : ii0;
     const int od = ord.v[kk];

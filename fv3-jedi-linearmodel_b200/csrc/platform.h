@@ -17,3 +17,15 @@
 // read-only data (metrics, stage inputs): ld.global.nc lets the compiler keep / reorder loads across the stores of the stage
 #define LDG(p) __ldg(p)
 #endif
+
+// blockIdx.z = tile * nk + level -> (tile, level).  On the device the quotient comes from a float multiply ((z + 0.5) / nk is at least
+// 0.5 / nk away from an integer, z < 2^16, nk <= 128: the rounding error cannot change the truncation), a handful of instructions
+// instead of the ~20 of an integer division by a run-time divisor.
+DEV void split_z(int z, int nk, int& tile, int& kk) {
+#ifdef FV3LM_HOST_EMU
+  tile = z / nk;
+#else
+  tile = (int)(((float)z + 0.5f) * __frcp_rn((float)nk));
+#endif
+  kk = z - tile * nk;
+}

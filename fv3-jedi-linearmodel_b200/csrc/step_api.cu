@@ -34,12 +34,13 @@ size_t compact_doubles(const Geom& g, int nk) { return (size_t)g.ntile * nk * g.
 
 void ensure_runner(fv3lm_handle* h) {
   if (h->step) return;
-  auto* r = new StepRunner();
+  if (h->ak.empty()) throw std::runtime_error("fv3lm: ak/bk were not given to fv3lm_create");
+  std::unique_ptr<StepRunner> owner(new StepRunner());     // released into the handle only once it is completely built
+  StepRunner* r = owner.get();
   const Geom& g = h->dv.g;
   r->P.dv = &h->dv; r->P.name = "step";
   ModuleParams prm; prm.cfg = &h->cfg; prm.ak = &h->ak; prm.bk = &h->bk;
   prm.v["bdt"] = h->cfg.dt;
-  if (h->ak.empty()) throw std::runtime_error("fv3lm: ak/bk were not given to fv3lm_create");
   build_module("step", r->P, h->mo, r->io, prm);
   r->nf = h->cfg.hydrostatic ? 8 : 10;
   for (auto& kv : r->io.inputs) {
@@ -60,7 +61,7 @@ void ensure_runner(fv3lm_handle* h) {
   for (int f = 0; f < r->nf; f++) r->pert[f] = (double*)dev::alloc(compact_doubles(g, g.K) * sizeof(double));
   r->phis = (double*)dev::alloc(compact_doubles(g, 1) * sizeof(double));
   dev::zero(r->phis, compact_doubles(g, 1) * sizeof(double));
-  h->step = r;
+  h->step = owner.release();
 }
 
 double** field_ptr(fv3lm_fields* f, int n) {
@@ -156,7 +157,7 @@ void run_step(fv3lm_handle* h, int slot, int mode) {
 extern "C" {
 
 int fv3lm_set_phis(fv3lm_handle* h, const double* phis) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   dev::h2d(h->step->phis, phis, compact_doubles(h->dv.g, 1) * sizeof(double));
   dev::sync();
@@ -164,7 +165,7 @@ int fv3lm_set_phis(fv3lm_handle* h, const double* phis) {
 }
 
 int fv3lm_traj_set(fv3lm_handle* h, int slot, const fv3lm_fields* traj) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   for (int f = 0; f < h->step->nf; f++) {
     double* src = *field_ptr(const_cast<fv3lm_fields*>(traj), f);
@@ -176,14 +177,14 @@ int fv3lm_traj_set(fv3lm_handle* h, int slot, const fv3lm_fields* traj) {
 }
 
 int fv3lm_traj_get(fv3lm_handle* h, int slot, fv3lm_fields* traj) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   for (int f = 0; f < h->step->nf; f++) { double* dst = *field_ptr(traj, f); if (dst) dev::d2h(dst, slot_field(h, slot, f), compact_doubles(h->dv.g, h->dv.g.K) * sizeof(double)); }
   FV3LM_CATCH(h)
 }
 
 int fv3lm_step_nl(fv3lm_handle* h, int slot_in, int slot_out) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   run_step(h, slot_in, MODE_NL);
   StepRunner* r = h->step;
@@ -206,7 +207,7 @@ int fv3lm_step_nl(fv3lm_handle* h, int slot_in, int slot_out) {
 // gridstruct%a11 .. a22 (init_cubed_to_latlon, model/fv_grid_utils_nlm.F90:2248-2310), compact (isc:iec, jsc:jec).  Once set, every
 // fv3lm_step_nl also produces the A-grid lon / lat winds of its result (fv3jedi_lm_dynamics_mod.F90:839-840: traj%ua, traj%va).
 int fv3lm_set_c2l(fv3lm_handle* h, const double* a11, const double* a12, const double* a21, const double* a22) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   StepRunner* r = h->step; const Geom& g = h->dv.g;
   if (!a11 || !a12 || !a21 || !a22) throw std::runtime_error("fv3lm_set_c2l: null array");
@@ -242,7 +243,7 @@ int fv3lm_set_c2l(fv3lm_handle* h, const double* a11, const double* a12, const d
 
 // ua, va of the last fv3lm_step_nl (compact, like the fields)
 int fv3lm_traj_get_winds(fv3lm_handle* h, double* ua, double* va) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   StepRunner* r = h->step; const Geom& g = h->dv.g;
   if (!r->c2l) throw std::runtime_error("fv3lm_traj_get_winds: fv3lm_set_c2l was not called");
@@ -252,7 +253,7 @@ int fv3lm_traj_get_winds(fv3lm_handle* h, double* ua, double* va) {
 }
 
 int fv3lm_pert_upload(fv3lm_handle* h, const fv3lm_fields* pert) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   for (int f = 0; f < h->step->nf; f++) {
     double* src = *field_ptr(const_cast<fv3lm_fields*>(pert), f);
@@ -263,21 +264,21 @@ int fv3lm_pert_upload(fv3lm_handle* h, const fv3lm_fields* pert) {
 }
 
 int fv3lm_pert_download(fv3lm_handle* h, fv3lm_fields* pert) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   for (int f = 0; f < h->step->nf; f++) { double* dst = *field_ptr(pert, f); if (dst) dev::d2h(dst, h->step->pert[f], compact_doubles(h->dv.g, h->dv.g.K) * sizeof(double)); }
   FV3LM_CATCH(h)
 }
 
 int fv3lm_step_tl_dev(fv3lm_handle* h, int slot) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   run_step(h, slot, MODE_TL);
   FV3LM_CATCH(h)
 }
 
 int fv3lm_step_ad_dev(fv3lm_handle* h, int slot) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   run_step(h, slot, MODE_AD);
   FV3LM_CATCH(h)
@@ -301,7 +302,7 @@ int fv3lm_step_ad(fv3lm_handle* h, int slot, fv3lm_fields* pert) {
 // set_ltraj :375-533 keeps BL_DRIVER (the nonlinear scheme that produces the diagonals, once per trajectory time level) on the
 // caller's side of the boundary; the decomposition, p^kappa and every TL / AD / NL application run here.
 int fv3lm_turb_set_ltraj(fv3lm_handle* h, int slot, const fv3lm_turb_coeffs* co) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   StepRunner* r = h->step; const Geom& g = h->dv.g;
   if (!co) throw std::runtime_error("fv3lm_turb_set_ltraj: null coefficients");
@@ -338,14 +339,14 @@ static void turb_apply(fv3lm_handle* h, int slot, double* const* f10, bool adjoi
 }
 
 int fv3lm_turb_step_tl_dev(fv3lm_handle* h, int slot) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   turb_apply(h, slot, h->step->pert, false);
   FV3LM_CATCH(h)
 }
 
 int fv3lm_turb_step_ad_dev(fv3lm_handle* h, int slot) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   turb_apply(h, slot, h->step->pert, true);
   FV3LM_CATCH(h)
@@ -368,7 +369,7 @@ int fv3lm_turb_step_ad(fv3lm_handle* h, int slot, fv3lm_fields* pert) {
 // step_nl :149-213: the same solves applied to the trajectory fields of slot_state, in place, with the local trajectory of
 // slot_ltraj (fv3jedi_lm_mod calls the physics after the dynamics: the state has moved on, src/fv3jedi_lm_mod.F90:153-156)
 int fv3lm_turb_step_nl(fv3lm_handle* h, int slot_ltraj, int slot_state) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   StepRunner* r = h->step;
   if (slot_state < 0 || (int)r->slots.size() <= slot_state || r->slots[slot_state].empty())
@@ -381,7 +382,7 @@ int fv3lm_turb_step_nl(fv3lm_handle* h, int slot_ltraj, int slot_state) {
 // Timed loop on the library's own stream (CUDA events): `iters` repetitions of one TL step followed
 // by one AD step on resident data.  ms[0] = TL ms/step, ms[1] = AD ms/step.  Used by bench.py.
 int fv3lm_time_steps(fv3lm_handle* h, int slot, int warmup, int iters, double* ms) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
 #ifndef FV3LM_HOST_EMU
   cudaEvent_t e0, e1, e2;
@@ -411,7 +412,7 @@ int fv3lm_time_steps(fv3lm_handle* h, int slot, int warmup, int iters, double* m
 
 // The same for the turbulence solves: ms[0] = TL ms/call, ms[1] = AD ms/call on the device-resident increments.
 int fv3lm_time_turb(fv3lm_handle* h, int slot, int warmup, int iters, double* ms) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
 #ifndef FV3LM_HOST_EMU
   cudaEvent_t e0, e1, e2;
@@ -442,13 +443,15 @@ int fv3lm_time_turb(fv3lm_handle* h, int slot, int warmup, int iters, double* ms
 // Profiling pass: per-op CUDA-event times of `iters` TL+AD steps (serialised; not a bench number).
 // Writes lines "name launches total_ms alg_bytes" into buf.
 int fv3lm_profile_steps(fv3lm_handle* h, int slot, int iters, char* buf, int buflen) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ensure_runner(h);
   dev::prof.clear();
-  dev::profiling = true;
-  for (int n = 0; n < iters; n++) { run_step(h, slot, MODE_TL); run_step(h, slot, MODE_AD); }
-  dev::sync();
-  dev::profiling = false;
+  struct ProfGuard { ProfGuard() { dev::profiling = true; } ~ProfGuard() { dev::profiling = false; } };   // also reset when a step throws
+  {
+    ProfGuard guard;
+    for (int n = 0; n < iters; n++) { run_step(h, slot, MODE_TL); run_step(h, slot, MODE_AD); }
+    dev::sync();
+  }
   std::string out;
   for (auto& kv : dev::prof) {
     char line[512];
@@ -462,7 +465,7 @@ int fv3lm_profile_steps(fv3lm_handle* h, int slot, int iters, char* buf, int buf
 
 // structural statistics of a module's program: ops, values, bytes if every value is kept (AD)
 int fv3lm_program_stats(fv3lm_handle* h, const char* module, double* out) {
-  FV3LM_TRY
+  FV3LM_TRY_H(h)
   ModuleParams prm; prm.cfg = &h->cfg; prm.ak = &h->ak; prm.bk = &h->bk; prm.v["bdt"] = h->cfg.dt;
   Program P; P.dv = &h->dv; ModuleIO io;
   build_module(module, P, h->mo, io, prm);

@@ -129,7 +129,15 @@ subroutine create(self,conf)
  cfg%do_vort_damp = merge(1, 0, self%FV_AtmP(1)%flagstruct%do_vort_damp_pert)
  cfg%rank = mpp_pe() - mpp_root_pe(); cfg%nranks = mpp_npes()
  cfg%layout_x = A%layout(1); cfg%layout_y = A%layout(2)
- cfg%reserved0 = 0
+ ! one GPU per MPI rank: rank modulo the devices visible on the node (fv3lm_create calls cudaSetDevice before any allocation)
+ cfg%device = -1
+ ! switches the reference hands to fv_dynamics (src/dynamics/fv3jedi_lm_dynamics_mod.F90:299) whose paths are not built: refuse
+ ! them here instead of computing something else silently (beta / d_ext / a_imp are checked by fv3lm_create itself)
+ if (A%flagstruct%consv_te > 0.0_kind_real) call mpp_error(FATAL, 'fv3lm_b200: consv_te > 0 (energy fixer) is not supported')
+ if (A%flagstruct%consv_am) call mpp_error(FATAL, 'fv3lm_b200: consv_am (angular-momentum fixer) is not supported')
+ if (A%flagstruct%fill) call mpp_error(FATAL, 'fv3lm_b200: fill (tracer filling in the remap) is not supported')
+ if (A%flagstruct%tau > 0.0_kind_real) call mpp_error(FATAL, 'fv3lm_b200: tau > 0 (Rayleigh friction) is not supported')
+ if (A%flagstruct%nwat /= 3) call mpp_error(FATAL, 'fv3lm_b200: nwat must be 3')
  ! q_split = 0 in fv_core_nml: tracer sub-steps chosen from the Courant numbers at run time
  cfg%q_split_dynamic = merge(1, 0, A%flagstruct%q_split == 0); cfg%q_split_max = 4
  ! two-sided mode: the fields above carry the perturbation model's switches, cfg%traj the nonlinear model's

@@ -26,7 +26,7 @@ type, bind(c) :: fv3lm_config
   real(c_double) :: zvir, kappa, cp, rdgas, grav
   integer(c_int) :: do_vort_damp
   integer(c_int) :: rank, nranks, layout_x, layout_y
-  integer(c_int) :: reserved0
+  integer(c_int) :: device
   real(c_double) :: a_imp, p_fac, d_con
   integer(c_int) :: two_sided, split_damp, hord_ks_pert, hord_ks_traj
   integer(c_int) :: q_split_dynamic, q_split_max

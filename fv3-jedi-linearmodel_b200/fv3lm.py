@@ -34,7 +34,7 @@ class Config(C.Structure):
                 ("d2_bg_k1", C.c_double), ("d2_bg_k2", C.c_double), ("d_ext", C.c_double), ("beta", C.c_double),
                 ("zvir", C.c_double), ("kappa", C.c_double), ("cp", C.c_double), ("rdgas", C.c_double),
                 ("grav", C.c_double), ("do_vort_damp", C.c_int),
-                ("rank", C.c_int), ("nranks", C.c_int), ("layout_x", C.c_int), ("layout_y", C.c_int), ("reserved0", C.c_int),
+                ("rank", C.c_int), ("nranks", C.c_int), ("layout_x", C.c_int), ("layout_y", C.c_int), ("device", C.c_int),
                 ("a_imp", C.c_double), ("p_fac", C.c_double), ("d_con", C.c_double),
                 ("two_sided", C.c_int), ("split_damp", C.c_int), ("hord_ks_pert", C.c_int), ("hord_ks_traj", C.c_int),
                 ("q_split_dynamic", C.c_int), ("q_split_max", C.c_int), ("traj", TrajFlags), ("d2_bg_ks", C.c_double)]
@@ -92,7 +92,7 @@ def default_config(N, npz, **kw):
     cfg.n_sponge = 0; cfg.nord = 1
     cfg.dt = 900.0; cfg.ptop = 1.0
     cfg.dddmp = 0.2; cfg.d2_bg = 0.015; cfg.d4_bg = 0.15; cfg.vtdm4 = 0.0005
-    cfg.d2_bg_k1 = 4.0; cfg.d2_bg_k2 = 2.0; cfg.d_ext = 0.02; cfg.beta = 0.0
+    cfg.d2_bg_k1 = 4.0; cfg.d2_bg_k2 = 2.0; cfg.d_ext = 0.0; cfg.beta = 0.0     # d_ext > 0 / beta > 0 select paths that are not built: fv3lm_create refuses them
     cfg.rdgas = rdgas; cfg.cp = 3.5 * rdgas; cfg.kappa = rdgas / (3.5 * rdgas)
     cfg.zvir = (8314.47 / 18.015) / rdgas - 1.0; cfg.grav = 9.80665
     cfg.do_vort_damp = 1

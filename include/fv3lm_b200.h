@@ -46,7 +46,10 @@ typedef struct fv3lm_config {
    * (one process per GPU); each tile is split layout_x x layout_y (0 = choose automatically) and
    * the 6*layout_x*layout_y sub-domains are dealt out in consecutive blocks.  nranks = 0 means 1. */
   int rank, nranks, layout_x, layout_y;
-  int reserved0;          /* 0; keeps the doubles below 8-byte aligned                              */
+  /* CUDA device of this process: 0 = keep the process's current device (the caller has called cudaSetDevice, e.g. through
+   * torch); -1 = rank modulo the number of visible devices (what a Fortran/MPI host with several ranks per node wants);
+   * d > 0 = device d - 1.  fv3lm_create binds it before the first allocation and every entry point re-asserts it.      */
+  int device;
   /* non-hydrostatic solver (model/nh_core_nlm.F90:136-152).  0 = not set -> library default.
    * a_imp > 0.999: SIM1_solver (default 1.0); 0.5 < a_imp <= 0.999: SIM_solver in Riem_Solver3
    * (Riem_Solver_c keeps SIM1, model/nh_utils_nlm.F90:366-376); a_imp <= 0.5 (RIM_2D / SIM3) is an error.
