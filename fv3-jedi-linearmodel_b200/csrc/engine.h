@@ -25,6 +25,7 @@
 #include <vector>
 #include <stdexcept>
 #include <type_traits>
+#include <algorithm>
 #include "platform.h"
 #include "dual.h"
 
@@ -183,6 +184,14 @@ template <class S> struct KernNL {
     x.setpos(ii, jj, kk, tile, g.i0[tile], g.j0[tile]);
     S::eval(x, p);
   }
+  // levels k0 .. k1-1 of one (i, j): the context is built once and the loop is not unrolled, so that the level-invariant work of
+  // the stage (index set-up, rectangle / cube-edge tests, the loads of the 2-D metrics) is hoisted out of it
+  DEV void run(int ii, int jj, int k0, int k1, int tile) const {
+    CtxNL<S> x; x.g = g; x.m = m; x.in_ = in; x.out_ = out;
+    x.setpos(ii, jj, k0, tile, g.i0[tile], g.j0[tile]);
+#pragma unroll 1
+    for (int k = k0; k < k1; k++) { x.kk = k; S::eval(x, p); }
+  }
 };
 template <class S> struct KernTL {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in, ind; FArr<S::NO> out, outd; int nk;
@@ -190,6 +199,12 @@ template <class S> struct KernTL {
     CtxTL<S> x; x.g = g; x.m = m; x.in_ = in; x.ind_ = ind; x.out_ = out; x.outd_ = outd;
     x.setpos(ii, jj, kk, tile, g.i0[tile], g.j0[tile]);
     S::eval(x, p);
+  }
+  DEV void run(int ii, int jj, int k0, int k1, int tile) const {
+    CtxTL<S> x; x.g = g; x.m = m; x.in_ = in; x.ind_ = ind; x.out_ = out; x.outd_ = outd;
+    x.setpos(ii, jj, k0, tile, g.i0[tile], g.j0[tile]);
+#pragma unroll 1
+    for (int k = k0; k < k1; k++) { x.kk = k; S::eval(x, p); }
   }
 };
 
@@ -305,6 +320,10 @@ template <class S> struct KernAD {
       }
     }
   }
+  DEV void run(int ii, int jj, int k0, int k1, int tile) const {
+#pragma unroll 1
+    for (int k = k0; k < k1; k++) (*this)(ii, jj, k, tile);
+  }
 };
 
 // ---------------------------------------------------------------------------------
@@ -345,34 +364,40 @@ template <class F> void launch3d(const F& f, int nx, int ny, int nz) {
 }
 // stencil stages: every thread handles KPT consecutive levels of one (i, j): the 2-D metric loads, the
 // cube-edge branch conditions and the index set-up are level-invariant and get shared across them
-constexpr int KPT = 1;   // (2 was tried: ptxas does not share work across the unrolled levels, no gain)
+// (an unrolled variant was tried in round 1: ptxas did not share work across the unrolled levels; the loop in F::run is not unrolled
+// and the context is built once, so loop-invariant code motion does the sharing.)  FV3LM_KPT overrides the default.
+inline int stage_kpt() { static const int k = getenv("FV3LM_KPT") ? std::max(1, atoi(getenv("FV3LM_KPT"))) : 1; return k; }
 // blockIdx.z = tile * nkc + level chunk.  The quotient comes from a float multiply: (z + 0.5) / nkc is at least 0.5 / nkc away from
 // an integer and z < 2^16, so the rounding error of the product (< 1e-5) cannot change the truncation -- exact, 3 instructions
 // instead of the ~20 of an integer division by a run-time divisor.
 DEV int fast_div_small(int z, float inv) { return (int)(((float)z + 0.5f) * inv); }
-template <class F> GLOBAL void kern_stage(const __grid_constant__ F f, int nx, int ny, int nk, int nkc, float inv_nkc) {
+template <class F> GLOBAL void kern_stage(const __grid_constant__ F f, int nx, int ny, int nk, int nkc, float inv_nkc, int kpt) {
   int ii = blockIdx.x * blockDim.x + threadIdx.x;
   int jj = blockIdx.y * blockDim.y + threadIdx.y;
   if (ii >= nx || jj >= ny) return;
-  const int tile = fast_div_small(blockIdx.z, inv_nkc), k0 = (blockIdx.z - tile * nkc) * KPT;
-#pragma unroll
-  for (int q = 0; q < KPT; q++) {
-    const int k = k0 + q;
-    if (k < nk) f(ii, jj, k, tile);
-  }
+  const int tile = fast_div_small(blockIdx.z, inv_nkc), k0 = (blockIdx.z - tile * nkc) * kpt;
+  const int k1 = k0 + kpt < nk ? k0 + kpt : nk;
+  if (kpt == 1) f(ii, jj, k0, tile);
+  else f.run(ii, jj, k0, k1, tile);
 }
 template <class F> void launch_stage(const F& f, int nx, int ny, int ntile, int nk) {
   if (ntile * nk <= 0) return;
-  const int nkc = (nk + KPT - 1) / KPT;
+  const int kpt = stage_kpt(), nkc = (nk + kpt - 1) / kpt;
   dim3 b(32, 8, 1), gr((nx + 31) / 32, (ny + 7) / 8, ntile * nkc);
-  kern_stage<F><<<gr, b, 0, dev::stream()>>>(f, nx, ny, nk, nkc, 1.0f / (float)nkc);
+  kern_stage<F><<<gr, b, 0, dev::stream()>>>(f, nx, ny, nk, nkc, 1.0f / (float)nkc, kpt);
   dev::launches++;
 }
 #else
+inline int stage_kpt() { static const int k = getenv("FV3LM_KPT") ? std::max(1, atoi(getenv("FV3LM_KPT"))) : 1; return k; }
 template <class F> void launch_stage(const F& f, int nx, int ny, int ntile, int nk) {
-  for (int z = 0; z < ntile * nk; z++)
-    for (int jj = 0; jj < ny; jj++)
-      for (int ii = 0; ii < nx; ii++) f(ii, jj, z % nk, z / nk);
+  const int kpt = stage_kpt();
+  for (int t = 0; t < ntile; t++)
+    for (int k0 = 0; k0 < nk; k0 += kpt)
+      for (int jj = 0; jj < ny; jj++)
+        for (int ii = 0; ii < nx; ii++) {
+          if (kpt == 1) f(ii, jj, k0, t);
+          else f.run(ii, jj, k0, std::min(k0 + kpt, nk), t);
+        }
   dev::launches++;
 }
 template <class F> void launch3d(const F& f, int nx, int ny, int nz) {

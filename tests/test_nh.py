@@ -13,10 +13,13 @@ RD = 8314.47 / 28.965
 NHCFG = dict(CFG); NHCFG.update(rdgas=RD, grav=9.80665, p_fac=0.05)
 
 
-def column_state(N, K, seed):
+def column_state(N, K, seed, eta_levels=None):
     rng = np.random.default_rng(seed)
     ptop = CFG["ptop"]
     ak, bk = eta(K, ptop)
+    if eta_levels is not None:          # (ak, bk) given by the caller, e.g. the bench's 72 levels with ptop = 1 Pa
+        ak, bk = eta_levels
+        ptop = float(ak[0])
     ps = 1.0e5 + 300.0 * rnd(rng, N, 1)
     pe = ak[None, :, None, None] + bk[None, :, None, None] * ps
     delp = (pe[:, 1:] - pe[:, :-1]) * (1.0 + 0.02 * rnd(rng, N, K))
@@ -32,12 +35,14 @@ def column_state(N, K, seed):
     return dict(delp=delp, pt=pt, z=z, w=w, ws=ws, zb=zb), rng, ak, bk
 
 
-def _run_riem(emu, mode, a_imp=1.0):
-    N, K = 12, 5
-    f, rng, ak, bk = column_state(N, K, 3 + mode)
+def _run_riem(emu, mode, a_imp=1.0, K=5, eta_levels=None):
+    N = 12
+    f, rng, ak, bk = column_state(N, K, 3 + mode, eta_levels)
     dts = 150.0
     g = ograd(N)
     cfg = dict(NHCFG); cfg["a_imp"] = a_imp
+    if eta_levels is not None:
+        cfg["ptop"] = float(ak[0])
     if mode == 0:
         f["z"] = f["z"] * cfg["grav"]; f["zb"] = f["zb"] * cfg["grav"]   # Riem_Solver_c works on gz and phis
         def fn(delp, pt, z, w, ws, zb):
@@ -53,7 +58,7 @@ def _run_riem(emu, mode, a_imp=1.0):
         nk = dict(pp=K + 1, z_n=K + 1, w_n=K, dz_n=K)
     C = (0, N + 1, 0, N + 1) if mode == 0 else (1, N, 1, N)
     outs = {o: C for o in onames}
-    h = handle(N, K, emu, ak, bk)
+    h = handle(N, K, emu, ak, bk, ptop=cfg["ptop"]) if eta_levels is not None else handle(N, K, emu, ak, bk)
     p = dict(mode=mode, dts=dts, ptop=cfg["ptop"], akap=cfg["akap"], rdgas=cfg["rdgas"], grav=cfg["grav"], a_imp=a_imp)
     return check_module(h, "riem", N, K, f, list(f.keys()), outs, fn, p, rng, tol=1e-10, dot_tol=1e-11, pert_scale=1e-3, out_nk=nk)
 

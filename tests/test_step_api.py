@@ -51,9 +51,14 @@ def _run(emu, nonhydro=False, extra=None, taylor=True):
     full = {k: torch.from_numpy(f[k]) for k in ACT}
     o = ofv.step_nl(full, g, ak, bk, cfg, torch.from_numpy(f["phis"]))
     C = (slice(None), slice(None), R(1, N), R(1, N))
+    import common
+    errs = {}
     for k in ACT:
         ref = o[k][C].numpy()
-        assert np.abs(out[k] - ref).max() <= tol * max(np.abs(ref).max(), 1e-300), k
+        errs["nl." + k] = float(np.abs(out[k] - ref).max() / max(np.abs(ref).max(), 1e-300))
+    common.record(errs)
+    for k in ACT:
+        assert errs["nl." + k] <= tol, (k, errs["nl." + k])
     # ---- dot-product test  <M dx, y> = <dx, M^T y>
     dx = {k: rng.standard_normal(comp[k].shape) * (np.abs(comp[k]).mean() * 1e-3) for k in ACT}
     y = {k: rng.standard_normal(comp[k].shape) / (np.abs(comp[k]).mean() + 1e-30) for k in ACT}
@@ -63,6 +68,7 @@ def _run(emu, nonhydro=False, extra=None, taylor=True):
     h.step_ad(0, mty)
     lhs = sum((mdx[k] * y[k]).sum() for k in ACT)
     rhs = sum((dx[k] * mty[k]).sum() for k in ACT)
+    common.record(dict(dot=abs(lhs - rhs) / max(abs(lhs), abs(rhs))))
     assert abs(lhs - rhs) <= (1e-10 if nonhydro else 1e-11) * max(abs(lhs), abs(rhs)), (lhs, rhs)
     if not taylor:
         return dict(dot=abs(lhs - rhs) / max(abs(lhs), abs(rhs)))
@@ -83,6 +89,7 @@ def _run(emu, nonhydro=False, extra=None, taylor=True):
             den += ((eps * mdx[k] * sc) ** 2).sum()
         ratios.append(np.sqrt(num / den))
     # residual must shrink linearly with eps (second-order remainder)
+    common.record(dict(taylor=[float(r) for r in ratios]))
     assert ratios[1] < 0.2 * ratios[0] and ratios[2] < 0.2 * ratios[1] and ratios[3] < 0.2 * ratios[2], ratios
     return dict(dot=abs(lhs - rhs) / max(abs(lhs), abs(rhs)), taylor=ratios)
 
