@@ -53,6 +53,71 @@ template <class TT> struct TileCtx : CtxBase {
   DEV T in(int, int di = 0, int dj = 0, int = 0) const { return Num<TT>::lds(sv, sd, sp + dj * sw + di); }
 };
 
+// ---- lean tile machinery ---------------------------------------------------------------------------------------------
+// ncu of the first version of these kernels (profiles/r02e_*): 850 instructions per owned cell in the TL kernel B, 22 % of them fp64 --
+// the rest was per-cell index set-up (CtxBase::setpos / off with level clamps, rectangle tests, box look-ups).  Here everything that is
+// uniform over a block (level offset, rectangles clipped to the tile, index origin) is computed once per phase, a cell costs one
+// multiply-add for its offset, and the flux code sees a context that holds only what it reads.
+struct Rect {
+  int x0, x1, y0, y1;                       // inclusive, array coordinates
+  DEV bool has(int ii, int jj) const { return ii >= x0 && ii <= x1 && jj >= y0 && jj <= y1; }
+};
+DEV int imax(int a, int b) { return a > b ? a : b; }
+DEV int imin(int a, int b) { return a < b ? a : b; }
+struct Blk {                                // block-uniform geometry
+  int tile, kk, ii0, jj0;                   // sub-domain, level, array coordinates of the block's first cell
+  int ci, cj;                               // tile-global Fortran index = array index + ci / cj
+  int pitch, base, mb, NX, NY;              // row pitch, offset of (tile, level) in a 3-D field, of the tile in a 2-D metric
+  int xs, xe, ys, ye, ng;                   // compute domain is..ie, js..je in array coordinates; halo width
+  // the rectangle (il0..il1, jl0..jl1) of the local frame, shifted by (a, b, c, d), in array coordinates
+  DEV Rect rect(int a, int b, int c, int d) const { return Rect{xs + a, xe + b, ys + c, ye + d}; }
+  DEV Rect clip(Rect r, int x0, int x1, int y0, int y1) const {
+    return Rect{imax(imax(r.x0, x0), 0), imin(imin(r.x1, x1), NX - 1), imax(imax(r.y0, y0), 0), imin(imin(r.y1, y1), NY - 1)};
+  }
+  DEV int off(int ii, int jj) const { return base + jj * pitch + ii; }
+  DEV bool inside(int ii, int jj) const { return (unsigned)ii < (unsigned)NX && (unsigned)jj < (unsigned)NY; }
+};
+DEV Blk make_blk(const Geom& g, int nk, int bx, int by, int z) {
+  Blk b; split_z(z, nk, b.tile, b.kk);
+  b.ii0 = bx * TX; b.jj0 = by * TY;
+  const int lo = g.ng - 1;
+  b.ci = g.i0[b.tile] - lo; b.cj = g.j0[b.tile] - lo;
+  b.pitch = g.pitch; b.base = (b.tile * nk + b.kk) * g.slab; b.mb = b.tile * g.slab; b.NX = g.NX; b.NY = g.NY;
+  b.xs = g.is + lo; b.xe = g.ie + lo; b.ys = g.js + lo; b.ye = g.je + lo; b.ng = g.ng;
+  return b;
+}
+DEV Rect isect(Rect a, Rect b) { return Rect{imax(a.x0, b.x0), imin(a.x1, b.x1), imax(a.y0, b.y0), imin(a.y1, b.y1)}; }
+DEV bool rempty(Rect r) { return r.x1 < r.x0 || r.y1 < r.y0; }
+// "lean rectangle + generic complement": a phase evaluates its regular cells (a block-uniform rectangle: away from the cube edges and
+// the borders of the compute domain) with straight-line code, and the few cells of its box outside that rectangle -- up to four thin
+// strips, empty for most blocks -- with the stage's own generic eval(), densely mapped onto the block's threads.
+template <class F> DEV void for_strip(int tid, Rect s, F f) {
+  if (rempty(s)) return;
+  const int w = s.x1 - s.x0 + 1, n = w * (s.y1 - s.y0 + 1);
+  for (int c = tid; c < n; c += NTHR) { const int r = c / w; f(s.x0 + c - r * w, s.y0 + r); }
+}
+template <class F> DEV void for_complement(int tid, Rect box, Rect rr, F f) {
+  const Rect in = isect(box, rr);
+  if (rempty(in)) { for_strip(tid, box, f); return; }
+  for_strip(tid, Rect{box.x0, box.x1, box.y0, in.y0 - 1}, f);
+  for_strip(tid, Rect{box.x0, box.x1, in.y1 + 1, box.y1}, f);
+  for_strip(tid, Rect{box.x0, in.x0 - 1, in.y0, in.y1}, f);
+  for_strip(tid, Rect{in.x1 + 1, box.x1, in.y0, in.y1}, f);
+}
+// what tp::ppm_flux / ppm_coef / ppm_dc / S_ppm::al_w read: the tile, the Fortran index of the cell, npx / npy, dxa / dya
+template <class TT> struct LTile {
+  using T = TT;
+  static constexpr int mode = std::is_same<TT, double>::value ? 0 : 1;
+  struct { int npx, npy; } g;
+  struct { const double* dxa; const double* dya; } m;
+  const double* sv; const double* sd; int sw, sp;
+  int i, j, mpos, pitch;
+  DEV void init(const Geom& g_, const Metrics& m_) { g.npx = g_.npx; g.npy = g_.npy; m.dxa = m_.dxa; m.dya = m_.dya; pitch = g_.pitch; sd = nullptr; }
+  DEV void at(const Blk& b, int ii, int jj) { i = ii + b.ci; j = jj + b.cj; mpos = b.mb + jj * b.pitch + ii; }
+  DEV T in(int, int di = 0, int dj = 0, int = 0) const { return Num<TT>::lds(sv, sd, sp + dj * sw + di); }
+  DEV double M(const double* a, int di = 0, int dj = 0) const { return LDG(a + (mpos + dj * pitch + di)); }
+};
+
 // ---- kernel A: inner y sweep, outer x sweep ------------------------------------------------------------
 template <class TT, bool FULL> struct KernTpA {
   static constexpr bool TLM = !std::is_same<TT, double>::value;
@@ -62,48 +127,47 @@ template <class TT, bool FULL> struct KernTpA {
   struct Smem { SBuf<TLM, QW * QH> q; SBuf<TLM, QW*(TY + 1)> fy; SBuf<TLM, QW * TY> qi; };
   DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
     using N = Num<TT>;
-    int tile, kk; split_z(z, nk, tile, kk);
-    const int ii0 = bx * TX, jj0 = by * TY;
-    const int i0 = g.i0[tile], j0 = g.j0[tile];
-    const int is = g.is, ie = g.ie, js = g.js, je = g.je, isd = is - g.ng, ied = ie + g.ng;
-    TileCtx<TT> x; x.g = g; x.m = m;
+    const Blk b = make_blk(g, nk, bx, by, z);
+    const int ii0 = b.ii0, jj0 = b.jj0, od = ord.v[b.kk];
     if (ph == 0) {                 // q with its footprint
       for (int c = tid; c < QW * QH; c += NTHR) {
         const int ii = ii0 - 3 + c % QW, jj = jj0 - 3 + c / QW;
         TT a = TT(0.0);
-        if (ii >= 0 && ii < g.NX && jj >= 0 && jj < g.NY) { x.setpos(ii, jj, kk, tile, i0, j0); a = N::ld(q, x.off(q.nk, 0, 0, 0)); }
+        if (b.inside(ii, jj)) a = N::ld(q, b.off(ii, jj));
         N::sts(s.q.v, s.q.d, c, a);
       }
     } else if (ph == 1) {          // fy2 = yppm(q, cry) on (isd:ied, js:je+1)
+      const Rect r = b.clip(b.rect(-b.ng, b.ng, 0, 1), ii0 - 3, ii0 + TX + 2, jj0, jj0 + TY);
+      LTile<TT> x; x.init(g, m); x.sv = s.q.v; x.sd = s.q.d; x.sw = QW;
       for (int c = tid; c < QW * (TY + 1); c += NTHR) {
-        const int ii = ii0 - 3 + c % QW, jj = jj0 + c / QW;
-        if (ii < 0 || ii >= g.NX || jj >= g.NY) continue;
-        x.setpos(ii, jj, kk, tile, i0, j0);
-        if (!x.in_rect(isd, ied, js, je + 1)) continue;
-        x.sv = s.q.v; x.sd = s.q.d; x.sw = QW; x.sp = (jj - jj0 + 3) * QW + (ii - ii0 + 3);
-        const TT f = tp::ppm_flux<1, FULL>(x, 0, N::ld(cry, x.off(cry.nk, 0, 0, 0)), ord.v[kk]);
+        const int cx = c % QW, cy = c / QW, ii = ii0 - 3 + cx, jj = jj0 + cy;
+        if (!r.has(ii, jj)) continue;
+        const int o = b.off(ii, jj);
+        x.at(b, ii, jj); x.sp = (cy + 3) * QW + cx;
+        const TT f = tp::ppm_flux<1, FULL>(x, 0, N::ld(cry, o), od);
         N::sts(s.fy.v, s.fy.d, c, f);
-        if (ii >= ii0 && ii < ii0 + TX && jj < jj0 + TY) N::st(fy2, x.off(fy2.nk, 0, 0, 0), f);
+        if (cx >= 3 && cx < TX + 3 && cy < TY) N::st(fy2, o, f);
       }
     } else if (ph == 2) {          // q_i = (q area + yfx fy2 (j) - yfx fy2 (j+1)) / ra_y on (isd:ied, js:je)
+      const Rect r = b.clip(b.rect(-b.ng, b.ng, 0, 0), ii0 - 3, ii0 + TX + 2, jj0, jj0 + TY - 1);
       for (int c = tid; c < QW * TY; c += NTHR) {
-        const int ii = ii0 - 3 + c % QW, jj = jj0 + c / QW;
-        if (ii < 0 || ii >= g.NX || jj >= g.NY) continue;
-        x.setpos(ii, jj, kk, tile, i0, j0);
-        if (!x.in_rect(isd, ied, js, je)) continue;
-        const TT f0 = N::ld(yfx, x.off(yfx.nk, 0, 0, 0)) * N::lds(s.fy.v, s.fy.d, c);
-        const TT f1 = N::ld(yfx, x.off(yfx.nk, 0, 1, 0)) * N::lds(s.fy.v, s.fy.d, c + QW);
-        const TT qq = N::lds(s.q.v, s.q.d, (jj - jj0 + 3) * QW + (ii - ii0 + 3));
-        N::sts(s.qi.v, s.qi.d, c, (qq * x.M(x.m.area) + f0 - f1) / N::ld(ray, x.off(ray.nk, 0, 0, 0)));
+        const int cx = c % QW, cy = c / QW, ii = ii0 - 3 + cx, jj = jj0 + cy;
+        if (!r.has(ii, jj)) continue;
+        const int o = b.off(ii, jj);
+        const TT f0 = N::ld(yfx, o) * N::lds(s.fy.v, s.fy.d, c);
+        const TT f1 = N::ld(yfx, o + b.pitch) * N::lds(s.fy.v, s.fy.d, c + QW);
+        const TT qq = N::lds(s.q.v, s.q.d, (cy + 3) * QW + cx);
+        N::sts(s.qi.v, s.qi.d, c, (qq * LDG(m.area + (b.mb + jj * b.pitch + ii)) + f0 - f1) / N::ld(ray, o));
       }
     } else {                       // fx_ou = xppm(q_i, crx) on (is:ie+1, js:je)
+      const Rect r = b.clip(b.rect(0, 1, 0, 0), ii0, ii0 + TX - 1, jj0, jj0 + TY - 1);
+      LTile<TT> x; x.init(g, m); x.sv = s.qi.v; x.sd = s.qi.d; x.sw = QW;
       for (int c = tid; c < TX * TY; c += NTHR) {
-        const int ii = ii0 + c % TX, jj = jj0 + c / TX;
-        if (ii >= g.NX || jj >= g.NY) continue;
-        x.setpos(ii, jj, kk, tile, i0, j0);
-        if (!x.in_rect(is, ie + 1, js, je)) continue;
-        x.sv = s.qi.v; x.sd = s.qi.d; x.sw = QW; x.sp = (jj - jj0) * QW + (ii - ii0 + 3);
-        N::st(fxo, x.off(fxo.nk, 0, 0, 0), tp::ppm_flux<0, FULL>(x, 0, N::ld(crx, x.off(crx.nk, 0, 0, 0)), ord.v[kk]));
+        const int cx = c % TX, cy = c / TX, ii = ii0 + cx, jj = jj0 + cy;
+        if (!r.has(ii, jj)) continue;
+        const int o = b.off(ii, jj);
+        x.at(b, ii, jj); x.sp = cy * QW + cx + 3;
+        N::st(fxo, o, tp::ppm_flux<0, FULL>(x, 0, N::ld(crx, o), od));
       }
     }
   }
@@ -119,54 +183,52 @@ template <class TT, bool FULL> struct KernTpB {
   struct Smem { SBuf<TLM, QW * QH> q; SBuf<TLM, FW * QH> fx; SBuf<TLM, TX * QH> qj; };
   DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
     using N = Num<TT>;
-    int tile, kk; split_z(z, nk, tile, kk);
-    const int ii0 = bx * TX, jj0 = by * TY;
-    const int i0 = g.i0[tile], j0 = g.j0[tile];
-    const int is = g.is, ie = g.ie, js = g.js, je = g.je, jsd = js - g.ng, jed = je + g.ng;
-    TileCtx<TT> x; x.g = g; x.m = m;
+    const Blk b = make_blk(g, nk, bx, by, z);
+    const int ii0 = b.ii0, jj0 = b.jj0, od = ord.v[b.kk];
     if (ph == 0) {
       for (int c = tid; c < QW * QH; c += NTHR) {
         const int ii = ii0 - 3 + c % QW, jj = jj0 - 3 + c / QW;
         TT a = TT(0.0);
-        if (ii >= 0 && ii < g.NX && jj >= 0 && jj < g.NY) { x.setpos(ii, jj, kk, tile, i0, j0); a = N::ld(q, x.off(q.nk, 0, 0, 0)); }
+        if (b.inside(ii, jj)) a = N::ld(q, b.off(ii, jj));
         N::sts(s.q.v, s.q.d, c, a);
       }
     } else if (ph == 1) {          // fx2 = xppm(q, crx) on (is:ie+1, jsd:jed)
+      const Rect r = b.clip(b.rect(0, 1, -b.ng, b.ng), ii0, ii0 + TX, jj0 - 3, jj0 + TY + 2);
+      LTile<TT> x; x.init(g, m); x.sv = s.q.v; x.sd = s.q.d; x.sw = QW;
       for (int c = tid; c < FW * QH; c += NTHR) {
-        const int ii = ii0 + c % FW, jj = jj0 - 3 + c / FW;
-        if (ii >= g.NX || jj < 0 || jj >= g.NY) continue;
-        x.setpos(ii, jj, kk, tile, i0, j0);
-        if (!x.in_rect(is, ie + 1, jsd, jed)) continue;
-        x.sv = s.q.v; x.sd = s.q.d; x.sw = QW; x.sp = (jj - jj0 + 3) * QW + (ii - ii0 + 3);
-        N::sts(s.fx.v, s.fx.d, c, tp::ppm_flux<0, FULL>(x, 0, N::ld(crx, x.off(crx.nk, 0, 0, 0)), ord.v[kk]));
+        const int cx = c % FW, cy = c / FW, ii = ii0 + cx, jj = jj0 - 3 + cy;
+        if (!r.has(ii, jj)) continue;
+        x.at(b, ii, jj); x.sp = cy * QW + cx + 3;
+        N::sts(s.fx.v, s.fx.d, c, tp::ppm_flux<0, FULL>(x, 0, N::ld(crx, b.off(ii, jj)), od));
       }
     } else if (ph == 2) {          // q_j = (q area + xfx fx2 (i) - xfx fx2 (i+1)) / ra_x on (is:ie, jsd:jed)
+      const Rect r = b.clip(b.rect(0, 0, -b.ng, b.ng), ii0, ii0 + TX - 1, jj0 - 3, jj0 + TY + 2);
       for (int c = tid; c < TX * QH; c += NTHR) {
-        const int ii = ii0 + c % TX, jj = jj0 - 3 + c / TX;
-        if (ii >= g.NX || jj < 0 || jj >= g.NY) continue;
-        x.setpos(ii, jj, kk, tile, i0, j0);
-        if (!x.in_rect(is, ie, jsd, jed)) continue;
-        const int cf = (jj - jj0 + 3) * FW + (ii - ii0);
-        const TT f0 = N::ld(xfx, x.off(xfx.nk, 0, 0, 0)) * N::lds(s.fx.v, s.fx.d, cf);
-        const TT f1 = N::ld(xfx, x.off(xfx.nk, 1, 0, 0)) * N::lds(s.fx.v, s.fx.d, cf + 1);
-        const TT qq = N::lds(s.q.v, s.q.d, (jj - jj0 + 3) * QW + (ii - ii0 + 3));
-        N::sts(s.qj.v, s.qj.d, c, (qq * x.M(x.m.area) + f0 - f1) / N::ld(rax, x.off(rax.nk, 0, 0, 0)));
+        const int cx = c % TX, cy = c / TX, ii = ii0 + cx, jj = jj0 - 3 + cy;
+        if (!r.has(ii, jj)) continue;
+        const int o = b.off(ii, jj), cf = cy * FW + cx;
+        const TT f0 = N::ld(xfx, o) * N::lds(s.fx.v, s.fx.d, cf);
+        const TT f1 = N::ld(xfx, o + 1) * N::lds(s.fx.v, s.fx.d, cf + 1);
+        const TT qq = N::lds(s.q.v, s.q.d, cy * QW + cx + 3);
+        N::sts(s.qj.v, s.qj.d, c, (qq * LDG(m.area + (b.mb + jj * b.pitch + ii)) + f0 - f1) / N::ld(rax, o));
       }
     } else {                       // fy_ou = yppm(q_j, cry) on (is:ie, js:je+1); the two averages (tp_core_tlm.F90:2268-2313)
-      auto own = [&](int ii, int jj) {
-      if (ii >= g.NX || jj >= g.NY) return;
-      x.setpos(ii, jj, kk, tile, i0, j0);
-      if (x.in_rect(is, ie, js, je + 1)) {
-        x.sv = s.qj.v; x.sd = s.qj.d; x.sw = TX; x.sp = (jj - jj0 + 3) * TX + (ii - ii0);
-        const TT fyo = tp::ppm_flux<1, FULL>(x, 0, N::ld(cry, x.off(cry.nk, 0, 0, 0)), ord.v[kk]);
-        N::st(fy, x.off(fy.nk, 0, 0, 0), 0.5 * (fyo + N::ld(fy2, x.off(fy2.nk, 0, 0, 0))) * N::ld(my, x.off(my.nk, 0, 0, 0)));
+      const Rect ry = b.clip(b.rect(0, 0, 0, 1), ii0, ii0 + TX - 1, jj0, jj0 + TY - 1);
+      const Rect rx = b.clip(b.rect(0, 1, 0, 0), ii0, ii0 + TX - 1, jj0, jj0 + TY - 1);
+      LTile<TT> x; x.init(g, m); x.sv = s.qj.v; x.sd = s.qj.d; x.sw = TX;
+      for (int c = tid; c < TX * TY; c += NTHR) {
+        const int cx = c % TX, cy = c / TX, ii = ii0 + cx, jj = jj0 + cy;
+        const int o = b.off(ii, jj);
+        if (ry.has(ii, jj)) {
+          x.at(b, ii, jj); x.sp = (cy + 3) * TX + cx;
+          const TT fyo = tp::ppm_flux<1, FULL>(x, 0, N::ld(cry, o), od);
+          N::st(fy, o, 0.5 * (fyo + N::ld(fy2, o)) * N::ld(my, o));
+        }
+        if (rx.has(ii, jj)) {
+          const TT fx2 = N::lds(s.fx.v, s.fx.d, (cy + 3) * FW + cx);
+          N::st(fx, o, 0.5 * (N::ld(fxo, o) + fx2) * N::ld(mx, o));
+        }
       }
-      if (x.in_rect(is, ie + 1, js, je)) {
-        const TT fx2 = N::lds(s.fx.v, s.fx.d, (jj - jj0 + 3) * FW + (ii - ii0));
-        N::st(fx, x.off(fx.nk, 0, 0, 0), 0.5 * (N::ld(fxo, x.off(fxo.nk, 0, 0, 0)) + fx2) * N::ld(mx, x.off(mx.nk, 0, 0, 0)));
-      }
-      };
-      for (int c = tid; c < TX * TY; c += NTHR) own(ii0 + c % TX, jj0 + c / TX);
     }
   }
 };
@@ -272,7 +334,7 @@ template <int DIR, class X> DEV double ppm_dc(const X& x, double c, int ord) {
 
 template <int DIN, bool AVG> struct KernTpRev {
   static constexpr int DOUT = 1 - DIN;
-  static constexpr int NPH = 5;
+  static constexpr int NPH = 6;
   static constexpr int TA = DIN == 0 ? TX : TY, TB = DIN == 0 ? TY : TX;
   Geom g; Metrics m; LevOrd ord; int nk;
   // values: transported field, inner Courant number / flux area / ra, outer Courant number; AVG: the other two fluxes and the multipliers
@@ -281,10 +343,31 @@ template <int DIN, bool AVG> struct KernTpRev {
   Fld aI, aO;
   // accumulated adjoints (.v = adjoint array, null = inactive)
   OFld q_ad, ci_ad, fi_ad, ra_ad, co_ad, fin2_ad, fout2_ad, mI_ad, mO_ad;
-  struct Smem {
+  struct GenSmem {
     double q[QW * QH], Fi[(TA + 1) * (TB + 6)], qm[TA * (TB + 6)];
     double Fo_ad[(TA + 6) * (TB + 5)], qm_ad[(TA + 6) * TB], Fi_ad[(TA + 5) * TB];
   };
+  // ---- lean path (unlimited PPM, ord = 2): boxes with compile-time extents, relative to the block origin.  A box spans
+  // [a0 + LI, a0 + TA - 1 + HI] along the inner axis and [b0 + LO, b0 + TB - 1 + HO] along the outer one.
+  template <int LI, int HI, int LO, int HO> struct CB {
+    static constexpr int NI_ = TA + HI - LI, NO_ = TB + HO - LO;
+    static constexpr int W = DIN == 0 ? NI_ : NO_, H = DIN == 0 ? NO_ : NI_;
+    static constexpr int X0 = DIN == 0 ? LI : LO, Y0 = DIN == 0 ? LO : LI;     // relative to (ii0, jj0)
+    static constexpr int N = W * H;
+    static constexpr int SI = DIN == 0 ? 1 : W, SO = DIN == 0 ? W : 1;          // index steps along the inner / outer axis
+    DEV static int idx(int rx, int ry) { return (ry - Y0) * W + (rx - X0); }
+  };
+  using BQ = CB<-3, 3, -3, 3>;      // transported field
+  using BFI = CB<0, 1, -3, 3>;      // inner flux (values)
+  using BQM = CB<0, 0, -3, 3>;      // updated field (values)
+  using BT = CB<-3, 3, 0, 0>;       // t = qm_ad / ra
+  using BAO = CB<-3, 3, -2, 3>;     // adjoint of the outer flux and its Courant number
+  using BALO = CB<-3, 3, -1, 2>;    // adjoint of the outer sweep's edge values
+  using BFIAD = CB<-2, 3, 0, 0>;    // adjoint of the inner flux and its Courant number
+  using BALI = CB<-1, 2, 0, 0>;     // adjoint of the inner sweep's edge values
+  static constexpr int NU = (2 * BAO::N + BALO::N) > (2 * BFIAD::N + BALI::N) ? (2 * BAO::N + BALO::N) : (2 * BFIAD::N + BALI::N);
+  struct LeanSmem { double q[BQ::N], Fi[BFI::N], qm[BQM::N], t[BT::N], u[NU]; };   // u: outer-sweep tiles, then the inner-sweep ones
+  union Smem { GenSmem gen; LeanSmem lean; };
   DEV static int eIx() { return DIN == 0; }
   DEV static int eIy() { return DIN == 1; }
   DEV static int eOx() { return DIN == 1; }
@@ -301,7 +384,184 @@ template <int DIN, bool AVG> struct KernTpRev {
   DEV bool rect_fi(const CtxBase& x) const {  // AVG: where the averaged flux along I (fx) lives
     return x.in_rect(g.is, g.ie + 1, g.js, g.je);
   }
-  DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
+  DEV void phase(int ph, int tid, int bx, int by, int z, Smem& su) const {
+    int tile_, kk_; split_z(z, nk, tile_, kk_);
+    if (ord.v[kk_] == 2) lean_phase(ph, tid, bx, by, z, su.lean);
+    else if (ph < 5) gen_phase(ph, tid, bx, by, z, su.gen);
+  }
+  // d F / d qt, d F / d al0, d F / d (alm | alp) of the unlimited PPM flux, S_ppm::adjoint's formulas
+  DEV static void flux_partials(double c, double& dqt, double& dal0, double& dal2) {
+    if (c > 0.0) { dqt = 1.0 + (1.0 - c) * (2.0 * c - 1.0); dal0 = (1.0 - c) * (1.0 - c); dal2 = -(1.0 - c) * c; }
+    else { dqt = 1.0 - (1.0 + c) * (1.0 + 2.0 * c); dal0 = (1.0 + c) * (1.0 + c); dal2 = (1.0 + c) * c; }
+  }
+  // adjoint of the edge value AL(e) from the flux adjoints A and Courant numbers C of the faces e-1, e, e+1 (tile index n, step st):
+  // AL(e) is al0 of face e, alm of face e+1 (c > 0) and alp of face e-1 (c <= 0)
+  DEV static double edge_adjoint(const double* A, const double* C, int n, int st) {
+    double dqt, d0, d2, r = 0.0;
+    const double a0 = A[n], ap = A[n + st], am = A[n - st];
+    if (a0 != 0.0) { flux_partials(C[n], dqt, d0, d2); r += a0 * d0; }
+    if (ap != 0.0) { const double c = C[n + st]; if (c > 0.0) { flux_partials(c, dqt, d0, d2); r += ap * d2; } }
+    if (am != 0.0) { const double c = C[n - st]; if (!(c > 0.0)) { flux_partials(c, dqt, d0, d2); r += am * d2; } }
+    return r;
+  }
+  // adjoint of the cell value q(p) of a 1-D sweep along D: the faces p (c <= 0) and p+1 (c > 0) that use it as qt, and the four
+  // edge values AL(p-1 .. p+2) that it enters.  A, C: face tiles at index n (step st); AL: edge tile at index ne (step se).
+  template <int D, class X> DEV static double cell_adjoint(X& x, const Blk& b, int ii, int jj, const double* A, const double* C, int n, int st,
+                                                       const double* AL, int ne, int se) {
+    double dqt, d0, d2, r = 0.0;
+    const double a0 = A[n], ap = A[n + st];
+    if (a0 != 0.0) { const double c = C[n]; if (!(c > 0.0)) { flux_partials(c, dqt, d0, d2); r += a0 * dqt; } }
+    if (ap != 0.0) { const double c = C[n + st]; if (c > 0.0) { flux_partials(c, dqt, d0, d2); r += ap * dqt; } }
+    const int pos = (D == 0 ? ii + b.ci : jj + b.cj), np = D == 0 ? x.g.npx : x.g.npy;
+    if (pos >= 4 && pos <= np - 4) {
+      r += tp::p2 * (AL[ne - se] + AL[ne + 2 * se]) + tp::p1 * (AL[ne] + AL[ne + se]);
+    } else {
+#pragma unroll
+      for (int e = -1; e <= 2; e++) {
+        const double al = AL[ne + e * se];
+        if (al != 0.0) { x.at(b, ii + (D == 0 ? e : 0), jj + (D == 1 ? e : 0)); r += S_ppm<D>::al_w(x, 0, 2 - e) * al; }
+      }
+    }
+    return r;
+  }
+  DEV void lean_phase(int ph, int tid, int bx, int by, int z, LeanSmem& s) const {
+    const Blk b = make_blk(g, nk, bx, by, z);
+    const int ii0 = b.ii0, jj0 = b.jj0;
+    constexpr int eIx = DIN == 0, eIy = DIN == 1;
+    const int sI = DIN == 0 ? 1 : b.pitch;                       // global index step along the inner axis
+    const Rect r_i = DIN == 0 ? b.rect(0, 1, -b.ng, b.ng) : b.rect(-b.ng, b.ng, 0, 1);
+    const Rect r_m = DIN == 0 ? b.rect(0, 0, -b.ng, b.ng) : b.rect(-b.ng, b.ng, 0, 0);
+    const Rect r_o = DIN == 0 ? b.rect(0, 0, 0, 1) : b.rect(0, 1, 0, 0);
+    const Rect r_fi = b.rect(0, 1, 0, 0);
+    double* AO = s.u; double* CO = s.u + BAO::N; double* ALO = s.u + 2 * BAO::N;
+    double* FA = s.u; double* CI = s.u + BFIAD::N; double* ALI = s.u + 2 * BFIAD::N;
+    LTile<double> x; x.init(g, m);
+    if (ph == 0) {
+      for (int c = tid; c < BQ::N; c += NTHR) {
+        const int ii = ii0 + BQ::X0 + c % BQ::W, jj = jj0 + BQ::Y0 + c / BQ::W;
+        s.q[c] = b.inside(ii, jj) ? LDG(q.v + b.off(ii, jj)) : 0.0;
+      }
+      for (int c = tid; c < BAO::N; c += NTHR) {
+        const int ii = ii0 + BAO::X0 + c % BAO::W, jj = jj0 + BAO::Y0 + c / BAO::W;
+        double a = 0.0, cc = 0.0;
+        if (r_o.has(ii, jj)) {
+          const int o = b.off(ii, jj);
+          a = LDG(aO.v + o); cc = LDG(co.v + o);
+          if (AVG && a != 0.0) a *= 0.5 * LDG(mO.v + o);
+        }
+        AO[c] = a; CO[c] = cc;
+      }
+    } else if (ph == 1) {
+      x.sv = s.q; x.sw = BQ::W;
+      for (int c = tid; c < BFI::N; c += NTHR) {
+        const int rx = BFI::X0 + c % BFI::W, ry = BFI::Y0 + c / BFI::W, ii = ii0 + rx, jj = jj0 + ry;
+        if (!r_i.has(ii, jj)) continue;
+        x.at(b, ii, jj); x.sp = BQ::idx(rx, ry);
+        s.Fi[c] = tp::ppm_flux<DIN, false>(x, 0, LDG(ci.v + b.off(ii, jj)), 2);
+      }
+      for (int c = tid; c < BALO::N; c += NTHR) {
+        const int rx = BALO::X0 + c % BALO::W, ry = BALO::Y0 + c / BALO::W;
+        ALO[c] = edge_adjoint(AO, CO, BAO::idx(rx, ry), BAO::SO);
+      }
+    } else if (ph == 2) {
+      for (int c = tid; c < BQM::N; c += NTHR) {
+        const int rx = BQM::X0 + c % BQM::W, ry = BQM::Y0 + c / BQM::W, ii = ii0 + rx, jj = jj0 + ry;
+        if (!r_m.has(ii, jj)) continue;
+        const int o = b.off(ii, jj), nf = BFI::idx(rx, ry);
+        const double f0 = LDG(fi.v + o) * s.Fi[nf], f1 = LDG(fi.v + o + sI) * s.Fi[nf + BFI::SI];
+        s.qm[c] = (s.q[BQ::idx(rx, ry)] * LDG(m.area + (b.mb + jj * b.pitch + ii)) + f0 - f1) / LDG(ra.v + o);
+      }
+      for (int c = tid; c < BT::N; c += NTHR) {
+        const int rx = BT::X0 + c % BT::W, ry = BT::Y0 + c / BT::W, ii = ii0 + rx, jj = jj0 + ry;
+        double t = 0.0;
+        if (r_m.has(ii, jj)) {
+          const double qa = cell_adjoint<DOUT>(x, b, ii, jj, AO, CO, BAO::idx(rx, ry), BAO::SO, ALO, BALO::idx(rx, ry), BALO::SO);
+          if (qa != 0.0) t = qa / LDG(ra.v + b.off(ii, jj));
+        }
+        s.t[c] = t;
+      }
+    } else if (ph == 3) {
+      for (int c = tid; c < BFIAD::N; c += NTHR) {
+        const int rx = BFIAD::X0 + c % BFIAD::W, ry = BFIAD::Y0 + c / BFIAD::W, ii = ii0 + rx, jj = jj0 + ry;
+        double a = 0.0, cc = 0.0;
+        if (r_i.has(ii, jj)) {
+          const int o = b.off(ii, jj);
+          cc = LDG(ci.v + o);
+          if (AVG) { if (r_fi.has(ii, jj)) { a = LDG(aI.v + o); if (a != 0.0) a *= 0.5 * LDG(mI.v + o); } }
+          else a = LDG(aI.v + o);
+          const int nt = BT::idx(rx, ry);
+          const double dt = s.t[nt] - s.t[nt - BT::SI];
+          if (dt != 0.0) a += LDG(fi.v + o) * dt;
+        }
+        FA[c] = a; CI[c] = cc;
+      }
+    } else if (ph == 4) {
+      for (int c = tid; c < BALI::N; c += NTHR) {
+        const int rx = BALI::X0 + c % BALI::W, ry = BALI::Y0 + c / BALI::W;
+        ALI[c] = edge_adjoint(FA, CI, BFIAD::idx(rx, ry), BFIAD::SI);
+      }
+    } else {
+      for (int c = tid; c < TX * TY; c += NTHR) {
+        const int rx = c % TX, ry = c / TX, ii = ii0 + rx, jj = jj0 + ry;
+        if (!b.inside(ii, jj)) continue;
+        const int o = b.off(ii, jj);
+        const bool in_i = r_i.has(ii, jj), in_m = r_m.has(ii, jj), in_o = r_o.has(ii, jj);
+        const int nt = BT::idx(rx, ry);
+        double aq = 0.0;
+        if (in_m) {
+          const double tt = s.t[nt];
+          if (tt != 0.0) {
+            aq += tt * LDG(m.area + (b.mb + jj * b.pitch + ii));
+            if (ra_ad.v) ra_ad.v[o] += -s.qm[BQM::idx(rx, ry)] * tt;
+          }
+        }
+        if (in_i) {
+          if (fi_ad.v) {
+            const double dt = s.t[nt] - s.t[nt - BT::SI];
+            if (dt != 0.0) fi_ad.v[o] += s.Fi[BFI::idx(rx, ry)] * dt;
+          }
+          const double fa = FA[BFIAD::idx(rx, ry)];
+          if (ci_ad.v && fa != 0.0) {
+            x.sv = s.q; x.sw = BQ::W; x.sp = BQ::idx(rx, ry); x.at(b, ii, jj);
+            ci_ad.v[o] += ppm_dc<DIN>(x, LDG(ci.v + o), 2) * fa;
+          }
+        }
+        if (in_o) {
+          double oa = LDG(aO.v + o);
+          if (AVG && oa != 0.0) oa *= 0.5 * LDG(mO.v + o);
+          if (co_ad.v && oa != 0.0) {
+            x.sv = s.qm; x.sw = BQM::W; x.sp = BQM::idx(rx, ry); x.at(b, ii, jj);
+            co_ad.v[o] += ppm_dc<DOUT>(x, LDG(co.v + o), 2) * oa;
+          }
+        }
+        if (AVG) {
+          if (in_o) {             // fy = 0.5 (Fo + fy2) mO
+            const double a = LDG(aO.v + o);
+            if (a != 0.0) {
+              if (fin2_ad.v) fin2_ad.v[o] += 0.5 * LDG(mO.v + o) * a;
+              if (mO_ad.v) {
+                x.sv = s.qm; x.sw = BQM::W; x.sp = BQM::idx(rx, ry); x.at(b, ii, jj);
+                const double Fo = tp::ppm_flux<DOUT, false>(x, 0, LDG(co.v + o), 2);
+                mO_ad.v[o] += 0.5 * (Fo + LDG(fin2.v + o)) * a;
+              }
+            }
+          }
+          if (r_fi.has(ii, jj)) {       // fx = 0.5 (fx_ou + Fi) mI
+            const double a = LDG(aI.v + o);
+            if (a != 0.0) {
+              if (fout2_ad.v) fout2_ad.v[o] += 0.5 * LDG(mI.v + o) * a;
+              if (mI_ad.v) mI_ad.v[o] += 0.5 * (LDG(fout2.v + o) + s.Fi[BFI::idx(rx, ry)]) * a;
+            }
+          }
+        }
+        if (q_ad.v) {
+          aq += cell_adjoint<DIN>(x, b, ii, jj, FA, CI, BFIAD::idx(rx, ry), BFIAD::SI, ALI, BALI::idx(rx, ry), BALI::SI);
+          if (aq != 0.0) q_ad.v[o] += aq;
+        }
+      }
+    }
+  }
+  DEV void gen_phase(int ph, int tid, int bx, int by, int z, GenSmem& s) const {
     int tile, kk; split_z(z, nk, tile, kk);
     const int ii0 = bx * TX, jj0 = by * TY;
     const int i0 = g.i0[tile], j0 = g.j0[tile];
