@@ -180,7 +180,7 @@ def run_gpu(args):
                         fh.write("%-28s %5d %10.3f %9.1f %6.2f%%\n" % (r[0], r[1], r[2], (r[3] / (r[2] * 1e-3) / 1e9 if r[2] > 0 else 0.0), 100.0 * r[2] / ptot))
             side["pool_peak_gb"] = float(h.lib.fv3lm_pool_peak_bytes(h.h)) / 1e9
         if rank == 0:
-            out = {"kernel_only": True, "fused_tp": int(os.environ.get("FV3LM_FUSED_TP", "0") or 0), "fused_a2b": int(os.environ.get("FV3LM_FUSED_A2B", "0") or 0),
+            out = {"kernel_only": True, "fused_tp": int(os.environ.get("FV3LM_FUSED_TP", "2") or 0), "fused_a2b": int(os.environ.get("FV3LM_FUSED_A2B", "0") or 0),
                    "fused_chain": int(os.environ.get("FV3LM_FUSED_CHAIN", "0") or 0), "two_sided": bool(args.two_sided), "q_split_dynamic": int(args.q_split_dynamic), "res": N,
                    "tl_ms": ms_tl, "ad_ms": ms_ad, "gpu_launches": int(launches)}
             out.update(side)
@@ -259,7 +259,7 @@ def run_gpu(args):
         "config": {"workload": "C%d L%d %s dynamics-only TL+AD step, dt=%gs, n_split=%d, k_split=1, nq=4, linear schemes (hord=2, kord=17), whole sphere %s"
                                % (N, K, "hydrostatic" if hydro else "non-hydrostatic", dt, mc["n_split"],
                                   "on one GPU" if world == 1 else "sharded over %d GPUs (layout %dx%d, %d sub-domains per GPU)" % (world, h.lx, h.ly, h.nsub)),
-                   "fused_tp": int(os.environ.get("FV3LM_FUSED_TP", "0") or 0), "fused_a2b": int(os.environ.get("FV3LM_FUSED_A2B", "0") or 0),
+                   "fused_tp": int(os.environ.get("FV3LM_FUSED_TP", "2") or 0), "fused_a2b": int(os.environ.get("FV3LM_FUSED_A2B", "0") or 0),
                    "fused_chain": int(os.environ.get("FV3LM_FUSED_CHAIN", "0") or 0),
                    "l2": "working set (%.1f GB of fields per sweep) far exceeds the 126 MB L2" % (60 * field_bytes / 1e9),
                    "multi_gpu": ("cube sharded, halo exchange + adjoint halo accumulation over NCCL p2p (NVLink); %d exchanges, %.1f MB sent per rank so far"

@@ -189,79 +189,56 @@ template <class TT> struct KernA2b {
   static constexpr int NPH = 3;
   Geom g; Metrics m; int nk; Fld qin; OFld qout;
   struct Smem { SBuf<TLM, QW * QH> q; SBuf<TLM, TX * QH> qx; SBuf<TLM, QW * TY> qy; SBuf<TLM, (TX + 2) * (TY + 2)> qe; };
-  // Regular cells (a block-uniform rectangle away from the cube edges) run the uniform 4-point formulas straight from the tiles; the
-  // cells of a phase's box outside that rectangle run the stages' own eval() on tile contexts (for_complement, fused_tp.h).
   DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
     using N = Num<TT>;
-    const Blk b = make_blk(g, nk, bx, by, z);
-    const int ii0 = b.ii0, jj0 = b.jj0, kk = b.kk, tile = b.tile;
-    const int i0 = g.i0[tile], j0 = g.j0[tile], npx = g.npx, npy = g.npy;
+    int tile, kk; split_z(z, nk, tile, kk);
+    const int ii0 = bx * TX, jj0 = by * TY;
+    const int i0 = g.i0[tile], j0 = g.j0[tile];
     const Box bq{ii0 - 3, jj0 - 3, QW, QH}, bqx{ii0, jj0 - 3, TX, QH}, bqy{ii0 - 3, jj0, QW, TY}, bqe{ii0 - 1, jj0 - 1, TX + 2, TY + 2};
-    const Rect arr{0, b.NX - 1, 0, b.NY - 1};
+    auto inside = [&](int ii, int jj) { return ii >= 0 && ii < g.NX && jj >= 0 && jj < g.NY; };
     if (ph == 0) {
-      for (int c = tid; c < QW * QH; c += NTHR) {
-        const int ii = ii0 - 3 + c % QW, jj = jj0 - 3 + c / QW;
+      CtxBase x; x.g = g;
+      for (int c = tid; c < bq.n(); c += NTHR) {
+        const int ii = bq.x0 + c % bq.w, jj = bq.y0 + c / bq.w;
         TT a = TT(0.0);
-        if (b.inside(ii, jj)) a = N::ld(qin, b.off(ii, jj));
+        if (inside(ii, jj)) { x.setpos(ii, jj, kk, tile, i0, j0); a = N::ld(qin, x.off(qin.nk, 0, 0, 0)); }
         N::sts(s.q.v, s.q.d, c, a);
       }
     } else if (ph == 1) {
       TCtx<TT, 1, 1> x; x.g = g; x.m = m;
       x.ti[0] = TRef{s.q.v, s.q.d, bq}; x.gi[0] = Fld{nullptr, nullptr, 1}; x.go[0] = OFld{nullptr, nullptr, 1};
-      {   // qx: rows js-2..je+2 of the tile rows 1..npy-1; uniform weights on the faces 3..npx-2
-        const Rect rr{imax(b.xs, 3 - b.ci), imin(b.xe + 1, npx - 2 - b.ci), imax(b.ys - 2, 1 - b.cj), imin(b.ye + 2, npy - 1 - b.cj)};
-        for (int c = tid; c < TX * QH; c += NTHR) {
-          const int cx = c % TX, cy = c / TX, ii = ii0 + cx, jj = jj0 - 3 + cy;
-          if (!rr.has(ii, jj)) continue;
-          const int n = cy * QW + cx + 3;
-          N::sts(s.qx.v, s.qx.d, c, a2b::b2 * (N::lds(s.q.v, s.q.d, n - 2) + N::lds(s.q.v, s.q.d, n + 1)) + a2b::b1 * (N::lds(s.q.v, s.q.d, n - 1) + N::lds(s.q.v, s.q.d, n)));
-        }
-        x.to[0] = TOut{s.qx.v, s.qx.d, bqx};
-        for_complement(tid, isect(Rect{ii0, ii0 + TX - 1, jj0 - 3, jj0 + TY + 2}, arr), rr, [&](int ii, int jj) {
-          x.setpos(ii, jj, kk, tile, i0, j0);
-          S_a2b_q1<0>::eval(x, {0});
-        });
+      x.to[0] = TOut{s.qx.v, s.qx.d, bqx};
+      for (int c = tid; c < bqx.n(); c += NTHR) {
+        const int ii = bqx.x0 + c % bqx.w, jj = bqx.y0 + c / bqx.w;
+        if (!inside(ii, jj)) continue;
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        S_a2b_q1<0>::eval(x, {0});
       }
-      {   // qy
-        const Rect rr{imax(b.xs - 2, 1 - b.ci), imin(b.xe + 2, npx - 1 - b.ci), imax(b.ys, 3 - b.cj), imin(b.ye + 1, npy - 2 - b.cj)};
-        for (int c = tid; c < QW * TY; c += NTHR) {
-          const int cx = c % QW, cy = c / QW, ii = ii0 - 3 + cx, jj = jj0 + cy;
-          if (!rr.has(ii, jj)) continue;
-          const int n = (cy + 3) * QW + cx;
-          N::sts(s.qy.v, s.qy.d, c, a2b::b2 * (N::lds(s.q.v, s.q.d, n - 2 * QW) + N::lds(s.q.v, s.q.d, n + QW)) + a2b::b1 * (N::lds(s.q.v, s.q.d, n - QW) + N::lds(s.q.v, s.q.d, n)));
-        }
-        x.to[0] = TOut{s.qy.v, s.qy.d, bqy};
-        for_complement(tid, isect(Rect{ii0 - 3, ii0 + TX + 2, jj0, jj0 + TY - 1}, arr), rr, [&](int ii, int jj) {
-          x.setpos(ii, jj, kk, tile, i0, j0);
-          S_a2b_q1<1>::eval(x, {0});
-        });
+      x.to[0] = TOut{s.qy.v, s.qy.d, bqy};
+      for (int c = tid; c < bqy.n(); c += NTHR) {
+        const int ii = bqy.x0 + c % bqy.w, jj = bqy.y0 + c / bqy.w;
+        if (!inside(ii, jj)) continue;
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        S_a2b_q1<1>::eval(x, {0});
       }
-      {   // qe exists on the tile boundary only
-        const Rect rr{2 - b.ci, npx - 1 - b.ci, 2 - b.cj, npy - 1 - b.cj};
-        x.to[0] = TOut{s.qe.v, s.qe.d, bqe};
-        for_complement(tid, isect(Rect{ii0 - 1, ii0 + TX, jj0 - 1, jj0 + TY}, arr), rr, [&](int ii, int jj) {
-          x.setpos(ii, jj, kk, tile, i0, j0);
-          S_a2b_edge::eval(x, {0});
-        });
+      x.to[0] = TOut{s.qe.v, s.qe.d, bqe};
+      for (int c = tid; c < bqe.n(); c += NTHR) {
+        const int ii = bqe.x0 + c % bqe.w, jj = bqe.y0 + c / bqe.w;
+        if (!inside(ii, jj)) continue;
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        S_a2b_edge::eval(x, {0});
       }
     } else {
-      const Rect rr{imax(b.xs, 3 - b.ci), imin(b.xe + 1, npx - 2 - b.ci), imax(b.ys, 3 - b.cj), imin(b.ye + 1, npy - 2 - b.cj)};
-      for (int c = tid; c < TX * TY; c += NTHR) {
-        const int cx = c % TX, cy = c / TX, ii = ii0 + cx, jj = jj0 + cy;
-        if (!rr.has(ii, jj)) continue;
-        const int nx = (cy + 3) * TX + cx, ny = cy * QW + cx + 3;
-        const TT qxx = a2b::a2 * (N::lds(s.qx.v, s.qx.d, nx - 2 * TX) + N::lds(s.qx.v, s.qx.d, nx + TX)) + a2b::a1 * (N::lds(s.qx.v, s.qx.d, nx - TX) + N::lds(s.qx.v, s.qx.d, nx));
-        const TT qyy = a2b::a2 * (N::lds(s.qy.v, s.qy.d, ny - 2) + N::lds(s.qy.v, s.qy.d, ny + 1)) + a2b::a1 * (N::lds(s.qy.v, s.qy.d, ny - 1) + N::lds(s.qy.v, s.qy.d, ny));
-        N::st(qout, b.off(ii, jj), 0.5 * (qxx + qyy));
-      }
       TCtx<TT, 3, 1> x; x.g = g; x.m = m;
       x.ti[0] = TRef{s.qx.v, s.qx.d, bqx}; x.ti[1] = TRef{s.qy.v, s.qy.d, bqy}; x.ti[2] = TRef{s.qe.v, s.qe.d, bqe};
       for (int f = 0; f < 3; f++) x.gi[f] = Fld{nullptr, nullptr, 1};
       x.to[0] = TOut{nullptr, nullptr, bq}; x.go[0] = qout;
-      for_complement(tid, isect(Rect{ii0, ii0 + TX - 1, jj0, jj0 + TY - 1}, arr), rr, [&](int ii, int jj) {
+      for (int c = tid; c < TX * TY; c += NTHR) {
+        const int ii = ii0 + c % TX, jj = jj0 + c / TX;
+        if (!inside(ii, jj)) continue;
         x.setpos(ii, jj, kk, tile, i0, j0);
         S_a2b_q2::eval(x, {0});
-      });
+      }
     }
   }
 };
@@ -272,99 +249,89 @@ struct KernA2bRev {
   Geom g; Metrics m; int nk; Fld aout; OFld qin_ad;      // .v = adjoint arrays
   struct Smem { double oad[UW * UH], qx_ad[UW * TY], qy_ad[TX * UH], qe_ad[(TX + 3) * (TY + 3)]; };
   DEV void phase(int ph, int tid, int bx, int by, int z, Smem& s) const {
-    const Blk b = make_blk(g, nk, bx, by, z);
-    const int ii0 = b.ii0, jj0 = b.jj0, kk = b.kk, tile = b.tile;
-    const int i0 = g.i0[tile], j0 = g.j0[tile], npx = g.npx, npy = g.npy;
+    int tile, kk; split_z(z, nk, tile, kk);
+    const int ii0 = bx * TX, jj0 = by * TY;
+    const int i0 = g.i0[tile], j0 = g.j0[tile];
     const Box bu{ii0 - 2, jj0 - 2, UW, UH}, bqx{ii0 - 2, jj0, UW, TY}, bqy{ii0, jj0 - 2, TX, UH}, bqe{ii0 - 1, jj0 - 1, TX + 3, TY + 3};
-    const Rect arr{0, b.NX - 1, 0, b.NY - 1};
+    auto inside = [&](int ii, int jj) { return ii >= 0 && ii < g.NX && jj >= 0 && jj < g.NY; };
     if (ph == 0) {
-      for (int c = tid; c < UW * UH; c += NTHR) {
-        const int ii = ii0 - 2 + c % UW, jj = jj0 - 2 + c / UW;
-        s.oad[c] = b.inside(ii, jj) ? LDG(aout.v + b.off(ii, jj)) : 0.0;
+      CtxBase x; x.g = g;
+      for (int c = tid; c < bu.n(); c += NTHR) {
+        const int ii = bu.x0 + c % bu.w, jj = bu.y0 + c / bu.w;
+        double a = 0.0;
+        if (inside(ii, jj)) { x.setpos(ii, jj, kk, tile, i0, j0); a = LDG(aout.v + x.off(aout.nk, 0, 0, 0)); }
+        s.oad[c] = a;
       }
     } else if (ph == 1) {
       // reverse of S_a2b_q2: the adjoints of qx, qy and qe where the last phase needs them
       TCtxLinAD<S_a2b_q2> x; x.g = g; x.m = m; x.oad[0] = s.oad; x.ob[0] = bu;
-      {   // qx(i, j) is read by the regular outputs (i, j-1 .. j+2) only: i in 3..npx-2, j in 5..npy-5 (the outputs of rows 2 and npy-1 reach two
-        // rows further), all inside the output rectangle
-        const Rect rr{imax(b.xs, 3 - b.ci), imin(b.xe + 1, npx - 2 - b.ci), imax(b.ys + 1, 5 - b.cj), imin(b.ye - 1, npy - 5 - b.cj)};
-        for (int c = tid; c < UW * TY; c += NTHR) {
-          const int cx = c % UW, cy = c / UW, ii = ii0 - 2 + cx, jj = jj0 + cy;
-          if (rr.has(ii, jj)) {
-            const double* ap = s.oad + (cy + 2) * UW + cx;
-            s.qx_ad[c] = 0.5 * (a2b::a2 * (ap[-UW] + ap[2 * UW]) + a2b::a1 * (ap[0] + ap[UW]));
-          } else if (!b.inside(ii, jj)) s.qx_ad[c] = 0.0;
+      auto fast = [&](int ii, int jj) {    // (S_a2b_q2::adjoint: uniform weights, qe not read)
+        x.setpos(ii, jj, kk, tile, i0, j0);
+        return x.i >= 5 && x.i <= g.npx - 5 && x.j >= 5 && x.j <= g.npy - 5 && x.il - 1 >= g.is && x.il + 2 <= g.ie + 1 && x.jl - 1 >= g.js && x.jl + 2 <= g.je + 1;
+      };
+      for (int c = tid; c < bqx.n(); c += NTHR) {
+        const int ii = bqx.x0 + c % bqx.w, jj = bqx.y0 + c / bqx.w;
+        double a = 0.0;
+        if (inside(ii, jj)) {
+          if (fast(ii, jj)) {
+            const double* ap = s.oad + bu.idx(ii, jj);
+            a = 0.5 * (a2b::a2 * (ap[-UW] + ap[2 * UW]) + a2b::a1 * (ap[0] + ap[UW]));
+          } else { x.acc = 0.0; TileLinGather<S_a2b_q2, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); a = x.acc; }
         }
-        for_complement(tid, isect(Rect{ii0 - 2, ii0 + TX + 2, jj0, jj0 + TY - 1}, arr), rr, [&](int ii, int jj) {
-          x.acc = 0.0; TileLinGather<S_a2b_q2, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0);
-          s.qx_ad[bqx.idx(ii, jj)] = x.acc;
-        });
+        s.qx_ad[c] = a;
       }
-      {
-        const Rect rr{imax(b.xs + 1, 5 - b.ci), imin(b.xe - 1, npx - 5 - b.ci), imax(b.ys, 3 - b.cj), imin(b.ye + 1, npy - 2 - b.cj)};
-        for (int c = tid; c < TX * UH; c += NTHR) {
-          const int cx = c % TX, cy = c / TX, ii = ii0 + cx, jj = jj0 - 2 + cy;
-          if (rr.has(ii, jj)) {
-            const double* ap = s.oad + cy * UW + cx + 2;
-            s.qy_ad[c] = 0.5 * (a2b::a2 * (ap[-1] + ap[2]) + a2b::a1 * (ap[0] + ap[1]));
-          } else if (!b.inside(ii, jj)) s.qy_ad[c] = 0.0;
+      for (int c = tid; c < bqy.n(); c += NTHR) {
+        const int ii = bqy.x0 + c % bqy.w, jj = bqy.y0 + c / bqy.w;
+        double a = 0.0;
+        if (inside(ii, jj)) {
+          if (fast(ii, jj)) {
+            const double* ap = s.oad + bu.idx(ii, jj);
+            a = 0.5 * (a2b::a2 * (ap[-1] + ap[2]) + a2b::a1 * (ap[0] + ap[1]));
+          } else { x.acc = 0.0; TileLinGather<S_a2b_q2, 1>::run(x, {0}, ii, jj, kk, tile, i0, j0); a = x.acc; }
         }
-        for_complement(tid, isect(Rect{ii0, ii0 + TX - 1, jj0 - 2, jj0 + TY + 2}, arr), rr, [&](int ii, int jj) {
-          x.acc = 0.0; TileLinGather<S_a2b_q2, 1>::run(x, {0}, ii, jj, kk, tile, i0, j0);
-          s.qy_ad[bqy.idx(ii, jj)] = x.acc;
-        });
+        s.qy_ad[c] = a;
       }
-      {   // qe only exists on the tile boundary
-        const Rect rr{2 - b.ci, npx - 1 - b.ci, 2 - b.cj, npy - 1 - b.cj};
-        for (int c = tid; c < (TX + 3) * (TY + 3); c += NTHR) {
-          const int ii = ii0 - 1 + c % (TX + 3), jj = jj0 - 1 + c / (TX + 3);
-          if (rr.has(ii, jj) || !b.inside(ii, jj)) s.qe_ad[c] = 0.0;
+      for (int c = tid; c < bqe.n(); c += NTHR) {
+        const int ii = bqe.x0 + c % bqe.w, jj = bqe.y0 + c / bqe.w;
+        double a = 0.0;
+        if (inside(ii, jj)) {
+          x.setpos(ii, jj, kk, tile, i0, j0);
+          if (x.i == 1 || x.i == g.npx || x.j == 1 || x.j == g.npy) {     // qe only exists on the tile boundary
+            x.acc = 0.0; TileLinGather<S_a2b_q2, 2>::run(x, {0}, ii, jj, kk, tile, i0, j0); a = x.acc;
+          }
         }
-        for_complement(tid, isect(Rect{ii0 - 1, ii0 + TX + 1, jj0 - 1, jj0 + TY + 1}, arr), rr, [&](int ii, int jj) {
-          x.acc = 0.0; TileLinGather<S_a2b_q2, 2>::run(x, {0}, ii, jj, kk, tile, i0, j0);
-          s.qe_ad[bqe.idx(ii, jj)] = x.acc;
-        });
+        s.qe_ad[c] = a;
       }
     } else {
-      if (!qin_ad.v) return;
-      // regular cells: the four qx faces i-1..i+2 and the four qy faces j-1..j+2 that read the cell all use the uniform weights, and no
-      // boundary value reads it (S_a2b_q1::adjoint, S_a2b_edge::adjoint)
-      const Rect rr{imax(b.xs + 1, 5 - b.ci), imin(b.xe - 1, npx - 5 - b.ci), imax(b.ys + 1, 5 - b.cj), imin(b.ye - 1, npy - 5 - b.cj)};
-      for (int c = tid; c < TX * TY; c += NTHR) {
-        const int cx = c % TX, cy = c / TX, ii = ii0 + cx, jj = jj0 + cy;
-        if (!rr.has(ii, jj)) continue;
-        const double* ax = s.qx_ad + cy * UW + cx + 2;
-        const double* ay = s.qy_ad + (cy + 2) * TX + cx;
-        const double acc = a2b::b2 * (ax[-1] + ax[2]) + a2b::b1 * (ax[0] + ax[1]) + (a2b::b2 * (ay[-TX] + ay[2 * TX]) + a2b::b1 * (ay[0] + ay[TX]));
-        if (acc != 0.0) qin_ad.v[b.off(ii, jj)] += acc;
+      auto own = [&](int ii, int jj) {
+      if (!inside(ii, jj) || !qin_ad.v) return;
+      double acc = 0.0;
+      CtxBase xb; xb.g = g; xb.setpos(ii, jj, kk, tile, i0, j0);
+      {   // reverse of qx = S_a2b_q1<0>(qin)  (fast path: S_a2b_q1::adjoint)
+        const bool fast = xb.i - 1 >= 4 && xb.i + 2 <= g.npx - 3 && xb.il - 1 >= g.is && xb.il + 2 <= g.ie + 1 &&
+                          xb.jl >= g.js - 2 && xb.jl <= g.je + 2 && xb.j >= 1 && xb.j <= g.npy - 1;
+        if (fast) { const double* ap = s.qx_ad + bqx.idx(ii, jj); acc += a2b::b2 * (ap[-1] + ap[2]) + a2b::b1 * (ap[0] + ap[1]); }
+        else {
+          TCtxLinAD<S_a2b_q1<0>> x; x.g = g; x.m = m; x.oad[0] = s.qx_ad; x.ob[0] = bqx; x.acc = 0.0;
+          TileLinGather<S_a2b_q1<0>, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); acc += x.acc;
+        }
       }
-      for_complement(tid, isect(Rect{ii0, ii0 + TX - 1, jj0, jj0 + TY - 1}, arr), rr, [&](int ii, int jj) {
-        double acc = 0.0;
-        CtxBase xb; xb.g = g; xb.setpos(ii, jj, kk, tile, i0, j0);
-        {   // reverse of qx = S_a2b_q1<0>(qin)  (fast path: S_a2b_q1::adjoint)
-          const bool fast = xb.i - 1 >= 4 && xb.i + 2 <= g.npx - 3 && xb.il - 1 >= g.is && xb.il + 2 <= g.ie + 1 &&
-                            xb.jl >= g.js - 2 && xb.jl <= g.je + 2 && xb.j >= 1 && xb.j <= g.npy - 1;
-          if (fast) { const double* ap = s.qx_ad + bqx.idx(ii, jj); acc += a2b::b2 * (ap[-1] + ap[2]) + a2b::b1 * (ap[0] + ap[1]); }
-          else {
-            TCtxLinAD<S_a2b_q1<0>> x; x.g = g; x.m = m; x.oad[0] = s.qx_ad; x.ob[0] = bqx; x.acc = 0.0;
-            TileLinGather<S_a2b_q1<0>, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); acc += x.acc;
-          }
+      {
+        const bool fast = xb.j - 1 >= 4 && xb.j + 2 <= g.npy - 3 && xb.jl - 1 >= g.js && xb.jl + 2 <= g.je + 1 &&
+                          xb.il >= g.is - 2 && xb.il <= g.ie + 2 && xb.i >= 1 && xb.i <= g.npx - 1;
+        if (fast) { const double* ap = s.qy_ad + bqy.idx(ii, jj); acc += a2b::b2 * (ap[-TX] + ap[2 * TX]) + a2b::b1 * (ap[0] + ap[TX]); }
+        else {
+          TCtxLinAD<S_a2b_q1<1>> x; x.g = g; x.m = m; x.oad[0] = s.qy_ad; x.ob[0] = bqy; x.acc = 0.0;
+          TileLinGather<S_a2b_q1<1>, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); acc += x.acc;
         }
-        {
-          const bool fast = xb.j - 1 >= 4 && xb.j + 2 <= g.npy - 3 && xb.jl - 1 >= g.js && xb.jl + 2 <= g.je + 1 &&
-                            xb.il >= g.is - 2 && xb.il <= g.ie + 2 && xb.i >= 1 && xb.i <= g.npx - 1;
-          if (fast) { const double* ap = s.qy_ad + bqy.idx(ii, jj); acc += a2b::b2 * (ap[-TX] + ap[2 * TX]) + a2b::b1 * (ap[0] + ap[TX]); }
-          else {
-            TCtxLinAD<S_a2b_q1<1>> x; x.g = g; x.m = m; x.oad[0] = s.qy_ad; x.ob[0] = bqy; x.acc = 0.0;
-            TileLinGather<S_a2b_q1<1>, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); acc += x.acc;
-          }
-        }
-        if (!(xb.i > 3 && xb.i < g.npx - 3 && xb.j > 3 && xb.j < g.npy - 3)) {      // (S_a2b_edge::adjoint: boundary outputs read at most two cells inwards)
-          TCtxLinAD<S_a2b_edge> x; x.g = g; x.m = m; x.oad[0] = s.qe_ad; x.ob[0] = bqe; x.acc = 0.0;
-          TileLinGather<S_a2b_edge, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); acc += x.acc;
-        }
-        if (acc != 0.0) qin_ad.v[b.off(ii, jj)] += acc;
-      });
+      }
+      if (!(xb.i > 3 && xb.i < g.npx - 3 && xb.j > 3 && xb.j < g.npy - 3)) {      // (S_a2b_edge::adjoint: boundary outputs read at most two cells inwards)
+        TCtxLinAD<S_a2b_edge> x; x.g = g; x.m = m; x.oad[0] = s.qe_ad; x.ob[0] = bqe; x.acc = 0.0;
+        TileLinGather<S_a2b_edge, 0>::run(x, {0}, ii, jj, kk, tile, i0, j0); acc += x.acc;
+      }
+      if (acc != 0.0) { xb.setpos(ii, jj, kk, tile, i0, j0); qin_ad.v[xb.off(qin_ad.nk, 0, 0, 0)] += acc; }
+      };
+      for (int c = tid; c < TX * TY; c += NTHR) own(ii0 + c % TX, jj0 + c / TX);
     }
   }
 };

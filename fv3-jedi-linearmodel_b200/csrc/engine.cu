@@ -284,7 +284,13 @@ void Program::run_sweeps(Mode mode) {
       if (dv->comm) budget = dv->comm->min_over_ranks(budget);   // same decision on every rank
       budget -= 2.0 * largest;                      // a segment being reversed holds trajectory + adjoints, plus the boundary values
       ad_keep_from = nseg - 1;                      // the last segment is always kept
+      const double budget0 = budget;
       while (ad_keep_from > 0 && seg_bytes[ad_keep_from - 1] <= budget) { budget -= seg_bytes[ad_keep_from - 1]; ad_keep_from--; }
+      if (getenv("FV3LM_DEBUG_SEG")) {
+        fprintf(stderr, "fv3lm %s: %d segments, budget %.2f GB (after 2 x largest %.2f GB), kept from %d; bytes (GB):", name.c_str(), nseg, budget0 / 1e9, largest / 1e9, ad_keep_from);
+        for (double b : seg_bytes) fprintf(stderr, " %.2f", b / 1e9);
+        fprintf(stderr, "\n");
+      }
     }
     const int keep_from = ad_keep_from;
     // pass 1: plain forward; segment-local values are freed at their last use, boundary-crossing ones stay

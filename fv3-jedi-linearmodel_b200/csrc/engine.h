@@ -366,7 +366,7 @@ template <class F> void launch3d(const F& f, int nx, int ny, int nz) {
 // cube-edge branch conditions and the index set-up are level-invariant and get shared across them
 // (an unrolled variant was tried in round 1: ptxas did not share work across the unrolled levels; the loop in F::run is not unrolled
 // and the context is built once, so loop-invariant code motion does the sharing.)  FV3LM_KPT overrides the default.
-inline int stage_kpt() { static const int k = getenv("FV3LM_KPT") ? std::max(1, atoi(getenv("FV3LM_KPT"))) : 1; return k; }
+inline int stage_kpt() { static const int k = getenv("FV3LM_KPT") ? std::max(1, atoi(getenv("FV3LM_KPT"))) : 4; return k; }
 // blockIdx.z = tile * nkc + level chunk.  The quotient comes from a float multiply: (z + 0.5) / nkc is at least 0.5 / nkc away from
 // an integer and z < 2^16, so the rounding error of the product (< 1e-5) cannot change the truncation -- exact, 3 instructions
 // instead of the ~20 of an integer division by a run-time divisor.
@@ -388,7 +388,7 @@ template <class F> void launch_stage(const F& f, int nx, int ny, int ntile, int 
   dev::launches++;
 }
 #else
-inline int stage_kpt() { static const int k = getenv("FV3LM_KPT") ? std::max(1, atoi(getenv("FV3LM_KPT"))) : 1; return k; }
+inline int stage_kpt() { static const int k = getenv("FV3LM_KPT") ? std::max(1, atoi(getenv("FV3LM_KPT"))) : 4; return k; }
 template <class F> void launch_stage(const F& f, int nx, int ny, int ntile, int nk) {
   const int kpt = stage_kpt();
   for (int t = 0; t < ntile; t++)

@@ -21,7 +21,7 @@ TpOut build_fv_tp_2d(Program& P, Mosaic& mo, int q, int crx, int cry, int xfx, i
   const int isd = is - ng, ied = ie + ng, jsd = js - ng, jed = je + ng;
   auto nm = [&](const char* s) { return tag + "." + s; };
   const char* fe = getenv("FV3LM_FUSED_TP");
-  const int flevel = fe ? atoi(fe) : 0;
+  const int flevel = fe ? atoi(fe) : 2;      // default since round 2: tile kernels in every sweep (profiles/r02g_*)
   const bool fused = flevel != 0;
   // the reverse kernels cover the linear orders; a transport with a scheme of the nonlinear model has detached inputs and is never reversed
   const bool with_ad = flevel >= 2;
@@ -35,9 +35,9 @@ TpOut build_fv_tp_2d(Program& P, Mosaic& mo, int q, int crx, int cry, int xfx, i
     if (dir == 0) { if (lin) P.add<S_ppm<0>>(nm_, p0, {qq, cc}, {out}, nk); else P.add<S_ppm_nl<0>>(nm_, p0, {qq, cc}, {out}, nk); }
     else { if (lin) P.add<S_ppm<1>>(nm_, p1, {qq, cc}, {out}, nk); else P.add<S_ppm_nl<1>>(nm_, p1, {qq, cc}, {out}, nk); }
   };
-  // FV3LM_FUSED_TP=1: forward sweeps (NL, TL) run the two shared-memory-tile kernels of fused_tp.h instead of the eight stages,
-  // adjoint runs the stage chain.  FV3LM_FUSED_TP=2: the adjoint too runs tile kernels (forward values + one reverse kernel per half
-  // that recomputes the intermediates on chip); the chain is not built.  Opt-in until timed on a B200.
+  // FV3LM_FUSED_TP=2 (default): every sweep runs the shared-memory-tile kernels of fused_tp.h (forward values + one reverse kernel per
+  // half that recomputes the intermediates on chip); the chain is not built.  =1: forward sweeps (NL, TL) run the tile kernels, the
+  // adjoint the stage chain.  =0: the eight stages in every sweep (A/B runs, parity tests of the tile kernels against the chain).
   const int var0 = P.variant;
   auto chain = [&]() { if (fused) P.variant = VAR_AD; };
   auto common = [&]() { P.variant = var0; };

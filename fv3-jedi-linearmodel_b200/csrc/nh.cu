@@ -90,10 +90,10 @@ std::pair<int, int> build_update_dz_d(Program& P, Mosaic& mo, const LevD& dp0, c
   const int K = g.K, is = g.is, ie = g.ie, js = g.js, je = g.je, ng = g.ng;
   auto nm = [&](const char* s) { return tag + "." + s; };
   int crxa = P.val(nm("crx_adv"), K + 1), xfxa = P.val(nm("xfx_adv"), K + 1), crya = P.val(nm("cry_adv"), K + 1), yfxa = P.val(nm("yfx_adv"), K + 1);
-  add_col<S_edge_profile>(P, "edge_profile_crx", {dp0, K, is, ie + 1, js - ng, je + ng}, {crx}, {crxa});
-  add_col<S_edge_profile>(P, "edge_profile_xfx", {dp0, K, is, ie + 1, js - ng, je + ng}, {xfx}, {xfxa});
-  add_col<S_edge_profile>(P, "edge_profile_cry", {dp0, K, is - ng, ie + ng, js, je + 1}, {cry}, {crya});
-  add_col<S_edge_profile>(P, "edge_profile_yfx", {dp0, K, is - ng, ie + ng, js, je + 1}, {yfx}, {yfxa});
+  add_col<S_edge_profile>(P, "edge_profile_crx", S_edge_profile::make(dp0, K, is, ie + 1, js - ng, je + ng), {crx}, {crxa});
+  add_col<S_edge_profile>(P, "edge_profile_xfx", S_edge_profile::make(dp0, K, is, ie + 1, js - ng, je + ng), {xfx}, {xfxa});
+  add_col<S_edge_profile>(P, "edge_profile_cry", S_edge_profile::make(dp0, K, is - ng, ie + ng, js, je + 1), {cry}, {crya});
+  add_col<S_edge_profile>(P, "edge_profile_yfx", S_edge_profile::make(dp0, K, is - ng, ie + ng, js, je + 1), {yfx}, {yfxa});
   int ra_x = P.val(nm("ra_x"), K + 1), ra_y = P.val(nm("ra_y"), K + 1);
   P.add<S_ra>("dzd_ra", {0}, {xfxa, yfxa}, {ra_x, ra_y}, K + 1);
   LevOrd ho; for (int k = 0; k < 128; k++) ho.v[k] = (signed char)enc_hord(hord_tm);

@@ -115,49 +115,74 @@ struct S_dz_clamp {
 // edge_profile (non-uniform branch, limiter = 0): linear in q, coefficients from dp0 only.  in: q ; out: qe (K+1)
 struct S_edge_profile {
   static constexpr int NI = 1, NO = 1;
-  struct P { LevD dp0; int K; int i0, i1, j0, j1; };
-  template <class T, class GetQ> DEV static void sweep(const P& p, GetQ Q, T* qe, double* gam) {
-    const int K = p.K;
-    double g0 = p.dp0.v[1] / p.dp0.v[0], xt1 = 2.0 * g0 * (g0 + 1.0), bet = g0 * (g0 + 0.5);
-    qe[0] = (xt1 * Q(0) + Q(1)) / bet;
-    gam[0] = (1.0 + g0 * (g0 + 1.5)) / bet;
+  // The elimination coefficients depend on the reference thicknesses dp0 only -- the same for every column -- so they are computed once
+  // on the host (make) and the kernels keep no per-column work array: the forward sweep parks its result in the output array and the
+  // back substitution updates it in place (ncu, round 2: the version with per-thread qe[] / gam[] arrays ran at 0.9 TB/s of
+  // algorithmic traffic, its local arrays spilling through L2 into HBM).
+  struct P { int K; int i0, i1, j0, j1; double xt1_0, xt1_b, a_bot, xt2; LevD gk, bet, gam; };
+  static P make(const LevD& dp0, int K, int i0, int i1, int j0, int j1) {
+    P p; p.K = K; p.i0 = i0; p.i1 = i1; p.j0 = j0; p.j1 = j1;
+    for (int k = 0; k < 96; k++) p.gk.v[k] = p.bet.v[k] = p.gam.v[k] = 0.0;
+    const double g0 = dp0.v[1] / dp0.v[0];
+    p.xt1_0 = 2.0 * g0 * (g0 + 1.0); p.bet.v[0] = g0 * (g0 + 0.5);
+    p.gam.v[0] = (1.0 + g0 * (g0 + 1.5)) / p.bet.v[0];
     double gk = 0.0;
     for (int k = 1; k < K; k++) {
-      gk = p.dp0.v[k - 1] / p.dp0.v[k];
-      bet = 2.0 + 2.0 * gk - gam[k - 1];
-      qe[k] = (3.0 * (Q(k - 1) + gk * Q(k)) - qe[k - 1]) / bet;
-      gam[k] = gk / bet;
+      gk = dp0.v[k - 1] / dp0.v[k];
+      p.gk.v[k] = gk;
+      p.bet.v[k] = 2.0 + 2.0 * gk - p.gam.v[k - 1];
+      p.gam.v[k] = gk / p.bet.v[k];
     }
-    double a_bot = 1.0 + gk * (gk + 1.5);
-    xt1 = 2.0 * gk * (gk + 1.0);
-    double xt2 = gk * (gk + 0.5) - a_bot * gam[K - 1];
-    qe[K] = (xt1 * Q(K - 1) + Q(K - 2) - a_bot * qe[K - 1]) / xt2;
-    for (int k = K - 1; k >= 0; k--) qe[k] = qe[k] - gam[k] * qe[k + 1];
+    p.a_bot = 1.0 + gk * (gk + 1.5);
+    p.xt1_b = 2.0 * gk * (gk + 1.0);
+    p.xt2 = gk * (gk + 0.5) - p.a_bot * p.gam.v[K - 1];
+    return p;
   }
   template <class X> DEV static void eval(X& x, const P& p) {
     using T = typename X::T;
     if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
-    T qe[KMAX + 1]; double gam[KMAX + 1];
-    sweep<T>(p, [&](int k) { return x.in(0, k); }, qe, gam);
-    for (int k = 0; k <= p.K; k++) x.out(0, k, qe[k]);
+    const int K = p.K;
+    T qm = x.in(0, 0), q0 = x.in(0, 1);                 // Q(k-1), Q(k)
+    T qe = (p.xt1_0 * qm + q0) / p.bet.v[0];
+    x.out(0, 0, qe);
+    T qmm = qm;                                         // Q(k-2)
+    for (int k = 1; k < K; k++) {
+      if (k > 1) { qmm = qm; qm = q0; q0 = x.in(0, k); }
+      qe = (3.0 * (qm + p.gk.v[k] * q0) - qe) / p.bet.v[k];
+      x.out(0, k, qe);
+    }
+    // here q0 = Q(K-1), qm = Q(K-2)
+    T nx = (p.xt1_b * q0 + qm - p.a_bot * qe) / p.xt2;
+    x.out(0, K, nx);
+    (void)qmm;
+    for (int k = K - 1; k >= 0; k--) { nx = x.rd(0, k) - p.gam.v[k] * nx; x.out(0, k, nx); }
   }
+  // the operator is linear with constant coefficients: transpose the elimination.  The adjoint of the output (dead after this op) is
+  // the work array of the transposed back substitution.
   template <class X> DEV static void eval_ad(X& x, const P& p) {
     if (!x.in_rect(p.i0, p.i1, p.j0, p.j1)) return;
     const int K = p.K;
-    // the operator is linear with constant coefficients: transpose the elimination
-    double gam[KMAX + 1], bet[KMAX + 1], gkv[KMAX + 1], ad[KMAX + 1], q_ad[KMAX];
-    double g0 = p.dp0.v[1] / p.dp0.v[0], xt10 = 2.0 * g0 * (g0 + 1.0);
-    bet[0] = g0 * (g0 + 0.5);
-    gam[0] = (1.0 + g0 * (g0 + 1.5)) / bet[0];
-    for (int k = 1; k < K; k++) { gkv[k] = p.dp0.v[k - 1] / p.dp0.v[k]; bet[k] = 2.0 + 2.0 * gkv[k] - gam[k - 1]; gam[k] = gkv[k] / bet[k]; }
-    double gk = gkv[K - 1], a_bot = 1.0 + gk * (gk + 1.5), xt1 = 2.0 * gk * (gk + 1.0), xt2 = gk * (gk + 0.5) - a_bot * gam[K - 1];
-    for (int k = 0; k <= K; k++) ad[k] = x.oad(0, k);
-    for (int k = 0; k < K; k++) q_ad[k] = 0.0;
-    for (int k = 0; k < K; k++) ad[k + 1] -= gam[k] * ad[k];              // back substitution, transposed
-    { double n = ad[K] / xt2; q_ad[K - 1] += xt1 * n; q_ad[K - 2] += n; ad[K - 1] -= a_bot * n; }
-    for (int k = K - 1; k >= 1; k--) { double n = ad[k] / bet[k]; q_ad[k - 1] += 3.0 * n; q_ad[k] += 3.0 * gkv[k] * n; ad[k - 1] -= n; }
-    { double n = ad[0] / bet[0]; q_ad[0] += xt10 * n; q_ad[1] += n; }
-    for (int k = 0; k < K; k++) x.add(0, k, q_ad[k]);
+    double a = x.oad(0, 0);
+    for (int k = 0; k < K; k++) {                       // ad[k+1] -= gam[k] * ad[k]
+      const double upd = -(p.gam.v[k] * a);
+      a = x.oad(0, k + 1) + upd;
+      x.oad_add(0, k + 1, upd);
+    }
+    // a = ad[K]
+    double n = a / p.xt2;
+    double q_hi = p.xt1_b * n;                          // pending contribution to q_ad[k] of the row above (k = K-1 now)
+    double q_lo = n;                                    // ... and to q_ad[k-1]
+    double carry = -(p.a_bot * n);                      // ad[K-1] -= a_bot n
+    for (int k = K - 1; k >= 1; k--) {
+      n = (x.oad(0, k) + carry) / p.bet.v[k];
+      x.add(0, k, q_hi + 3.0 * p.gk.v[k] * n);
+      q_hi = q_lo + 3.0 * n; q_lo = 0.0;
+      carry = -n;
+    }
+    n = (x.oad(0, 0) + carry) / p.bet.v[0];
+    // K >= 2: q_hi holds what rows 1.. gave to q_ad[0]; row 0 adds xt1_0 n to q_ad[0] and n to q_ad[1]
+    x.add(0, 0, q_hi + p.xt1_0 * n);
+    x.add(0, 1, n);
   }
 };
 

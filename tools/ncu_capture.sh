@@ -9,6 +9,7 @@ env FV3LM_NO_GRAPH=1 "$@" timeout 300 ncu --set full --clock-control none --impo
     -o $REP python bench.py --kernel-only --steps 1 --warmup 0 > /tmp/${TAG}_${NAME}.log 2>&1
 if [ -f $REP.ncu-rep ]; then
   python tools/ncu_summary.py --opcodes $REP.ncu-rep > gpurun_out/${TAG}_ncu_${NAME}.txt 2>&1
+  python tools/ncu_summary.py --sass-counts $REP.ncu-rep | gzip > gpurun_out/${TAG}_ncu_${NAME}_sass.csv.gz
   rm -f $REP.ncu-rep
   grep -E "^==|duration|dram__bytes|dram_throughput|sm__throughput|registers|opcode" gpurun_out/${TAG}_ncu_${NAME}.txt | cut -c1-260
 else

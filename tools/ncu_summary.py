@@ -56,8 +56,28 @@ def opcode_histogram(path, top=16):
         print("   warp instructions executed: %d ; opcode mix: %s" % (tot, ", ".join("%s %.1f%%" % (k, 100.0 * v / tot) for k, v in ops.most_common(top))))
 
 
+def sass_counts(path):
+    """per-instruction executed counts of the first kernel (index, opcode text, warp instructions executed): joined with nvdisasm -g line
+    info by tools/sass_by_line.py"""
+    out = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = None
+    for n, r in enumerate(rows[:4]):
+        if 'Source' in r and 'Instructions Executed' in r:
+            hdr = r; rows = rows[n + 1:]; break
+    if hdr is None:
+        return
+    ia, ie = hdr.index('Source'), hdr.index('Instructions Executed')
+    w = csv.writer(sys.stdout)
+    for n, r in enumerate(rows):
+        if len(r) > ie:
+            w.writerow([n, r[ia].strip(), r[ie]])
+
+
 if __name__ == '__main__':
     args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    if '--sass-counts' in sys.argv:
+        sass_counts(args[0]); sys.exit(0)
     summarise(args)
     if '--opcodes' in sys.argv:
         for a in args:
