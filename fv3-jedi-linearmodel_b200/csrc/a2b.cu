@@ -337,11 +337,235 @@ struct KernA2bRev {
 };
 }  // namespace ftp
 
+// =====================================================================================================================
+// a2b_ord4 as a COMPILED LINEAR OPERATOR (FV3LM_FUSED_A2B=2, the default).
+//
+// a2b_ord4 is linear in qin with purely geometric coefficients (a2b_edge_tlm.F90:546: the tangent is the operator itself, the adjoint
+// its transpose).  Three cells away from the cube edges it is the constant 4 x 4 stencil
+//     qout(i,j) = sum_ab 0.5 (B_a A_b + A_a B_b) qin(i+a-2, j+b-2),   A = (a2, a1, a1, a2), B = (b2, b1, b1, b2)
+// (the two 1-D interpolations of :108-227 composed); near the edges and corners the rows differ cell by cell.  Instead of evaluating the
+// edge formulas per thread in every sweep (the stage chain spends 4 launches and ~600 instructions per cell on them everywhere), the
+// operator is compiled ONCE per handle: the generic stage chain above is run on 64 probe fields (unit impulses with period 8 in i and j,
+// one per "level"), which yields every row of the matrix; rows inside the regular rectangle are checked against the constant stencil,
+// the others are kept as sparse rows (and, transposed, as sparse columns for the adjoint).  A sweep is then
+//     1 launch over the regular rectangle (16 loads, 3 multiplies per cell) + 1 launch over the sparse rows (one thread per row and level),
+// one read and one write of the field in each of NL / TL / AD.  The compiled operator is verified against the chain on a random field
+// before it is used (compile_a2b throws otherwise), so a geometry the derivation above does not cover cannot slip through.
+// =====================================================================================================================
+namespace a2bc {
+constexpr int PER = 8, NPROBE = PER * PER;
+constexpr double WC = a2b::a2 * a2b::b2, WE = 0.5 * (a2b::a1 * a2b::b2 + a2b::a2 * a2b::b1), WM = a2b::a1 * a2b::b1;
+
+struct Rects { short x0[MAXSUB], x1[MAXSUB], y0[MAXSUB], y1[MAXSUB]; };
+struct Tables {
+  int nf = 0, nt = 0;
+  int *f_ptr = nullptr, *f_tile = nullptr, *f_pos = nullptr, *f_src = nullptr; double* f_w = nullptr;
+  int *t_ptr = nullptr, *t_tile = nullptr, *t_pos = nullptr, *t_src = nullptr; double* t_w = nullptr;
+  Rects ro, ri;          // regular rectangles of the outputs / of the inputs (transposed operator), array coordinates; empty: x1 < x0
+  std::vector<void*> owned;
+  ~Tables() { for (void* p : owned) dev::free_(p); }
+  template <class T> T* up(const std::vector<T>& v) {
+    T* d = (T*)dev::alloc(sizeof(T) * std::max<size_t>(v.size(), 1));
+    if (!v.empty()) dev::h2d(d, v.data(), sizeof(T) * v.size());
+    owned.push_back(d);
+    return d;
+  }
+};
+
+// q points at the cell; the taps span O0 .. O0+3 in both directions (O0 = -2: the operator, O0 = -1: its transpose)
+template <int O0> DEV double stencil(const double* q, int pitch) {
+  const double *r0 = q + O0 * pitch + O0, *r1 = r0 + pitch, *r2 = r1 + pitch, *r3 = r2 + pitch;
+  const double corners = (r0[0] + r0[3]) + (r3[0] + r3[3]);
+  const double edges = ((r0[1] + r0[2]) + (r3[1] + r3[2])) + ((r1[0] + r1[3]) + (r2[0] + r2[3]));
+  const double centers = (r1[1] + r1[2]) + (r2[1] + r2[2]);
+  return WC * corners + WE * edges + WM * centers;
+}
+template <bool TL> struct KReg {      // regular outputs
+  Rects r; int pitch, slab, nk; const double* in; const double* ind; double* out; double* outd;
+  DEV void operator()(int ii, int jj, int z) const {
+    int tile, kk; split_z(z, nk, tile, kk);
+    if (ii < r.x0[tile] || ii > r.x1[tile] || jj < r.y0[tile] || jj > r.y1[tile]) return;
+    const int p = (tile * nk + kk) * slab + jj * pitch + ii;
+    out[p] = stencil<-2>(in + p, pitch);
+    if (TL) outd[p] = stencil<-2>(ind + p, pitch);
+  }
+};
+struct KRegT {                        // regular inputs of the transposed operator
+  Rects r; int pitch, slab, nk; const double* oad; double* iad;
+  DEV void operator()(int ii, int jj, int z) const {
+    int tile, kk; split_z(z, nk, tile, kk);
+    if (ii < r.x0[tile] || ii > r.x1[tile] || jj < r.y0[tile] || jj > r.y1[tile]) return;
+    const int p = (tile * nk + kk) * slab + jj * pitch + ii;
+    iad[p] += stencil<-1>(oad + p, pitch);
+  }
+};
+template <bool TL> struct KRows {     // sparse rows: one thread per (row, level)
+  const int *ptr, *tile, *pos, *src; const double* w; int slab, nk; const double* in; const double* ind; double* out; double* outd;
+  DEV void operator()(int r, int k, int) const {
+    const int base = (tile[r] * nk + k) * slab;
+    double s = 0.0, sd = 0.0;
+    for (int q = ptr[r]; q < ptr[r + 1]; q++) { s += w[q] * in[base + src[q]]; if (TL) sd += w[q] * ind[base + src[q]]; }
+    out[base + pos[r]] = s;
+    if (TL) outd[base + pos[r]] = sd;
+  }
+};
+struct KRowsT {
+  const int *ptr, *tile, *pos, *src; const double* w; int slab, nk; const double* oad; double* iad;
+  DEV void operator()(int r, int k, int) const {
+    const int base = (tile[r] * nk + k) * slab;
+    double s = 0.0;
+    for (int q = ptr[r]; q < ptr[r + 1]; q++) s += w[q] * oad[base + src[q]];
+    iad[base + pos[r]] += s;
+  }
+};
+
+static void add_chain(Program& T, int qin, int qout, int nk) {
+  int qx = T.val("qx", nk), qy = T.val("qy", nk), qe = T.val("qe", nk);
+  T.add<S_a2b_q1<0>>("a2b_qx", {0}, {qin}, {qx}, nk);
+  T.add<S_a2b_q1<1>>("a2b_qy", {0}, {qin}, {qy}, nk);
+  T.add<S_a2b_edge>("a2b_edge", {0}, {qin}, {qe}, nk);
+  T.add<S_a2b_q2>("a2b_q2", {0}, {qx, qy, qe}, {qout}, nk);
+}
+
+static std::shared_ptr<Tables> compile(Device* dv) {
+  const Geom& g = dv->g;
+  const int NP = NPROBE + 1, lo = g.ng - 1;          // the last "level" is a random field: the check of the compiled operator
+  Program T; T.dv = dv; T.name = "a2b_probe";
+  int qin = T.val("qin", NP, true), qout = T.val("qout", NP, true);
+  add_chain(T, qin, qout, NP);
+  const size_t n = T.val_doubles(qin);
+  std::vector<double> hin(n, 0.0), hout(n, 0.0);
+  auto at = [&](int t, int p, int jj, int ii) { return (((size_t)t * NP + p) * g.NY + jj) * g.pitch + ii; };
+  unsigned long long seed = 88172645463325252ULL;
+  auto rnd = [&]() { seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17; return (double)(seed >> 11) / 9007199254740992.0 - 0.5; };
+  for (int t = 0; t < g.ntile; t++)
+    for (int jj = 0; jj < g.NY; jj++)
+      for (int ii = 0; ii < g.NX; ii++) {
+        hin[at(t, (jj % PER) * PER + ii % PER, jj, ii)] = 1.0;
+        hin[at(t, NPROBE, jj, ii)] = rnd();
+      }
+  double* din = dv->pool.get(n); double* dout = dv->pool.get(n);
+  dev::h2d(din, hin.data(), n * sizeof(double));
+  dev::zero(dout, n * sizeof(double));
+  T.vals[qin].traj = din; T.vals[qout].traj = dout;
+  try { T.run(MODE_NL); dev::sync(); dev::d2h(hout.data(), dout, n * sizeof(double)); }
+  catch (...) { dv->pool.put(din); dv->pool.put(dout); throw; }
+  dv->pool.put(din); dv->pool.put(dout);
+
+  auto tb = std::make_shared<Tables>();
+  std::vector<int> f_ptr{0}, f_tile, f_pos, f_src, t_ptr{0}, t_tile, t_pos, t_src;
+  std::vector<double> f_w, t_w;
+  struct Ent { int cell; double w; };
+  const double tol = 1e-13;
+  for (int t = 0; t < g.ntile; t++) {
+    const int ci = g.i0[t] - lo, cj = g.j0[t] - lo;
+    const int xs = g.is + lo, xe = g.ie + lo + 1, ys = g.js + lo, ye = g.je + lo + 1;      // computed outputs (is..ie+1, js..je+1)
+    // every row of the operator from the impulse responses
+    std::vector<std::vector<Ent>> rows((size_t)g.NY * g.NX), cols((size_t)g.NY * g.NX);
+    double worst = 0.0;
+    for (int jj = ys; jj <= ye; jj++)
+      for (int ii = xs; ii <= xe; ii++) {
+        auto& row = rows[(size_t)jj * g.NX + ii];
+        double chk = 0.0;
+        for (int p = 0; p < NPROBE; p++) {
+          const double v = hout[at(t, p, jj, ii)];
+          if (v == 0.0) continue;
+          const int a = p % PER, b = p / PER;
+          const int si = ii - 4 + (((a - (ii - 4)) % PER) + PER) % PER, sj = jj - 4 + (((b - (jj - 4)) % PER) + PER) % PER;
+          if (si < 0 || si >= g.NX || sj < 0 || sj >= g.NY) throw std::runtime_error("a2b_ord4 compile: an impulse response outside the array");
+          row.push_back({sj * g.NX + si, v});
+          chk += v * hin[at(t, NPROBE, sj, si)];
+        }
+        const double ref = hout[at(t, NPROBE, jj, ii)];
+        worst = std::max(worst, fabs(chk - ref) / std::max(1.0, fabs(ref)));
+      }
+    if (worst > 1e-12) throw std::runtime_error("a2b_ord4 compile: the probed operator does not reproduce the stage chain (footprint wider than the probe period?)");
+    // regular outputs: faces 3 .. npx-2 / npy-2 of the cube tile; every row there must be the constant stencil
+    int ox0 = std::max(xs, 3 - ci), ox1 = std::min(xe, g.npx - 2 - ci), oy0 = std::max(ys, 3 - cj), oy1 = std::min(ye, g.npy - 2 - cj);
+    auto weight = [](int d0, int d1) {   // d = 0..3 along each direction
+      const bool e0 = d0 == 0 || d0 == 3, e1 = d1 == 0 || d1 == 3;
+      return e0 && e1 ? WC : (e0 || e1 ? WE : WM);
+    };
+    auto is_stencil = [&](const std::vector<Ent>& r, int ii, int jj, int o0) {
+      if (r.size() != 16) return false;
+      for (const Ent& e : r) {
+        const int di = e.cell % g.NX - ii - o0, dj = e.cell / g.NX - jj - o0;
+        if (di < 0 || di > 3 || dj < 0 || dj > 3 || fabs(e.w - weight(di, dj)) > tol) return false;
+      }
+      return true;
+    };
+    for (int jj = oy0; jj <= oy1; jj++)
+      for (int ii = ox0; ii <= ox1; ii++)
+        if (!is_stencil(rows[(size_t)jj * g.NX + ii], ii, jj, -2)) throw std::runtime_error("a2b_ord4 compile: a row of the regular rectangle is not the constant stencil");
+    tb->ro.x0[t] = (short)ox0; tb->ro.x1[t] = (short)ox1; tb->ro.y0[t] = (short)oy0; tb->ro.y1[t] = (short)oy1;
+    for (int jj = ys; jj <= ye; jj++)
+      for (int ii = xs; ii <= xe; ii++) {
+        const auto& row = rows[(size_t)jj * g.NX + ii];
+        for (const Ent& e : row) cols[e.cell].push_back({jj * g.NX + ii, e.w});
+        if (ii >= ox0 && ii <= ox1 && jj >= oy0 && jj <= oy1) continue;
+        f_tile.push_back(t); f_pos.push_back(jj * g.pitch + ii);
+        for (const Ent& e : row) { f_src.push_back((e.cell / g.NX) * g.pitch + e.cell % g.NX); f_w.push_back(e.w); }
+        f_ptr.push_back((int)f_src.size());
+      }
+    // regular inputs of the transpose: all sixteen readers are regular outputs and nothing else reads the cell
+    int ix0 = ox0 + 1, ix1 = ox1 - 2, iy0 = oy0 + 1, iy1 = oy1 - 2;
+    for (int shrink = 0; shrink < 8; shrink++) {
+      bool ok = true;
+      for (int jj = iy0; jj <= iy1 && ok; jj++)
+        for (int ii = ix0; ii <= ix1 && ok; ii++) ok = is_stencil(cols[(size_t)jj * g.NX + ii], ii, jj, -1);
+      if (ok) break;
+      ix0++; ix1--; iy0++; iy1--;
+      if (shrink == 7) { ix1 = ix0 - 1; iy1 = iy0 - 1; }
+    }
+    tb->ri.x0[t] = (short)ix0; tb->ri.x1[t] = (short)ix1; tb->ri.y0[t] = (short)iy0; tb->ri.y1[t] = (short)iy1;
+    for (int jj = 0; jj < g.NY; jj++)
+      for (int ii = 0; ii < g.NX; ii++) {
+        const auto& col = cols[(size_t)jj * g.NX + ii];
+        if (col.empty() || (ii >= ix0 && ii <= ix1 && jj >= iy0 && jj <= iy1)) continue;
+        t_tile.push_back(t); t_pos.push_back(jj * g.pitch + ii);
+        for (const Ent& e : col) { t_src.push_back((e.cell / g.NX) * g.pitch + e.cell % g.NX); t_w.push_back(e.w); }
+        t_ptr.push_back((int)t_src.size());
+      }
+  }
+  for (int t = g.ntile; t < MAXSUB; t++) { tb->ro.x0[t] = tb->ri.x0[t] = 1; tb->ro.x1[t] = tb->ri.x1[t] = 0; tb->ro.y0[t] = tb->ri.y0[t] = 1; tb->ro.y1[t] = tb->ri.y1[t] = 0; }
+  tb->nf = (int)f_tile.size(); tb->nt = (int)t_tile.size();
+  tb->f_ptr = tb->up(f_ptr); tb->f_tile = tb->up(f_tile); tb->f_pos = tb->up(f_pos); tb->f_src = tb->up(f_src); tb->f_w = tb->up(f_w);
+  tb->t_ptr = tb->up(t_ptr); tb->t_tile = tb->up(t_tile); tb->t_pos = tb->up(t_pos); tb->t_src = tb->up(t_src); tb->t_w = tb->up(t_w);
+  return tb;
+}
+}  // namespace a2bc
+
 int build_a2b_ord4(Program& P, Mosaic& mo, int qin, int nk, const std::string& tag) {
   (void)mo;
   auto nm = [&](const char* s) { return tag + "." + s; };
   const char* fe = getenv("FV3LM_FUSED_A2B");
-  if (fe && atoi(fe) != 0) {
+  const int level = fe ? atoi(fe) : 2;
+  if (level == 2 && P.name != "a2b_probe") {
+    if (P.vals[qin].nk != nk) throw std::runtime_error("compiled a2b_ord4: the field must have the launch's number of levels");
+    if (!P.dv->a2b_tables) P.dv->a2b_tables = a2bc::compile(P.dv);
+    std::shared_ptr<a2bc::Tables> tb = std::static_pointer_cast<a2bc::Tables>(P.dv->a2b_tables);
+    int qout = P.val(nm("qout"), nk);
+    Op op; op.name = "a2b_compiled"; op.in = {qin}; op.out = {qout}; op.nk_launch = nk; op.tl_only = P.tl_only; op.variant = P.variant;
+    op.run = [tb](Program& P, Op& o, int mode) {
+      const Geom& g = P.dv->g;
+      const Value &vi = P.vals[o.in[0]], &vo = P.vals[o.out[0]];
+      const int nk = o.nk_launch;
+      if (mode == MODE_AD) {
+        if (!vi.active || !vo.active || !vo.pert || !vi.pert) return;
+        launch3d(a2bc::KRegT{tb->ri, g.pitch, g.slab, nk, vo.pert, vi.pert}, g.NX, g.NY, g.ntile * nk);
+        if (tb->nt) launch3d(a2bc::KRowsT{tb->t_ptr, tb->t_tile, tb->t_pos, tb->t_src, tb->t_w, g.slab, nk, vo.pert, vi.pert}, tb->nt, nk, 1);
+      } else if (mode == MODE_TL && vi.active && vi.pert && vo.pert) {
+        launch3d(a2bc::KReg<true>{tb->ro, g.pitch, g.slab, nk, vi.traj, vi.pert, vo.traj, vo.pert}, g.NX, g.NY, g.ntile * nk);
+        if (tb->nf) launch3d(a2bc::KRows<true>{tb->f_ptr, tb->f_tile, tb->f_pos, tb->f_src, tb->f_w, g.slab, nk, vi.traj, vi.pert, vo.traj, vo.pert}, tb->nf, nk, 1);
+      } else {
+        launch3d(a2bc::KReg<false>{tb->ro, g.pitch, g.slab, nk, vi.traj, nullptr, vo.traj, nullptr}, g.NX, g.NY, g.ntile * nk);
+        if (tb->nf) launch3d(a2bc::KRows<false>{tb->f_ptr, tb->f_tile, tb->f_pos, tb->f_src, tb->f_w, g.slab, nk, vi.traj, nullptr, vo.traj, nullptr}, tb->nf, nk, 1);
+      }
+    };
+    P.ops.push_back(op);
+    return qout;
+  }
+  if (level == 1) {
     if (P.vals[qin].nk != nk) throw std::runtime_error("fused a2b_ord4: the field must have the launch's number of levels");
     int qout = P.val(nm("qout"), nk);
     Op op; op.name = "a2b_fused"; op.in = {qin}; op.out = {qout}; op.nk_launch = nk; op.tl_only = P.tl_only; op.variant = P.variant;

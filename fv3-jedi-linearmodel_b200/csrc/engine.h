@@ -512,7 +512,9 @@ template <class S> struct ColNL : CtxBase {
   using T = double;
   FArr<S::NI> in_; FArr<S::NO> out_;
   DEV int o2(int nkf, int k, int di, int dj) const { bounds(di, dj, "column field"); return (tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + pos + dj * g.pitch + di; }
-  DEV T in(int f, int k, int di = 0, int dj = 0) const { return in_.p[f][o2(in_.nk[f], k, di, dj)]; }
+  // inputs are never outputs of the same op (SSA values): the read-only path lets the compiler start the loads of the next levels
+  // before the stores of this one (a column sweep is otherwise one exposed DRAM latency per level)
+  DEV T in(int f, int k, int di = 0, int dj = 0) const { return LDG(in_.p[f] + o2(in_.nk[f], k, di, dj)); }
   DEV void out(int o, int k, T v) const { out_.p[o][o2(out_.nk[o], k, 0, 0)] = v; }
   DEV T rd(int o, int k) const { return out_.p[o][o2(out_.nk[o], k, 0, 0)]; }   // read back own output
 };
@@ -522,7 +524,7 @@ template <class S> struct ColTL : CtxBase {
   DEV int o2(int nkf, int k, int di, int dj) const { bounds(di, dj, "column field"); return (tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + pos + dj * g.pitch + di; }
   DEV T in(int f, int k, int di = 0, int dj = 0) const {
     const int o = o2(in_.nk[f], k, di, dj);
-    return Dual(in_.p[f][o], ind_.p[f] ? ind_.p[f][o] : 0.0);
+    return Dual(LDG(in_.p[f] + o), ind_.p[f] ? LDG(ind_.p[f] + o) : 0.0);
   }
   DEV void out(int o, int k, T v) const {
     const int q = o2(out_.nk[o], k, 0, 0);
@@ -534,8 +536,8 @@ template <class S> struct ColTL : CtxBase {
 template <class S> struct ColAD : CtxBase {
   FArr<S::NI> in_, inad_; FArr<S::NO> out_, outad_;
   DEV int o2(int nkf, int k) const { return (tile * nkf + (nkf == 1 ? 0 : k)) * g.slab + pos; }
-  DEV double in(int f, int k) const { return in_.p[f][o2(in_.nk[f], k)]; }
-  DEV double outv(int o, int k) const { return out_.p[o][o2(out_.nk[o], k)]; }          // stored forward value
+  DEV double in(int f, int k) const { return LDG(in_.p[f] + o2(in_.nk[f], k)); }
+  DEV double outv(int o, int k) const { return LDG(out_.p[o] + o2(out_.nk[o], k)); }          // stored forward value
   DEV double oad(int o, int k) const { return outad_.p[o] ? outad_.p[o][o2(outad_.nk[o], k)] : 0.0; }
   DEV void oad_add(int o, int k, double v) const { if (outad_.p[o]) outad_.p[o][o2(outad_.nk[o], k)] += v; }  // workspace use
   DEV void add(int f, int k, double v) const { if (inad_.p[f]) inad_.p[f][o2(inad_.nk[f], k)] += v; }
@@ -608,6 +610,7 @@ struct Device {
   struct Comm* comm = nullptr;     // for the collective (min over ranks) version of that budget
   std::vector<double*> metric_bufs;
   Pool pool;
+  std::shared_ptr<void> a2b_tables;   // a2b_ord4 compiled into a constant stencil + sparse edge rows (a2b.cu), built on first use
   std::string err;
 };
 

@@ -4,7 +4,8 @@ import pytest
 import torch
 from oracle import d_sw as odsw
 from oracle.a2b_edge import a2b_ord4
-from common import metrics, ograd, handle, rnd, check_module
+from common import metrics, ograd, handle, rnd, check_module, region
+import fv3lm
 
 
 def dsw_inputs(N, K, seed):
@@ -93,6 +94,23 @@ def _run_a2b(emu, N=12):
     g = ograd(N)
     h = handle(N, K, emu)
     return check_module(h, "a2b_ord4", N, K, f, ["qin"], {"qout": (1, N + 1, 1, N + 1)}, lambda q: (a2b_ord4(q, g),), {}, rng)
+
+
+def _a2b_nl_ad(emu, N):
+    """NL result and the adjoint of a random output adjoint through the module interface (used to compare implementations)"""
+    K = 2
+    rng = np.random.default_rng(31)
+    q = rnd(rng, N, K)
+    y = np.zeros_like(q)
+    region(y, 1, N + 1, 1, N + 1)[...] = region(rnd(rng, N, K), 1, N + 1, 1, N + 1)
+    h = handle(N, K, emu)
+    traj = {"qin": q.copy(), "qout": np.zeros_like(q)}
+    h.module_run("a2b_ord4", fv3lm.MODE_NL, traj)
+    nl = region(traj["qout"], 1, N + 1, 1, N + 1).copy()
+    traj = {"qin": q.copy(), "qout": np.zeros_like(q)}
+    pert = {"qin": np.zeros_like(q), "qout": y.copy()}
+    h.module_run("a2b_ord4", fv3lm.MODE_AD, traj, pert)
+    return nl, pert["qin"].copy()
 
 
 def test_a2b_ord4_emu():

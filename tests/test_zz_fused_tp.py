@@ -200,6 +200,43 @@ def test_fused_a2b_vs_oracle_emu(fused_all, N):
     test_d_sw._run_a2b(True, N)
 
 
+# ---- a2b_ord4 compiled into a constant stencil + sparse edge rows (FV3LM_FUSED_A2B=2, the default since round 2; csrc/a2b.cu a2bc) ----
+@pytest.fixture
+def a2b_compiled(monkeypatch):
+    common._handles.clear()
+    monkeypatch.setenv("FV3LM_FUSED_A2B", "2")
+    yield
+    common._handles.clear()
+
+
+@pytest.mark.parametrize("N", [12, 40])
+def test_compiled_a2b_vs_oracle_emu(a2b_compiled, N):
+    """NL, TL, AD against the oracle + dot-product test; N = 40 has a wide regular rectangle, N = 12 is mostly edge rows"""
+    test_d_sw._run_a2b(True, N)
+
+
+def test_compiled_a2b_layout_2x2_emu(a2b_compiled):
+    """sub-domains with zero, one or two cube edges: the regular rectangles and the sparse rows are built per resident sub-domain"""
+    print(test_decomp._layout("a2b_ord4", True, (2, 2)))
+
+
+def test_compiled_a2b_vs_chain_emu(monkeypatch):
+    """the compiled operator against the stage chain it was probed from (NL and AD of the module, N = 40)"""
+    res = {}
+    for flag in ("0", "2"):
+        common._handles.clear()
+        monkeypatch.setenv("FV3LM_FUSED_A2B", flag)
+        res[flag] = test_d_sw._a2b_nl_ad(True, 40)
+    common._handles.clear()
+    for a, b in zip(res["0"], res["2"]):
+        assert np.abs(a).max() > 0 and relerr(b, a) <= 1e-13, relerr(b, a)
+
+
+@pytest.mark.gpu
+def test_compiled_a2b_vs_oracle_gpu(a2b_compiled):
+    test_d_sw._run_a2b(False, 40)
+
+
 @pytest.mark.parametrize("case", ["a2b_ord4", "fv_tp_2d", "step_nonhydro"])
 def test_fused_layout_2x2_emu(fused_all, case):
     """tile kernels on layout(2, 2) sub-domains (cube-edge cases keyed on the tile-global index, 24 sub-domains in one launch)"""
