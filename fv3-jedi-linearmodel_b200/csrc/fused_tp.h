@@ -43,6 +43,17 @@ template <> struct Num<Dual> {
   DEV static void sts(double* sv, double* sd, int o, Dual a) { sv[o] = a.v; sd[o] = a.d; }
   DEV static void st(const OFld& f, int o, Dual a) { f.v[o] = a.v; if (f.d) f.d[o] = a.d; }
 };
+// L2 prefetch of what a later phase (tile kernels) or the next row (marching kernels) reads: these kernels start every phase with global
+// loads followed by a block barrier and were found latency bound (ncu r02g / r02j: long-scoreboard stalls 14 per issue at < 50 % occupancy)
+DEV void pf_l2(const double* p) {
+#ifndef FV3LM_HOST_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+DEV void pf_fld(const Fld& f, int o) { pf_l2(f.v + o); if (f.d) pf_l2(f.d + o); }
+
 template <bool TLM, int N> struct SBuf { double v[N]; double d[TLM ? N : 1]; };
 
 // the context tp::ppm_flux sees: the transported field (its only input) is a shared-memory tile, metrics stay global
@@ -437,6 +448,24 @@ template <int DIN, bool AVG> struct KernTpRev {
     double* FA = s.u; double* CI = s.u + BFIAD::N; double* ALI = s.u + 2 * BFIAD::N;
     LTile<double> x; x.init(g, m);
     if (ph == 0) {
+      for (int c = tid; c < TX * TY; c += NTHR) {       // what the later phases read / accumulate at the block's own cells
+        const int ii = ii0 + c % TX, jj = jj0 + c / TX;
+        if (!b.inside(ii, jj)) continue;
+        const int o = b.off(ii, jj);
+        pf_l2(ci.v + o); pf_l2(fi.v + o); pf_l2(ra.v + o); pf_l2(aI.v + o);
+        if (q_ad.v) pf_l2(q_ad.v + o);
+        if (ci_ad.v) pf_l2(ci_ad.v + o);
+        if (fi_ad.v) pf_l2(fi_ad.v + o);
+        if (ra_ad.v) pf_l2(ra_ad.v + o);
+        if (co_ad.v) pf_l2(co_ad.v + o);
+        if (AVG) {
+          pf_l2(mI.v + o); pf_l2(fin2.v + o); pf_l2(fout2.v + o);
+          if (fin2_ad.v) pf_l2(fin2_ad.v + o);
+          if (fout2_ad.v) pf_l2(fout2_ad.v + o);
+          if (mI_ad.v) pf_l2(mI_ad.v + o);
+          if (mO_ad.v) pf_l2(mO_ad.v + o);
+        }
+      }
       for (int c = tid; c < BQ::N; c += NTHR) {
         const int ii = ii0 + BQ::X0 + c % BQ::W, jj = jj0 + BQ::Y0 + c / BQ::W;
         s.q[c] = b.inside(ii, jj) ? LDG(q.v + b.off(ii, jj)) : 0.0;
@@ -806,6 +835,10 @@ void run_fused(Program& P, Op& o, int mode, bool full, const Fill& fill) {
   else { if (full) go(K<double, true>{}); else go(K<double, false>{}); }
 }
 
+// row-marching forward kernels (fused_tp_march.h); return false when they do not apply (rows longer than a block)
+inline bool march_fwd_a(Program& P, Op& o, int mode, bool full, const LevOrd& hord);
+inline bool march_fwd_b(Program& P, Op& o, int mode, bool full, const LevOrd& hord);
+
 inline Fld adj_in(const Value& v) { return Fld{v.active ? v.pert : nullptr, nullptr, v.nk}; }
 inline OFld adj_out(const Value& v) { return OFld{v.active ? v.pert : nullptr, nullptr, v.nk}; }
 inline Fld val_in(const Value& v) { return Fld{v.traj, nullptr, v.nk}; }
@@ -832,6 +865,7 @@ inline void add_fused_a(Program& P, const std::string& nm, int q, int cry, int y
       launch_tile(k, g.NX, g.NY, g.ntile * o.nk_launch);
       return;
     }
+    if (march_fwd_a(P, o, mode, full, hord)) return;
     run_fused<KernTpA>(P, o, mode, full, [&](auto& k, bool tl) {
       k.ord = hord;
       k.q = fld(P.vals[o.in[0]], tl); k.cry = fld(P.vals[o.in[1]], tl); k.yfx = fld(P.vals[o.in[2]], tl);
@@ -863,6 +897,7 @@ inline void add_fused_b(Program& P, const std::string& nm, int q, int crx, int x
       launch_tile(k, g.NX, g.NY, g.ntile * o.nk_launch);
       return;
     }
+    if (march_fwd_b(P, o, mode, full, hord)) return;
     run_fused<KernTpB>(P, o, mode, full, [&](auto& k, bool tl) {
       k.ord = hord;
       k.q = fld(P.vals[o.in[0]], tl); k.crx = fld(P.vals[o.in[1]], tl); k.xfx = fld(P.vals[o.in[2]], tl); k.rax = fld(P.vals[o.in[3]], tl);

@@ -1,6 +1,7 @@
 #include "modules.h"
 #include "stages_tp.h"
 #include "fused_tp.h"
+#include "fused_tp_march.h"
 
 namespace fv3lm {
 

@@ -146,6 +146,7 @@ struct S_edge_profile {
     T qe = (p.xt1_0 * qm + q0) / p.bet.v[0];
     x.out(0, 0, qe);
     T qmm = qm;                                         // Q(k-2)
+#pragma unroll 4
     for (int k = 1; k < K; k++) {
       if (k > 1) { qmm = qm; qm = q0; q0 = x.in(0, k); }
       qe = (3.0 * (qm + p.gk.v[k] * q0) - qe) / p.bet.v[k];

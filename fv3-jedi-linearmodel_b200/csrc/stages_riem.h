@@ -30,10 +30,12 @@ struct S_cum {
     if (p.mode == 0) {
       T s = T(p.top);
       x.out(0, 0, s);
+#pragma unroll 4
       for (int k = 0; k < p.K; k++) { s = s + x.in(0, k); x.out(0, k + 1, s); }
     } else {
       T s = x.in(1, 0);
       x.out(0, p.K, s);
+#pragma unroll 4
       for (int k = p.K - 1; k >= 0; k--) { s = s - p.c * x.in(0, k); x.out(0, k, s); }
     }
   }
@@ -67,6 +69,7 @@ struct S_tri {
     T gam[KMAX], xs[KMAX];
     T bet = x.in(1, 0);
     xs[0] = x.in(3, 0) / bet;
+#pragma unroll 4
     for (int k = 1; k < K; k++) {
       T lo = p.lo_one ? T(1.0) : x.in(0, k + p.lo_off);
       gam[k] = x.in(2, k - 1 + p.up_off) / bet;
@@ -88,6 +91,7 @@ struct S_tri {
     auto UP = [&](int k) { return x.in(2, k + p.up_off); };
     double bet = x.in(1, 0);
     lam[0] = x.oad(0, p.out_off) / bet;
+#pragma unroll 4
     for (int k = 1; k < K; k++) {
       gam[k] = LO(k) / bet;                       // super-diagonal of row k-1 of A^T is lo(k)
       bet = x.in(1, k) - UP(k - 1) * gam[k];      // sub-diagonal of row k is up(k-1)
@@ -116,6 +120,7 @@ template <bool SIM> struct S_rs_pe2_t {
     if (!x.in_rect(g.is - p.halo, g.ie + p.halo, g.js - p.halo, g.je + p.halo)) return;
     T s = T(0.0);
     x.out(0, 0, s);
+#pragma unroll 4
     for (int k = 0; k < p.K; k++) {
       if constexpr (SIM) s = s + ((x.in(0, k) * p.rgrav) * (x.in(1, k) - x.in(2, k)) * p.rdt - p.beta * (x.in(3, k + 1) - x.in(3, k))) * p.ra;
       else s = s + (x.in(0, k) * p.rgrav) * (x.in(1, k) - x.in(2, k)) * p.rdt;
@@ -149,6 +154,7 @@ struct S_rs_p1 {
     const int K = p.K;
     T p1 = (x.in(0, K - 1) + 2.0 * x.in(0, K)) * rmp::r3;
     x.out(0, K - 1, p1);
+#pragma unroll 4
     for (int k = K - 2; k >= 0; k--) {
       T gk = x.in(2, k);
       p1 = (x.in(0, k) + x.in(1, k) * x.in(0, k + 1) + gk * x.in(0, k + 2)) * rmp::r3 - gk * p1;
