@@ -542,11 +542,13 @@ int build_a2b_ord4(Program& P, Mosaic& mo, int qin, int nk, const std::string& t
   const int level = fe ? atoi(fe) : 2;
   if (level == 2 && P.name != "a2b_probe") {
     if (P.vals[qin].nk != nk) throw std::runtime_error("compiled a2b_ord4: the field must have the launch's number of levels");
-    if (!P.dv->a2b_tables) P.dv->a2b_tables = a2bc::compile(P.dv);
-    std::shared_ptr<a2bc::Tables> tb = std::static_pointer_cast<a2bc::Tables>(P.dv->a2b_tables);
     int qout = P.val(nm("qout"), nk);
     Op op; op.name = "a2b_compiled"; op.in = {qin}; op.out = {qout}; op.nk_launch = nk; op.tl_only = P.tl_only; op.variant = P.variant;
-    op.run = [tb](Program& P, Op& o, int mode) {
+    op.run = [](Program& P, Op& o, int mode) {
+      // compiled on first use (the metrics must be on the device; the first run of a step program is eager, so the probe sweep and its
+      // host round trip never fall into a graph capture)
+      if (!P.dv->a2b_tables) P.dv->a2b_tables = a2bc::compile(P.dv);
+      const a2bc::Tables* tb = static_cast<const a2bc::Tables*>(P.dv->a2b_tables.get());
       const Geom& g = P.dv->g;
       const Value &vi = P.vals[o.in[0]], &vo = P.vals[o.out[0]];
       const int nk = o.nk_launch;

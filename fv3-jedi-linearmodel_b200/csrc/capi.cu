@@ -150,6 +150,38 @@ int fv3lm_set_metric(fv3lm_handle* h, const char* name, const double* host, int 
   FV3LM_METRIC_LIST(X)
 #undef X
   if (!found) throw std::runtime_error("fv3lm_set_metric: unknown metric " + nm);
+  if (nm == "dxa" || nm == "dya") {
+    // weights of q(e-2 .. e+1) in the PPM edge value AL(e) on a cube edge (e = 1 or np along the sweep direction): the mean of the two
+    // one-sided extrapolations of tp_core_tlm.F90:2405-2417 (x) / :2573-2585 (y); S_ppm::al_w's formulas, evaluated once per handle
+    const bool xdir = nm == "dxa";
+    const int lo = g.ng - 1;
+    std::vector<double> w[4];
+    for (int n = 0; n < 4; n++) w[n].assign((size_t)g.ntile * g.NY * g.NX, 0.0);
+    for (int t = 0; t < g.ntile; t++) {
+      const int cpos = (xdir ? g.i0[t] : g.j0[t]) - lo, np = xdir ? g.npx : g.npy;
+      for (int jj = 0; jj < g.NY; jj++)
+        for (int ii = 0; ii < g.NX; ii++) {
+          const int a = xdir ? ii : jj, e = a + cpos, len = xdir ? g.NX : g.NY;
+          if ((e != 1 && e != np) || a - 2 < 0 || a + 1 >= len) continue;
+          auto D = [&](int d) { return host[((size_t)t * g.NY + (xdir ? jj : jj + d)) * g.NX + (xdir ? ii + d : ii)]; };
+          const double a0 = D(-1), am = D(-2), a1 = D(0), a2 = D(1);
+          const size_t o = ((size_t)t * g.NY + jj) * g.NX + ii;
+          w[0][o] = -0.5 * a0 / (am + a0); w[1][o] = 0.5 * (2.0 * a0 + am) / (am + a0);
+          w[2][o] = 0.5 * (2.0 * a1 + a2) / (a1 + a2); w[3][o] = -0.5 * a1 / (a1 + a2);
+        }
+    }
+    for (int n = 0; n < 4; n++) {
+      const std::string wn = std::string(xdir ? "ppmw_x" : "ppmw_y") + char('0' + n);
+      double*& dw = h->metric_dev[wn];
+      if (!dw) { dw = (double*)dev::alloc((size_t)g.ntile * g.slab * sizeof(double)); dev::zero(dw, (size_t)g.ntile * g.slab * sizeof(double)); }
+      up2d(g, dw, w[n].data(), (size_t)g.ntile * g.NY);
+      double** slot = nullptr;
+      if (xdir) slot = n == 0 ? (double**)&h->dv.m.ppmw_x0 : n == 1 ? (double**)&h->dv.m.ppmw_x1 : n == 2 ? (double**)&h->dv.m.ppmw_x2 : (double**)&h->dv.m.ppmw_x3;
+      else slot = n == 0 ? (double**)&h->dv.m.ppmw_y0 : n == 1 ? (double**)&h->dv.m.ppmw_y1 : n == 2 ? (double**)&h->dv.m.ppmw_y2 : (double**)&h->dv.m.ppmw_y3;
+      *slot = dw;
+    }
+    dev::sync();
+  }
   if (nm == "grid_lon" || nm == "grid_lat" || nm == "agrid_lon" || nm == "agrid_lat") {
     h->geo_host[nm].assign(host, host + (size_t)g.ntile * g.NY * g.NX);
     if (h->geo_host.size() == 4) {

@@ -60,9 +60,12 @@ struct Geom {
   X(sin_sg3) X(sin_sg4) X(cos_sg1) X(cos_sg2) X(cos_sg3) X(cos_sg4) X(divg_u) X(divg_v)   \
   X(del6_u) X(del6_v) X(f0) X(fC) X(agrid_lon) X(agrid_lat) X(grid_lon) X(grid_lat)       \
   X(edge_w) X(edge_e) X(edge_s) X(edge_n) X(edge_vect_w) X(edge_vect_e) X(edge_vect_s)    \
-  X(edge_vect_n) X(a2b_cw)
+  X(edge_vect_n) X(a2b_cw) X(ppmw_x0) X(ppmw_x1) X(ppmw_x2) X(ppmw_x3) X(ppmw_y0) X(ppmw_y1)  \
+  X(ppmw_y2) X(ppmw_y3)
 // (the edge_* arrays are 1-D, stored in row 0 of a slab so they share the layout; a2b_cw holds the 4 x 3
-// extrap_corner weights of a2b_ord4, derived by the library from grid / agrid once they are all uploaded)
+// extrap_corner weights of a2b_ord4, derived by the library from grid / agrid once they are all uploaded; ppmw_x0..3 / ppmw_y0..3 the four
+// weights of the PPM edge value on the cube edges (faces 1 and npx / npy: two one-sided extrapolations, tp_core_tlm.F90:2405-2417), derived
+// from dxa / dya when those are uploaded, so that the hot kernels load four numbers there instead of dividing)
 
 struct Metrics {
 #define X(n) const double* n;
@@ -307,16 +310,29 @@ template <class S> struct HasCustomAd<S, std::enable_if_t<S::custom_ad>> { stati
 template <class S> struct KernAD {
   typename S::P p; Geom g; Metrics m; FArr<S::NI> in, inad; FArr<S::NO> outad; int nk, nk_fwd;
   DEV void operator()(int ii, int jj, int kk, int tile) const {
-    double acc[S::NI];
-#pragma unroll
-    for (int f = 0; f < S::NI; f++) acc[f] = 0.0;
-    if constexpr (HasCustomAd<S>::value) S::adjoint(*this, ii, jj, kk, tile, acc);
-    else AdTaps<S, 0>::run(*this, ii, jj, kk, tile, acc);
+    double acc[S::NI], old[S::NI];
+    // the accumulators' current values are requested BEFORE the evaluations: issued as `p[o] += acc` at the end, every field's load would wait
+    // behind the previous field's store (the compiler cannot prove the adjoint arrays distinct) -- one exposed DRAM latency per input field
 #pragma unroll
     for (int f = 0; f < S::NI; f++) {
-      if (inad.p[f] && kk < inad.nk[f]) {
+      acc[f] = 0.0; old[f] = 0.0;
+      if (inad.p[f] && kk < inad.nk[f]) old[f] = inad.p[f][(tile * inad.nk[f] + kk) * g.slab + jj * g.pitch + ii];
+    }
+    if constexpr (HasCustomAd<S>::value) S::adjoint(*this, ii, jj, kk, tile, acc);
+    else AdTaps<S, 0>::run(*this, ii, jj, kk, tile, acc);
+    // the same value may be bound to two inputs (del_fx reads d2 twice): their contributions go to one accumulator
+    unsigned dup = 0u;
+#pragma unroll
+    for (int f = S::NI - 1; f >= 1; f--) {
+#pragma unroll
+      for (int h = 0; h < f; h++)
+        if (!(dup & (1u << f)) && inad.p[h] == inad.p[f] && inad.p[f]) { acc[h] += acc[f]; dup |= 1u << f; }
+    }
+#pragma unroll
+    for (int f = 0; f < S::NI; f++) {
+      if (!(dup & (1u << f)) && inad.p[f] && kk < inad.nk[f]) {
         const int o = (tile * inad.nk[f] + kk) * g.slab + jj * g.pitch + ii;
-        inad.p[f][o] += acc[f];
+        inad.p[f][o] = old[f] + acc[f];
       }
     }
   }
@@ -541,6 +557,11 @@ template <class S> struct ColAD : CtxBase {
   DEV double oad(int o, int k) const { return outad_.p[o] ? outad_.p[o][o2(outad_.nk[o], k)] : 0.0; }
   DEV void oad_add(int o, int k, double v) const { if (outad_.p[o]) outad_.p[o][o2(outad_.nk[o], k)] += v; }  // workspace use
   DEV void add(int f, int k, double v) const { if (inad_.p[f]) inad_.p[f][o2(inad_.nk[f], k)] += v; }
+  // split form of add(): request the accumulators of a level (or of a few levels) first, store afterwards -- `add, add, add` makes every
+  // load wait behind the previous store (the compiler cannot prove the adjoint arrays distinct): one exposed DRAM latency per call
+  DEV double iad(int f, int k) const { return inad_.p[f] ? inad_.p[f][o2(inad_.nk[f], k)] : 0.0; }
+  DEV void iad_set(int f, int k, double v) const { if (inad_.p[f]) inad_.p[f][o2(inad_.nk[f], k)] = v; }
+  DEV bool same_ad(int f, int h) const { return inad_.p[f] == inad_.p[h]; }
   DEV bool active(int f) const { return inad_.p[f] != nullptr; }
 };
 template <class S> struct KernColNL {

@@ -120,10 +120,13 @@ template <class TT> struct LTile {
   using T = TT;
   static constexpr int mode = std::is_same<TT, double>::value ? 0 : 1;
   struct { int npx, npy; } g;
-  struct { const double* dxa; const double* dya; } m;
+  struct MM { const double *dxa, *dya, *ppmw_x0, *ppmw_x1, *ppmw_x2, *ppmw_x3, *ppmw_y0, *ppmw_y1, *ppmw_y2, *ppmw_y3; } m;
   const double* sv; const double* sd; int sw, sp;
   int i, j, mpos, pitch;
-  DEV void init(const Geom& g_, const Metrics& m_) { g.npx = g_.npx; g.npy = g_.npy; m.dxa = m_.dxa; m.dya = m_.dya; pitch = g_.pitch; sd = nullptr; }
+  DEV void init(const Geom& g_, const Metrics& m_) {
+    g.npx = g_.npx; g.npy = g_.npy; pitch = g_.pitch; sd = nullptr;
+    m = MM{m_.dxa, m_.dya, m_.ppmw_x0, m_.ppmw_x1, m_.ppmw_x2, m_.ppmw_x3, m_.ppmw_y0, m_.ppmw_y1, m_.ppmw_y2, m_.ppmw_y3};
+  }
   DEV void at(const Blk& b, int ii, int jj) { i = ii + b.ci; j = jj + b.cj; mpos = b.mb + jj * b.pitch + ii; }
   DEV T in(int, int di = 0, int dj = 0, int = 0) const { return Num<TT>::lds(sv, sd, sp + dj * sw + di); }
   DEV double M(const double* a, int di = 0, int dj = 0) const { return LDG(a + (mpos + dj * pitch + di)); }
@@ -334,6 +337,20 @@ template <int DIR, class X> DEV double ppm_dc(const X& x, double c, int ord) {
     const double curv = c > 0.0 ? q0 - 2.0 * qm1 + tp::Q<DIR>(x, 0, -2) : tp::Q<DIR>(x, 0, 1) - 2.0 * q0 + qm1;
     return -0.5 * (q0 - qm1) + c / 3.0 * curv;
   }
+  {
+    // regular faces: straight-line code, no edge tests (the same fast path as tp::ppm_flux)
+    const int ia = DIR == 0 ? x.i : x.j, np = DIR == 0 ? x.g.npx : x.g.npy;
+    if (ia >= 4 && ia <= np - 3) {
+      const double qm2 = tp::Q<DIR>(x, 0, -2), qm1 = tp::Q<DIR>(x, 0, -1), q0 = tp::Q<DIR>(x, 0, 0), q1 = tp::Q<DIR>(x, 0, 1);
+      const double al0 = tp::p1 * (qm1 + q0) + tp::p2 * (qm2 + q1);
+      if (c > 0.0) {
+        const double b = tp::p1 * (qm2 + qm1) + tp::p2 * (tp::Q<DIR>(x, 0, -3) + q0) + al0 - (qm1 + qm1);
+        return -(al0 - qm1 - c * b) - (1.0 - c) * b;
+      }
+      const double b = al0 + (tp::p1 * (q0 + q1) + tp::p2 * (qm1 + tp::Q<DIR>(x, 0, 2))) - (q0 + q0);
+      return (al0 - q0 + c * b) + (1.0 + c) * b;
+    }
+  }
   const double al0 = tp::edge_al<DIR>(x, 0, 0);
   if (c > 0.0) {
     const double qt = tp::Q<DIR>(x, 0, -1), b = tp::edge_al<DIR>(x, 0, -1) + al0 - (qt + qt);
@@ -448,24 +465,6 @@ template <int DIN, bool AVG> struct KernTpRev {
     double* FA = s.u; double* CI = s.u + BFIAD::N; double* ALI = s.u + 2 * BFIAD::N;
     LTile<double> x; x.init(g, m);
     if (ph == 0) {
-      for (int c = tid; c < TX * TY; c += NTHR) {       // what the later phases read / accumulate at the block's own cells
-        const int ii = ii0 + c % TX, jj = jj0 + c / TX;
-        if (!b.inside(ii, jj)) continue;
-        const int o = b.off(ii, jj);
-        pf_l2(ci.v + o); pf_l2(fi.v + o); pf_l2(ra.v + o); pf_l2(aI.v + o);
-        if (q_ad.v) pf_l2(q_ad.v + o);
-        if (ci_ad.v) pf_l2(ci_ad.v + o);
-        if (fi_ad.v) pf_l2(fi_ad.v + o);
-        if (ra_ad.v) pf_l2(ra_ad.v + o);
-        if (co_ad.v) pf_l2(co_ad.v + o);
-        if (AVG) {
-          pf_l2(mI.v + o); pf_l2(fin2.v + o); pf_l2(fout2.v + o);
-          if (fin2_ad.v) pf_l2(fin2_ad.v + o);
-          if (fout2_ad.v) pf_l2(fout2_ad.v + o);
-          if (mI_ad.v) pf_l2(mI_ad.v + o);
-          if (mO_ad.v) pf_l2(mO_ad.v + o);
-        }
-      }
       for (int c = tid; c < BQ::N; c += NTHR) {
         const int ii = ii0 + BQ::X0 + c % BQ::W, jj = jj0 + BQ::Y0 + c / BQ::W;
         s.q[c] = b.inside(ii, jj) ? LDG(q.v + b.off(ii, jj)) : 0.0;
@@ -536,56 +535,64 @@ template <int DIN, bool AVG> struct KernTpRev {
         const int o = b.off(ii, jj);
         const bool in_i = r_i.has(ii, jj), in_m = r_m.has(ii, jj), in_o = r_o.has(ii, jj);
         const int nt = BT::idx(rx, ry);
-        double aq = 0.0;
+        // the accumulators' current values are requested first: written as `p[o] += d` one after the other, every load would wait behind the
+        // previous store (the compiler cannot prove the arrays distinct) -- up to nine exposed DRAM latencies per cell
+        const double o_q = q_ad.v ? q_ad.v[o] : 0.0, o_ra = ra_ad.v ? ra_ad.v[o] : 0.0, o_fi = fi_ad.v ? fi_ad.v[o] : 0.0;
+        const double o_ci = ci_ad.v ? ci_ad.v[o] : 0.0, o_co = co_ad.v ? co_ad.v[o] : 0.0;
+        double o_fin2 = 0.0, o_mO = 0.0, o_fout2 = 0.0, o_mI = 0.0;
+        if (AVG) {
+          o_fin2 = fin2_ad.v ? fin2_ad.v[o] : 0.0; o_mO = mO_ad.v ? mO_ad.v[o] : 0.0;
+          o_fout2 = fout2_ad.v ? fout2_ad.v[o] : 0.0; o_mI = mI_ad.v ? mI_ad.v[o] : 0.0;
+        }
+        double aq = 0.0, d_ra = 0.0, d_fi = 0.0, d_ci = 0.0, d_co = 0.0, d_fin2 = 0.0, d_mO = 0.0, d_fout2 = 0.0, d_mI = 0.0;
         if (in_m) {
           const double tt = s.t[nt];
           if (tt != 0.0) {
             aq += tt * LDG(m.area + (b.mb + jj * b.pitch + ii));
-            if (ra_ad.v) ra_ad.v[o] += -s.qm[BQM::idx(rx, ry)] * tt;
+            d_ra = -s.qm[BQM::idx(rx, ry)] * tt;
           }
         }
         if (in_i) {
-          if (fi_ad.v) {
-            const double dt = s.t[nt] - s.t[nt - BT::SI];
-            if (dt != 0.0) fi_ad.v[o] += s.Fi[BFI::idx(rx, ry)] * dt;
-          }
+          const double dt = s.t[nt] - s.t[nt - BT::SI];
+          if (dt != 0.0) d_fi = s.Fi[BFI::idx(rx, ry)] * dt;
           const double fa = FA[BFIAD::idx(rx, ry)];
           if (ci_ad.v && fa != 0.0) {
             x.sv = s.q; x.sw = BQ::W; x.sp = BQ::idx(rx, ry); x.at(b, ii, jj);
-            ci_ad.v[o] += ppm_dc<DIN>(x, LDG(ci.v + o), 2) * fa;
+            d_ci = ppm_dc<DIN>(x, LDG(ci.v + o), 2) * fa;
           }
         }
         if (in_o) {
-          double oa = LDG(aO.v + o);
+          const double a = LDG(aO.v + o);
+          double oa = a;
           if (AVG && oa != 0.0) oa *= 0.5 * LDG(mO.v + o);
-          if (co_ad.v && oa != 0.0) {
+          if ((co_ad.v || (AVG && mO_ad.v)) && a != 0.0) {
             x.sv = s.qm; x.sw = BQM::W; x.sp = BQM::idx(rx, ry); x.at(b, ii, jj);
-            co_ad.v[o] += ppm_dc<DOUT>(x, LDG(co.v + o), 2) * oa;
+            const double cc = LDG(co.v + o);
+            if (co_ad.v) d_co = ppm_dc<DOUT>(x, cc, 2) * oa;
+            if (AVG && mO_ad.v) d_mO = 0.5 * (tp::ppm_flux<DOUT, false>(x, 0, cc, 2) + LDG(fin2.v + o)) * a;     // fy = 0.5 (Fo + fy2) mO
+          }
+          if (AVG && a != 0.0) d_fin2 = 0.5 * LDG(mO.v + o) * a;
+        }
+        if (AVG && r_fi.has(ii, jj)) {       // fx = 0.5 (fx_ou + Fi) mI
+          const double a = LDG(aI.v + o);
+          if (a != 0.0) {
+            d_fout2 = 0.5 * LDG(mI.v + o) * a;
+            d_mI = 0.5 * (LDG(fout2.v + o) + s.Fi[BFI::idx(rx, ry)]) * a;
           }
         }
+        if (q_ad.v) aq += cell_adjoint<DIN>(x, b, ii, jj, FA, CI, BFIAD::idx(rx, ry), BFIAD::SI, ALI, BALI::idx(rx, ry), BALI::SI);
+        // (delp / vorticity form of fv_tp_2d: the multiplier of the averaged inner flux IS the flux area -- one accumulator, two contributions)
+        if (AVG && mI_ad.v == fi_ad.v) { d_fi += d_mI; d_mI = 0.0; }
+        if (q_ad.v && aq != 0.0) q_ad.v[o] = o_q + aq;
+        if (ra_ad.v && d_ra != 0.0) ra_ad.v[o] = o_ra + d_ra;
+        if (fi_ad.v && d_fi != 0.0) fi_ad.v[o] = o_fi + d_fi;
+        if (ci_ad.v && d_ci != 0.0) ci_ad.v[o] = o_ci + d_ci;
+        if (co_ad.v && d_co != 0.0) co_ad.v[o] = o_co + d_co;
         if (AVG) {
-          if (in_o) {             // fy = 0.5 (Fo + fy2) mO
-            const double a = LDG(aO.v + o);
-            if (a != 0.0) {
-              if (fin2_ad.v) fin2_ad.v[o] += 0.5 * LDG(mO.v + o) * a;
-              if (mO_ad.v) {
-                x.sv = s.qm; x.sw = BQM::W; x.sp = BQM::idx(rx, ry); x.at(b, ii, jj);
-                const double Fo = tp::ppm_flux<DOUT, false>(x, 0, LDG(co.v + o), 2);
-                mO_ad.v[o] += 0.5 * (Fo + LDG(fin2.v + o)) * a;
-              }
-            }
-          }
-          if (r_fi.has(ii, jj)) {       // fx = 0.5 (fx_ou + Fi) mI
-            const double a = LDG(aI.v + o);
-            if (a != 0.0) {
-              if (fout2_ad.v) fout2_ad.v[o] += 0.5 * LDG(mI.v + o) * a;
-              if (mI_ad.v) mI_ad.v[o] += 0.5 * (LDG(fout2.v + o) + s.Fi[BFI::idx(rx, ry)]) * a;
-            }
-          }
-        }
-        if (q_ad.v) {
-          aq += cell_adjoint<DIN>(x, b, ii, jj, FA, CI, BFIAD::idx(rx, ry), BFIAD::SI, ALI, BALI::idx(rx, ry), BALI::SI);
-          if (aq != 0.0) q_ad.v[o] += aq;
+          if (fin2_ad.v && d_fin2 != 0.0) fin2_ad.v[o] = o_fin2 + d_fin2;
+          if (mO_ad.v && d_mO != 0.0) mO_ad.v[o] = o_mO + d_mO;
+          if (fout2_ad.v && d_fout2 != 0.0) fout2_ad.v[o] = o_fout2 + d_fout2;
+          if (mI_ad.v && d_mI != 0.0) mI_ad.v[o] = o_mI + d_mI;
         }
       }
     }
@@ -911,3 +918,5 @@ inline void add_fused_b(Program& P, const std::string& nm, int q, int crx, int x
 
 }  // namespace ftp
 }  // namespace fv3lm
+
+#include "fused_tp_march.h"   // definitions of march_fwd_a / march_fwd_b (needs everything above)

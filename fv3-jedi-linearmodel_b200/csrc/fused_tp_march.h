@@ -30,7 +30,7 @@ template <class TT, int DIR> struct WinCtx {
   using T = TT;
   static constexpr int mode = std::is_same<TT, double>::value ? 0 : 1;
   struct { int npx, npy; } g;
-  struct { const double* dxa; const double* dya; } m;
+  typename LTile<TT>::MM m;
   TT w[6];
   int i, j, mpos, pitch;
   DEV T in(int, int di = 0, int dj = 0, int = 0) const { return w[(DIR == 0 ? di : dj) + 3]; }
@@ -100,7 +100,7 @@ template <class TT, bool FULL> struct MarchA {
       TT f = TT(0.0);
       const bool col_y = ii <= b.xe + b.ng;      // (isd:ied) = array columns 0 .. xe+ng
       if (col_y && r >= b.ys && r <= b.ye + 1) {
-        WinCtx<TT, 1> x; x.g.npx = g.npx; x.g.npy = g.npy; x.m.dxa = m.dxa; x.m.dya = m.dya; x.pitch = b.pitch;
+        WinCtx<TT, 1> x; x.g.npx = g.npx; x.g.npy = g.npy; x.m = typename LTile<TT>::MM{m.dxa, m.dya, m.ppmw_x0, m.ppmw_x1, m.ppmw_x2, m.ppmw_x3, m.ppmw_y0, m.ppmw_y1, m.ppmw_y2, m.ppmw_y3}; x.pitch = b.pitch;
 #pragma unroll
         for (int n = 0; n < 6; n++) x.w[n] = st.w[n];
         x.i = ii + b.ci; x.j = r + b.cj; x.mpos = b.mb + r * b.pitch + ii;
@@ -116,7 +116,7 @@ template <class TT, bool FULL> struct MarchA {
       if (r > b.jj0) s.row[r & 1].put(ii, qi);
     } else {
       if (!col || !row_c || ii < b.xs || ii > b.xe + 1) return;
-      WinCtx<TT, 0> x; x.g.npx = g.npx; x.g.npy = g.npy; x.m.dxa = m.dxa; x.m.dya = m.dya; x.pitch = b.pitch;
+      WinCtx<TT, 0> x; x.g.npx = g.npx; x.g.npy = g.npy; x.m = typename LTile<TT>::MM{m.dxa, m.dya, m.ppmw_x0, m.ppmw_x1, m.ppmw_x2, m.ppmw_x3, m.ppmw_y0, m.ppmw_y1, m.ppmw_y2, m.ppmw_y3}; x.pitch = b.pitch;
       const RowBuf<TT>& rb = s.row[r & 1];
 #pragma unroll
       for (int n = 0; n < 6; n++) x.w[n] = rb.get(ii - 3 + n);
@@ -160,7 +160,7 @@ template <class TT, bool FULL> struct MarchB {
       TT fxx = TT(0.0);
       st.fx2 = TT(0.0);
       if (row_in && ii >= b.xs && ii <= b.xe + 1) {
-        WinCtx<TT, 0> x; x.g.npx = g.npx; x.g.npy = g.npy; x.m.dxa = m.dxa; x.m.dya = m.dya; x.pitch = b.pitch;
+        WinCtx<TT, 0> x; x.g.npx = g.npx; x.g.npy = g.npy; x.m = typename LTile<TT>::MM{m.dxa, m.dya, m.ppmw_x0, m.ppmw_x1, m.ppmw_x2, m.ppmw_x3, m.ppmw_y0, m.ppmw_y1, m.ppmw_y2, m.ppmw_y3}; x.pitch = b.pitch;
 #pragma unroll
         for (int n = 0; n < 6; n++) x.w[n] = s.qrow.get(ii - 3 + n);
         x.i = ii + b.ci; x.j = r + b.cj; x.mpos = b.mb + r * b.pitch + ii;
@@ -177,7 +177,7 @@ template <class TT, bool FULL> struct MarchB {
       st.w[5] = qj;
       const int f = r - 2;                       // the outer face whose six rows are now complete
       if (f >= b.jj0 && f < b.jj0 + MARCH_RY && f >= b.ys && f <= b.ye + 1 && ii >= b.xs && ii <= b.xe) {
-        WinCtx<TT, 1> x; x.g.npx = g.npx; x.g.npy = g.npy; x.m.dxa = m.dxa; x.m.dya = m.dya; x.pitch = b.pitch;
+        WinCtx<TT, 1> x; x.g.npx = g.npx; x.g.npy = g.npy; x.m = typename LTile<TT>::MM{m.dxa, m.dya, m.ppmw_x0, m.ppmw_x1, m.ppmw_x2, m.ppmw_x3, m.ppmw_y0, m.ppmw_y1, m.ppmw_y2, m.ppmw_y3}; x.pitch = b.pitch;
 #pragma unroll
         for (int n = 0; n < 6; n++) x.w[n] = st.w[n];
         x.i = ii + b.ci; x.j = f + b.cj; x.mpos = b.mb + f * b.pitch + ii;

@@ -174,11 +174,17 @@ struct S_edge_profile {
     double q_hi = p.xt1_b * n;                          // pending contribution to q_ad[k] of the row above (k = K-1 now)
     double q_lo = n;                                    // ... and to q_ad[k-1]
     double carry = -(p.a_bot * n);                      // ad[K-1] -= a_bot n
-    for (int k = K - 1; k >= 1; k--) {
-      n = (x.oad(0, k) + carry) / p.bet.v[k];
-      x.add(0, k, q_hi + 3.0 * p.gk.v[k] * n);
-      q_hi = q_lo + 3.0 * n; q_lo = 0.0;
-      carry = -n;
+    for (int k = K - 1; k >= 1; k -= 4) {        // four levels per batch: work array and accumulators requested together
+      double o[4], t[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (k - u >= 1) { o[u] = x.oad(0, k - u); t[u] = x.iad(0, k - u); }
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (k - u >= 1) {
+        n = (o[u] + carry) / p.bet.v[k - u];
+        x.iad_set(0, k - u, t[u] + (q_hi + 3.0 * p.gk.v[k - u] * n));
+        q_hi = q_lo + 3.0 * n; q_lo = 0.0;
+        carry = -n;
+      }
     }
     n = (x.oad(0, 0) + carry) / p.bet.v[0];
     // K >= 2: q_hi holds what rows 1.. gave to q_ad[0]; row 0 adds xt1_0 n to q_ad[0] and n to q_ad[1]

@@ -43,10 +43,23 @@ struct S_cum {
     const Geom& g = x.g;
     if (!x.in_rect(g.is - p.halo, g.ie + p.halo, g.js - p.halo, g.je + p.halo)) return;
     double a = 0.0;
+    // four levels per batch: their output adjoints and accumulators are requested together (distinct addresses), then updated
     if (p.mode == 0) {
-      for (int k = p.K; k >= 1; k--) { a += x.oad(0, k); x.add(0, k - 1, a); }
+      for (int k = p.K; k >= 1; k -= 4) {
+        double o[4], t[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (k - u >= 1) { o[u] = x.oad(0, k - u); t[u] = x.iad(0, k - u - 1); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (k - u >= 1) { a += o[u]; x.iad_set(0, k - u - 1, t[u] + a); }
+      }
     } else {
-      for (int k = 0; k < p.K; k++) { a += x.oad(0, k); x.add(0, k, -a * p.c); }
+      for (int k = 0; k < p.K; k += 4) {
+        double o[4], t[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (k + u < p.K) { o[u] = x.oad(0, k + u); t[u] = x.iad(0, k + u); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (k + u < p.K) { a += o[u]; x.iad_set(0, k + u, t[u] + (-a * p.c)); }
+      }
       a += x.oad(0, p.K);
       x.add(1, 0, a);
     }
@@ -98,12 +111,33 @@ struct S_tri {
       lam[k] = (x.oad(0, k + p.out_off) - UP(k - 1) * lam[k - 1]) / bet;
     }
     for (int k = K - 2; k >= 0; k--) lam[k] = lam[k] - gam[k + 1] * lam[k + 1];
+    // per level: the four accumulators are requested together, then stored (lo and up may be the same interface array read at k + lo_off
+    // and k + up_off: distinct addresses within a level as long as the offsets differ, else the two contributions are merged)
+    const bool lo_up_same = x.same_ad(0, 2) && p.lo_off == p.up_off;
+    // any other coincidence of accumulators (the same value bound to two inputs at the same level) keeps the plain sequence of add()s
+    const bool alias = (!p.lo_one && (x.same_ad(0, 1) || x.same_ad(0, 3))) || x.same_ad(1, 2) || x.same_ad(1, 3) || x.same_ad(2, 3);
+    if (alias) {
+      for (int k = 0; k < K; k++) {
+        const double l = lam[k], xk = x.outv(0, k + p.out_off);
+        x.add(3, k, l);
+        x.add(1, k, -l * xk);
+        if (k >= 1 && !p.lo_one) x.add(0, k + p.lo_off, -l * x.outv(0, k - 1 + p.out_off));
+        if (k < K - 1) x.add(2, k + p.up_off, -l * x.outv(0, k + 1 + p.out_off));
+      }
+      return;
+    }
     for (int k = 0; k < K; k++) {
       const double l = lam[k], xk = x.outv(0, k + p.out_off);
-      x.add(3, k, l);
-      x.add(1, k, -l * xk);
-      if (k >= 1 && !p.lo_one) x.add(0, k + p.lo_off, -l * x.outv(0, k - 1 + p.out_off));
-      if (k < K - 1) x.add(2, k + p.up_off, -l * x.outv(0, k + 1 + p.out_off));
+      const bool has_lo = k >= 1 && !p.lo_one, has_up = k < K - 1;
+      const double o3 = x.iad(3, k), o1 = x.iad(1, k);
+      const double o0 = has_lo ? x.iad(0, k + p.lo_off) : 0.0, o2 = has_up ? x.iad(2, k + p.up_off) : 0.0;
+      double d0 = has_lo ? -l * x.outv(0, k - 1 + p.out_off) : 0.0;
+      const double d2 = has_up ? -l * x.outv(0, k + 1 + p.out_off) : 0.0;
+      x.iad_set(3, k, o3 + l);
+      x.iad_set(1, k, o1 + -l * xk);
+      if (lo_up_same && has_lo && has_up) { x.iad_set(0, k + p.lo_off, o0 + d0 + d2); continue; }
+      if (has_lo) x.iad_set(0, k + p.lo_off, o0 + d0);
+      if (has_up) x.iad_set(2, k + p.up_off, o2 + d2);
     }
   }
 };
@@ -132,10 +166,11 @@ template <bool SIM> struct S_rs_pe2_t {
     if (!x.in_rect(g.is - p.halo, g.ie + p.halo, g.js - p.halo, g.je + p.halo)) return;
     double a = 0.0;
     for (int k = p.K - 1; k >= 0; k--) {
+      const double o0 = x.iad(0, k), o1 = x.iad(1, k), o2 = x.iad(2, k);     // requested together with the output adjoint, stored below
       a += x.oad(0, k + 1);
       const double dm = x.in(0, k) * p.rgrav, dw = x.in(1, k) - x.in(2, k);
       const double b = SIM ? a * p.ra : a;
-      x.add(0, k, b * p.rgrav * dw * p.rdt); x.add(1, k, b * dm * p.rdt); x.add(2, k, -b * dm * p.rdt);
+      x.iad_set(0, k, o0 + b * p.rgrav * dw * p.rdt); x.iad_set(1, k, o1 + b * dm * p.rdt); x.iad_set(2, k, o2 + -b * dm * p.rdt);
       if constexpr (SIM) { x.add(3, k + 1, -b * p.beta); x.add(3, k, b * p.beta); }
     }
   }
@@ -168,9 +203,11 @@ struct S_rs_p1 {
     const double r3 = rmp::r3;
     double carry = 0.0;
     for (int k = 0; k < K - 1; k++) {
+      // the five accumulators of the level (distinct addresses) are requested together, then stored
+      const double a0 = x.iad(0, k), a01 = x.iad(0, k + 1), a02 = x.iad(0, k + 2), a1 = x.iad(1, k), a2 = x.iad(2, k);
       const double Pk = x.oad(0, k) + carry, gk = x.in(2, k);
-      x.add(0, k, Pk * r3); x.add(1, k, Pk * r3 * x.in(0, k + 1)); x.add(0, k + 1, Pk * r3 * x.in(1, k));
-      x.add(2, k, Pk * (r3 * x.in(0, k + 2) - x.outv(0, k + 1))); x.add(0, k + 2, Pk * r3 * gk);
+      x.iad_set(0, k, a0 + Pk * r3); x.iad_set(1, k, a1 + Pk * r3 * x.in(0, k + 1)); x.iad_set(0, k + 1, a01 + Pk * r3 * x.in(1, k));
+      x.iad_set(2, k, a2 + Pk * (r3 * x.in(0, k + 2) - x.outv(0, k + 1))); x.iad_set(0, k + 2, a02 + Pk * r3 * gk);
       carry = -gk * Pk;
     }
     const double Pk = x.oad(0, K - 1) + carry;

@@ -34,6 +34,14 @@ template <int DIR, class X> DEV typename X::T Q(const X& x, int f, int d) {
 template <int DIR, class X> DEV double DA(const X& x, int d) {   // dxa / dya
   return DIR == 0 ? x.M(x.m.dxa, d, 0) : x.M(x.m.dya, 0, d);
 }
+// weight of q(e-2+n) in the edge value AL(e) on a cube edge (e = 1 or np), e at offset d from the current position: precomputed from
+// dxa / dya when the metrics are uploaded (capi.cu), so that a warp with lanes on a cube edge loads four numbers instead of running two
+// double-precision divisions per edge value (ncu r02k: the division paths were a quarter of the reverse tile kernel's instructions)
+template <int DIR, class X> DEV double PW(const X& x, int n, int d) {
+  const double* a = DIR == 0 ? (n == 0 ? x.m.ppmw_x0 : n == 1 ? x.m.ppmw_x1 : n == 2 ? x.m.ppmw_x2 : x.m.ppmw_x3)
+                             : (n == 0 ? x.m.ppmw_y0 : n == 1 ? x.m.ppmw_y1 : n == 2 ? x.m.ppmw_y2 : x.m.ppmw_y3);
+  return DIR == 0 ? x.M(a, d, 0) : x.M(a, 0, d);
+}
 
 // PPM edge value al at index (pos + d), pos = current i (DIR 0) or j (DIR 1).
 // tp_core_tlm.F90:2396-2430 (x) and the symmetric y code.
@@ -43,13 +51,25 @@ template <int DIR, class X> DEV typename X::T edge_al(const X& x, int f, int d) 
   const int np = DIR == 0 ? x.g.npx : x.g.npy;
   if (ia == 0 || ia == np - 1) return c1 * Q<DIR>(x, f, d - 2) + c2 * Q<DIR>(x, f, d - 1) + c3 * Q<DIR>(x, f, d);
   if (ia == 2 || ia == np + 1) return c3 * Q<DIR>(x, f, d - 1) + c2 * Q<DIR>(x, f, d) + c1 * Q<DIR>(x, f, d + 1);
+  if (ia == 1 || ia == np)     // 0.5 (l + r) of the two one-sided extrapolations, as four precomputed weights
+    return (PW<DIR>(x, 0, d) * Q<DIR>(x, f, d - 2) + PW<DIR>(x, 1, d) * Q<DIR>(x, f, d - 1)) + (PW<DIR>(x, 2, d) * Q<DIR>(x, f, d) + PW<DIR>(x, 3, d) * Q<DIR>(x, f, d + 1));
+  return p1 * (Q<DIR>(x, f, d - 1) + Q<DIR>(x, f, d)) + p2 * (Q<DIR>(x, f, d - 2) + Q<DIR>(x, f, d + 1));
+}
+
+// the same edge value with the cube-edge extrapolation evaluated exactly as the reference writes it (two divisions): used by the
+// smoothness-switch schemes of the nonlinear model (iord = 3 .. 7), whose discrete switches compare edge values and must see the reference's
+// rounding on plateaus (tests/test_tp_core.py: integer-valued fields); the linear schemes have no switches and use the precomputed weights
+template <int DIR, class X> DEV typename X::T edge_al_ref(const X& x, int f, int d) {
+  using T = typename X::T;
+  const int ia = (DIR == 0 ? x.i : x.j) + d;
+  const int np = DIR == 0 ? x.g.npx : x.g.npy;
   if (ia == 1 || ia == np) {
     double a0 = DA<DIR>(x, d - 1), am = DA<DIR>(x, d - 2), a1 = DA<DIR>(x, d), a2 = DA<DIR>(x, d + 1);
     T l = ((2.0 * a0 + am) * Q<DIR>(x, f, d - 1) - a0 * Q<DIR>(x, f, d - 2)) / (am + a0);
     T r = ((2.0 * a1 + a2) * Q<DIR>(x, f, d) - a1 * Q<DIR>(x, f, d + 1)) / (a1 + a2);
     return 0.5 * (l + r);
   }
-  return p1 * (Q<DIR>(x, f, d - 1) + Q<DIR>(x, f, d)) + p2 * (Q<DIR>(x, f, d - 2) + Q<DIR>(x, f, d + 1));
+  return edge_al<DIR>(x, f, d);
 }
 
 // ---- monotone PPM (iord = 8 .. 13) in perturbation form: bl = AL - q, br = AR - q of the cell at offset co from the current face
@@ -141,7 +161,7 @@ template <int DIR, bool FULL, class X> DEV typename X::T ppm_flux(const X& x, in
   if (ord >= 3 && ord <= 7) {
     // iord = 3 .. 7 (tp_core_nlm.F90:386-467): unlimited edge values, the second-order increment only where the profile is smooth
     auto AL = [&](int d) {
-      T a = edge_al<DIR>(x, fq, d);
+      T a = edge_al_ref<DIR>(x, fq, d);
       if (ord == 7 && val(a) < 0.0) {       // :343-346, :358-362, :369-373: positivity of the edge values
         const int ia = (DIR == 0 ? x.i : x.j) + d, np = DIR == 0 ? x.g.npx : x.g.npy;
         const bool edge = ia <= 2 || ia >= np - 1;
@@ -241,10 +261,7 @@ template <int DIR> struct S_ppm {
     const int np = DIR == 0 ? x.g.npx : x.g.npy;
     if (ia == 0 || ia == np - 1) return n == 0 ? tp::c1 : n == 1 ? tp::c2 : n == 2 ? tp::c3 : 0.0;
     if (ia == 2 || ia == np + 1) return n == 0 ? 0.0 : n == 1 ? tp::c3 : n == 2 ? tp::c2 : tp::c1;
-    if (ia == 1 || ia == np) {
-      double a0 = tp::DA<DIR>(x, eo - 1), am = tp::DA<DIR>(x, eo - 2), a1 = tp::DA<DIR>(x, eo), a2 = tp::DA<DIR>(x, eo + 1);
-      return n == 0 ? -0.5 * a0 / (am + a0) : n == 1 ? 0.5 * (2.0 * a0 + am) / (am + a0) : n == 2 ? 0.5 * (2.0 * a1 + a2) / (a1 + a2) : -0.5 * a1 / (a1 + a2);
-    }
+    if (ia == 1 || ia == np) return tp::PW<DIR>(x, n, eo);
     return (n == 0 || n == 3) ? tp::p2 : tp::p1;
   }
   template <class K> DEV static void adjoint(const K& kn, int ii, int jj, int kk, int tile, double* acc) {
