@@ -233,4 +233,16 @@ void mod_dyn_core(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm)
   io.out(P, "pkz", o.pkz); io.out(P, "pe", o.pe); io.out(P, "peln", o.peln); io.out(P, "pk", o.pk);
 }
 
+// geopk / compute_fv3_pressures on its own (model/dyn_core_nlm.F90:1954-2087; fv3jedi_lm_dynamics_mod.F90 compute_fv3_pressures_{tlm,bwd}):
+// halo = 0 is the compute-domain form the step driver uses for the output pressures, 1 / 2 the C- / D-grid calls
+void mod_geopk(Program& P, Mosaic&, ModuleIO& io, const ModuleParams& prm) {
+  const int K = P.dv->g.K;
+  const fv3lm_config* f = prm.cfg;
+  int delp = io.in(P, "delp", K), pt = io.in(P, "pt", K), phis = io.in(P, "phis", 1);
+  int pk = P.val("pk", K + 1), gz = P.val("gz", K + 1), pe = P.val("pe", K + 1), peln = P.val("peln", K + 1), pkz = P.val("pkz", K);
+  add_col<S_geopk>(P, "geopk", {prm.get("ptop", f->ptop), prm.get("akap", f->kappa), prm.get("cp_air", f->cp), prm.geti("halo", 0), prm.geti("cg", 0), K},
+                   {delp, pt, phis}, {pk, gz, pe, peln, pkz});
+  io.out(P, "pk", pk); io.out(P, "gz", gz); io.out(P, "pe", pe); io.out(P, "peln", peln); io.out(P, "pkz", pkz);
+}
+
 }  // namespace fv3lm

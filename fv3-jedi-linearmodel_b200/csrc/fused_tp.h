@@ -535,64 +535,57 @@ template <int DIN, bool AVG> struct KernTpRev {
         const int o = b.off(ii, jj);
         const bool in_i = r_i.has(ii, jj), in_m = r_m.has(ii, jj), in_o = r_o.has(ii, jj);
         const int nt = BT::idx(rx, ry);
-        // the accumulators' current values are requested first: written as `p[o] += d` one after the other, every load would wait behind the
-        // previous store (the compiler cannot prove the arrays distinct) -- up to nine exposed DRAM latencies per cell
-        const double o_q = q_ad.v ? q_ad.v[o] : 0.0, o_ra = ra_ad.v ? ra_ad.v[o] : 0.0, o_fi = fi_ad.v ? fi_ad.v[o] : 0.0;
-        const double o_ci = ci_ad.v ? ci_ad.v[o] : 0.0, o_co = co_ad.v ? co_ad.v[o] : 0.0;
-        double o_fin2 = 0.0, o_mO = 0.0, o_fout2 = 0.0, o_mI = 0.0;
-        if (AVG) {
-          o_fin2 = fin2_ad.v ? fin2_ad.v[o] : 0.0; o_mO = mO_ad.v ? mO_ad.v[o] : 0.0;
-          o_fout2 = fout2_ad.v ? fout2_ad.v[o] : 0.0; o_mI = mI_ad.v ? mI_ad.v[o] : 0.0;
-        }
-        double aq = 0.0, d_ra = 0.0, d_fi = 0.0, d_ci = 0.0, d_co = 0.0, d_fin2 = 0.0, d_mO = 0.0, d_fout2 = 0.0, d_mI = 0.0;
+        // (requesting all nine accumulators ahead of the stores was tried: 64 -> 112 registers, 1.9 -> 2.8 ms per launch, profiles/r02m_ncu_TpRevB.txt)
+        double aq = 0.0;
         if (in_m) {
           const double tt = s.t[nt];
           if (tt != 0.0) {
             aq += tt * LDG(m.area + (b.mb + jj * b.pitch + ii));
-            d_ra = -s.qm[BQM::idx(rx, ry)] * tt;
+            if (ra_ad.v) ra_ad.v[o] += -s.qm[BQM::idx(rx, ry)] * tt;
           }
         }
         if (in_i) {
-          const double dt = s.t[nt] - s.t[nt - BT::SI];
-          if (dt != 0.0) d_fi = s.Fi[BFI::idx(rx, ry)] * dt;
+          if (fi_ad.v) {
+            const double dt = s.t[nt] - s.t[nt - BT::SI];
+            if (dt != 0.0) fi_ad.v[o] += s.Fi[BFI::idx(rx, ry)] * dt;
+          }
           const double fa = FA[BFIAD::idx(rx, ry)];
           if (ci_ad.v && fa != 0.0) {
             x.sv = s.q; x.sw = BQ::W; x.sp = BQ::idx(rx, ry); x.at(b, ii, jj);
-            d_ci = ppm_dc<DIN>(x, LDG(ci.v + o), 2) * fa;
+            ci_ad.v[o] += ppm_dc<DIN>(x, LDG(ci.v + o), 2) * fa;
           }
         }
         if (in_o) {
-          const double a = LDG(aO.v + o);
-          double oa = a;
+          double oa = LDG(aO.v + o);
           if (AVG && oa != 0.0) oa *= 0.5 * LDG(mO.v + o);
-          if ((co_ad.v || (AVG && mO_ad.v)) && a != 0.0) {
+          if (co_ad.v && oa != 0.0) {
             x.sv = s.qm; x.sw = BQM::W; x.sp = BQM::idx(rx, ry); x.at(b, ii, jj);
-            const double cc = LDG(co.v + o);
-            if (co_ad.v) d_co = ppm_dc<DOUT>(x, cc, 2) * oa;
-            if (AVG && mO_ad.v) d_mO = 0.5 * (tp::ppm_flux<DOUT, false>(x, 0, cc, 2) + LDG(fin2.v + o)) * a;     // fy = 0.5 (Fo + fy2) mO
-          }
-          if (AVG && a != 0.0) d_fin2 = 0.5 * LDG(mO.v + o) * a;
-        }
-        if (AVG && r_fi.has(ii, jj)) {       // fx = 0.5 (fx_ou + Fi) mI
-          const double a = LDG(aI.v + o);
-          if (a != 0.0) {
-            d_fout2 = 0.5 * LDG(mI.v + o) * a;
-            d_mI = 0.5 * (LDG(fout2.v + o) + s.Fi[BFI::idx(rx, ry)]) * a;
+            co_ad.v[o] += ppm_dc<DOUT>(x, LDG(co.v + o), 2) * oa;
           }
         }
-        if (q_ad.v) aq += cell_adjoint<DIN>(x, b, ii, jj, FA, CI, BFIAD::idx(rx, ry), BFIAD::SI, ALI, BALI::idx(rx, ry), BALI::SI);
-        // (delp / vorticity form of fv_tp_2d: the multiplier of the averaged inner flux IS the flux area -- one accumulator, two contributions)
-        if (AVG && mI_ad.v == fi_ad.v) { d_fi += d_mI; d_mI = 0.0; }
-        if (q_ad.v && aq != 0.0) q_ad.v[o] = o_q + aq;
-        if (ra_ad.v && d_ra != 0.0) ra_ad.v[o] = o_ra + d_ra;
-        if (fi_ad.v && d_fi != 0.0) fi_ad.v[o] = o_fi + d_fi;
-        if (ci_ad.v && d_ci != 0.0) ci_ad.v[o] = o_ci + d_ci;
-        if (co_ad.v && d_co != 0.0) co_ad.v[o] = o_co + d_co;
         if (AVG) {
-          if (fin2_ad.v && d_fin2 != 0.0) fin2_ad.v[o] = o_fin2 + d_fin2;
-          if (mO_ad.v && d_mO != 0.0) mO_ad.v[o] = o_mO + d_mO;
-          if (fout2_ad.v && d_fout2 != 0.0) fout2_ad.v[o] = o_fout2 + d_fout2;
-          if (mI_ad.v && d_mI != 0.0) mI_ad.v[o] = o_mI + d_mI;
+          if (in_o) {             // fy = 0.5 (Fo + fy2) mO
+            const double a = LDG(aO.v + o);
+            if (a != 0.0) {
+              if (fin2_ad.v) fin2_ad.v[o] += 0.5 * LDG(mO.v + o) * a;
+              if (mO_ad.v) {
+                x.sv = s.qm; x.sw = BQM::W; x.sp = BQM::idx(rx, ry); x.at(b, ii, jj);
+                const double Fo = tp::ppm_flux<DOUT, false>(x, 0, LDG(co.v + o), 2);
+                mO_ad.v[o] += 0.5 * (Fo + LDG(fin2.v + o)) * a;
+              }
+            }
+          }
+          if (r_fi.has(ii, jj)) {       // fx = 0.5 (fx_ou + Fi) mI
+            const double a = LDG(aI.v + o);
+            if (a != 0.0) {
+              if (fout2_ad.v) fout2_ad.v[o] += 0.5 * LDG(mI.v + o) * a;
+              if (mI_ad.v) mI_ad.v[o] += 0.5 * (LDG(fout2.v + o) + s.Fi[BFI::idx(rx, ry)]) * a;
+            }
+          }
+        }
+        if (q_ad.v) {
+          aq += cell_adjoint<DIN>(x, b, ii, jj, FA, CI, BFIAD::idx(rx, ry), BFIAD::SI, ALI, BALI::idx(rx, ry), BALI::SI);
+          if (aq != 0.0) q_ad.v[o] += aq;
         }
       }
     }

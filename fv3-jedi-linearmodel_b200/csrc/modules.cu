@@ -108,6 +108,7 @@ void mod_update_dz_d(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& p
 void mod_dyn_core_nh(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_d_sw(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 void mod_a2b_ord4(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
+void mod_geopk(Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm);
 
 struct ModEntry { const char* name; void (*fn)(Program&, Mosaic&, ModuleIO&, const ModuleParams&); const char* doc; };
 static const ModEntry g_mods[] = {
@@ -127,6 +128,7 @@ static const ModEntry g_mods[] = {
     {"del2_cubed", mod_del2_cubed, "in: q; out: q_n; params: cd (coefficient relative to da_min) nmax"},
     {"heat_update", mod_heat_update, "in: heat pt delp aux (pkz if hydrostatic, else delz); out: pt_n; params: hydrostatic bdt nord vtdm4 d2_bg_k1 d2_bg_k2 + constants"},
     {"halo", mod_halo, "in/out: q qc u v uc vc; params: corners"},
+    {"geopk", mod_geopk, "in: delp pt phis; out: pk gz pe peln pkz; params: halo (0 = compute_fv3_pressures, 1 = C grid, 2 = D grid) cg ptop akap cp_air"},
 };
 
 void build_module(const std::string& name, Program& P, Mosaic& mo, ModuleIO& io, const ModuleParams& prm) {

@@ -261,8 +261,25 @@ struct S_remap {
       dp_ad[1] += grat_ad / dp[0]; dp_ad[0] -= grat_ad * grat / dp[0];
     }
     for (int k = 0; k < K; k++) { pe1_ad[k + 1] += dp_ad[k]; pe1_ad[k] -= dp_ad[k]; }
-    for (int k = 0; k < K; k++) { x.add(0, k, a_ad[k]); if (p.use_dp2) x.add(4, k, dp2_ad[k]); }
-    for (int k = 0; k <= K; k++) { x.add(1, k, pe1_ad[k]); x.add(2, k, pe2_ad[k]); }
+    // flush: four levels per batch, accumulators requested before the stores (see ColAD::iad)
+    for (int k = 0; k < K; k += 4) {
+      double t0[4], t4[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (k + u < K) { t0[u] = x.iad(0, k + u); t4[u] = p.use_dp2 ? x.iad(4, k + u) : 0.0; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (k + u < K) { x.iad_set(0, k + u, t0[u] + a_ad[k + u]); if (p.use_dp2) x.iad_set(4, k + u, t4[u] + dp2_ad[k + u]); }
+    }
+    if (x.same_ad(1, 2)) {
+      for (int k = 0; k <= K; k++) { x.add(1, k, pe1_ad[k]); x.add(2, k, pe2_ad[k]); }
+    } else {
+      for (int k = 0; k <= K; k += 4) {
+        double t1[4], t2[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (k + u <= K) { t1[u] = x.iad(1, k + u); t2[u] = x.iad(2, k + u); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (k + u <= K) { x.iad_set(1, k + u, t1[u] + pe1_ad[k + u]); x.iad_set(2, k + u, t2[u] + pe2_ad[k + u]); }
+      }
+    }
   }
 };
 

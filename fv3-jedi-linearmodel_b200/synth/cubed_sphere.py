@@ -8,7 +8,7 @@ parity unpinned: the reference ships no golden vectors; th
 vector rotation/sign rules live in un-vendored FMS (mpp_domains_mod, no version
 pin, CMakeLists.txt:70-74) and are re-derived here from the contact table
  tools/fv_mp_nlm_mod.F90:524-573 and checked by geometric invariants in
-tests/test_geometry.py.
+tests/test_invariants.py.
 
 Array convention used by the whole oracle: a per-tile 2-D slab is stored as
 [..., NY, NX] with NX = NY = N + 2*ng + 1 (ng = 3, tools/fv_mp_nlm_mod.F90:63),

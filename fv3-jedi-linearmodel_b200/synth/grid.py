@@ -10,7 +10,7 @@ Deviation (documented in DESIGN.md): the reference sorts the four corner points 
 cell before summing (sorted_inta/sorted_intb) to make tiles bitwise mirror-symmetric;
 we sum in natural order (differences are O(1e-16) relative).
 
-The reference holds no golden grid data; tests/test_geometry.py
+The reference holds no golden grid data; tests/test_invariants.py
 checks invariants (sum(area)=4 pi R^2, edge continuity, sin^2+cos^2=1, symmetry).
 
 Every array is [6, NY, NX] (or [6, NY, NX, c]); Fortran index (i,j) -> [j+2, i+2].

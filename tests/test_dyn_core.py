@@ -179,3 +179,31 @@ def test_del2_cubed_and_heat_gpu():
 @pytest.mark.parametrize("n_split", [1, 3])
 def test_dyn_core_hydro_gpu(n_split):
     _run(False, n_split)
+
+
+# ---- geopk on its own: the compute-domain form is compute_fv3_pressures (fvdyn.cu "compute_fv3_pressures") ----
+def _run_geopk(emu, halo):
+    from oracle.dyn_core import geopk
+    N, K = 12, 6
+    rng = np.random.default_rng(17)
+    g = ograd(N)
+    ptop, akap, cp_air = 100.0, 2.0 / 7.0, 1004.6
+    f = {"delp": 1.0e4 / K * (1.0 + 0.2 * rng.random((6, K, N + 7, N + 7))), "pt": 300.0 + 5.0 * rnd(rng, N, K),
+         "phis": 50.0 * rnd(rng, N, 1)}
+    h = handle(N, K, emu)
+    lo, hi = 1 - halo, N + halo
+    outs = {"pk": (lo, hi, lo, hi), "gz": (lo, hi, lo, hi), "pe": (1, N, 1, N), "peln": (1, N, 1, N), "pkz": (1, N, 1, N)}
+    hs = torch.from_numpy(f["phis"])
+    return check_module(h, "geopk", N, K, f, ["delp", "pt"], outs, lambda dp, pt: geopk(dp, pt, hs, g, ptop, akap, cp_air, halo, False),
+                        {"halo": halo, "cg": 0, "ptop": ptop, "akap": akap, "cp_air": cp_air}, rng,
+                        out_nk={"pk": K + 1, "gz": K + 1, "pe": K + 1, "peln": K + 1, "pkz": K})
+
+
+@pytest.mark.parametrize("halo", [0, 2])
+def test_geopk_compute_fv3_pressures_emu(halo):
+    print(_run_geopk(True, halo))
+
+
+@pytest.mark.gpu
+def test_geopk_compute_fv3_pressures_gpu():
+    print(_run_geopk(False, 0))
