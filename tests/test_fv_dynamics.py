@@ -97,7 +97,7 @@ def _run_step(emu, k_split, n_split, K=4, nonhydro=False, N=12):
         z = np.zeros_like(f[k]); z[..., R(1, N), R(1, N)] = f[k][..., R(1, N), R(1, N)]; f[k] = z
     if nonhydro:
         inputs = {k: f[k] for k in ["u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz", "phis"]}
-        return check_module(h, "step", N, K, inputs, act, outs, fn, p, rng, tol=2e-9, dot_tol=1e-10, pert_scale=1e-3)
+        return check_module(h, "step", N, K, inputs, act, outs, fn, p, rng, tol=3e-11, dot_tol=1e-12, pert_scale=1e-3)     # achieved 1.2e-12 / 6e-16 on the B200 (profiles/parity_errors.json)
     return check_module(h, "step", N, K, f, act, outs, fn, p, rng, tol=2e-10, dot_tol=1e-11, pert_scale=1e-3)
 
 

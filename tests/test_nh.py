@@ -60,7 +60,7 @@ def _run_riem(emu, mode, a_imp=1.0, K=5, eta_levels=None):
     outs = {o: C for o in onames}
     h = handle(N, K, emu, ak, bk, ptop=cfg["ptop"]) if eta_levels is not None else handle(N, K, emu, ak, bk)
     p = dict(mode=mode, dts=dts, ptop=cfg["ptop"], akap=cfg["akap"], rdgas=cfg["rdgas"], grav=cfg["grav"], a_imp=a_imp)
-    return check_module(h, "riem", N, K, f, list(f.keys()), outs, fn, p, rng, tol=1e-10, dot_tol=1e-11, pert_scale=1e-3, out_nk=nk)
+    return check_module(h, "riem", N, K, f, list(f.keys()), outs, fn, p, rng, tol=1e-10, dot_tol=1e-13, pert_scale=1e-3, out_nk=nk)     # achieved 6.7e-12 (SIM solver) / 1e-15
 
 
 def _run_dzc(emu):
@@ -146,7 +146,7 @@ def _run_dyn_nh(emu, n_split, a_imp=1.0, extra=None):
     outs = dict(u_n=(1, N, 1, npx), v_n=(1, npx, 1, N), pt_n=C, delp_n=C, w_n=C, delz_n=C, mfx=(1, npx, 1, N), cx=(1, npx, -2, N + 3))
     h = handle(N, K, emu, ak, bk)
     p = two_sided_params(cfg); p.update(do_vort_damp=int(cfg["do_vort_damp"]), hydrostatic=0)
-    return check_module(h, "dyn_core_nh", N, K, f, act, outs, fn, p, rng, tol=1e-9, dot_tol=1e-10, pert_scale=1e-3)
+    return check_module(h, "dyn_core_nh", N, K, f, act, outs, fn, p, rng, tol=5e-11, dot_tol=1e-12, pert_scale=1e-3)     # achieved 2.4e-12 / 1e-15 on the B200
 
 
 @pytest.mark.parametrize("mode", [0, 1])

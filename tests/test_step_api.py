@@ -42,7 +42,9 @@ def make(emu, N=12, K=4, n_split=2, k_split=1, nonhydro=False, extra=None):
 def _run(emu, nonhydro=False, extra=None, taylor=True):
     N, K = 12, 4
     h, f, comp, rng, cfg, ak, bk = make(emu, N, K, nonhydro=nonhydro, extra=extra)
-    tol = 2e-9 if nonhydro else 2e-10
+    # achieved on the B200 (profiles/parity_errors.json): 1.5e-12 non-hydrostatic (exp / log of the Riemann solver through n_split
+    # sub-steps), 5e-14 hydrostatic; the bounds are ~20x that
+    tol = 3e-11 if nonhydro else 2e-12
     g = ograd(N)
     # ---- step_nl against the oracle
     h.step_nl(0, 1)
@@ -69,7 +71,7 @@ def _run(emu, nonhydro=False, extra=None, taylor=True):
     lhs = sum((mdx[k] * y[k]).sum() for k in ACT)
     rhs = sum((dx[k] * mty[k]).sum() for k in ACT)
     common.record(dict(dot=abs(lhs - rhs) / max(abs(lhs), abs(rhs))))
-    assert abs(lhs - rhs) <= (1e-10 if nonhydro else 1e-11) * max(abs(lhs), abs(rhs)), (lhs, rhs)
+    assert abs(lhs - rhs) <= (1e-11 if nonhydro else 1e-13) * max(abs(lhs), abs(rhs)), (lhs, rhs)     # achieved 3e-13 / 1e-16
     if not taylor:
         return dict(dot=abs(lhs - rhs) / max(abs(lhs), abs(rhs)))
     # ---- Taylor test:  || N(x + e dx) - N(x) - e M dx || / || e M dx ||  = O(e)
@@ -204,7 +206,7 @@ def _repeat(emu, nonhydro, extra=None):
                 assert np.array_equal(b[k], ref_ad[k]), ("ad", it, k)
     lhs = sum((ref_tl[k] * y[k]).sum() for k in ACT)
     rhs = sum((dx[k] * ref_ad[k]).sum() for k in ACT)
-    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs))
 
 
 def test_step_repeat_emu():
