@@ -1,7 +1,6 @@
 #include "modules.h"
 #include "stages_tp.h"
-#include "fused_tp.h"
-#include "fused_tp_march.h"
+#include "fused_tp_ops.h"
 
 namespace fv3lm {
 
