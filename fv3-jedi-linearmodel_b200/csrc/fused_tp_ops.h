@@ -16,7 +16,7 @@ void run_fused(Program& P, Op& o, int mode, bool full, const Fill& fill) {
   auto go = [&](auto kern) {
     kern.g = g; kern.m = P.dv->m; kern.nk = o.nk_launch;
     fill(kern, tl);
-    launch_tile(kern, g.NX, g.NY, g.ntile * o.nk_launch);
+    launch_tile(kern, g.NX - 1, g.NY - 1, g.ntile * o.nk_launch);   // (the last array column / row lies outside every rectangle of fv_tp_2d)
   };
   if (tl) { if (full) go(K<Dual, true>{}); else go(K<Dual, false>{}); }
   else { if (full) go(K<double, true>{}); else go(K<double, false>{}); }
@@ -41,7 +41,7 @@ inline void add_fused_a(Program& P, const std::string& nm, int q, int cry, int y
       k.aI = adj_in(P.vals[o.out[0]]); k.aO = adj_in(P.vals[o.out[1]]);
       if (!k.aI.v || !k.aO.v) throw std::runtime_error("fused fv_tp_2d: output adjoints missing");
       k.q_ad = adj_out(vq); k.ci_ad = adj_out(vci); k.fi_ad = adj_out(vfi); k.ra_ad = adj_out(vra); k.co_ad = adj_out(vco);
-      launch_tile(k, g.NX, g.NY, g.ntile * o.nk_launch);
+      launch_tile(k, g.NX - 1, g.NY - 1, g.ntile * o.nk_launch);
       return;
     }
     if (march_fwd_a(P, o, mode, full, hord)) return;
@@ -73,7 +73,7 @@ inline void add_fused_b(Program& P, const std::string& nm, int q, int crx, int x
       if (!k.aI.v || !k.aO.v) throw std::runtime_error("fused fv_tp_2d: output adjoints missing");
       k.q_ad = adj_out(vq); k.ci_ad = adj_out(vci); k.fi_ad = adj_out(vfi); k.ra_ad = adj_out(vra); k.co_ad = adj_out(vco);
       k.fin2_ad = adj_out(vfy2); k.fout2_ad = adj_out(vfxo); k.mI_ad = adj_out(vmx); k.mO_ad = adj_out(vmy);
-      launch_tile(k, g.NX, g.NY, g.ntile * o.nk_launch);
+      launch_tile(k, g.NX - 1, g.NY - 1, g.ntile * o.nk_launch);
       return;
     }
     if (march_fwd_b(P, o, mode, full, hord)) return;
