@@ -78,3 +78,31 @@ def test_sim1_solver_tlm_pins_oracle():
     assert np.abs(w2n_tl).max() > 0 and np.abs(dzn_tl).max() > 0
     print('sim1 errs', errs)
     assert max(errs.values()) <= 1e-12, errs      # achieved 1e-13 (exp / log round-off through 72 levels)
+
+
+def test_a2b_ord4_tlm_pins_oracle():
+    """A2B_ORD4_TLM (model_tlmadm/a2b_edge_tlm.F90:546-1158, with EXTRAP_CORNER_TLM :1491) on whole cube tiles: all four corners, all four
+    edges, the interior; the operator is linear, so the oracle's jvp must be the operator applied to the perturbation"""
+    from oracle.a2b_edge import a2b_ord4
+    from ref_tlm.a2b_ord4_tlm import a2b_ord4_tlm
+    N, K = 12, 1
+    rng = np.random.default_rng(23)
+    g = ograd(N)
+    M = metrics(N)
+    q = rnd(rng, N, K, 1.0, 5.0); dq = rnd(rng, N, K, 0.3)
+    fn = lambda a: a2b_ord4(a, g)
+    out_o, dout_o = torch.func.jvp(fn, (torch.from_numpy(q),), (torch.from_numpy(dq),))
+    npx = npy = N + 1
+    worst = 0.0
+    for t in range(6):
+        P = lambda a, i, j: a[t, j + 2, i + 2]                # Fortran (i, j) of a [6, NY, NX(, 2)] metric
+        qout, qout_tl = a2b_ord4_tlm(_fa(q[t, 0], N), _fa(dq[t, 0], N), lambda i, j: P(M["grid"], i, j), lambda i, j: P(M["agrid"], i, j),
+                                     _fa(M["dxa"][t], N), _fa(M["dya"][t], N),
+                                     lambda j: M["edge_w"][t, j + 2], lambda j: M["edge_e"][t, j + 2], lambda i: M["edge_s"][t, i + 2], lambda i: M["edge_n"][t, i + 2],
+                                     npx, npy, 1, N, 1, N, 3)
+        ref = qout.a.T; ref_tl = qout_tl.a.T                   # [j + 2, i + 2]
+        o = region(out_o[t, 0].numpy(), 1, N + 1, 1, N + 1); o_tl = region(dout_o[t, 0].numpy(), 1, N + 1, 1, N + 1)
+        worst = max(worst, relerr(o, region(ref, 1, N + 1, 1, N + 1)), relerr(o_tl, region(ref_tl, 1, N + 1, 1, N + 1)))
+        assert np.abs(region(ref_tl, 1, N + 1, 1, N + 1)).min() > 0        # every corner point of the tile is defined
+    print("a2b_ord4 worst", worst)
+    assert worst <= TOL, worst
