@@ -9,7 +9,8 @@ SRCS="engine.cu comm.cu mosaic.cu modules.cu csw.cu dsw.cu a2b.cu dyn.cu fvdyn.c
 OUT=..
 OBJ=/tmp/fv3lm_obj_$(id -u)
 DEFS=""
-if [ -n "$FV3LM_TILE_TY" ]; then DEFS="-DFV3LM_TILE_TY=$FV3LM_TILE_TY"; fi    # tile height of the shared-memory-tile kernels (csrc/fused_tp.h)
+if [ -n "$FV3LM_TILE_TY" ]; then DEFS="-DFV3LM_TILE_TY=$FV3LM_TILE_TY"; fi
+if [ -n "$FV3LM_TILE_MINBLOCKS" ]; then DEFS="$DEFS -DFV3LM_TILE_MINBLOCKS=$FV3LM_TILE_MINBLOCKS"; fi   # __launch_bounds__ of the tile kernels (A/B runs)    # tile height of the shared-memory-tile kernels (csrc/fused_tp.h)
 mkdir -p $OBJ
 pids=""
 if [ "$1" != "emu" ]; then

@@ -248,7 +248,10 @@ template <class TT, bool FULL> struct KernTpB {
 };
 
 #ifndef FV3LM_HOST_EMU
-template <class K> GLOBAL void __launch_bounds__(NTHR) kern_tile(const __grid_constant__ K k) {
+#ifndef FV3LM_TILE_MINBLOCKS
+#define FV3LM_TILE_MINBLOCKS 5     // 48 registers: five resident blocks instead of four (reverse kernels 1.79 -> 1.58 ms, profiles/r02t_*)
+#endif
+template <class K> GLOBAL void __launch_bounds__(NTHR, FV3LM_TILE_MINBLOCKS) kern_tile(const __grid_constant__ K k) {
   __shared__ typename K::Smem s;
   const int tid = threadIdx.x;
 #pragma unroll
