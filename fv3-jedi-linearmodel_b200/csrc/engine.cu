@@ -215,6 +215,11 @@ void Program::run_op(Op& op, int mode) {
   r.n++; r.ms += ms; r.alg_bytes += b;
 }
 
+// Fraction of the free device memory the adjoint may plan with when it decides how many forward segments to keep.  The plan also sets aside
+// 2 x the largest segment for the segment being reversed, which is far more than the reverse sweep holds at any time (measured pool peak at
+// C180: 113 GB for a plan of 146 GB), so 0.95 keeps one more acoustic segment on a 183 GB B200 (6 of 9) with ~45 GB to spare.
+static const double kAdStoreFraction = 0.95;
+
 // The adjoint can skip the per-segment recomputation (one whole nonlinear sweep) when the complete forward sweep
 // fits in device memory -- the case once the cube is sharded over several GPUs.
 bool Program::ad_fits_store_all() {
@@ -226,7 +231,7 @@ bool Program::ad_fits_store_all() {
   }
   double budget = dv->ad_store_budget;
   if (const char* e = getenv("FV3LM_AD_STORE_BUDGET")) budget = atof(e);   // tests force either path
-  if (budget < 0.0) budget = 0.85 * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
+  if (budget < 0.0) budget = kAdStoreFraction * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
   if (dv->comm) budget = dv->comm->min_over_ranks(budget);     // every rank must take the same path (same exchange sequence)
   ad_store_all_cached = (need <= budget) ? 1 : 0;
   return ad_store_all_cached != 0;
@@ -280,7 +285,7 @@ void Program::run_sweeps(Mode mode) {
       double largest = 0.0; for (double b : seg_bytes) largest = std::max(largest, b);
       double budget = dv->ad_store_budget;
       if (const char* e = getenv("FV3LM_AD_STORE_BUDGET")) budget = atof(e);
-      if (budget < 0.0) budget = 0.85 * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
+      if (budget < 0.0) budget = kAdStoreFraction * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
       if (dv->comm) budget = dv->comm->min_over_ranks(budget);   // same decision on every rank
       budget -= 2.0 * largest;                      // a segment being reversed holds trajectory + adjoints, plus the boundary values
       ad_keep_from = nseg - 1;                      // the last segment is always kept
