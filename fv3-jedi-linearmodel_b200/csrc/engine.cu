@@ -216,8 +216,7 @@ void Program::run_op(Op& op, int mode) {
 }
 
 // Fraction of the free device memory the adjoint may plan with when it decides how many forward segments to keep.  The plan also sets aside
-// 2 x the largest segment for the segment being reversed, which is far more than the reverse sweep holds at any time (measured pool peak at
-// C180: 113 GB for a plan of 146 GB), so 0.95 keeps one more acoustic segment on a 183 GB B200 (6 of 9) with ~45 GB to spare.
+// the largest segment for the segment being reversed (see below); at C180 on one 183 GB B200 that keeps 7 of 9 acoustic segments.
 static const double kAdStoreFraction = 0.95;
 
 // The adjoint can skip the per-segment recomputation (one whole nonlinear sweep) when the complete forward sweep
@@ -287,7 +286,10 @@ void Program::run_sweeps(Mode mode) {
       if (const char* e = getenv("FV3LM_AD_STORE_BUDGET")) budget = atof(e);
       if (budget < 0.0) budget = kAdStoreFraction * (dev::free_bytes() + (double)(dv->pool.bytes_total - dv->pool.bytes_live));
       if (dv->comm) budget = dv->comm->min_over_ranks(budget);   // same decision on every rank
-      budget -= 2.0 * largest;                      // a segment being reversed holds trajectory + adjoints, plus the boundary values
+      // reserve for the segment being reversed.  Its adjoints are allocated and released op by op and a recomputed segment reuses what the
+      // already reversed ones gave back: measured 6.5 - 7.7 GB beyond the kept segments at C180 (segments of 20.5 GB; pool peak 113 / 132 GB with
+      // 5 / 6 acoustic segments kept, profiles/r02i, r02v), so one whole segment is a 2.7x margin (it used to be two)
+      budget -= 1.0 * largest;
       ad_keep_from = nseg - 1;                      // the last segment is always kept
       const double budget0 = budget;
       while (ad_keep_from > 0 && seg_bytes[ad_keep_from - 1] <= budget) { budget -= seg_bytes[ad_keep_from - 1]; ad_keep_from--; }
