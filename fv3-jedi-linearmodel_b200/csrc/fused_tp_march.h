@@ -232,7 +232,8 @@ template <class K> void launch_march(const K& k, int nx, int ny, int nz) {
 #endif
 
 inline bool march_enabled(int nx) {
-  static const int on = getenv("FV3LM_TP_MARCH") ? atoi(getenv("FV3LM_TP_MARCH")) : 0;   // opt-in: measured slower than the tile kernels (profiles/r02k_*)
+  const char* e = getenv("FV3LM_TP_MARCH");          // read per call (a host-side branch per op): tests switch it
+  const int on = e ? atoi(e) : 0;   // opt-in: measured slower than the tile kernels (profiles/r02k_*)
   return on != 0 && nx <= MARCH_MAXT;
 }
 

@@ -1,5 +1,6 @@
-"""(named zz: runs last -- the kernels have not been on a B200 yet and must not mask the rest of the suite under -x)
-fv_tp_2d as two shared-memory-tile kernels (csrc/fused_tp.h, FV3LM_FUSED_TP=1): forward sweeps (NL, TL) must reproduce the
+"""Routine-level kernels (default since round 2; the file keeps its round-1 name, it used to run last because the kernels had not been on a
+B200 yet): fv_tp_2d as shared-memory-tile kernels (csrc/fused_tp.h), the row-marching variant, a2b_ord4 as tile kernel and as compiled operator,
+automatically fused stage chains.  Forward sweeps (NL, TL) of the tile kernels (FV3LM_FUSED_TP=1) must reproduce the
 stage-by-stage chain of model_tlmadm/tp_core_tlm.F90:2123-2324 -- same arithmetic, so the comparison is to round-off -- and the
 adjoint (which keeps the chain) must stay the transpose of the fused tangent."""
 import numpy as np
@@ -181,6 +182,32 @@ def test_fused_vs_chain_trajectory_schemes_gpu(monkeypatch):
 @pytest.mark.gpu
 def test_fused_step_gpu(fused):
     print(test_step_api._run(False, nonhydro=True))
+
+
+# ---- row-marching forward kernels (csrc/fused_tp_march.h, FV3LM_TP_MARCH=1: opt-in, measured slower than the tile kernels) ----
+@pytest.fixture
+def marching(monkeypatch):
+    common._handles.clear()
+    monkeypatch.setenv("FV3LM_FUSED_TP", "2")
+    monkeypatch.setenv("FV3LM_TP_MARCH", "1")
+    yield
+    common._handles.clear()
+
+
+@pytest.mark.parametrize("hord", [1, 2, 333])
+def test_march_vs_oracle_emu(marching, hord):
+    test_tp_core._run(True, hord)
+
+
+def test_march_vs_chain_emu(monkeypatch):
+    """NL and TL of the marching kernels against the stage chain (N = 40: two row chunks of 24, both cube edges)"""
+    monkeypatch.setenv("FV3LM_TP_MARCH", "1")
+    _fused_vs_chain(True, monkeypatch, 40, 2, dict(hord=2))
+    _fused_vs_chain(True, monkeypatch, 40, 2, dict(hord=2, use_mf=1, n_sponge=1))
+
+
+def test_march_step_emu(marching):
+    print(test_step_api._run(True, nonhydro=True))
 
 
 # ---- a2b_ord4 as one tile kernel per direction (FV3LM_FUSED_A2B=1, csrc/a2b.cu: KernA2b / KernA2bRev) ----------------------
