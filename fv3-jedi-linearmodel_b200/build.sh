@@ -5,7 +5,7 @@
 # usage: build.sh [cuda|emu]   (default: both).  Objects are compiled in parallel.
 set -e
 cd "$(dirname "$0")/csrc"
-SRCS="engine.cu comm.cu mosaic.cu modules.cu csw.cu dsw.cu a2b.cu dyn.cu fvdyn.cu nh.cu capi.cu step_api.cu turb.cu"
+SRCS="engine.cu comm.cu mosaic.cu modules.cu tp_fwd.cu tp_rev.cu tp_march.cu csw.cu dsw.cu a2b.cu dyn.cu fvdyn.cu nh.cu capi.cu step_api.cu turb.cu"
 OUT=..
 OBJ=/tmp/fv3lm_obj_$(id -u)
 DEFS=""

@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/csrc"
 MODE=$1; shift
-SRCS="engine.cu comm.cu mosaic.cu modules.cu csw.cu dsw.cu a2b.cu dyn.cu fvdyn.cu nh.cu capi.cu step_api.cu turb.cu"
+SRCS="engine.cu comm.cu mosaic.cu modules.cu tp_fwd.cu tp_rev.cu tp_march.cu csw.cu dsw.cu a2b.cu dyn.cu fvdyn.cu nh.cu capi.cu step_api.cu turb.cu"
 OBJ=/tmp/fv3lm_obj_$(id -u)
 DEFS=""
 if [ -n "$FV3LM_TILE_TY" ]; then DEFS="-DFV3LM_TILE_TY=$FV3LM_TILE_TY"; fi

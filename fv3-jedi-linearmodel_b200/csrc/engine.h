@@ -387,22 +387,21 @@ inline int stage_kpt() { static const int k = getenv("FV3LM_KPT") ? std::max(1, 
 // an integer and z < 2^16, so the rounding error of the product (< 1e-5) cannot change the truncation -- exact, 3 instructions
 // instead of the ~20 of an integer division by a run-time divisor.
 DEV int fast_div_small(int z, float inv) { return (int)(((float)z + 0.5f) * inv); }
-template <class F> GLOBAL void kern_stage(const __grid_constant__ F f, int nx, int ny, int nk, int nkc, float inv_nkc, int kpt) {
-  int ii = blockIdx.x * blockDim.x + threadIdx.x;
-  int jj = blockIdx.y * blockDim.y + threadIdx.y;
-  if (ii >= nx || jj >= ny) return;
-  const int tile = fast_div_small(blockIdx.z, inv_nkc), k0 = (blockIdx.z - tile * nkc) * kpt;
-  const int k1 = k0 + kpt < nk ? k0 + kpt : nk;
-  if (kpt == 1) f(ii, jj, k0, tile);
-  else f.run(ii, jj, k0, k1, tile);
-}
-// the same with the cells of a level packed onto consecutive threads (a warp may straddle two rows): on small sub-domains a 32 x 8 block
+// ncell > 0: the cells of a level are packed onto consecutive threads (a warp may straddle two rows): on small sub-domains a 32 x 8 block
 // grid wastes lanes (97-cell rows of C180 on 8 GPUs fill 3 1/32 blocks: 76 % lane efficiency), the packed form none.  The row comes from
-// the same exact float quotient as the level (cells per level < 2^16).
-template <class F> GLOBAL void kern_stage_packed(const __grid_constant__ F f, int nx, int ncell, float inv_nx, int nk, int nkc, float inv_nkc, int kpt) {
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= ncell) return;
-  const int jj = fast_div_small(id, inv_nx), ii = id - jj * nx;
+// the same exact float quotient as the level (cells per level < 2^16).  One kernel serves both mappings (a second instantiation of every
+// stage kernel doubled the build time).
+template <class F> GLOBAL void kern_stage(const __grid_constant__ F f, int nx, int ny, int nk, int nkc, float inv_nkc, int kpt, int ncell, float inv_nx) {
+  int ii, jj;
+  if (ncell > 0) {
+    const int id = blockIdx.x * 256 + threadIdx.y * 32 + threadIdx.x;
+    if (id >= ncell) return;
+    jj = fast_div_small(id, inv_nx); ii = id - jj * nx;
+  } else {
+    ii = blockIdx.x * blockDim.x + threadIdx.x;
+    jj = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ii >= nx || jj >= ny) return;
+  }
   const int tile = fast_div_small(blockIdx.z, inv_nkc), k0 = (blockIdx.z - tile * nkc) * kpt;
   const int k1 = k0 + kpt < nk ? k0 + kpt : nk;
   if (kpt == 1) f(ii, jj, k0, tile);
@@ -414,13 +413,9 @@ template <class F> void launch_stage(const F& f, int nx, int ny, int ntile, int 
   const int padded = ((nx + 31) / 32 * 32) * ((ny + 7) / 8 * 8), ncell = nx * ny;
   static const int packed_mode = getenv("FV3LM_PACKED") ? atoi(getenv("FV3LM_PACKED")) : -1;     // -1: automatic, 0 / 1: forced (A/B runs)
   const bool packed = ncell < 65536 && (packed_mode == 1 || (packed_mode == -1 && ncell * 100 < padded * 92));
-  if (packed) {
-    dim3 b(256, 1, 1), gr((ncell + 255) / 256, 1, ntile * nkc);
-    kern_stage_packed<F><<<gr, b, 0, dev::stream()>>>(f, nx, ncell, 1.0f / (float)nx, nk, nkc, 1.0f / (float)nkc, kpt);
-  } else {
-    dim3 b(32, 8, 1), gr((nx + 31) / 32, (ny + 7) / 8, ntile * nkc);
-    kern_stage<F><<<gr, b, 0, dev::stream()>>>(f, nx, ny, nk, nkc, 1.0f / (float)nkc, kpt);
-  }
+  dim3 b(32, 8, 1), gr((nx + 31) / 32, (ny + 7) / 8, ntile * nkc);
+  if (packed) gr = dim3((ncell + 255) / 256, 1, ntile * nkc);
+  kern_stage<F><<<gr, b, 0, dev::stream()>>>(f, nx, ny, nk, nkc, 1.0f / (float)nkc, kpt, packed ? ncell : 0, 1.0f / (float)nx);
   dev::launches++;
 }
 #else
