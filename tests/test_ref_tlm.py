@@ -106,3 +106,56 @@ def test_a2b_ord4_tlm_pins_oracle():
         assert np.abs(region(ref_tl, 1, N + 1, 1, N + 1)).min() > 0        # every corner point of the tile is defined
     print("a2b_ord4 worst", worst)
     assert worst <= TOL, worst
+
+
+@pytest.mark.parametrize("case", ["plain_ord2", "plain_ord333", "plain_ord1", "damp_nord2", "damp_nord0", "mass_flux", "mass_flux_damp_nord1"])
+def test_fv_tp_2d_tlm_pins_oracle(case):
+    """FV_TP_2D_TLM with YPPM_TLM, COPY_CORNERS_TLM and DELN_FLUX_TLM (model_tlmadm/tp_core_tlm.F90:2123-2924) on two whole cube tiles:
+    the inner / outer sweeps, the corner copies between them, the flux averaging with either mass-flux convention and both del-n
+    branches (damp * q without mass, mass-weighted with it)."""
+    from ref_tlm.fv_tp_2d_tlm import fv_tp_2d_tlm, BD
+    N, K = 12, 1
+    rng = np.random.default_rng(23)
+    M = metrics(N); g = ograd(N)
+    hord = dict(plain_ord333=333, plain_ord1=1).get(case, 2)
+    mf = case.startswith("mass_flux")
+    nord, damp_c = dict(damp_nord2=(2, 0.06), damp_nord0=(0, 0.12), mass_flux_damp_nord1=(1, 0.05)).get(case, (None, None))
+    area = M["area"][:, None]
+    names = ["q", "crx", "cry", "xfx", "yfx", "ra_x", "ra_y"] + (["mfx", "mfy", "mass"] if mf else [])
+    v = dict(q=rnd(rng, N, K, 1.0, 10.0), crx=rnd(rng, N, K, 0.4), cry=rnd(rng, N, K, 0.4),
+             xfx=area * rnd(rng, N, K, 0.3), yfx=area * rnd(rng, N, K, 0.3),
+             ra_x=area * (1.0 + 0.1 * rnd(rng, N, K)), ra_y=area * (1.0 + 0.1 * rnd(rng, N, K)),
+             mfx=area * rnd(rng, N, K, 30.0), mfy=area * rnd(rng, N, K, 30.0), mass=rnd(rng, N, K, 5.0, 100.0))
+    d = {n: 1e-2 * np.abs(v[n]).mean() * rnd(rng, N, K) for n in names}
+
+    def fn(*a):
+        kw = dict(zip(names, a))
+        fx, fy, _ = otp.fv_tp_2d_damp(kw["q"], kw["crx"], kw["cry"], hord, kw["xfx"], kw["yfx"], g, kw["ra_x"], kw["ra_y"],
+                                      kw.get("mfx"), kw.get("mfy"), kw.get("mass"),
+                                      None if nord is None else [nord] * K, None if nord is None else [damp_c] * K)
+        return fx, fy
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    (fx_o, fy_o), (dfx_o, dfy_o) = torch.func.jvp(fn, tuple(T(v[n]) for n in names), tuple(T(d[n]) for n in names))
+    bd = BD(N)
+    worst = {}
+    for t in (0, 4):
+        gs = {k: _fa(M[k][t], N) for k in ("area", "rarea", "dxa", "dya", "del6_u", "del6_v")}
+        gs["da_min"] = M["da_min"]
+        a = {n: _fa(v[n][t, 0], N) for n in names}
+        a_tl = {n: _fa(d[n][t, 0], N) for n in names}
+        opt = {}
+        if mf:
+            opt = dict(mfx=a["mfx"], mfx_tl=a_tl["mfx"], mfy=a["mfy"], mfy_tl=a_tl["mfy"])
+            if nord is not None:
+                opt.update(mass=a["mass"], mass_tl=a_tl["mass"])
+        if nord is not None:
+            opt.update(nord=nord, damp_c=damp_c)
+        fx, fx_tl, fy, fy_tl = fv_tp_2d_tlm(a["q"], a_tl["q"], a["crx"], a_tl["crx"], a["cry"], a_tl["cry"], N + 1, N + 1, hord,
+                                            a["xfx"], a_tl["xfx"], a["yfx"], a_tl["yfx"], gs, bd, a["ra_x"], a_tl["ra_x"],
+                                            a["ra_y"], a_tl["ra_y"], **opt)
+        for nm, ref, o, rg in (("fx", fx, fx_o, (1, N + 1, 1, N)), ("fx_tl", fx_tl, dfx_o, (1, N + 1, 1, N)),
+                               ("fy", fy, fy_o, (1, N, 1, N + 1)), ("fy_tl", fy_tl, dfy_o, (1, N, 1, N + 1))):
+            assert np.abs(ref.a).max() > 0
+            worst[nm] = max(worst.get(nm, 0.0), relerr(region(o[t, 0].numpy(), *rg), ref.a.T))
+    print("fv_tp_2d", case, worst)
+    assert max(worst.values()) <= TOL, worst
