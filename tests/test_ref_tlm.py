@@ -159,3 +159,28 @@ def test_fv_tp_2d_tlm_pins_oracle(case):
             worst[nm] = max(worst.get(nm, 0.0), relerr(region(o[t, 0].numpy(), *rg), ref.a.T))
     print("fv_tp_2d", case, worst)
     assert max(worst.values()) <= TOL, worst
+
+
+@pytest.mark.parametrize("iord", [1, 2, 333])
+def test_xtp_u_ytp_v_tlm_pin_oracle(iord):
+    """XTP_U_TLM / YTP_V_TLM (model_tlmadm/sw_core_tlm.F90:7272-7757) on two whole cube tiles: the momentum transport of d_sw with its
+    cube-edge one-sided values and the zeroed corner rows (j = 1, npy for u; i = 1, npx for v)."""
+    from oracle import d_sw as odsw
+    from ref_tlm.xtp_ytp_tlm import xtp_u_tlm, ytp_v_tlm
+    N, K = 12, 1
+    rng = np.random.default_rng(31)
+    M = metrics(N); g = ograd(N)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    worst = {}
+    for nm, fn_o, fn_r, dn, rdn in (("xtp_u", odsw.xtp_u, xtp_u_tlm, "dx", "rdx"), ("ytp_v", odsw.ytp_v, ytp_v_tlm, "dy", "rdy")):
+        w = rnd(rng, N, K, 5.0, 10.0); c = M[dn][:, None] * rnd(rng, N, K, 0.4)
+        dw = rnd(rng, N, K, 0.1); dc = M[dn][:, None] * rnd(rng, N, K, 0.01)
+        f_o, df_o = torch.func.jvp(lambda c_, w_: fn_o(c_, w_, g, iord), (T(c), T(w)), (T(dc), T(dw)))
+        for t in (1, 5):
+            flux, flux_tl = fn_r(1, N, 1, N, -2, N + 3, -2, N + 3, _fa(c[t, 0], N), _fa(dc[t, 0], N), _fa(w[t, 0], N), _fa(dw[t, 0], N), iord,
+                                 _fa(M[dn][t], N), _fa(M[rdn][t], N), N + 1, N + 1)
+            assert np.abs(flux_tl.a).max() > 0
+            worst[nm] = max(worst.get(nm, 0.0), relerr(region(f_o[t, 0].numpy(), 1, N + 1, 1, N + 1), flux.a.T))
+            worst[nm + "_tl"] = max(worst.get(nm + "_tl", 0.0), relerr(region(df_o[t, 0].numpy(), 1, N + 1, 1, N + 1), flux_tl.a.T))
+    print("xtp/ytp", iord, worst)
+    assert max(worst.values()) <= TOL, worst
