@@ -184,3 +184,53 @@ def test_xtp_u_ytp_v_tlm_pin_oracle(iord):
             worst[nm + "_tl"] = max(worst.get(nm + "_tl", 0.0), relerr(region(df_o[t, 0].numpy(), 1, N + 1, 1, N + 1), flux_tl.a.T))
     print("xtp/ytp", iord, worst)
     assert max(worst.values()) <= TOL, worst
+
+
+def _fa3(a3d, N):
+    """[K, NY, NX] -> F((isd, ied + 1), (jsd, jed + 1), (1, K)) indexed (i, j, k)"""
+    return F((-2, N + 4), (-2, N + 4), (1, a3d.shape[0]), data=np.ascontiguousarray(a3d.transpose(2, 1, 0)))
+
+
+def test_update_dz_d_tlm_pins_oracle():
+    """UPDATE_DZ_D_TLM (model_tlmadm/nh_utils_tlm.F90:381-588) with EDGE_PROFILE_TLM (:3319-3472) and DEL6_VT_FLUX_TLM
+    (sw_core_tlm.F90:3621-3728) on one whole cube tile: interface Courant numbers / fluxes, transport of the interface heights with and
+    without del-n damping, the surface vertical velocity and the minimum-thickness limiter (a thin layer makes it active)."""
+    from oracle import nh as onh
+    from ref_tlm.update_dz_tlm import update_dz_d_tlm
+    from ref_tlm.fv_tp_2d_tlm import BD
+    N, K = 12, 5
+    rng = np.random.default_rng(41)
+    M = metrics(N); g = ograd(N)
+    area = M["area"][:, None]
+    dp0 = np.array([300., 700., 1500., 2500., 3000.])
+    ndif = [2, 1, 0, 0, 0]; dampc = [0.06, 0.05, 0.04, 0.0, 0.0]
+    damp = [(d * M["da_min"]) ** (n + 1) if d > 0 else 0.0 for n, d in zip(ndif, dampc)]
+    hord, rdt = 2, 1. / 30.
+    NX = N + 7
+    zs = 100.0 * rng.standard_normal((6, 1, NX, NX))
+    thick = np.array([900., 800., 1.0, 600., 500., 0.0])[::-1].cumsum()[::-1]          # layer 3 is 1 m thick: limiter active there
+    zh = zs + thick.reshape(1, K + 1, 1, 1) + 1.5 * rng.standard_normal((6, K + 1, NX, NX))
+    v = dict(zh=zh, crx=rnd(rng, N, K, 0.3), cry=rnd(rng, N, K, 0.3), xfx=area * rnd(rng, N, K, 0.2), yfx=area * rnd(rng, N, K, 0.2))
+    names = list(v)
+    d = {n: 1e-2 * max(np.abs(v[n]).std(), 1e-30) * rng.standard_normal(v[n].shape) for n in names}
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    def fn(zh_, crx_, cry_, xfx_, yfx_):
+        return onh.update_dz_d(ndif, damp, hord, dp0, T(zs), zh_, crx_, cry_, xfx_, yfx_, g, rdt)
+    (zh_o, ws_o), (dzh_o, dws_o) = torch.func.jvp(fn, tuple(T(v[n]) for n in names), tuple(T(d[n]) for n in names))
+    t = 2
+    gs = {k: _fa(M[k][t], N) for k in ("area", "rarea", "dxa", "dya", "del6_u", "del6_v")}
+    gs["da_min"] = M["da_min"]
+    a = {n: _fa3(v[n][t], N) for n in names}; a_tl = {n: _fa3(d[n][t], N) for n in names}
+    ws, ws_tl = update_dz_d_tlm(ndif + [0], damp + [0.0], hord, 1, N, 1, N, K, 3, N + 1, N + 1, F((1, K), data=dp0), _fa(zs[t, 0], N),
+                                a["zh"], a_tl["zh"], a["crx"], a_tl["crx"], a["cry"], a_tl["cry"], a["xfx"], a_tl["xfx"],
+                                a["yfx"], a_tl["yfx"], rdt, gs, BD(N))
+    own = lambda x: region(x, 1, N, 1, N)
+    ref_zh = a["zh"].a.transpose(2, 1, 0); ref_zh_tl = a_tl["zh"].a.transpose(2, 1, 0)
+    limited = (own(ref_zh)[:-1] - own(ref_zh)[1:] == 2.0).mean()
+    assert 0.05 < limited < 0.5, limited                # the dz_min branch is exercised, and not everywhere
+    errs = dict(zh=relerr(own(zh_o[t].numpy()), own(ref_zh)), zh_tl=relerr(own(dzh_o[t].numpy()), own(ref_zh_tl)),
+                ws=relerr(own(ws_o[t, 0].numpy()), ws.a.T), ws_tl=relerr(own(dws_o[t, 0].numpy()), ws_tl.a.T))
+    print("update_dz_d", errs, "limited", limited)
+    assert np.abs(ws_tl.a).max() > 0
+    assert max(errs.values()) <= TOL, errs
