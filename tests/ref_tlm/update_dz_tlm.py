@@ -138,3 +138,113 @@ def update_dz_d_tlm(ndif, damp, hord, is_, ie, js, je, km, ng, npx, npy, dp0, zs
                     zh_tl[i, j, k] = zh_tl[i, j, k + 1]
                     zh[i, j, k] = zh[i, j, k + 1] + dz_min
     return ws, ws_tl
+
+
+def fill_4corners_tlm(q, q_tl, dir_, npx, npy):
+    """FILL_4CORNERS_TLM, model_tlmadm/sw_core_tlm.F90:7138-7211, all four corners present"""
+    if dir_ == 1:
+        q_tl[-1, 0] = q_tl[0, 2]; q[-1, 0] = q[0, 2]
+        q_tl[0, 0] = q_tl[0, 1]; q[0, 0] = q[0, 1]
+        q_tl[npx + 1, 0] = q_tl[npx, 2]; q[npx + 1, 0] = q[npx, 2]
+        q_tl[npx, 0] = q_tl[npx, 1]; q[npx, 0] = q[npx, 1]
+        q_tl[0, npy] = q_tl[0, npy - 1]; q[0, npy] = q[0, npy - 1]
+        q_tl[-1, npy] = q_tl[0, npy - 2]; q[-1, npy] = q[0, npy - 2]
+        q_tl[npx, npy] = q_tl[npx, npy - 1]; q[npx, npy] = q[npx, npy - 1]
+        q_tl[npx + 1, npy] = q_tl[npx, npy - 2]; q[npx + 1, npy] = q[npx, npy - 2]
+    elif dir_ == 2:
+        q_tl[0, 0] = q_tl[1, 0]; q[0, 0] = q[1, 0]
+        q_tl[0, -1] = q_tl[2, 0]; q[0, -1] = q[2, 0]
+        q_tl[npx, 0] = q_tl[npx - 1, 0]; q[npx, 0] = q[npx - 1, 0]
+        q_tl[npx, -1] = q_tl[npx - 2, 0]; q[npx, -1] = q[npx - 2, 0]
+        q_tl[0, npy] = q_tl[1, npy]; q[0, npy] = q[1, npy]
+        q_tl[0, npy + 1] = q_tl[2, npy]; q[0, npy + 1] = q[2, npy]
+        q_tl[npx, npy] = q_tl[npx - 1, npy]; q[npx, npy] = q[npx - 1, npy]
+        q_tl[npx, npy + 1] = q_tl[npx - 2, npy]; q[npx, npy + 1] = q[npx - 2, npy]
+
+
+def update_dz_c_tlm(is_, ie, js, je, km, ng, dt, dp0, zs, area, ut, ut_tl, vt, vt_tl, gz, gz_tl, npx, npy):
+    """UPDATE_DZ_C_TLM, model_tlmadm/nh_utils_tlm.F90:51-233.  gz, gz_tl: F((isd,ied),(jsd,jed),(1,km+1)) updated in place on
+    (is-1:ie+1, js-1:je+1); returns ws, ws_tl F((isd,ied),(jsd,jed))."""
+    isd = is_ - ng; ied = ie + ng; jsd = js - ng; jed = je + ng
+    ws = F((isd, ied), (jsd, jed)); ws_tl = F((isd, ied), (jsd, jed))
+    gz2 = F((isd, ied), (jsd, jed)); gz2_tl = F((isd, ied), (jsd, jed))
+    xfx = F((is_ - 1, ie + 2), (js - 1, je + 1)); fx = F((is_ - 1, ie + 2), (js - 1, je + 1))
+    xfx_tl = F((is_ - 1, ie + 2), (js - 1, je + 1)); fx_tl = F((is_ - 1, ie + 2), (js - 1, je + 1))
+    yfx = F((is_ - 1, ie + 1), (js - 1, je + 2)); fy = F((is_ - 1, ie + 1), (js - 1, je + 2))
+    yfx_tl = F((is_ - 1, ie + 1), (js - 1, je + 2)); fy_tl = F((is_ - 1, ie + 1), (js - 1, je + 2))
+    rdt = 1. / dt
+    top_ratio = dp0[1] / (dp0[1] + dp0[2])
+    bot_ratio = dp0[km] / (dp0[km - 1] + dp0[km])
+    is1 = is_ - 1; js1 = js - 1; ie1 = ie + 1; je1 = je + 1; ie2 = ie + 2; je2 = je + 2
+    for k in range(1, km + 2):
+        if k == 1:
+            for j in range(js1, je1 + 1):
+                for i in range(is1, ie2 + 1):
+                    xfx_tl[i, j] = ut_tl[i, j, 1] + top_ratio * (ut_tl[i, j, 1] - ut_tl[i, j, 2])
+                    xfx[i, j] = ut[i, j, 1] + (ut[i, j, 1] - ut[i, j, 2]) * top_ratio
+            for j in range(js1, je2 + 1):
+                for i in range(is1, ie1 + 1):
+                    yfx_tl[i, j] = vt_tl[i, j, 1] + top_ratio * (vt_tl[i, j, 1] - vt_tl[i, j, 2])
+                    yfx[i, j] = vt[i, j, 1] + (vt[i, j, 1] - vt[i, j, 2]) * top_ratio
+        elif k == km + 1:
+            for j in range(js1, je1 + 1):
+                for i in range(is1, ie2 + 1):
+                    xfx_tl[i, j] = ut_tl[i, j, km] + bot_ratio * (ut_tl[i, j, km] - ut_tl[i, j, km - 1])
+                    xfx[i, j] = ut[i, j, km] + (ut[i, j, km] - ut[i, j, km - 1]) * bot_ratio
+            for j in range(js1, je2 + 1):
+                for i in range(is1, ie1 + 1):
+                    yfx_tl[i, j] = vt_tl[i, j, km] + bot_ratio * (vt_tl[i, j, km] - vt_tl[i, j, km - 1])
+                    yfx[i, j] = vt[i, j, km] + (vt[i, j, km] - vt[i, j, km - 1]) * bot_ratio
+        else:
+            int_ratio = 1. / (dp0[k - 1] + dp0[k])
+            for j in range(js1, je1 + 1):
+                for i in range(is1, ie2 + 1):
+                    xfx_tl[i, j] = int_ratio * (dp0[k] * ut_tl[i, j, k - 1] + dp0[k - 1] * ut_tl[i, j, k])
+                    xfx[i, j] = (dp0[k] * ut[i, j, k - 1] + dp0[k - 1] * ut[i, j, k]) * int_ratio
+            for j in range(js1, je2 + 1):
+                for i in range(is1, ie1 + 1):
+                    yfx_tl[i, j] = int_ratio * (dp0[k] * vt_tl[i, j, k - 1] + dp0[k - 1] * vt_tl[i, j, k])
+                    yfx[i, j] = (dp0[k] * vt[i, j, k - 1] + dp0[k - 1] * vt[i, j, k]) * int_ratio
+        for j in range(js - ng, je + ng + 1):
+            for i in range(is_ - ng, ie + ng + 1):
+                gz2_tl[i, j] = gz_tl[i, j, k]
+                gz2[i, j] = gz[i, j, k]
+        fill_4corners_tlm(gz2, gz2_tl, 1, npx, npy)
+        for j in range(js1, je1 + 1):
+            for i in range(is1, ie2 + 1):
+                if xfx[i, j] > 0.:
+                    fx_tl[i, j] = gz2_tl[i - 1, j]
+                    fx[i, j] = gz2[i - 1, j]
+                else:
+                    fx_tl[i, j] = gz2_tl[i, j]
+                    fx[i, j] = gz2[i, j]
+                fx_tl[i, j] = xfx_tl[i, j] * fx[i, j] + xfx[i, j] * fx_tl[i, j]
+                fx[i, j] = xfx[i, j] * fx[i, j]
+        fill_4corners_tlm(gz2, gz2_tl, 2, npx, npy)
+        for j in range(js1, je2 + 1):
+            for i in range(is1, ie1 + 1):
+                if yfx[i, j] > 0.:
+                    fy_tl[i, j] = gz2_tl[i, j - 1]
+                    fy[i, j] = gz2[i, j - 1]
+                else:
+                    fy_tl[i, j] = gz2_tl[i, j]
+                    fy[i, j] = gz2[i, j]
+                fy_tl[i, j] = yfx_tl[i, j] * fy[i, j] + yfx[i, j] * fy_tl[i, j]
+                fy[i, j] = yfx[i, j] * fy[i, j]
+        for j in range(js1, je1 + 1):
+            for i in range(is1, ie1 + 1):
+                den = area[i, j] + (xfx[i, j] - xfx[i + 1, j]) + (yfx[i, j] - yfx[i, j + 1])
+                gz_tl[i, j, k] = (((area[i, j] * gz2_tl[i, j] + fx_tl[i, j] - fx_tl[i + 1, j] + fy_tl[i, j] - fy_tl[i, j + 1]) * den
+                                   - (gz2[i, j] * area[i, j] + (fx[i, j] - fx[i + 1, j]) + (fy[i, j] - fy[i, j + 1]))
+                                   * (xfx_tl[i, j] - xfx_tl[i + 1, j] + yfx_tl[i, j] - yfx_tl[i, j + 1])) / den ** 2)
+                gz[i, j, k] = (gz2[i, j] * area[i, j] + (fx[i, j] - fx[i + 1, j]) + (fy[i, j] - fy[i, j + 1])) / den
+    for j in range(js1, je1 + 1):
+        for i in range(is1, ie1 + 1):
+            ws_tl[i, j] = -(rdt * gz_tl[i, j, km + 1])
+            ws[i, j] = (zs[i, j] - gz[i, j, km + 1]) * rdt
+        for k in range(km, 0, -1):
+            for i in range(is1, ie1 + 1):
+                if gz[i, j, k] < gz[i, j, k + 1] + dz_min:
+                    gz_tl[i, j, k] = gz_tl[i, j, k + 1]
+                    gz[i, j, k] = gz[i, j, k + 1] + dz_min
+    return ws, ws_tl

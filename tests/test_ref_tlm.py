@@ -234,3 +234,40 @@ def test_update_dz_d_tlm_pins_oracle():
     print("update_dz_d", errs, "limited", limited)
     assert np.abs(ws_tl.a).max() > 0
     assert max(errs.values()) <= TOL, errs
+
+
+def test_update_dz_c_tlm_pins_oracle():
+    """UPDATE_DZ_C_TLM (model_tlmadm/nh_utils_tlm.F90:51-233) with FILL_4CORNERS_TLM (sw_core_tlm.F90:7138-7211) on two whole cube tiles:
+    interface fluxes from the layer winds, first-order upwind transport of the heights over (0:npx, 0:npy) and the dz_min limiter."""
+    from oracle import nh as onh
+    from ref_tlm.update_dz_tlm import update_dz_c_tlm
+    N, K = 12, 5
+    rng = np.random.default_rng(43)
+    M = metrics(N); g = ograd(N)
+    area = M["area"][:, None]
+    dp0 = np.array([300., 700., 1500., 2500., 3000.])
+    dt = 15.0
+    NX = N + 7
+    zs = 100.0 * rng.standard_normal((6, 1, NX, NX))
+    thick = np.array([900., 800., 1.0, 600., 500., 0.0])[::-1].cumsum()[::-1]
+    gz = zs + thick.reshape(1, K + 1, 1, 1) + 1.5 * rng.standard_normal((6, K + 1, NX, NX))
+    v = dict(ut=area * rnd(rng, N, K, 0.2), vt=area * rnd(rng, N, K, 0.2), gz=gz)
+    names = list(v)
+    d = {n: 1e-2 * np.abs(v[n]).std() * rng.standard_normal(v[n].shape) for n in names}
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    (gz_o, ws_o), (dgz_o, dws_o) = torch.func.jvp(lambda ut_, vt_, gz_: onh.update_dz_c(dt, dp0, T(zs), ut_, vt_, gz_, g),
+                                                  tuple(T(v[n]) for n in names), tuple(T(d[n]) for n in names))
+    errs = {}
+    for t in (0, 3):
+        a = {n: _fa3(v[n][t], N) for n in names}; a_tl = {n: _fa3(d[n][t], N) for n in names}
+        ws, ws_tl = update_dz_c_tlm(1, N, 1, N, K, 3, dt, F((1, K), data=dp0), _fa(zs[t, 0], N), _fa(M["area"][t], N),
+                                    a["ut"], a_tl["ut"], a["vt"], a_tl["vt"], a["gz"], a_tl["gz"], N + 1, N + 1)
+        ext = lambda x: region(x, 0, N + 1, 0, N + 1)
+        ref = dict(gz=a["gz"].a.transpose(2, 1, 0), gz_tl=a_tl["gz"].a.transpose(2, 1, 0),
+                   ws=np.pad(ws.a.T, ((0, 1), (0, 1))), ws_tl=np.pad(ws_tl.a.T, ((0, 1), (0, 1))))
+        got = dict(gz=gz_o[t].numpy(), gz_tl=dgz_o[t].numpy(), ws=ws_o[t, 0].numpy(), ws_tl=dws_o[t, 0].numpy())
+        for k in ref:
+            errs[k] = max(errs.get(k, 0.0), relerr(ext(got[k]), ext(ref[k])))
+        assert np.abs(ws_tl.a).max() > 0
+    print("update_dz_c", errs)
+    assert max(errs.values()) <= TOL, errs
