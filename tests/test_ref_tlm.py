@@ -271,3 +271,44 @@ def test_update_dz_c_tlm_pins_oracle():
         assert np.abs(ws_tl.a).max() > 0
     print("update_dz_c", errs)
     assert max(errs.values()) <= TOL, errs
+
+
+def test_riem_solver_tlm_pins_oracle():
+    """RIEM_SOLVER_C_TLM (model_tlmadm/nh_utils_tlm.F90:723-845) and RIEM_SOLVER3_TLM (model_tlmadm/nh_core_tlm.F90:49-243), SIM1 branch,
+    on the columns of one cube tile with atmosphere-like profiles (10 layers)."""
+    from oracle import nh as onh
+    from test_nh import column_state, NHCFG
+    from ref_tlm.riem_solver_tlm import riem_solver_c_tlm, riem_solver3_tlm
+    N, K = 12, 10
+    f, rng, ak, bk = column_state(N, K, 17)
+    cfg = dict(NHCFG); cfg["a_imp"] = 1.0
+    dts = 75.0
+    names = ["delp", "pt", "z", "w", "ws"]
+    d = {n: 1e-3 * np.abs(f[n]).std() * rng.standard_normal(f[n].shape) for n in names}
+    d["w"] *= 100.0; d["ws"] *= 100.0
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    t = 0
+    col = lambda a: np.ascontiguousarray(a[t].reshape(a.shape[1], -1))        # [K(+1), ncol]
+    ws_c = lambda a: col(a)[0]
+    zb = T(f["zb"])
+    # C-grid solver: heights in, geopotential out, hs = grav * zb
+    (pef_o, gz_o), (dpef_o, dgz_o) = torch.func.jvp(
+        lambda delp, pt, z, w, ws: onh.riem_solver_c(dts, delp, pt, z, w, ws, zb * cfg["grav"], cfg),
+        tuple(T(f[n]) for n in names), tuple(T(d[n]) for n in names))
+    gz, gz_tl, pef, pef_tl = riem_solver_c_tlm(cfg["grav"], cfg["rdgas"], dts, K, cfg["akap"], cfg["ptop"], ws_c(f["zb"]) * cfg["grav"],
+                                               col(f["w"]), col(d["w"]), col(f["pt"]), col(d["pt"]), col(f["delp"]), col(d["delp"]),
+                                               col(f["z"]), col(d["z"]), ws_c(f["ws"]), ws_c(d["ws"]), cfg["p_fac"])
+    errs = dict(c_gz=relerr(col(gz_o.numpy()), gz), c_gz_tl=relerr(col(dgz_o.numpy()), gz_tl),
+                c_pef=relerr(col(pef_o.numpy()), pef), c_pef_tl=relerr(col(dpef_o.numpy()), pef_tl))
+    # D-grid solver
+    (w_o, dz_o, zh_o, pp_o), (dw_o, ddz_o, dzh_o, dpp_o) = torch.func.jvp(
+        lambda delp, pt, z, w, ws: onh.riem_solver3(dts, delp, pt, z, w, ws, zb, cfg),
+        tuple(T(f[n]) for n in names), tuple(T(d[n]) for n in names))
+    r = riem_solver3_tlm(cfg["grav"], cfg["rdgas"], dts, K, cfg["akap"], cfg["ptop"], ws_c(f["zb"]), col(f["w"]), col(d["w"]),
+                         col(f["pt"]), col(d["pt"]), col(f["delp"]), col(d["delp"]), col(f["z"]), col(d["z"]), ws_c(f["ws"]), ws_c(d["ws"]),
+                         cfg["p_fac"])
+    for nm, o, do in (("w", w_o, dw_o), ("delz", dz_o, ddz_o), ("zh", zh_o, dzh_o), ("ppe", pp_o, dpp_o)):
+        errs["d_" + nm] = relerr(col(o.numpy()), r[nm]); errs["d_" + nm + "_tl"] = relerr(col(do.numpy()), r[nm + "_tl"])
+        assert np.abs(r[nm + "_tl"]).max() > 0
+    print("riem", errs)
+    assert max(errs.values()) <= TOL, errs          # achieved 7e-15
