@@ -312,3 +312,42 @@ def test_riem_solver_tlm_pins_oracle():
         assert np.abs(r[nm + "_tl"]).max() > 0
     print("riem", errs)
     assert max(errs.values()) <= TOL, errs          # achieved 7e-15
+
+
+def test_nh_p_grad_tlm_pins_oracle():
+    """NH_P_GRAD_TLM (model_tlmadm/dyn_core_tlm.F90:3340-3470) on one whole cube tile: a2b_ord4 of pp / pk / gz / delp, the hydrostatic and
+    the non-hydrostatic pressure-gradient increments of the D-grid winds."""
+    from oracle import dyn_core as odc
+    from ref_tlm.nh_p_grad_tlm import nh_p_grad_tlm
+    from ref_tlm.a2b_ord4_tlm import a2b_ord4_tlm
+    from ref_tlm.fv_tp_2d_tlm import BD
+    N, K = 12, 3
+    rng = np.random.default_rng(53)
+    M = metrics(N); g = ograd(N)
+    NX = N + 7
+    akap, dt, ptk = 2. / 7., 20.0, 100.0 ** (2. / 7.)
+    pe = np.array([100., 3.0e4, 7.0e4, 1.0e5]).reshape(1, K + 1, 1, 1) * (1.0 + 0.01 * rng.standard_normal((6, K + 1, NX, NX)))
+    v = dict(u=rnd(rng, N, K, 10.0) * M["dx"][:, None], v=rnd(rng, N, K, 10.0) * M["dy"][:, None], pk=pe ** akap,
+             gz=9.80665 * (np.array([30000., 9000., 3000., 0.]).reshape(1, K + 1, 1, 1) + 50.0 * rng.standard_normal((6, K + 1, NX, NX))),
+             pp=30.0 * rng.standard_normal((6, K + 1, NX, NX)), delp=pe[:, 1:] - pe[:, :-1])
+    names = list(v)
+    d = {n: 1e-2 * np.abs(v[n]).std() * rng.standard_normal(v[n].shape) for n in names}
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    (u_o, v_o), (du_o, dv_o) = torch.func.jvp(lambda u, v_, pk, gz, pp, delp: odc.grad_p(u, v_, pk, gz, g, dt, ptk, pp=pp, delp=delp),
+                                              tuple(T(v[n]) for n in names), tuple(T(d[n]) for n in names))
+    t = 4
+    P = lambda a, i, j: a[t, j + 2, i + 2]
+    dxa, dya = F((-2, N + 3), (-2, N + 3), data=M["dxa"][t].T[:-1, :-1]), F((-2, N + 3), (-2, N + 3), data=M["dya"][t].T[:-1, :-1])
+    a2b = lambda qin, qin_tl: a2b_ord4_tlm(qin, qin_tl, lambda i, j: P(M["grid"], i, j), lambda i, j: P(M["agrid"], i, j), dxa, dya,
+                                           lambda j: M["edge_w"][t, j + 2], lambda j: M["edge_e"][t, j + 2],
+                                           lambda i: M["edge_s"][t, i + 2], lambda i: M["edge_n"][t, i + 2], N + 1, N + 1, 1, N, 1, N, 3)
+    a = {n: _fa3(v[n][t], N) for n in names}; a_tl = {n: _fa3(d[n][t], N) for n in names}
+    nh_p_grad_tlm(a["u"], a_tl["u"], a["v"], a_tl["v"], a["pp"], a_tl["pp"], a["gz"], a_tl["gz"], a["delp"], a_tl["delp"], a["pk"], a_tl["pk"],
+                  dt, _fa(M["rdx"][t], N), _fa(M["rdy"][t], N), BD(N), K, ptk, a2b)
+    back = lambda f: f.a.transpose(2, 1, 0)
+    errs = dict(u=relerr(region(u_o[t].numpy(), 1, N, 1, N + 1), region(back(a["u"]), 1, N, 1, N + 1)),
+                u_tl=relerr(region(du_o[t].numpy(), 1, N, 1, N + 1), region(back(a_tl["u"]), 1, N, 1, N + 1)),
+                v=relerr(region(v_o[t].numpy(), 1, N + 1, 1, N), region(back(a["v"]), 1, N + 1, 1, N)),
+                v_tl=relerr(region(dv_o[t].numpy(), 1, N + 1, 1, N), region(back(a_tl["v"]), 1, N + 1, 1, N)))
+    print("nh_p_grad", errs)
+    assert max(errs.values()) <= TOL, errs
