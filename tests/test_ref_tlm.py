@@ -351,3 +351,36 @@ def test_nh_p_grad_tlm_pins_oracle():
                 v_tl=relerr(region(dv_o[t].numpy(), 1, N + 1, 1, N), region(back(a_tl["v"]), 1, N + 1, 1, N)))
     print("nh_p_grad", errs)
     assert max(errs.values()) <= TOL, errs
+
+
+@pytest.mark.parametrize("hydrostatic", [False, True])
+def test_p_grad_c_tlm_pins_oracle(hydrostatic):
+    """P_GRAD_C_TLM (model_tlmadm/dyn_core_tlm.F90:3194-3275) on one whole cube tile, both weightings (delpc / pkc differences)"""
+    from oracle import dyn_core as odc
+    from ref_tlm.p_grad_c_tlm import p_grad_c_tlm
+    from ref_tlm.fv_tp_2d_tlm import BD
+    N, K = 12, 3
+    rng = np.random.default_rng(59)
+    M = metrics(N); g = ograd(N)
+    NX = N + 7
+    dt2 = 10.0
+    pe = np.array([100., 3.0e4, 7.0e4, 1.0e5]).reshape(1, K + 1, 1, 1) * (1.0 + 0.01 * rng.standard_normal((6, K + 1, NX, NX)))
+    v = dict(delpc=pe[:, 1:] - pe[:, :-1], pkc=(pe ** (2. / 7.) if hydrostatic else pe),
+             gz=9.80665 * (np.array([30000., 9000., 3000., 0.]).reshape(1, K + 1, 1, 1) + 50.0 * rng.standard_normal((6, K + 1, NX, NX))),
+             uc=rnd(rng, N, K, 10.0), vc=rnd(rng, N, K, 10.0))
+    names = list(v)
+    d = {n: 1e-2 * np.abs(v[n]).std() * rng.standard_normal(v[n].shape) for n in names}
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    (u_o, v_o), (du_o, dv_o) = torch.func.jvp(lambda delpc, pkc, gz, uc, vc: odc.p_grad_c(dt2, delpc, pkc, gz, uc, vc, g, hydrostatic),
+                                              tuple(T(v[n]) for n in names), tuple(T(d[n]) for n in names))
+    t = 3
+    a = {n: _fa3(v[n][t], N) for n in names}; a_tl = {n: _fa3(d[n][t], N) for n in names}
+    p_grad_c_tlm(dt2, K, a["delpc"], a_tl["delpc"], a["pkc"], a_tl["pkc"], a["gz"], a_tl["gz"], a["uc"], a_tl["uc"], a["vc"], a_tl["vc"],
+                 BD(N), _fa(M["rdxc"][t], N), _fa(M["rdyc"][t], N), hydrostatic)
+    back = lambda f: f.a.transpose(2, 1, 0)
+    errs = dict(uc=relerr(region(u_o[t].numpy(), 1, N + 1, 1, N), region(back(a["uc"]), 1, N + 1, 1, N)),
+                uc_tl=relerr(region(du_o[t].numpy(), 1, N + 1, 1, N), region(back(a_tl["uc"]), 1, N + 1, 1, N)),
+                vc=relerr(region(v_o[t].numpy(), 1, N, 1, N + 1), region(back(a["vc"]), 1, N, 1, N + 1)),
+                vc_tl=relerr(region(dv_o[t].numpy(), 1, N, 1, N + 1), region(back(a_tl["vc"]), 1, N, 1, N + 1)))
+    print("p_grad_c", hydrostatic, errs)
+    assert max(errs.values()) <= TOL, errs
