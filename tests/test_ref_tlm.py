@@ -384,3 +384,42 @@ def test_p_grad_c_tlm_pins_oracle(hydrostatic):
                 vc_tl=relerr(region(dv_o[t].numpy(), 1, N, 1, N + 1), region(back(a_tl["vc"]), 1, N, 1, N + 1)))
     print("p_grad_c", hydrostatic, errs)
     assert max(errs.values()) <= TOL, errs
+
+
+def test_d2a2c_vect_divergence_corner_tlm_pin_oracle():
+    """D2A2C_VECT_TLM (model_tlmadm/sw_core_tlm.F90:5874-6395) and DIVERGENCE_CORNER_TLM (:3805-3966) on two whole cube tiles: the D -> A -> C
+    wind interpolation with its edge / corner special cases and upstream sin_sg choice, then the corner divergence from its outputs."""
+    from oracle import sw_core as osw
+    from ref_tlm.d2a2c_vect_tlm import d2a2c_vect_tlm, divergence_corner_tlm
+    from ref_tlm.fv_tp_2d_tlm import BD
+    N, K = 12, 1
+    rng = np.random.default_rng(61)
+    M = metrics(N); g = ograd(N)
+    u = rnd(rng, N, K, 10.0, 3.0); v = rnd(rng, N, K, 10.0, -2.0)
+    du = rnd(rng, N, K, 0.1); dv = rnd(rng, N, K, 0.1)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    def fn(u_, v_):
+        ua, va, uc, vc, ut, vt = osw.d2a2c_vect(u_, v_, g, True)
+        return ua, va, uc, vc, ut, vt, osw.divergence_corner(u_, v_, ua, va, g)
+    out_o, dout_o = torch.func.jvp(fn, (T(u), T(v)), (T(du), T(dv)))
+    onames = ["ua", "va", "uc", "vc", "ut", "vt", "divg_d"]
+    # regions the reference defines (and the callers read): ua / va with dord4 on is-2..ie+2, uc / ut on 0..npx+1 x 0..npy-1+1, ...
+    regs = dict(ua=(-1, N + 2, -1, N + 2), va=(-1, N + 2, -1, N + 2), uc=(0, N + 2, 0, N + 1), ut=(0, N + 2, 0, N + 1),
+                vc=(0, N + 1, 0, N + 2), vt=(0, N + 1, 0, N + 2), divg_d=(1, N + 1, 1, N + 1))
+    errs = {}
+    for t in (0, 5):
+        gs = {k: _fa(M[k][t], N) for k in ("cosa_u", "cosa_v", "cosa_s", "rsin_u", "rsin_v", "rsin2", "dxa", "dya", "dxc", "dyc", "rarea_c")}
+        gs["sin_sg"] = lambda i, j, n, t=t: M["sin_sg"][t, j + 2, i + 2, n]
+        gs["cos_sg"] = lambda i, j, n, t=t: M["cos_sg"][t, j + 2, i + 2, n]
+        fu, fu_tl, fv, fv_tl = _fa(u[t, 0], N), _fa(du[t, 0], N), _fa(v[t, 0], N), _fa(dv[t, 0], N)
+        r = d2a2c_vect_tlm(fu, fu_tl, fv, fv_tl, True, gs, BD(N), N + 1, N + 1)
+        r["divg_d"], r["divg_d_tl"] = divergence_corner_tlm(fu, fu_tl, fv, fv_tl, r["ua"], r["ua_tl"], r["va"], r["va_tl"], gs, BD(N), N + 1, N + 1)
+        for k, nm in enumerate(onames):
+            for sfx, src in (("", out_o), ("_tl", dout_o)):
+                ref = r[nm + sfx].a.T
+                ref = np.pad(ref, ((0, N + 7 - ref.shape[0]), (0, N + 7 - ref.shape[1])))
+                errs[nm + sfx] = max(errs.get(nm + sfx, 0.0), relerr(region(src[k][t, 0].numpy(), *regs[nm]), region(ref, *regs[nm])))
+                assert np.abs(region(ref, *regs[nm])).max() > 0 and np.abs(region(ref, *regs[nm])).max() < 1e20
+    print("d2a2c / divergence_corner", errs)
+    assert max(errs.values()) <= TOL, errs
