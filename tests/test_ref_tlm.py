@@ -423,3 +423,46 @@ def test_d2a2c_vect_divergence_corner_tlm_pin_oracle():
                 assert np.abs(region(ref, *regs[nm])).max() > 0 and np.abs(region(ref, *regs[nm])).max() < 1e20
     print("d2a2c / divergence_corner", errs)
     assert max(errs.values()) <= TOL, errs
+
+
+@pytest.mark.parametrize("hydrostatic", [False, True])
+def test_c_sw_tlm_pins_oracle(hydrostatic):
+    """C_SW_TLM (model_tlmadm/sw_core_tlm.F90:87-645) on two whole cube tiles: the complete C-grid half step (winds on A / C grids, corner
+    divergence, upwind transport of delp / pt / w, kinetic energy, absolute vorticity and the time-centred C-grid winds)."""
+    from oracle import sw_core as osw
+    from test_c_sw import smooth_state
+    from ref_tlm.c_sw_tlm import c_sw_tlm
+    from ref_tlm.fv_tp_2d_tlm import BD
+    N, K = 12, 1
+    f, rng = smooth_state(N, K, 71)
+    M = metrics(N); g = ograd(N)
+    dt2 = 225.0
+    names = ["delp", "pt", "u", "v", "w"]
+    d = {n: 1e-2 * np.abs(f[n]).std() * rnd(rng, N, K) for n in names}
+    onames = ["delpc", "ptc", "uc", "vc", "ua", "va", "ut", "vt", "divg_d"] + ([] if hydrostatic else ["wc"])
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    def fn(*a):
+        o = osw.c_sw(*a, g, dt2, hydrostatic, 1)
+        return tuple(o[k] for k in onames)
+    out_o, dout_o = torch.func.jvp(fn, tuple(T(f[n]) for n in names), tuple(T(d[n]) for n in names))
+    npx = N + 1
+    regs = {"delpc": (0, npx, 0, npx), "ptc": (0, npx, 0, npx), "wc": (0, npx, 0, npx), "uc": (1, npx, 1, N), "vc": (1, N, 1, npx),
+            "ua": (0, npx, 0, npx), "va": (0, npx, 0, npx), "ut": (0, npx + 1, 0, npx), "vt": (0, npx, 0, npx + 1), "divg_d": (1, npx, 1, npx)}
+    errs = {}
+    for t in (1, 4):
+        gs = {k: _fa(M[k][t], N) for k in ("cosa_u", "cosa_v", "cosa_s", "sina_u", "sina_v", "rsin_u", "rsin_v", "rsin2", "dxa", "dya", "dx", "dy",
+                                           "dxc", "dyc", "rarea", "rarea_c", "rdxc", "rdyc", "fC")}
+        gs["sin_sg"] = lambda i, j, n, t=t: M["sin_sg"][t, j + 2, i + 2, n]
+        gs["cos_sg"] = lambda i, j, n, t=t: M["cos_sg"][t, j + 2, i + 2, n]
+        a = {n: _fa(f[n][t, 0], N) for n in names}; a_tl = {n: _fa(d[n][t, 0], N) for n in names}
+        r = c_sw_tlm(a["delp"], a_tl["delp"], a["pt"], a_tl["pt"], a["u"], a_tl["u"], a["v"], a_tl["v"], a["w"], a_tl["w"], 1, dt2, hydrostatic,
+                     True, BD(N), gs, npx, npx)
+        for k, nm in enumerate(onames):
+            for sfx, src in (("", out_o), ("_tl", dout_o)):
+                ref = r[nm + sfx].a.T
+                ref = np.pad(ref, ((0, N + 7 - ref.shape[0]), (0, N + 7 - ref.shape[1])))
+                errs[nm + sfx] = max(errs.get(nm + sfx, 0.0), relerr(region(src[k][t, 0].numpy(), *regs[nm]), region(ref, *regs[nm])))
+                assert np.abs(region(ref, *regs[nm])).max() > 0
+    print("c_sw", hydrostatic, errs)
+    assert max(errs.values()) <= TOL, errs
