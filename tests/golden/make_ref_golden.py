@@ -1,0 +1,147 @@
+"""Generates tests/golden/ref_*.npz: outputs of the REFERENCE'S OWN Fortran routines, executed IN THIS CONTAINER from /root/reference by the
+Fortran -> Python transpiler tests/ref_tlm/f90py.py (no Fortran compiler, FMS or MPI exists in the image, so the reference cannot be
+compiled; the transpiler runs its source statement by statement in float64).  Run once here:
+
+    python tests/golden/make_ref_golden.py            # writes tests/golden/ref_d_sw_tlm.npz, ...
+
+The fixtures hold the seeded inputs and every output (values and tangents); tests/test_ref_golden.py compares the oracle (torch.func.jvp of
+the restated primal) and the library (host emulation through the C ABI) with them.  /root/reference is needed only by this script.
+The grid metrics are the repository's own (oracle/grid.py): the reference reads them from FMS at run time."""
+import os
+import sys
+import types
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "fv3-jedi-linearmodel_b200"))
+from ref_tlm import f90py                      # noqa: E402
+from ref_tlm.f90py import FA                   # noqa: E402
+
+REF = "/root/reference/src/dynamics/atmos_cubed_sphere/model_tlmadm/"
+NG = 3
+
+
+def great_circle_dist(q1, q2, radius=None):
+    """fv_grid_utils_nlm great_circle_dist (haversine); q1, q2: (lon, lat) sections"""
+    p1 = np.asarray(q1.a if isinstance(q1, FA) else q1); p2 = np.asarray(q2.a if isinstance(q2, FA) else q2)
+    beta = np.arcsin(np.sqrt(np.sin((p1[1] - p2[1]) / 2.) ** 2 + np.cos(p1[1]) * np.cos(p2[1]) * np.sin((p1[0] - p2[0]) / 2.) ** 2)) * 2.
+    return beta if radius is None else radius * beta
+
+
+def load_reference():
+    only = {"xppm_tlm", "yppm_tlm", "fv_tp_2d_tlm", "copy_corners_tlm", "deln_flux_tlm", "d_sw_tlm", "xtp_u_tlm", "ytp_v_tlm", "del6_vt_flux_tlm",
+            "compute_divergence_damping_tlm", "smag_corner_tlm", "fv_tp_2d", "xppm", "yppm", "copy_corners", "deln_flux", "pert_ppm", "xtp_u", "ytp_v",
+            "del6_vt_flux", "compute_divergence_damping", "smag_corner", "a2b_ord4_tlm", "a2b_ord4", "extrap_corner_tlm", "extrap_corner",
+            "fill_corners_tlm", "fill_corners", "c_sw_tlm", "d2a2c_vect_tlm", "divergence_corner_tlm", "fill_4corners_tlm", "fill2_4corners_tlm",
+            "edge_interpolate4_tlm", "edge_interpolate4"}
+    extra = dict(ng=NG, great_circle_dist=great_circle_dist, fpp=types.SimpleNamespace(fpp_overload_r4=False))
+    return f90py.load([REF + "tp_core_tlm.F90", REF + "sw_core_tlm.F90", REF + "a2b_edge_tlm.F90"], extra=extra, only=only)
+
+
+def fa(a, i0, i1, j0, j1):
+    """[NY, NX(, c)] array with Fortran (i, j) at [j + 2, i + 2] -> FA over (i0:i1, j0:j1(, 1:c))"""
+    s = a[j0 + 2: j1 + 3, i0 + 2: i1 + 3]
+    if s.ndim == 3:
+        return FA(np.ascontiguousarray(s.transpose(1, 0, 2)), (i0, j0, 1))
+    return FA(np.ascontiguousarray(s.T), (i0, j0))
+
+
+def back(f, N):
+    """FA over any (i0:i1, j0:j1) -> [NY, NX] array, zero outside"""
+    out = np.zeros((N + 7, N + 7))
+    i0, j0 = f.lo
+    ni, nj = f.a.shape
+    out[j0 + 2: j0 + 2 + nj, i0 + 2: i0 + 2 + ni] = f.a.T
+    return out
+
+
+def grid_structs(M, t, N):
+    bd = types.SimpleNamespace(is_=1, ie=N, js=1, je=N, isd=1 - NG, ied=N + NG, jsd=1 - NG, jed=N + NG, ng=NG)
+    gs = types.SimpleNamespace(nested=False, grid_type=0, stretched_grid=False, sw_corner=True, se_corner=True, nw_corner=True, ne_corner=True,
+                               da_min=M["da_min"], da_min_c=M["da_min_c"])
+    isd, ied, jsd, jed = bd.isd, bd.ied, bd.jsd, bd.jed
+    A = (isd, ied, jsd, jed); B = (isd, ied + 1, jsd, jed + 1); U = (isd, ied, jsd, jed + 1); V = (isd, ied + 1, jsd, jed)
+    for k, b in dict(area=A, rarea=A, dxa=A, dya=A, rdxa=A, rdya=A, cosa_s=A, rsin2=A, dx=U, rdx=U, dy=V, rdy=V, dxc=V, rdxc=V, dyc=U, rdyc=U,
+                     area_c=B, rarea_c=B, cosa=B, sina=B, rsina=(1, N + 1, 1, N + 1), cosa_u=V, sina_u=V, rsin_u=V, cosa_v=U, sina_v=U, rsin_v=U,
+                     f0=A, fC=B, divg_u=U, divg_v=V, del6_u=U, del6_v=V).items():
+        setattr(gs, k.lower(), fa(M[k][t], *b))
+    gs.fc = gs.fc if hasattr(gs, "fc") else None
+    gs.sin_sg = FA(np.ascontiguousarray(M["sin_sg"][t, :N + 6, :N + 6, 1:].transpose(1, 0, 2)), (isd, jsd, 1))
+    gs.cos_sg = FA(np.ascontiguousarray(M["cos_sg"][t, :N + 6, :N + 6, 1:].transpose(1, 0, 2)), (isd, jsd, 1))
+    gs.grid = fa(M["grid"][t], *B); gs.agrid = fa(M["agrid"][t], *A)
+    for e in ("edge_w", "edge_e", "edge_s", "edge_n"):
+        setattr(gs, e, FA(np.ascontiguousarray(M[e][t, 3:3 + N + 1]), (1,)))     # Fortran index j at [j + 2]
+    fl = types.SimpleNamespace(npx=N + 1, npy=N + 1, grid_type=0, do_f3d=False)
+    return bd, gs, fl
+
+
+D_SW_BOUNDS = None
+
+
+def d_sw_case(fns, M, N, t, f, d, prm, dt, hydrostatic, d_con=0.0):
+    """one level of D_SW_TLM on tile t.  f, d: dict name -> [NY, NX] value / tangent of delp pt u v w uc vc ua va divg_d"""
+    bd, gs, fl = grid_structs(M, t, N)
+    isd, ied, jsd, jed = bd.isd, bd.ied, bd.jsd, bd.jed
+    A = (isd, ied, jsd, jed)
+    bnd = dict(delp=A, pt=A, w=A, ua=A, va=A, u=(isd, ied, jsd, jed + 1), vc=(isd, ied, jsd, jed + 1), v=(isd, ied + 1, jsd, jed),
+               uc=(isd, ied + 1, jsd, jed), divg_d=(isd, ied + 1, jsd, jed + 1))
+    a = {n: fa(f[n], *bnd[n]) for n in bnd}; a_tl = {n: fa(d[n], *bnd[n]) for n in bnd}
+    Z = lambda b: FA.alloc(((b[0], b[1]), (b[2], b[3])))
+    X = (1, N + 1, jsd, jed); Y = (isd, ied, 1, N + 1); C = (1, N, 1, N)
+    o = {}
+    for n, b in dict(delpc=A, ptc=A, xflux=(1, N + 1, 1, N), yflux=(1, N, 1, N + 1), cx=X, cy=Y, crx_adv=X, cry_adv=Y, xfx_adv=X, yfx_adv=Y,
+                     heat_source=C, dpx=C, z_rat=A, q_con=A).items():
+        o[n] = Z(b); o[n + "_tl"] = Z(b)
+    q = FA.alloc(((isd, ied), (jsd, jed), (1, 1), (1, 1))); q_tl = FA.alloc(((isd, ied), (jsd, jed), (1, 1), (1, 1)))
+    p = prm
+    fns["d_sw_tlm"](o["delpc"], o["delpc_tl"], a["delp"], a_tl["delp"], o["ptc"], o["ptc_tl"], a["pt"], a_tl["pt"], a["u"], a_tl["u"], a["v"], a_tl["v"],
+                    a["w"], a_tl["w"], a["uc"], a_tl["uc"], a["vc"], a_tl["vc"], a["ua"], a_tl["ua"], a["va"], a_tl["va"], a["divg_d"], a_tl["divg_d"],
+                    o["xflux"], o["xflux_tl"], o["yflux"], o["yflux_tl"], o["cx"], o["cx_tl"], o["cy"], o["cy_tl"], o["crx_adv"], o["crx_adv_tl"],
+                    o["cry_adv"], o["cry_adv_tl"], o["xfx_adv"], o["xfx_adv_tl"], o["yfx_adv"], o["yfx_adv_tl"], o["q_con"], o["z_rat"], o["z_rat_tl"],
+                    0.0, o["heat_source"], o["heat_source_tl"], o["dpx"], o["dpx_tl"], 0.0, 1, 1, q, q_tl, 1, 1, False, dt,
+                    p["hord_tr"], p["hord_mt"], p["hord_vt"], p["hord_tm"], p["hord_dp"], p["nord"], p["nord_v"], p["nord_w"], p["nord_t"],
+                    p["dddmp"], p["d2_bg"], p["d4_bg"], p["damp_v"], p["damp_w"], p["damp_t"], d_con, hydrostatic, gs, fl, bd,
+                    p["hord_tr"], p["hord_mt"], p["hord_vt"], p["hord_tm"], p["hord_dp"], False, p["nord"], p["nord_v"], p["nord_w"], p["nord_t"],
+                    p["dddmp"], p["d2_bg"], p["d4_bg"], p["damp_v"], p["damp_w"], p["damp_t"])
+    res = {}
+    for n in ("delp", "pt", "u", "v", "w"):
+        res[n] = back(a[n], N); res[n + "_tl"] = back(a_tl[n], N)
+    for n, key in (("xflux", "fx"), ("yflux", "fy"), ("crx_adv", "crx"), ("cry_adv", "cry"), ("xfx_adv", "xfx"), ("yfx_adv", "yfx"), ("heat_source", "heat")):
+        res[key] = back(o[n], N); res[key + "_tl"] = back(o[n + "_tl"], N)
+    return res
+
+
+def main():
+    from common import metrics, rnd
+    from test_d_sw import dsw_inputs
+    spaces, fns, src = load_reference()
+    N, K = 12, 1
+    M = metrics(N)
+    f, rng = dsw_inputs(N, K, 11)
+    d = {n: 1e-2 * np.abs(f[n]).std() * rnd(rng, N, K) for n in f}
+    base = dict(hord_tr=2, hord_mt=2, hord_vt=2, hord_tm=2, hord_dp=2, nord=1, nord_v=1, nord_w=1, nord_t=1, d2_bg=0.015, damp_v=0.0005,
+                damp_w=0.0005, damp_t=0.0005, dddmp=0.2, d4_bg=0.15)
+    sponge = dict(base, hord_mt=1, hord_vt=1, hord_tm=1, hord_dp=1, nord=0, d2_bg=4.0, nord_w=0, damp_w=4.0, nord_v=0, damp_v=2.0, nord_t=0)
+    cases = dict(nonhydro=(base, False, 0.0), sponge=(sponge, False, 0.0), hydro=(base, True, 0.0), heating=(base, False, 0.5),
+                 ord333=(dict(base, hord_mt=333, hord_vt=333, hord_tm=333, hord_dp=333), False, 0.0))
+    out = {"N": N, "dt": 450.0}
+    for n in f:
+        out["in." + n] = f[n]; out["in_tl." + n] = d[n]
+    tiles = (0, 3)
+    out["tiles"] = np.array(tiles)
+    for name, (prm, hydro, d_con) in cases.items():
+        for t in tiles:
+            r = d_sw_case(fns, M, N, t, {n: f[n][t, 0] for n in f}, {n: d[n][t, 0] for n in f}, prm, 450.0, hydro, d_con)
+            for k, v in r.items():
+                out["%s.t%d.%s" % (name, t, k)] = v
+        print("d_sw_tlm", name, "done")
+    import json
+    out["cases"] = json.dumps({k: dict(prm=v[0], hydrostatic=v[1], d_con=v[2]) for k, v in cases.items()})
+    np.savez_compressed(os.path.join(HERE, "ref_d_sw_tlm.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

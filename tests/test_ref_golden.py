@@ -1,0 +1,118 @@
+"""Reference-generated golden vectors (tests/golden/ref_*.npz, written by tests/golden/make_ref_golden.py): outputs of the reference's own
+Fortran tangent-linear routines, executed in the build container from /root/reference by the transpiler tests/ref_tlm/f90py.py.
+(1) the ORACLE (values and torch.func.jvp tangents) reproduces them; (2) the LIBRARY (host emulation of the CUDA kernels through the C ABI;
+the CUDA build on the GPU box is compared with the oracle by the -m gpu tests) reproduces them without the oracle in the loop.
+Nothing here reads /root/reference."""
+import json
+import os
+import numpy as np
+import pytest
+import torch
+from common import metrics, ograd, handle, region, relerr
+import fv3lm
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-13      # achieved: values bit-identical, tangents <= 6e-15 (same arithmetic, a few additions in a different order)
+LIB_TOL = 2e-12  # the library against the same vectors (its tolerance against the oracle in tests/test_d_sw.py)
+
+D_SW_NAMES = ["delp", "pt", "u", "v", "w", "uc", "vc", "ua", "va", "divg_d"]
+
+
+def _d_sw_regions(N, hydrostatic, d_con):
+    npx = N + 1
+    C = (1, N, 1, N)
+    r = dict(delp=C, pt=C, u=(1, N, 1, npx), v=(1, npx, 1, N), fx=(1, npx, 1, N), fy=(1, N, 1, npx),
+             crx=(1, npx, -2, N + 3), xfx=(1, npx, -2, N + 3), cry=(-2, N + 3, 1, npx), yfx=(-2, N + 3, 1, npx))
+    if not hydrostatic:
+        r["w"] = C
+    if d_con > 0.0:
+        r["heat"] = C
+    return r
+
+
+def _prm(case):
+    p = {k: ([v] if k not in ("dddmp", "d4_bg") else v) for k, v in case["prm"].items() if k != "hord_tr"}
+    p["hydrostatic"] = case["hydrostatic"]
+    if case["d_con"] > 0.0:
+        p["d_con"] = [case["d_con"]]
+    return p
+
+
+@pytest.mark.parametrize("name", ["nonhydro", "sponge", "hydro", "heating", "ord333"])
+def test_oracle_reproduces_reference_d_sw_tlm(name):
+    """D_SW_TLM (model_tlmadm/sw_core_tlm.F90:1047-3620, with everything it calls: FV_TP_2D_TLM, XTP_U_TLM, YTP_V_TLM,
+    COMPUTE_DIVERGENCE_DAMPING_TLM, A2B_ORD4_TLM, DEL6_VT_FLUX_TLM ...) on two cube tiles: the D-grid step of the shallow-water core."""
+    from oracle import d_sw as odsw
+    gold = np.load(os.path.join(GOLD, "ref_d_sw_tlm.npz"))
+    case = json.loads(str(gold["cases"]))[name]
+    N = int(gold["N"]); dt = float(gold["dt"])
+    g = ograd(N)
+    f = {n: gold["in." + n] for n in D_SW_NAMES}; d = {n: gold["in_tl." + n] for n in D_SW_NAMES}
+    prm = _prm(case)
+    regs = _d_sw_regions(N, case["hydrostatic"], case["d_con"])
+    onames = list(regs)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    def fn(*a):
+        o = odsw.d_sw(*a, g, dt, prm)
+        return tuple(o[k] for k in onames)
+    out, dout = torch.func.jvp(fn, tuple(T(f[n]) for n in D_SW_NAMES), tuple(T(d[n]) for n in D_SW_NAMES))
+    errs = {}
+    for t in gold["tiles"]:
+        for k, nm in enumerate(onames):
+            for sfx, src in (("", out), ("_tl", dout)):
+                ref = gold["%s.t%d.%s%s" % (name, t, nm, sfx)]
+                assert np.abs(region(ref, *regs[nm])).max() > 0, (nm, sfx)
+                errs[nm + sfx] = max(errs.get(nm + sfx, 0.0), relerr(region(src[k][t, 0].numpy(), *regs[nm]), region(ref, *regs[nm])))
+    print("d_sw_tlm vs reference", name, {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= TOL, errs
+
+
+def _lib_vs_reference_d_sw(emu, name):
+    from test_d_sw import flat_params
+    gold = np.load(os.path.join(GOLD, "ref_d_sw_tlm.npz"))
+    case = json.loads(str(gold["cases"]))[name]
+    N = int(gold["N"]); dt = float(gold["dt"]); K = 2          # the fixture's level twice: K = 2 is the depth the d_sw module tests run at
+    rep = lambda a: np.ascontiguousarray(np.repeat(a, K, axis=1))
+    f = {n: rep(gold["in." + n]) for n in D_SW_NAMES}; d = {n: rep(gold["in_tl." + n]) for n in D_SW_NAMES}
+    prm = {k: (v * K if isinstance(v, list) else v) for k, v in _prm(case).items()}
+    regs = _d_sw_regions(N, case["hydrostatic"], case["d_con"])
+    key = dict(delp="delp_n", pt="pt_n", u="u_n", v="v_n", w="w_n")
+    p = flat_params(prm, K); p["dt"] = dt; p["hydrostatic"] = int(case["hydrostatic"])
+    h = handle(N, K, emu)
+    NX = N + 7
+    act = [n for n in D_SW_NAMES if not (case["hydrostatic"] and n == "w")]
+
+    def run(mode):
+        traj = {n: f[n].copy() for n in D_SW_NAMES}
+        for o in regs:
+            traj[key.get(o, o)] = np.zeros((6, K, NX, NX))
+        pert = None
+        if mode == fv3lm.MODE_TL:
+            pert = {n: d[n].copy() for n in act}
+            for o in regs:
+                pert[key.get(o, o)] = np.zeros((6, K, NX, NX))
+        h.module_run("d_sw", mode, traj, pert, params=p)
+        return traj if mode == fv3lm.MODE_NL else pert
+    errs = {}
+    for sfx, res in (("", run(fv3lm.MODE_NL)), ("_tl", run(fv3lm.MODE_TL))):
+        for t in gold["tiles"]:
+            for o, rg in regs.items():
+                ref = region(gold["%s.t%d.%s%s" % (name, t, o, sfx)], *rg)
+                for k in range(K):
+                    errs[o + sfx] = max(errs.get(o + sfx, 0.0), relerr(region(res[key.get(o, o)][t, k], *rg), ref))
+    print("library d_sw vs reference", name, {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= LIB_TOL, errs
+
+
+@pytest.mark.parametrize("name", ["nonhydro", "sponge", "hydro", "heating", "ord333"])
+def test_library_reproduces_reference_d_sw_tlm_emu(name):
+    """the C-ABI library (host emulation of the CUDA kernels) against the reference's own D_SW / D_SW_TLM outputs, no oracle in the loop"""
+    _lib_vs_reference_d_sw(True, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["nonhydro", "sponge", "heating"])
+def test_library_reproduces_reference_d_sw_tlm_gpu(name):
+    """the CUDA library on the B200 against the reference's own D_SW / D_SW_TLM outputs"""
+    _lib_vs_reference_d_sw(False, name)
