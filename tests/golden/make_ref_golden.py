@@ -114,6 +114,51 @@ def d_sw_case(fns, M, N, t, f, d, prm, dt, hydrostatic, d_con=0.0):
     return res
 
 
+def load_reference_adjoint():
+    extra = dict(ng=NG, great_circle_dist=great_circle_dist, fpp=types.SimpleNamespace(fpp_overload_r4=False))
+    return f90py.load([REF + "tp_core_adm.F90", REF + "sw_core_adm.F90", REF + "a2b_edge_adm.F90"], extra=extra, strict=False)
+
+
+def d_sw_adjoint_case(fns, M, N, t, f, seed, prm, dt, hydrostatic, d_con=0.0):
+    """D_SW_FWD then D_SW_BWD (model_tlmadm/sw_core_adm.F90:1773, :3269) on tile t.  seed: dict output name -> [NY, NX] adjoint seed of
+    delp pt u v w (in-place outputs) and fx fy crx cry xfx yfx heat.  Returns the adjoints of the ten inputs."""
+    bd, gs, fl = grid_structs(M, t, N)
+    isd, ied, jsd, jed = bd.isd, bd.ied, bd.jsd, bd.jed
+    A = (isd, ied, jsd, jed)
+    bnd = dict(delp=A, pt=A, w=A, ua=A, va=A, u=(isd, ied, jsd, jed + 1), vc=(isd, ied, jsd, jed + 1), v=(isd, ied + 1, jsd, jed),
+               uc=(isd, ied + 1, jsd, jed), divg_d=(isd, ied + 1, jsd, jed + 1))
+    a = {n: fa(f[n], *bnd[n]) for n in bnd}
+    Z = lambda b: FA.alloc(((b[0], b[1]), (b[2], b[3])))
+    X = (1, N + 1, jsd, jed); Y = (isd, ied, 1, N + 1); C = (1, N, 1, N)
+    ob = dict(delpc=A, ptc=A, xflux=(1, N + 1, 1, N), yflux=(1, N, 1, N + 1), cx=X, cy=Y, crx_adv=X, cry_adv=Y, xfx_adv=X, yfx_adv=Y,
+              heat_source=C, dpx=C, z_rat=A, q_con=A)
+    o = {n: Z(b) for n, b in ob.items()}
+    q = FA.alloc(((isd, ied), (jsd, jed), (1, 1), (1, 1))); q_ad = FA.alloc(((isd, ied), (jsd, jed), (1, 1), (1, 1)))
+    p = prm
+    sw = (p["hord_tr"], p["hord_mt"], p["hord_vt"], p["hord_tm"], p["hord_dp"], p["nord"], p["nord_v"], p["nord_w"], p["nord_t"],
+          p["dddmp"], p["d2_bg"], p["d4_bg"], p["damp_v"], p["damp_w"], p["damp_t"], d_con, hydrostatic, gs, fl, bd,
+          p["hord_tr"], p["hord_mt"], p["hord_vt"], p["hord_tm"], p["hord_dp"], False, p["nord"], p["nord_v"], p["nord_w"], p["nord_t"],
+          p["dddmp"], p["d2_bg"], p["d4_bg"], p["damp_v"], p["damp_w"], p["damp_t"])
+    stack = f90py.RUNTIME["_stack"]
+    assert not stack
+    fns["d_sw_fwd"](o["delpc"], a["delp"], o["ptc"], a["pt"], a["u"], a["v"], a["w"], a["uc"], a["vc"], a["ua"], a["va"], a["divg_d"],
+                    o["xflux"], o["yflux"], o["cx"], o["cy"], o["crx_adv"], o["cry_adv"], o["xfx_adv"], o["yfx_adv"], o["q_con"], o["z_rat"],
+                    0.0, o["heat_source"], o["dpx"], 0.0, 1, 1, q, 1, 1, False, dt, *sw)
+    ad = {n: Z(b) for n, b in bnd.items()}
+    oad = {n: Z(b) for n, b in ob.items()}
+    for n in ("delp", "pt", "u", "v", "w"):
+        ad[n] = fa(seed[n], *bnd[n])
+    for n, key in (("xflux", "fx"), ("yflux", "fy"), ("crx_adv", "crx"), ("cry_adv", "cry"), ("xfx_adv", "xfx"), ("yfx_adv", "yfx"), ("heat_source", "heat")):
+        oad[n] = fa(seed[key], *ob[n])
+    fns["d_sw_bwd"](o["delpc"], oad["delpc"], a["delp"], ad["delp"], o["ptc"], oad["ptc"], a["pt"], ad["pt"], a["u"], ad["u"], a["v"], ad["v"],
+                    a["w"], ad["w"], a["uc"], ad["uc"], a["vc"], ad["vc"], a["ua"], ad["ua"], a["va"], ad["va"], a["divg_d"], ad["divg_d"],
+                    o["xflux"], oad["xflux"], o["yflux"], oad["yflux"], o["cx"], oad["cx"], o["cy"], oad["cy"], o["crx_adv"], oad["crx_adv"],
+                    o["cry_adv"], oad["cry_adv"], o["xfx_adv"], oad["xfx_adv"], o["yfx_adv"], oad["yfx_adv"], o["q_con"], o["z_rat"], oad["z_rat"],
+                    0.0, o["heat_source"], oad["heat_source"], o["dpx"], oad["dpx"], 0.0, 1, 1, q, q_ad, 1, 1, False, dt, *sw)
+    assert not stack, ("checkpoint stack not empty after the backward sweep", len(stack))
+    return {n + "_ad": back(ad[n], N) for n in bnd}
+
+
 def main():
     from common import metrics, rnd
     from test_d_sw import dsw_inputs
@@ -138,6 +183,26 @@ def main():
             for k, v in r.items():
                 out["%s.t%d.%s" % (name, t, k)] = v
         print("d_sw_tlm", name, "done")
+    # adjoint: the reference's own reverse-mode code (D_SW_FWD / D_SW_BWD with Tapenade's checkpoint stack)
+    sp_a, fns_a, src_a = load_reference_adjoint()
+    from common import region
+    npx = N + 1
+    C = (1, N, 1, N)
+    regs = dict(delp=C, pt=C, w=C, heat=C, u=(1, N, 1, npx), v=(1, npx, 1, N), fx=(1, npx, 1, N), fy=(1, N, 1, npx),
+                crx=(1, npx, -2, N + 3), xfx=(1, npx, -2, N + 3), cry=(-2, N + 3, 1, npx), yfx=(-2, N + 3, 1, npx))
+    seed = {}
+    for n, rg in regs.items():
+        y = np.zeros((6, 1, N + 7, N + 7))
+        region(y, *rg)[...] = region(rnd(rng, N, 1), *rg)
+        seed[n] = y
+        out["seed." + n] = y
+    for name, (prm, hydro, d_con) in cases.items():
+        sd = {n: (v if not ((hydro and n == "w") or (d_con == 0.0 and n == "heat")) else 0 * v) for n, v in seed.items()}
+        for t in tiles:
+            r = d_sw_adjoint_case(fns_a, M, N, t, {n: f[n][t, 0] for n in f}, {n: sd[n][t, 0] for n in sd}, prm, 450.0, hydro, d_con)
+            for k, v in r.items():
+                out["%s.t%d.%s" % (name, t, k)] = v
+        print("d_sw_fwd / d_sw_bwd", name, "done")
     import json
     out["cases"] = json.dumps({k: dict(prm=v[0], hydrostatic=v[1], d_con=v[2]) for k, v in cases.items()})
     np.savez_compressed(os.path.join(HERE, "ref_d_sw_tlm.npz"), **out)

@@ -68,6 +68,44 @@ def test_oracle_reproduces_reference_d_sw_tlm(name):
     assert max(errs.values()) <= TOL, errs
 
 
+AD_SEEDS = ["delp", "pt", "u", "v", "w", "fx", "fy", "crx", "cry", "xfx", "yfx", "heat"]
+
+
+@pytest.mark.parametrize("name", ["nonhydro", "sponge", "hydro", "heating", "ord333"])
+def test_oracle_reproduces_reference_d_sw_adjoint(name):
+    """D_SW_FWD + D_SW_BWD (model_tlmadm/sw_core_adm.F90:1773-4974 with FV_TP_2D_FWD/BWD, XTP_U / YTP_V / A2B_ORD4 / DEL6_VT_FLUX /
+    COMPUTE_DIVERGENCE_DAMPING adjoints and Tapenade's checkpoint stack): the reference's own reverse-mode code against torch.func.vjp of
+    the oracle, same random output adjoints."""
+    from oracle import d_sw as odsw
+    gold = np.load(os.path.join(GOLD, "ref_d_sw_tlm.npz"))
+    case = json.loads(str(gold["cases"]))[name]
+    N = int(gold["N"]); dt = float(gold["dt"])
+    g = ograd(N)
+    f = {n: gold["in." + n] for n in D_SW_NAMES}
+    prm = _prm(case)
+    regs = _d_sw_regions(N, case["hydrostatic"], case["d_con"])
+    onames = list(regs)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    def fn(*a):
+        o = odsw.d_sw(*a, g, dt, prm)
+        return tuple(o[k] for k in onames)
+    _, vjp = torch.func.vjp(fn, *[T(f[n]) for n in D_SW_NAMES])
+    ad = vjp(tuple(T(gold["seed." + o]) for o in onames))
+    errs = {}
+    for t in gold["tiles"]:
+        for n, a in zip(D_SW_NAMES, ad):
+            ref = gold["%s.t%d.%s_ad" % (name, t, n)]
+            if case["hydrostatic"] and n == "w":
+                continue
+            if np.abs(ref).max() == 0.0:           # an input this configuration does not read (ua / va, divg_d with nord = 0)
+                assert np.abs(a[t, 0].numpy()).max() == 0.0, n
+                continue
+            errs[n + "_ad"] = max(errs.get(n + "_ad", 0.0), relerr(a[t, 0].numpy(), ref))
+    print("d_sw adjoint vs reference", name, {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= TOL, errs
+
+
 def _lib_vs_reference_d_sw(emu, name):
     from test_d_sw import flat_params
     gold = np.load(os.path.join(GOLD, "ref_d_sw_tlm.npz"))
@@ -92,9 +130,22 @@ def _lib_vs_reference_d_sw(emu, name):
             pert = {n: d[n].copy() for n in act}
             for o in regs:
                 pert[key.get(o, o)] = np.zeros((6, K, NX, NX))
+        elif mode == fv3lm.MODE_AD:
+            pert = {n: np.zeros_like(f[n]) for n in act}
+            for o in regs:
+                pert[key.get(o, o)] = rep(gold["seed." + o])
         h.module_run("d_sw", mode, traj, pert, params=p)
         return traj if mode == fv3lm.MODE_NL else pert
     errs = {}
+    ad = run(fv3lm.MODE_AD)
+    for t in gold["tiles"]:
+        for n in act:
+            ref = gold["%s.t%d.%s_ad" % (name, t, n)]
+            for k in range(K):
+                if np.abs(ref).max() == 0.0:
+                    assert np.abs(ad[n][t, k]).max() == 0.0, n
+                else:
+                    errs[n + "_ad"] = max(errs.get(n + "_ad", 0.0), relerr(ad[n][t, k], ref))
     for sfx, res in (("", run(fv3lm.MODE_NL)), ("_tl", run(fv3lm.MODE_TL))):
         for t in gold["tiles"]:
             for o, rg in regs.items():
@@ -107,12 +158,13 @@ def _lib_vs_reference_d_sw(emu, name):
 
 @pytest.mark.parametrize("name", ["nonhydro", "sponge", "hydro", "heating", "ord333"])
 def test_library_reproduces_reference_d_sw_tlm_emu(name):
-    """the C-ABI library (host emulation of the CUDA kernels) against the reference's own D_SW / D_SW_TLM outputs, no oracle in the loop"""
+    """the C-ABI library (host emulation of the CUDA kernels) against the reference's own D_SW / D_SW_TLM / D_SW_FWD + D_SW_BWD outputs
+    (values, tangents, adjoints), no oracle in the loop"""
     _lib_vs_reference_d_sw(True, name)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["nonhydro", "sponge", "heating"])
 def test_library_reproduces_reference_d_sw_tlm_gpu(name):
-    """the CUDA library on the B200 against the reference's own D_SW / D_SW_TLM outputs"""
+    """the CUDA library on the B200 against the reference's own D_SW / D_SW_TLM / D_SW_FWD + D_SW_BWD outputs"""
     _lib_vs_reference_d_sw(False, name)
