@@ -208,5 +208,36 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_d_sw_tlm.npz"), **out)
 
 
+def dyn_core_inputs():
+    """the state and two-sided configuration of tests/test_nh.py::test_dyn_core_nh_two_sided_emu and a seeded perturbation"""
+    from common import rnd
+    from test_nh import nh_state, NHCFG
+    from test_dyn_core import CFG, TWO_SIDED
+    from test_fv_dynamics import eta
+    N, K = 12, 4
+    ak, bk = eta(K, CFG["ptop"])
+    f, rng = nh_state(N, K, 17, ak, bk)
+    cfg = dict(NHCFG); cfg.update(n_split=2, bdt=600.0, a_imp=1.0); cfg.update(TWO_SIDED)
+    act = ["u", "v", "pt", "delp", "w", "delz"]
+    d = {n: (1e-3 * np.abs(f[n]).mean() * rnd(rng, N, f[n].shape[1]) if n in act else 0 * f[n]) for n in f}
+    return N, K, ak, bk, f, d, cfg, act
+
+
+def main_dyn_core():
+    """DYN_CORE_TLM (non-hydrostatic, two acoustic sub-steps, six tiles with halo exchanges): tests/golden/ref_dyn_core_nh_tlm.npz"""
+    import ref_dyn_core as rd
+    from common import metrics
+    N, K, ak, bk, f, d, cfg, act = dyn_core_inputs()
+    ex = rd.Exchanger(N)
+    consts = dict(rdgas=cfg["rdgas"], cp_air=cfg["cp_air"], grav=cfg["grav"])
+    sp, fns, src = rd.load_reference(ex, consts, great_circle_dist, N)
+    out = rd.run(fns, ex, grid_structs, metrics(N), N, K, f, d, cfg, ak, bk)
+    np.savez_compressed(os.path.join(HERE, "ref_dyn_core_nh_tlm.npz"), **{k: v.astype(np.float64) for k, v in out.items()})
+    print("dyn_core_tlm done")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] == "d_sw":
+        main()
+    if len(sys.argv) < 2 or sys.argv[1] == "dyn_core":
+        main_dyn_core()

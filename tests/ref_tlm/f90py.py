@@ -71,7 +71,8 @@ def bind(actual, bounds, name):
     lo = []
     for d, (l, h) in enumerate(bounds):
         l = 1 if l is None else int(l)
-        if h is not None:
+        if h is not None and d < len(bounds) - 1:       # the last extent may differ (sequence association keeps the memory layout):
+            #                                                  an access beyond the actual's storage is caught by the subscript check
             assert max(int(h) - l + 1, 0) == actual.a.shape[d], ("extent mismatch for dummy %s dim %d" % (name, d + 1), (l, h), actual.a.shape)
         lo.append(l)
     return FA(actual.a, lo)
@@ -170,7 +171,8 @@ def logical_lines(text, defines=()):
             if w[0] in ("ifdef", "ifndef"):
                 stack.append((w[1] in defines) == (w[0] == "ifdef"))
             elif w[0] == "if":
-                stack.append(False)           # `#if defined(...)` blocks: none of the macros is defined in this build
+                m = re.match(r"^if\s*(!?)\s*defined\s*\(?\s*(\w+)\s*\)?\s*$", s[1:].strip())
+                stack.append(bool(m) and ((m.group(2) in defines) != bool(m.group(1))))
             elif w[0] == "else":
                 stack[-1] = not stack[-1]
             elif w[0] == "endif":
@@ -280,7 +282,8 @@ def parse_decl(line, unit_decl):
         assert m, ("declaration entity", e, line)
         d = dict(info)
         dd = m.group(2) if m.group(2) is not None else dims
-        d["dims"] = None if dd is None else [tuple(x.strip() for x in (split_top(p, ":") if ":" in p else ["1", p])) for p in split_top(dd)]
+        d["dims"] = None if dd is None else [tuple("" if x.strip() == "*" else x.strip() for x in (split_top(p, ":") if ":" in p else ["1", p]))
+                                             for p in split_top(dd)]
         d["init"] = init
         unit_decl[m.group(1)] = d
 
@@ -342,9 +345,14 @@ class Translator:
         """tokens -> python source.  callarg: a bare array name / section stays an FA object (actual argument of a user procedure)"""
         out = []
         i = 0
+        toks = self.int_div(toks)
         n = len(toks)
         while i < n:
             k, v = toks[i]
+            if k == "raw":
+                out.append(v)
+                i += 1
+                continue
             if k == "name":
                 if i + 1 < n and toks[i + 1] == ("op", "("):
                     j = self.match(toks, i + 1)
@@ -371,6 +379,24 @@ class Translator:
                 out.append({"/=": "!=", "//": "+"}.get(v, v))
             i += 1
         return "".join(out)
+
+    def int_div(self, toks):
+        """a / b with single-token operands -> _div(a, b): Fortran integer division when both are integers at run time"""
+        res = []
+        i = 0
+        isint = lambda t: t[0] == "num" and re.match(r"^\d+$", t[1])
+        simple = lambda t: (t[0] == "name" and not self.is_array(t[1])) or isint(t)
+        while i < len(toks):
+            if (i + 2 < len(toks) + 0 and toks[i + 1] == ("op", "/") and i + 2 < len(toks) and simple(toks[i]) and simple(toks[i + 2])
+                    and (i == 0 or toks[i - 1] not in (("op", "*"), ("op", "/"), ("op", "**"), ("op", ")")))
+                    and (i + 3 >= len(toks) or toks[i + 3] not in (("op", "**"), ("op", "(")))):
+                f = lambda t: pyname(t[1]) if t[0] == "name" else t[1]
+                res.append(("raw", "_div(%s, %s)" % (f(toks[i]), f(toks[i + 2]))))
+                i += 3
+            else:
+                res.append(toks[i])
+                i += 1
+        return res
 
     def match(self, toks, i):
         depth = 0
@@ -682,6 +708,9 @@ class Translator:
             d = u.decl.get(a, {})
             sig.append(pyname(a) + ("=None" if d.get("optional") else ""))
         head.append("def %s(%s):" % (pyname(u.name), ", ".join(sig)))
+        modvars = sorted(n for n in u.assigned if "%" not in n and n not in u.decl and n not in u.args and n != u.result)
+        if modvars:                      # module variables the unit sets (visible to the other units of the module)
+            head.append("    global " + ", ".join(pyname(n) for n in modvars))
         # dummies first (their bounds may use other dummies), then local arrays; parameters as plain assignments
         for n, d in u.decl.items():
             if d.get("parameter") and d.get("init") is not None:

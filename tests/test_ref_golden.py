@@ -168,3 +168,83 @@ def test_library_reproduces_reference_d_sw_tlm_emu(name):
 def test_library_reproduces_reference_d_sw_tlm_gpu(name):
     """the CUDA library on the B200 against the reference's own D_SW / D_SW_TLM / D_SW_FWD + D_SW_BWD outputs"""
     _lib_vs_reference_d_sw(False, name)
+
+
+# ---------------------------------------------------------------------------------------------------------------- DYN_CORE_TLM
+DYN_OUT = ["u", "v", "pt", "delp", "w", "delz", "mfx", "mfy", "cx", "cy"]
+
+
+def _dyn_regions(N):
+    C = (1, N, 1, N); npx = N + 1
+    return dict(u=(1, N, 1, npx), v=(1, npx, 1, N), pt=C, delp=C, w=C, delz=C, mfx=(1, npx, 1, N), mfy=(1, N, 1, npx),
+                cx=(1, npx, -2, N + 3), cy=(-2, N + 3, 1, npx))
+
+
+def test_oracle_reproduces_reference_dyn_core_tlm():
+    """DYN_CORE_TLM (model_tlmadm/dyn_core_tlm.F90:93-2600: the non-hydrostatic acoustic loop with C_SW_TLM, UPDATE_DZ_C_TLM,
+    RIEM_SOLVER_C_TLM, P_GRAD_C_TLM, D_SW_TLM, UPDATE_DZ_D_TLM, RIEM_SOLVER3_TLM, NH_P_GRAD_TLM and the per-level switch logic of both the
+    trajectory and the perturbation side), two acoustic sub-steps on all six tiles.  The reference's FMS halo exchanges were served by the
+    repository's cubed-sphere index maps at generation time (tests/golden/ref_dyn_core.py)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_ref_golden import dyn_core_inputs
+    from oracle import nh as onh
+    gold = np.load(os.path.join(GOLD, "ref_dyn_core_nh_tlm.npz"))
+    N, K, ak, bk, f, d, cfg, act = dyn_core_inputs()
+    g = ograd(N)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    def fn(*a):
+        st = {n: T(f[n]) for n in f}; st.update(dict(zip(act, a)))
+        o = onh.dyn_core_nh(st, g, cfg, ak, bk)
+        return tuple(o[k] for k in DYN_OUT)
+    out, dout = torch.func.jvp(fn, tuple(T(f[n]) for n in act), tuple(T(d[n]) for n in act))
+    regs = _dyn_regions(N)
+    errs = {}
+    for k, nm in enumerate(DYN_OUT):
+        errs[nm] = relerr(region(out[k].numpy(), *regs[nm]), region(gold[nm], *regs[nm]))
+        errs[nm + "_tl"] = relerr(region(dout[k].numpy(), *regs[nm]), region(gold[nm + "_tl"], *regs[nm]))
+        assert np.abs(region(gold[nm + "_tl"], *regs[nm])).max() > 0
+    print("dyn_core_tlm vs reference", {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 1e-12, errs          # achieved 5e-15
+
+
+def _lib_vs_reference_dyn_core(emu):
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_ref_golden import dyn_core_inputs
+    from test_dyn_core import two_sided_params
+    gold = np.load(os.path.join(GOLD, "ref_dyn_core_nh_tlm.npz"))
+    N, K, ak, bk, f, d, cfg, act = dyn_core_inputs()
+    h = handle(N, K, emu, ak, bk)
+    p = two_sided_params(cfg); p.update(do_vort_damp=int(cfg["do_vort_damp"]), hydrostatic=0)
+    key = dict(u="u_n", v="v_n", pt="pt_n", delp="delp_n", w="w_n", delz="delz_n")
+    regs = _dyn_regions(N)
+    onames = ["u", "v", "pt", "delp", "w", "delz", "mfx", "cx"]          # the module's outputs (tests/test_nh.py)
+    NX = N + 7
+    errs = {}
+    for sfx, mode in (("", fv3lm.MODE_NL), ("_tl", fv3lm.MODE_TL)):
+        traj = {n: f[n].copy() for n in f}
+        for o in onames:
+            traj[key.get(o, o)] = np.zeros((6, K, NX, NX))
+        pert = None
+        if mode == fv3lm.MODE_TL:
+            pert = {n: d[n].copy() for n in act}
+            for o in onames:
+                pert[key.get(o, o)] = np.zeros((6, K, NX, NX))
+        h.module_run("dyn_core_nh", mode, traj, pert, params=p)
+        res = traj if mode == fv3lm.MODE_NL else pert
+        for o in onames:
+            errs[o + sfx] = relerr(region(res[key.get(o, o)], *regs[o]), region(gold[o + sfx], *regs[o]))
+    print("library dyn_core_nh vs reference", {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 5e-11, errs          # the module's tolerance against the oracle (tests/test_nh.py); achieved: see the print
+
+
+def test_library_reproduces_reference_dyn_core_tlm_emu():
+    """the C-ABI library's dyn_core_nh module (host emulation) against the reference's own DYN_CORE / DYN_CORE_TLM outputs"""
+    _lib_vs_reference_dyn_core(True)
+
+
+@pytest.mark.gpu
+def test_library_reproduces_reference_dyn_core_tlm_gpu():
+    _lib_vs_reference_dyn_core(False)
