@@ -3,7 +3,7 @@ interpolation, restated from model/a2b_edge_nlm.F90:49-329 (extrap_corner :800-8
 TL model_tlmadm/a2b_edge_tlm.F90:546, AD a2b_edge_adm.F90:72).  Linear in qin: the TL is
 the same operator and the AD its transpose (obtained here by autograd).
 
-parity unpinned (no reference vectors).  Whole tile: is=js=1, ie=je=N.
+parity: pinned by tests/test_ref_tlm.py (A2B_ORD4_TLM + EXTRAP_CORNER_TLM transliterated, 1e-16) and through D_SW_TLM / NH_P_GRAD_TLM.  Whole tile: is=js=1, ie=je=N.
 """
 import numpy as np
 import torch

@@ -8,7 +8,8 @@ grid_type 0, non-nested, non-stretched, inline_q = F, d_con = 0 (no dissipative 
 do_f3d = F, no USE_COND / SW_DYNAMICS / OVERLOAD_R4.  Per-level parameters (sponge
 layers, dyn_core_nlm.F90:579-625) are passed as python lists of length K.
 
-parity unpinned (no reference vectors).
+parity: pinned by tests/test_ref_golden.py (the reference's D_SW_TLM and D_SW_FWD / D_SW_BWD executed on seeded inputs: values bit for
+bit, tangents and adjoints to 6e-15) and tests/test_ref_tlm.py (XTP_U / YTP_V / DEL6_VT_FLUX _TLM).
 """
 import torch
 from .cubed_sphere import R, NG, copy_corners, fill_corners_bgrid, fill_corners_dgrid

@@ -6,7 +6,8 @@ Configuration restated: grid_type 0, non-nested, beta = 0, d_ext = 0 (divg2 = 0)
 inline_q = F, no USE_COND.  Halo exchanges (mpp_update_domains, un-vendored FMS) are the
 index maps of oracle/cubed_sphere.py.
 
-parity unpinned (no reference vectors).
+parity: P_GRAD_C_TLM / NH_P_GRAD_TLM pinned by tests/test_ref_tlm.py, the non-hydrostatic loop by the reference's DYN_CORE_TLM executed
+(tests/test_ref_golden.py); the hydrostatic loop, del2_cubed and the heating update have no reference pin.
 """
 import numpy as np
 import torch

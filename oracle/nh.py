@@ -7,7 +7,9 @@
   (TL: model_tlmadm/nh_utils_tlm.F90, nh_core_tlm.F90; AD: nh_utils_adm.F90, nh_core_adm.F90)
 
 Configuration: a_imp = 1 (fully implicit SIM1) or 0.5 < a_imp <= 0.999 (SIM_solver, Riem_Solver3 only; scale_m = 0), p_fac = 0.05, no MOIST_CAPPA / USE_COND,
-beta = 0 (nh_p_grad), use_logp = F.   parity unpinned (no reference vectors).
+beta = 0 (nh_p_grad), use_logp = F.   parity: pinned by tests/test_ref_tlm.py (SIM1_SOLVER / RIEM_SOLVER_C / RIEM_SOLVER3 /
+UPDATE_DZ_C / UPDATE_DZ_D / EDGE_PROFILE _TLM) and by the reference's DYN_CORE_TLM executed on six tiles (tests/test_ref_golden.py: 5e-15);
+the SIM solver (a_imp < 0.999) has no reference pin.
 """
 import numpy as np
 import torch

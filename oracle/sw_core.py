@@ -9,7 +9,8 @@ restated in torch float64 (differentiable: TL = jvp, AD = vjp) from
 Whole-tile decomposition (is=js=1, ie=je=N): every tile has all four cube corners and
 all four edges.  grid_type = 0, non-nested, non-stretched.  Linear orders only (1, 2).
 
-parity unpinned (no reference vectors).  Arrays [6, K, NY, NX]; (i,j) at [..., j+2, i+2].
+parity: pinned by tests/test_ref_tlm.py (C_SW_TLM, D2A2C_VECT_TLM, DIVERGENCE_CORNER_TLM transliterated: bit for bit / 6e-15) and by the
+reference's DYN_CORE_TLM executed (tests/test_ref_golden.py).  Arrays [6, K, NY, NX]; (i,j) at [..., j+2, i+2].
 """
 import torch
 from .cubed_sphere import R, NG, fill_4corners, copy_corners, fill_corners_bgrid, fill_corners_dgrid

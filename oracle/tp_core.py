@@ -10,7 +10,8 @@ AD oracle is torch.func.vjp -- exactly what Tapenade's tangent / reverse modes c
 for the same primal.  Only the linear orders the reference TL/AD
 implement are restated (iord = 1, 2, 333; tp_core_tlm.F90:2431-2488).
 
-parity unpinned: the reference holds no test vectors for this routine.
+parity: pinned to the reference's own tangent code (tests/test_ref_tlm.py: XPPM / YPPM / FV_TP_2D / DELN_FLUX / COPY_CORNERS _TLM
+transliterated; tests/test_ref_golden.py: the reference's D_SW_TLM / D_SW_BWD / DYN_CORE_TLM executed, which call these routines).
 
 Arrays: [6, K, NY, NX], Fortran (i, j) at [..., j+2, i+2].  Whole-tile decomposition:
 is = js = 1, ie = je = N, npx = npy = N + 1.

@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE ONLY: statement-by-statement numpy transliterations of three Tapenade tangent-mode routines of the reference
+"""TEST INFRASTRUCTURE ONLY: statement-by-statement numpy transliterations of Tapenade tangent-mode routines of the reference
 (model_tlmadm/*_tlm.F90).  They pin the ORACLE (oracle/, whose TL is torch.func.jvp of a restated primal) to the reference's own
 tangent code: which variables are active, which branch is differentiated, the cube-edge special cases.  Nothing under
 fv3-jedi-linearmodel_b200/ imports this package.  The reference cannot be compiled in this image (no Fortran compiler, FMS, MPI), so
-this is the closest available reference-derived pin."""
+these and the reference-executed
+fixtures of tests/golden/ref_*.npz (transpiler f90py.py in this package, generation time only) are the reference-derived pins."""
 import numpy as np
 
 
