@@ -236,8 +236,60 @@ def main_dyn_core():
     print("dyn_core_tlm done")
 
 
+FV_ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz"]
+
+
+def fv_dynamics_inputs(K=5):
+    """state and two-sided configuration of tests/test_step_api.py::test_step_api_two_sided_emu at npz = 5 (the reference skips the vertical
+    remap for npz <= 4, fv_dynamics_tlm.F90: `IF (npz .GT. 4)`), and a seeded perturbation of the compute-domain prognostics"""
+    from test_fv_dynamics import api_state, eta, ZVIR, RD
+    from test_dyn_core import CFG, TWO_SIDED
+    N = 12
+    ak, bk = eta(K, CFG["ptop"])
+    f, _ = api_state(N, K, 41, ak, bk, True)
+    cfg = dict(CFG); cfg.update(zvir=ZVIR, hydrostatic=False, k_split=1, n_split=2, dt=900.0, hord_tr=2, rdgas=RD, grav=9.80665, p_fac=0.05)
+    cfg.update(TWO_SIDED)
+    rng = np.random.default_rng(20261019)
+    d = {}
+    for n in FV_ACT:
+        x = np.zeros_like(f[n])
+        x[..., 3:3 + N, 3:3 + N] = 1e-3 * np.abs(f[n]).mean() * rng.standard_normal((6, K, N, N))
+        d[n] = x
+    return N, K, ak, bk, f, d, cfg
+
+
+def main_fv_dynamics():
+    """FV_DYNAMICS_TLM: one whole non-hydrostatic dynamics step (acoustic loop, tracer transport, vertical remap) on six tiles:
+    tests/golden/ref_fv_dynamics_tlm.npz (compute-domain values and tangents of the ten prognostics)"""
+    import torch
+    import ref_dyn_core as rd
+    import ref_fv_dynamics as rf
+    from common import metrics, ograd
+    from oracle.dyn_core import halo_of
+    N, K, ak, bk, f, d, cfg = fv_dynamics_inputs()
+    g = ograd(N)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    st, st_tl = torch.func.jvp(lambda *a: rf.pre(dict(zip(FV_ACT, a)), g, cfg, None), tuple(T(f[n]) for n in FV_ACT), tuple(T(d[n]) for n in FV_ACT))
+    st = {k: v.numpy() for k, v in st.items()}; st_tl = {k: v.numpy() for k, v in st_tl.items()}
+    phis = halo_of(N)[0].scalar(T(f["phis"])).numpy()
+    ex = rd.Exchanger(N)
+    consts = dict(rdgas=cfg["rdgas"], cp_air=cfg["cp_air"], grav=cfg["grav"], rvgas=461.5, pi=np.pi, radius=6371.0e3, kappa=cfg["akap"],
+                  cp_vapor=4 * 461.5, hlv=2.5e6)
+    sp, fns, src = rf.load_reference(ex, consts, great_circle_dist, N)
+    out = rf.run(fns, ex, grid_structs, metrics(N), N, K, st, st_tl, phis, cfg, ak, bk)
+    key = dict(t="pt")
+    sav = {}
+    for n in FV_ACT:
+        for sfx in ("", "_tl"):
+            sav[n + sfx] = np.ascontiguousarray(out[key.get(n, n) + sfx][:, :, 3:3 + N, 3:3 + N])
+    np.savez_compressed(os.path.join(HERE, "ref_fv_dynamics_tlm.npz"), **sav)
+    print("fv_dynamics_tlm done")
+
+
 if __name__ == "__main__":
     if len(sys.argv) < 2 or sys.argv[1] == "d_sw":
         main()
     if len(sys.argv) < 2 or sys.argv[1] == "dyn_core":
         main_dyn_core()
+    if len(sys.argv) < 2 or sys.argv[1] == "fv_dynamics":
+        main_fv_dynamics()

@@ -49,10 +49,10 @@ class Exchanger:
 
     def gather(self, fas):
         a0 = fas[0].a
-        nk = a0.shape[2] if a0.ndim == 3 else 1
+        nk = int(np.prod(a0.shape[2:])) if a0.ndim >= 3 else 1
         x = torch.zeros((6, nk, self.NX, self.NX), dtype=torch.float64)
         for t, f in enumerate(fas):
-            a = f.a if f.a.ndim == 3 else f.a[:, :, None]
+            a = f.a.reshape(f.a.shape[0], f.a.shape[1], -1, order="F")
             x[t, :, :a.shape[1], :a.shape[0]] = torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0)))
         return x
 
@@ -60,7 +60,7 @@ class Exchanger:
         for t, f in enumerate(fas):
             ni, nj = f.a.shape[0], f.a.shape[1]
             v = x[t, :, :nj, :ni].numpy().transpose(2, 1, 0)
-            f.a[...] = v if f.a.ndim == 3 else v[:, :, 0]
+            f.a[...] = v.reshape(f.a.shape, order="F")
 
     def update(self, tile, fields, kind):
         """fields: this tile's FA list, [f] or [u, v] (value and tangent lists are exchanged by separate calls)"""

@@ -1,0 +1,153 @@
+"""Driver used by make_ref_golden.py: the reference's FV_DYNAMICS_TLM (model_tlmadm/fv_dynamics_tlm.F90:87: the whole dynamics step of the
+tangent-linear model -- DYN_CORE_TLM, TRACER_2D_TLM, LAGRANGIAN_TO_EULERIAN_TLM ...) on all six tiles, one thread per tile in lock step
+(ref_dyn_core.py supplies the halo-exchange and fill_corners plumbing).  Needs /root/reference: generation time only."""
+import threading
+import types
+import numpy as np
+import torch
+from ref_tlm import f90py
+from ref_tlm.f90py import FA
+import ref_dyn_core as rd
+
+REF = rd.REF
+NG = 3
+
+
+def pre(x, g, cfg, phis):
+    """the part of oracle/fv_dynamics.py::step_nl in front of fv_dynamics (fv3jedi_lm_dynamics_mod.F90:268-300: compute-domain state ->
+    FV_Atm with edge winds and pressures), as a function of the API prognostics so that its tangent is available"""
+    from oracle.fv_dynamics import compute_pressures
+    from oracle.dyn_core import halo_of
+    from oracle.cubed_sphere import R
+    from oracle.fv_mapz import put
+    N = g.N
+    halo, getb = halo_of(N)
+    C = (slice(None), slice(None), R(1, N), R(1, N))
+    dom = lambda a: put(torch.zeros_like(a), C, a[C])
+    u, v = getb(dom(x["u"]), dom(x["v"]))
+    delp = dom(x["delp"])
+    pe, pk, pkz, peln = compute_pressures(delp, cfg["ptop"], cfg["akap"])
+    st = dict(u=u, v=v, pt=dom(x["t"]), delp=delp, pe=dom(pe), pk=dom(pk), pkz=dom(pkz), peln=dom(peln), w=dom(x["w"]), delz=dom(x["delz"]))
+    for n in ("qv", "ql", "qi", "o3"):
+        st[n] = dom(x[n])
+    return st
+
+
+def more_stubs(ex):
+    def mpp_update_domains_tlm(*args, **kw):
+        domain = [a for a in args if isinstance(a, types.SimpleNamespace)][0]
+        fl = [a for a in args if isinstance(a, FA)]
+        if len(fl) == 4:
+            ex.update(domain.tile, [fl[0], fl[2]], "dgrid"); ex.update(domain.tile, [fl[1], fl[3]], "dgrid")
+        else:
+            for f in fl:
+                ex.update(domain.tile, [f], "scalar")
+
+    def mp_reduce_max(a, n=None):
+        def work(slots):
+            m = np.max(np.stack([s.a for s in slots]), axis=0)
+            for s in slots:
+                s.a[...] = m
+        ex.ls.run(threading.current_thread().tile, a, work)
+    noop = lambda *a, **k: None
+    d = dict(mpp_update_domains_tlm=mpp_update_domains_tlm, mpp_update_domains=mpp_update_domains_tlm, mp_reduce_max=mp_reduce_max,
+             start_group_halo_update=noop)
+    for n in ("mpp_error", "fill2d", "range_check", "neg_adj3", "qsmith", "fillz", "mpp_sync", "prt_maxmin", "nested_grid_bc_apply_intt",
+              "nested_grid_bc_apply_intt_tlm", "setup_nested_grid_bcs", "setup_nested_grid_bcs_tlm", "get_tracer_index", "qs_init",
+              "mpp_global_sum", "mp_reduce_sum", "fv_sat_adj", "fv_sat_adj_tlm", "get_eta_level"):
+        d[n] = noop
+    return d
+
+
+def load_reference(ex, consts, great_circle_dist, N):
+    files = [REF + x for x in ("tp_core_tlm.F90", "sw_core_tlm.F90", "a2b_edge_tlm.F90", "dyn_core_tlm.F90", "nh_core_tlm.F90", "nh_utils_tlm.F90",
+                               "fv_dynamics_tlm.F90", "fv_mapz_tlm.F90", "fv_tracer2d_tlm.F90", "fv_grid_utils_tlm.F90")]
+    extra = dict(ng=NG, great_circle_dist=great_circle_dist, fpp=types.SimpleNamespace(fpp_overload_r4=False, fpp_mapl_mode=True),
+                 do_adiabatic_init=False, model_atmos=0, fv_time=0)
+    extra.update(rd.make_stubs(ex)); extra.update(more_stubs(ex)); extra.update(consts); extra.update(rd.load_fill_corners(N))
+    return f90py.load(files, extra=extra, strict=False, skip=("great_circle_dist",))
+
+
+def run(fns, ex, grid_structs, M, N, K, st, st_tl, phis, cfg, ak, bk):
+    """st, st_tl: dict of [6, K(+1), NY, NX] arrays from pre() and its tangent.  Returns the prognostics after the step and their tangents."""
+    NX = N + 7
+    isd, ied, jsd, jed = 1 - NG, N + NG, 1 - NG, N + NG
+    A3 = lambda nk: ((isd, ied), (jsd, jed), (1, nk))
+    bnd = dict(u=((isd, ied), (jsd, jed + 1), (1, K)), v=((isd, ied + 1), (jsd, jed), (1, K)), w=A3(K), delz=A3(K), pt=A3(K), delp=A3(K),
+               q=((isd, ied), (jsd, jed), (1, K), (1, 4)), ps=((isd, ied), (jsd, jed)), pe=((0, N + 1), (1, K + 1), (0, N + 1)),
+               pk=((1, N), (1, N), (1, K + 1)), peln=((1, N), (1, K + 1), (1, N)), pkz=((1, N), (1, N), (1, K)), omga=A3(K), ua=A3(K), va=A3(K),
+               uc=((isd, ied + 1), (jsd, jed), (1, K)), vc=((isd, ied), (jsd, jed + 1), (1, K)), mfx=((1, N + 1), (1, N), (1, K)),
+               mfy=((1, N), (1, N + 1), (1, K)), cx=((1, N + 1), (jsd, jed), (1, K)), cy=((isd, ied), (1, N + 1), (1, K)))
+    res = [None] * 6
+    errors = []
+    ct = dict(cfg); ct.update(cfg.get("traj") or {})
+
+    def put3(fa, x):          # [K, NY, NX] oracle array -> FA (i, j, k) with its own bounds
+        i0, j0 = fa.lo[0], fa.lo[1]
+        ni, nj = fa.a.shape[0], fa.a.shape[1]
+        fa.a[...] = x[:, j0 + 2: j0 + 2 + nj, i0 + 2: i0 + 2 + ni].transpose(2, 1, 0)
+
+    def tile_main(t):
+        try:
+            threading.current_thread().tile = t
+            bd, gs, _ = grid_structs(M, t, N)
+            gs.area_64 = gs.area; gs.square_domain = False
+            fl = rd.flags_from_cfg(ct, N)
+            for k, v in dict(adiabatic=False, check_negative=False, consv_am=False, dnats=0, do_sat_adj=False, make_nh=False, moist_phys=True,
+                             nf_omega=1, no_dycore=False, nord_tr=0, nwat=3, p_ref=1.e5, range_warn=False, remap_option=0, rf_cutoff=0.0, tau=0.0,
+                             trdm2=0.0, z_tracer=False, kord_mt=17, kord_wz=17, kord_tm=17, kord_tr=17, k_split=cfg["k_split"],
+                             hord_tr=ct["hord_tr"]).items():
+                setattr(fl, k, v)
+            flp = rd.pert_flags_from_cfg(cfg)
+            for k, v in dict(kord_mt_pert=17, kord_wz_pert=17, kord_tm_pert=17, kord_tr_pert=17, nord_tr_pert=0, trdm2_pert=0.0,
+                             split_damp_tr=False).items():
+                setattr(flp, k, v)
+            a = {n: FA.alloc(b) for n, b in bnd.items()}; a_tl = {n: FA.alloc(b) for n, b in bnd.items()}
+            for src, dst in ((st, a), (st_tl, a_tl)):
+                for n in ("u", "v", "w", "delz", "pt", "delp"):
+                    put3(dst[n], src[n][t])
+                for iq, n in enumerate(("qv", "ql", "qi", "o3")):
+                    dst["q"].a[:, :, :, iq] = src[n][t][:, :N + 6, :N + 6].transpose(2, 1, 0)
+                dst["pe"].a[...] = src["pe"][t][:, 1 + 1: N + 2 + 2, 1 + 1: N + 2 + 2].transpose(2, 0, 1)         # (i, k, j), i, j = 0 .. N+1
+                dst["peln"].a[...] = src["peln"][t][:, 3: N + 3, 3: N + 3].transpose(2, 0, 1)
+                dst["pk"].a[...] = src["pk"][t][:, 3: N + 3, 3: N + 3].transpose(2, 1, 0)
+                dst["pkz"].a[...] = src["pkz"][t][:, 3: N + 3, 3: N + 3].transpose(2, 1, 0)
+            fphis = FA(np.ascontiguousarray(phis[t, 0][:N + 6, :N + 6].T), (isd, jsd))
+            q_con = FA.alloc(A3(K)); ze0 = FA.alloc(((1, 1), (1, 1), (1, 1)))
+            fak = FA(np.array(ak, dtype=float), (1,)); fbk = FA(np.array(bk, dtype=float), (1,))
+            domain = types.SimpleNamespace(tile=t)
+            nest = types.SimpleNamespace(nest_timestep=0, tracer_nest_timestep=0, child_grids=[False], nested=False, nestbctype=0, pt_bc=None)
+            idiag = types.SimpleNamespace(id_ws=0, id_zratio=0, id_aam=0, id_amdt=0, id_divg=0, id_mdt=0, id_te=0, zxg=None)
+            P = lambda n: (a[n], a_tl[n])
+            fns["fv_dynamics_tlm"](N + 1, N + 1, K, 4, NG, cfg["dt"], 0.0, False, False, cfg["akap"], cfg["cp_air"], cfg["zvir"], cfg["ptop"], 0, 4,
+                                   cfg["n_split"], cfg.get("q_split", 1), *P("u"), *P("v"), *P("w"), *P("delz"), False, *P("pt"), *P("delp"), *P("q"),
+                                   *P("ps"), *P("pe"), *P("pk"), *P("peln"), *P("pkz"), fphis, q_con, *P("omga"), *P("ua"), *P("va"), *P("uc"),
+                                   *P("vc"), fak, fbk, *P("mfx"), *P("mfy"), *P("cx"), *P("cy"), ze0, False, gs, fl, flp, nest, idiag, bd, None,
+                                   domain)
+            res[t] = (a, a_tl)
+        except BaseException:
+            import traceback
+            errors.append((t, traceback.format_exc()))
+            ex.ls.barrier.abort()
+    th = [threading.Thread(target=tile_main, args=(t,)) for t in range(6)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    if errors:
+        raise RuntimeError("tile %d failed:\n%s" % (errors[0][0], errors[0][1]))
+    out = {}
+    for sfx, idx in (("", 0), ("_tl", 1)):
+        for n in ("u", "v", "w", "delz", "pt", "delp"):
+            x = np.zeros((6, K, NX, NX))
+            for t in range(6):
+                fa = res[t][idx][n]
+                ni, nj = fa.a.shape[0], fa.a.shape[1]
+                x[t, :, :nj, :ni] = fa.a.transpose(2, 1, 0)
+            out[n + sfx] = x
+        for iq, n in enumerate(("qv", "ql", "qi", "o3")):
+            x = np.zeros((6, K, NX, NX))
+            for t in range(6):
+                x[t, :, :N + 6, :N + 6] = res[t][idx]["q"].a[:, :, :, iq].transpose(2, 1, 0)
+            out[n + sfx] = x
+    return out

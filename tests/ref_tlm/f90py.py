@@ -110,7 +110,7 @@ def f_div(a, b):
     return a / b
 
 
-RUNTIME = dict(_stack=STACK, _push=f_push, _pop=f_pop, _Goto=Goto, FA=FA, _bind=bind, _alloc=FA.alloc, np=np, _sign=f_sign, _div=f_div, _real=f_real, r_grid=8,
+RUNTIME = dict(_any=lambda x: bool(np.any(x.a if isinstance(x, FA) else x)), _stack=STACK, _push=f_push, _pop=f_pop, _Goto=Goto, FA=FA, _bind=bind, _alloc=FA.alloc, np=np, _sign=f_sign, _div=f_div, _real=f_real, r_grid=8,
                log=np.log, exp=np.exp, sqrt=np.sqrt, sin=np.sin, cos=np.cos, tan=np.tan, atan=np.arctan, asin=np.arcsin, acos=np.arccos,
                tanh=np.tanh, atan2=np.arctan2)
 
@@ -129,7 +129,7 @@ DOTOPS = {".and.": " and ", ".or.": " or ", ".not.": " not ", ".eqv.": "==", ".n
           ".le.": "<=", ".gt.": ">", ".ge.": ">=", ".true.": "True", ".false.": "False"}
 INTRINSICS = {"abs": "abs", "max": "max", "min": "min", "log": "log", "exp": "exp", "sqrt": "sqrt", "sin": "sin", "cos": "cos", "tan": "tan",
               "atan": "atan", "asin": "asin", "acos": "acos", "tanh": "tanh", "atan2": "atan2", "sign": "_sign", "real": "_real", "dble": "_real",
-              "float": "_real", "int": "int", "nint": "round", "mod": "_mod"}
+              "float": "_real", "any": "_any", "int": "int", "nint": "round", "mod": "_mod"}
 
 
 def tokenize(s):
@@ -243,6 +243,7 @@ class Unit:
         self.body = []
         self.assigned = set()
         self.out_scalars = []     # dummy scalars the unit assigns (returned to the caller, in this order)
+        self.do_labels = []
 
 
 DECL = re.compile(r"^(real|integer|logical|character|type|double\s*precision|complex)\b")
@@ -319,7 +320,17 @@ def parse_module(text, defines=()):
         if DECL.match(ln) and ("::" in ln or re.match(r"^(real|integer|logical|double\s*precision)\s*(\*\s*\d+)?\s+[a-z_]", ln)):
             parse_decl(ln, cur.decl)
             continue
+        # labelled DO (`do 555 k = 1, kn` ... `555 continue`): rewritten as a block DO closed right after the labelled statement
+        m = re.match(r"^do\s+(\d+)\s*,?\s*(\w+\s*=.*)$", ln)
+        if m:
+            cur.do_labels.append(m.group(1))
+            cur.body.append("do " + m.group(2))
+            continue
         cur.body.append(ln)
+        m = re.match(r"^(\d+)\s+", ln)
+        while m and cur.do_labels and cur.do_labels[-1] == m.group(1):
+            cur.do_labels.pop()
+            cur.body.append("end do")
     return mod_decl, units
 
 # ---------------------------------------------------------------------------------------------------------------- translation
@@ -704,9 +715,11 @@ class Translator:
         assert ind == 1, ("unbalanced blocks in " + u.name, ind)
         head = []
         sig = []
+        seen_opt = False
         for a in u.args:
             d = u.decl.get(a, {})
-            sig.append(pyname(a) + ("=None" if d.get("optional") else ""))
+            seen_opt = seen_opt or bool(d.get("optional"))
+            sig.append(pyname(a) + ("=None" if seen_opt else ""))
         head.append("def %s(%s):" % (pyname(u.name), ", ".join(sig)))
         modvars = sorted(n for n in u.assigned if "%" not in n and n not in u.decl and n not in u.args and n != u.result)
         if modvars:                      # module variables the unit sets (visible to the other units of the module)
@@ -790,7 +803,7 @@ def analyse_outs(units):
                         changed = True
 
 
-def load(paths, extra=None, defines=(), only=None, strict=True):
+def load(paths, extra=None, defines=(), only=None, strict=True, skip=()):
     """transpile the given Fortran files; -> dict module-path -> namespace (every unit of every file callable from each namespace).
     extra: names injected into every namespace (module variables, constants of modules outside the tree, stubs of external procedures).
     only: optional set of unit names to translate (the others are skipped: they may use unsupported constructs)."""
@@ -801,7 +814,7 @@ def load(paths, extra=None, defines=(), only=None, strict=True):
             mod_decl, us = parse_module(f.read(), defines)
         parsed[p] = (mod_decl, us)
         for u in us:
-            if only is None or u.name in only:
+            if (only is None or u.name in only) and u.name not in skip:
                 units.setdefault(u.name, u)
     analyse_outs(units)
     spaces = {}
@@ -814,7 +827,10 @@ def load(paths, extra=None, defines=(), only=None, strict=True):
         tr = Translator(dummy, {}, units)
         for n, d in mod_decl.items():
             if d.get("init") is not None and d["dims"] is None:
-                exec("%s = %s" % (pyname(n), tr.expr(tokenize(d["init"]))), ns)
+                try:
+                    exec("%s = %s" % (pyname(n), tr.expr(tokenize(d["init"]))), ns)
+                except (NameError, AssertionError):      # a constant of a module outside the tree: a unit that reads it fails by name
+                    pass
         spaces[p] = ns
     src = {}
     for p, (mod_decl, us) in parsed.items():

@@ -248,3 +248,72 @@ def test_library_reproduces_reference_dyn_core_tlm_emu():
 @pytest.mark.gpu
 def test_library_reproduces_reference_dyn_core_tlm_gpu():
     _lib_vs_reference_dyn_core(False)
+
+
+# ---------------------------------------------------------------------------------------------------------------- FV_DYNAMICS_TLM (whole step)
+def test_oracle_reproduces_reference_fv_dynamics_tlm():
+    """FV_DYNAMICS_TLM (model_tlmadm/fv_dynamics_tlm.F90:87-995: DYN_CORE_TLM, TRACER_2D_TLM, LAGRANGIAN_TO_EULERIAN_TLM with its map
+    routines, the pt <-> T conversions; two-sided switches, npz = 5, n_split = 2) on all six tiles: the whole dynamics step of the
+    tangent-linear model, i.e. the path the benchmark times, against oracle/fv_dynamics.py::step_nl and its jvp."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_ref_golden import fv_dynamics_inputs, FV_ACT
+    from oracle import fv_dynamics as ofv
+    gold = np.load(os.path.join(GOLD, "ref_fv_dynamics_tlm.npz"))
+    N, K, ak, bk, f, d, cfg = fv_dynamics_inputs()
+    g = ograd(N)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    phis = T(f["phis"])
+
+    def fn(*a):
+        o = ofv.step_nl(dict(zip(FV_ACT, a)), g, ak, bk, cfg, phis)
+        return tuple(o[k] for k in FV_ACT)
+    out, dout = torch.func.jvp(fn, tuple(T(f[n]) for n in FV_ACT), tuple(T(d[n]) for n in FV_ACT))
+    errs = {}
+    for k, n in enumerate(FV_ACT):
+        errs[n] = relerr(region(out[k].numpy(), 1, N, 1, N), gold[n])
+        errs[n + "_tl"] = relerr(region(dout[k].numpy(), 1, N, 1, N), gold[n + "_tl"])
+        assert np.abs(gold[n + "_tl"]).max() > 0
+    print("fv_dynamics_tlm vs reference", {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 1e-11, errs          # achieved 2e-13 (w), others <= 5e-15
+
+
+def _api_vs_reference_fv_dynamics(emu):
+    """the PUBLIC API (fv3lm_create / traj_set / step_nl / step_tl through the C ABI, what the reference's fv3jedi_lm_dynamics_mod would call)
+    against the reference's FV_DYNAMICS / FV_DYNAMICS_TLM outputs"""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_ref_golden import fv_dynamics_inputs, FV_ACT
+    from test_dyn_core import CFG, TWO_SIDED
+    from test_fv_dynamics import ZVIR
+    from oracle.cubed_sphere import R
+    gold = np.load(os.path.join(GOLD, "ref_fv_dynamics_tlm.npz"))
+    N, K, ak, bk, f, d, cfg = fv_dynamics_inputs()
+    kw = dict(n_split=2, k_split=1, dt=900.0, ptop=CFG["ptop"], d2_bg_k1=CFG["d2_bg_k1"], d2_bg_k2=CFG["d2_bg_k2"], kappa=CFG["akap"],
+              cp=CFG["cp_air"], zvir=ZVIR, hydrostatic=0)
+    for k_, v_ in TWO_SIDED.items():
+        kw[k_] = (tuple(sorted(v_.items())) if k_ == "traj" else int(v_) if isinstance(v_, bool) else v_)
+    h = handle(N, K, emu, ak, bk, **kw)
+    C = (slice(None), slice(None), R(1, N), R(1, N))
+    comp = {k: np.ascontiguousarray(f[k][C]) for k in FV_ACT}
+    h.set_phis(np.ascontiguousarray(f["phis"][:, 0][:, R(1, N), R(1, N)]))
+    h.traj_set(0, comp)
+    h.step_nl(0, 1)
+    out = {k: np.zeros_like(comp[k]) for k in FV_ACT}
+    h.traj_get(1, out)
+    mdx = {k: np.ascontiguousarray(d[k][C]) for k in FV_ACT}
+    h.step_tl(0, mdx)
+    errs = {}
+    for n in FV_ACT:
+        errs[n] = relerr(out[n], gold[n]); errs[n + "_tl"] = relerr(mdx[n], gold[n + "_tl"])
+    print("public API step_nl / step_tl vs reference", {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 3e-11, errs          # the step's tolerance against the oracle (tests/test_step_api.py)
+
+
+def test_api_reproduces_reference_fv_dynamics_tlm_emu():
+    _api_vs_reference_fv_dynamics(True)
+
+
+@pytest.mark.gpu
+def test_api_reproduces_reference_fv_dynamics_tlm_gpu():
+    _api_vs_reference_fv_dynamics(False)
