@@ -56,8 +56,8 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
     throw std::runtime_error("fv3lm_create: a_imp <= 0.5 selects the RIM_2D / SIM3 solvers (model/nh_core_nlm.F90:136-146), which are not built; use 0.5 < a_imp <= 1");
   if (cfg->npx < 9) throw std::runtime_error("fv3lm_create: need at least 8 cells per tile edge");
   // switches whose paths are not built change the dynamics in the reference: refuse them rather than ignore them
-  if (cfg->beta != 0.0)
-    throw std::runtime_error("fv3lm_create: beta != 0 selects split_p_grad / grad1_p_update (model/dyn_core_nlm.F90:865-876), which are not built");
+  if (cfg->beta < 0.0 || cfg->beta >= 1.0)
+    throw std::runtime_error("fv3lm_create: beta must be in [0, 1): beta > 0 selects grad1_p_update / split_p_grad, beta < -0.1 the one_grad_p branch of the non-hydrostatic core (model/dyn_core_nlm.F90:865-877), which is not built");
   if (cfg->d_ext > 0.0)
     throw std::runtime_error("fv3lm_create: d_ext > 0 switches on the external-mode divergence damping (model/dyn_core_nlm.F90:642-720), which is not built");
   int device = -1;

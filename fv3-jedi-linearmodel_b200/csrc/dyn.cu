@@ -118,7 +118,7 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, co
   DswParams dpp; const bool two = level_params_pert(c, K, dpp); dpp.dt = dt;
   DynOut o;
   int u = s.u, v = s.v, pt = s.pt, delp = s.delp, w = s.w;
-  int mfx = -1, mfy = -1, cx = -1, cy = -1, heat = -1;
+  int mfx = -1, mfy = -1, cx = -1, cy = -1, heat = -1, du_prev = -1, dv_prev = -1;
   for (int it = 1; it <= c.n_split; it++) {
     const std::string tg = tag + ".it" + std::to_string(it);
     P.mark_segment();
@@ -153,6 +153,13 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, co
     o.pk = pkd;
     int pkb = build_a2b_ord4(P, mo, pkd, K + 1, tg + ".a2b_pk"), gzb = build_a2b_ord4(P, mo, gzd, K + 1, tg + ".a2b_gz");
     u = P.val(tg + ".u", K); v = P.val(tg + ".v", K);
+    if (c.beta > 0.0) {   // grad1_p_update (:865-866); beta_d = 0 on the first sub-step (:373-375), du / dv go to the next one
+      int dun = P.val(tg + ".du", K), dvn = P.val(tg + ".dv", K);
+      const bool first = it == 1;
+      P.add<S_gradp_beta>("grad1_p_update", {dt, pow(c.ptop, c.akap), first ? 0.0 : c.beta, 0, first ? 1 : 0},
+                          {ds.u, ds.v, pkb, gzb, pkb, pkb, first ? ds.u : du_prev, first ? ds.v : dv_prev}, {u, v, dun, dvn}, K);
+      du_prev = dun; dv_prev = dvn;
+    } else
     P.add<S_gradp>("one_grad_p", {dt, pow(c.ptop, c.akap), 0}, {ds.u, ds.v, pkb, gzb, pkb, pkb}, {u, v}, K);
     if (it == c.n_split) add_patch(P, "get_boundary_uv", &mo.gb_dgrid, {u, v});
     else add_patch(P, "halo_uv", &mo.h_dgrid, {u, v});
@@ -181,6 +188,7 @@ void dyn_config_from(DynConfig& c, const ModuleParams& prm) {
   // 0 in the config = "not set": the library defaults (fully implicit SIM1 solver, p_fac = 0.05)
   c.a_imp = prm.get("a_imp", f->a_imp != 0.0 ? f->a_imp : 1.0);
   c.p_fac = prm.get("p_fac", f->p_fac != 0.0 ? f->p_fac : 0.05);
+  c.beta = prm.get("beta", f->beta);
   c.d_con = prm.get("d_con", f->d_con);
   c.q_split = prm.geti("q_split", f->q_split_dynamic ? 0 : 1);
   c.q_split_max = prm.geti("q_split_max", f->q_split_max > 0 ? f->q_split_max : 3);

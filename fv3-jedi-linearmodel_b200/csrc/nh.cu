@@ -137,7 +137,7 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
   const LevD dp0 = dp_ref_of(ak, bk, K);
   DynOut o;
   int u = s.u, v = s.v, pt = s.pt, delp = s.delp, w = s.w, delz = s.delz;
-  int mfx = -1, mfy = -1, cx = -1, cy = -1, heat = -1;
+  int mfx = -1, mfy = -1, cx = -1, cy = -1, heat = -1, du_prev = -1, dv_prev = -1;
   int zs = P.val(tag + ".zs", 1);
   P.add<S_scale>("zs", {1.0 / c.grav, ng}, {s.phis}, {zs}, 1);
   int zh = -1, ws_d = -1;
@@ -198,6 +198,13 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
     int ppb = build_a2b_ord4(P, mo, ppe, K + 1, tg + ".a2b_pp"), pkb = build_a2b_ord4(P, mo, pk3, K + 1, tg + ".a2b_pk");
     int gzb = build_a2b_ord4(P, mo, gzg, K + 1, tg + ".a2b_gz"), dpb = build_a2b_ord4(P, mo, delp, K, tg + ".a2b_dp");
     u = P.val(tg + ".u", K); v = P.val(tg + ".v", K);
+    if (c.beta > 0.0) {   // split_p_grad (model/dyn_core_nlm.F90:874-875); beta_d = 0 on the first sub-step (:373-375)
+      int dun = P.val(tg + ".du", K), dvn = P.val(tg + ".dv", K);
+      const bool first = it == 1;
+      P.add<S_gradp_beta>("split_p_grad", {dt, pow(c.ptop, c.akap), first ? 0.0 : c.beta, 1, first ? 1 : 0},
+                          {ds.u, ds.v, pkb, gzb, ppb, dpb, first ? ds.u : du_prev, first ? ds.v : dv_prev}, {u, v, dun, dvn}, K);
+      du_prev = dun; dv_prev = dvn;
+    } else
     P.add<S_gradp>("nh_p_grad", {dt, pow(c.ptop, c.akap), 1}, {ds.u, ds.v, pkb, gzb, ppb, dpb}, {u, v}, K);
     if (it == c.n_split) add_patch(P, "get_boundary_uv", &mo.gb_dgrid, {u, v});
     else add_patch(P, "halo_uv", &mo.h_dgrid, {u, v});

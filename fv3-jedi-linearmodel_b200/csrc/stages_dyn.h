@@ -232,6 +232,55 @@ struct S_gradp {
   }
 };
 
+// split_p_grad (model/dyn_core_nlm.F90:1531-1643, TL model_tlmadm/dyn_core_tlm.F90:3592-3757) and grad1_p_update (:1781-1872, TL :4163-4293;
+// d_ext = 0, so divg2 = 0 :726): the pressure gradient with the hydrostatic part of the previous acoustic sub-step blended in,
+//   u <- u + beta du_prev ;  du = dt (A B + C D) / den ;  u <- (u + alpha du [+ dn]) rdx,   alpha = 1 - beta
+// beta is the caller's beta_d (0 on the first sub-step, :373-375, where du_prev is not read).  The geometry is S_gradp's.
+// in: u v pkb gzb ppb dpb du_prev dv_prev ; out: u_new v_new du dv
+struct S_gradp_beta {
+  static constexpr int NI = 8, NO = 4;
+  struct P { double dt, top, beta; int nonhydro, first; };
+  static constexpr int NT = 25;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0},
+                                   {2, 0, 0, 0}, {2, 1, 0, 0}, {2, 0, 1, 0}, {2, 0, 0, 1}, {2, 1, 0, 1}, {2, 0, 1, 1},
+                                   {3, 0, 0, 0}, {3, 1, 0, 0}, {3, 0, 1, 0}, {3, 0, 0, 1}, {3, 1, 0, 1}, {3, 0, 1, 1},
+                                   {4, 0, 0, 0}, {4, 1, 0, 0}, {4, 0, 1, 0}, {4, 0, 0, 1}, {4, 1, 0, 1}, {4, 0, 1, 1},
+                                   {5, 0, 0, 0}, {5, 1, 0, 0}, {5, 0, 1, 0}, {6, 0, 0, 0}, {7, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    const double alpha = 1.0 - p.beta;
+    auto PK = [&](int di, int dj, int dk) -> T { return (x.kk + dk == 0) ? T(p.top) : x.in(2, di, dj, dk); };
+    auto PP = [&](int di, int dj, int dk) -> T { return (x.kk + dk == 0) ? T(0.0) : x.in(4, di, dj, dk); };
+    auto GZ = [&](int di, int dj, int dk) -> T { return x.in(3, di, dj, dk); };
+    auto wk = [&](int di, int dj) -> T { return PK(di, dj, 1) - PK(di, dj, 0); };
+    if (x.in_rect(g.is, g.ie, g.js, g.je + 1)) {
+      T ub = x.in(0);
+      if (!p.first) ub = ub + p.beta * x.in(6);
+      T du = p.dt / (wk(0, 0) + wk(1, 0)) * ((GZ(0, 0, 1) - GZ(1, 0, 0)) * (PK(1, 0, 1) - PK(0, 0, 0)) + (GZ(0, 0, 0) - GZ(1, 0, 1)) * (PK(0, 0, 1) - PK(1, 0, 0)));
+      x.out(2, du);
+      if (p.nonhydro) {
+        T dn = p.dt / (x.in(5, 0, 0) + x.in(5, 1, 0)) * ((GZ(0, 0, 1) - GZ(1, 0, 0)) * (PP(1, 0, 1) - PP(0, 0, 0)) + (GZ(0, 0, 0) - GZ(1, 0, 1)) * (PP(0, 0, 1) - PP(1, 0, 0)));
+        x.out(0, (ub + alpha * du + dn) * x.M(x.m.rdx));
+      } else {
+        x.out(0, (ub + alpha * du) * x.M(x.m.rdx));
+      }
+    }
+    if (x.in_rect(g.is, g.ie + 1, g.js, g.je)) {
+      T vb = x.in(1);
+      if (!p.first) vb = vb + p.beta * x.in(7);
+      T dv = p.dt / (wk(0, 0) + wk(0, 1)) * ((GZ(0, 0, 1) - GZ(0, 1, 0)) * (PK(0, 1, 1) - PK(0, 0, 0)) + (GZ(0, 0, 0) - GZ(0, 1, 1)) * (PK(0, 0, 1) - PK(0, 1, 0)));
+      x.out(3, dv);
+      if (p.nonhydro) {
+        T dn = p.dt / (x.in(5, 0, 0) + x.in(5, 0, 1)) * ((GZ(0, 0, 1) - GZ(0, 1, 0)) * (PP(0, 1, 1) - PP(0, 0, 0)) + (GZ(0, 0, 0) - GZ(0, 1, 1)) * (PP(0, 0, 1) - PP(0, 1, 0)));
+        x.out(1, (vb + alpha * dv + dn) * x.M(x.m.rdy));
+      } else {
+        x.out(1, (vb + alpha * dv) * x.M(x.m.rdy));
+      }
+    }
+  }
+};
+
 // out = a + b on a rectangle (flux / Courant-number accumulators, dyn_core/d_sw :913-931)
 struct S_add2 {
   static constexpr int NI = 2, NO = 1;

@@ -92,7 +92,7 @@ def default_config(N, npz, **kw):
     cfg.n_sponge = 0; cfg.nord = 1
     cfg.dt = 900.0; cfg.ptop = 1.0
     cfg.dddmp = 0.2; cfg.d2_bg = 0.015; cfg.d4_bg = 0.15; cfg.vtdm4 = 0.0005
-    cfg.d2_bg_k1 = 4.0; cfg.d2_bg_k2 = 2.0; cfg.d_ext = 0.0; cfg.beta = 0.0     # d_ext > 0 / beta > 0 select paths that are not built: fv3lm_create refuses them
+    cfg.d2_bg_k1 = 4.0; cfg.d2_bg_k2 = 2.0; cfg.d_ext = 0.0; cfg.beta = 0.0     # d_ext > 0 selects a path that is not built: fv3lm_create refuses it
     cfg.rdgas = rdgas; cfg.cp = 3.5 * rdgas; cfg.kappa = rdgas / (3.5 * rdgas)
     cfg.zvir = (8314.47 / 18.015) / rdgas - 1.0; cfg.grav = 9.80665
     cfg.do_vort_damp = 1

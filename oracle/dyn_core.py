@@ -103,8 +103,11 @@ def p_grad_c(dt2, delpc, pkc, gz, uc, vc, g, hydrostatic):
     return put(uc, is_, ie + 1, js, je, ucn), put(vc, is_, ie, js, je + 1, vcn)
 
 
-def grad_p(u, v, pk, gz, g, dt, top_value, pp=None, delp=None):
-    """one_grad_p (:1645, hydrostatic, d_ext = 0) when pp is None, nh_p_grad (:1431) otherwise"""
+def grad_p(u, v, pk, gz, g, dt, top_value, pp=None, delp=None, beta=None, du_dv=None):
+    """one_grad_p (:1645, hydrostatic, d_ext = 0) when pp is None, nh_p_grad (:1431) otherwise.
+    beta is not None (the caller's beta_d, 0 on the first acoustic sub-step, dyn_core :373-375): grad1_p_update (:1781-1872, d_ext = 0 so
+    divg2 = 0 :726) / split_p_grad (:1531-1643): u += beta * du_prev, then the hydrostatic part enters with alpha = 1 - beta and is
+    handed to the next sub-step; du_dv = (du_prev, dv_prev) on the output rectangles or None; returns (u, v, (du, dv))."""
     N = g.N
     is_, ie, js, je = 1, N, 1, N
     pkb = a2b_ord4(pk, g)
@@ -120,21 +123,32 @@ def grad_p(u, v, pk, gz, g, dt, top_value, pp=None, delp=None):
                 (S(lo(gzb), i0, i1, j0, j1) - S(hi(gzb), i0 + di, i1 + di, j0 + dj, j1 + dj)) * (S(hi(q), i0, i1, j0, j1) - S(lo(q), i0 + di, i1 + di, j0 + dj, j1 + dj)))
     i0, i1, j0, j1 = is_, ie, js, je + 1
     du = dt / (S(wk, i0, i1, j0, j1) + S(wk, i0 + 1, i1 + 1, j0, j1)) * lin(pkb, i0, i1, j0, j1, 1, 0)
-    if pp is None:
+    if beta is not None:
+        alpha = 1.0 - beta
+        ub = S(u, i0, i1, j0, j1) + (beta * du_dv[0] if du_dv is not None else 0.0)
+    if beta is not None and pp is None:
+        un = (ub + alpha * du) * S(g.rdx, i0, i1, j0, j1)
+    elif pp is None:
         un = S(g.rdx, i0, i1, j0, j1) * (0.0 + S(u, i0, i1, j0, j1) + du)
     else:
         ppb = a2b_ord4(pp, g)
         ppb = torch.cat([torch.zeros_like(ppb[:, :1]), ppb[:, 1:]], dim=1)
         wk1 = a2b_ord4(delp, g)
         dn = dt / (S(wk1, i0, i1, j0, j1) + S(wk1, i0 + 1, i1 + 1, j0, j1)) * lin(ppb, i0, i1, j0, j1, 1, 0)
-        un = (S(u, i0, i1, j0, j1) + du + dn) * S(g.rdx, i0, i1, j0, j1)
+        un = ((S(u, i0, i1, j0, j1) + du + dn) if beta is None else (ub + alpha * du + dn)) * S(g.rdx, i0, i1, j0, j1)
     i0, i1, j0, j1 = is_, ie + 1, js, je
     dv = dt / (S(wk, i0, i1, j0, j1) + S(wk, i0, i1, j0 + 1, j1 + 1)) * lin(pkb, i0, i1, j0, j1, 0, 1)
-    if pp is None:
+    if beta is not None:
+        vb = S(v, i0, i1, j0, j1) + (beta * du_dv[1] if du_dv is not None else 0.0)
+    if beta is not None and pp is None:
+        vn = (vb + alpha * dv) * S(g.rdy, i0, i1, j0, j1)
+    elif pp is None:
         vn = S(g.rdy, i0, i1, j0, j1) * (0.0 + S(v, i0, i1, j0, j1) + dv)
     else:
         dn = dt / (S(wk1, i0, i1, j0, j1) + S(wk1, i0, i1, j0 + 1, j1 + 1)) * lin(ppb, i0, i1, j0, j1, 0, 1)
-        vn = (S(v, i0, i1, j0, j1) + dv + dn) * S(g.rdy, i0, i1, j0, j1)
+        vn = ((S(v, i0, i1, j0, j1) + dv + dn) if beta is None else (vb + alpha * dv + dn)) * S(g.rdy, i0, i1, j0, j1)
+    if beta is not None:
+        return put(u, is_, ie, js, je + 1, un), put(v, is_, ie + 1, js, je, vn), (du, dv)
     return put(u, is_, ie, js, je + 1, un), put(v, is_, ie + 1, js, je, vn)
 
 
@@ -322,7 +336,10 @@ def dyn_core_hydro(st, g, cfg):
             heat = d["heat"] if heat is None else heat + d["heat"]
         delp = halo.scalar(d["delp"]); pt = halo.scalar(d["pt"])
         pkc, gz, pe, peln, pkz = geopk(delp, pt, hs, g, ptop, akap, cp_air, 2, False)
-        u, v = grad_p(d["u"], d["v"], pkc, gz, g, dt, ptop ** akap)
+        if cfg.get("beta", 0.0) > 0.0:      # grad1_p_update (:865-866), beta_d = 0 on the first sub-step (:373-375)
+            u, v, du_dv = grad_p(d["u"], d["v"], pkc, gz, g, dt, ptop ** akap, beta=0.0 if it == 1 else cfg["beta"], du_dv=None if it == 1 else du_dv)
+        else:
+            u, v = grad_p(d["u"], d["v"], pkc, gz, g, dt, ptop ** akap)
         if it == n_split:
             u, v = getb(u, v)
         else:

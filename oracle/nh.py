@@ -354,7 +354,11 @@ def dyn_core_nh(st, g, cfg, ak, bk, first_call=True):
         # pk3 (interior from the solver, halo ring from pk3_halo) = exp(akap log(ptop + cumsum(delp))) everywhere
         pk3, _, pe, peln, _ = geopk(delp, pt, hs, g, ptop, akap, cfg["cp_air"], 2, True)
         gz = zh * grav
-        u, v = grad_p(d["u"], d["v"], pk3, gz, g, dt, ptop ** akap, pp=pkc, delp=delp)
+        if cfg.get("beta", 0.0) > 0.0:      # split_p_grad (dyn_core_nlm.F90:874-875), beta_d = 0 on the first sub-step (:373-375)
+            u, v, du_dv = grad_p(d["u"], d["v"], pk3, gz, g, dt, ptop ** akap, pp=pkc, delp=delp, beta=0.0 if it == 1 else cfg["beta"],
+                                 du_dv=None if it == 1 else du_dv)
+        else:
+            u, v = grad_p(d["u"], d["v"], pk3, gz, g, dt, ptop ** akap, pp=pkc, delp=delp)
         if it == n_split:
             u, v = getb(u, v)
         else:

@@ -139,7 +139,7 @@ def d_sw_adjoint_case(fns, M, N, t, f, seed, prm, dt, hydrostatic, d_con=0.0):
           p["dddmp"], p["d2_bg"], p["d4_bg"], p["damp_v"], p["damp_w"], p["damp_t"], d_con, hydrostatic, gs, fl, bd,
           p["hord_tr"], p["hord_mt"], p["hord_vt"], p["hord_tm"], p["hord_dp"], False, p["nord"], p["nord_v"], p["nord_w"], p["nord_t"],
           p["dddmp"], p["d2_bg"], p["d4_bg"], p["damp_v"], p["damp_w"], p["damp_t"])
-    stack = f90py.RUNTIME["_stack"]
+    stack = f90py.stack()
     assert not stack
     fns["d_sw_fwd"](o["delpc"], a["delp"], o["ptc"], a["pt"], a["u"], a["v"], a["w"], a["uc"], a["vc"], a["ua"], a["va"], a["divg_d"],
                     o["xflux"], o["yflux"], o["cx"], o["cy"], o["crx_adv"], o["cry_adv"], o["xfx_adv"], o["yfx_adv"], o["q_con"], o["z_rat"],
@@ -208,8 +208,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_d_sw_tlm.npz"), **out)
 
 
-def dyn_core_inputs():
-    """the state and two-sided configuration of tests/test_nh.py::test_dyn_core_nh_two_sided_emu and a seeded perturbation"""
+def dyn_core_inputs(beta=0.0):
+    """the state and two-sided configuration of tests/test_nh.py::test_dyn_core_nh_two_sided_emu and a seeded perturbation;
+    beta > 0: three acoustic sub-steps with split_p_grad (the blended gradient du / dv is handed on twice)"""
     from common import rnd
     from test_nh import nh_state, NHCFG
     from test_dyn_core import CFG, TWO_SIDED
@@ -218,22 +219,26 @@ def dyn_core_inputs():
     ak, bk = eta(K, CFG["ptop"])
     f, rng = nh_state(N, K, 17, ak, bk)
     cfg = dict(NHCFG); cfg.update(n_split=2, bdt=600.0, a_imp=1.0); cfg.update(TWO_SIDED)
+    if beta > 0.0:
+        cfg.update(n_split=3, beta=beta)
     act = ["u", "v", "pt", "delp", "w", "delz"]
     d = {n: (1e-3 * np.abs(f[n]).mean() * rnd(rng, N, f[n].shape[1]) if n in act else 0 * f[n]) for n in f}
     return N, K, ak, bk, f, d, cfg, act
 
 
-def main_dyn_core():
-    """DYN_CORE_TLM (non-hydrostatic, two acoustic sub-steps, six tiles with halo exchanges): tests/golden/ref_dyn_core_nh_tlm.npz"""
+def main_dyn_core(beta=0.0):
+    """DYN_CORE_TLM (non-hydrostatic, two acoustic sub-steps, six tiles with halo exchanges): tests/golden/ref_dyn_core_nh_tlm.npz;
+    beta = 0.4 (SPLIT_P_GRAD_TLM instead of NH_P_GRAD_TLM, three sub-steps): tests/golden/ref_dyn_core_nh_beta_tlm.npz"""
     import ref_dyn_core as rd
     from common import metrics
-    N, K, ak, bk, f, d, cfg, act = dyn_core_inputs()
+    N, K, ak, bk, f, d, cfg, act = dyn_core_inputs(beta)
     ex = rd.Exchanger(N)
     consts = dict(rdgas=cfg["rdgas"], cp_air=cfg["cp_air"], grav=cfg["grav"])
     sp, fns, src = rd.load_reference(ex, consts, great_circle_dist, N)
     out = rd.run(fns, ex, grid_structs, metrics(N), N, K, f, d, cfg, ak, bk)
-    np.savez_compressed(os.path.join(HERE, "ref_dyn_core_nh_tlm.npz"), **{k: v.astype(np.float64) for k, v in out.items()})
-    print("dyn_core_tlm done")
+    np.savez_compressed(os.path.join(HERE, "ref_dyn_core_nh_beta_tlm.npz" if beta > 0.0 else "ref_dyn_core_nh_tlm.npz"),
+                        **{k: v.astype(np.float64) for k, v in out.items()})
+    print("dyn_core_tlm done, beta =", beta)
 
 
 FV_ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz"]
@@ -291,5 +296,7 @@ if __name__ == "__main__":
         main()
     if len(sys.argv) < 2 or sys.argv[1] == "dyn_core":
         main_dyn_core()
+    if len(sys.argv) < 2 or sys.argv[1] == "dyn_core_beta":
+        main_dyn_core(0.4)
     if len(sys.argv) < 2 or sys.argv[1] == "fv_dynamics":
         main_fv_dynamics()

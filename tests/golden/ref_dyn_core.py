@@ -80,6 +80,41 @@ class Exchanger:
                 self.scatter(y, [s[i] for s in slots])
         self.ls.run(tile, fields, work)
 
+    def update_adj(self, tile, fields, kind):
+        """adjoint of update(): field_ad <- H^T field_ad, H the halo fill (torch.func.vjp of the same index maps)"""
+        def work(slots):
+            if slots[0][0].a.size == 0:
+                return
+            xs = [self.gather([s[i] for s in slots]) for i in range(len(slots[0]))]
+            if kind in ("scalar", "corner"):
+                fn = self.halo.scalar if kind == "scalar" else self.halo.corner
+                _, vjp = torch.func.vjp(fn, torch.zeros_like(xs[0]))
+                ys = [vjp(xs[0])[0]]
+            else:
+                fn = self.halo.cgrid if kind == "cgrid" else self.halo.dgrid
+                _, vjp = torch.func.vjp(fn, torch.zeros_like(xs[0]), torch.zeros_like(xs[1]))
+                ys = list(vjp((xs[0], xs[1])))
+            for i, y in enumerate(ys):
+                self.scatter(y, [s[i] for s in slots])
+        self.ls.run(tile, fields, work)
+
+    def boundary_adj(self, tile, u_ad, v_ad, ebuf_ad, nbuf_ad):
+        """adjoint of boundary(): u_ad, v_ad += B^T (nbufferx_ad, ebuffery_ad); the buffers' adjoints are consumed"""
+        N = self.N
+        def fn(xu, xv):
+            un, vn = self.getb(xu, xv)
+            return un[:, :, N + 3, 3: N + 3], vn[:, :, 3: N + 3, N + 3]
+        def work(slots):
+            xu = self.gather([s[0] for s in slots]); xv = self.gather([s[1] for s in slots])
+            nb = torch.stack([torch.from_numpy(np.ascontiguousarray(s[3][:N, :].T)) for s in slots])     # [6, K, N]
+            eb = torch.stack([torch.from_numpy(np.ascontiguousarray(s[2][:N, :].T)) for s in slots])
+            _, vjp = torch.func.vjp(fn, torch.zeros_like(xu), torch.zeros_like(xv))
+            du, dv = vjp((nb, eb))
+            self.scatter(xu + du, [s[0] for s in slots]); self.scatter(xv + dv, [s[1] for s in slots])
+            for s in slots:
+                s[2][...] = 0.0; s[3][...] = 0.0
+        self.ls.run(tile, (u_ad, v_ad, ebuf_ad, nbuf_ad), work)
+
     def boundary(self, tile, u, v, ebuf, nbuf):
         """mpp_get_boundary(u, v, gridtype = DGRID_NE): nbufferx(1:ie-is+1, k) = u(is:ie, je+1), ebuffery(1:je-js+1, k) = v(ie+1, js:je)"""
         N = self.N
@@ -115,8 +150,28 @@ def make_stubs(ex):
     def mpp_get_boundary_tlm(u, u_tl, v, v_tl, domain, ebuffery=None, ebuffery_tl=None, nbufferx=None, nbufferx_tl=None, gridtype=None):
         ex.boundary(domain.tile, u, v, ebuffery, nbufferx)
         ex.boundary(domain.tile, u_tl, v_tl, ebuffery_tl, nbufferx_tl)
+    def kind_of(kw):
+        return ("corner" if kw.get("position") == CORNER else "cgrid" if kw.get("gridtype") == CGRID_NE
+                else "dgrid" if kw.get("gridtype") == DGRID_NE else "scalar")
+
+    def start_group_halo_update(pack, *args, **kw):
+        domain = args[-1]
+        ex.update(domain.tile, list(args[:-1]), kind_of(kw))
+
+    def start_group_halo_update_adm(pack, *args, **kw):
+        domain = args[-1]
+        fl = list(args[:-1])
+        ex.update_adj(domain.tile, [fl[1], fl[3]] if len(fl) == 4 else [fl[1]], kind_of(kw))
+
+    def mpp_get_boundary(u, v, domain, ebuffery=None, nbufferx=None, gridtype=None):
+        ex.boundary(domain.tile, u, v, ebuffery, nbufferx)
+
+    def mpp_get_boundary_adm(u, u_ad, v, v_ad, domain, ebuffery=None, ebuffery_ad=None, nbufferx=None, nbufferx_ad=None, gridtype=None):
+        ex.boundary_adj(domain.tile, u_ad, v_ad, ebuffery_ad, nbufferx_ad)
     noop = lambda *a, **k: None
-    return dict(start_group_halo_update_tlm=start_group_halo_update_tlm, complete_group_halo_update=noop, mpp_get_boundary_tlm=mpp_get_boundary_tlm,
+    return dict(start_group_halo_update=start_group_halo_update, start_group_halo_update_adm=start_group_halo_update_adm,
+                mpp_get_boundary=mpp_get_boundary, mpp_get_boundary_adm=mpp_get_boundary_adm,
+                start_group_halo_update_tlm=start_group_halo_update_tlm, complete_group_halo_update=noop, mpp_get_boundary_tlm=mpp_get_boundary_tlm,
                 timing_on=noop, timing_off=noop, prt_mxm=noop, prt_maxmin=noop, is_master=lambda: False, send_data=lambda *a, **k: False,
                 corner=CORNER, cgrid_ne=CGRID_NE, dgrid_ne=DGRID_NE)
 
@@ -125,14 +180,15 @@ def load_fill_corners(N):
     """the reference's fill_corners family (tools/fv_mp_nlm_mod.F90, model_tlmadm/fv_mp_tlm.F90: they read the module's domain indices)
     with Python dispatchers for the generic names"""
     names = ["fill_corners_2d_r8", "fill_corners_xy_2d_r8", "fill_corners_agrid_r8", "fill_corners_cgrid_r8", "fill_corners_dgrid_r8"]
-    only = set(names) | {n + "_tlm" for n in names}
+    only = set(names) | {n + "_tlm" for n in names} | {n + "_adm" for n in names}
     idx = dict(is_=1, ie=N, js=1, je=N, isd=1 - NG, ied=N + NG, jsd=1 - NG, jed=N + NG, ng=NG, xdir=1, ydir=2)
-    sp, fns, _ = f90py.load([REF + "../tools/fv_mp_nlm_mod.F90", REF + "fv_mp_tlm.F90"], extra=idx, only=only, defines=("SPMD",))
+    sp, fns, _ = f90py.load([REF + "../tools/fv_mp_nlm_mod.F90", REF + "fv_mp_tlm.F90", REF + "fv_mp_adm.F90"], extra=idx, only=only, defines=("SPMD",))
     g = {}
     g["fill_corners"] = lambda *a, **k: (fns["fill_corners_xy_2d_r8"] if isinstance(a[1], FA) else fns["fill_corners_2d_r8"])(*a, **k)
     g["fill_corners_tlm"] = lambda *a, **k: (fns["fill_corners_xy_2d_r8_tlm"] if isinstance(a[2], FA) else fns["fill_corners_2d_r8_tlm"])(*a, **k)
+    g["fill_corners_adm"] = lambda *a, **k: (fns["fill_corners_xy_2d_r8_adm"] if isinstance(a[2], FA) else fns["fill_corners_2d_r8_adm"])(*a, **k)
     for kind in ("agrid", "cgrid", "dgrid"):
-        for sfx in ("", "_tlm"):
+        for sfx in ("", "_tlm", "_adm"):
             if "fill_corners_%s_r8%s" % (kind, sfx) in fns:
                 g["fill_corners_%s%s" % (kind, sfx)] = fns["fill_corners_%s_r8%s" % (kind, sfx)]
     g.update(xdir=1, ydir=2)
@@ -152,7 +208,7 @@ def flags_from_cfg(cfg, N):
     """fv_flags_type fields DYN_CORE_TLM reads, from the oracle's configuration dictionary (same names as the reference's namelist)"""
     d = dict(npx=N + 1, npy=N + 1, grid_type=0, k_split=1, m_split=0, d_ext=0.0, inline_q=False, fv_debug=False, a2b_ord=4, use_old_omega=False,
              use_logp=False, delt_max=1.0, d_con=cfg.get("d_con", 0.0), hydrostatic=False, scale_z=0.0, p_fac=cfg["p_fac"],
-             breed_vortex_inline=False, a_imp=cfg.get("a_imp", 1.0), nwat=0, ke_bg=0.0, fill_dp=False, do_f3d=False, convert_ke=False, beta=0.0,
+             breed_vortex_inline=False, a_imp=cfg.get("a_imp", 1.0), nwat=0, ke_bg=0.0, fill_dp=False, do_f3d=False, convert_ke=False, beta=cfg.get("beta", 0.0),
              n_sponge=cfg.get("n_sponge", 0))
     for k in ("nord", "d2_bg", "d2_bg_k1", "d2_bg_k2", "vtdm4", "do_vort_damp", "dddmp", "d4_bg", "hord_mt", "hord_vt", "hord_tm", "hord_dp"):
         d[k] = cfg[k]

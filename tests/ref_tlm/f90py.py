@@ -78,15 +78,23 @@ def bind(actual, bounds, name):
     return FA(actual.a, lo)
 
 
-STACK = []
+import threading                      # noqa: E402
+_TLS = threading.local()
+
+
+def stack():
+    """Tapenade's checkpoint stack: one per thread (the six-tile drivers run one thread per tile)"""
+    if not hasattr(_TLS, "s"):
+        _TLS.s = []
+    return _TLS.s
 
 
 def f_push(kind, v):
-    STACK.append((kind, v))
+    stack().append((kind, v))
 
 
 def f_pop(kind):
-    k, v = STACK.pop()
+    k, v = stack().pop()
     assert k == kind, ("checkpoint stack out of step: pushed %s, popped as %s" % (k, kind))
     return v
 
@@ -110,7 +118,7 @@ def f_div(a, b):
     return a / b
 
 
-RUNTIME = dict(_any=lambda x: bool(np.any(x.a if isinstance(x, FA) else x)), _stack=STACK, _push=f_push, _pop=f_pop, _Goto=Goto, FA=FA, _bind=bind, _alloc=FA.alloc, np=np, _sign=f_sign, _div=f_div, _real=f_real, r_grid=8,
+RUNTIME = dict(_any=lambda x: bool(np.any(x.a if isinstance(x, FA) else x)), _stack=stack, _push=f_push, _pop=f_pop, _Goto=Goto, FA=FA, _bind=bind, _alloc=FA.alloc, np=np, _sign=f_sign, _div=f_div, _real=f_real, r_grid=8,
                log=np.log, exp=np.exp, sqrt=np.sqrt, sin=np.sin, cos=np.cos, tan=np.tan, atan=np.arctan, asin=np.arcsin, acos=np.arccos,
                tanh=np.tanh, atan2=np.arctan2)
 

@@ -163,6 +163,16 @@ def test_dyn_core_hydro_two_sided_gpu():
     _run(False, 2, K=5, extra=TWO_SIDED)
 
 
+def test_dyn_core_hydro_beta_emu():
+    """beta = 0.4: grad1_p_update (model/dyn_core_nlm.F90:1781-1872, TL dyn_core_tlm.F90:4163-4293) replaces one_grad_p"""
+    print(_run(True, 3, extra=dict(beta=0.4)))
+
+
+@pytest.mark.gpu
+def test_dyn_core_hydro_beta_gpu():
+    _run(False, 3, extra=dict(beta=0.4))
+
+
 def test_dyn_core_hydro_heat_emu():
     """d_con = 1: heat source accumulated over the acoustic steps, filtered by del2_cubed, added to pt (dyn_core_nlm.F90:1052-1075)"""
     print(_run(True, 2, K=5, extra=dict(d_con=1.0)))     # layers 1-3 are sponge layers (d_con_k = 0): K = 5 leaves two heated ones

@@ -184,6 +184,17 @@ def test_dyn_core_nh_heat_emu():
     print(_run_dyn_nh(True, 2, extra=dict(d_con=1.0)))
 
 
+def test_dyn_core_nh_beta_emu():
+    """beta = 0.4: split_p_grad (model/dyn_core_nlm.F90:1531-1643, TL dyn_core_tlm.F90:3592-3757) replaces nh_p_grad; three acoustic
+    sub-steps so that the blended hydrostatic gradient du / dv is handed on twice (beta_d = 0 on the first, :373-375)"""
+    print(_run_dyn_nh(True, 3, extra=dict(beta=0.4)))
+
+
+@pytest.mark.gpu
+def test_dyn_core_nh_beta_gpu():
+    _run_dyn_nh(False, 3, extra=dict(beta=0.4))
+
+
 def test_update_dz_c_emu():
     print(_run_dzc(True))
 

@@ -180,8 +180,10 @@ def _dyn_regions(N):
                 cx=(1, npx, -2, N + 3), cy=(-2, N + 3, 1, npx))
 
 
-def test_oracle_reproduces_reference_dyn_core_tlm():
-    """DYN_CORE_TLM (model_tlmadm/dyn_core_tlm.F90:93-2600: the non-hydrostatic acoustic loop with C_SW_TLM, UPDATE_DZ_C_TLM,
+@pytest.mark.parametrize("beta", [0.0, 0.4])
+def test_oracle_reproduces_reference_dyn_core_tlm(beta):
+    """beta = 0.4: SPLIT_P_GRAD_TLM (model_tlmadm/dyn_core_tlm.F90:3592-3757) instead of NH_P_GRAD_TLM, three sub-steps.
+    DYN_CORE_TLM (model_tlmadm/dyn_core_tlm.F90:93-2600: the non-hydrostatic acoustic loop with C_SW_TLM, UPDATE_DZ_C_TLM,
     RIEM_SOLVER_C_TLM, P_GRAD_C_TLM, D_SW_TLM, UPDATE_DZ_D_TLM, RIEM_SOLVER3_TLM, NH_P_GRAD_TLM and the per-level switch logic of both the
     trajectory and the perturbation side), two acoustic sub-steps on all six tiles.  The reference's FMS halo exchanges were served by the
     repository's cubed-sphere index maps at generation time (tests/golden/ref_dyn_core.py)."""
@@ -189,8 +191,8 @@ def test_oracle_reproduces_reference_dyn_core_tlm():
     sys.path.insert(0, GOLD)
     from make_ref_golden import dyn_core_inputs
     from oracle import nh as onh
-    gold = np.load(os.path.join(GOLD, "ref_dyn_core_nh_tlm.npz"))
-    N, K, ak, bk, f, d, cfg, act = dyn_core_inputs()
+    gold = np.load(os.path.join(GOLD, "ref_dyn_core_nh_beta_tlm.npz" if beta > 0.0 else "ref_dyn_core_nh_tlm.npz"))
+    N, K, ak, bk, f, d, cfg, act = dyn_core_inputs(beta)
     g = ograd(N)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
 
@@ -209,13 +211,13 @@ def test_oracle_reproduces_reference_dyn_core_tlm():
     assert max(errs.values()) <= 1e-12, errs          # achieved 5e-15
 
 
-def _lib_vs_reference_dyn_core(emu):
+def _lib_vs_reference_dyn_core(emu, beta=0.0):
     import sys
     sys.path.insert(0, GOLD)
     from make_ref_golden import dyn_core_inputs
     from test_dyn_core import two_sided_params
-    gold = np.load(os.path.join(GOLD, "ref_dyn_core_nh_tlm.npz"))
-    N, K, ak, bk, f, d, cfg, act = dyn_core_inputs()
+    gold = np.load(os.path.join(GOLD, "ref_dyn_core_nh_beta_tlm.npz" if beta > 0.0 else "ref_dyn_core_nh_tlm.npz"))
+    N, K, ak, bk, f, d, cfg, act = dyn_core_inputs(beta)
     h = handle(N, K, emu, ak, bk)
     p = two_sided_params(cfg); p.update(do_vort_damp=int(cfg["do_vort_damp"]), hydrostatic=0)
     key = dict(u="u_n", v="v_n", pt="pt_n", delp="delp_n", w="w_n", delz="delz_n")
@@ -240,14 +242,16 @@ def _lib_vs_reference_dyn_core(emu):
     assert max(errs.values()) <= 5e-11, errs          # the module's tolerance against the oracle (tests/test_nh.py); achieved: see the print
 
 
-def test_library_reproduces_reference_dyn_core_tlm_emu():
+@pytest.mark.parametrize("beta", [0.0, 0.4])
+def test_library_reproduces_reference_dyn_core_tlm_emu(beta):
     """the C-ABI library's dyn_core_nh module (host emulation) against the reference's own DYN_CORE / DYN_CORE_TLM outputs"""
-    _lib_vs_reference_dyn_core(True)
+    _lib_vs_reference_dyn_core(True, beta)
 
 
 @pytest.mark.gpu
-def test_library_reproduces_reference_dyn_core_tlm_gpu():
-    _lib_vs_reference_dyn_core(False)
+@pytest.mark.parametrize("beta", [0.0, 0.4])
+def test_library_reproduces_reference_dyn_core_tlm_gpu(beta):
+    _lib_vs_reference_dyn_core(False, beta)
 
 
 # ---------------------------------------------------------------------------------------------------------------- FV_DYNAMICS_TLM (whole step)

@@ -109,6 +109,16 @@ def test_step_api_sim_solver_emu():
     print(_run(True, nonhydro=True, extra=dict(a_imp=0.75)))
 
 
+def test_step_api_beta_emu():
+    """beta = 0.4 through fv3lm_config: split_p_grad in the non-hydrostatic acoustic loop of a whole step (dyn_core_nlm.F90:874-875)"""
+    print(_run(True, nonhydro=True, extra=dict(beta=0.4)))
+
+
+@pytest.mark.gpu
+def test_step_api_beta_gpu():
+    _run(False, nonhydro=True, extra=dict(beta=0.4))
+
+
 def test_step_api_hord333_emu():
     """hord_* = 333 (third-order linear scheme of the TL/AD, tp_core_tlm.F90:2467) for every transport of a hydrostatic step"""
     print(_run(True, extra=dict(hord_mt=333, hord_vt=333, hord_tm=333, hord_dp=333, hord_tr=333)))
