@@ -207,7 +207,7 @@ def load_reference(ex, consts, great_circle_dist, N=12):
 def flags_from_cfg(cfg, N):
     """fv_flags_type fields DYN_CORE_TLM reads, from the oracle's configuration dictionary (same names as the reference's namelist)"""
     d = dict(npx=N + 1, npy=N + 1, grid_type=0, k_split=1, m_split=0, d_ext=0.0, inline_q=False, fv_debug=False, a2b_ord=4, use_old_omega=False,
-             use_logp=False, delt_max=1.0, d_con=cfg.get("d_con", 0.0), hydrostatic=False, scale_z=0.0, p_fac=cfg["p_fac"],
+             use_logp=False, delt_max=1.0, d_con=cfg.get("d_con", 0.0), hydrostatic=bool(cfg.get("hydrostatic", False)), scale_z=0.0, p_fac=cfg["p_fac"],
              breed_vortex_inline=False, a_imp=cfg.get("a_imp", 1.0), nwat=0, ke_bg=0.0, fill_dp=False, do_f3d=False, convert_ke=False, beta=cfg.get("beta", 0.0),
              n_sponge=cfg.get("n_sponge", 0))
     for k in ("nord", "d2_bg", "d2_bg_k1", "d2_bg_k2", "vtdm4", "do_vort_damp", "dddmp", "d4_bg", "hord_mt", "hord_vt", "hord_tm", "hord_dp"):
@@ -254,7 +254,8 @@ def run(fns, ex, grid_structs, M, N, K, f, d, cfg, ak, bk):
             ct = dict(cfg); ct.update(cfg["traj"])
             fl = flags_from_cfg(ct, N); flp = pert_flags_from_cfg(cfg)
             a = {n: FA.alloc(b) for n, b in bnd.items()}; a_tl = {n: FA.alloc(b) for n, b in bnd.items()}
-            for n in ("u", "v", "w", "delz", "pt", "delp"):
+            hyd = bool(cfg.get("hydrostatic", False))
+            for n in (("u", "v", "pt", "delp") if hyd else ("u", "v", "w", "delz", "pt", "delp")):
                 ni, nj = a[n].a.shape[0], a[n].a.shape[1]
                 a[n].a[...] = f[n][t][:, :nj, :ni].transpose(2, 1, 0)
                 a_tl[n].a[...] = d[n][t][:, :nj, :ni].transpose(2, 1, 0)
@@ -267,7 +268,7 @@ def run(fns, ex, grid_structs, M, N, K, f, d, cfg, ak, bk):
             domain = types.SimpleNamespace(tile=t)
             nest = types.SimpleNamespace(nest_timestep=0)
             P = lambda n: (a[n], a_tl[n])
-            fns["dyn_core_tlm"](N + 1, N + 1, K, NG, 1, 0, cfg["bdt"], cfg["n_split"], 0.0, cfg["cp_air"], cfg["akap"], cappa, cfg["grav"], False,
+            fns["dyn_core_tlm"](N + 1, N + 1, K, NG, 1, 0, cfg["bdt"], cfg["n_split"], 0.0, cfg["cp_air"], cfg["akap"], cappa, cfg["grav"], hyd,
                                 *P("u"), *P("v"), *P("w"), *P("delz"), *P("pt"), q, q_tl, *P("delp"), *P("pe"), *P("pk"), phis, *P("ws"), *P("omga"),
                                 cfg["ptop"], pfull, *P("ua"), *P("va"), *P("uc"), *P("vc"), *P("mfx"), *P("mfy"), *P("cx"), *P("cy"), *P("pkz"),
                                 *P("peln"), q_con, fak, fbk, *P("dpx"), 0, gs, fl, flp, nest, types.SimpleNamespace(id_ws=0, id_zratio=0), bd, domain, True, i_pack, True,
@@ -286,7 +287,8 @@ def run(fns, ex, grid_structs, M, N, K, f, d, cfg, ak, bk):
     if errors:
         raise RuntimeError("tile %d failed:\n%s" % (errors[0][0], errors[0][1]))
     out = {}
-    for n in ("u", "v", "w", "delz", "pt", "delp", "mfx", "mfy", "cx", "cy"):
+    for n in (("u", "v", "pt", "delp", "mfx", "mfy", "cx", "cy", "pkz") if cfg.get("hydrostatic", False) else
+              ("u", "v", "w", "delz", "pt", "delp", "mfx", "mfy", "cx", "cy")):
         for sfx, idx in (("", 0), ("_tl", 1)):
             x = np.zeros((6, K, NX, NX))
             for t in range(6):

@@ -254,6 +254,78 @@ def test_library_reproduces_reference_dyn_core_tlm_gpu(beta):
     _lib_vs_reference_dyn_core(False, beta)
 
 
+HYD_OUT = ["u", "v", "pt", "delp", "mfx", "mfy", "cx", "cy", "pkz"]
+
+
+def _hyd_gold(beta):
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_ref_golden import dyn_core_hydro_inputs
+    gold = np.load(os.path.join(GOLD, "ref_dyn_core_hydro_beta_tlm.npz" if beta > 0.0 else "ref_dyn_core_hydro_tlm.npz"))
+    return gold, dyn_core_hydro_inputs(beta)
+
+
+@pytest.mark.parametrize("beta", [0.0, 0.4])
+def test_oracle_reproduces_reference_dyn_core_hydro_tlm(beta):
+    """DYN_CORE_TLM with hydrostatic = T (model_tlmadm/dyn_core_tlm.F90:93-2600: GEOPK_TLM on both grids, P_GRAD_C_TLM, ONE_GRAD_P_TLM :3761;
+    beta = 0.4: GRAD1_P_UPDATE_TLM :4163-4293), three acoustic sub-steps on all six tiles, two-sided switches."""
+    from oracle import dyn_core as odyn
+    gold, (N, K, ak, bk, f, d, cfg, act) = _hyd_gold(beta)
+    g = ograd(N)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    def fn(*a):
+        st = {n: T(f[n]) for n in f}; st.update(dict(zip(act, a)))
+        o = odyn.dyn_core_hydro(st, g, cfg)
+        return tuple(o[k] for k in HYD_OUT)
+    out, dout = torch.func.jvp(fn, tuple(T(f[n]) for n in act), tuple(T(d[n]) for n in act))
+    regs = _dyn_regions(N); regs["pkz"] = (1, N, 1, N)
+    errs = {}
+    for k, nm in enumerate(HYD_OUT):
+        errs[nm] = relerr(region(out[k].numpy(), *regs[nm]), region(gold[nm], *regs[nm]))
+        errs[nm + "_tl"] = relerr(region(dout[k].numpy(), *regs[nm]), region(gold[nm + "_tl"], *regs[nm]))
+        assert np.abs(region(gold[nm + "_tl"], *regs[nm])).max() > 0
+    print("dyn_core_tlm (hydrostatic) vs reference", {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 1e-12, errs
+
+
+def _lib_vs_reference_dyn_core_hydro(emu, beta):
+    from test_dyn_core import two_sided_params
+    gold, (N, K, ak, bk, f, d, cfg, act) = _hyd_gold(beta)
+    h = handle(N, K, emu)
+    p = two_sided_params(cfg); p.update(do_vort_damp=int(cfg["do_vort_damp"]), hydrostatic=1)
+    key = dict(u="u_n", v="v_n", pt="pt_n", delp="delp_n")
+    regs = _dyn_regions(N); regs["pkz"] = (1, N, 1, N)
+    NX = N + 7
+    errs = {}
+    for sfx, mode in (("", fv3lm.MODE_NL), ("_tl", fv3lm.MODE_TL)):
+        traj = {n: f[n].copy() for n in f}
+        for o in HYD_OUT:
+            traj[key.get(o, o)] = np.zeros((6, K, NX, NX))
+        pert = None
+        if mode == fv3lm.MODE_TL:
+            pert = {n: d[n].copy() for n in act}
+            for o in HYD_OUT:
+                pert[key.get(o, o)] = np.zeros((6, K, NX, NX))
+        h.module_run("dyn_core", mode, traj, pert, params=p)
+        res = traj if mode == fv3lm.MODE_NL else pert
+        for o in HYD_OUT:
+            errs[o + sfx] = relerr(region(res[key.get(o, o)], *regs[o]), region(gold[o + sfx], *regs[o]))
+    print("library dyn_core vs reference", {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 5e-11, errs          # the module's tolerance against the oracle (tests/test_dyn_core.py); achieved: see the print
+
+
+@pytest.mark.parametrize("beta", [0.0, 0.4])
+def test_library_reproduces_reference_dyn_core_hydro_tlm_emu(beta):
+    _lib_vs_reference_dyn_core_hydro(True, beta)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("beta", [0.0, 0.4])
+def test_library_reproduces_reference_dyn_core_hydro_tlm_gpu(beta):
+    _lib_vs_reference_dyn_core_hydro(False, beta)
+
+
 # ---------------------------------------------------------------------------------------------------------------- FV_DYNAMICS_TLM (whole step)
 def test_oracle_reproduces_reference_fv_dynamics_tlm():
     """FV_DYNAMICS_TLM (model_tlmadm/fv_dynamics_tlm.F90:87-995: DYN_CORE_TLM, TRACER_2D_TLM, LAGRANGIAN_TO_EULERIAN_TLM with its map
