@@ -58,8 +58,10 @@ int fv3lm_create(const fv3lm_config* cfg, const double* ak, const double* bk, fv
   // switches whose paths are not built change the dynamics in the reference: refuse them rather than ignore them
   if (cfg->beta < 0.0 || cfg->beta >= 1.0)
     throw std::runtime_error("fv3lm_create: beta must be in [0, 1): beta > 0 selects grad1_p_update / split_p_grad, beta < -0.1 the one_grad_p branch of the non-hydrostatic core (model/dyn_core_nlm.F90:865-877), which is not built");
-  if (cfg->d_ext > 0.0)
-    throw std::runtime_error("fv3lm_create: d_ext > 0 switches on the external-mode divergence damping (model/dyn_core_nlm.F90:642-720), which is not built");
+  if (cfg->d_ext < 0.0) throw std::runtime_error("fv3lm_create: d_ext < 0");
+  // d_ext > 0: external-mode divergence damping of the hydrostatic core (model/dyn_core_nlm.F90:642-726, one_grad_p :1713-1727).  The
+  // non-hydrostatic pressure gradients (nh_p_grad, split_p_grad) never read divg2, so there the switch changes nothing (checked against the
+  // reference's own DYN_CORE_TLM: bit-identical outputs with d_ext = 0.02 and 0) and is accepted as is.
   int device = -1;
 #ifndef FV3LM_HOST_EMU
   int ndev = 0;

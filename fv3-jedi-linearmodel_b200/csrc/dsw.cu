@@ -61,7 +61,7 @@ static bool same_lev(const LevD& a, const LevD& b, int nk) { for (int k = 0; k <
 // (model_tlmadm/sw_core_tlm.F90 D_SW_TLM :1047): where the two differ, the operator is evaluated twice -- with pp for the
 // perturbation (linearised about the same inputs) and with prm, on detached inputs, for the trajectory -- and spliced.
 DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w, int uc, int vc, int ua, int va, int divg_d,
-                  const DswParams& prm, int nk, const std::string& tag, const DswParams* pp_) {
+                  const DswParams& prm, int nk, const std::string& tag, const DswParams* pp_, bool want_divg) {
   auto nm = [&](const char* s) { return tag + "." + s; };
   const double da_min_c = P.dv->m.da_min_c;
   const DswParams& pp = pp_ ? *pp_ : prm;
@@ -168,12 +168,13 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
   int wk = P.val(nm("wk"), nk);
   P.add<S_relvort>("relvort", {0}, {u, v}, {wk}, nk);
   // divergence damping (compute_divergence_damping, :1264-1434; split_damp: :2341-2366)
-  auto div_damp = [&](const DswParams& q, int u, int v, int ua, int va, int uc, int vc, int divg_d, int wk, const std::string& tg) -> int {
+  auto div_damp = [&](const DswParams& q, int u, int v, int ua, int va, int uc, int vc, int divg_d, int wk, const std::string& tg, int* divg_out) -> int {
     auto nm = [&](const char* s) { return tg + "." + s; };
     int delpc0 = P.val(nm("delpc0"), nk), vq = P.val(nm("vq0"), nk), dd = divg_d;
     bool any0 = false; int nmax = 0;
     for (int k = 0; k < nk; k++) { if (q.nord.v[k] == 0) any0 = true; nmax = std::max(nmax, (int)q.nord.v[k]); }
     if (any0) P.add<S_ddiv0>("ddiv0", {q.nord}, {u, v, ua, va, uc, vc}, {delpc0}, nk);
+    if (want_divg) { *divg_out = P.val(nm("divg"), nk); P.add<S_sel_div>("sel_div", {q.nord}, {delpc0, divg_d}, {*divg_out}, nk); }
     if (nmax > 0) {
       for (int it = 1; it <= nmax; it++) {
         const bool fill_c = (nmax - it) != 0;
@@ -193,13 +194,15 @@ DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w,
     return vd;
   };
   int vd;
-  if (!split_damp) vd = div_damp(prm, u, v, ua, va, uc, vc, divg_d, wk, tag);
+  if (!split_damp) vd = div_damp(prm, u, v, ua, va, uc, vc, divg_d, wk, tag, &o.divg);
   else {
+    int ga = -1, gb = -1;
     P.tl_only = true;
-    int a = div_damp(pp, u, v, ua, va, uc, vc, divg_d, wk, tag + ".dd_p");
+    int a = div_damp(pp, u, v, ua, va, uc, vc, divg_d, wk, tag + ".dd_p", &ga);
     P.tl_only = false;
-    int b = div_damp(prm, D(u), D(v), D(ua), D(va), D(uc), D(vc), D(divg_d), D(wk), tag + ".dd_t");
+    int b = div_damp(prm, D(u), D(v), D(ua), D(va), D(uc), D(vc), D(divg_d), D(wk), tag + ".dd_t", &gb);
     vd = splice(a, b, tag + ".vd");
+    if (want_divg) o.divg = splice(ga, gb, tag + ".divg");
   }
   // vorticity transport
   int avort = P.val(nm("avort"), nk);

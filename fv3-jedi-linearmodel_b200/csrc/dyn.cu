@@ -129,7 +129,12 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, co
     int uc = P.val(tg + ".uc", K), vc = P.val(tg + ".vc", K);
     P.add<S_pgrad_c>("p_grad_c", {dt2, 1}, {cs.uc, cs.vc, pkc, gz, cs.delpc}, {uc, vc}, K);
     add_patch(P, "halo_ucvc", &mo.h_cgrid, {uc, vc});
-    DswOut ds = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, cs.ua, cs.va, cs.divg_d, dp, K, tg + ".dsw", two ? &dpp : nullptr);
+    const bool ext = c.d_ext > 0.0;
+    int dpc = -1;
+    if (ext) { dpc = P.val(tg + ".dpc", K); P.add<S_a2b_ord2>("a2b_ord2_delp", {0}, {delp}, {dpc}, K); }   // delp at the corners, before d_sw (:642-644)
+    DswOut ds = build_d_sw(P, mo, delp, pt, u, v, w, uc, vc, cs.ua, cs.va, cs.divg_d, dp, K, tg + ".dsw", two ? &dpp : nullptr, ext);
+    int divg2 = -1;
+    if (ext) { divg2 = P.val(tg + ".divg2", K); add_col<S_divg2>(P, "divg2", {K, c.d_ext * P.dv->m.da_min_c}, {dpc, ds.divg}, {divg2}); }
     // flux capacitors (d_sw :913-931)
     if (mfx < 0) { mfx = ds.fx; mfy = ds.fy; cx = ds.crx; cy = ds.cry; }
     else {
@@ -153,11 +158,11 @@ DynOut build_dyn_core(Program& P, Mosaic& mo, const DynConfig& c, DynState s, co
     o.pk = pkd;
     int pkb = build_a2b_ord4(P, mo, pkd, K + 1, tg + ".a2b_pk"), gzb = build_a2b_ord4(P, mo, gzd, K + 1, tg + ".a2b_gz");
     u = P.val(tg + ".u", K); v = P.val(tg + ".v", K);
-    if (c.beta > 0.0) {   // grad1_p_update (:865-866); beta_d = 0 on the first sub-step (:373-375), du / dv go to the next one
+    if (c.beta > 0.0 || ext) {   // grad1_p_update (:865-866); beta_d = 0 on the first sub-step (:373-375), du / dv go to the next one; d_ext > 0 without beta: one_grad_p with its wk1 / wk2 terms
       int dun = P.val(tg + ".du", K), dvn = P.val(tg + ".dv", K);
-      const bool first = it == 1;
-      P.add<S_gradp_beta>("grad1_p_update", {dt, pow(c.ptop, c.akap), first ? 0.0 : c.beta, 0, first ? 1 : 0},
-                          {ds.u, ds.v, pkb, gzb, pkb, pkb, first ? ds.u : du_prev, first ? ds.v : dv_prev}, {u, v, dun, dvn}, K);
+      const bool first = it == 1 || !(c.beta > 0.0);
+      P.add<S_gradp_beta>(c.beta > 0.0 ? "grad1_p_update" : "one_grad_p_ext", {dt, pow(c.ptop, c.akap), first ? 0.0 : c.beta, 0, first ? 1 : 0, ext ? 1 : 0, c.beta > 0.0 ? 1 : 0},
+                          {ds.u, ds.v, pkb, gzb, pkb, pkb, first ? ds.u : du_prev, first ? ds.v : dv_prev, ext ? divg2 : pkb}, {u, v, dun, dvn}, K);
       du_prev = dun; dv_prev = dvn;
     } else
     P.add<S_gradp>("one_grad_p", {dt, pow(c.ptop, c.akap), 0}, {ds.u, ds.v, pkb, gzb, pkb, pkb}, {u, v}, K);
@@ -189,6 +194,7 @@ void dyn_config_from(DynConfig& c, const ModuleParams& prm) {
   c.a_imp = prm.get("a_imp", f->a_imp != 0.0 ? f->a_imp : 1.0);
   c.p_fac = prm.get("p_fac", f->p_fac != 0.0 ? f->p_fac : 0.05);
   c.beta = prm.get("beta", f->beta);
+  c.d_ext = prm.get("d_ext", f->d_ext);
   c.d_con = prm.get("d_con", f->d_con);
   c.q_split = prm.geti("q_split", f->q_split_dynamic ? 0 : 1);
   c.q_split_max = prm.geti("q_split_max", f->q_split_max > 0 ? f->q_split_max : 3);

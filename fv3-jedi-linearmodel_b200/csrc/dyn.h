@@ -19,6 +19,7 @@ struct DynConfig {
   bool do_vort_damp = true;
   double ptop = 1.0, akap = 2.0 / 7.0, cp_air = 1004.6, rdgas = 287.05, grav = 9.80665, zvir = 0.6078;
   double a_imp = 1.0, p_fac = 0.05;
+  double d_ext = 0.0;      // > 0 (hydrostatic only): external-mode divergence damping (model/dyn_core_nlm.F90:642-726, one_grad_p :1713-1727); the non-hydrostatic gradient never reads it
   double beta = 0.0;       // > 0: grad1_p_update / split_p_grad instead of one_grad_p / nh_p_grad (model/dyn_core_nlm.F90:865-876)
   int q_split = 1, q_split_max = 3;   // tracer sub-cycling: 1 = one step; 0 = chosen at run time from the Courant numbers (fv_tracer2d_nlm.F90:351-420)
   int kord_mt = 17, kord_wz = 17, kord_tm = 17, kord_tr = 17;   // trajectory remap (two-sided mode: 8 .. 14 monotone); the increment is always |kord| = 17

@@ -201,8 +201,8 @@ DynOut build_dyn_core_nh(Program& P, Mosaic& mo, const DynConfig& c, const std::
     if (c.beta > 0.0) {   // split_p_grad (model/dyn_core_nlm.F90:874-875); beta_d = 0 on the first sub-step (:373-375)
       int dun = P.val(tg + ".du", K), dvn = P.val(tg + ".dv", K);
       const bool first = it == 1;
-      P.add<S_gradp_beta>("split_p_grad", {dt, pow(c.ptop, c.akap), first ? 0.0 : c.beta, 1, first ? 1 : 0},
-                          {ds.u, ds.v, pkb, gzb, ppb, dpb, first ? ds.u : du_prev, first ? ds.v : dv_prev}, {u, v, dun, dvn}, K);
+      P.add<S_gradp_beta>("split_p_grad", {dt, pow(c.ptop, c.akap), first ? 0.0 : c.beta, 1, first ? 1 : 0, 0, 0},
+                          {ds.u, ds.v, pkb, gzb, ppb, dpb, first ? ds.u : du_prev, first ? ds.v : dv_prev, pkb}, {u, v, dun, dvn}, K);
       du_prev = dun; dv_prev = dvn;
     } else
     P.add<S_gradp>("nh_p_grad", {dt, pow(c.ptop, c.akap), 1}, {ds.u, ds.v, pkb, gzb, ppb, dpb}, {u, v}, K);

@@ -522,6 +522,20 @@ struct S_ddiv0 {
   }
 };
 
+// the divergence d_sw hands back in delpc (the caller's vt, model/dyn_core_nlm.F90:656): its own nord = 0 divergence (:1340) on the
+// levels with nord(k) = 0, a copy of the C-grid step's divg_d (:1353) elsewhere.  in: delpc0 divg_d ; out: divg
+struct S_sel_div {
+  static constexpr int NI = 2, NO = 1;
+  struct P { LevOrd nord; };
+  static constexpr int NT = 2;
+  static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie + 1, g.js, g.je + 1)) return;
+    if (p.nord.v[x.kk] == 0) x.out(0, x.in(0)); else x.out(0, x.in(1));
+  }
+};
+
 // higher-order divergence damping iteration (:1358-1400)
 // vc = (divg(i+1,j) - divg(i,j)) * divg_u ; uc = (divg(i,j+1) - divg(i,j)) * divg_v.  in: dd ; out: w
 template <int DIR> struct S_dd_grad {
@@ -694,9 +708,9 @@ struct DswParams {
   bool heat = false;   // d_con > 1e-5: build the dissipative-heating stages
   LevD d_con;          // d_con_k per level (0 in the sponge layers)
 };
-struct DswOut { int delp, pt, u, v, w, fx, fy, crx, cry, xfx, yfx; int heat = -1; };
+struct DswOut { int delp, pt, u, v, w, fx, fy, crx, cry, xfx, yfx; int heat = -1; int divg = -1; };   // divg: the corner divergence d_sw leaves in its first argument (want_divg)
 DswOut build_d_sw(Program& P, Mosaic& mo, int delp, int pt, int u, int v, int w, int uc, int vc, int ua, int va, int divg_d,
-                  const DswParams& prm, int nk, const std::string& tag, const DswParams* pert = nullptr);
+                  const DswParams& prm, int nk, const std::string& tag, const DswParams* pert = nullptr, bool want_divg = false);
 // a2b_ord4 (a2b.cu)
 int build_a2b_ord4(Program& P, Mosaic& mo, int qin, int nk, const std::string& tag);
 

@@ -236,16 +236,20 @@ struct S_gradp {
 // d_ext = 0, so divg2 = 0 :726): the pressure gradient with the hydrostatic part of the previous acoustic sub-step blended in,
 //   u <- u + beta du_prev ;  du = dt (A B + C D) / den ;  u <- (u + alpha du [+ dn]) rdx,   alpha = 1 - beta
 // beta is the caller's beta_d (0 on the first sub-step, :373-375, where du_prev is not read).  The geometry is S_gradp's.
-// in: u v pkb gzb ppb dpb du_prev dv_prev ; out: u_new v_new du dv
+// ext (hydrostatic, d_ext > 0): the external-mode damping term divg2(i,j) - divg2(i+1,j) joins the wind before the metric factor
+// (one_grad_p :1713-1727, :1758-1771 when grad1 = 0; grad1_p_update :1858, :1867 when grad1 = 1); divg2 is input 8 (the same
+// value on every level, S_divg2).
+// in: u v pkb gzb ppb dpb du_prev dv_prev divg2 ; out: u_new v_new du dv
 struct S_gradp_beta {
-  static constexpr int NI = 8, NO = 4;
-  struct P { double dt, top, beta; int nonhydro, first; };
-  static constexpr int NT = 25;
+  static constexpr int NI = 9, NO = 4;
+  struct P { double dt, top, beta; int nonhydro, first, ext, grad1; };
+  static constexpr int NT = 28;
   static constexpr Tap taps[NT] = {{0, 0, 0, 0}, {1, 0, 0, 0},
                                    {2, 0, 0, 0}, {2, 1, 0, 0}, {2, 0, 1, 0}, {2, 0, 0, 1}, {2, 1, 0, 1}, {2, 0, 1, 1},
                                    {3, 0, 0, 0}, {3, 1, 0, 0}, {3, 0, 1, 0}, {3, 0, 0, 1}, {3, 1, 0, 1}, {3, 0, 1, 1},
                                    {4, 0, 0, 0}, {4, 1, 0, 0}, {4, 0, 1, 0}, {4, 0, 0, 1}, {4, 1, 0, 1}, {4, 0, 1, 1},
-                                   {5, 0, 0, 0}, {5, 1, 0, 0}, {5, 0, 1, 0}, {6, 0, 0, 0}, {7, 0, 0, 0}};
+                                   {5, 0, 0, 0}, {5, 1, 0, 0}, {5, 0, 1, 0}, {6, 0, 0, 0}, {7, 0, 0, 0},
+                                   {8, 0, 0, 0}, {8, 1, 0, 0}, {8, 0, 1, 0}};
   template <class X> DEV static void eval(X& x, const P& p) {
     using T = typename X::T;
     const Geom& g = x.g;
@@ -257,6 +261,7 @@ struct S_gradp_beta {
     if (x.in_rect(g.is, g.ie, g.js, g.je + 1)) {
       T ub = x.in(0);
       if (!p.first) ub = ub + p.beta * x.in(6);
+      if (p.ext) { if (p.grad1) ub = (ub + x.in(8)) - x.in(8, 1, 0); else ub = (x.in(8) - x.in(8, 1, 0)) + ub; }
       T du = p.dt / (wk(0, 0) + wk(1, 0)) * ((GZ(0, 0, 1) - GZ(1, 0, 0)) * (PK(1, 0, 1) - PK(0, 0, 0)) + (GZ(0, 0, 0) - GZ(1, 0, 1)) * (PK(0, 0, 1) - PK(1, 0, 0)));
       x.out(2, du);
       if (p.nonhydro) {
@@ -269,6 +274,7 @@ struct S_gradp_beta {
     if (x.in_rect(g.is, g.ie + 1, g.js, g.je)) {
       T vb = x.in(1);
       if (!p.first) vb = vb + p.beta * x.in(7);
+      if (p.ext) { if (p.grad1) vb = (vb + x.in(8)) - x.in(8, 0, 1); else vb = (x.in(8) - x.in(8, 0, 1)) + vb; }
       T dv = p.dt / (wk(0, 0) + wk(0, 1)) * ((GZ(0, 0, 1) - GZ(0, 1, 0)) * (PK(0, 1, 1) - PK(0, 0, 0)) + (GZ(0, 0, 0) - GZ(0, 1, 1)) * (PK(0, 0, 1) - PK(0, 1, 0)));
       x.out(3, dv);
       if (p.nonhydro) {
@@ -278,6 +284,65 @@ struct S_gradp_beta {
         x.out(1, (vb + alpha * dv) * x.M(x.m.rdy));
       }
     }
+  }
+};
+
+// a2b_ord2 (model/a2b_edge_nlm.F90:677-798, TL model_tlmadm/a2b_edge_tlm.F90 A2B_ORD2_TLM): A-grid -> corners by the four-cell mean, on
+// the cube edges the mean of the two cells across the edge interpolated with edge_w/e/s/n, at the cube vertices the mean of the three
+// cells that exist.  in: qin ; out: qout on is..ie+1, js..je+1
+struct S_a2b_ord2 {
+  static constexpr int NI = 1, NO = 1;
+  struct P { int dummy; };
+  static constexpr int NT = 4;
+  static constexpr Tap taps[NT] = {{0, -1, -1, 0}, {0, 0, -1, 0}, {0, -1, 0, 0}, {0, 0, 0, 0}};
+  template <class X> DEV static void eval(X& x, const P&) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie + 1, g.js, g.je + 1)) return;
+    const int i = x.i, j = x.j, npx = g.npx, npy = g.npy;
+    const bool ei = (i == 1 || i == npx), ej = (j == 1 || j == npy);
+    const double r3 = 1.0 / 3.0;
+    T r;
+    if (ei && ej) {
+      if (i == 1 && j == 1) r = r3 * (x.in(0, 0, 0) + x.in(0, 0, -1) + x.in(0, -1, 0));
+      else if (i == npx && j == 1) r = r3 * (x.in(0, -1, 0) + x.in(0, -1, -1) + x.in(0, 0, 0));
+      else if (i == npx && j == npy) r = r3 * (x.in(0, -1, -1) + x.in(0, 0, -1) + x.in(0, -1, 0));
+      else r = r3 * (x.in(0, 0, -1) + x.in(0, -1, -1) + x.in(0, 0, 0));
+    } else if (ei) {
+      const double e = x.M1(i == 1 ? x.m.edge_w : x.m.edge_e, j);
+      r = e * (0.5 * (x.in(0, -1, -1) + x.in(0, 0, -1))) + (1.0 - e) * (0.5 * (x.in(0, -1, 0) + x.in(0, 0, 0)));
+    } else if (ej) {
+      const double e = x.M1(j == 1 ? x.m.edge_s : x.m.edge_n, i);
+      r = e * (0.5 * (x.in(0, -1, -1) + x.in(0, -1, 0))) + (1.0 - e) * (0.5 * (x.in(0, 0, -1) + x.in(0, 0, 0)));
+    } else {
+      r = 0.25 * (x.in(0, -1, -1) + x.in(0, 0, -1) + x.in(0, -1, 0) + x.in(0, 0, 0));
+    }
+    x.out(0, r);
+  }
+};
+
+// external-mode divergence (model/dyn_core_nlm.F90:707-724): the delp-weighted column mean of the corner divergence,
+//   divg2 = c sum_k(dpc_k vt_k) / sum_k(dpc_k),  c = d_ext da_min_c;  written to every level of the output.
+// in: dpc vt ; out: divg2 (K levels, all equal)
+struct S_divg2 {
+  static constexpr int NI = 2, NO = 1;
+  struct P { int K; double c; };
+  template <class X> DEV static void eval(X& x, const P& p) {
+    using T = typename X::T;
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie + 1, g.js, g.je + 1)) return;
+    T wk = x.in(0, 0), d = wk * x.in(1, 0);
+    for (int k = 1; k < p.K; k++) { wk = wk + x.in(0, k); d = d + x.in(0, k) * x.in(1, k); }
+    d = p.c * d / wk;
+    for (int k = 0; k < p.K; k++) x.out(0, k, d);
+  }
+  template <class X> DEV static void eval_ad(X& x, const P& p) {
+    const Geom& g = x.g;
+    if (!x.in_rect(g.is, g.ie + 1, g.js, g.je + 1)) return;
+    double a = 0.0, wk = 0.0, s = 0.0;
+    for (int k = 0; k < p.K; k++) { a += x.oad(0, k); wk += x.in(0, k); s += x.in(0, k) * x.in(1, k); }
+    const double f = a * p.c / wk, mean = s / wk;
+    for (int k = 0; k < p.K; k++) { x.add(0, k, f * (x.in(1, k) - mean)); x.add(1, k, f * x.in(0, k)); }
   }
 };
 

@@ -130,3 +130,28 @@ def a2b_ord4(qin, g):
               C2 * (S(qout, npx, npx, j0, j1) + S(qyy, npx - 2, npx - 2, j0, j1)))
     qout = put(qout, 2, npx - 1, 2, npy - 1, 0.5 * (S(qxx, 2, npx - 1, 2, npy - 1) + S(qyy, 2, npx - 1, 2, npy - 1)))
     return qout
+
+
+def a2b_ord2(qin, g):
+    """a2b_ord2 (model/a2b_edge_nlm.F90:677-798; TL A2B_ORD2_TLM in model_tlmadm/a2b_edge_tlm.F90): four-cell mean in the interior, edge
+    interpolation of the two-cell means across a cube edge, three-cell mean at the cube vertices.  Whole tile; valid on 1..npx, 1..npy."""
+    npx, npy = g.npx, g.npy
+
+    def S(a, i0, i1, j0, j1): return a[..., R(j0, j1), R(i0, i1)]
+    def Pq(a, i, j): return a[..., j + O, i + O]
+    qout = torch.zeros_like(qin)
+    i0, i1, j0, j1 = 2, npx - 1, 2, npy - 1
+    qout[..., R(j0, j1), R(i0, i1)] = 0.25 * (S(qin, i0 - 1, i1 - 1, j0 - 1, j1 - 1) + S(qin, i0, i1, j0 - 1, j1 - 1) + S(qin, i0 - 1, i1 - 1, j0, j1) + S(qin, i0, i1, j0, j1))
+    qout[..., 1 + O, 1 + O] = R3 * (Pq(qin, 1, 1) + Pq(qin, 1, 0) + Pq(qin, 0, 1))
+    qout[..., 1 + O, npx + O] = R3 * (Pq(qin, npx - 1, 1) + Pq(qin, npx - 1, 0) + Pq(qin, npx, 1))
+    qout[..., npy + O, npx + O] = R3 * (Pq(qin, npx - 1, npy - 1) + Pq(qin, npx, npy - 1) + Pq(qin, npx - 1, npy))
+    qout[..., npy + O, 1 + O] = R3 * (Pq(qin, 1, npy - 1) + Pq(qin, 0, npy - 1) + Pq(qin, 1, npy))
+    def col(i): return 0.5 * (qin[..., R(1, npy - 1), i - 1 + O] + qin[..., R(1, npy - 1), i + O])     # q2(j), j = 1..npy-1
+    def row(j): return 0.5 * (qin[..., j - 1 + O, R(1, npx - 1)] + qin[..., j + O, R(1, npx - 1)])     # q1(i), i = 1..npx-1
+    ew = g.edge_w[..., R(2, npy - 1)]; ee = g.edge_e[..., R(2, npy - 1)]
+    es = g.edge_s[..., R(2, npx - 1)]; en = g.edge_n[..., R(2, npx - 1)]
+    q2 = col(1); qout[..., R(2, npy - 1), 1 + O] = ew * q2[..., :-1] + (1. - ew) * q2[..., 1:]
+    q2 = col(npx); qout[..., R(2, npy - 1), npx + O] = ee * q2[..., :-1] + (1. - ee) * q2[..., 1:]
+    q1 = row(1); qout[..., 1 + O, R(2, npx - 1)] = es * q1[..., :-1] + (1. - es) * q1[..., 1:]
+    q1 = row(npy); qout[..., npy + O, R(2, npx - 1)] = en * q1[..., :-1] + (1. - en) * q1[..., 1:]
+    return qout

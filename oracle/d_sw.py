@@ -424,6 +424,7 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm, pp=None):
         da_min_c = g.da_min_c
         C = (is_, ie + 1, js, je + 1)
         ke_damp = {}
+        divg = {}          # what d_sw leaves in delpc (the caller's vt, dyn_core_nlm.F90:656): its own divergence (:1340) or divg_d (:1353)
         if any(n == 0 for n in nord_l):
             # nord == 0 :  del-2 on the divergence computed from the D-grid winds
             ptc = Z(u)
@@ -451,6 +452,7 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm, pp=None):
             dpcv = S(g.rarea_c, *C) * S(dpc, *C)
             damp = da_min_c * torch.maximum(d2bg, torch.clamp(dddmp * torch.abs(dpcv * dt), max=0.20))
             ke_damp["0"] = put(Z(u), *C, damp * dpcv)
+            divg["0"] = put(Z(u), *C, dpcv)
         if any(n > 0 for n in nord_l):
             nmax = max(nord_l)
             variants = {}
@@ -487,10 +489,15 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm, pp=None):
                 dd8 = (da_min_c * d4_bg) ** (nord + 1)
                 damp2 = da_min_c * torch.maximum(d2bg, torch.clamp(dddmp * S(vort, *C), max=0.20))
                 variants[str(nord)] = put(Z(u), *C, damp2 * S(delpc, *C) + dd8 * S(dd, *C))
+                divg[str(nord)] = delpc
             ke_damp.update(variants)
         vort_d = tp.lev_select([str(n) for n in nord_l], ke_damp)
-        return vort_d
-    vort_d = div_damp(prm) if not split_damp else splice(div_damp(pp), div_damp(prm))
+        return vort_d, tp.lev_select([str(n) for n in nord_l], divg)
+    if not split_damp:
+        vort_d, divg_out = div_damp(prm)
+    else:
+        (va_, ga_), (vb_, gb_) = div_damp(pp), div_damp(prm)
+        vort_d, divg_out = splice(va_, vb_), splice(ga_, gb_)
     ke = put(ke, *C, S(ke, *C) + S(vort_d, *C))
 
     # ---- vorticity transport and wind update (:1449-1483)
@@ -516,7 +523,7 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm, pp=None):
         vn = vn - S(ut3, is_, ie + 1, js, je)
     u_new = put(u, is_, ie, js, je + 1, un)
     v_new = put(v, is_, ie + 1, js, je, vn)
-    out = dict(delp=delp_new, pt=pt_new, u=u_new, v=v_new, w=w_new, fx=fx, fy=fy, crx=crx, cry=cry, xfx=xfx, yfx=yfx)
+    out = dict(delp=delp_new, pt=pt_new, u=u_new, v=v_new, w=w_new, fx=fx, fy=fy, crx=crx, cry=cry, xfx=xfx, yfx=yfx, divg=divg_out)
     # ---- dissipative heating (:938-951 the w part with ke_bg = 0, :1436-1446, :1494-1525).  prm["d_con"]: d_con_k per level
     dcon = prm.get("d_con")
     if dcon is not None and any(d > 1.e-5 for d in dcon):

@@ -15,7 +15,7 @@ from .cubed_sphere import R, NG, Halo, neighbour, to_neighbour, STAG, copy_corne
 from .sw_core import c_sw, S, put, Z, O
 from .sw_core import P as Pt
 from .d_sw import d_sw
-from .a2b_edge import a2b_ord4
+from .a2b_edge import a2b_ord4, a2b_ord2
 
 
 class GetBoundary:
@@ -103,11 +103,13 @@ def p_grad_c(dt2, delpc, pkc, gz, uc, vc, g, hydrostatic):
     return put(uc, is_, ie + 1, js, je, ucn), put(vc, is_, ie, js, je + 1, vcn)
 
 
-def grad_p(u, v, pk, gz, g, dt, top_value, pp=None, delp=None, beta=None, du_dv=None):
+def grad_p(u, v, pk, gz, g, dt, top_value, pp=None, delp=None, beta=None, du_dv=None, divg2=None):
     """one_grad_p (:1645, hydrostatic, d_ext = 0) when pp is None, nh_p_grad (:1431) otherwise.
     beta is not None (the caller's beta_d, 0 on the first acoustic sub-step, dyn_core :373-375): grad1_p_update (:1781-1872, d_ext = 0 so
     divg2 = 0 :726) / split_p_grad (:1531-1643): u += beta * du_prev, then the hydrostatic part enters with alpha = 1 - beta and is
-    handed to the next sub-step; du_dv = (du_prev, dv_prev) on the output rectangles or None; returns (u, v, (du, dv))."""
+    handed to the next sub-step; du_dv = (du_prev, dv_prev) on the output rectangles or None; returns (u, v, (du, dv)).
+    divg2 (hydrostatic, d_ext > 0; [6, 1, NY, NX] at the corners): the external-mode damping term of one_grad_p (:1713-1727, :1758-1771)
+    and grad1_p_update (:1858, :1867)."""
     N = g.N
     is_, ie, js, je = 1, N, 1, N
     pkb = a2b_ord4(pk, g)
@@ -126,10 +128,13 @@ def grad_p(u, v, pk, gz, g, dt, top_value, pp=None, delp=None, beta=None, du_dv=
     if beta is not None:
         alpha = 1.0 - beta
         ub = S(u, i0, i1, j0, j1) + (beta * du_dv[0] if du_dv is not None else 0.0)
+        if divg2 is not None:
+            ub = (ub + S(divg2, i0, i1, j0, j1)) - S(divg2, i0 + 1, i1 + 1, j0, j1)
     if beta is not None and pp is None:
         un = (ub + alpha * du) * S(g.rdx, i0, i1, j0, j1)
     elif pp is None:
-        un = S(g.rdx, i0, i1, j0, j1) * (0.0 + S(u, i0, i1, j0, j1) + du)
+        wk2 = 0.0 if divg2 is None else S(divg2, i0, i1, j0, j1) - S(divg2, i0 + 1, i1 + 1, j0, j1)
+        un = S(g.rdx, i0, i1, j0, j1) * (wk2 + S(u, i0, i1, j0, j1) + du)
     else:
         ppb = a2b_ord4(pp, g)
         ppb = torch.cat([torch.zeros_like(ppb[:, :1]), ppb[:, 1:]], dim=1)
@@ -140,10 +145,13 @@ def grad_p(u, v, pk, gz, g, dt, top_value, pp=None, delp=None, beta=None, du_dv=
     dv = dt / (S(wk, i0, i1, j0, j1) + S(wk, i0, i1, j0 + 1, j1 + 1)) * lin(pkb, i0, i1, j0, j1, 0, 1)
     if beta is not None:
         vb = S(v, i0, i1, j0, j1) + (beta * du_dv[1] if du_dv is not None else 0.0)
+        if divg2 is not None:
+            vb = (vb + S(divg2, i0, i1, j0, j1)) - S(divg2, i0, i1, j0 + 1, j1 + 1)
     if beta is not None and pp is None:
         vn = (vb + alpha * dv) * S(g.rdy, i0, i1, j0, j1)
     elif pp is None:
-        vn = S(g.rdy, i0, i1, j0, j1) * (0.0 + S(v, i0, i1, j0, j1) + dv)
+        wk1 = 0.0 if divg2 is None else S(divg2, i0, i1, j0, j1) - S(divg2, i0, i1, j0 + 1, j1 + 1)
+        vn = S(g.rdy, i0, i1, j0, j1) * (wk1 + S(v, i0, i1, j0, j1) + dv)
     else:
         dn = dt / (S(wk1, i0, i1, j0, j1) + S(wk1, i0, i1, j0 + 1, j1 + 1)) * lin(ppb, i0, i1, j0, j1, 0, 1)
         vn = ((S(v, i0, i1, j0, j1) + dv + dn) if beta is None else (vb + alpha * dv + dn)) * S(g.rdy, i0, i1, j0, j1)
@@ -327,7 +335,17 @@ def dyn_core_hydro(st, g, cfg):
         pkc, gz, _, _, _ = geopk(c["delpc"], c["ptc"], hs, g, ptop, akap, cp_air, 1, True)
         uc, vc = p_grad_c(dt2, c["delpc"], pkc, gz, c["uc"], c["vc"], g, True)
         uc, vc = halo.cgrid(uc, vc)
+        d_ext = cfg.get("d_ext", 0.0)
+        dpc = a2b_ord2(delp, g) if d_ext > 0.0 else None          # delp at the corners, before d_sw (:642-644)
         d = d_sw(delp, pt, u, v, w, uc, vc, c["ua"], c["va"], divgd, g, dt, prm, pp)
+        divg2 = None
+        if d_ext > 0.0:           # external-mode divergence damping (:707-724): delp-weighted column mean of the corner divergence
+            CC = (is_, ie + 1, js, je + 1)
+            wkc = S(dpc, *CC); vtc = S(d["divg"], *CC)
+            s0 = wkc[:, 0]; s1 = wkc[:, 0] * vtc[:, 0]
+            for k in range(1, K):
+                s0 = s0 + wkc[:, k]; s1 = s1 + wkc[:, k] * vtc[:, k]
+            divg2 = put(torch.zeros_like(delp[:, :1]), *CC, ((d_ext * g.da_min_c) * s1 / s0)[:, None])
         mfx = put(mfx, is_, ie + 1, js, je, S(mfx, is_, ie + 1, js, je) + S(d["fx"], is_, ie + 1, js, je))
         mfy = put(mfy, is_, ie, js, je + 1, S(mfy, is_, ie, js, je + 1) + S(d["fy"], is_, ie, js, je + 1))
         cx = put(cx, is_, ie + 1, jsd, jed, S(cx, is_, ie + 1, jsd, jed) + S(d["crx"], is_, ie + 1, jsd, jed))
@@ -337,9 +355,10 @@ def dyn_core_hydro(st, g, cfg):
         delp = halo.scalar(d["delp"]); pt = halo.scalar(d["pt"])
         pkc, gz, pe, peln, pkz = geopk(delp, pt, hs, g, ptop, akap, cp_air, 2, False)
         if cfg.get("beta", 0.0) > 0.0:      # grad1_p_update (:865-866), beta_d = 0 on the first sub-step (:373-375)
-            u, v, du_dv = grad_p(d["u"], d["v"], pkc, gz, g, dt, ptop ** akap, beta=0.0 if it == 1 else cfg["beta"], du_dv=None if it == 1 else du_dv)
+            u, v, du_dv = grad_p(d["u"], d["v"], pkc, gz, g, dt, ptop ** akap, beta=0.0 if it == 1 else cfg["beta"], du_dv=None if it == 1 else du_dv,
+                                 divg2=divg2)
         else:
-            u, v = grad_p(d["u"], d["v"], pkc, gz, g, dt, ptop ** akap)
+            u, v = grad_p(d["u"], d["v"], pkc, gz, g, dt, ptop ** akap, divg2=divg2)
         if it == n_split:
             u, v = getb(u, v)
         else:

@@ -241,7 +241,7 @@ def main_dyn_core(beta=0.0):
     print("dyn_core_tlm done, beta =", beta)
 
 
-def dyn_core_hydro_inputs(beta=0.0):
+def dyn_core_hydro_inputs(beta=0.0, d_ext=0.0):
     """the state of tests/test_dyn_core.py (K = 5) with the two-sided configuration, three sub-steps, and a seeded perturbation"""
     from common import rnd
     from test_dyn_core import CFG, TWO_SIDED, hydro_state
@@ -250,25 +250,30 @@ def dyn_core_hydro_inputs(beta=0.0):
     cfg = dict(CFG); cfg.update(n_split=3, bdt=900.0, hydrostatic=True, rdgas=8314.47 / 28.965, grav=9.80665, p_fac=0.05); cfg.update(TWO_SIDED)
     if beta > 0.0:
         cfg["beta"] = beta
+    if d_ext > 0.0:
+        cfg["d_ext"] = d_ext
     act = ["u", "v", "pt", "delp"]
     d = {n: (1e-3 * np.abs(f[n]).mean() * rnd(rng, N, f[n].shape[1]) if n in act else 0 * f[n]) for n in f}
     bk = np.linspace(0.0, 1.0, K + 1); ak = CFG["ptop"] * (1.0 - bk)
     return N, K, ak, bk, f, d, cfg, act
 
 
-def main_dyn_core_hydro(beta=0.0):
+def hydro_file(beta, d_ext):
+    return "ref_dyn_core_hydro%s%s_tlm.npz" % ("_beta" if beta > 0.0 else "", "_dext" if d_ext > 0.0 else "")
+
+
+def main_dyn_core_hydro(beta=0.0, d_ext=0.0):
     """DYN_CORE_TLM, hydrostatic (GEOPK_TLM, ONE_GRAD_P_TLM; beta = 0.4: GRAD1_P_UPDATE_TLM), three sub-steps, six tiles:
     tests/golden/ref_dyn_core_hydro[_beta]_tlm.npz"""
     import ref_dyn_core as rd
     from common import metrics
-    N, K, ak, bk, f, d, cfg, act = dyn_core_hydro_inputs(beta)
+    N, K, ak, bk, f, d, cfg, act = dyn_core_hydro_inputs(beta, d_ext)
     ex = rd.Exchanger(N)
     consts = dict(rdgas=cfg["rdgas"], cp_air=cfg["cp_air"], grav=cfg["grav"])
     sp, fns, src = rd.load_reference(ex, consts, great_circle_dist, N)
     out = rd.run(fns, ex, grid_structs, metrics(N), N, K, f, d, cfg, ak, bk)
-    np.savez_compressed(os.path.join(HERE, "ref_dyn_core_hydro_beta_tlm.npz" if beta > 0.0 else "ref_dyn_core_hydro_tlm.npz"),
-                        **{k: v.astype(np.float64) for k, v in out.items()})
-    print("dyn_core_tlm (hydrostatic) done, beta =", beta)
+    np.savez_compressed(os.path.join(HERE, hydro_file(beta, d_ext)), **{k: v.astype(np.float64) for k, v in out.items()})
+    print("dyn_core_tlm (hydrostatic) done, beta =", beta, "d_ext =", d_ext)
 
 
 FV_ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz"]
@@ -332,5 +337,9 @@ if __name__ == "__main__":
         main_dyn_core_hydro()
     if len(sys.argv) < 2 or sys.argv[1] == "dyn_core_hydro_beta":
         main_dyn_core_hydro(0.4)
+    if len(sys.argv) < 2 or sys.argv[1] == "dyn_core_hydro_dext":          # external-mode damping (A2B_ORD2_TLM, the wk1 / wk2 terms of ONE_GRAD_P_TLM)
+        main_dyn_core_hydro(0.0, 0.02)
+    if len(sys.argv) < 2 or sys.argv[1] == "dyn_core_hydro_beta_dext":     # ... and of GRAD1_P_UPDATE_TLM
+        main_dyn_core_hydro(0.4, 0.02)
     if len(sys.argv) < 2 or sys.argv[1] == "fv_dynamics":
         main_fv_dynamics()

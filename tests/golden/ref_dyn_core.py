@@ -206,7 +206,7 @@ def load_reference(ex, consts, great_circle_dist, N=12):
 
 def flags_from_cfg(cfg, N):
     """fv_flags_type fields DYN_CORE_TLM reads, from the oracle's configuration dictionary (same names as the reference's namelist)"""
-    d = dict(npx=N + 1, npy=N + 1, grid_type=0, k_split=1, m_split=0, d_ext=0.0, inline_q=False, fv_debug=False, a2b_ord=4, use_old_omega=False,
+    d = dict(npx=N + 1, npy=N + 1, grid_type=0, k_split=1, m_split=0, d_ext=cfg.get("d_ext", 0.0), inline_q=False, fv_debug=False, a2b_ord=4, use_old_omega=False,
              use_logp=False, delt_max=1.0, d_con=cfg.get("d_con", 0.0), hydrostatic=bool(cfg.get("hydrostatic", False)), scale_z=0.0, p_fac=cfg["p_fac"],
              breed_vortex_inline=False, a_imp=cfg.get("a_imp", 1.0), nwat=0, ke_bg=0.0, fill_dp=False, do_f3d=False, convert_ke=False, beta=cfg.get("beta", 0.0),
              n_sponge=cfg.get("n_sponge", 0))

@@ -55,8 +55,11 @@ def test_bad_decomposition_is_an_error():
 def test_unsupported_flags_are_errors():
     """the reference aborts on inconsistent set-ups (src/fv3jedi_lm_mod.F90:91-94); here create returns an error status"""
     for kw in (dict(hord_mt=9), dict(hord_tr=12), dict(nq=5), dict(n_split=0), dict(nord=4), dict(dt=0.0), dict(q_split_max=9),
-               dict(q_split_dynamic=2), dict(beta=0.4), dict(d_ext=0.02)):
+               dict(q_split_dynamic=2), dict(beta=-0.2), dict(beta=1.0), dict(d_ext=-0.02)):
         with pytest.raises(RuntimeError):
             fv3lm.FV3LM(fv3lm.default_config(12, 4, **kw), emu=True)
+    # beta > 0 (grad1_p_update / split_p_grad) and the reference's default d_ext = 0.02 are built
+    for kw in (dict(beta=0.4), dict(d_ext=0.02), dict(d_ext=0.02, hydrostatic=0)):
+        fv3lm.FV3LM(fv3lm.default_config(12, 4, **kw), emu=True)
     with pytest.raises(RuntimeError):
         fv3lm.FV3LM(fv3lm.default_config(12, 120), emu=True)

@@ -173,6 +173,24 @@ def test_dyn_core_hydro_beta_gpu():
     _run(False, 3, extra=dict(beta=0.4))
 
 
+@pytest.mark.parametrize("beta", [0.0, 0.4])
+def test_dyn_core_hydro_d_ext_emu(beta):
+    """d_ext = 0.02 (the reference's default, model/fv_arrays_nlm.F90:328): external-mode divergence damping of the hydrostatic core
+    (a2b_ord2 of delp, the delp-weighted column mean of d_sw's corner divergence, dyn_core_nlm.F90:642-726; the wk1 / wk2 terms of
+    one_grad_p :1713-1771 and, with beta > 0, of grad1_p_update :1858-1867); the sponge layer runs nord = 0 (d_sw's own divergence)"""
+    print(_run(True, 2, K=4, extra=dict(d_ext=0.02, beta=beta, n_sponge=2)))
+
+
+@pytest.mark.gpu
+def test_dyn_core_hydro_d_ext_gpu():
+    _run(False, 2, K=4, extra=dict(d_ext=0.02, beta=0.4, n_sponge=2))
+
+
+def test_dyn_core_hydro_d_ext_two_sided_emu():
+    ts = dict(TWO_SIDED); ts["d_ext"] = 0.02
+    print(_run(True, 2, K=5, extra=ts))
+
+
 def test_dyn_core_hydro_heat_emu():
     """d_con = 1: heat source accumulated over the acoustic steps, filtered by del2_cubed, added to pt (dyn_core_nlm.F90:1052-1075)"""
     print(_run(True, 2, K=5, extra=dict(d_con=1.0)))     # layers 1-3 are sponge layers (d_con_k = 0): K = 5 leaves two heated ones

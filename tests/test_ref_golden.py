@@ -257,20 +257,24 @@ def test_library_reproduces_reference_dyn_core_tlm_gpu(beta):
 HYD_OUT = ["u", "v", "pt", "delp", "mfx", "mfy", "cx", "cy", "pkz"]
 
 
-def _hyd_gold(beta):
+def _hyd_gold(beta, d_ext=0.0):
     import sys
     sys.path.insert(0, GOLD)
-    from make_ref_golden import dyn_core_hydro_inputs
-    gold = np.load(os.path.join(GOLD, "ref_dyn_core_hydro_beta_tlm.npz" if beta > 0.0 else "ref_dyn_core_hydro_tlm.npz"))
-    return gold, dyn_core_hydro_inputs(beta)
+    from make_ref_golden import dyn_core_hydro_inputs, hydro_file
+    gold = np.load(os.path.join(GOLD, hydro_file(beta, d_ext)))
+    return gold, dyn_core_hydro_inputs(beta, d_ext)
 
 
-@pytest.mark.parametrize("beta", [0.0, 0.4])
-def test_oracle_reproduces_reference_dyn_core_hydro_tlm(beta):
+HYD_CASES = [(0.0, 0.0), (0.4, 0.0), (0.0, 0.02), (0.4, 0.02)]
+
+
+@pytest.mark.parametrize("beta,d_ext", HYD_CASES)
+def test_oracle_reproduces_reference_dyn_core_hydro_tlm(beta, d_ext):
     """DYN_CORE_TLM with hydrostatic = T (model_tlmadm/dyn_core_tlm.F90:93-2600: GEOPK_TLM on both grids, P_GRAD_C_TLM, ONE_GRAD_P_TLM :3761;
-    beta = 0.4: GRAD1_P_UPDATE_TLM :4163-4293), three acoustic sub-steps on all six tiles, two-sided switches."""
+    beta = 0.4: GRAD1_P_UPDATE_TLM :4163-4293; d_ext = 0.02: A2B_ORD2_TLM, the external-mode divergence and the wk1 / wk2 terms of the
+    two gradient routines), three acoustic sub-steps on all six tiles, two-sided switches."""
     from oracle import dyn_core as odyn
-    gold, (N, K, ak, bk, f, d, cfg, act) = _hyd_gold(beta)
+    gold, (N, K, ak, bk, f, d, cfg, act) = _hyd_gold(beta, d_ext)
     g = ograd(N)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
 
@@ -289,9 +293,9 @@ def test_oracle_reproduces_reference_dyn_core_hydro_tlm(beta):
     assert max(errs.values()) <= 1e-12, errs
 
 
-def _lib_vs_reference_dyn_core_hydro(emu, beta):
+def _lib_vs_reference_dyn_core_hydro(emu, beta, d_ext=0.0):
     from test_dyn_core import two_sided_params
-    gold, (N, K, ak, bk, f, d, cfg, act) = _hyd_gold(beta)
+    gold, (N, K, ak, bk, f, d, cfg, act) = _hyd_gold(beta, d_ext)
     h = handle(N, K, emu)
     p = two_sided_params(cfg); p.update(do_vort_damp=int(cfg["do_vort_damp"]), hydrostatic=1)
     key = dict(u="u_n", v="v_n", pt="pt_n", delp="delp_n")
@@ -315,15 +319,15 @@ def _lib_vs_reference_dyn_core_hydro(emu, beta):
     assert max(errs.values()) <= 5e-11, errs          # the module's tolerance against the oracle (tests/test_dyn_core.py); achieved: see the print
 
 
-@pytest.mark.parametrize("beta", [0.0, 0.4])
-def test_library_reproduces_reference_dyn_core_hydro_tlm_emu(beta):
-    _lib_vs_reference_dyn_core_hydro(True, beta)
+@pytest.mark.parametrize("beta,d_ext", HYD_CASES)
+def test_library_reproduces_reference_dyn_core_hydro_tlm_emu(beta, d_ext):
+    _lib_vs_reference_dyn_core_hydro(True, beta, d_ext)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("beta", [0.0, 0.4])
-def test_library_reproduces_reference_dyn_core_hydro_tlm_gpu(beta):
-    _lib_vs_reference_dyn_core_hydro(False, beta)
+@pytest.mark.parametrize("beta,d_ext", HYD_CASES)
+def test_library_reproduces_reference_dyn_core_hydro_tlm_gpu(beta, d_ext):
+    _lib_vs_reference_dyn_core_hydro(False, beta, d_ext)
 
 
 # ---------------------------------------------------------------------------------------------------------------- FV_DYNAMICS_TLM (whole step)

@@ -119,6 +119,16 @@ def test_step_api_beta_gpu():
     _run(False, nonhydro=True, extra=dict(beta=0.4))
 
 
+def test_step_api_d_ext_emu():
+    """d_ext = 0.02 (the reference's default) through fv3lm_config: external-mode divergence damping in a whole hydrostatic step"""
+    print(_run(True, extra=dict(d_ext=0.02)))
+
+
+@pytest.mark.gpu
+def test_step_api_d_ext_gpu():
+    _run(False, extra=dict(d_ext=0.02))
+
+
 def test_step_api_hord333_emu():
     """hord_* = 333 (third-order linear scheme of the TL/AD, tp_core_tlm.F90:2467) for every transport of a hydrostatic step"""
     print(_run(True, extra=dict(hord_mt=333, hord_vt=333, hord_tm=333, hord_dp=333, hord_tr=333)))
