@@ -132,7 +132,7 @@ subroutine create(self,conf)
  ! one GPU per MPI rank: rank modulo the devices visible on the node (fv3lm_create calls cudaSetDevice before any allocation)
  cfg%device = -1
  ! switches the reference hands to fv_dynamics (src/dynamics/fv3jedi_lm_dynamics_mod.F90:299) whose paths are not built: refuse
- ! them here instead of computing something else silently (beta / d_ext / a_imp are checked by fv3lm_create itself)
+ ! them here instead of computing something else silently (the ranges of beta / d_ext / a_imp are checked by fv3lm_create itself)
  if (A%flagstruct%consv_te > 0.0_kind_real) call mpp_error(FATAL, 'fv3lm_b200: consv_te > 0 (energy fixer) is not supported')
  if (A%flagstruct%consv_am) call mpp_error(FATAL, 'fv3lm_b200: consv_am (angular-momentum fixer) is not supported')
  if (A%flagstruct%fill) call mpp_error(FATAL, 'fv3lm_b200: fill (tracer filling in the remap) is not supported')
