@@ -279,26 +279,32 @@ def main_dyn_core_hydro(beta=0.0, d_ext=0.0):
 FV_ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz"]
 
 
-def fv_dynamics_inputs(K=5):
+def fv_act(hydro):
+    return FV_ACT[:8] if hydro else FV_ACT
+
+
+def fv_dynamics_inputs(K=5, hydro=False):
     """state and two-sided configuration of tests/test_step_api.py::test_step_api_two_sided_emu at npz = 5 (the reference skips the vertical
     remap for npz <= 4, fv_dynamics_tlm.F90: `IF (npz .GT. 4)`), and a seeded perturbation of the compute-domain prognostics"""
     from test_fv_dynamics import api_state, eta, ZVIR, RD
     from test_dyn_core import CFG, TWO_SIDED
     N = 12
     ak, bk = eta(K, CFG["ptop"])
-    f, _ = api_state(N, K, 41, ak, bk, True)
-    cfg = dict(CFG); cfg.update(zvir=ZVIR, hydrostatic=False, k_split=1, n_split=2, dt=900.0, hord_tr=2, rdgas=RD, grav=9.80665, p_fac=0.05)
+    f, _ = api_state(N, K, 41, ak, bk, not hydro)
+    cfg = dict(CFG); cfg.update(zvir=ZVIR, hydrostatic=hydro, k_split=1, n_split=2, dt=900.0, hord_tr=2, rdgas=RD, grav=9.80665, p_fac=0.05)
     cfg.update(TWO_SIDED)
+    if hydro:                      # the reference's default external-mode damping (model/fv_arrays_nlm.F90:328), active in hydrostatic mode only
+        cfg["d_ext"] = 0.02
     rng = np.random.default_rng(20261019)
     d = {}
-    for n in FV_ACT:
+    for n in fv_act(hydro):
         x = np.zeros_like(f[n])
         x[..., 3:3 + N, 3:3 + N] = 1e-3 * np.abs(f[n]).mean() * rng.standard_normal((6, K, N, N))
         d[n] = x
     return N, K, ak, bk, f, d, cfg
 
 
-def main_fv_dynamics():
+def main_fv_dynamics(hydro=False):
     """FV_DYNAMICS_TLM: one whole non-hydrostatic dynamics step (acoustic loop, tracer transport, vertical remap) on six tiles:
     tests/golden/ref_fv_dynamics_tlm.npz (compute-domain values and tangents of the ten prognostics)"""
     import torch
@@ -306,10 +312,11 @@ def main_fv_dynamics():
     import ref_fv_dynamics as rf
     from common import metrics, ograd
     from oracle.dyn_core import halo_of
-    N, K, ak, bk, f, d, cfg = fv_dynamics_inputs()
+    N, K, ak, bk, f, d, cfg = fv_dynamics_inputs(hydro=hydro)
+    ACT = fv_act(hydro)
     g = ograd(N)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
-    st, st_tl = torch.func.jvp(lambda *a: rf.pre(dict(zip(FV_ACT, a)), g, cfg, None), tuple(T(f[n]) for n in FV_ACT), tuple(T(d[n]) for n in FV_ACT))
+    st, st_tl = torch.func.jvp(lambda *a: rf.pre(dict(zip(ACT, a)), g, cfg, None), tuple(T(f[n]) for n in ACT), tuple(T(d[n]) for n in ACT))
     st = {k: v.numpy() for k, v in st.items()}; st_tl = {k: v.numpy() for k, v in st_tl.items()}
     phis = halo_of(N)[0].scalar(T(f["phis"])).numpy()
     ex = rd.Exchanger(N)
@@ -319,11 +326,11 @@ def main_fv_dynamics():
     out = rf.run(fns, ex, grid_structs, metrics(N), N, K, st, st_tl, phis, cfg, ak, bk)
     key = dict(t="pt")
     sav = {}
-    for n in FV_ACT:
+    for n in ACT:
         for sfx in ("", "_tl"):
             sav[n + sfx] = np.ascontiguousarray(out[key.get(n, n) + sfx][:, :, 3:3 + N, 3:3 + N])
-    np.savez_compressed(os.path.join(HERE, "ref_fv_dynamics_tlm.npz"), **sav)
-    print("fv_dynamics_tlm done")
+    np.savez_compressed(os.path.join(HERE, "ref_fv_dynamics_hydro_tlm.npz" if hydro else "ref_fv_dynamics_tlm.npz"), **sav)
+    print("fv_dynamics_tlm done, hydrostatic =", hydro)
 
 
 if __name__ == "__main__":
@@ -343,3 +350,5 @@ if __name__ == "__main__":
         main_dyn_core_hydro(0.4, 0.02)
     if len(sys.argv) < 2 or sys.argv[1] == "fv_dynamics":
         main_fv_dynamics()
+    if len(sys.argv) < 2 or sys.argv[1] == "fv_dynamics_hydro":
+        main_fv_dynamics(True)

@@ -27,7 +27,9 @@ def pre(x, g, cfg, phis):
     u, v = getb(dom(x["u"]), dom(x["v"]))
     delp = dom(x["delp"])
     pe, pk, pkz, peln = compute_pressures(delp, cfg["ptop"], cfg["akap"])
-    st = dict(u=u, v=v, pt=dom(x["t"]), delp=delp, pe=dom(pe), pk=dom(pk), pkz=dom(pkz), peln=dom(peln), w=dom(x["w"]), delz=dom(x["delz"]))
+    st = dict(u=u, v=v, pt=dom(x["t"]), delp=delp, pe=dom(pe), pk=dom(pk), pkz=dom(pkz), peln=dom(peln))
+    for n in ("w", "delz"):                  # (absent in hydrostatic mode: the arrays stay zero)
+        st[n] = dom(x[n]) if n in x else torch.zeros_like(delp)
     for n in ("qv", "ql", "qi", "o3"):
         st[n] = dom(x[n])
     return st
@@ -93,6 +95,7 @@ def run(fns, ex, grid_structs, M, N, K, st, st_tl, phis, cfg, ak, bk):
             bd, gs, _ = grid_structs(M, t, N)
             gs.area_64 = gs.area; gs.square_domain = False
             fl = rd.flags_from_cfg(ct, N)
+            hyd = bool(cfg.get("hydrostatic", False))
             for k, v in dict(adiabatic=False, check_negative=False, consv_am=False, dnats=0, do_sat_adj=False, make_nh=False, moist_phys=True,
                              nf_omega=1, no_dycore=False, nord_tr=0, nwat=3, p_ref=1.e5, range_warn=False, remap_option=0, rf_cutoff=0.0, tau=0.0,
                              trdm2=0.0, z_tracer=False, kord_mt=17, kord_wz=17, kord_tm=17, kord_tr=17, k_split=cfg["k_split"],
@@ -120,7 +123,7 @@ def run(fns, ex, grid_structs, M, N, K, st, st_tl, phis, cfg, ak, bk):
             idiag = types.SimpleNamespace(id_ws=0, id_zratio=0, id_aam=0, id_amdt=0, id_divg=0, id_mdt=0, id_te=0, zxg=None)
             P = lambda n: (a[n], a_tl[n])
             fns["fv_dynamics_tlm"](N + 1, N + 1, K, 4, NG, cfg["dt"], 0.0, False, False, cfg["akap"], cfg["cp_air"], cfg["zvir"], cfg["ptop"], 0, 4,
-                                   cfg["n_split"], cfg.get("q_split", 1), *P("u"), *P("v"), *P("w"), *P("delz"), False, *P("pt"), *P("delp"), *P("q"),
+                                   cfg["n_split"], cfg.get("q_split", 1), *P("u"), *P("v"), *P("w"), *P("delz"), hyd, *P("pt"), *P("delp"), *P("q"),
                                    *P("ps"), *P("pe"), *P("pk"), *P("peln"), *P("pkz"), fphis, q_con, *P("omga"), *P("ua"), *P("va"), *P("uc"),
                                    *P("vc"), fak, fbk, *P("mfx"), *P("mfy"), *P("cx"), *P("cy"), ze0, False, gs, fl, flp, nest, idiag, bd, None,
                                    domain)
@@ -138,7 +141,7 @@ def run(fns, ex, grid_structs, M, N, K, st, st_tl, phis, cfg, ak, bk):
         raise RuntimeError("tile %d failed:\n%s" % (errors[0][0], errors[0][1]))
     out = {}
     for sfx, idx in (("", 0), ("_tl", 1)):
-        for n in ("u", "v", "w", "delz", "pt", "delp"):
+        for n in (("u", "v", "pt", "delp") if cfg.get("hydrostatic", False) else ("u", "v", "w", "delz", "pt", "delp")):
             x = np.zeros((6, K, NX, NX))
             for t in range(6):
                 fa = res[t][idx][n]

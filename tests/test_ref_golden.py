@@ -331,16 +331,20 @@ def test_library_reproduces_reference_dyn_core_hydro_tlm_gpu(beta, d_ext):
 
 
 # ---------------------------------------------------------------------------------------------------------------- FV_DYNAMICS_TLM (whole step)
-def test_oracle_reproduces_reference_fv_dynamics_tlm():
-    """FV_DYNAMICS_TLM (model_tlmadm/fv_dynamics_tlm.F90:87-995: DYN_CORE_TLM, TRACER_2D_TLM, LAGRANGIAN_TO_EULERIAN_TLM with its map
+@pytest.mark.parametrize("hydro", [False, True])
+def test_oracle_reproduces_reference_fv_dynamics_tlm(hydro):
+    """hydro = True: the hydrostatic step with the reference's default d_ext = 0.02 (hydrostatic branches of DYN_CORE_TLM and of
+    LAGRANGIAN_TO_EULERIAN_TLM, omega remap and pkz update included).
+    FV_DYNAMICS_TLM (model_tlmadm/fv_dynamics_tlm.F90:87-995: DYN_CORE_TLM, TRACER_2D_TLM, LAGRANGIAN_TO_EULERIAN_TLM with its map
     routines, the pt <-> T conversions; two-sided switches, npz = 5, n_split = 2) on all six tiles: the whole dynamics step of the
     tangent-linear model, i.e. the path the benchmark times, against oracle/fv_dynamics.py::step_nl and its jvp."""
     import sys
     sys.path.insert(0, GOLD)
-    from make_ref_golden import fv_dynamics_inputs, FV_ACT
+    from make_ref_golden import fv_dynamics_inputs, fv_act
     from oracle import fv_dynamics as ofv
-    gold = np.load(os.path.join(GOLD, "ref_fv_dynamics_tlm.npz"))
-    N, K, ak, bk, f, d, cfg = fv_dynamics_inputs()
+    gold = np.load(os.path.join(GOLD, "ref_fv_dynamics_hydro_tlm.npz" if hydro else "ref_fv_dynamics_tlm.npz"))
+    N, K, ak, bk, f, d, cfg = fv_dynamics_inputs(hydro=hydro)
+    FV_ACT = fv_act(hydro)
     g = ograd(N)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
     phis = T(f["phis"])
@@ -358,19 +362,20 @@ def test_oracle_reproduces_reference_fv_dynamics_tlm():
     assert max(errs.values()) <= 1e-11, errs          # achieved 2e-13 (w), others <= 5e-15
 
 
-def _api_vs_reference_fv_dynamics(emu):
+def _api_vs_reference_fv_dynamics(emu, hydro=False):
     """the PUBLIC API (fv3lm_create / traj_set / step_nl / step_tl through the C ABI, what the reference's fv3jedi_lm_dynamics_mod would call)
     against the reference's FV_DYNAMICS / FV_DYNAMICS_TLM outputs"""
     import sys
     sys.path.insert(0, GOLD)
-    from make_ref_golden import fv_dynamics_inputs, FV_ACT
+    from make_ref_golden import fv_dynamics_inputs, fv_act
     from test_dyn_core import CFG, TWO_SIDED
     from test_fv_dynamics import ZVIR
     from oracle.cubed_sphere import R
-    gold = np.load(os.path.join(GOLD, "ref_fv_dynamics_tlm.npz"))
-    N, K, ak, bk, f, d, cfg = fv_dynamics_inputs()
+    gold = np.load(os.path.join(GOLD, "ref_fv_dynamics_hydro_tlm.npz" if hydro else "ref_fv_dynamics_tlm.npz"))
+    N, K, ak, bk, f, d, cfg = fv_dynamics_inputs(hydro=hydro)
+    FV_ACT = fv_act(hydro)
     kw = dict(n_split=2, k_split=1, dt=900.0, ptop=CFG["ptop"], d2_bg_k1=CFG["d2_bg_k1"], d2_bg_k2=CFG["d2_bg_k2"], kappa=CFG["akap"],
-              cp=CFG["cp_air"], zvir=ZVIR, hydrostatic=0)
+              cp=CFG["cp_air"], zvir=ZVIR, hydrostatic=1 if hydro else 0, d_ext=cfg.get("d_ext", 0.0))
     for k_, v_ in TWO_SIDED.items():
         kw[k_] = (tuple(sorted(v_.items())) if k_ == "traj" else int(v_) if isinstance(v_, bool) else v_)
     h = handle(N, K, emu, ak, bk, **kw)
@@ -390,10 +395,12 @@ def _api_vs_reference_fv_dynamics(emu):
     assert max(errs.values()) <= 3e-11, errs          # the step's tolerance against the oracle (tests/test_step_api.py)
 
 
-def test_api_reproduces_reference_fv_dynamics_tlm_emu():
-    _api_vs_reference_fv_dynamics(True)
+@pytest.mark.parametrize("hydro", [False, True])
+def test_api_reproduces_reference_fv_dynamics_tlm_emu(hydro):
+    _api_vs_reference_fv_dynamics(True, hydro)
 
 
 @pytest.mark.gpu
-def test_api_reproduces_reference_fv_dynamics_tlm_gpu():
-    _api_vs_reference_fv_dynamics(False)
+@pytest.mark.parametrize("hydro", [False, True])
+def test_api_reproduces_reference_fv_dynamics_tlm_gpu(hydro):
+    _api_vs_reference_fv_dynamics(False, hydro)
