@@ -276,6 +276,47 @@ def main_dyn_core_hydro(beta=0.0, d_ext=0.0):
     print("dyn_core_tlm (hydrostatic) done, beta =", beta, "d_ext =", d_ext)
 
 
+ADJ_OUT = ["u", "v", "pt", "delp", "w", "delz", "mfx", "cx"]          # the outputs of the library's dyn_core_nh module (tests/test_nh.py)
+# outputs that carry a seed.  With seeds on u / w / delz (the outputs behind the LAST Riem_Solver3 of the loop) the reference's reverse sweep
+# is not the transpose of its own tangent-linear code, see tests/test_ref_golden.py::test_oracle_reproduces_reference_dyn_core_adjoint
+ADJ_SEEDED = ["pt", "delp", "mfx", "cx"]
+
+
+def dyn_core_adjoint_inputs():
+    """one-sided variant of dyn_core_inputs() (both sides run the trajectory's switches) and seeded output adjoints, scaled by the size of
+    each output so that every path contributes to the input adjoints"""
+    N, K, ak, bk, f, d, cfg, act = dyn_core_inputs()
+    one = dict(cfg["traj"])
+    cfg.update(one); cfg["traj"] = dict(one); cfg["split_damp"] = False; cfg["d2_bg_ks"] = cfg["d2_bg_k2"]
+    npx = N + 1; C = (1, N, 1, N)
+    regions = dict(u=(1, N, 1, npx), v=(1, npx, 1, N), pt=C, delp=C, w=C, delz=C, mfx=(1, npx, 1, N), cx=(1, npx, -2, N + 3))
+    scale = np.load(os.path.join(HERE, "ref_dyn_core_nh_tlm.npz"))
+    rng = np.random.default_rng(777)
+    seed = {}
+    for n in ADJ_OUT:
+        i0, i1, j0, j1 = regions[n]
+        s = np.zeros((6, K, N + 7, N + 7))
+        if n in ADJ_SEEDED:
+            s[:, :, j0 + 2: j1 + 3, i0 + 2: i1 + 3] = rng.standard_normal((6, K, j1 - j0 + 1, i1 - i0 + 1)) / np.abs(scale[n]).max()
+        seed[n] = s
+    return N, K, ak, bk, f, cfg, act, seed, regions
+
+
+def main_dyn_core_adjoint():
+    """DYN_CORE_FWD + DYN_CORE_BWD: the reference's reverse sweep of the non-hydrostatic acoustic loop (two sub-steps, six tiles, the adjoint
+    halo exchanges served by the transposes of the cubed-sphere index maps): tests/golden/ref_dyn_core_nh_adm.npz"""
+    import ref_dyn_core as rd
+    from common import metrics
+    N, K, ak, bk, f, cfg, act, seed, regions = dyn_core_adjoint_inputs()
+    ex = rd.Exchanger(N)
+    consts = dict(rdgas=cfg["rdgas"], cp_air=cfg["cp_air"], grav=cfg["grav"])
+    sp, fns, src = rd.load_reference_adjoint(ex, consts, great_circle_dist, N)
+    sd = dict(seed); sd["regions"] = regions
+    out = rd.run_adjoint(fns, ex, grid_structs, metrics(N), N, K, f, sd, cfg, ak, bk)
+    np.savez_compressed(os.path.join(HERE, "ref_dyn_core_nh_adm.npz"), **out)
+    print("dyn_core_fwd / dyn_core_bwd done", {k: float(np.abs(v).max()) for k, v in out.items()})
+
+
 FV_ACT = ["u", "v", "t", "delp", "qv", "ql", "qi", "o3", "w", "delz"]
 
 
@@ -348,6 +389,8 @@ if __name__ == "__main__":
         main_dyn_core_hydro(0.0, 0.02)
     if len(sys.argv) < 2 or sys.argv[1] == "dyn_core_hydro_beta_dext":     # ... and of GRAD1_P_UPDATE_TLM
         main_dyn_core_hydro(0.4, 0.02)
+    if len(sys.argv) < 2 or sys.argv[1] == "dyn_core_adjoint":
+        main_dyn_core_adjoint()
     if len(sys.argv) < 2 or sys.argv[1] == "fv_dynamics":
         main_fv_dynamics()
     if len(sys.argv) < 2 or sys.argv[1] == "fv_dynamics_hydro":

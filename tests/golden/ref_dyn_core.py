@@ -298,3 +298,91 @@ def run(fns, ex, grid_structs, M, N, K, f, d, cfg, ak, bk):
                 x[t, :, j0 + 2: j0 + 2 + nj, i0 + 2: i0 + 2 + ni] = fa.a.transpose(2, 1, 0)
             out[n + sfx] = x
     return out
+
+
+def load_reference_adjoint(ex, consts, great_circle_dist, N=12):
+    files = [REF + x for x in ("tp_core_adm.F90", "sw_core_adm.F90", "a2b_edge_adm.F90", "dyn_core_adm.F90", "nh_core_adm.F90", "nh_utils_adm.F90")]
+    extra = dict(ng=NG, great_circle_dist=great_circle_dist, fpp=types.SimpleNamespace(fpp_overload_r4=False))
+    extra.update(make_stubs(ex)); extra.update(consts); extra.update(load_fill_corners(N))
+    return f90py.load(files, extra=extra, strict=False)
+
+
+def run_adjoint(fns, ex, grid_structs, M, N, K, f, seed, cfg, ak, bk):
+    """DYN_CORE_FWD then DYN_CORE_BWD (model_tlmadm/dyn_core_adm.F90:115, :1686) on six tiles in lock step.  seed: dict output name ->
+    [6, K, NY, NX] adjoint seeds and seed["regions"]: name -> (i0, i1, j0, j1).  Returns the adjoints of the prognostic inputs."""
+    NX = N + 7
+    isd, ied, jsd, jed = 1 - NG, N + NG, 1 - NG, N + NG
+    A3 = lambda nk: ((isd, ied), (jsd, jed), (1, nk))
+    bnd = dict(u=((isd, ied), (jsd, jed + 1), (1, K)), v=((isd, ied + 1), (jsd, jed), (1, K)), w=A3(K), delz=A3(K), pt=A3(K), delp=A3(K),
+               pe=((0, N + 1), (1, K + 1), (0, N + 1)), pk=((1, N), (1, N), (1, K + 1)), omga=A3(K), ua=A3(K), va=A3(K),
+               uc=((isd, ied + 1), (jsd, jed), (1, K)), vc=((isd, ied), (jsd, jed + 1), (1, K)), mfx=((1, N + 1), (1, N), (1, K)),
+               mfy=((1, N), (1, N + 1), (1, K)), cx=((1, N + 1), (jsd, jed), (1, K)), cy=((isd, ied), (1, N + 1), (1, K)),
+               pkz=((1, N), (1, N), (1, K)), peln=((1, N), (1, K + 1), (1, N)), dpx=((1, N), (1, N)), ws=((1, N), (1, N)),
+               gz=A3(K + 1), pkc=A3(K + 1), ptc=A3(K), crx=((1, N + 1), (jsd, jed), (1, K)), xfx=((1, N + 1), (jsd, jed), (1, K)),
+               cry=((isd, ied), (1, N + 1), (1, K)), yfx=((isd, ied), (1, N + 1), (1, K)), divgd=((isd, ied + 1), (jsd, jed + 1), (1, K)),
+               delpc=A3(K), ut=A3(K), vt=A3(K), zh=A3(K + 1), pk3=A3(K + 1), du=((isd, ied), (jsd, jed + 1), (1, K)),
+               dv=((isd, ied + 1), (jsd, jed), (1, K)))
+    res = [None] * 6
+    errors = []
+    hyd = bool(cfg.get("hydrostatic", False))
+    def tile_main(t):
+        try:
+            bd, gs, fl0 = grid_structs(M, t, N)
+            gs.area_64 = gs.area; gs.square_domain = False
+            ct = dict(cfg); ct.update(cfg["traj"])
+            fl = flags_from_cfg(ct, N); flp = pert_flags_from_cfg(cfg)
+            a = {n: FA.alloc(b) for n, b in bnd.items()}; a_ad = {n: FA.alloc(b) for n, b in bnd.items()}
+            for n in (("u", "v", "pt", "delp") if hyd else ("u", "v", "w", "delz", "pt", "delp")):
+                ni, nj = a[n].a.shape[0], a[n].a.shape[1]
+                a[n].a[...] = f[n][t][:, :nj, :ni].transpose(2, 1, 0)
+            phis = FA(np.ascontiguousarray(f["phis"][t, 0][:N + 6, :N + 6].T), (isd, jsd))
+            q = FA.alloc(((isd, ied), (jsd, jed), (1, K), (1, 0))); q_ad = FA.alloc(((isd, ied), (jsd, jed), (1, K), (1, 0)))
+            cappa = FA.alloc(A3(K)); q_con = FA.alloc(A3(K))
+            pfull = FA(np.array([0.5 * (ak[k] + ak[k + 1]) + 0.5 * (bk[k] + bk[k + 1]) * 1.e5 for k in range(K)]), (1,))
+            fak = FA(np.array(ak, dtype=float), (1,)); fbk = FA(np.array(bk, dtype=float), (1,))
+            i_pack = FA(np.arange(1, 13), (1,))
+            domain = types.SimpleNamespace(tile=t)
+            nest = types.SimpleNamespace(nest_timestep=0)
+            idiag = types.SimpleNamespace(id_ws=0, id_zratio=0)
+            V = lambda n: a[n]
+            P = lambda n: (a[n], a_ad[n])
+            assert not f90py.stack()
+            fns["dyn_core_fwd"](N + 1, N + 1, K, NG, 1, 0, cfg["bdt"], cfg["n_split"], 0.0, cfg["cp_air"], cfg["akap"], cappa, cfg["grav"], hyd,
+                                V("u"), V("v"), V("w"), V("delz"), V("pt"), q, V("delp"), V("pe"), V("pk"), phis, V("ws"), V("omga"),
+                                cfg["ptop"], pfull, V("ua"), V("va"), V("uc"), V("vc"), V("mfx"), V("mfy"), V("cx"), V("cy"), V("pkz"),
+                                V("peln"), q_con, fak, fbk, V("dpx"), 0, gs, fl, flp, nest, idiag, bd, domain, True, i_pack, True,
+                                V("gz"), V("pkc"), V("ptc"), V("crx"), V("xfx"), V("cry"), V("yfx"), V("divgd"), V("delpc"), V("ut"), V("vt"),
+                                V("zh"), V("pk3"), V("du"), V("dv"))
+            for n, rg in seed["regions"].items():
+                i0, i1, j0, j1 = rg
+                fa_ = a_ad[n]
+                li, lj = fa_.lo[0], fa_.lo[1]
+                # seed[n][t]: [K, NY, NX] oracle layout (index = coordinate + 2)
+                fa_.a[i0 - li: i1 - li + 1, j0 - lj: j1 - lj + 1, :] = seed[n][t][:, j0 + 2: j1 + 3, i0 + 2: i1 + 3].transpose(2, 1, 0)
+            fns["dyn_core_bwd"](N + 1, N + 1, K, NG, 1, 0, cfg["bdt"], cfg["n_split"], 0.0, cfg["cp_air"], cfg["akap"], cappa, cfg["grav"], hyd,
+                                *P("u"), *P("v"), *P("w"), *P("delz"), *P("pt"), q, q_ad, *P("delp"), *P("pe"), *P("pk"), phis, *P("ws"), *P("omga"),
+                                cfg["ptop"], pfull, *P("ua"), *P("va"), *P("uc"), *P("vc"), *P("mfx"), *P("mfy"), *P("cx"), *P("cy"), *P("pkz"),
+                                *P("peln"), q_con, fak, fbk, *P("dpx"), 0, gs, fl, flp, nest, idiag, bd, domain, True, i_pack, True,
+                                *P("gz"), *P("pkc"), *P("ptc"), *P("crx"), *P("xfx"), *P("cry"), *P("yfx"), *P("divgd"), *P("delpc"), *P("ut"), *P("vt"),
+                                *P("zh"), *P("pk3"), *P("du"), *P("dv"))
+            assert not f90py.stack(), "checkpoint stack not empty after the backward sweep"
+            res[t] = (a, a_ad)
+        except BaseException as e:
+            import traceback
+            errors.append((t, traceback.format_exc()))
+            ex.ls.barrier.abort()
+    th = [threading.Thread(target=tile_main, args=(t,)) for t in range(6)]
+    for x in th: x.start()
+    for x in th: x.join()
+    if errors:
+        raise RuntimeError("tile %d failed:\n%s" % (errors[0][0], errors[0][1]))
+    out = {}
+    for n in (("u", "v", "pt", "delp") if hyd else ("u", "v", "w", "delz", "pt", "delp")):
+        x = np.zeros((6, K, NX, NX))
+        for t in range(6):
+            fa_ = res[t][1][n]
+            i0, j0 = fa_.lo[0], fa_.lo[1]
+            ni, nj = fa_.a.shape[0], fa_.a.shape[1]
+            x[t, :, j0 + 2: j0 + 2 + nj, i0 + 2: i0 + 2 + ni] = fa_.a.transpose(2, 1, 0)
+        out[n + "_ad"] = x
+    return out
