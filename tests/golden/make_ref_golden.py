@@ -374,6 +374,47 @@ def main_fv_dynamics(hydro=False):
     print("fv_dynamics_tlm done, hydrostatic =", hydro)
 
 
+def fv_dynamics_adjoint_inputs():
+    """the hydrostatic whole-step case of fv_dynamics_inputs() with one-sided switches (both sides run the trajectory's; d_ext = 0.02) and
+    seeded compute-domain output adjoints scaled by the size of each output"""
+    N, K, ak, bk, f, d, cfg = fv_dynamics_inputs(hydro=True)
+    one = dict(cfg["traj"])
+    cfg.update(one); cfg["traj"] = dict(one); cfg["split_damp"] = False; cfg["d2_bg_ks"] = cfg["d2_bg_k2"]
+    act = fv_act(True)
+    scale = np.load(os.path.join(HERE, "ref_fv_dynamics_hydro_tlm.npz"))
+    rng = np.random.default_rng(99)
+    seed = {n: rng.standard_normal((6, K, N, N)) / np.abs(scale[n]).max() for n in act}
+    return N, K, ak, bk, f, cfg, act, seed
+
+
+def main_fv_dynamics_adjoint():
+    """FV_DYNAMICS_FWD + FV_DYNAMICS_BWD: the reference's reverse sweep of one whole hydrostatic dynamics step (acoustic loop with the
+    external-mode damping, tracer transport, vertical remap) on six tiles: tests/golden/ref_fv_dynamics_hydro_adm.npz (adjoints of the
+    eight API prognostics on the compute domain, pulled back through the state conversion in front of fv_dynamics)"""
+    import torch
+    import ref_dyn_core as rd
+    import ref_fv_dynamics as rf
+    from common import metrics, ograd
+    from oracle.dyn_core import halo_of
+    N, K, ak, bk, f, cfg, act, seed = fv_dynamics_adjoint_inputs()
+    g = ograd(N)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    x0 = tuple(T(f[n]) for n in act)
+    st = rf.pre(dict(zip(act, x0)), g, cfg, None)
+    keys = list(st)
+    phis = halo_of(N)[0].scalar(T(f["phis"])).numpy()
+    ex = rd.Exchanger(N)
+    consts = dict(rdgas=cfg["rdgas"], cp_air=cfg["cp_air"], grav=cfg["grav"], rvgas=461.5, pi=np.pi, radius=6371.0e3, kappa=cfg["akap"],
+                  cp_vapor=4 * 461.5, hlv=2.5e6)
+    sp, fns, src = rf.load_reference_adjoint(ex, consts, great_circle_dist, N)
+    st_ad = rf.run_adjoint(fns, ex, grid_structs, metrics(N), N, K, {k: v.numpy() for k, v in st.items()}, seed, act, phis, cfg, ak, bk)
+    _, vjp_pre = torch.func.vjp(lambda *a: tuple(rf.pre(dict(zip(act, a)), g, cfg, None)[k] for k in keys), *x0)
+    ad = vjp_pre(tuple(T(st_ad[k]) for k in keys))
+    sav = {n + "_ad": np.ascontiguousarray(a.numpy()[:, :, 3:3 + N, 3:3 + N]) for n, a in zip(act, ad)}
+    np.savez_compressed(os.path.join(HERE, "ref_fv_dynamics_hydro_adm.npz"), **sav)
+    print("fv_dynamics_fwd / fv_dynamics_bwd done", {k: float(np.abs(v).max()) for k, v in sav.items()})
+
+
 if __name__ == "__main__":
     if len(sys.argv) < 2 or sys.argv[1] == "d_sw":
         main()
@@ -395,3 +436,5 @@ if __name__ == "__main__":
         main_fv_dynamics()
     if len(sys.argv) < 2 or sys.argv[1] == "fv_dynamics_hydro":
         main_fv_dynamics(True)
+    if len(sys.argv) < 2 or sys.argv[1] == "fv_dynamics_adjoint":
+        main_fv_dynamics_adjoint()

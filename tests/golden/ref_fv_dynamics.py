@@ -154,3 +154,150 @@ def run(fns, ex, grid_structs, M, N, K, st, st_tl, phis, cfg, ak, bk):
                 x[t, :, :N + 6, :N + 6] = res[t][idx]["q"].a[:, :, :, iq].transpose(2, 1, 0)
             out[n + sfx] = x
     return out
+
+
+def load_reference_adjoint(ex, consts, great_circle_dist, N):
+    """the reverse-mode sources (model_tlmadm/*_adm.F90) of the whole dynamics step, with the adjoint halo exchanges of ref_dyn_core.py"""
+    files = [REF + x for x in ("tp_core_adm.F90", "sw_core_adm.F90", "a2b_edge_adm.F90", "dyn_core_adm.F90", "nh_core_adm.F90", "nh_utils_adm.F90",
+                               "fv_dynamics_adm.F90", "fv_mapz_adm.F90", "fv_tracer2d_adm.F90", "fv_grid_utils_adm.F90")]
+    extra = dict(ng=NG, great_circle_dist=great_circle_dist, fpp=types.SimpleNamespace(fpp_overload_r4=False, fpp_mapl_mode=True),
+                 do_adiabatic_init=False, model_atmos=0, fv_time=0)
+    base = rd.make_stubs(ex)
+    extra.update(base); extra.update(more_stubs(ex)); extra.update(consts); extra.update(rd.load_fill_corners(N))
+    extra["start_group_halo_update"] = base["start_group_halo_update"]      # (more_stubs turns the plain one into a no-op: the TLM run never calls it)
+
+    def fields_of(args):
+        return [a for a in args if isinstance(a, types.SimpleNamespace)][0], [a for a in args if isinstance(a, FA)]
+
+    def mpp_update_domains(*args, **kw):
+        domain, fl = fields_of(args)
+        if len(fl) == 2 and kw.get("gridtype") is not None:
+            ex.update(domain.tile, fl, "dgrid")
+        else:
+            for f_ in fl:
+                ex.update(domain.tile, [f_], "scalar")
+
+    def mpp_update_domains_adm(*args, **kw):
+        domain, fl = fields_of(args)
+        if len(fl) == 4:
+            ex.update_adj(domain.tile, [fl[1], fl[3]], "dgrid")
+        else:
+            ex.update_adj(domain.tile, [fl[1]], "scalar")
+    extra["mpp_update_domains"] = mpp_update_domains; extra["mpp_update_domains_adm"] = mpp_update_domains_adm
+    return f90py.load(files, extra=extra, strict=False, skip=("great_circle_dist",))
+
+
+def run_adjoint(fns, ex, grid_structs, M, N, K, st, seed, act, phis, cfg, ak, bk):
+    """FV_DYNAMICS_FWD then FV_DYNAMICS_BWD (model_tlmadm/fv_dynamics_adm.F90) on six tiles in lock step.  st: dict from pre(); seed: dict
+    API field -> [6, K, N, N] compute-domain output adjoints.  Returns the adjoints of the FV_Atm-level inputs (the keys of st),
+    [6, K(+1), NY, NX]; pull them back through pre() to get the adjoints of the API fields."""
+    NX = N + 7
+    hyd = bool(cfg.get("hydrostatic", False))
+    isd, ied, jsd, jed = 1 - NG, N + NG, 1 - NG, N + NG
+    A3 = lambda nk: ((isd, ied), (jsd, jed), (1, nk))
+    bnd = dict(u=((isd, ied), (jsd, jed + 1), (1, K)), v=((isd, ied + 1), (jsd, jed), (1, K)), w=A3(K), delz=A3(K), pt=A3(K), delp=A3(K),
+               q=((isd, ied), (jsd, jed), (1, K), (1, 4)), ps=((isd, ied), (jsd, jed)), pe=((0, N + 1), (1, K + 1), (0, N + 1)),
+               pk=((1, N), (1, N), (1, K + 1)), peln=((1, N), (1, K + 1), (1, N)), pkz=((1, N), (1, N), (1, K)), omga=A3(K), ua=A3(K), va=A3(K),
+               uc=((isd, ied + 1), (jsd, jed), (1, K)), vc=((isd, ied), (jsd, jed + 1), (1, K)), mfx=((1, N + 1), (1, N), (1, K)),
+               mfy=((1, N), (1, N + 1), (1, K)), cx=((1, N + 1), (jsd, jed), (1, K)), cy=((isd, ied), (1, N + 1), (1, K)))
+    res = [None] * 6
+    errors = []
+    ct = dict(cfg); ct.update(cfg.get("traj") or {})
+    TR = ("qv", "ql", "qi", "o3")
+
+    def put3(fa, x):
+        i0, j0 = fa.lo[0], fa.lo[1]
+        ni, nj = fa.a.shape[0], fa.a.shape[1]
+        fa.a[...] = x[:, j0 + 2: j0 + 2 + nj, i0 + 2: i0 + 2 + ni].transpose(2, 1, 0)
+
+    def tile_main(t):
+        try:
+            threading.current_thread().tile = t
+            bd, gs, _ = grid_structs(M, t, N)
+            gs.area_64 = gs.area; gs.square_domain = False
+            fl = rd.flags_from_cfg(ct, N)
+            for k, v in dict(adiabatic=False, check_negative=False, consv_am=False, dnats=0, do_sat_adj=False, make_nh=False, moist_phys=True,
+                             nf_omega=1, no_dycore=False, nord_tr=0, nwat=3, p_ref=1.e5, range_warn=False, remap_option=0, rf_cutoff=0.0, tau=0.0,
+                             trdm2=0.0, z_tracer=False, kord_mt=17, kord_wz=17, kord_tm=17, kord_tr=17, k_split=cfg["k_split"],
+                             hord_tr=ct["hord_tr"]).items():
+                setattr(fl, k, v)
+            flp = rd.pert_flags_from_cfg(cfg)
+            for k, v in dict(kord_mt_pert=17, kord_wz_pert=17, kord_tm_pert=17, kord_tr_pert=17, nord_tr_pert=0, trdm2_pert=0.0,
+                             split_damp_tr=False).items():
+                setattr(flp, k, v)
+            a = {n: FA.alloc(b) for n, b in bnd.items()}; a_ad = {n: FA.alloc(b) for n, b in bnd.items()}
+            for n in ("u", "v", "w", "delz", "pt", "delp"):
+                put3(a[n], st[n][t])
+            for iq, n in enumerate(TR):
+                a["q"].a[:, :, :, iq] = st[n][t][:, :N + 6, :N + 6].transpose(2, 1, 0)
+            # corner ghost cells have no neighbour on the cubed sphere: FMS leaves some finite value there; zero would give 0 / 0 in c_sw's
+            # ptc = ... / delpc (never used by a valid output, but the reverse sweep would spread the NaN)
+            for n in ("pt", "delp", "q"):
+                x = a[n].a
+                for (ci, si) in ((slice(0, NG), NG), (slice(NG + N, None), NG + N - 1)):
+                    for (cj, sj) in ((slice(0, NG), NG), (slice(NG + N, None), NG + N - 1)):
+                        x[ci, cj] = x[si, sj][None, None]
+            a["pe"].a[...] = st["pe"][t][:, 2: N + 4, 2: N + 4].transpose(2, 0, 1)
+            a["peln"].a[...] = st["peln"][t][:, 3: N + 3, 3: N + 3].transpose(2, 0, 1)
+            a["pk"].a[...] = st["pk"][t][:, 3: N + 3, 3: N + 3].transpose(2, 1, 0)
+            a["pkz"].a[...] = st["pkz"][t][:, 3: N + 3, 3: N + 3].transpose(2, 1, 0)
+            fphis = FA(np.ascontiguousarray(phis[t, 0][:N + 6, :N + 6].T), (isd, jsd))
+            q_con = FA.alloc(A3(K)); ze0 = FA.alloc(((1, 1), (1, 1), (1, 1)))
+            fak = FA(np.array(ak, dtype=float), (1,)); fbk = FA(np.array(bk, dtype=float), (1,))
+            domain = types.SimpleNamespace(tile=t)
+            nest = types.SimpleNamespace(nest_timestep=0, tracer_nest_timestep=0, child_grids=[False], nested=False, nestbctype=0, pt_bc=None)
+            idiag = types.SimpleNamespace(id_ws=0, id_zratio=0, id_aam=0, id_amdt=0, id_divg=0, id_mdt=0, id_te=0, zxg=None)
+            V = lambda n: (a[n],)
+            P = lambda n: (a[n], a_ad[n])
+            head = (N + 1, N + 1, K, 4, NG, cfg["dt"], 0.0, False, False, cfg["akap"], cfg["cp_air"], cfg["zvir"], cfg["ptop"], 0, 4, cfg["n_split"],
+                    cfg.get("q_split", 1))
+
+            def call(fn, W):
+                fn(*head, *W("u"), *W("v"), *W("w"), *W("delz"), hyd, *W("pt"), *W("delp"), *W("q"), *W("ps"), *W("pe"), *W("pk"), *W("peln"),
+                   *W("pkz"), fphis, q_con, *W("omga"), *W("ua"), *W("va"), *W("uc"), *W("vc"), fak, fbk, *W("mfx"), *W("mfy"), *W("cx"), *W("cy"),
+                   ze0, False, gs, fl, flp, nest, idiag, bd, None, domain)
+            assert not f90py.stack()
+            call(fns["fv_dynamics_fwd"], V)
+            key = dict(t="pt")
+            for n in act:
+                if n in TR:
+                    a_ad["q"].a[NG:NG + N, NG:NG + N, :, TR.index(n)] = seed[n][t].transpose(2, 1, 0)
+                else:
+                    a_ad[key.get(n, n)].a[NG:NG + N, NG:NG + N, :] = seed[n][t].transpose(2, 1, 0)
+            call(fns["fv_dynamics_bwd"], P)
+            assert not f90py.stack(), "checkpoint stack not empty after the backward sweep"
+            res[t] = a_ad
+        except BaseException:
+            import traceback
+            errors.append((t, traceback.format_exc()))
+            ex.ls.barrier.abort()
+    th = [threading.Thread(target=tile_main, args=(t,)) for t in range(6)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    if errors:
+        raise RuntimeError("tile %d failed:\n%s" % (errors[0][0], errors[0][1]))
+
+    def get3(fa):
+        x = np.zeros((fa.a.shape[2], NX, NX)); i0, j0 = fa.lo[0], fa.lo[1]
+        ni, nj = fa.a.shape[0], fa.a.shape[1]
+        x[:, j0 + 2: j0 + 2 + nj, i0 + 2: i0 + 2 + ni] = fa.a.transpose(2, 1, 0)
+        return x
+    st_ad = {}
+    for k in st:
+        x = np.zeros(st[k].shape)
+        for t in range(6):
+            aa = res[t]
+            if k in ("u", "v", "w", "delz", "pt", "delp"):
+                x[t] = get3(aa[k])
+            elif k in TR:
+                x[t][:, :N + 6, :N + 6] = aa["q"].a[:, :, :, TR.index(k)].transpose(2, 1, 0)
+            elif k == "pe":
+                x[t][:, 2:N + 4, 2:N + 4] = aa["pe"].a.transpose(1, 2, 0)
+            elif k == "peln":
+                x[t][:, 3:N + 3, 3:N + 3] = aa["peln"].a.transpose(1, 2, 0)
+            elif k in ("pk", "pkz"):
+                x[t][:, 3:N + 3, 3:N + 3] = aa[k].a.transpose(2, 1, 0)
+        st_ad[k] = x
+    return st_ad

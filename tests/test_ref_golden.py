@@ -476,3 +476,69 @@ def test_api_reproduces_reference_fv_dynamics_tlm_emu(hydro):
 @pytest.mark.parametrize("hydro", [False, True])
 def test_api_reproduces_reference_fv_dynamics_tlm_gpu(hydro):
     _api_vs_reference_fv_dynamics(False, hydro)
+
+
+# ---------------------------------------------------------------------------------------------------------------- FV_DYNAMICS_FWD / _BWD (whole step, adjoint)
+def _fv_adjoint_gold():
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_ref_golden import fv_dynamics_adjoint_inputs
+    return np.load(os.path.join(GOLD, "ref_fv_dynamics_hydro_adm.npz")), fv_dynamics_adjoint_inputs()
+
+
+def test_oracle_reproduces_reference_fv_dynamics_adjoint():
+    """FV_DYNAMICS_FWD + FV_DYNAMICS_BWD (model_tlmadm/fv_dynamics_adm.F90 with DYN_CORE_FWD/BWD, TRACER_2D_FWD/BWD, LAGRANGIAN_TO_EULERIAN_FWD/BWD
+    and its map routines, the pt <-> T conversions, Tapenade's checkpoint stack): the reference's own REVERSE-MODE code for one whole
+    hydrostatic dynamics step (two acoustic sub-steps with the external-mode damping d_ext = 0.02, tracer transport, vertical remap) on six
+    tiles, against torch.func.vjp of oracle/fv_dynamics.py::step_nl with the same seeded output adjoints of the eight prognostics."""
+    from oracle import fv_dynamics as ofv
+    gold, (N, K, ak, bk, f, cfg, act, seed) = _fv_adjoint_gold()
+    g = ograd(N)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    phis = T(f["phis"])
+
+    def fn(*a):
+        o = ofv.step_nl(dict(zip(act, a)), g, ak, bk, cfg, phis)
+        return tuple(o[k] for k in act)
+    _, vjp = torch.func.vjp(fn, *[T(f[n]) for n in act])
+    sd = []
+    for n in act:
+        s_ = np.zeros((6, K, N + 7, N + 7)); s_[:, :, 3:3 + N, 3:3 + N] = seed[n]; sd.append(T(s_))
+    ad = vjp(tuple(sd))
+    errs = {n + "_ad": relerr(region(a.numpy(), 1, N, 1, N), gold[n + "_ad"]) for n, a in zip(act, ad)}
+    print("fv_dynamics adjoint vs reference", {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 1e-12, errs          # achieved 3e-15
+
+
+def _api_vs_reference_fv_dynamics_adjoint(emu):
+    """the PUBLIC API's fv3lm_step_ad (what fv3jedi_lm_dynamics_mod::step_ad would call) against the reference's FV_DYNAMICS_BWD"""
+    from test_dyn_core import CFG
+    from test_fv_dynamics import ZVIR
+    from oracle.cubed_sphere import R
+    gold, (N, K, ak, bk, f, cfg, act, seed) = _fv_adjoint_gold()
+    from test_dyn_core import TWO_SIDED
+    kw = dict(n_split=cfg["n_split"], k_split=1, dt=cfg["dt"], ptop=CFG["ptop"], kappa=CFG["akap"], cp=CFG["cp_air"], zvir=ZVIR, hydrostatic=1,
+              d_ext=cfg["d_ext"])
+    # the reference always carries both flag sets: equal switches on both sides still run the perturbation side's sponge logic
+    # (hord_ks_pert, dyn_core_tlm.F90:835-921), so the handle is created in two-sided mode like the generator's configuration
+    for k_ in TWO_SIDED:
+        v_ = cfg[k_]
+        kw[k_] = (tuple(sorted(v_.items())) if k_ == "traj" else int(v_) if isinstance(v_, bool) else v_)
+    h = handle(N, K, emu, ak, bk, **kw)
+    C = (slice(None), slice(None), R(1, N), R(1, N))
+    h.set_phis(np.ascontiguousarray(f["phis"][:, 0][:, R(1, N), R(1, N)]))
+    h.traj_set(0, {k: np.ascontiguousarray(f[k][C]) for k in act})
+    mty = {k: np.ascontiguousarray(seed[k]) for k in act}
+    h.step_ad(0, mty)
+    errs = {n + "_ad": relerr(mty[n], gold[n + "_ad"]) for n in act}
+    print("public API step_ad vs reference", {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 2e-12, errs          # the hydrostatic step's tolerance against the oracle (tests/test_step_api.py)
+
+
+def test_api_reproduces_reference_fv_dynamics_adjoint_emu():
+    _api_vs_reference_fv_dynamics_adjoint(True)
+
+
+@pytest.mark.gpu
+def test_api_reproduces_reference_fv_dynamics_adjoint_gpu():
+    _api_vs_reference_fv_dynamics_adjoint(False)
