@@ -9,7 +9,8 @@ explicit overlap masks between target layer k and source layer m; every per-piec
 is the reference's.  Summation over the source layers uses torch.sum (pairwise) instead of
 the sequential loop: differences are O(1e-16) relative.
 
-parity unpinned (no reference vectors).  Arrays [6, K, NY, NX] / [6, K+1, NY, NX].
+parity: pinned through the reference's own LAGRANGIAN_TO_EULERIAN_TLM / _FWD / _BWD executed inside FV_DYNAMICS_TLM (non-hydrostatic and
+hydrostatic) and FV_DYNAMICS_FWD/BWD (hydrostatic): tests/test_ref_golden.py, fixtures tests/golden/ref_fv_dynamics_*.npz.  Arrays [6, K, NY, NX] / [6, K+1, NY, NX].
 """
 import numpy as np
 import torch

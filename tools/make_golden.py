@@ -2,7 +2,7 @@
 """Regenerates tests/golden/*.npz: outputs of the ORACLE (torch fp64 restatement) for one C12 fv3jedi_lm dynamics
 step, hydrostatic, non-hydrostatic and non-hydrostatic in two-sided mode (both flag structures at the reference's defaults): NL result, TL result (jvp) for a seeded increment and AD result (vjp) for a
 seeded adjoint vector; physics_c12.npz: turbulence TL / AD, cubed_to_latlon, tracer_2d with q_split = 0.  The reference itself cannot be run here (no Fortran/FMS/MPI), so these fixtures pin the
-oracle against silent regressions between rounds -- they are NOT reference outputs (parity unpinned).
+oracle against silent regressions between rounds -- they are NOT reference outputs (the reference-executed fixtures are tests/golden/ref_*.npz, written by tests/golden/make_ref_golden.py).
   python tools/make_golden.py
 """
 import os
