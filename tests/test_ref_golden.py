@@ -276,7 +276,7 @@ def test_oracle_reproduces_reference_dyn_core_adjoint():
     delz) carries a seed.  In both cases the reference's reverse sweep is not the transpose of the reference's own tangent-linear code --
     which the oracle's jvp reproduces to 5e-15 (test_oracle_reproduces_reference_dyn_core_tlm) and whose exact transpose the oracle's vjp
     is (dot-product identity to 1e-16 against the reference's DYN_CORE_TLM output).  Localised so far: with ONE sub-step the same seeds
-    give all six adjoints to 1e-15; SIM1_SOLVER_FWD/BWD and RIEM_SOLVER3_FWD/BWD executed on their own satisfy the dot-product identity
+    give all six adjoints to 1e-15 (and a seed on the w output all but w_ad); SIM1_SOLVER_FWD/BWD and RIEM_SOLVER3_FWD/BWD executed on their own satisfy the dot-product identity
     with their TLM to 1e-15, and so does C_SW_FWD/BWD against the oracle's vjp for an incoming w_ad on the compute domain (the reference's
     c_sw fills the corner ghosts of w IN PLACE, fill_4corners, so its adjoint moves corner-ghost adjoints of w; the oracle's c_sw leaves
     the caller's w alone); the deviation appears when the C-grid half of a sub-step receives a NON-ZERO incoming w_ad from the D-grid
