@@ -18,6 +18,12 @@ from .a2b_edge import a2b_ord4
 from .sw_core import S, P, put, Z, sg, O, C1, C2, C3, P1, P2
 
 
+# Test hook.  True: the damping of w carries its derivative, as in the reference's tangent-linear model (dyn_core_tlm.F90:856-858, 915-916 set
+# nord_w_pert / damp_w_pert per level).  False reproduces the reference's REVERSE sweep, where dyn_core_adm.F90 only ever initialises those two
+# switches to 0 (:338, :378, :1954, :1994), so D_SW_BWD runs without the adjoint of the w damping (tests/test_ref_golden.py).
+W_DAMP_DERIVATIVE = True
+
+
 class _Splice(torch.autograd.Function):
     """value of b (trajectory-scheme chain), derivative of a (perturbation-scheme chain): the split_hord / split_damp
     semantics of the TL/AD model (model_tlmadm/sw_core_tlm.F90:1664-1682, 2341-2366, 2436-2451)"""
@@ -366,6 +372,8 @@ def d_sw(delp, pt, u, v, w, uc, vc, ua, va, divg_d, g, dt, prm, pp=None):
         dmpw = prm["damp_w"]; nordw = prm["nord_w"]
         damp4 = [(dmpw[k] * g.da_min_c) ** (nordw[k] + 1) if dmpw[k] > 1.e-5 else 0.0 for k in range(K)]
         fx2, fy2 = del6_by_level(nordw, damp4, w, g)
+        if not W_DAMP_DERIVATIVE:
+            fx2, fy2 = fx2.detach(), fy2.detach()
         on = _lv([1.0 if dmpw[k] > 1.e-5 else 0.0 for k in range(K)])
         dw = div(fx2, fy2) * on
         gx, gy, _ = tp_site(prm["hord_vt"] == pp["hord_vt"], lambda p: tp.fv_tp_2d(w, crx, cry, p["hord_vt"], xfx, yfx, g, ra_x, ra_y, mfx=fx, mfy=fy))

@@ -261,7 +261,7 @@ def _dyn_adjoint_gold():
     return np.load(os.path.join(GOLD, "ref_dyn_core_nh_adm.npz")), dyn_core_adjoint_inputs(), ADJ_OUT
 
 
-# the reference's own w adjoint does not transpose its tangent (see the docstring below): compared for information only
+# the reference's reverse sweep leaves out the adjoint of the w damping (see the docstring below): w_ad is compared with that term removed
 ADJ_CHECKED = ["u", "v", "pt", "delp", "delz"]
 
 
@@ -269,19 +269,19 @@ def test_oracle_reproduces_reference_dyn_core_adjoint():
     """DYN_CORE_FWD + DYN_CORE_BWD (model_tlmadm/dyn_core_adm.F90:115-2896 with C_SW / D_SW / UPDATE_DZ_C / UPDATE_DZ_D / RIEM_SOLVER_C /
     RIEM_SOLVER3 / P_GRAD_C / NH_P_GRAD forward-and-backward pairs, Tapenade's checkpoint stack, and the adjoint halo exchanges
     START_GROUP_HALO_UPDATE_ADM / MPP_GET_BOUNDARY_ADM served by the transposes of the cubed-sphere index maps): the reference's
-    reverse sweep of the whole non-hydrostatic acoustic loop on six tiles against torch.func.vjp of the oracle, same seeded output adjoints.
-    One-sided configuration, two sub-steps, output adjoints seeded on pt, delp, mfx and cx: the adjoints of u, v, pt, delp and delz agree
-    to 1e-15.  Two things do NOT agree and are documented instead of asserted: (i) the reference's adjoint of the INPUT w
-    (13 - 22 % off at the top level, decaying downwards) and (ii) everything, once an output behind the loop's last Riem_Solver3 (u, w,
-    delz) carries a seed.  In both cases the reference's reverse sweep is not the transpose of the reference's own tangent-linear code --
-    which the oracle's jvp reproduces to 5e-15 (test_oracle_reproduces_reference_dyn_core_tlm) and whose exact transpose the oracle's vjp
-    is (dot-product identity to 1e-16 against the reference's DYN_CORE_TLM output).  Localised so far: with ONE sub-step the same seeds
-    give all six adjoints to 1e-15 (and a seed on the w output all but w_ad); SIM1_SOLVER_FWD/BWD and RIEM_SOLVER3_FWD/BWD executed on their own satisfy the dot-product identity
-    with their TLM to 1e-15, and so does C_SW_FWD/BWD against the oracle's vjp for an incoming w_ad on the compute domain (the reference's
-    c_sw fills the corner ghosts of w IN PLACE, fill_4corners, so its adjoint moves corner-ghost adjoints of w; the oracle's c_sw leaves
-    the caller's w alone); the deviation appears when the C-grid half of a sub-step receives a NON-ZERO incoming w_ad from the D-grid
-    half.  Whether the rest is the reference or the transpiler's execution of it was not settled, so w_ad is printed, not asserted."""
+    reverse sweep of the whole non-hydrostatic acoustic loop on six tiles against torch.func.vjp of the oracle, same seeded output adjoints
+    (on pt, delp, mfx, cx; two sub-steps).  The adjoints of u, v, pt, delp and delz agree to 3e-16.
+
+    REFERENCE QUIRK, found with these vectors: the reference's adjoint of w is not the transpose of the reference's own tangent-linear
+    code.  dyn_core_tlm.F90 sets the perturbation side's w-damping switches per level (nord_w_pert = nord_v_pert(k), damp_w_pert =
+    damp_vt_pert(k) :856-858; sponge layers nord_w_pert = 0, damp_w_pert = d2_divg_pert :915-916), dyn_core_adm.F90 only ever initialises
+    them to 0 (DYN_CORE_FWD :338, :378; DYN_CORE_BWD :1954, :1994), so D_SW_BWD runs without the adjoint of the w damping.  The oracle's vjp
+    (the exact transpose of the tangent the reference's DYN_CORE_TLM fixtures pin) therefore differs in w_ad by 16 % here, and in every
+    adjoint once an output behind the loop's last Riem_Solver3 (u, w, delz) carries a seed.  With the derivative of that one term removed
+    (oracle.d_sw.W_DAMP_DERIVATIVE = False) the oracle reproduces the reference's w_ad to 1e-15 as well: asserted below.  The library
+    implements the transpose of the tangent (dot-product identity), not this omission."""
     from oracle import nh as onh
+    from oracle import d_sw as odsw
     gold, (N, K, ak, bk, f, cfg, act, seed, regions), OUT = _dyn_adjoint_gold()
     g = ograd(N)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
@@ -290,11 +290,22 @@ def test_oracle_reproduces_reference_dyn_core_adjoint():
         st = {n: T(f[n]) for n in f}; st.update(dict(zip(act, a)))
         o = onh.dyn_core_nh(st, g, cfg, ak, bk)
         return tuple(o[k] for k in OUT)
-    _, vjp = torch.func.vjp(fn, *[T(f[n]) for n in act])
-    ad = vjp(tuple(T(seed[n]) for n in OUT))
-    errs = {n + "_ad": relerr(a.numpy(), gold[n + "_ad"]) for n, a in zip(act, ad)}
+
+    def adjoints():
+        _, vjp = torch.func.vjp(fn, *[T(f[n]) for n in act])
+        ad = vjp(tuple(T(seed[n]) for n in OUT))
+        return {n + "_ad": relerr(a.numpy(), gold[n + "_ad"]) for n, a in zip(act, ad)}
+    errs = adjoints()
     print("dyn_core adjoint vs reference", {k: "%.1e" % v for k, v in errs.items()})
     assert max(errs[n + "_ad"] for n in ADJ_CHECKED) <= 1e-11, errs
+    assert errs["w_ad"] > 1e-2, errs                       # the exact transpose does differ from the reference in w_ad
+    odsw.W_DAMP_DERIVATIVE = False
+    try:
+        errs_q = adjoints()
+    finally:
+        odsw.W_DAMP_DERIVATIVE = True
+    print("dyn_core adjoint vs reference, w-damping adjoint left out like dyn_core_adm.F90 does", {k: "%.1e" % v for k, v in errs_q.items()})
+    assert max(errs_q.values()) <= 1e-11, errs_q           # all six, w_ad included
 
 
 def _lib_vs_reference_dyn_core_adjoint(emu):
@@ -317,7 +328,8 @@ def _lib_vs_reference_dyn_core_adjoint(emu):
 
 def test_library_reproduces_reference_dyn_core_adjoint_emu():
     """the library's AD mode of the dyn_core_nh module (host emulation through the C ABI; hand-written column and gather adjoints, adjoint
-    halo accumulation) against the reference's DYN_CORE_BWD, no oracle in the loop"""
+    halo accumulation) against the reference's DYN_CORE_BWD, no oracle in the loop; w_ad is not compared: the library is the transpose of the
+    tangent, the reference's reverse sweep leaves out the adjoint of the w damping (test_oracle_reproduces_reference_dyn_core_adjoint)"""
     _lib_vs_reference_dyn_core_adjoint(True)
 
 
